@@ -1,0 +1,213 @@
+/* ivlm_b200 -- C ABI of the B200-native (sm_100a) InteractVLM inference hot path.
+ *
+ * The reference (saidwivedi/InteractVLM) has no FFI: its boundary is the Python class
+ * InteractVLMForCausalLM (model/InteractVLM.py:139-638).  interactvlm_b200/model.py mirrors that
+ * class and drives the kernels below through ctypes.  Every entry point names the reference code it
+ * replaces.  Conventions:
+ *   - all pointers are DEVICE pointers unless the name ends in _h (host);
+ *   - bf16 tensors are raw uint16 storage, row-major, innermost dimension contiguous;
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *     there is no hidden cudaDeviceSynchronize and no internal cudaMalloc on the hot path
+ *     (ivlm_lift_build_* is the one-time exception and says so);
+ *   - return 0 on success, negative ivlm_status otherwise; ivlm_last_error() gives the message;
+ *   - a handle is bound to one device, not thread-safe; independent handles may run concurrently.
+ */
+#ifndef IVLM_B200_H
+#define IVLM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVLM_API __attribute__((visibility("default")))
+
+typedef struct ivlm_ctx* ivlm_handle;
+
+enum ivlm_status { IVLM_OK = 0, IVLM_ERR_ARG = -1, IVLM_ERR_CUDA = -2, IVLM_ERR_NOMEM = -3 };
+enum ivlm_dtype { IVLM_BF16 = 0, IVLM_F32 = 1, IVLM_I32 = 2, IVLM_I64 = 3 };
+enum ivlm_act { IVLM_ACT_NONE = 0, IVLM_ACT_GELU = 1, IVLM_ACT_QUICK_GELU = 2, IVLM_ACT_RELU = 3, IVLM_ACT_SILU = 4 };
+enum ivlm_lift_mode {
+    IVLM_LIFT_HUMAN = 0,       /* HumanContact3DPredictor: clamp +-20, sigmoid, final clamp [0,1] */
+    IVLM_LIFT_OBJECT_MESH = 1, /* ObjectMeshContact3DPredictor: sigmoid, only pixels with p > thr vote */
+    IVLM_LIFT_POINTS = 2       /* ObjectPCAfford3DPredictor: raw values, unit weights */
+};
+
+IVLM_API int ivlm_create(ivlm_handle* out, int device);
+IVLM_API int ivlm_destroy(ivlm_handle h);
+IVLM_API const char* ivlm_last_error(void);
+IVLM_API int ivlm_abi_version(void);
+/* kernels launched through this handle so far (bench.py's "gpu_launches") */
+IVLM_API uint64_t ivlm_launch_count(ivlm_handle h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense contraction (tcgen05 / TMEM / TMA).  Replaces every nn.Linear / 1x1-or-patch Conv2d call on
+ * the path: SAM image_encoder.py:235-260 (qkv, proj), common.py:13-26 (MLPBlock), image_encoder.py:
+ * 418-426 (PatchEmbed as im2col GEMM), :92-108 (neck); HF CLIPVisionModel / LlamaModel projections
+ * (clip_encoder.py:46-56, llava_llama.py:93-105); mm_projector (llava_arch.py:93-96);
+ * text_hidden_fcs (InteractVLM.py:100-112); mask-decoder projections (transformer.py:205-242).
+ *   out[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) + residual[M,N]
+ * With out_dtype == IVLM_BF16 the epilogue rounds to bf16 after the bias add, after the activation
+ * and after the residual add, like the eager bf16 reference does at those op boundaries.
+ */
+typedef struct ivlm_gemm_args {
+    const void* a;        /* [M,K] bf16 */
+    int64_t lda;
+    const void* w;        /* [N,K] bf16 (nn.Linear.weight layout) */
+    int64_t ldw;
+    void* out;            /* [M,N] bf16 or fp32 */
+    int64_t ldo;
+    const void* bias;     /* [N] bf16 or NULL */
+    const void* residual; /* [M,N] bf16 or NULL (added after the activation) */
+    int64_t ldr;
+    const int32_t* row_map; /* optional [M]: output (and residual) row for A-row m; -1 drops the row */
+    int32_t M, N, K;
+    int32_t act;          /* ivlm_act */
+    int32_t out_dtype;    /* IVLM_BF16 or IVLM_F32 */
+    int32_t k_splits;     /* >1: split-K, atomically accumulates raw fp32 into a pre-zeroed `out` */
+    int32_t force_swap;   /* 0 auto, 1 weights-as-128-row-operand, -1 never */
+    int32_t no_round;     /* 1: skip the intermediate bf16 roundings */
+    int32_t res_row_mod;  /* >0: residual row = out_row % res_row_mod (broadcast tables, e.g. pos_embed) */
+} ivlm_gemm_args;
+IVLM_API int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise normalisation and elementwise kernels. */
+/* y[m,:] = act(LayerNorm(x[row_map[m],:])) (zeros if row_map[m] < 0).  nn.LayerNorm / LayerNorm2d
+ * (common.py:31-43) on token-major rows; row_map implements window_partition + zero pad
+ * (image_encoder.py:263-288) when given. */
+IVLM_API int ivlm_layernorm_bf16(ivlm_handle h, const void* x, void* y, const void* gamma, const void* beta,
+                        int64_t out_rows, int32_t D, float eps, const int32_t* row_map, int32_t act, void* stream);
+/* HF LlamaRMSNorm: y = gamma * bf16(x * rsqrt(mean(x^2) + eps)), variance in fp32. */
+IVLM_API int ivlm_rmsnorm_bf16(ivlm_handle h, const void* x, void* y, const void* gamma, int64_t rows, int32_t D, float eps,
+                      void* stream);
+/* out[i] = bf16(a[i] + b[i % period]) (period == 0 -> n).  `keys + key_pe`, `x + pos_embed`. */
+IVLM_API int ivlm_add_bcast_bf16(ivlm_handle h, const void* a, const void* b, void* out, int64_t n, int64_t period,
+                        void* stream);
+/* SwiGLU gate: out[r,j] = bf16(bf16(silu(gu[r,j])) * gu[r,F+j]); HF LlamaMLP. */
+IVLM_API int ivlm_silu_mul_bf16(ivlm_handle h, const void* gate_up, void* out, int64_t rows, int32_t F, void* stream);
+/* fp32 split-K accumulator -> bf16 with optional bias / activation / residual. */
+IVLM_API int ivlm_finalize_f32_bf16(ivlm_handle h, const float* acc, void* out, const void* bias, const void* residual,
+                           int64_t rows, int32_t N, int32_t act, void* stream);
+/* x [n] fp32 -> bf16 and back (utility for staging inputs). */
+IVLM_API int ivlm_cast_f32_bf16(ivlm_handle h, const float* x, void* y, int64_t n, void* stream);
+IVLM_API int ivlm_cast_bf16_f32(ivlm_handle h, const void* x, float* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Patch / conv lowering. */
+/* img [N,C,H,W] bf16 -> cols [N*(H/p)*(W/p), ldk] with k = c*p*p + dy*p + dx (Conv2d weight flatten order),
+ * columns [C*p*p, ldk) zero filled.  PatchEmbed (image_encoder.py:395-426), CLIP patch_embedding. */
+IVLM_API int ivlm_im2col_patch_bf16(ivlm_handle h, const void* img, void* cols, int32_t N, int32_t C, int32_t H, int32_t W,
+                           int32_t p, int32_t ldk, void* stream);
+/* x [N,H,W,C] token-major bf16 -> cols [N*H*W, 9*C] with k = (ky*3+kx)*C + c, zero padding 1.
+ * SAM neck 3x3 conv (image_encoder.py:99-106); the weight is repacked to [Cout,3,3,Cin] at bind time. */
+IVLM_API int ivlm_im2col_3x3_bf16(ivlm_handle h, const void* x, void* cols, int32_t N, int32_t H, int32_t W, int32_t C,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention. */
+typedef struct ivlm_attn_args {
+    const void* q; const void* k; const void* v; void* out;  /* bf16 */
+    int64_t q_bs, q_ts, q_hs;   /* element strides: batch, token, head (head_dim contiguous) */
+    int64_t k_bs, k_ts, k_hs;
+    int64_t v_bs, v_ts, v_hs;
+    int64_t o_bs, o_ts, o_hs;
+    int32_t B, H, Sq, Sk, D;    /* D (head_dim) in {64, 80, 128} */
+    float scale;
+    int32_t causal;             /* query i attends keys j <= i + (Sk - Sq) */
+    const float* rel_h;         /* optional decomposed rel-pos bias [B,H,Sq,kh] (fp32) */
+    const float* rel_w;         /* [B,H,Sq,kw]; key j -> (j / kw, j % kw) */
+    int32_t kh, kw;
+} ivlm_attn_args;
+/* Fused softmax(QK^T*scale + bias)V.  SAM Attention.forward (image_encoder.py:235-260), HF CLIPAttention,
+ * HF LlamaAttention prefill (eager path of transformers 4.31). */
+IVLM_API int ivlm_attention_bf16(ivlm_handle h, const ivlm_attn_args* args, void* stream);
+/* SAM decomposed relative position terms (image_encoder.py:354-392): rel_h[b,h,q,kh] = q . Rh[qy-kh+H-1],
+ * rel_w[b,h,q,kw] = q . Rw[qx-kw+W-1]; q read from the packed qkv rows [B*S, 3*heads*hd]. */
+IVLM_API int ivlm_sam_relpos(ivlm_handle h, const void* qkv, const void* rel_pos_h, const void* rel_pos_w, float* rel_h,
+                    float* rel_w, int32_t B, int32_t heads, int32_t Hq, int32_t Wq, int32_t hd, void* stream);
+/* Attention with few queries or few keys and small head_dim (SAM TwoWayTransformer, transformer.py:185-242):
+ * q [B,Nq,heads*hd], k/v [B,Nk,heads*hd], out [B,Nq,heads*hd]; hd in {16,32}. q batch may be 1 (broadcast). */
+IVLM_API int ivlm_attn_small_bf16(ivlm_handle h, const void* q, const void* k, const void* v, void* out, int32_t B,
+                         int32_t q_batch_stride_zero, int32_t Nq, int32_t Nk, int32_t heads, int32_t hd, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LLaVA / LLaMA glue. */
+/* prepare_inputs_labels_for_multimodal (llava_arch.py:98-347, branch :185-208): embed_tokens gather with the
+ * single IMAGE_TOKEN_INDEX (-200) of each row replaced by `n_img` projected CLIP rows.
+ * ids [B,L] int32; out [B, L-1+n_img, D]. */
+IVLM_API int ivlm_embed_splice_bf16(ivlm_handle h, const void* embed, const int32_t* ids, const void* img_feats, void* out,
+                           int32_t B, int32_t L, int32_t n_img, int32_t D, int32_t vocab, void* stream);
+/* embed_tokens gather for decode steps: out[b,:] = embed[ids[b],:] */
+IVLM_API int ivlm_embed_gather_bf16(ivlm_handle h, const void* embed, const int32_t* ids, void* out, int32_t n, int32_t D,
+                           int32_t vocab, void* stream);
+/* HF apply_rotary_pos_emb (rotate_half, bf16 cos/sin tables [max_pos, hd]) on the packed qkv rows
+ * [T, 3*H*hd]; writes rotated q [T,H*hd], and k/v both contiguous [T,H*hd] (may be NULL) and into the paged
+ * KV cache at slot_map[t] (cache layout [slots, H, hd]). */
+IVLM_API int ivlm_rope_kv_store_bf16(ivlm_handle h, const void* qkv, const int32_t* positions, const int32_t* slot_map,
+                            const void* cos_t, const void* sin_t, void* q_out, void* k_out, void* v_out,
+                            void* k_cache, void* v_cache, int32_t T, int32_t H, int32_t hd, void* stream);
+/* One-token attention over the paged KV cache: q [B,H*hd], block_table [B,max_pages], seq_lens [B]
+ * (keys 0..seq_len-1, the current token already stored). */
+IVLM_API int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, const void* k_cache, const void* v_cache,
+                                     const int32_t* block_table, const int32_t* seq_lens, void* out, int32_t B,
+                                     int32_t H, int32_t hd, int32_t page_size, int32_t max_pages, float scale,
+                                     void* stream);
+/* greedy token: argmax over fp32 logits [B, ld] (first `vocab` columns), lowest index wins ties (torch.argmax). */
+IVLM_API int ivlm_argmax_f32(ivlm_handle h, const float* logits, int32_t* out, int32_t B, int32_t vocab, int64_t ld,
+                    void* stream);
+/* rows gather: out[i,:] = x[idx[i],:] (bf16), e.g. the [SEG]-1 hidden rows (InteractVLM.py:545-556). */
+IVLM_API int ivlm_gather_rows_bf16(ivlm_handle h, const void* x, const int32_t* idx, void* out, int32_t n, int32_t D,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Prompt side. */
+/* VIv1CamPoseEncoder (components.py:541-572) + the gate multiply of process_embeddings
+ * (InteractVLM.py:268-282): out[b,v,:] = bf16(emb[b,:] * sigmoid(W_v relu(W2 relu(W1 cam[b,v] + b1) + b2) + b_v)).
+ * cam [B,V,5] bf16, emb [B,256] bf16, w1 [128,5], w2 [128,128], wv [V,256,128]. */
+IVLM_API int ivlm_cam_gate_bf16(ivlm_handle h, const void* cam, const void* emb, const void* w1, const void* b1,
+                       const void* w2, const void* b2, const void* wv, const void* bv, void* out, int32_t B, int32_t V,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mask decoder tail. */
+/* Second ConvTranspose2d(64->32,k2,s2)+GELU of output_upscaling fused with the hypernetwork dot product
+ * (mask_decoder.py:143-157): up1 [Bv,64*64,4,64] bf16 (token, first-stage sub-pixel, channel),
+ * w2 [4,32,64] bf16 (sub-pixel, out-ch, in-ch), b2 [32], hyper [Bv,32] bf16 -> low-res logits [Bv,256,256] fp32
+ * holding bf16-rounded values (the reference emits bf16 masks then .float()s them, sam.py:161). */
+IVLM_API int ivlm_upscale_hyper_dot(ivlm_handle h, const void* up1, const void* w2, const void* b2, const void* hyper,
+                           float* lowres, int32_t Bv, int32_t grid, void* stream);
+/* F.interpolate(mode="bilinear", align_corners=False) used twice by Sam.postprocess_masks (sam.py:137-172):
+ * src [N,sh,sw] fp32, only the top-left (crop_h,crop_w) window is read -> dst [N,dh,dw]. */
+IVLM_API int ivlm_bilinear_f32(ivlm_handle h, const float* src, float* dst, int32_t N, int32_t sh, int32_t sw, int32_t crop_h,
+                      int32_t crop_w, int32_t dh, int32_t dw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Render-Localise-Lift: 2D masks -> per-vertex contact. */
+typedef struct ivlm_lift_map ivlm_lift_map;
+/* One-time build (allocates device memory, synchronises): per-vertex CSR of (pixel, barycentric weight)
+ * from the reference's maps pixel_to_vertex [V,H,W,3] int64 (-1 background) and bary [V,H,W,3] fp32 host
+ * arrays (components.py:203-218; lift2d_dict.pkl, components.py:392-424).  A pixel votes only when all three
+ * vertex ids are in [0, n_verts) (components.py:241-245). */
+IVLM_API int ivlm_lift_build_mesh(ivlm_handle h, const int64_t* p2v_h, const float* bary_h, int32_t V, int32_t H, int32_t W,
+                         int32_t n_verts, ivlm_lift_map** out);
+/* Point-cloud variant: pixel_to_point [V,H,W] int64 (-1 background), unit weights (components.py:319-347). */
+IVLM_API int ivlm_lift_build_points(ivlm_handle h, const int64_t* p2p_h, int32_t V, int32_t H, int32_t W, int32_t n_points,
+                           ivlm_lift_map** out);
+IVLM_API int ivlm_lift_free(ivlm_lift_map* m);
+IVLM_API int64_t ivlm_lift_nnz(const ivlm_lift_map* m);
+/* masks [B,V,H,W] fp32 logits (POINTS mode: values) -> contact [B,n_verts] fp32.
+ * HumanContact3DPredictor.forward (components.py:220-277), ObjectMeshContact3DPredictor (components.py:430-489,
+ * thr = 0.3), ObjectPCAfford3DPredictor (components.py:289-347). Deterministic gather, no atomics. */
+IVLM_API int ivlm_lift(ivlm_handle h, const ivlm_lift_map* m, const float* masks, float* contact, int32_t B, int32_t mode,
+              float thr, void* stream);
+/* convert_contacts (utils/utils.py:428-443): SMPL->SMPL-X dense [R,C] matrix applied as CSR SpMV.
+ * csr built once from the host dense matrix. */
+typedef struct ivlm_csr ivlm_csr;
+IVLM_API int ivlm_csr_build_dense(ivlm_handle h, const float* dense_h, int32_t rows, int32_t cols, ivlm_csr** out);
+IVLM_API int ivlm_csr_free(ivlm_csr* m);
+IVLM_API int ivlm_csr_spmv(ivlm_handle h, const ivlm_csr* m, const float* x, float* y, int32_t B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVLM_B200_H */

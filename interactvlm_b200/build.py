@@ -1,0 +1,85 @@
+"""In-tree build of libivlm_b200.so (sm_100a only) with nvcc.
+
+`python -m interactvlm_b200.build` or `__graft_entry__.build()`.  nvcc cross-compiles without a GPU.
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+BUILD = PKG / "_build"
+LIB = PKG / "libivlm_b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fvisibility=hidden",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def sources() -> list[Path]:
+    return sorted(CSRC.glob("*.cu"))
+
+
+def _deps_mtime() -> float:
+    files = list(CSRC.glob("*")) + [PKG.parent / "include" / "ivlm_b200.h"]
+    return max(f.stat().st_mtime for f in files)
+
+
+def needs_build() -> bool:
+    return not LIB.exists() or LIB.stat().st_mtime < _deps_mtime()
+
+
+def _compile(src: Path, verbose: bool) -> Path:
+    obj = BUILD / (src.stem + ".o")
+    hdr_m = max(f.stat().st_mtime for f in list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) +
+                [PKG.parent / "include" / "ivlm_b200.h"])
+    if obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr_m):
+        return obj
+    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    BUILD.mkdir(exist_ok=True)
+    if force:
+        for o in BUILD.glob("*.o"):
+            o.unlink()
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        objs = list(ex.map(lambda s: _compile(s, verbose), sources()))
+    # the visible symbols are exactly the extern "C" ABI of include/ivlm_b200.h
+    cmd = [_nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

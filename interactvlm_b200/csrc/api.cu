@@ -1,0 +1,41 @@
+// Context management and error reporting for the C ABI (include/ivlm_b200.h).
+#include <stdarg.h>
+
+#include "runtime.h"
+
+namespace ivlm {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace ivlm
+
+extern "C" const char* ivlm_last_error(void) { return ivlm::g_err; }
+extern "C" int ivlm_abi_version(void) { return 1; }
+
+extern "C" int ivlm_create(ivlm_handle* out, int device) {
+    IVLM_REQUIRE(out != nullptr, "ivlm_create: null out");
+    int ndev = 0;
+    IVLM_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+    IVLM_REQUIRE(device >= 0 && device < ndev, "ivlm_create: device %d out of range (%d visible)", device, ndev);
+    IVLM_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    IVLM_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    IVLM_REQUIRE(prop.major == 10, "ivlm_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                 device, prop.major, prop.minor);
+    ivlm_ctx* h = new ivlm_ctx();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    *out = h;
+    return IVLM_OK;
+}
+
+extern "C" int ivlm_destroy(ivlm_handle h) {
+    delete h;
+    return IVLM_OK;
+}
+
+extern "C" uint64_t ivlm_launch_count(ivlm_handle h) { return h ? h->launches : 0; }

@@ -1,0 +1,439 @@
+// out[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual)   -- the nn.Linear contraction on the hot path
+// (SAM ViT-H qkv/proj/MLP, CLIP-L, LLaMA-13B projections, mask-decoder image-side projections).
+//
+// Blackwell-native design (sm_100a):
+//   * persistent CTAs (one per SM), static round-robin tile scheduler, optional split-K work units;
+//   * warp 0 lane 0: TMA producer (cp.async.bulk.tensor, 128B swizzle, multi-stage mbarrier ring);
+//   * warp 1 lane 0: tcgen05.mma issuer (UMMA 128 x BN x 16, bf16 -> fp32 accumulators in TMEM);
+//   * warp 2: TMEM allocator; warps 4-7: epilogue (tcgen05.ld -> bias/act/residual -> global);
+//   * TMEM accumulators are double buffered (2 x BN columns) so the epilogue of tile i overlaps the
+//     MMAs of tile i+1.
+// Small token counts (LLaMA decode, mask-decoder tokens) are run "swapped": the weight matrix is the
+// 128-row UMMA operand, the tokens are the narrow BN operand, and the epilogue writes transposed.
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "runtime.h"
+
+namespace ivlm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+struct GemmParams {
+    int M, N, K;  // kernel view: A-operand rows (128-row tiles), B-operand rows (BN tiles), reduction length
+    int num_m_tiles, num_n_tiles;
+    int k_blocks, k_splits, k_blocks_per_split;
+    void* out;
+    long long out_rs, out_cs;  // element strides of out for (row r of A-operand, row c of B-operand)
+    const bf16* bias;
+    int bias_on_rows;  // bias indexed by r (swapped mode) instead of c
+    const bf16* res;
+    long long res_rs, res_cs;
+    const int* row_map;  // optional remap of r -> output row (normal mode only), -1 drops the row
+    int res_row_mod;     // >0: residual row = output row % res_row_mod (normal mode only)
+    int act;
+    int out_f32;      // out is fp32 (else bf16)
+    int atomic;       // split-K: red.add.f32 into out (fp32), no bias/act/res
+    int round_steps;  // mirror torch bf16 op boundaries: round after bias, after act, after residual
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int MAX_STAGES = 8;
+    static constexpr int SMEM_BUDGET = 200 * 1024;
+    static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) < MAX_STAGES ? (SMEM_BUDGET / STAGE_BYTES) : MAX_STAGES;
+    static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzle atoms need 1024-byte aligned tiles.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tfull_bar = bars + 2 * STAGES;
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const int ks = u % p.k_splits;
+                const int t = u / p.k_splits;
+                const int m0 = (t % p.num_m_tiles) * BM;
+                const int n0 = (t / p.num_m_tiles) * BN;
+                const int kb0 = ks * p.k_blocks_per_split;
+                const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
+                    tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+                const int ks = u % p.k_splits;
+                const int kb0 = ks * p.k_blocks_per_split;
+                const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * Cfg::A_BYTES));
+                    const uint64_t db = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ------------------------------------------------------------ epilogue
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        int it = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+            const int t = u / p.k_splits;
+            const int m0 = (t % p.num_m_tiles) * BM;
+            const int n0 = (t / p.num_m_tiles) * BN;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+
+            const int r = m0 + quad * 32 + lane;
+            const bool r_ok = r < p.M;
+            int orow = r;
+            if (p.row_map != nullptr && r_ok) orow = p.row_map[r];
+            const bool row_live = r_ok && orow >= 0;
+            float bias_r = 0.f;
+            if (p.bias != nullptr && p.bias_on_rows && r_ok) bias_r = __bfloat162float(p.bias[r]);
+
+            constexpr int CH = BN < 32 ? BN : 32;  // columns per TMEM load
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CH) {
+                float v[CH];
+                {
+                    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN + c0);
+                    if constexpr (CH == 32) {
+                        uint32_t raw[32];
+                        tmem_ld_32x32(taddr, raw);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                    } else {
+                        uint32_t raw[16];
+                        tmem_ld_32x16(taddr, raw);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+                    }
+                }
+                const int cbase = n0 + c0;
+                if (!row_live || cbase >= p.N) continue;
+
+                if (p.atomic) {
+                    float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        const int c = cbase + j;
+                        if (c < p.N) atomicAdd(o + (long long)orow * p.out_rs + (long long)c * p.out_cs, v[j]);
+                    }
+                    continue;
+                }
+                // bias -> act -> residual, rounding like the eager bf16 reference at each op boundary
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int c = cbase + j;
+                    float x = v[j];
+                    if (p.bias != nullptr) {
+                        x += p.bias_on_rows ? bias_r : ((c < p.N) ? __bfloat162float(p.bias[c]) : 0.f);
+                    }
+                    if (p.round_steps) x = bf16_round(x);
+                    if (p.act != ACT_NONE) {
+                        x = apply_act(x, p.act);
+                        if (p.round_steps) x = bf16_round(x);
+                    }
+                    v[j] = x;
+                }
+                if (p.out_cs == 1) {
+                    // row-major output: this thread owns CH consecutive columns of one row
+                    const long long obase = (long long)orow * p.out_rs + cbase;
+                    if (p.res != nullptr) {
+                        const int rrow = p.res_row_mod > 0 ? (orow % p.res_row_mod) : orow;
+                        const bf16* rp = p.res + (long long)rrow * p.res_rs + cbase;
+                        if (cbase + CH <= p.N) {
+#pragma unroll
+                            for (int j = 0; j < CH; j += 8) {
+                                uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+                                float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z),
+                                       f3 = unpack_bf16x2(q.w);
+                                v[j + 0] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
+                                v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j)
+                                if (cbase + j < p.N) v[j] += __bfloat162float(rp[j]);
+                        }
+                    }
+                    if (p.out_f32) {
+                        float* o = reinterpret_cast<float*>(p.out) + obase;
+                        if (cbase + CH <= p.N) {
+#pragma unroll
+                            for (int j = 0; j < CH; j += 4)
+                                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j)
+                                if (cbase + j < p.N) o[j] = v[j];
+                        }
+                    } else {
+                        bf16* o = reinterpret_cast<bf16*>(p.out) + obase;
+                        if (cbase + CH <= p.N) {
+#pragma unroll
+                            for (int j = 0; j < CH; j += 8) {
+                                uint4 q;
+                                q.x = pack_bf16x2(v[j + 0], v[j + 1]);
+                                q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                                q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                                q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                                *reinterpret_cast<uint4*>(o + j) = q;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j)
+                                if (cbase + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+                        }
+                    }
+                } else {
+                    // transposed output (swapped operands): lanes hold consecutive r -> coalesced per column
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        const int c = cbase + j;
+                        if (c >= p.N) continue;
+                        float x = v[j];
+                        if (p.res != nullptr)
+                            x += __bfloat162float(p.res[(long long)orow * p.res_rs + (long long)c * p.res_cs]);
+                        const long long oi = (long long)orow * p.out_rs + (long long)c * p.out_cs;
+                        if (p.out_f32) reinterpret_cast<float*>(p.out)[oi] = x;
+                        else reinterpret_cast<bf16*>(p.out)[oi] = __float2bfloat16_rn(x);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    return fn;
+}
+
+int get_tmap_bf16(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                  const CUtensorMap** out) {
+    TmapKey key{ptr, rows, cols, ld, box_rows};
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) {
+        *out = &it->second;
+        return IVLM_OK;
+    }
+    auto enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return IVLM_ERR_CUDA;
+    }
+    IVLM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand base %p is not 16-byte aligned", ptr);
+    IVLM_REQUIRE((ld * 2) % 16 == 0, "TMA operand row pitch %llu elements is not a multiple of 8",
+                 (unsigned long long)ld);
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+        return IVLM_ERR_CUDA;
+    }
+    if (h->tmaps.size() > 4096) h->tmaps.clear();  // activations churn pointers; keep the cache bounded
+    auto ins = h->tmaps.emplace(key, m);
+    *out = &ins.first->second;
+    return IVLM_OK;
+}
+
+template <int BN>
+static int launch_gemm(ivlm_ctx* h, const CUtensorMap* ta, const CUtensorMap* tb, const GemmParams& p,
+                       cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
+    const int grid = units < h->num_sms ? units : h->num_sms;
+    gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, p);
+    h->launches++;
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    return IVLM_OK;
+}
+
+static int pick_bn(int n) {
+    if (n > 128) return 256;
+    if (n > 64) return 128;
+    if (n > 32) return 64;
+    if (n > 16) return 32;
+    return 16;
+}
+
+}  // namespace ivlm
+
+using namespace ivlm;
+
+extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    IVLM_REQUIRE(h && a, "null handle/args");
+    IVLM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
+    IVLM_REQUIRE(a->K % 8 == 0, "gemm: K=%d must be a multiple of 8", a->K);
+    const bool split = a->k_splits > 1;
+    IVLM_REQUIRE(!split || (a->out_dtype == IVLM_F32 && !a->bias && !a->residual && a->act == 0),
+                 "gemm: split-K accumulates raw fp32 (no bias/act/residual)");
+
+    // Swap operands when the token count is small: the weight rows fill the 128-row UMMA operand.
+    const bool swap = a->force_swap == 1 || (a->force_swap == 0 && a->M <= 64 && a->row_map == nullptr);
+    GemmParams p{};
+    const void *pa, *pb;
+    int64_t lda, ldb;
+    if (!swap) {
+        p.M = a->M; p.N = a->N;
+        pa = a->a; lda = a->lda; pb = a->w; ldb = a->ldw;
+        p.out_rs = a->ldo; p.out_cs = 1;
+        p.res_rs = a->ldr; p.res_cs = 1;
+        p.bias_on_rows = 0;
+        IVLM_REQUIRE(a->N % 8 == 0 && a->ldo % 8 == 0, "gemm: row-major epilogue needs N, ldo multiples of 8");
+        IVLM_REQUIRE(!a->residual || a->ldr % 8 == 0, "gemm: residual pitch must be a multiple of 8");
+    } else {
+        p.M = a->N; p.N = a->M;
+        pa = a->w; lda = a->ldw; pb = a->a; ldb = a->lda;
+        p.out_rs = 1; p.out_cs = a->ldo;
+        p.res_rs = 1; p.res_cs = a->ldr;
+        p.bias_on_rows = 1;
+        IVLM_REQUIRE(a->row_map == nullptr, "gemm: row_map unsupported with swapped operands");
+    }
+    p.K = a->K;
+    const int bn = pick_bn(p.N);
+    p.num_m_tiles = (p.M + BM - 1) / BM;
+    p.num_n_tiles = (p.N + bn - 1) / bn;
+    p.k_blocks = (p.K + BK - 1) / BK;
+    p.k_splits = split ? a->k_splits : 1;
+    if (p.k_splits > p.k_blocks) p.k_splits = p.k_blocks;
+    p.k_blocks_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
+    p.k_splits = (p.k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;  // no empty splits
+    p.out = a->out;
+    p.bias = reinterpret_cast<const bf16*>(a->bias);
+    p.res = reinterpret_cast<const bf16*>(a->residual);
+    p.row_map = a->row_map;
+    p.res_row_mod = a->res_row_mod;
+    IVLM_REQUIRE(!(swap && a->res_row_mod > 0), "gemm: res_row_mod unsupported with swapped operands");
+    p.act = a->act;
+    p.out_f32 = a->out_dtype == IVLM_F32;
+    p.atomic = split ? 1 : 0;
+    p.round_steps = (a->out_dtype == IVLM_BF16 && !a->no_round) ? 1 : 0;
+
+    const CUtensorMap *ta, *tb;
+    IVLM_TRY(get_tmap_bf16(h, pa, p.M, p.K, lda, BM, &ta));
+    IVLM_TRY(get_tmap_bf16(h, pb, p.N, p.K, ldb, bn, &tb));
+    switch (bn) {
+        case 256: return launch_gemm<256>(h, ta, tb, p, stream);
+        case 128: return launch_gemm<128>(h, ta, tb, p, stream);
+        case 64: return launch_gemm<64>(h, ta, tb, p, stream);
+        case 32: return launch_gemm<32>(h, ta, tb, p, stream);
+        default: return launch_gemm<16>(h, ta, tb, p, stream);
+    }
+}

@@ -1,0 +1,126 @@
+// RoPE + paged KV-cache store (LLaMA), and the fused tail of the SAM mask decoder
+// (second ConvTranspose2d + GELU + hypernetwork dot product).
+#include "common.cuh"
+#include "runtime.h"
+
+namespace ivlm {
+
+// HF apply_rotary_pos_emb (transformers 4.31): q_embed = q*cos + rotate_half(q)*sin with bf16 cos/sin tables;
+// every product and the sum are bf16 ops in the reference, so each is rounded here.
+// One CTA per token; thread i handles (head, pair) items.
+__global__ void rope_kv_store_kernel(const bf16* __restrict__ qkv, const int* __restrict__ positions,
+                                     const int* __restrict__ slot_map, const bf16* __restrict__ cos_t,
+                                     const bf16* __restrict__ sin_t, bf16* __restrict__ q_out, bf16* __restrict__ k_out,
+                                     bf16* __restrict__ v_out, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
+                                     int H, int hd) {
+    const long long tkn = blockIdx.x;
+    const int pos = positions[tkn];
+    const long long slot = slot_map ? slot_map[tkn] : -1;
+    const int half = hd >> 1;
+    const int D = H * hd;
+    const bf16* qr = qkv + tkn * 3LL * D;
+    const bf16* kr = qr + D;
+    const bf16* vr = kr + D;
+    for (int i = threadIdx.x; i < H * half; i += blockDim.x) {
+        const int hh = i / half, j = i % half;
+        const float c = __bfloat162float(cos_t[(long long)pos * hd + j]);
+        const float s = __bfloat162float(sin_t[(long long)pos * hd + j]);
+        const int i1 = hh * hd + j, i2 = i1 + half;
+        {
+            const float x1 = __bfloat162float(qr[i1]), x2 = __bfloat162float(qr[i2]);
+            q_out[tkn * D + i1] = __float2bfloat16_rn(bf16_round(x1 * c) + bf16_round(-x2 * s));
+            q_out[tkn * D + i2] = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * s));
+        }
+        {
+            const float x1 = __bfloat162float(kr[i1]), x2 = __bfloat162float(kr[i2]);
+            const bf16 o1 = __float2bfloat16_rn(bf16_round(x1 * c) + bf16_round(-x2 * s));
+            const bf16 o2 = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * s));
+            if (k_out) { k_out[tkn * D + i1] = o1; k_out[tkn * D + i2] = o2; }
+            if (slot >= 0) { k_cache[slot * D + i1] = o1; k_cache[slot * D + i2] = o2; }
+        }
+    }
+    for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) {
+        const uint4 u = reinterpret_cast<const uint4*>(vr)[i];
+        if (v_out) reinterpret_cast<uint4*>(v_out + tkn * D)[i] = u;
+        if (slot >= 0) reinterpret_cast<uint4*>(v_cache + slot * D)[i] = u;
+    }
+}
+
+// up1: [Bv, G*G tokens, 4 (dy1*2+dx1), 64] bf16 (LayerNorm2d+GELU already applied).
+// For each first-stage pixel: z[p2][c] = gelu(bf16(sum_k u[k] W2[p2][c][k] + b2[c])), mask = bf16(sum_c hyper[c] z[p2][c]).
+// Warp = 32 consecutive first-stage pixels with one p2 => shared-memory weight reads are broadcasts.
+__global__ void __launch_bounds__(128) upscale_hyper_dot_kernel(const bf16* __restrict__ up1, const bf16* __restrict__ w2,
+                                                                const bf16* __restrict__ b2,
+                                                                const bf16* __restrict__ hyper, float* __restrict__ lowres,
+                                                                int G) {
+    __shared__ float w_s[4 * 32 * 64];
+    __shared__ float b_s[32], h_s[32];
+    const int bv = blockIdx.y;
+    for (int i = threadIdx.x; i < 4 * 32 * 64; i += blockDim.x) w_s[i] = __bfloat162float(w2[i]);
+    if (threadIdx.x < 32) {
+        b_s[threadIdx.x] = __bfloat162float(b2[threadIdx.x]);
+        h_s[threadIdx.x] = __bfloat162float(hyper[bv * 32 + threadIdx.x]);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p2 = warp;  // 4 warps <-> 4 second-stage sub-pixels
+    const long long vec = (long long)blockIdx.x * 32 + lane;  // first-stage pixel index in [0, G*G*4)
+    const long long nvec = (long long)G * G * 4;
+    if (vec >= nvec) return;
+    const uint4* up = reinterpret_cast<const uint4*>(up1 + ((long long)bv * nvec + vec) * 64);
+    float u[64];
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+        uint4 q = up[c8];
+        float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+        u[c8 * 8 + 0] = a.x; u[c8 * 8 + 1] = a.y; u[c8 * 8 + 2] = b.x; u[c8 * 8 + 3] = b.y;
+        u[c8 * 8 + 4] = c.x; u[c8 * 8 + 5] = c.y; u[c8 * 8 + 6] = d.x; u[c8 * 8 + 7] = d.y;
+    }
+    float m = 0.f;
+    const float* wp = w_s + p2 * 32 * 64;
+#pragma unroll 4
+    for (int c = 0; c < 32; ++c) {
+        float z = 0.f;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) z += u[k] * wp[c * 64 + k];
+        z = bf16_round(z + b_s[c]);
+        z = bf16_round(apply_act(z, ACT_GELU));
+        m += h_s[c] * z;
+    }
+    const long long tok = vec >> 2;
+    const int p1 = (int)(vec & 3);
+    const int y = (int)(tok / G), x = (int)(tok % G);
+    const int Y = (y * 2 + (p1 >> 1)) * 2 + (p2 >> 1);
+    const int X = (x * 2 + (p1 & 1)) * 2 + (p2 & 1);
+    const int LR = G * 4;
+    lowres[((long long)bv * LR + Y) * LR + X] = bf16_round(m);
+}
+
+}  // namespace ivlm
+
+using namespace ivlm;
+
+extern "C" int ivlm_rope_kv_store_bf16(ivlm_handle h, const void* qkv, const int32_t* positions, const int32_t* slot_map,
+                                       const void* cos_t, const void* sin_t, void* q_out, void* k_out, void* v_out,
+                                       void* k_cache, void* v_cache, int32_t T, int32_t H, int32_t hd, void* stream) {
+    IVLM_REQUIRE(h && T > 0 && (H * hd) % 8 == 0 && hd % 2 == 0, "rope: bad shape");
+    IVLM_REQUIRE(slot_map == nullptr || (k_cache && v_cache), "rope: slot_map given without caches");
+    rope_kv_store_kernel<<<T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const bf16*)qkv, positions, slot_map, (const bf16*)cos_t, (const bf16*)sin_t, (bf16*)q_out, (bf16*)k_out,
+        (bf16*)v_out, (bf16*)k_cache, (bf16*)v_cache, H, hd);
+    h->launches++;
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    return IVLM_OK;
+}
+
+extern "C" int ivlm_upscale_hyper_dot(ivlm_handle h, const void* up1, const void* w2, const void* b2, const void* hyper,
+                                      float* lowres, int32_t Bv, int32_t grid_, void* stream) {
+    IVLM_REQUIRE(h && Bv > 0 && grid_ > 0, "upscale_hyper_dot: empty");
+    const long long nvec = (long long)grid_ * grid_ * 4;
+    dim3 grid((unsigned)((nvec + 31) / 32), Bv);
+    upscale_hyper_dot_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const bf16*)up1, (const bf16*)w2, (const bf16*)b2, (const bf16*)hyper, lowres, grid_);
+    h->launches++;
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    return IVLM_OK;
+}

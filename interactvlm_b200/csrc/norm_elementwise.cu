@@ -1,0 +1,449 @@
+// HBM-bound row-wise and elementwise kernels: LayerNorm / RMSNorm (warp per row, 16-byte loads, warp-shuffle
+// reductions, fp32 statistics), broadcast add, SwiGLU gate, split-K finalize, casts, im2col lowering,
+// embedding gather / image splice, greedy argmax, bilinear resize, camera gate.
+#include "common.cuh"
+#include "runtime.h"
+
+namespace ivlm {
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per output row; D multiple of 8. x is re-read from L1 for the second/third pass.
+__global__ void layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ gamma,
+                                 const bf16* __restrict__ beta, long long out_rows, int D, float eps,
+                                 const int* __restrict__ row_map, int act) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= out_rows) return;
+    const int lane = threadIdx.x & 31;
+    long long src = row;
+    if (row_map != nullptr) src = row_map[row];
+    bf16* yr = y + row * D;
+    const int nvec = D >> 3;
+    if (src < 0) {  // window padding rows are zeros AFTER the norm (image_encoder.py:179-183)
+        for (int i = lane; i < nvec; i += 32) reinterpret_cast<uint4*>(yr)[i] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const uint4* xr = reinterpret_cast<const uint4*>(x + src * D);
+    float s = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+        uint4 q = xr[i];
+        float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+        s += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float ss = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+        uint4 q = xr[i];
+        float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+        float t;
+        t = a.x - mean; ss += t * t; t = a.y - mean; ss += t * t;
+        t = b.x - mean; ss += t * t; t = b.y - mean; ss += t * t;
+        t = c.x - mean; ss += t * t; t = c.y - mean; ss += t * t;
+        t = d.x - mean; ss += t * t; t = d.y - mean; ss += t * t;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
+    const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
+    const uint4* b4 = reinterpret_cast<const uint4*>(beta);
+    for (int i = lane; i < nvec; i += 32) {
+        uint4 q = xr[i], g = g4[i], b = b4[i];
+        uint32_t xi[4] = {q.x, q.y, q.z, q.w}, gi[4] = {g.x, g.y, g.z, g.w}, bi[4] = {b.x, b.y, b.z, b.w}, o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 xv = unpack_bf16x2(xi[j]), gv = unpack_bf16x2(gi[j]), bv = unpack_bf16x2(bi[j]);
+            float r0 = (xv.x - mean) * rstd * gv.x + bv.x;
+            float r1 = (xv.y - mean) * rstd * gv.y + bv.y;
+            if (act != ACT_NONE) {
+                r0 = apply_act(bf16_round(r0), act);
+                r1 = apply_act(bf16_round(r1), act);
+            }
+            o[j] = pack_bf16x2(r0, r1);
+        }
+        reinterpret_cast<uint4*>(yr)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// HF LlamaRMSNorm (transformers 4.31 modeling_llama.py): variance in fp32, normalised value cast to bf16,
+// then multiplied by the bf16 weight.
+__global__ void rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ gamma,
+                               long long rows, int D, float eps) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
+    const int nvec = D >> 3;
+    float ss = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+        uint4 q = xr[i];
+        float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+        ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
+    const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
+    uint4* yr = reinterpret_cast<uint4*>(y + row * D);
+    for (int i = lane; i < nvec; i += 32) {
+        uint4 q = xr[i], g = g4[i];
+        uint32_t xi[4] = {q.x, q.y, q.z, q.w}, gi[4] = {g.x, g.y, g.z, g.w}, o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 xv = unpack_bf16x2(xi[j]), gv = unpack_bf16x2(gi[j]);
+            o[j] = pack_bf16x2(gv.x * bf16_round(xv.x * rstd), gv.y * bf16_round(xv.y * rstd));
+        }
+        yr[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+__global__ void add_bcast_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                                 long long nvec, long long pvec) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+         i += (long long)gridDim.x * blockDim.x) {
+        uint4 x = a[i], y = b[pvec ? (i % pvec) : i];
+        uint32_t xi[4] = {x.x, x.y, x.z, x.w}, yi[4] = {y.x, y.y, y.z, y.w}, o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 p = unpack_bf16x2(xi[j]), q = unpack_bf16x2(yi[j]);
+            o[j] = pack_bf16x2(p.x + q.x, p.y + q.y);
+        }
+        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__global__ void silu_mul_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, long long rows, int F) {
+    const int fvec = F >> 3;
+    const long long total = rows * fvec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / fvec;
+        const int c = (int)(i % fvec);
+        uint4 g = reinterpret_cast<const uint4*>(gu + r * 2 * F)[c];
+        uint4 u = reinterpret_cast<const uint4*>(gu + r * 2 * F + F)[c];
+        uint32_t gi[4] = {g.x, g.y, g.z, g.w}, ui[4] = {u.x, u.y, u.z, u.w}, o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 gv = unpack_bf16x2(gi[j]), uv = unpack_bf16x2(ui[j]);
+            o[j] = pack_bf16x2(bf16_round(apply_act(gv.x, ACT_SILU)) * uv.x, bf16_round(apply_act(gv.y, ACT_SILU)) * uv.y);
+        }
+        reinterpret_cast<uint4*>(out + r * F)[c] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__global__ void finalize_kernel(const float* __restrict__ acc, bf16* __restrict__ out, const bf16* __restrict__ bias,
+                                const bf16* __restrict__ res, long long rows, int N, int act) {
+    const long long total = rows * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % N);
+        float x = acc[i];
+        if (bias) x += __bfloat162float(bias[c]);
+        x = bf16_round(x);
+        if (act != ACT_NONE) x = bf16_round(apply_act(x, act));
+        if (res) x += __bfloat162float(res[i]);
+        out[i] = __float2bfloat16_rn(x);
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = __bfloat162float(x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ im2col
+// One thread per output element pair is overkill; one thread per (row, k) element with k fastest keeps the
+// stores coalesced and the loads contiguous along dx.
+__global__ void im2col_patch_kernel(const bf16* __restrict__ img, bf16* __restrict__ cols, int N, int C, int H, int W,
+                                    int p, int ldk) {
+    const int gw = W / p, gh = H / p;
+    const long long total = (long long)N * gh * gw * ldk;
+    const int kk = C * p * p;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % ldk);
+        const long long row = i / ldk;
+        bf16 v = __float2bfloat16_rn(0.f);
+        if (k < kk) {
+            const int dx = k % p, dy = (k / p) % p, c = k / (p * p);
+            const int px = (int)(row % gw), py = (int)((row / gw) % gh);
+            const long long n = row / ((long long)gw * gh);
+            v = img[((n * C + c) * H + (py * p + dy)) * (long long)W + (px * p + dx)];
+        }
+        cols[i] = v;
+    }
+}
+
+// 3x3, pad 1, token-major input [N,H,W,C]; 8 channels (16 B) per thread.
+__global__ void im2col_3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ cols, int N, int H, int W, int C) {
+    const int cvec = C >> 3;
+    const long long total = (long long)N * H * W * 9 * cvec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % cvec);
+        const int tap = (int)((i / cvec) % 9);
+        const long long row = i / (9LL * cvec);
+        const int xx = (int)(row % W), yy = (int)((row / W) % H);
+        const long long n = row / ((long long)W * H);
+        const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W)
+            v = reinterpret_cast<const uint4*>(x + ((n * H + sy) * (long long)W + sx) * C)[cv];
+        reinterpret_cast<uint4*>(cols + row * 9LL * C + (long long)tap * C)[cv] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ LLaVA glue
+// out row (b, j): j < pos -> embed[ids[b,j]]; pos <= j < pos+n_img -> img[b, j-pos]; else embed[ids[b, j-n_img+1]].
+// pos = index of the single IMAGE_TOKEN_INDEX (-200) in row b.
+__global__ void embed_splice_kernel(const bf16* __restrict__ embed, const int* __restrict__ ids,
+                                    const bf16* __restrict__ img, bf16* __restrict__ out, int B, int L, int n_img, int D,
+                                    int vocab) {
+    const int S = L - 1 + n_img;
+    const long long row = blockIdx.x;
+    const int b = (int)(row / S), j = (int)(row % S);
+    __shared__ int s_pos;
+    if (threadIdx.x == 0) {
+        int pos = L;
+        for (int t = 0; t < L; ++t)
+            if (ids[b * L + t] < 0) { pos = t; break; }
+        s_pos = pos;
+    }
+    __syncthreads();
+    const int pos = s_pos;
+    const uint4* src;
+    if (j < pos) {
+        int id = ids[b * L + j];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        src = reinterpret_cast<const uint4*>(embed + (long long)id * D);
+    } else if (j < pos + n_img) {
+        src = reinterpret_cast<const uint4*>(img + ((long long)b * n_img + (j - pos)) * D);
+    } else {
+        int id = ids[b * L + (j - n_img + 1)];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        src = reinterpret_cast<const uint4*>(embed + (long long)id * D);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + row * D);
+    for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void gather_rows_kernel(const bf16* __restrict__ x, const int* __restrict__ idx, bf16* __restrict__ out, int n,
+                                   int D, int max_row) {
+    const int r = blockIdx.x;
+    int s = idx[r];
+    if (max_row > 0) s = s < 0 ? 0 : (s >= max_row ? max_row - 1 : s);
+    const uint4* src = reinterpret_cast<const uint4*>(x + (long long)s * D);
+    uint4* dst = reinterpret_cast<uint4*>(out + (long long)r * D);
+    for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) dst[i] = src[i];
+}
+
+// torch.argmax semantics: first maximal index. One CTA per row.
+__global__ void argmax_kernel(const float* __restrict__ logits, int* __restrict__ out, int vocab, long long ld) {
+    const float* row = logits + (long long)blockIdx.x * ld;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+        const float v = row[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        best = lane < nw ? sv[lane] : -INFINITY;
+        bi = lane < nw ? si[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) out[blockIdx.x] = bi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ bilinear
+// PyTorch upsample_bilinear2d, align_corners=False: src = max((dst+0.5)*scale-0.5, 0), scale = in/out.
+__global__ void bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int sh, int sw, int ch,
+                                int cw, int dh, int dw) {
+    const float sy = (float)ch / (float)dh, sx = (float)cw / (float)dw;
+    const long long total = (long long)N * dh * dw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % dw), y = (int)((i / dw) % dh);
+        const long long n = i / ((long long)dw * dh);
+        float fy = fmaxf(((float)y + 0.5f) * sy - 0.5f, 0.f);
+        float fx = fmaxf(((float)x + 0.5f) * sx - 0.5f, 0.f);
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < ch - 1 ? 1 : 0), x1 = x0 + (x0 < cw - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const float* s = src + n * (long long)sh * sw;
+        // same association as ATen's upsample_bilinear2d: hy*(hx*a + lx*b) + ly*(hx*c + lx*d)
+        const float top = __fadd_rn(__fmul_rn(hx, s[(long long)y0 * sw + x0]), __fmul_rn(lx, s[(long long)y0 * sw + x1]));
+        const float bot = __fadd_rn(__fmul_rn(hx, s[(long long)y1 * sw + x0]), __fmul_rn(lx, s[(long long)y1 * sw + x1]));
+        dst[i] = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ camera gate
+// One CTA of 256 threads per (sample, view). Every nn.Linear output is rounded to bf16 like the reference.
+__global__ void cam_gate_kernel(const bf16* __restrict__ cam, const bf16* __restrict__ emb, const bf16* __restrict__ w1,
+                                const bf16* __restrict__ b1, const bf16* __restrict__ w2, const bf16* __restrict__ b2,
+                                const bf16* __restrict__ wv, const bf16* __restrict__ bv, bf16* __restrict__ out, int V) {
+    const int b = blockIdx.x / V, v = blockIdx.x % V;
+    __shared__ float h1[128], h2[128], c[5];
+    const int t = threadIdx.x;
+    if (t < 5) c[t] = __bfloat162float(cam[(b * V + v) * 5 + t]);
+    __syncthreads();
+    if (t < 128) {
+        float s = 0.f;
+        for (int k = 0; k < 5; ++k) s += c[k] * __bfloat162float(w1[t * 5 + k]);
+        s = bf16_round(s + __bfloat162float(b1[t]));
+        h1[t] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    if (t < 128) {
+        float s = 0.f;
+        for (int k = 0; k < 128; ++k) s += h1[k] * __bfloat162float(w2[t * 128 + k]);
+        s = bf16_round(s + __bfloat162float(b2[t]));
+        h2[t] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    {
+        const bf16* w = wv + ((long long)v * 256 + t) * 128;
+        float s = 0.f;
+        for (int k = 0; k < 128; ++k) s += h2[k] * __bfloat162float(w[k]);
+        s = bf16_round(s + __bfloat162float(bv[v * 256 + t]));
+        const float g = bf16_round(1.f / (1.f + __expf(-s)));
+        out[((long long)b * V + v) * 256 + t] = __float2bfloat16_rn(__bfloat162float(emb[b * 256 + t]) * g);
+    }
+}
+
+static inline int grid_for(long long work, int block, int sms) {
+    long long g = (work + block - 1) / block;
+    long long cap = (long long)sms * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace ivlm
+
+using namespace ivlm;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+#define DONE()                          \
+    h->launches++;                      \
+    IVLM_CHECK_CUDA(cudaGetLastError()); \
+    return IVLM_OK
+
+extern "C" int ivlm_layernorm_bf16(ivlm_handle h, const void* x, void* y, const void* gamma, const void* beta,
+                                   int64_t out_rows, int32_t D, float eps, const int32_t* row_map, int32_t act,
+                                   void* stream) {
+    IVLM_REQUIRE(h && D % 8 == 0 && out_rows > 0, "layernorm: D=%d must be a multiple of 8, rows>0", D);
+    const int wpb = 8;
+    layernorm_kernel<<<(unsigned)((out_rows + wpb - 1) / wpb), wpb * 32, 0, STREAM>>>(
+        (const bf16*)x, (bf16*)y, (const bf16*)gamma, (const bf16*)beta, out_rows, D, eps, row_map, act);
+    DONE();
+}
+extern "C" int ivlm_rmsnorm_bf16(ivlm_handle h, const void* x, void* y, const void* gamma, int64_t rows, int32_t D,
+                                 float eps, void* stream) {
+    IVLM_REQUIRE(h && D % 8 == 0 && rows > 0, "rmsnorm: D=%d must be a multiple of 8, rows>0", D);
+    const int wpb = 8;
+    rmsnorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, STREAM>>>((const bf16*)x, (bf16*)y,
+                                                                                (const bf16*)gamma, rows, D, eps);
+    DONE();
+}
+extern "C" int ivlm_add_bcast_bf16(ivlm_handle h, const void* a, const void* b, void* out, int64_t n, int64_t period,
+                                   void* stream) {
+    IVLM_REQUIRE(h && n % 8 == 0 && period % 8 == 0, "add_bcast: n and period must be multiples of 8");
+    add_bcast_kernel<<<grid_for(n / 8, 256, h->num_sms), 256, 0, STREAM>>>((const uint4*)a, (const uint4*)b, (uint4*)out,
+                                                                           n / 8, period / 8);
+    DONE();
+}
+extern "C" int ivlm_silu_mul_bf16(ivlm_handle h, const void* gate_up, void* out, int64_t rows, int32_t F, void* stream) {
+    IVLM_REQUIRE(h && F % 8 == 0, "silu_mul: F must be a multiple of 8");
+    silu_mul_kernel<<<grid_for(rows * (F / 8), 256, h->num_sms), 256, 0, STREAM>>>((const bf16*)gate_up, (bf16*)out, rows,
+                                                                                  F);
+    DONE();
+}
+extern "C" int ivlm_finalize_f32_bf16(ivlm_handle h, const float* acc, void* out, const void* bias, const void* residual,
+                                      int64_t rows, int32_t N, int32_t act, void* stream) {
+    IVLM_REQUIRE(h && rows > 0 && N > 0, "finalize: empty");
+    finalize_kernel<<<grid_for(rows * N, 256, h->num_sms), 256, 0, STREAM>>>(acc, (bf16*)out, (const bf16*)bias,
+                                                                            (const bf16*)residual, rows, N, act);
+    DONE();
+}
+extern "C" int ivlm_cast_f32_bf16(ivlm_handle h, const float* x, void* y, int64_t n, void* stream) {
+    IVLM_REQUIRE(h && n > 0, "cast: empty");
+    cast_f32_bf16_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, STREAM>>>(x, (bf16*)y, n);
+    DONE();
+}
+extern "C" int ivlm_cast_bf16_f32(ivlm_handle h, const void* x, float* y, int64_t n, void* stream) {
+    IVLM_REQUIRE(h && n > 0, "cast: empty");
+    cast_bf16_f32_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, STREAM>>>((const bf16*)x, y, n);
+    DONE();
+}
+extern "C" int ivlm_im2col_patch_bf16(ivlm_handle h, const void* img, void* cols, int32_t N, int32_t C, int32_t H,
+                                      int32_t W, int32_t p, int32_t ldk, void* stream) {
+    IVLM_REQUIRE(h && H % p == 0 && W % p == 0 && ldk >= C * p * p && ldk % 8 == 0, "im2col_patch: bad geometry");
+    const long long total = (long long)N * (H / p) * (W / p) * ldk;
+    im2col_patch_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, STREAM>>>((const bf16*)img, (bf16*)cols, N, C, H, W, p,
+                                                                             ldk);
+    DONE();
+}
+extern "C" int ivlm_im2col_3x3_bf16(ivlm_handle h, const void* x, void* cols, int32_t N, int32_t H, int32_t W, int32_t C,
+                                    void* stream) {
+    IVLM_REQUIRE(h && C % 8 == 0, "im2col_3x3: C must be a multiple of 8");
+    const long long total = (long long)N * H * W * 9 * (C / 8);
+    im2col_3x3_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, STREAM>>>((const bf16*)x, (bf16*)cols, N, H, W, C);
+    DONE();
+}
+extern "C" int ivlm_embed_splice_bf16(ivlm_handle h, const void* embed, const int32_t* ids, const void* img_feats,
+                                      void* out, int32_t B, int32_t L, int32_t n_img, int32_t D, int32_t vocab,
+                                      void* stream) {
+    IVLM_REQUIRE(h && D % 8 == 0 && B > 0 && L > 0, "embed_splice: bad shape");
+    embed_splice_kernel<<<B * (L - 1 + n_img), 128, 0, STREAM>>>((const bf16*)embed, ids, (const bf16*)img_feats,
+                                                                  (bf16*)out, B, L, n_img, D, vocab);
+    DONE();
+}
+extern "C" int ivlm_embed_gather_bf16(ivlm_handle h, const void* embed, const int32_t* ids, void* out, int32_t n,
+                                      int32_t D, int32_t vocab, void* stream) {
+    IVLM_REQUIRE(h && D % 8 == 0 && n > 0, "embed_gather: bad shape");
+    gather_rows_kernel<<<n, 128, 0, STREAM>>>((const bf16*)embed, ids, (bf16*)out, n, D, vocab);
+    DONE();
+}
+extern "C" int ivlm_gather_rows_bf16(ivlm_handle h, const void* x, const int32_t* idx, void* out, int32_t n, int32_t D,
+                                     void* stream) {
+    IVLM_REQUIRE(h && D % 8 == 0 && n > 0, "gather_rows: bad shape");
+    gather_rows_kernel<<<n, 128, 0, STREAM>>>((const bf16*)x, idx, (bf16*)out, n, D, 0);
+    DONE();
+}
+extern "C" int ivlm_argmax_f32(ivlm_handle h, const float* logits, int32_t* out, int32_t B, int32_t vocab, int64_t ld,
+                               void* stream) {
+    IVLM_REQUIRE(h && B > 0 && vocab > 0, "argmax: empty");
+    argmax_kernel<<<B, 1024, 0, STREAM>>>(logits, out, vocab, ld);
+    DONE();
+}
+extern "C" int ivlm_bilinear_f32(ivlm_handle h, const float* src, float* dst, int32_t N, int32_t sh, int32_t sw,
+                                 int32_t crop_h, int32_t crop_w, int32_t dh, int32_t dw, void* stream) {
+    IVLM_REQUIRE(h && crop_h <= sh && crop_w <= sw && crop_h > 0 && crop_w > 0 && N > 0, "bilinear: bad geometry");
+    bilinear_kernel<<<grid_for((long long)N * dh * dw, 256, h->num_sms), 256, 0, STREAM>>>(src, dst, N, sh, sw, crop_h,
+                                                                                         crop_w, dh, dw);
+    DONE();
+}
+extern "C" int ivlm_cam_gate_bf16(ivlm_handle h, const void* cam, const void* emb, const void* w1, const void* b1,
+                                  const void* w2, const void* b2, const void* wv, const void* bv, void* out, int32_t B,
+                                  int32_t V, void* stream) {
+    IVLM_REQUIRE(h && B > 0 && V > 0, "cam_gate: empty");
+    cam_gate_kernel<<<B * V, 256, 0, STREAM>>>((const bf16*)cam, (const bf16*)emb, (const bf16*)w1, (const bf16*)b1,
+                                               (const bf16*)w2, (const bf16*)b2, (const bf16*)wv, (const bf16*)bv,
+                                               (bf16*)out, V);
+    DONE();
+}

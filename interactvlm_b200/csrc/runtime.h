@@ -1,0 +1,94 @@
+// Internal host-side runtime shared by the C-ABI translation units: context, error reporting,
+// TMA tensor-map cache, bump workspace. Not part of the public ABI (see include/ivlm_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ivlm_b200.h"
+
+namespace ivlm {
+
+void set_error(const char* fmt, ...);
+
+#define IVLM_CHECK_CUDA(expr)                                                                 \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ivlm::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,             \
+                            cudaGetErrorString(_e));                                          \
+            return IVLM_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define IVLM_REQUIRE(cond, ...)                                                               \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            ivlm::set_error(__VA_ARGS__);                                                     \
+            return IVLM_ERR_ARG;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define IVLM_TRY(expr)                                                                        \
+    do {                                                                                      \
+        int _s = (expr);                                                                      \
+        if (_s != IVLM_OK) return _s;                                                         \
+    } while (0)
+
+struct TmapKey {
+    const void* ptr;
+    uint64_t rows, cols, ld;
+    uint32_t box_rows;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        h = h * 1000003u ^ k.rows;
+        h = h * 1000003u ^ k.cols;
+        h = h * 1000003u ^ k.ld;
+        h = h * 1000003u ^ k.box_rows;
+        return h;
+    }
+};
+
+struct Weight {
+    const void* ptr = nullptr;
+    int dtype = 0;  // IVLM_BF16 / IVLM_F32 / IVLM_I32
+    int ndim = 0;
+    int64_t shape[4] = {0, 0, 0, 0};
+};
+
+}  // namespace ivlm
+
+struct ivlm_ctx {
+    int device = 0;
+    int num_sms = 148;
+    uint64_t launches = 0;  // kernels launched through this handle (bench "gpu_launches")
+    std::unordered_map<ivlm::TmapKey, CUtensorMap, ivlm::TmapKeyHash> tmaps;
+    std::unordered_map<std::string, ivlm::Weight> weights;
+    // caller-provided scratch (bump allocated inside stage drivers)
+    char* ws = nullptr;
+    size_t ws_bytes = 0;
+    size_t ws_off = 0;
+
+    void* ws_alloc(size_t bytes) {
+        size_t a = (ws_off + 255) & ~size_t(255);
+        if (a + bytes > ws_bytes) return nullptr;
+        ws_off = a + bytes;
+        return ws + a;
+    }
+};
+
+namespace ivlm {
+// Returns (creating and caching if needed) a 2D bf16 tensor map: rows x cols, row pitch ld elements,
+// box = box_rows x 64 elements, 128B swizzle, zero OOB fill.
+int get_tmap_bf16(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                  const CUtensorMap** out);
+}  // namespace ivlm
