@@ -1,0 +1,78 @@
+"""ctypes binding of libivlm_b200.so (the C ABI declared in include/ivlm_b200.h).
+
+There is no fallback: if the shared library is missing or a symbol is absent, importing the product
+path raises.  The oracle under oracle/ is test infrastructure and is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libivlm_b200.so"
+HEADER = PKG.parent / "include" / "ivlm_b200.h"
+
+BF16, F32, I32, I64 = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_RELU, ACT_SILU = 0, 1, 2, 3, 4
+LIFT_HUMAN, LIFT_OBJECT_MESH, LIFT_POINTS = 0, 1, 2
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_int64),
+        ("w", C.c_void_p), ("ldw", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("row_map", C.c_void_p),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("act", C.c_int32), ("out_dtype", C.c_int32), ("k_splits", C.c_int32),
+        ("force_swap", C.c_int32), ("no_round", C.c_int32), ("res_row_mod", C.c_int32),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("q_bs", C.c_int64), ("q_ts", C.c_int64), ("q_hs", C.c_int64),
+        ("k_bs", C.c_int64), ("k_ts", C.c_int64), ("k_hs", C.c_int64),
+        ("v_bs", C.c_int64), ("v_ts", C.c_int64), ("v_hs", C.c_int64),
+        ("o_bs", C.c_int64), ("o_ts", C.c_int64), ("o_hs", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32), ("D", C.c_int32),
+        ("scale", C.c_float), ("causal", C.c_int32),
+        ("rel_h", C.c_void_p), ("rel_w", C.c_void_p),
+        ("kh", C.c_int32), ("kw", C.c_int32),
+    ]
+
+
+def declared_symbols() -> list[str]:
+    """Every function the public header declares (used by the CPU-side ABI test)."""
+    txt = HEADER.read_text()
+    return sorted(set(re.findall(r"IVLM_API\s+[\w\s\*]+?\b(ivlm_\w+)\s*\(", txt)))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m interactvlm_b200.build` "
+                "(there is no CPU or PyTorch fallback for the hot path)")
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.ivlm_last_error.restype = C.c_char_p
+        _lib.ivlm_launch_count.restype = C.c_uint64
+        _lib.ivlm_lift_nnz.restype = C.c_int64
+        for name in declared_symbols():
+            if not hasattr(_lib, name):
+                raise RuntimeError(f"libivlm_b200.so does not export {name}")
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().ivlm_last_error().decode(errors="replace")
+        raise RuntimeError(f"ivlm_b200 {what} failed ({status}): {msg}")

@@ -1,0 +1,378 @@
+"""Torch-tensor front end of the C ABI.  PyTorch is plumbing only: it owns device memory and streams;
+every computation below is one of our sm_100a kernels launched through libivlm_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._lib import (ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_RELU, ACT_SILU, BF16, F32, LIFT_HUMAN,  # noqa: F401
+                   LIFT_OBJECT_MESH, LIFT_POINTS)
+
+i32, i64, f32c = C.c_int32, C.c_int64, C.c_float
+
+
+def P(t):
+    if t is None:
+        return C.c_void_p(None)
+    return C.c_void_p(t.data_ptr())
+
+
+def _bf16(t, name="tensor"):
+    assert t.dtype == torch.bfloat16 and t.is_cuda, f"{name}: expected a CUDA bf16 tensor, got {t.dtype} on {t.device}"
+    return t
+
+
+class Context:
+    """One ivlm handle bound to one CUDA device."""
+
+    def __init__(self, device: int | torch.device = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("interactvlm_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+        self.device = torch.device("cuda", device if isinstance(device, int) else (device.index or 0))
+        self.lib = L.lib()
+        h = C.c_void_p()
+        torch.cuda.set_device(self.device)
+        L.check(self.lib.ivlm_create(C.byref(h), i32(self.device.index)), "ivlm_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ivlm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_count(self) -> int:
+        return int(self.lib.ivlm_launch_count(self.h))
+
+    # ------------------------------------------------------------------ dense
+    def gemm(self, a, w, bias=None, act=ACT_NONE, residual=None, out=None, out_dtype=torch.bfloat16, row_map=None,
+             out_rows=None, k_splits=1, force_swap=0, no_round=False, res_row_mod=0):
+        """out = act(a @ w.T + bias) + residual.  a [M,K], w [N,K] bf16 (last dim contiguous)."""
+        _bf16(a, "a"); _bf16(w, "w")
+        assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
+        assert a.stride(1) == 1 and w.stride(1) == 1
+        M, K = a.shape
+        N = w.shape[0]
+        if out is None:
+            rows = M if out_rows is None else out_rows
+            out = torch.empty((rows, N), device=a.device, dtype=out_dtype)
+            if k_splits > 1:
+                out.zero_()
+        assert out.stride(1) == 1
+        args = L.GemmArgs()
+        args.a, args.lda = a.data_ptr(), a.stride(0)
+        args.w, args.ldw = w.data_ptr(), w.stride(0)
+        args.out, args.ldo = out.data_ptr(), out.stride(0)
+        args.bias = _bf16(bias, "bias").data_ptr() if bias is not None else None
+        if residual is not None:
+            _bf16(residual, "residual")
+            assert residual.stride(1) == 1
+            args.residual, args.ldr = residual.data_ptr(), residual.stride(0)
+        if row_map is not None:
+            assert row_map.dtype == torch.int32 and row_map.numel() == M
+            args.row_map = row_map.data_ptr()
+        args.M, args.N, args.K = M, N, K
+        args.act = act
+        args.out_dtype = BF16 if out.dtype == torch.bfloat16 else F32
+        args.k_splits = k_splits
+        args.force_swap = force_swap
+        args.no_round = 1 if no_round else 0
+        args.res_row_mod = res_row_mod
+        L.check(self.lib.ivlm_gemm_bf16(self.h, C.byref(args), self.stream), "gemm")
+        return out
+
+    # ------------------------------------------------------------------ norms / elementwise
+    def layernorm(self, x, gamma, beta, eps, row_map=None, out_rows=None, act=ACT_NONE, out=None):
+        _bf16(x)
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        rows = x2.shape[0] if row_map is None else (row_map.numel() if out_rows is None else out_rows)
+        if out is None:
+            out = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_layernorm_bf16(self.h, P(x2), P(out), P(gamma), P(beta), i64(rows), i32(D), f32c(eps),
+                                             P(row_map), i32(act), self.stream), "layernorm")
+        return out if row_map is not None else out.view(x.shape)
+
+    def rmsnorm(self, x, gamma, eps, out=None):
+        _bf16(x)
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        if out is None:
+            out = torch.empty_like(x2)
+        L.check(self.lib.ivlm_rmsnorm_bf16(self.h, P(x2), P(out), P(gamma), i64(x2.shape[0]), i32(D), f32c(eps),
+                                           self.stream), "rmsnorm")
+        return out.view(x.shape)
+
+    def add_bcast(self, a, b, out=None):
+        _bf16(a); _bf16(b)
+        assert a.is_contiguous() and b.is_contiguous()
+        if out is None:
+            out = torch.empty_like(a)
+        period = 0 if b.numel() == a.numel() else b.numel()
+        L.check(self.lib.ivlm_add_bcast_bf16(self.h, P(a), P(b), P(out), i64(a.numel()), i64(period), self.stream),
+                "add_bcast")
+        return out
+
+    def silu_mul(self, gate_up, out=None):
+        _bf16(gate_up)
+        rows, F2 = gate_up.shape
+        if out is None:
+            out = torch.empty((rows, F2 // 2), device=gate_up.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_silu_mul_bf16(self.h, P(gate_up), P(out), i64(rows), i32(F2 // 2), self.stream), "silu_mul")
+        return out
+
+    def finalize(self, acc, bias=None, residual=None, act=ACT_NONE, out=None):
+        assert acc.dtype == torch.float32 and acc.is_contiguous()
+        rows, N = acc.shape
+        if out is None:
+            out = torch.empty((rows, N), device=acc.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_finalize_f32_bf16(self.h, P(acc), P(out), P(bias), P(residual), i64(rows), i32(N), i32(act),
+                                                self.stream), "finalize")
+        return out
+
+    def to_bf16(self, x):
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_cast_f32_bf16(self.h, P(x), P(out), i64(x.numel()), self.stream), "cast")
+        return out
+
+    def to_f32(self, x):
+        _bf16(x)
+        assert x.is_contiguous()
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        L.check(self.lib.ivlm_cast_bf16_f32(self.h, P(x), P(out), i64(x.numel()), self.stream), "cast")
+        return out
+
+    # ------------------------------------------------------------------ lowering
+    def im2col_patch(self, img, p, ldk=None):
+        _bf16(img)
+        assert img.is_contiguous()
+        N, Cc, H, W = img.shape
+        kk = Cc * p * p
+        ldk = ldk or ((kk + 7) // 8) * 8
+        out = torch.empty((N * (H // p) * (W // p), ldk), device=img.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_im2col_patch_bf16(self.h, P(img), P(out), i32(N), i32(Cc), i32(H), i32(W), i32(p), i32(ldk),
+                                                self.stream), "im2col_patch")
+        return out
+
+    def im2col_3x3(self, x, N, H, W):
+        _bf16(x)
+        assert x.is_contiguous()
+        Cc = x.shape[-1]
+        out = torch.empty((N * H * W, 9 * Cc), device=x.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_im2col_3x3_bf16(self.h, P(x), P(out), i32(N), i32(H), i32(W), i32(Cc), self.stream),
+                "im2col_3x3")
+        return out
+
+    # ------------------------------------------------------------------ attention
+    def attention(self, q, k, v, scale, causal=False, rel_h=None, rel_w=None, kh=0, kw=0, out=None):
+        """q [B,Sq,H,D], k/v [B,Sk,H,D] bf16 views (any batch/token/head strides, D contiguous) -> [B,Sq,H,D]."""
+        _bf16(q); _bf16(k); _bf16(v)
+        B, Sq, H, D = q.shape
+        Sk = k.shape[1]
+        assert q.stride(3) == 1 and k.stride(3) == 1 and v.stride(3) == 1
+        if out is None:
+            out = torch.empty((B, Sq, H, D), device=q.device, dtype=torch.bfloat16)
+        a = L.AttnArgs()
+        a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+        a.q_bs, a.q_ts, a.q_hs = q.stride(0), q.stride(1), q.stride(2)
+        a.k_bs, a.k_ts, a.k_hs = k.stride(0), k.stride(1), k.stride(2)
+        a.v_bs, a.v_ts, a.v_hs = v.stride(0), v.stride(1), v.stride(2)
+        a.o_bs, a.o_ts, a.o_hs = out.stride(0), out.stride(1), out.stride(2)
+        a.B, a.H, a.Sq, a.Sk, a.D = B, H, Sq, Sk, D
+        a.scale = scale
+        a.causal = 1 if causal else 0
+        if rel_h is not None:
+            assert rel_h.dtype == torch.float32 and rel_w.dtype == torch.float32
+            a.rel_h, a.rel_w, a.kh, a.kw = rel_h.data_ptr(), rel_w.data_ptr(), kh, kw
+        L.check(self.lib.ivlm_attention_bf16(self.h, C.byref(a), self.stream), "attention")
+        return out
+
+    def sam_relpos(self, qkv, rel_pos_h, rel_pos_w, B, heads, Hq, Wq, hd):
+        _bf16(qkv)
+        S = Hq * Wq
+        rel_h = torch.empty((B, heads, S, Hq), device=qkv.device, dtype=torch.float32)
+        rel_w = torch.empty((B, heads, S, Wq), device=qkv.device, dtype=torch.float32)
+        L.check(self.lib.ivlm_sam_relpos(self.h, P(qkv), P(rel_pos_h), P(rel_pos_w), P(rel_h), P(rel_w), i32(B),
+                                         i32(heads), i32(Hq), i32(Wq), i32(hd), self.stream), "sam_relpos")
+        return rel_h, rel_w
+
+    def attn_small(self, q, k, v, heads):
+        """q [Bq,Nq,C] (Bq == 1 broadcasts), k/v [B,Nk,C] -> [B,Nq,C]."""
+        _bf16(q); _bf16(k); _bf16(v)
+        assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+        B, Nk, Cc = k.shape
+        Nq = q.shape[1]
+        bcast = 1 if (q.shape[0] == 1 and B > 1) else 0
+        out = torch.empty((B, Nq, Cc), device=q.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_attn_small_bf16(self.h, P(q), P(k), P(v), P(out), i32(B), i32(bcast), i32(Nq), i32(Nk),
+                                              i32(heads), i32(Cc // heads), self.stream), "attn_small")
+        return out
+
+    # ------------------------------------------------------------------ LLaVA / LLaMA glue
+    def embed_splice(self, embed, ids, img_feats):
+        _bf16(embed); _bf16(img_feats)
+        assert ids.dtype == torch.int32 and ids.is_contiguous() and img_feats.is_contiguous()
+        B, Lq = ids.shape
+        n_img, D = img_feats.shape[1], img_feats.shape[2]
+        out = torch.empty((B, Lq - 1 + n_img, D), device=embed.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_embed_splice_bf16(self.h, P(embed), P(ids), P(img_feats), P(out), i32(B), i32(Lq), i32(n_img),
+                                                i32(D), i32(embed.shape[0]), self.stream), "embed_splice")
+        return out
+
+    def embed_gather(self, embed, ids, out=None):
+        assert ids.dtype == torch.int32
+        n, D = ids.numel(), embed.shape[1]
+        if out is None:
+            out = torch.empty((n, D), device=embed.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_embed_gather_bf16(self.h, P(embed), P(ids), P(out), i32(n), i32(D), i32(embed.shape[0]),
+                                                self.stream), "embed_gather")
+        return out
+
+    def gather_rows(self, x, idx):
+        _bf16(x)
+        assert idx.dtype == torch.int32 and x.is_contiguous()
+        out = torch.empty((idx.numel(), x.shape[-1]), device=x.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_gather_rows_bf16(self.h, P(x), P(idx), P(out), i32(idx.numel()), i32(x.shape[-1]),
+                                               self.stream), "gather_rows")
+        return out
+
+    def rope_kv_store(self, qkv, positions, slot_map, cos_t, sin_t, H, hd, k_cache=None, v_cache=None, want_kv=True,
+                      q_out=None):
+        _bf16(qkv)
+        T = qkv.shape[0]
+        D = H * hd
+        if q_out is None:
+            q_out = torch.empty((T, D), device=qkv.device, dtype=torch.bfloat16)
+        k_out = torch.empty((T, D), device=qkv.device, dtype=torch.bfloat16) if want_kv else None
+        v_out = torch.empty((T, D), device=qkv.device, dtype=torch.bfloat16) if want_kv else None
+        L.check(self.lib.ivlm_rope_kv_store_bf16(self.h, P(qkv), P(positions), P(slot_map), P(cos_t), P(sin_t), P(q_out),
+                                                 P(k_out), P(v_out), P(k_cache), P(v_cache), i32(T), i32(H), i32(hd),
+                                                 self.stream), "rope_kv_store")
+        return q_out, k_out, v_out
+
+    def decode_attention(self, q, k_cache, v_cache, block_table, seq_lens, H, hd, page_size, out=None):
+        _bf16(q)
+        B = q.shape[0]
+        if out is None:
+            out = torch.empty((B, H * hd), device=q.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_decode_attention_paged_bf16(self.h, P(q), P(k_cache), P(v_cache), P(block_table), P(seq_lens),
+                                                          P(out), i32(B), i32(H), i32(hd), i32(page_size),
+                                                          i32(block_table.shape[1]), f32c(1.0 / math.sqrt(hd)),
+                                                          self.stream), "decode_attention")
+        return out
+
+    def argmax(self, logits, vocab=None, out=None):
+        assert logits.dtype == torch.float32 and logits.stride(1) == 1
+        B = logits.shape[0]
+        vocab = vocab or logits.shape[1]
+        if out is None:
+            out = torch.empty((B,), device=logits.device, dtype=torch.int32)
+        L.check(self.lib.ivlm_argmax_f32(self.h, P(logits), P(out), i32(B), i32(vocab), i64(logits.stride(0)),
+                                         self.stream), "argmax")
+        return out
+
+    # ------------------------------------------------------------------ prompt / mask tail
+    def cam_gate(self, cam, emb, w1, b1, w2, b2, wv, bv):
+        _bf16(cam); _bf16(emb)
+        B, V = cam.shape[0], cam.shape[1]
+        out = torch.empty((B, V, 256), device=cam.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_cam_gate_bf16(self.h, P(cam.contiguous()), P(emb.contiguous()), P(w1), P(b1), P(w2), P(b2),
+                                            P(wv), P(bv), P(out), i32(B), i32(V), self.stream), "cam_gate")
+        return out
+
+    def upscale_hyper_dot(self, up1, w2, b2, hyper, Bv, grid):
+        _bf16(up1); _bf16(hyper)
+        out = torch.empty((Bv, grid * 4, grid * 4), device=up1.device, dtype=torch.float32)
+        L.check(self.lib.ivlm_upscale_hyper_dot(self.h, P(up1), P(w2), P(b2), P(hyper.contiguous()), P(out), i32(Bv),
+                                                i32(grid), self.stream), "upscale_hyper_dot")
+        return out
+
+    def bilinear(self, src, dh, dw, crop_h=None, crop_w=None, out=None):
+        assert src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 3
+        N, sh, sw = src.shape
+        crop_h, crop_w = crop_h or sh, crop_w or sw
+        if out is None:
+            out = torch.empty((N, dh, dw), device=src.device, dtype=torch.float32)
+        L.check(self.lib.ivlm_bilinear_f32(self.h, P(src), P(out), i32(N), i32(sh), i32(sw), i32(crop_h), i32(crop_w),
+                                           i32(dh), i32(dw), self.stream), "bilinear")
+        return out
+
+
+class LiftMap:
+    """Per-(view, vertex) CSR built once from the reference's pixel->vertex / barycentric maps."""
+
+    def __init__(self, ctx: Context, p2v: np.ndarray, bary: np.ndarray | None, n_verts: int):
+        self.ctx = ctx
+        p2v = np.ascontiguousarray(p2v, dtype=np.int64)
+        self.ptr = C.c_void_p()
+        if bary is not None:
+            bary = np.ascontiguousarray(bary, dtype=np.float32)
+            V, H, W, three = p2v.shape
+            assert three == 3 and bary.shape == p2v.shape
+            L.check(ctx.lib.ivlm_lift_build_mesh(ctx.h, p2v.ctypes.data_as(C.c_void_p), bary.ctypes.data_as(C.c_void_p),
+                                                 i32(V), i32(H), i32(W), i32(n_verts), C.byref(self.ptr)),
+                    "lift_build_mesh")
+        else:
+            V, H, W = p2v.shape
+            L.check(ctx.lib.ivlm_lift_build_points(ctx.h, p2v.ctypes.data_as(C.c_void_p), i32(V), i32(H), i32(W),
+                                                   i32(n_verts), C.byref(self.ptr)), "lift_build_points")
+        self.V, self.H, self.W, self.n = V, H, W, n_verts
+        self.nnz = int(ctx.lib.ivlm_lift_nnz(self.ptr))
+
+    def __call__(self, masks: torch.Tensor, mode: int, thr: float = 0.3) -> torch.Tensor:
+        assert masks.dtype == torch.float32 and masks.is_cuda and masks.is_contiguous()
+        B = masks.shape[0]
+        assert tuple(masks.shape[1:]) == (self.V, self.H, self.W), (masks.shape, (self.V, self.H, self.W))
+        out = torch.empty((B, self.n), device=masks.device, dtype=torch.float32)
+        L.check(self.ctx.lib.ivlm_lift(self.ctx.h, self.ptr, P(masks), P(out), i32(B), i32(mode), f32c(thr),
+                                       self.ctx.stream), "lift")
+        return out
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.ctx.lib.ivlm_lift_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class CsrMatrix:
+    """Sparse form of a dense host matrix (SMPL -> SMPL-X vertex mapping, utils/utils.py:428-443)."""
+
+    def __init__(self, ctx: Context, dense: np.ndarray):
+        self.ctx = ctx
+        dense = np.ascontiguousarray(dense, dtype=np.float32)
+        self.rows, self.cols = dense.shape
+        self.ptr = C.c_void_p()
+        L.check(ctx.lib.ivlm_csr_build_dense(ctx.h, dense.ctypes.data_as(C.c_void_p), i32(self.rows), i32(self.cols),
+                                             C.byref(self.ptr)), "csr_build_dense")
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous() and x.shape[-1] == self.cols
+        B = x.reshape(-1, self.cols).shape[0]
+        y = torch.empty((B, self.rows), device=x.device, dtype=torch.float32)
+        L.check(self.ctx.lib.ivlm_csr_spmv(self.ctx.h, self.ptr, P(x), P(y), i32(B), self.ctx.stream), "csr_spmv")
+        return y
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.ctx.lib.ivlm_csr_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
