@@ -70,8 +70,7 @@ def apply(clip_config=None):
     # 3. CLIP comes from the hub in the reference; build it locally from a config with random init
     cfg = clip_config or tiny_clip_config()
     transformers.CLIPVisionConfig.from_pretrained = classmethod(lambda cls, *a, **k: cfg)
-    transformers.CLIPVisionModel.from_pretrained = classmethod(
-        lambda cls, *a, **k: transformers.CLIPVisionModel(_eager(cfg)))
+    transformers.CLIPVisionModel.from_pretrained = classmethod(lambda cls, *a, **k: _clip_431_class()(_eager(cfg)))
     transformers.CLIPImageProcessor.from_pretrained = classmethod(lambda cls, *a, **k: transformers.CLIPImageProcessor())
     # 4. hard-coded .cuda() calls (InteractVLM.py:335,339,393,547,561) on a CPU-only box
     if not torch.cuda.is_available():
@@ -84,6 +83,29 @@ def apply(clip_config=None):
     import importlib
 
     return importlib.import_module("model.InteractVLM")
+
+
+def _clip_431_class():
+    """transformers 5.x collects `hidden_states` with forward hooks that double-record once the tower has been called
+    from inside another model's forward (probed: 7 entries instead of 4 after one LLaVA forward), which shifts
+    `hidden_states[-2]`.  transformers 4.31 (the reference's pin) returns (embeddings, layer_1, ..., layer_L); this
+    subclass builds exactly that tuple from the stock sub-modules."""
+    import types as _t
+
+    import transformers
+
+    class CLIPVisionModel431(transformers.CLIPVisionModel):
+        def forward(self, pixel_values=None, output_hidden_states=False, **kw):
+            vm = self.vision_model
+            h = vm.pre_layrnorm(vm.embeddings(pixel_values))
+            states = [h]
+            for layer in vm.encoder.layers:
+                h = layer(h, None)
+                h = h[0] if isinstance(h, tuple) else h
+                states.append(h)
+            return _t.SimpleNamespace(last_hidden_state=h, hidden_states=tuple(states))
+
+    return CLIPVisionModel431
 
 
 def _eager(cfg):
