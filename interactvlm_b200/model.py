@@ -1,0 +1,752 @@
+"""InteractVLMForCausalLM: the reference's inference API (model/InteractVLM.py:139-638) on the sm_100a kernels.
+
+Host code only: this module decides WHAT runs (shapes, order, index bookkeeping) and owns the buffers; every
+floating-point operation is one of the kernels behind the C ABI (interactvlm_b200/ops.py -> libivlm_b200.so).
+Differences from the reference that do not change results:
+  * generate() keeps a paged KV cache and encodes the CLIP image once; the reference recomputes the whole sequence
+    every step (use_cache=False) -- the hidden states it finally reads equal one causal pass over output_ids[:, :-1];
+  * text_hidden_fcs runs on the [SEG]-1 rows only, not on every position;
+  * SAM embeddings stay token-major ([N, 64*64, 256]); the decoder flattens them that way anyway;
+  * the dense positional encoding and the window-partition maps are built once;
+  * lifting uses the per-vertex CSR gather (ops.LiftMap) instead of atomically scattering 150 MB of maps.
+"""
+from __future__ import annotations
+
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .config import IVLMConfig
+from .synthetic import CLIP_PREFIX, SAM_PREFIX
+
+IMAGE_TOKEN_INDEX = -200
+ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_RELU, ACT_SILU = 0, 1, 2, 3, 4
+LIFT_HUMAN, LIFT_OBJECT_MESH, LIFT_POINTS = 0, 1, 2
+PAGE = 16  # KV-cache page size (tokens)
+
+
+def _i32(x, device):
+    return torch.as_tensor(np.asarray(x, dtype=np.int32), device=device)
+
+
+class _Weights:
+    """bf16 device copies of the checkpoint tensors, re-laid-out once for the kernels (fused qkv / gate-up,
+    conv weights flattened to GEMM operands).  Keys follow the reference checkpoint."""
+
+    def __init__(self, sd: dict, cfg: IVLMConfig, device):
+        self.device = device
+        dt = torch.bfloat16
+
+        def g(name):
+            if name not in sd:
+                raise KeyError(f"checkpoint is missing {name}")
+            return sd[name].detach().to(device=device, dtype=dt).contiguous()
+
+        self.g = g
+        L = self.llm = []
+        for i in range(cfg.num_hidden_layers):
+            p = f"model.layers.{i}."
+            L.append(dict(
+                ln1=g(p + "input_layernorm.weight"), ln2=g(p + "post_attention_layernorm.weight"),
+                wqkv=torch.cat([g(p + f"self_attn.{n}_proj.weight") for n in "qkv"], 0).contiguous(),
+                wo=g(p + "self_attn.o_proj.weight"),
+                wgu=torch.cat([g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")], 0).contiguous(),
+                wd=g(p + "mlp.down_proj.weight")))
+        self.embed = g("model.embed_tokens.weight")
+        self.norm = g("model.norm.weight")
+        self.lm_head = g("lm_head.weight")
+        hd = cfg.head_dim
+        inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+        fr = torch.outer(torch.arange(cfg.max_position_embeddings, dtype=torch.float32), inv)
+        emb = torch.cat((fr, fr), -1)
+        self.rope_cos, self.rope_sin = emb.cos().to(dt).to(device), emb.sin().to(dt).to(device)
+        # CLIP
+        c = CLIP_PREFIX
+        C = cfg.clip_hidden_size
+        kk = 3 * cfg.clip_patch_size ** 2
+        self.clip_ldk = (kk + 7) // 8 * 8
+        wpe = torch.zeros((C, self.clip_ldk), device=device, dtype=dt)
+        wpe[:, :kk] = g(c + "embeddings.patch_embedding.weight").reshape(C, kk)
+        pos = g(c + "embeddings.position_embedding.weight")
+        self.clip = dict(w_patch=wpe, pos=pos,
+                         cls_pos=(g(c + "embeddings.class_embedding") + pos[0]).contiguous(),
+                         pre_g=g(c + "pre_layrnorm.weight"), pre_b=g(c + "pre_layrnorm.bias"), layers=[])
+        for i in range(cfg.clip_layers_used):
+            p = c + f"encoder.layers.{i}."
+            self.clip["layers"].append(dict(
+                ln1g=g(p + "layer_norm1.weight"), ln1b=g(p + "layer_norm1.bias"),
+                wqkv=torch.cat([g(p + f"self_attn.{n}_proj.weight") for n in "qkv"], 0).contiguous(),
+                bqkv=torch.cat([g(p + f"self_attn.{n}_proj.bias") for n in "qkv"], 0).contiguous(),
+                wo=g(p + "self_attn.out_proj.weight"), bo=g(p + "self_attn.out_proj.bias"),
+                ln2g=g(p + "layer_norm2.weight"), ln2b=g(p + "layer_norm2.bias"),
+                w1=g(p + "mlp.fc1.weight"), b1=g(p + "mlp.fc1.bias"), w2=g(p + "mlp.fc2.weight"), b2=g(p + "mlp.fc2.bias")))
+        self.mm_w, self.mm_b = g("model.mm_projector.weight"), g("model.mm_projector.bias")
+        # SAM image encoder
+        e = SAM_PREFIX + "image_encoder."
+        E = cfg.sam_embed_dim
+        self.sam = dict(w_patch=g(e + "patch_embed.proj.weight").reshape(E, -1).contiguous(), b_patch=g(e + "patch_embed.proj.bias"),
+                        pos=g(e + "pos_embed").reshape(-1, E).contiguous(), blocks=[],
+                        neck0=g(e + "neck.0.weight").reshape(cfg.sam_out_chans, E).contiguous(),
+                        n1g=g(e + "neck.1.weight"), n1b=g(e + "neck.1.bias"),
+                        neck2=g(e + "neck.2.weight").permute(0, 2, 3, 1).reshape(cfg.sam_out_chans, -1).contiguous(),
+                        n3g=g(e + "neck.3.weight"), n3b=g(e + "neck.3.bias"))
+        for i in range(cfg.sam_depth):
+            p = e + f"blocks.{i}."
+            self.sam["blocks"].append(dict(
+                n1g=g(p + "norm1.weight"), n1b=g(p + "norm1.bias"), rph=g(p + "attn.rel_pos_h"), rpw=g(p + "attn.rel_pos_w"),
+                wqkv=g(p + "attn.qkv.weight"), bqkv=g(p + "attn.qkv.bias"), wo=g(p + "attn.proj.weight"), bo=g(p + "attn.proj.bias"),
+                n2g=g(p + "norm2.weight"), n2b=g(p + "norm2.bias"), w1=g(p + "mlp.lin1.weight"), b1=g(p + "mlp.lin1.bias"),
+                w2=g(p + "mlp.lin2.weight"), b2=g(p + "mlp.lin2.bias")))
+        # prompt encoder constants + mask decoder
+        self.no_mask = g(SAM_PREFIX + "prompt_encoder.no_mask_embed.weight").reshape(-1).contiguous()
+        self.dense_pe = self._dense_pe(g(SAM_PREFIX + "prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"), cfg)
+        d = SAM_PREFIX + "mask_decoder."
+
+        def attn(p):
+            return dict(wq=g(p + "q_proj.weight"), bq=g(p + "q_proj.bias"), wk=g(p + "k_proj.weight"), bk=g(p + "k_proj.bias"),
+                        wv=g(p + "v_proj.weight"), bv=g(p + "v_proj.bias"), wo=g(p + "out_proj.weight"), bo=g(p + "out_proj.bias"))
+
+        self.dec = dict(layers=[], final=attn(d + "transformer.final_attn_token_to_image."),
+                        nfg=g(d + "transformer.norm_final_attn.weight"), nfb=g(d + "transformer.norm_final_attn.bias"),
+                        out_tokens=torch.cat([g(d + "iou_token.weight"), g(d + "mask_tokens.weight")], 0).contiguous())
+        for i in range(cfg.sam_dec_depth):
+            p = d + f"transformer.layers.{i}."
+            self.dec["layers"].append(dict(
+                self_attn=attn(p + "self_attn."), t2i=attn(p + "cross_attn_token_to_image."), i2t=attn(p + "cross_attn_image_to_token."),
+                n=[(g(p + f"norm{k}.weight"), g(p + f"norm{k}.bias")) for k in (1, 2, 3, 4)],
+                w1=g(p + "mlp.lin1.weight"), b1=g(p + "mlp.lin1.bias"), w2=g(p + "mlp.lin2.weight"), b2=g(p + "mlp.lin2.bias")))
+        up0 = g(d + "output_upscaling.0.weight")  # [ci, co, dy, dx]
+        co = up0.shape[1]
+        self.dec["up0_w"] = up0.permute(2, 3, 1, 0).reshape(4 * co, up0.shape[0]).contiguous()  # row (dy*2+dx)*co + c
+        self.dec["up0_b"] = g(d + "output_upscaling.0.bias").repeat(4).contiguous()
+        self.dec["up_ln"] = (g(d + "output_upscaling.1.weight"), g(d + "output_upscaling.1.bias"))
+        up3 = g(d + "output_upscaling.3.weight")
+        self.dec["up3_w"] = up3.permute(2, 3, 1, 0).reshape(4, up3.shape[1], up3.shape[0]).contiguous()  # [sub-pixel, co, ci]
+        self.dec["up3_b"] = g(d + "output_upscaling.3.bias")
+        hp = d + "output_hypernetworks_mlps.0.layers."  # multimask_output=False keeps mask token 0 only
+        self.dec["hyper"] = [(g(hp + f"{k}.weight"), g(hp + f"{k}.bias")) for k in range(3)]
+        # [SEG] projection, camera gate
+        self.fc = (g("model.text_hidden_fcs.0.0.weight"), g("model.text_hidden_fcs.0.0.bias"),
+                   g("model.text_hidden_fcs.0.2.weight"), g("model.text_hidden_fcs.0.2.bias"))
+        self.cam = None
+        if cfg.multiview_cam_cond:
+            if cfg.cam_encoder_type != "vi_v1":
+                raise NotImplementedError("only cam_encoder_type='vi_v1' (the released checkpoints) is on the hot path")
+            V = cfg.multiview_channels
+            self.cam = (g("cam_pose_encoder.spatial_encoder.0.weight"), g("cam_pose_encoder.spatial_encoder.0.bias"),
+                        g("cam_pose_encoder.spatial_encoder.2.weight"), g("cam_pose_encoder.spatial_encoder.2.bias"),
+                        torch.stack([g(f"cam_pose_encoder.view_transforms.{v}.weight") for v in range(V)], 0).contiguous(),
+                        torch.stack([g(f"cam_pose_encoder.view_transforms.{v}.bias") for v in range(V)], 0).contiguous())
+        del self.g
+
+    @staticmethod
+    def _dense_pe(G, cfg):
+        """PromptEncoder.get_dense_pe() (prompt_encoder.py:203-229), evaluated ONCE at load time in the model dtype like
+        the reference does on every call (the gaussian matrix is a buffer, so model.bfloat16() casts it and the whole
+        encoding runs in bf16).  Returns token-major [grid*grid, 256]."""
+        g = cfg.sam_grid
+        grid = torch.ones((g, g), device=G.device, dtype=G.dtype)
+        y = (grid.cumsum(0) - 0.5) / g
+        x = (grid.cumsum(1) - 0.5) / g
+        c = 2 * torch.stack([x, y], -1) - 1
+        c = c @ G
+        c = 2 * np.pi * c
+        return torch.cat([torch.sin(c), torch.cos(c)], -1).reshape(g * g, -1).contiguous()
+
+
+class _Engine:
+    """Stage drivers: each method is a fixed sequence of kernel launches on `ctx`."""
+
+    def __init__(self, ctx, cfg: IVLMConfig, w: _Weights):
+        self.ctx, self.cfg, self.w = ctx, cfg, w
+        self.device = w.device
+        self._win_maps = {}
+
+    # ------------------------------------------------------------------ CLIP + projector (a4)
+    def clip_encode(self, images_clip):
+        """[B,3,224,224] bf16 -> projected patch features [B,256,D] (clip_encoder.py:31-60, llava_arch.py:93-96)."""
+        ctx, cfg, w = self.ctx, self.cfg, self.w.clip
+        B = images_clip.shape[0]
+        C, nh = cfg.clip_hidden_size, cfg.clip_num_attention_heads
+        hd = C // nh
+        T = cfg.clip_tokens
+        cols = ctx.im2col_patch(images_clip.contiguous(), cfg.clip_patch_size, ldk=self.w.clip_ldk)
+        rm = (torch.arange(B, dtype=torch.int32)[:, None] * T + 1 + torch.arange(T - 1, dtype=torch.int32)[None]).reshape(-1)
+        h = torch.empty((B * T, C), device=self.device, dtype=torch.bfloat16)
+        h.view(B, T, C)[:, 0] = w["cls_pos"]
+        ctx.gemm(cols, w["w_patch"], residual=w["pos"], res_row_mod=T, row_map=rm.to(self.device), out=h, force_swap=-1)
+        h = ctx.layernorm(h, w["pre_g"], w["pre_b"], cfg.clip_layer_norm_eps)
+        for lw in w["layers"]:
+            y = ctx.layernorm(h, lw["ln1g"], lw["ln1b"], cfg.clip_layer_norm_eps)
+            qkv = ctx.gemm(y, lw["wqkv"], bias=lw["bqkv"]).view(B, T, 3, nh, hd)
+            o = ctx.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], hd ** -0.5)
+            h = ctx.gemm(o.view(B * T, C), lw["wo"], bias=lw["bo"], residual=h)
+            y = ctx.layernorm(h, lw["ln2g"], lw["ln2b"], cfg.clip_layer_norm_eps)
+            y = ctx.gemm(y, lw["w1"], bias=lw["b1"], act=ACT_QUICK_GELU)
+            h = ctx.gemm(y, lw["w2"], bias=lw["b2"], residual=h)
+        patches = ctx.gather_rows(h, rm.to(self.device))
+        return ctx.gemm(patches, self.w.mm_w, bias=self.w.mm_b).view(B, T - 1, cfg.hidden_size)
+
+    # ------------------------------------------------------------------ SAM ViT (a9)
+    def _window_map(self, N):
+        """Row map of window_partition with zero padding (image_encoder.py:263-288): window-major row -> token or -1."""
+        if N not in self._win_maps:
+            g, ws = self.cfg.sam_grid, self.cfg.sam_window_size
+            nw = (g + ws - 1) // ws
+            n, wy, wx, iy, ix = np.meshgrid(np.arange(N), np.arange(nw), np.arange(nw), np.arange(ws), np.arange(ws), indexing="ij")
+            y, x = wy * ws + iy, wx * ws + ix
+            src = np.where((y < g) & (x < g), n * g * g + y * g + x, -1)
+            self._win_maps[N] = (_i32(src.reshape(-1), self.device), nw)
+        return self._win_maps[N]
+
+    def sam_encode(self, images):
+        """[N,3,1024,1024] bf16 -> token-major embeddings [N, 4096, 256] (image_encoder.py:110-125)."""
+        ctx, cfg, w = self.ctx, self.cfg, self.w.sam
+        N = images.shape[0]
+        g, E, nh, ws = cfg.sam_grid, cfg.sam_embed_dim, cfg.sam_num_heads, cfg.sam_window_size
+        hd = E // nh
+        S = g * g
+        cols = ctx.im2col_patch(images.contiguous(), cfg.sam_patch_size)
+        x = ctx.gemm(cols, w["w_patch"], bias=w["b_patch"], residual=w["pos"], res_row_mod=S, force_swap=-1)
+        del cols
+        wmap, nw = self._window_map(N)
+        for i, bw in enumerate(w["blocks"]):
+            if i in cfg.sam_global_attn_indexes:
+                y = ctx.layernorm(x, bw["n1g"], bw["n1b"], 1e-6)
+                qkv = ctx.gemm(y, bw["wqkv"], bias=bw["bqkv"], force_swap=-1)
+                rel_h, rel_w = ctx.sam_relpos(qkv, bw["rph"], bw["rpw"], N, nh, g, g, hd)
+                t = qkv.view(N, S, 3, nh, hd)
+                o = ctx.attention(t[:, :, 0], t[:, :, 1], t[:, :, 2], hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=g, kw=g)
+                x = ctx.gemm(o.view(N * S, E), bw["wo"], bias=bw["bo"], residual=x, force_swap=-1)
+            else:
+                Bw, Sw = N * nw * nw, ws * ws
+                y = ctx.layernorm(x, bw["n1g"], bw["n1b"], 1e-6, row_map=wmap)
+                qkv = ctx.gemm(y, bw["wqkv"], bias=bw["bqkv"], force_swap=-1)
+                rel_h, rel_w = ctx.sam_relpos(qkv, bw["rph"], bw["rpw"], Bw, nh, ws, ws, hd)
+                t = qkv.view(Bw, Sw, 3, nh, hd)
+                o = ctx.attention(t[:, :, 0], t[:, :, 1], t[:, :, 2], hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=ws, kw=ws)
+                xn = torch.empty_like(x)
+                ctx.gemm(o.view(Bw * Sw, E), bw["wo"], bias=bw["bo"], residual=x, row_map=wmap, out=xn, force_swap=-1)
+                x = xn
+            del qkv, rel_h, rel_w, t, o
+            y = ctx.layernorm(x, bw["n2g"], bw["n2b"], 1e-6)
+            y = ctx.gemm(y, bw["w1"], bias=bw["b1"], act=ACT_GELU, force_swap=-1)
+            x = ctx.gemm(y, bw["w2"], bias=bw["b2"], residual=x, force_swap=-1)
+            del y
+        y = ctx.gemm(x, w["neck0"], force_swap=-1)
+        y = ctx.layernorm(y, w["n1g"], w["n1b"], 1e-6)
+        cols = ctx.im2col_3x3(y, N, g, g)
+        y = ctx.gemm(cols, w["neck2"], force_swap=-1)
+        return ctx.layernorm(y, w["n3g"], w["n3b"], 1e-6).view(N, S, cfg.sam_out_chans)
+
+    # ------------------------------------------------------------------ LLaMA (a5, a6)
+    def llm_alloc(self, B, max_len):
+        cfg = self.cfg
+        pages_per = (max_len + PAGE - 1) // PAGE
+        st = dict(B=B, max_len=max_len, pages_per=pages_per)
+        st["block_table"] = torch.arange(B * pages_per, dtype=torch.int32, device=self.device).view(B, pages_per).contiguous()
+        slots = B * pages_per * PAGE
+        st["k"] = [torch.empty((slots, cfg.num_attention_heads, cfg.head_dim), device=self.device, dtype=torch.bfloat16)
+                   for _ in range(cfg.num_hidden_layers)]
+        st["v"] = [torch.empty_like(k) for k in st["k"]]
+        st["hidden"] = torch.zeros((B, max_len, cfg.hidden_size), device=self.device, dtype=torch.bfloat16)
+        return st
+
+    def llm_prefill(self, st, embeds):
+        """embeds [B,S,D] -> writes K/V pages and the normed last-layer hidden states of all S positions; returns the
+        greedy next token per sample [B] int32 (HF LlamaModel + lm_head, eager 4.31 numerics)."""
+        ctx, cfg, W = self.ctx, self.cfg, self.w
+        B, S, D = embeds.shape
+        nh, hd = cfg.num_attention_heads, cfg.head_dim
+        pos = torch.arange(S, dtype=torch.int32).repeat(B)
+        slot = (torch.arange(B, dtype=torch.int32)[:, None] * (st["pages_per"] * PAGE) + torch.arange(S, dtype=torch.int32)[None]).reshape(-1)
+        pos, slot = pos.to(self.device), slot.to(self.device)
+        x = embeds.reshape(B * S, D)
+        for i, lw in enumerate(W.llm):
+            y = ctx.rmsnorm(x, lw["ln1"], cfg.rms_norm_eps)
+            qkv = ctx.gemm(y, lw["wqkv"])
+            q, k, v = ctx.rope_kv_store(qkv, pos, slot, W.rope_cos, W.rope_sin, nh, hd, st["k"][i], st["v"][i])
+            o = ctx.attention(q.view(B, S, nh, hd), k.view(B, S, nh, hd), v.view(B, S, nh, hd), 1.0 / math.sqrt(hd), causal=True)
+            x = ctx.gemm(o.view(B * S, D), lw["wo"], residual=x)
+            y = ctx.rmsnorm(x, lw["ln2"], cfg.rms_norm_eps)
+            y = ctx.silu_mul(ctx.gemm(y, lw["wgu"]))
+            x = ctx.gemm(y, lw["wd"], residual=x)
+        hn = ctx.rmsnorm(x, W.norm, cfg.rms_norm_eps).view(B, S, D)
+        st["hidden"][:, :S] = hn
+        st["len"] = S
+        return self._greedy(hn[:, S - 1].contiguous())
+
+    def _greedy(self, h, out=None):
+        """lm_head + argmax.  Rows go through the swapped-operand GEMM in chunks of <= 64 (the vocabulary size of the
+        released checkpoints, 32004, is not a multiple of 8, which the row-major epilogue would need)."""
+        ctx, cfg = self.ctx, self.cfg
+        B = h.shape[0]
+        if out is None:
+            out = torch.empty((B,), device=self.device, dtype=torch.int32)
+        for b0 in range(0, B, 64):
+            logits = ctx.gemm(h[b0:b0 + 64], self.w.lm_head, out_dtype=torch.float32, force_swap=1)
+            ctx.argmax(logits, vocab=cfg.vocab_size, out=out[b0:b0 + 64])
+        return out
+
+    def llm_decode_buffers(self, st):
+        B = st["B"]
+        st["tok"] = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        st["pos"] = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        st["slot"] = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        st["seq_lens"] = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        st["next"] = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        st["hid_step"] = torch.zeros((B, self.cfg.hidden_size), dtype=torch.bfloat16, device=self.device)
+        st["slot_base"] = (torch.arange(B, dtype=torch.int32, device=self.device) * (st["pages_per"] * PAGE)).contiguous()
+
+    def llm_decode_step(self, st):
+        """One token per sample through the paged KV cache.  Reads st['tok'|'pos'|'slot'|'seq_lens'] (device),
+        writes st['next'] (greedy token) and st['hid_step'] (normed hidden of the fed token).  Fixed launch sequence
+        with fixed buffers -> CUDA-graph capturable."""
+        ctx, cfg, W = self.ctx, self.cfg, self.w
+        nh, hd = cfg.num_attention_heads, cfg.head_dim
+        x = ctx.embed_gather(W.embed, st["tok"])
+        for i, lw in enumerate(W.llm):
+            y = ctx.rmsnorm(x, lw["ln1"], cfg.rms_norm_eps)
+            qkv = ctx.gemm(y, lw["wqkv"])
+            q, _, _ = ctx.rope_kv_store(qkv, st["pos"], st["slot"], W.rope_cos, W.rope_sin, nh, hd, st["k"][i], st["v"][i],
+                                        want_kv=False)
+            o = ctx.decode_attention(q, st["k"][i], st["v"][i], st["block_table"], st["seq_lens"], nh, hd, PAGE)
+            x = ctx.gemm(o, lw["wo"], residual=x)
+            y = ctx.rmsnorm(x, lw["ln2"], cfg.rms_norm_eps)
+            y = ctx.silu_mul(ctx.gemm(y, lw["wgu"]))
+            x = ctx.gemm(y, lw["wd"], residual=x)
+        ctx.rmsnorm(x, W.norm, cfg.rms_norm_eps, out=st["hid_step"])
+        self._greedy(st["hid_step"], out=st["next"])
+
+    # ------------------------------------------------------------------ [SEG] head (a7, a10)
+    def seg_prompt(self, hidden_rows, cam_params):
+        """hidden_rows [n,D] bf16, cam_params [n,V,5] bf16 -> view-gated prompt tokens [n,V,256]."""
+        ctx, w = self.ctx, self.w
+        y = ctx.gemm(hidden_rows, w.fc[0], bias=w.fc[1], act=ACT_RELU)
+        emb = ctx.gemm(y, w.fc[2], bias=w.fc[3])
+        if w.cam is None:
+            return emb[:, None, :].repeat(1, self.cfg.multiview_channels, 1).contiguous(), emb
+        return ctx.cam_gate(cam_params, emb, *w.cam), emb
+
+    # ------------------------------------------------------------------ prompt encoder + mask decoder (a11, a12)
+    def _dec_attn(self, aw, q, k, v, heads, residual=None):
+        """transformer.py:185-242 Attention: q [Bq,Nq,256], k/v [Bk,Nk,256] -> [Bk,Nq,256] (+ residual)."""
+        ctx = self.ctx
+        C = q.shape[-1]
+        qp = ctx.gemm(q.reshape(-1, C), aw["wq"], bias=aw["bq"]).view(q.shape[0], q.shape[1], -1)
+        kp = ctx.gemm(k.reshape(-1, C), aw["wk"], bias=aw["bk"]).view(k.shape[0], k.shape[1], -1)
+        vp = ctx.gemm(v.reshape(-1, C), aw["wv"], bias=aw["bv"]).view(v.shape[0], v.shape[1], -1)
+        o = ctx.attn_small(qp, kp, vp, heads)
+        res = residual.reshape(-1, C) if residual is not None else None
+        return ctx.gemm(o.reshape(-1, o.shape[-1]), aw["wo"], bias=aw["bo"], residual=res).view(o.shape[0], o.shape[1], C)
+
+    def mask_decode(self, emb, prompt):
+        """emb [n*V,4096,256] token-major SAM embeddings, prompt [n,V,256] -> low-res logits [n*V,256,256] fp32.
+        Every view of a sample sees the sample's 5 output tokens + all V gated prompt tokens."""
+        ctx, cfg, w = self.ctx, self.cfg, self.w.dec
+        n, V, C = prompt.shape
+        nv, S = emb.shape[0], emb.shape[1]
+        heads = cfg.sam_dec_heads
+        ntok = w["out_tokens"].shape[0] + V
+        tokens = torch.empty((n, V, ntok, C), device=self.device, dtype=torch.bfloat16)
+        tokens[:, :, : ntok - V] = w["out_tokens"]
+        tokens[:, :, ntok - V:] = prompt[:, None]
+        tokens = tokens.view(nv, ntok, C)
+        keys = ctx.add_bcast(emb.contiguous(), self.w.no_mask)
+        key_pe = self.w.dense_pe
+        ln = lambda x, gb: ctx.layernorm(x, gb[0], gb[1], 1e-5)
+        queries = tokens
+        for i, lw in enumerate(w["layers"]):
+            if i == 0:
+                queries = self._dec_attn(lw["self_attn"], queries, queries, queries, heads)
+            else:
+                q = ctx.add_bcast(queries, tokens)
+                queries = self._dec_attn(lw["self_attn"], q, q, queries, heads, residual=queries)
+            queries = ln(queries, lw["n"][0])
+            q = ctx.add_bcast(queries, tokens)
+            k = ctx.add_bcast(keys, key_pe)
+            queries = ln(self._dec_attn(lw["t2i"], q, k, keys, heads, residual=queries), lw["n"][1])
+            m = ctx.gemm(queries.view(-1, C), lw["w1"], bias=lw["b1"], act=ACT_RELU)
+            queries = ln(ctx.gemm(m, lw["w2"], bias=lw["b2"], residual=queries.view(-1, C)).view(nv, ntok, C), lw["n"][2])
+            q = ctx.add_bcast(queries, tokens)
+            keys = ln(self._dec_attn(lw["i2t"], k, q, queries, heads, residual=keys), lw["n"][3])
+        q = ctx.add_bcast(queries, tokens)
+        k = ctx.add_bcast(keys, key_pe)
+        hs = ln(self._dec_attn(w["final"], q, k, keys, heads, residual=queries), (w["nfg"], w["nfb"]))
+        x = hs[:, 1].contiguous()  # mask token 0 (row 0 is the IoU token)
+        x = ctx.gemm(x, w["hyper"][0][0], bias=w["hyper"][0][1], act=ACT_RELU)
+        x = ctx.gemm(x, w["hyper"][1][0], bias=w["hyper"][1][1], act=ACT_RELU)
+        hyper = ctx.gemm(x, w["hyper"][2][0], bias=w["hyper"][2][1])
+        up1 = ctx.gemm(keys.view(nv * S, C), w["up0_w"], bias=w["up0_b"], force_swap=-1)  # [nv*S, 4*64]
+        co = w["up0_w"].shape[0] // 4
+        up1 = ctx.layernorm(up1.view(nv * S * 4, co), w["up_ln"][0], w["up_ln"][1], 1e-6, act=ACT_GELU)
+        return ctx.upscale_hyper_dot(up1, w["up3_w"], w["up3_b"], hyper, nv, cfg.sam_grid)
+
+    def postprocess(self, low, input_size, original_size):
+        """Sam.postprocess_masks (sam.py:137-172): [nv,256,256] fp32 -> [nv,H,W] fp32 logits."""
+        S = self.cfg.sam_img_size
+        full = self.ctx.bilinear(low, S, S)
+        ih, iw = int(input_size[0]), int(input_size[1])
+        oh, ow = int(original_size[0]), int(original_size[1])
+        if (ih, iw) == (S, S) and (oh, ow) == (S, S):
+            return full  # the second interpolate is an exact identity
+        return self.ctx.bilinear(full, oh, ow, crop_h=ih, crop_w=iw)
+
+
+class _Predictor:
+    """Callable attribute mirroring HumanContact3DPredictor / ObjectMeshContact3DPredictor / ObjectPCAfford3DPredictor
+    (model/components.py:195-489): list of [V,H,W] fp32 maps -> [B,n] fp32."""
+
+    def __init__(self, model, mode):
+        self.model, self.mode = model, mode
+        self.map = None
+
+    def set_maps(self, p2v, bary, n_verts):
+        from .ops import LiftMap
+
+        self.map = LiftMap(self.model.ctx, p2v, bary, n_verts) if not self.model._emulated else self.model.ctx.LiftMap(p2v, bary, n_verts)
+        return self
+
+    def __call__(self, seg_maps, ds_names=None, mask_paths_list=None, lift2d_dict_path=None):
+        m = self.map
+        if lift2d_dict_path is not None:
+            m = self.model._lift_map_from_pickle(lift2d_dict_path)
+        if m is None:
+            raise RuntimeError("lifting maps not loaded: call set_maps(p2v, bary, n_verts) or pass lift2d_dict_path")
+        masks = torch.stack([s.float() for s in seg_maps], 0).contiguous()
+        return m(masks, self.mode, 0.3)
+
+
+class _GetModel:
+    """Object returned by get_model(): the harness calls these to place CLIP / SAM modules (run_demo.py:143-168,
+    evaluate.py:548-563).  Weights are already bound here, so they are no-ops that keep the call sites working."""
+
+    def __init__(self, outer):
+        self._outer = outer
+        self.config = outer.config
+
+    def initialize_vision_modules(self, cfg=None):
+        return None
+
+    def initialize_ivlm_modules(self, cfg=None):
+        return None
+
+    def initialize_separate_decoders(self):
+        return None
+
+    def get_vision_tower(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+
+class InteractVLMForCausalLM:
+    """Drop-in for model/InteractVLM.py:139 (inference surface only).  bf16, CUDA (sm_100a) only."""
+
+    def __init__(self, config: IVLMConfig, state_dict: dict, device=0, ctx=None, use_cuda_graph=True):
+        self.config = config
+        self._emulated = ctx is not None and getattr(ctx, "emulated", False)
+        if ctx is None:
+            from .ops import Context
+
+            ctx = Context(device)
+        self.ctx = ctx
+        self.device = ctx.device
+        self.w = _Weights(state_dict, config, self.device)
+        self.eng = _Engine(ctx, config, self.w)
+        self.use_cuda_graph = use_cuda_graph and self.device.type == "cuda"
+        self._graphs = {}
+        self._lift_cache = {}
+        self.seg_token_idx = config.seg_token_idx
+        self.img_emb_len = config.img_emb_len
+        self.multiview_channels = config.multiview_channels
+        self.hC_loss_weight, self.oC_loss_weight = config.hC_loss_weight, config.oC_loss_weight
+        self.hC_sam_view_type, self.oC_sam_view_type = config.hC_sam_view_type, config.oC_sam_view_type
+        self.human_3d_contact_predictor = _Predictor(self, LIFT_HUMAN)
+        self.object_3d_contact_predictor = _Predictor(self, LIFT_OBJECT_MESH)
+        self.object_3d_afford_predictor = _Predictor(self, LIFT_POINTS)
+        self.sam_chunk = 8
+        self.timings = None
+
+    # ---- construction -------------------------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, path, low_cpu_mem_usage=True, vision_tower=None, torch_dtype=torch.bfloat16,
+                        train_from_LISA=False, train_from_LLAVA=False, device=0, clip_state_dict=None, **kwargs):
+        """Reads an HF checkpoint directory: config.json (+ the reference's custom attributes) and *.safetensors /
+        pytorch_model*.bin shards with the key groups of SURVEY.md 8b.  CLIP weights are not part of the released
+        checkpoints (merge_lora_weights_and_save_hf_model.py:156-160): pass `clip_state_dict` or a `vision_tower`
+        directory holding them."""
+        if torch_dtype not in (torch.bfloat16, None):
+            raise ValueError("interactvlm_b200 runs in bfloat16 only (evaluate.py:532 of the reference enforces bf16 too)")
+        path = Path(path)
+        cfg = config_from_hf(json.loads((path / "config.json").read_text()))
+        for k in ("oC_sam_view_type", "oC_question_type", "hC_question_type"):
+            if kwargs.get(k) is not None:
+                setattr(cfg, k, kwargs[k])
+        sd = load_checkpoint_dir(path)
+        if clip_state_dict is not None:
+            sd.update(clip_state_dict)
+        elif vision_tower is not None and Path(str(vision_tower)).is_dir():
+            for k, v in load_checkpoint_dir(Path(vision_tower)).items():
+                sd[k if k.startswith("model.vision_tower.") else "model.vision_tower.vision_tower." + k] = v
+        return cls(cfg, sd, device=device)
+
+    def get_model(self):
+        return _GetModel(self)
+
+    def bfloat16(self):
+        return self
+
+    def float(self):
+        raise RuntimeError("interactvlm_b200 is bf16-only")
+
+    def cuda(self, *a, **k):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    @property
+    def module(self):  # DeepSpeed-engine style access (evaluate.py:95)
+        return self
+
+    def resize_token_embeddings(self, n):
+        if n != self.w.embed.shape[0]:
+            raise ValueError(f"checkpoint has {self.w.embed.shape[0]} token embeddings, harness asked for {n}")
+        return None
+
+    def set_human_lift_maps(self, p2v, bary, n_verts=6890):
+        self.human_3d_contact_predictor.set_maps(p2v, bary, n_verts)
+
+    def load_human_lift_maps(self, data_root="./data"):
+        """The two npz files HumanContact3DPredictor.__init__ reads (components.py:203-218)."""
+        from .synthetic import HUMAN_VIEWS
+
+        d = Path(data_root) / "hcontact_vitruvian"
+        p2v = np.load(d / "pixel_to_vertex_map_1024.npz")
+        bary = np.load(d / "bary_coords_map_1024.npz")
+        self.set_human_lift_maps(np.stack([p2v[v] for v in HUMAN_VIEWS]), np.stack([bary[v] for v in HUMAN_VIEWS]))
+
+    def _lift_map_from_pickle(self, path):
+        """lift2d_dict.pkl written by generate_sam_inp_objs (utils/demo_utils.py:171-257)."""
+        if path not in self._lift_cache:
+            import joblib
+
+            from .ops import LiftMap
+
+            d = joblib.load(path)
+            p2v = np.stack([np.asarray(a) for a in d["pixel_to_vertices_map"]])
+            bary = np.stack([np.asarray(a) for a in d["bary_coords_map"]])
+            mk = self.ctx.LiftMap if self._emulated else (lambda *a: LiftMap(self.ctx, *a))
+            self._lift_cache[path] = mk(p2v, bary, int(d["num_vertices"]))
+        return self._lift_cache[path]
+
+    # ---- stages -------------------------------------------------------------------------------------------------
+    def get_visual_embs(self, images):
+        """[B,V,3,1024,1024] -> [B*V, 4096, 256] token-major (InteractVLM.py:251-261)."""
+        B, V = images.shape[:2]
+        flat = images.reshape(B * V, *images.shape[2:])
+        outs = [self.eng.sam_encode(self._bf16(flat[i:i + self.sam_chunk])) for i in range(0, B * V, self.sam_chunk)]
+        return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+
+    def _bf16(self, t):
+        t = t.to(self.device)
+        return t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
+
+    def _llm_state(self, B, max_len):
+        """KV pages, decode buffers and the captured decode graph, kept across calls per (batch, page count)."""
+        key = (B, (max_len + PAGE - 1) // PAGE)
+        if key not in self._graphs:
+            st = self.eng.llm_alloc(B, key[1] * PAGE)
+            self.eng.llm_decode_buffers(st)
+            self._graphs = {key: st}  # one resident configuration: a new shape releases the previous pages
+        return self._graphs[key]
+
+    def _decode_graph(self, st):
+        if not self.use_cuda_graph:
+            return None
+        for _ in range(2):  # warm-up outside capture: lazy function attributes, allocator pools
+            self.eng.llm_decode_step(st)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.eng.llm_decode_step(st)
+        return g
+
+    def generate(self, images_clip, input_ids, max_new_tokens=32, scripted=None):
+        """Greedy decoding with a paged KV cache.  Returns (output_ids [B,L'] int64 on host, hidden [B,max_len,D] device
+        buffer holding the normed last-layer state of every position of output_ids[:, :-1]).  `scripted` [B,G] forces
+        the generated tokens (teacher forcing: same arithmetic, known [SEG] position)."""
+        cfg, eng = self.config, self.eng
+        ids = torch.as_tensor(input_ids).cpu().to(torch.int64)
+        B, L = ids.shape
+        if int((ids == IMAGE_TOKEN_INDEX).sum(1).min()) != 1 or int((ids == IMAGE_TOKEN_INDEX).sum(1).max()) != 1:
+            raise ValueError("every prompt must contain exactly one IMAGE_TOKEN_INDEX (-200)")
+        n_img = cfg.clip_tokens - 1
+        S = L - 1 + n_img
+        max_len = S + max_new_tokens
+        if max_len > cfg.max_position_embeddings:
+            raise ValueError(f"sequence {max_len} exceeds max_position_embeddings {cfg.max_position_embeddings}")
+        feats = eng.clip_encode(self._bf16(images_clip))
+        embeds = self.ctx.embed_splice(self.w.embed, ids.to(torch.int32).to(self.device).contiguous(), feats.contiguous())
+        st = self._llm_state(B, max_len)
+        nxt = eng.llm_prefill(st, embeds)
+        graph = st.get("graph")
+        out = [ids]
+        done = torch.zeros(B, dtype=torch.bool)
+        scripted = None if scripted is None else torch.as_tensor(scripted).cpu().to(torch.int64)
+        for step in range(max_new_tokens):
+            tok = nxt.cpu().to(torch.int64) if scripted is None else scripted[:, step]
+            tok = torch.where(done, torch.full_like(tok, cfg.pad_token_id), tok)
+            out.append(tok[:, None])
+            done |= tok == cfg.eos_token_id
+            if bool(done.all()) or step == max_new_tokens - 1:
+                break
+            # feed `tok` at position S+step
+            p = S + step
+            st["tok"].copy_(tok.to(torch.int32), non_blocking=False)
+            st["pos"].fill_(p)
+            st["slot"].copy_(st["slot_base"] + p)
+            st["seq_lens"].fill_(p + 1)
+            if self.use_cuda_graph and graph is None:
+                graph = st["graph"] = self._decode_graph(st)
+            if graph is not None:
+                graph.replay()
+            else:
+                eng.llm_decode_step(st)
+            st["hidden"][:, p] = st["hid_step"]
+            nxt = st["next"]
+        return torch.cat(out, 1), st["hidden"]
+
+    # ---- public API ---------------------------------------------------------------------------------------------
+    def evaluate(self, images_clip, images, input_ids, cam_params, resize_list, original_size_list,
+                 lift2d_dict_path=None, contact_type="hcontact", max_new_tokens=32, tokenizer=None, scripted=None):
+        """model/InteractVLM.py:510-638.  Returns {"output_ids", "pred_masks" (list of [V,H,W] fp32 logits),
+        "pred_contact_3d" ([B,6890] / [1,Nv] fp32 or None)}."""
+        cfg = self.config
+        if cfg.token_type != "Gen":
+            raise NotImplementedError("token_type != 'Gen' (AttentionSplitter variants) is outside the hot path")
+        output_ids, hidden = self.generate(images_clip, input_ids, max_new_tokens, scripted)
+        pred_masks = self._masks_from_hidden(hidden, output_ids, images, cam_params, resize_list, original_size_list)
+        pred_contact_3d = None
+        if pred_masks[0].shape[0] > 0:
+            if self.hC_loss_weight > 0 and "hcontact" in contact_type:
+                pred_contact_3d = self.human_3d_contact_predictor(pred_masks)
+            elif (self.oC_loss_weight > 0 and "ocontact" in contact_type) or "oafford" in contact_type:  # sic (:626)
+                pred_contact_3d = self.object_3d_contact_predictor(pred_masks, ds_names=["ocontact"],
+                                                                   lift2d_dict_path=lift2d_dict_path)
+        return {"output_ids": output_ids.to(self.device), "pred_masks": pred_masks, "pred_contact_3d": pred_contact_3d}
+
+    def _masks_from_hidden(self, hidden, output_ids, images, cam_params, resize_list, original_size_list):
+        cfg, eng = self.config, self.eng
+        B = output_ids.shape[0]
+        V = cfg.multiview_channels
+        rows, owners = [], []
+        for b in range(B):
+            js = (output_ids[b] == cfg.seg_token_idx).nonzero().flatten().tolist()
+            r = [j - 1 + cfg.img_emb_len for j in js if j >= 1]
+            if len(r) > 1:
+                raise NotImplementedError("multi-view decoding supports one [SEG] per sample (SURVEY.md section 0.5)")
+            if r:
+                rows.append(b * hidden.shape[1] + r[0])
+                owners.append(b)
+        image_embeddings = self.get_visual_embs(images)  # computed for every sample, like the reference (:578)
+        S, C = image_embeddings.shape[1], image_embeddings.shape[2]
+        pred_masks = [None] * B
+        if owners:
+            hrows = self.ctx.gather_rows(hidden.view(-1, hidden.shape[-1]), _i32(rows, self.device))
+            cam = self._bf16(torch.as_tensor(cam_params))[owners].contiguous()
+            prompt, _ = eng.seg_prompt(hrows, cam)
+            emb = image_embeddings.view(B, V, S, C)[owners].reshape(len(owners) * V, S, C)
+            low = eng.mask_decode(emb, prompt).view(len(owners), V, 4 * cfg.sam_grid, 4 * cfg.sam_grid)
+            for k, b in enumerate(owners):
+                pred_masks[b] = eng.postprocess(low[k].contiguous(), resize_list[b], original_size_list[b])
+        for b in range(B):
+            if pred_masks[b] is None:
+                oh, ow = int(original_size_list[b][0]), int(original_size_list[b][1])
+                pred_masks[b] = torch.zeros((0, oh, ow), device=self.device, dtype=torch.float32)
+        return pred_masks
+
+    def forward(self, **kw):
+        return self.model_forward(**kw)
+
+    __call__ = forward
+
+    def model_forward(self, images, images_clip, input_ids, labels=None, attention_masks=None, offset=None,
+                      masks_list=None, label_list=None, gt_contact_3d_list=None, cam_params=None, resize_list=None,
+                      ds_name_list=None, mask_paths_list=None, inference=True, **kwargs):
+        """Teacher-forced inference (model/InteractVLM.py:296-474, inference=True branch): one causal pass over
+        prompt+answer; [SEG] rows taken from input_ids."""
+        if not inference:
+            raise NotImplementedError("training (inference=False) is outside the hot path")
+        cfg, eng = self.config, self.eng
+        ids = torch.as_tensor(input_ids).cpu().to(torch.int64)
+        B, L = ids.shape
+        clip = self._bf16(images_clip)
+        if clip.shape[0] == 1 and B > 1:
+            clip = clip.expand(B, -1, -1, -1)
+        feats = eng.clip_encode(clip.contiguous())
+        embeds = self.ctx.embed_splice(self.w.embed, ids.to(torch.int32).to(self.device).contiguous(), feats.contiguous())
+        st = eng.llm_alloc(B, embeds.shape[1])
+        eng.llm_prefill(st, embeds)
+        sizes = [tuple(l.shape[-2:]) for l in label_list] if label_list is not None else list(resize_list)
+        pred_masks = self._masks_from_hidden(st["hidden"], ids, images, cam_params, resize_list, sizes)
+        ds = ds_name_list or ["hcontact"] * B
+        for i, name in enumerate(ds):  # HM view types feed sigmoid-ed maps to the affordance lift (:452-456)
+            if "oafford" in name and cfg.oC_sam_view_type and "HM" in cfg.oC_sam_view_type:
+                pred_masks[i] = torch.sigmoid(pred_masks[i])
+        result = {"gt_masks": [m[:, 0] for m in masks_list] if masks_list is not None else None, "pred_masks": pred_masks}
+        if self.hC_loss_weight > 0:
+            result["pred_human_3d_contact"] = self.human_3d_contact_predictor(pred_masks, ds)
+        if self.oC_loss_weight > 0:
+            result["pred_object_3d_contact"] = self.object_3d_contact_predictor(pred_masks, ds, mask_paths_list)
+            result["pred_object_3d_afford"] = self.object_3d_afford_predictor(pred_masks, ds, mask_paths_list)
+        return result
+
+
+# ------------------------------------------------------------------------------------------------ checkpoint IO
+def config_from_hf(d: dict) -> IVLMConfig:
+    """HF config.json of a released checkpoint (LlavaConfig + the attributes InteractVLM.py:146-199 adds)."""
+    cfg = IVLMConfig.full()
+    for k, v in d.items():
+        if k in cfg.__dataclass_fields__ and v is not None:
+            setattr(cfg, k, tuple(v) if k == "sam_global_attn_indexes" else v)
+    if "rope_parameters" in d and isinstance(d["rope_parameters"], dict):
+        cfg.rope_theta = d["rope_parameters"].get("rope_theta", cfg.rope_theta)
+    if "mm_vision_tower" in d and "vision_tower" not in d:
+        cfg.vision_tower = d["mm_vision_tower"]
+    return cfg
+
+
+def load_checkpoint_dir(path: Path) -> dict:
+    sd = {}
+    files = sorted(path.glob("*.safetensors"))
+    if files:
+        from safetensors.torch import load_file
+
+        for f in files:
+            sd.update(load_file(str(f)))
+        return sd
+    files = sorted(path.glob("pytorch_model*.bin"))
+    if not files:
+        raise FileNotFoundError(f"no *.safetensors or pytorch_model*.bin under {path}")
+    for f in files:
+        sd.update(torch.load(f, map_location="cpu", weights_only=True))
+    return sd
+
+
+def save_pretrained(path, cfg: IVLMConfig, sd: dict):
+    """Writes the HF layout from_pretrained() reads (used by tests and the demo on synthetic weights)."""
+    from safetensors.torch import save_file
+
+    path = Path(path)
+    path.mkdir(parents=True, exist_ok=True)
+    (path / "config.json").write_text(json.dumps(cfg.to_dict(), indent=1))
+    save_file({k: v.detach().cpu().to(torch.bfloat16).contiguous() for k, v in sd.items()}, str(path / "model.safetensors"))

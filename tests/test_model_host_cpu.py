@@ -1,0 +1,107 @@
+"""CPU: host logic of interactvlm_b200/model.py (stage order, weight re-layout, window row maps, KV-cache and [SEG]
+bookkeeping, API surface) with the kernels replaced by tests/emu.py, against the oracle pinned to the reference.
+The numbers here are NOT the product's (the CUDA kernels are checked by the -m gpu tests); the structure is."""
+import numpy as np
+import pytest
+import torch
+
+from interactvlm_b200 import synthetic as S
+from interactvlm_b200.config import IVLMConfig
+from interactvlm_b200.model import InteractVLMForCausalLM, config_from_hf, save_pretrained
+from oracle import model as OM
+from oracle.make_goldens_model import TINY_SEED, tiny_inputs
+
+from emu import EmuContext
+
+SIZE = (1024, 1024)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    cfg = IVLMConfig.tiny()
+    sd = S.make_state_dict(cfg, seed=TINY_SEED["weights"])
+    model = InteractVLMForCausalLM(cfg, sd, ctx=EmuContext())
+    p2v, bary = S.make_mesh_lift_maps(seed=TINY_SEED["maps"])
+    model.set_human_lift_maps(p2v, bary)
+    return cfg, sd, model, (p2v, bary)
+
+
+def test_evaluate_structure_matches_oracle(setup):
+    cfg, sd, model, (p2v, bary) = setup
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 1)
+    out = model.evaluate(clip, sam, ids, cam, [SIZE], [SIZE], contact_type="hcontact", max_new_tokens=ans.shape[1],
+                         scripted=ans)
+    ref = OM.evaluate(sd, cfg, clip, sam, ids, cam, [SIZE], [SIZE], lift_maps=(p2v, bary, S.N_SMPL),
+                      max_new_tokens=ans.shape[1], scripted=ans, dtype=torch.float32)
+    assert torch.equal(out["output_ids"].cpu(), ref["output_ids"])
+    pm, rm = out["pred_masks"][0], ref["pred_masks"][0]
+    assert pm.shape == rm.shape == (4, 1024, 1024) and pm.dtype == torch.float32
+    # bf16 storage between stages: a few percent of the logit scale, far below any structural error (O(scale))
+    assert (pm - rm).abs().max().item() < 0.08 * rm.abs().max().item()
+    c, rc = out["pred_contact_3d"].numpy(), ref["pred_contact_3d"].numpy()
+    assert c.shape == (1, S.N_SMPL)
+    assert np.abs(c - rc).max() < 0.08
+    assert ((c >= 0.5) == (rc >= 0.5)).mean() > 0.97
+
+
+def test_greedy_decode_through_kv_cache_matches_oracle(setup):
+    cfg, sd, model, _ = setup
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 1)
+    w = OM.W(sd)
+    with torch.no_grad():
+        seq, hidden, _ = OM.greedy_generate(w, cfg, clip, ids, 4)
+    out_ids, hid = model.generate(clip, ids, max_new_tokens=4)
+    assert out_ids.tolist() == seq.tolist()
+    n = hidden.shape[1]
+    err = (hid[:, :n].float() - hidden).abs().max().item()
+    assert err < 0.05 * hidden.abs().max().item(), err
+
+
+def test_batch_of_two_and_missing_seg(setup):
+    cfg, sd, model, (p2v, bary) = setup
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
+    ans = ans.clone()
+    ans[1, -3] = 5  # second sample never emits [SEG]
+    with pytest.raises(Exception):
+        # the reference indexes pred_masks[0] and lifts every sample; a sample without [SEG] has an empty mask stack
+        model.evaluate(clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, max_new_tokens=ans.shape[1], scripted=ans)
+    ans[1, -3] = cfg.seg_token_idx
+    out = model.evaluate(clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, max_new_tokens=ans.shape[1], scripted=ans)
+    ref = OM.evaluate(sd, cfg, clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, lift_maps=(p2v, bary, S.N_SMPL),
+                      max_new_tokens=ans.shape[1], scripted=ans)
+    assert out["pred_contact_3d"].shape == (2, S.N_SMPL)
+    assert np.abs(out["pred_contact_3d"].numpy() - ref["pred_contact_3d"].numpy()).max() < 0.08
+
+
+def test_model_forward_teacher_forced(setup):
+    cfg, sd, model, (p2v, bary) = setup
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 1)
+    full = torch.cat([ids, ans], 1)
+    out = model(images=sam, images_clip=clip, input_ids=full, labels=full, attention_masks=torch.ones_like(full),
+                offset=torch.tensor([0, 1]), masks_list=[torch.zeros(4, 1, *SIZE)], label_list=[torch.zeros(SIZE)],
+                gt_contact_3d_list=[None], cam_params=cam, resize_list=[SIZE], ds_name_list=["damon_hcontact"],
+                mask_paths_list=[None], inference=True)
+    ev = model.evaluate(clip, sam, ids, cam, [SIZE], [SIZE], max_new_tokens=ans.shape[1], scripted=ans)
+    # the teacher-forced pass and the generate path see the same hidden state at the [SEG]-1 row
+    assert (out["pred_masks"][0] - ev["pred_masks"][0]).abs().max().item() < 0.05 * ev["pred_masks"][0].abs().max().item()
+    assert out["pred_human_3d_contact"].shape == (1, S.N_SMPL)
+
+
+def test_checkpoint_roundtrip_and_api_surface(tmp_path, setup):
+    cfg, sd, model, _ = setup
+    save_pretrained(tmp_path / "ckpt", cfg, sd)
+    from interactvlm_b200.model import load_checkpoint_dir
+    import json
+    cfg2 = config_from_hf(json.loads((tmp_path / "ckpt" / "config.json").read_text()))
+    assert cfg2.to_dict() == cfg.to_dict()
+    sd2 = load_checkpoint_dir(tmp_path / "ckpt")
+    assert set(sd2) == set(sd) and all(torch.equal(sd2[k].float(), sd[k]) for k in sd)
+    gm = model.get_model()
+    gm.initialize_vision_modules(gm.config)
+    assert gm.get_vision_tower().to(dtype=torch.bfloat16, device="cpu") is not None
+    assert model.bfloat16().cuda().eval() is model and model.module is model
+    model.resize_token_embeddings(cfg.vocab_size)
+    with pytest.raises(ValueError):
+        model.resize_token_embeddings(cfg.vocab_size + 1)
+    with pytest.raises(RuntimeError):
+        model.float()
