@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Throughput of the InteractVLM 3D human-contact hot path (BASELINE.json metric: images/sec, 1024x1024).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One step = model.evaluate() on a batch of B synthetic samples per GPU: one 224^2 CLIP image + V=4 SAM views of
+1024^2 + a 75-token prompt -> greedy decode (scripted 24-token answer through the paged KV cache) -> [SEG] prompt
+-> SAM ViT-H on the 4 views -> two-way mask decoder -> 4x1024^2 logits -> per-vertex SMPL contact [6890].
+Workload = BASELINE.json configs[1]: batch 8, LLaMA-2-13B + CLIP-L/14 + SAM ViT-H, random-init weights.
+`value` times the step with inputs resident in HBM; `e2e` times the same call with pinned-host inputs (H2D inside)
+and the contact vector read back (D2H inside).  N>1: one process per GPU (torchrun), the batch is sharded (8 per
+rank, weak scaling) and the per-sample contact vectors are all-gathered over NCCL once per step.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, no KV cache, as the reference
+runs it) on the host cores, on a bounded sample that is extrapolated layer-wise (the sample is described in the line).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from interactvlm_b200 import synthetic as S  # noqa: E402
+from interactvlm_b200.config import IVLMConfig  # noqa: E402
+
+METRIC = "images/sec (3D hcontact, 1024x1024)"
+SIZE = (1024, 1024)
+N_PRE, N_POST, N_ANS = 40, 30, 24  # prompt 1+40+3+30 = 74 ids (+255 image rows) and a 24-token scripted answer
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of this rank's GPU during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "power_w_max": max(float(r[2]) for r in self.rows),
+                "samples": len(self.rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_batch(cfg, batch, seed):
+    ids, ans = S.make_prompt_ids(cfg, batch, n_pre=N_PRE, n_post=N_POST, n_answer=N_ANS, seed=seed)
+    rng = np.random.default_rng(seed + 6000)
+    V = cfg.multiview_channels
+    # uint8 U[0,255] pixels, normalised like run_demo.py:65-79 / CLIPImageProcessor, stored bf16 (the dtype the
+    # reference hands to evaluate()); generated with torch to keep host RAM and time bounded at batch 8+
+    g = torch.Generator().manual_seed(seed)
+    clip = torch.randint(0, 256, (batch, 3, cfg.clip_image_size, cfg.clip_image_size), generator=g, dtype=torch.uint8)
+    sam = torch.randint(0, 256, (batch, V, 3, cfg.sam_img_size, cfg.sam_img_size), generator=g, dtype=torch.uint8)
+    cm = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(1, 3, 1, 1)
+    cs = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(1, 3, 1, 1)
+    sm = torch.tensor([123.675, 116.28, 103.53]).view(1, 1, 3, 1, 1)
+    ss = torch.tensor([58.395, 57.12, 57.375]).view(1, 1, 3, 1, 1)
+    clip = ((clip.float() / 255.0 - cm) / cs).bfloat16()
+    sam = ((sam.float() - sm) / ss).bfloat16()
+    cam = torch.from_numpy(np.broadcast_to(S.HCONTACT_CAM_PARAMS, (batch, V, 5)).copy()).bfloat16()
+    del rng
+    return torch.from_numpy(ids), torch.from_numpy(ans), clip, sam, cam
+
+
+def algorithmic_flops(cfg, B, L, G):
+    """2*MAC of the KV-cached path per batch, dense contractions + attention."""
+    D, F, nl, V = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.multiview_channels
+    S_ = L - 1 + cfg.clip_tokens - 1
+    lin_tok = 2 * nl * (4 * D * D + 3 * D * F)
+    llm = B * ((S_ + G - 1) * lin_tok + 2 * (1 + G - 1) * D * cfg.vocab_size)
+    llm += B * nl * 4 * D * (S_ * S_ / 2 + sum(S_ + t for t in range(G - 1)))
+    E, T = cfg.sam_embed_dim, cfg.sam_grid ** 2
+    nwin = ((cfg.sam_grid + cfg.sam_window_size - 1) // cfg.sam_window_size) ** 2 * cfg.sam_window_size ** 2
+    n_glob = len(cfg.sam_global_attn_indexes)
+    n_win = cfg.sam_depth - n_glob
+    per_view = 2 * T * 768 * E + cfg.sam_depth * 2 * T * 8 * E * E  # patch embed + MLP
+    per_view += n_glob * (2 * T * 4 * E * E + 4 * T * T * E) + n_win * (2 * nwin * 4 * E * E + 4 * nwin * cfg.sam_window_size ** 2 * E)
+    per_view += 2 * T * E * 256 + 2 * T * 2304 * 256
+    C, CF, CT = cfg.clip_hidden_size, cfg.clip_intermediate_size, cfg.clip_tokens
+    clip = cfg.clip_layers_used * (2 * CT * (4 * C * C + 2 * C * CF) + 4 * CT * CT * C) + 2 * 256 * 588 * C + 2 * 256 * C * D
+    dec = 14.6e9 / 4  # per view
+    return dict(llm=llm, sam=B * V * per_view, clip=B * clip, decoder=B * V * dec, total=llm + B * V * (per_view + dec) + B * clip)
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+_REF_SD = {}
+
+
+def cpu_reference(cfg, threads=None, dtypes=(torch.bfloat16, torch.float32)):
+    """Times the oracle's restatement of the reference algorithm on the host cores, layer-wise, at full widths:
+    one SAM window block, one SAM global block, patch-embed + neck, one CLIP layer, one LLaMA layer at the prompt
+    length, lm_head, the mask decoder and the lift; then sums them the way the reference executes them per image
+    (no KV cache: every generated token re-runs CLIP and all 40 layers over the whole sequence).
+    Returns (images_per_sec, description, cores, dtype used)."""
+    from oracle import lift as OL
+    from oracle import model as OM
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    one = IVLMConfig.from_dict(cfg.to_dict())
+    one.num_hidden_layers, one.clip_num_hidden_layers, one.sam_depth, one.sam_global_attn_indexes = 1, 2, 2, (1,)
+    one.vocab_size = cfg.vocab_size
+    if "sd" not in _REF_SD:
+        _REF_SD["sd"] = S.make_state_dict(one, seed=1, device="cpu", gain=0.5)
+    sd = _REF_SD["sd"]
+    best = {}
+    for dtype in dtypes:  # the reference mandates bf16 (evaluate.py:532); keep the faster of bf16 / fp32 on this CPU
+        w = OM.W(sd, dtype)
+        t = {}
+
+        def clock(name, fn, reps=1):
+            fn()  # warm (allocator, oneDNN primitive cache)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            t[name] = (time.perf_counter() - t0) / reps
+
+        with torch.no_grad():
+            img = torch.randn(1, 3, 1024, 1024).to(dtype)
+            full = lambda: OM.sam_image_encoder(w, one, img)
+            clock("sam_2blocks_embed_neck", full)
+            zero = IVLMConfig.from_dict(one.to_dict())
+            zero.sam_depth, zero.sam_global_attn_indexes = 1, ()
+            clock("sam_window_block_embed_neck", lambda: OM.sam_image_encoder(w, zero, img))
+            zero0 = IVLMConfig.from_dict(one.to_dict())
+            zero0.sam_depth = 0
+            clock("sam_embed_neck", lambda: OM.sam_image_encoder(w, zero0, img))
+            S_ = N_PRE + N_POST + 4 - 1 + 256
+            emb = torch.randn(1, S_, cfg.hidden_size).to(dtype)
+            clock("llama_layer_prefill", lambda: OM.llama_forward(w, one, emb))
+            clock("lm_head", lambda: OM.lm_logits(w, emb[:, -1]))
+            ci = torch.randn(1, 3, 224, 224).to(dtype)
+            clock("clip_1layer", lambda: OM.clip_tower(w, one, ci))
+            c0 = IVLMConfig.from_dict(one.to_dict())
+            c0.clip_num_hidden_layers, c0.mm_vision_select_layer = 1, -2
+            clock("clip_0layer", lambda: OM.clip_tower(w, c0, ci))
+            se = torch.randn(4, 256, 64, 64).to(dtype)
+            pr = torch.randn(1, 4, 256).to(dtype)
+            clock("mask_decoder_postprocess", lambda: OM.postprocess_masks(one, OM.mask_decoder(w, one, se, pr), SIZE, SIZE))
+        win = t["sam_window_block_embed_neck"] - t["sam_embed_neck"]
+        glob = t["sam_2blocks_embed_neck"] - t["sam_window_block_embed_neck"]
+        n_glob = len(cfg.sam_global_attn_indexes)
+        sam = cfg.multiview_channels * (t["sam_embed_neck"] + (cfg.sam_depth - n_glob) * max(win, 0) + n_glob * max(glob, 0))
+        clip_layer = max(t["clip_1layer"] - t["clip_0layer"], 0)
+        clip = t["clip_0layer"] + cfg.clip_layers_used * clip_layer
+        # no KV cache: G forwards over S_, S_+1, ... tokens; cost ~ linear in tokens at these lengths
+        lm = sum((S_ + g) / S_ for g in range(N_ANS)) * cfg.num_hidden_layers * t["llama_layer_prefill"] + N_ANS * (t["lm_head"] + clip)
+        total = sam + lm + t["mask_decoder_postprocess"]
+        best[dtype] = (total, dict(t), dict(sam=sam, lm=lm, dec=t["mask_decoder_postprocess"]))
+    p2v, bary = S.make_mesh_lift_maps(seed=0)
+    logits = S.make_mask_logits(1, seed=1)
+    t0 = time.perf_counter()
+    OL.lift_human(logits, p2v, bary, S.N_SMPL)
+    t_lift = time.perf_counter() - t0
+    key = min(best, key=lambda k: best[k][0])
+    total, parts, agg = best[key]
+    total += t_lift
+    desc = (f"oracle (reference algorithm, no KV cache) on {threads} host threads, {key}: timed 1 SAM window block, 1 global block, "
+            f"patch-embed+neck at ViT-H width on one 1024^2 view, 1 LLaMA-13B layer at {S_} tokens, lm_head, CLIP-L layer, "
+            f"mask decoder + postprocess (4 views), lift; extrapolated to 4 views x 32 blocks, {N_ANS} no-cache decode passes x 40 layers "
+            f"(+CLIP each pass): sam {agg['sam']:.1f}s lm {agg['lm']:.1f}s dec {agg['dec']:.2f}s lift {t_lift:.2f}s per image")
+    return 1.0 / total, desc, threads, key
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="samples per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="full", choices=["full", "tiny"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = IVLMConfig.full() if args.config == "full" else IVLMConfig.tiny()
+    workload = (f"configs[1]: batch={args.batch}/GPU synthetic RGB, 3D human-contact (DAMON-shape), "
+                f"{'LLaMA-2-13B + CLIP-L/14 + SAM ViT-H' if args.config == 'full' else 'TINY debug config'}, "
+                f"prompt {N_PRE + N_POST + 4} ids (+255 image rows), {N_ANS} scripted answer tokens, V=4 views 1024^2")
+    config = {"workload": workload, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+              "views": cfg.multiview_channels, "parallelism": f"dp{world} (batch-sharded, one NCCL all-gather of [B,6890])",
+              "l2": "inputs (201 MB/step) and weights (28 GB) exceed the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        t_all = []
+        desc, cores, dtypes = "", 0, (torch.bfloat16, torch.float32)
+        for i in range(args.warmup + args.steps):
+            v, desc, cores, fastest = cpu_reference(cfg, dtypes=dtypes)
+            dtypes = (fastest,)  # the first pass picks the faster arithmetic type; later passes repeat it
+            if i >= args.warmup:
+                t_all.append(1.0 / v)
+        sec = float(np.mean(t_all)) if t_all else 1.0 / v
+        val = 1.0 / sec
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec * 1e3 * args.batch, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc},
+                "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from interactvlm_b200 import build as _b
+
+    if _b.needs_build():
+        _b.build()
+    from interactvlm_b200.model import InteractVLMForCausalLM
+    from interactvlm_b200.parallel import gather_contacts
+
+    dev = torch.device("cuda", local_rank)
+    sd = S.make_state_dict(cfg, seed=0, device=dev, gain=0.5)
+    model = InteractVLMForCausalLM(cfg, sd, device=local_rank)
+    del sd
+    p2v, bary = S.make_mesh_lift_maps(seed=0)
+    model.set_human_lift_maps(p2v, bary)
+    del p2v, bary
+    ids, ans, clip_h, sam_h, cam_h = make_batch(cfg, args.batch, seed=1234 + rank)
+    clip_h, sam_h, cam_h = clip_h.pin_memory(), sam_h.pin_memory(), cam_h.pin_memory()
+    clip_d, sam_d, cam_d = clip_h.to(dev), sam_h.to(dev), cam_h.to(dev)
+    sizes = [SIZE] * args.batch
+    host_out = torch.empty((args.batch * world, S.N_SMPL), dtype=torch.float32).pin_memory()
+
+    def step(resident: bool):
+        if resident:
+            c, s, k = clip_d, sam_d, cam_d
+        else:
+            c, s, k = clip_h.to(dev, non_blocking=True), sam_h.to(dev, non_blocking=True), cam_h.to(dev, non_blocking=True)
+        out = model.evaluate(c, s, ids, k, sizes, sizes, contact_type="hcontact", max_new_tokens=N_ANS, scripted=ans)
+        allc = gather_contacts(out["pred_contact_3d"], dist)
+        if not resident:
+            host_out.copy_(allc, non_blocking=True)
+        return allc
+
+    def timed(resident, steps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = model.ctx.launch_count()
+        e0.record()
+        for _ in range(steps):
+            step(resident)
+        e1.record()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, model.ctx.launch_count() - n0
+
+    for _ in range(args.warmup):
+        last = step(True)
+    step(False)
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as cs:
+        ms, launches = timed(True, args.steps)
+        ms_e2e, _ = timed(False, args.steps)
+    clocks = cs.summary()
+    # launches inside CUDA-graph replays are not seen by the handle's counter: add them explicitly
+    graph_launches = 0
+    st = next(iter(model._graphs.values()), None)
+    if st is not None and st.get("graph") is not None:
+        graph_launches = st.get("graph_launches", 0) * (N_ANS - 1) * args.steps
+    images = args.batch * world * args.steps
+    value = images / (ms / 1e3)
+    e2e = images / (ms_e2e / 1e3)
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(clip_h.numel() * 2 + sam_h.numel() * 2 + cam_h.numel() * 2) * world,
+                    "d2h_bytes_per_step": int(host_out.numel() * 4)},
+            "gpu_launches": int(launches + graph_launches), "sam_views_per_s": value * cfg.multiview_channels}
+
+    if rank == 0:
+        pk = peaks()
+        fl = algorithmic_flops(cfg, args.batch, ids.shape[1], N_ANS)
+        line["algorithmic_tflop_per_step_per_gpu"] = fl["total"] / 1e12
+        line["path_tensor_frac"] = (fl["total"] / (ms / args.steps / 1e3) / 1e12) / pk["tf_sustained"]
+        if not args.no_profile:
+            # roofline of the dominant kernel (tcgen05 GEMM), timed per launch with CUDA events on the launching stream
+            model.use_cuda_graph = False
+            model._graphs = {}
+            model.ctx.enable_profile()
+            step(True)
+            rep = model.ctx.profile_report()
+            model.ctx.disable_profile()
+            model.use_cuda_graph = True
+            tot = sum(r["ms"] for r in rep.values())
+            g = rep["gemm"]
+            ach = g["work"] / (g["ms"] / 1e3) / 1e12
+            line["roofline"] = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"],
+                                "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None,
+                                "peak_source": pk["source"] + " sustained cuBLAS bf16 (kernel timed inside a long step)",
+                                "launches_per_step": g["launches"], "share_of_kernel_time": g["ms"] / tot}
+            line["kernel_time_shares"] = {k: round(r["ms"] / tot, 4) for k, r in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
+            if "attention" in rep:
+                a = rep["attention"]
+                line["attention_tflops"] = a["work"] / (a["ms"] / 1e3) / 1e12
+        if not args.no_cpu_baseline and world == 1:
+            v, desc, cores, _ = cpu_reference(cfg)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -573,7 +573,9 @@ class InteractVLMForCausalLM:
         if not self.use_cuda_graph:
             return None
         for _ in range(2):  # warm-up outside capture: lazy function attributes, allocator pools
+            n0 = self.ctx.launch_count()
             self.eng.llm_decode_step(st)
+            st["graph_launches"] = self.ctx.launch_count() - n0  # kernels per replay (the handle cannot see replays)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

@@ -57,6 +57,51 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.ivlm_launch_count(self.h))
 
+    # ------------------------------------------------------------------ per-kernel timing (bench.py roofline pass)
+    _PROFILED = ("gemm", "attention", "layernorm", "rmsnorm", "add_bcast", "silu_mul", "im2col_patch", "im2col_3x3",
+                 "sam_relpos", "attn_small", "embed_splice", "embed_gather", "gather_rows", "rope_kv_store",
+                 "decode_attention", "argmax", "cam_gate", "upscale_hyper_dot", "bilinear", "finalize")
+
+    def enable_profile(self):
+        """Bracket every launch with CUDA events on the launching stream (no synchronisation until profile_report()).
+        Adds a few microseconds of host time per launch, so bench.py uses it in a separate pass from the headline timing."""
+        self._prof = []
+        for name in self._PROFILED:
+            fn = getattr(type(self), name)
+
+            def wrapped(*a, _fn=fn, _name=name, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = _fn(self, *a, **k)
+                e1.record()
+                work = 0.0
+                if _name == "gemm":
+                    work = 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0]
+                elif _name == "attention":
+                    B, Sq, H, D = a[0].shape
+                    work = 4.0 * B * H * Sq * a[1].shape[1] * D * (0.5 if k.get("causal") else 1.0)
+                self._prof.append((_name, e0, e1, work))
+                return r
+
+            setattr(self, name, wrapped)
+
+    def disable_profile(self):
+        for name in self._PROFILED:
+            if name in self.__dict__:
+                delattr(self, name)
+
+    def profile_report(self) -> dict:
+        """{kernel family: {"launches", "ms", "work" (FLOPs where defined)}} since enable_profile()."""
+        torch.cuda.synchronize(self.device)
+        rep = {}
+        for name, e0, e1, work in self._prof:
+            r = rep.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+            r["launches"] += 1
+            r["ms"] += e0.elapsed_time(e1)
+            r["work"] += work
+        self._prof = []
+        return rep
+
     # ------------------------------------------------------------------ dense
     def gemm(self, a, w, bias=None, act=ACT_NONE, residual=None, out=None, out_dtype=torch.bfloat16, row_map=None,
              out_rows=None, k_splits=1, force_swap=0, no_round=False, res_row_mod=0):

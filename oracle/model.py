@@ -41,14 +41,16 @@ IMAGE_TOKEN_INDEX = -200
 class W:
     """State-dict view with a dtype cast (the reference calls model.bfloat16(); fp32 buffers stay fp32)."""
 
-    def __init__(self, sd, dtype=torch.float32):
-        self.sd, self.dtype = sd, dtype
+    def __init__(self, sd, dtype=torch.float32, device="cpu"):
+        # device="cpu" is the oracle proper; tests may pass a CUDA device to use the same restatement (stock torch
+        # fp32 ops) as the checker at full model sizes, where the CPU would take minutes per stage.
+        self.sd, self.dtype, self.device = sd, dtype, torch.device(device)
         self._cache = {}
 
     def __call__(self, name, prefix=""):
         k = prefix + name
         if k not in self._cache:
-            self._cache[k] = self.sd[k].detach().to("cpu").to(self.dtype)
+            self._cache[k] = self.sd[k].detach().to(self.device).to(self.dtype)
         return self._cache[k]
 
     def has(self, name):
@@ -64,7 +66,7 @@ def clip_tower(w: W, cfg, images):
     """images [B,3,224,224] -> [B,256,C]: hidden_states[mm_vision_select_layer] without the CLS row."""
     p = CLIP_PREFIX
     B = images.shape[0]
-    x = images.to(w.dtype)
+    x = images.to(w.device, w.dtype)
     pe = F.conv2d(x, w("embeddings.patch_embedding.weight", p), stride=cfg.clip_patch_size)
     pe = pe.flatten(2).transpose(1, 2)
     cls = w("embeddings.class_embedding", p).expand(B, 1, -1)
@@ -130,8 +132,8 @@ def llama_forward(w: W, cfg, embeds):
     """embeds [B,S,D] -> last hidden state after the final RMSNorm [B,S,D] (causal, no padding)."""
     B, S, D = embeds.shape
     nh, hd = cfg.num_attention_heads, cfg.head_dim
-    cos, sin = _rope_tables(cfg, S, embeds.dtype)
-    mask = torch.full((S, S), torch.finfo(embeds.dtype).min, dtype=embeds.dtype).triu(1)
+    cos, sin = (t.to(embeds.device) for t in _rope_tables(cfg, S, embeds.dtype))
+    mask = torch.full((S, S), torch.finfo(embeds.dtype).min, dtype=embeds.dtype, device=embeds.device).triu(1)
     h = embeds
     for i in range(cfg.num_hidden_layers):
         p = f"model.layers.{i}."
@@ -182,7 +184,7 @@ def cam_gate(w: W, cfg, pred_emb, cam_params):
     assert cfg.cam_encoder_type == "vi_v1"
     encs = []
     for v in range(V):
-        c = cam_params[[v]].to(w.dtype)
+        c = cam_params[[v]].to(w.device, w.dtype)
         y = F.relu(F.linear(c, w("cam_pose_encoder.spatial_encoder.0.weight"), w("cam_pose_encoder.spatial_encoder.0.bias")))
         y = F.relu(F.linear(y, w("cam_pose_encoder.spatial_encoder.2.weight"), w("cam_pose_encoder.spatial_encoder.2.bias")))
         y = torch.sigmoid(F.linear(y, w(f"cam_pose_encoder.view_transforms.{v}.weight"),
@@ -194,7 +196,7 @@ def cam_gate(w: W, cfg, pred_emb, cam_params):
 # ---------------------------------------------------------------------------------------------- SAM encoder
 def _rel_pos(size, rel_pos):
     idx = torch.arange(size)[:, None] - torch.arange(size)[None, :] + (size - 1)
-    return rel_pos[idx]  # [q, k, hd]; table length is always 2*size-1 on this path (no interpolation)
+    return rel_pos[idx.to(rel_pos.device)]  # [q, k, hd]; table length is always 2*size-1 on this path (no interpolation)
 
 
 def _sam_attention(w: W, p, x, nh):
@@ -223,7 +225,7 @@ def _ln2d(x, g, b, eps=1e-6):
 def sam_image_encoder(w: W, cfg, images):
     """images [N,3,1024,1024] -> [N,256,64,64]."""
     e = SAM_PREFIX + "image_encoder."
-    x = F.conv2d(images.to(w.dtype), w("patch_embed.proj.weight", e), w("patch_embed.proj.bias", e),
+    x = F.conv2d(images.to(w.device, w.dtype), w("patch_embed.proj.weight", e), w("patch_embed.proj.bias", e),
                  stride=cfg.sam_patch_size).permute(0, 2, 3, 1)
     x = x + w("pos_embed", e)
     ws = cfg.sam_window_size
@@ -260,7 +262,7 @@ def dense_pe(w: W, cfg):
     model.bfloat16() casts too, so the whole encoding runs in the model dtype (prompt_encoder.py:203-229)."""
     g = cfg.sam_grid
     G = w(SAM_PREFIX + "prompt_encoder.pe_layer.positional_encoding_gaussian_matrix")
-    grid = torch.ones((g, g), dtype=G.dtype)
+    grid = torch.ones((g, g), dtype=G.dtype, device=G.device)
     y = (grid.cumsum(0) - 0.5) / g
     x = (grid.cumsum(1) - 0.5) / g
     c = 2 * torch.stack([x, y], -1) - 1
