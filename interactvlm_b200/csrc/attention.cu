@@ -256,44 +256,89 @@ __global__ void sam_relpos_kernel(const bf16* __restrict__ qkv, const bf16* __re
 }
 
 // ------------------------------------------------------------------------------------------------ paged decode
-// CTA per (b, head). HF LlamaAttention eager numerics (transformers 4.31): scores = bf16(bf16(q.k)/sqrt(hd)),
-// softmax in fp32 cast to bf16, bf16 P.V.
+// CTA per (b, head), 8 warps. HF LlamaAttention eager numerics (transformers 4.31): scores = bf16(bf16(q.k)/sqrt(hd)),
+// softmax in fp32 cast to bf16, bf16 P.V.  HBM-bound: every K/V row of the head (HD*2 bytes, contiguous) is read
+// once by one warp with 8-byte (HD=128) loads; keys are dealt to warps in groups of 4 so that four independent row
+// loads are in flight per warp before the first shuffle reduction.
+constexpr int DEC_WARPS = 8;
 template <int HD>
-__global__ void __launch_bounds__(128) decode_attn_paged_kernel(const bf16* __restrict__ q,
-                                                                const bf16* __restrict__ k_cache,
-                                                                const bf16* __restrict__ v_cache,
-                                                                const int* __restrict__ block_table,
-                                                                const int* __restrict__ seq_lens, bf16* __restrict__ out,
-                                                                int H, int page, int max_pages, float inv_scale) {
-    extern __shared__ float sc[];  // [seq_len]
-    __shared__ float red[4];
+__global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const bf16* __restrict__ q,
+                                                                          const bf16* __restrict__ k_cache,
+                                                                          const bf16* __restrict__ v_cache,
+                                                                          const int* __restrict__ block_table,
+                                                                          const int* __restrict__ seq_lens,
+                                                                          bf16* __restrict__ out, int H, int page,
+                                                                          int max_pages, float inv_scale) {
+    extern __shared__ float sc[];  // [seq_len] scores, then probabilities
+    __shared__ float red[DEC_WARPS];
+    __shared__ float part[DEC_WARPS][HD];
     const int h = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int len = seq_lens[b];
     const int* bt = block_table + (long long)b * max_pages;
-    constexpr int EPL = HD / 32;  // elements per lane
+    constexpr int EPL = HD / 32;  // elements per lane (4 -> 8-byte loads, 2 -> 4-byte loads)
     float qr[EPL];
-    const bf16* qp = q + ((long long)b * H + h) * HD + lane * EPL;
+    {
+        const bf16* qp = q + ((long long)b * H + h) * HD + lane * EPL;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) qr[e] = __bfloat162float(qp[e]);
-    float lmax = -INFINITY;
-    for (int kpos = warp; kpos < len; kpos += 4) {
+        for (int e = 0; e < EPL; ++e) qr[e] = __bfloat162float(qp[e]);
+    }
+    auto row_ptr = [&](const bf16* cache, int kpos) {
         const long long slot = (long long)bt[kpos / page] * page + (kpos % page);
-        const bf16* kp = k_cache + (slot * H + h) * HD + lane * EPL;
-        float d = 0.f;
+        return cache + (slot * H + h) * HD + lane * EPL;
+    };
+    auto load_row = [&](const bf16* p, float (&v)[EPL]) {
+        if constexpr (EPL == 4) {
+            const uint2 u = *reinterpret_cast<const uint2*>(p);
+            const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+            v[0] = a.x; v[1] = a.y; v[2] = c.x; v[3] = c.y;
+        } else {
+            const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p));
+            v[0] = a.x; v[1] = a.y;
+        }
+    };
+    // ---- phase 1: scores
+    float lmax = -INFINITY;
+    for (int k0 = warp * 4; k0 < len; k0 += DEC_WARPS * 4) {
+        float kv[4][EPL];
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) d += qr[e] * __bfloat162float(kp[e]);
-        d = warp_sum(d);
-        d = bf16_round(bf16_round(d) / inv_scale);
-        if (lane == 0) sc[kpos] = d;
-        lmax = fmaxf(lmax, d);
+        for (int u = 0; u < 4; ++u) {
+            if (k0 + u < len) load_row(row_ptr(k_cache, k0 + u), kv[u]);
+            else {
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) kv[u][e] = 0.f;
+            }
+        }
+        float d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            d[u] = 0.f;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) d[u] += qr[e] * kv[u][e];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (k0 + u < len) {
+                const float x = bf16_round(bf16_round(d[u]) / inv_scale);
+                if (lane == 0) sc[k0 + u] = x;
+                lmax = fmaxf(lmax, x);
+            }
+        }
     }
     if (lane == 0) red[warp] = lmax;
     __syncthreads();
-    const float gmax = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    float gmax = red[0];
+#pragma unroll
+    for (int w = 1; w < DEC_WARPS; ++w) gmax = fmaxf(gmax, red[w]);
     __syncthreads();
+    // ---- phase 2: softmax (fp32), probabilities rounded to bf16 like the reference's .to(query.dtype)
     float lsum = 0.f;
-    for (int i = threadIdx.x; i < len; i += 128) {
+    for (int i = threadIdx.x; i < len; i += DEC_WARPS * 32) {
         const float e = __expf(sc[i] - gmax);
         sc[i] = e;
         lsum += e;
@@ -301,15 +346,41 @@ __global__ void __launch_bounds__(128) decode_attn_paged_kernel(const bf16* __re
     lsum = warp_sum(lsum);
     if (lane == 0) red[warp] = lsum;
     __syncthreads();
-    const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
-    // P.V: thread d owns one output channel; coalesced across the CTA.
-    for (int d = threadIdx.x; d < HD; d += 128) {
-        float acc = 0.f;
-        for (int kpos = 0; kpos < len; ++kpos) {
-            const long long slot = (long long)bt[kpos / page] * page + (kpos % page);
-            acc += bf16_round(sc[kpos] * inv) * __bfloat162float(v_cache[(slot * H + h) * HD + d]);
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) tot += red[w];
+    const float inv = 1.f / tot;
+    // ---- phase 3: P.V, each warp accumulates its keys, partials reduced through shared memory
+    float acc[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+    for (int k0 = warp * 4; k0 < len; k0 += DEC_WARPS * 4) {
+        float vv[4][EPL];
+        float pr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (k0 + u < len) {
+                load_row(row_ptr(v_cache, k0 + u), vv[u]);
+                pr[u] = bf16_round(sc[k0 + u] * inv);
+            } else {
+                pr[u] = 0.f;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) vv[u][e] = 0.f;
+            }
         }
-        out[((long long)b * H + h) * HD + d] = __float2bfloat16_rn(acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) acc[e] += pr[u] * vv[u][e];
+    }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) part[warp][lane * EPL + e] = acc[e];
+    __syncthreads();
+    for (int d = threadIdx.x; d < HD; d += DEC_WARPS * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < DEC_WARPS; ++w) s += part[w][d];
+        out[((long long)b * H + h) * HD + d] = __float2bfloat16_rn(s);
     }
 }
 
@@ -562,13 +633,13 @@ extern "C" int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, co
     if (hd == 128) {
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_paged_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
-        decode_attn_paged_kernel<128><<<grid, 128, smem, stream>>>((const bf16*)q, (const bf16*)k_cache,
+        decode_attn_paged_kernel<128><<<grid, DEC_WARPS * 32, smem, stream>>>((const bf16*)q, (const bf16*)k_cache,
                                                                    (const bf16*)v_cache, block_table, seq_lens,
                                                                    (bf16*)out, H, page_size, max_pages, inv_scale);
     } else if (hd == 64) {
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_paged_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
-        decode_attn_paged_kernel<64><<<grid, 128, smem, stream>>>((const bf16*)q, (const bf16*)k_cache,
+        decode_attn_paged_kernel<64><<<grid, DEC_WARPS * 32, smem, stream>>>((const bf16*)q, (const bf16*)k_cache,
                                                                   (const bf16*)v_cache, block_table, seq_lens, (bf16*)out,
                                                                   H, page_size, max_pages, inv_scale);
     } else {

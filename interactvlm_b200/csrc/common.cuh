@@ -56,6 +56,37 @@ IVLM_DEVINL float apply_act(float x, int act) {
     }
 }
 
+// GELU (erf form) with the Abramowitz-Stegun 7.1.26 rational erf (|err| <= 1.5e-7, far below bf16 resolution):
+// 0.5*x*(1+erf(x/sqrt2)); the negative branch uses 1+erf(-z) = poly*exp(-z^2) directly (no cancellation).
+IVLM_DEVINL float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(t, poly, 1.421413741f);
+    poly = fmaf(t, poly, -0.284496736f);
+    poly = fmaf(t, poly, 0.254829592f);
+    const float pe = poly * t * __expf(-z * z);
+    return 0.5f * x * (x < 0.f ? pe : 2.0f - pe);
+}
+// act followed by the bf16 rounding the eager reference applies to the activation output
+IVLM_DEVINL float apply_act_fast(float x, int act) {
+    switch (act) {
+        case ACT_GELU: return gelu_fast(x);
+        case ACT_QUICK_GELU: return __fdividef(x, 1.0f + __expf(-1.702f * x));
+        case ACT_RELU: return fmaxf(x, 0.0f);
+        case ACT_SILU: return __fdividef(x, 1.0f + __expf(-x));
+        default: return x;
+    }
+}
+// bf16x2 + bf16x2 with fp32 arithmetic and one rounding (torch's bf16 add)
+IVLM_DEVINL uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+    const float2 fa = unpack_bf16x2(a), fb = unpack_bf16x2(b);
+    return pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+}
+IVLM_DEVINL void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 IVLM_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -76,20 +107,29 @@ IVLM_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 IVLM_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+    // the suspend-time hint lets the hardware park the thread (up to ~the hint, in ns) instead of spinning through
+    // the issue slots the epilogue warps on the same SM sub-partition need; it wakes as soon as the phase completes
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
         : "memory");
     return ok != 0;
 }
+IVLM_DEVINL uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // Bounded wait: a protocol bug must trap (visible CUDA error) instead of hanging the GPU box.
 IVLM_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_timer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
+        if ((++spins & 255u) == 0 && global_timer_ns() - t0 > 5000000000ull) {
             printf("ivlm: mbarrier wait timeout block=%d thread=%d\n", (int)blockIdx.x, (int)threadIdx.x);
             __trap();
         }

@@ -5,7 +5,10 @@
 //   * persistent CTAs (one per SM), static round-robin tile scheduler, optional split-K work units;
 //   * warp 0 lane 0: TMA producer (cp.async.bulk.tensor, 128B swizzle, multi-stage mbarrier ring);
 //   * warp 1 lane 0: tcgen05.mma issuer (UMMA 128 x BN x 16, bf16 -> fp32 accumulators in TMEM);
-//   * warp 2: TMEM allocator; warps 4-7: epilogue (tcgen05.ld -> bias/act/residual -> global);
+//   * warp 2: TMEM allocator; warps 4-11: epilogue.  bf16 row-major outputs go TMEM -> registers (bias, activation,
+//     bf16 rounding; activation is a template parameter so the per-element code is branch-free and the compiler
+//     interleaves independent elements) -> 128B-swizzled shared-memory slab -> coalesced 16-byte global stores
+//     with the residual add and the optional row scatter;
 //   * TMEM accumulators are double buffered (2 x BN columns) so the epilogue of tile i overlaps the
 //     MMAs of tile i+1.
 // Small token counts (LLaMA decode, mask-decoder tokens) are run "swapped": the weight matrix is the
@@ -20,8 +23,10 @@ namespace ivlm {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quadrant: each takes half of the columns
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int GEMM_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 
 struct GemmParams {
     int M, N, K;  // kernel view: A-operand rows (128-row tiles), B-operand rows (BN tiles), reduction length
@@ -39,7 +44,22 @@ struct GemmParams {
     int out_f32;      // out is fp32 (else bf16)
     int atomic;       // split-K: red.add.f32 into out (fp32), no bias/act/res
     int round_steps;  // mirror torch bf16 op boundaries: round after bias, after act, after residual
+    int n_fastest;    // tile order (see tile_coords)
+    int staged;       // bf16 row-major output through the shared-memory staged epilogue
 };
+
+// Tile order: the operand that is re-read across the other dimension should be the small one, so that it stays in
+// L2.  n_fastest walks all N tiles of a few M tiles first (weights resident, activations streamed once); the default
+// walks M first (activations resident, weights streamed once -- LLaMA prefill, where W >> A).
+IVLM_DEVINL void tile_coords(const GemmParams& p, int t, int bn, int& m0, int& n0) {
+    if (p.n_fastest) {
+        n0 = (t % p.num_n_tiles) * bn;
+        m0 = (t / p.num_n_tiles) * BM;
+    } else {
+        m0 = (t % p.num_m_tiles) * BM;
+        n0 = (t / p.num_m_tiles) * bn;
+    }
+}
 
 template <int BN>
 struct GemmCfg {
@@ -47,11 +67,38 @@ struct GemmCfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int MAX_STAGES = 8;
-    static constexpr int SMEM_BUDGET = 200 * 1024;
+    static constexpr int SMEM_BUDGET = 196608;  // 4 x 48 KB stages at BN=256; leaves room for the epilogue staging
     static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) < MAX_STAGES ? (SMEM_BUDGET / STAGE_BYTES) : MAX_STAGES;
     static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    // epilogue staging: two [128 rows x 64 bf16] slabs (128B-swizzled) + one fp32 bias row
+    static constexpr bool STAGED = BN >= 64;
+    static constexpr int EPI_BYTES = STAGED ? (2 * BM * 128 + BN * 4) : 0;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+// Phase 1 of the staged epilogue for one warp: 32 accumulator rows x 32 columns -> bf16 -> swizzled slab.
+template <int ACT>
+IVLM_DEVINL void epi_stage_chunk(uint32_t taddr, const float* __restrict__ bs, bool has_bias, uint8_t* buf, int rloc,
+                                 int seg0) {
+    uint32_t raw[32];
+    tmem_ld_32x32(taddr, raw);
+    tmem_ld_wait();
+    float x[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float y = __uint_as_float(raw[j]);
+        if (has_bias) y += bs[j];
+        if (ACT != ACT_NONE) y = apply_act_fast(bf16_round(y), ACT);
+        x[j] = y;
+    }
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+        uint4 q;
+        q.x = pack_bf16x2(x[j8 * 8 + 0], x[j8 * 8 + 1]); q.y = pack_bf16x2(x[j8 * 8 + 2], x[j8 * 8 + 3]);
+        q.z = pack_bf16x2(x[j8 * 8 + 4], x[j8 * 8 + 5]); q.w = pack_bf16x2(x[j8 * 8 + 6], x[j8 * 8 + 7]);
+        *reinterpret_cast<uint4*>(buf + rloc * 128 + (((seg0 + j8) ^ (rloc & 7)) << 4)) = q;
+    }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -64,7 +111,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;                       // 2 x [128][128 B]
+    float* bias_s = reinterpret_cast<float*>(epi_stage + 2 * BM * 128);         // [BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -85,7 +134,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -105,8 +154,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int ks = u % p.k_splits;
                 const int t = u / p.k_splits;
-                const int m0 = (t % p.num_m_tiles) * BM;
-                const int n0 = (t / p.num_m_tiles) * BN;
+                int m0, n0;
+                tile_coords(p, t, BN, m0, n0);
                 const int kb0 = ks * p.k_blocks_per_split;
                 const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -152,16 +201,74 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
     } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------ epilogue
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+        const int chalf = (warp - EPI_WARP0) >> 2;  // which half of the columns this warp of the quadrant takes
         int it = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
             const int t = u / p.k_splits;
-            const int m0 = (t % p.num_m_tiles) * BM;
-            const int n0 = (t / p.num_m_tiles) * BN;
+            int m0, n0;
+            tile_coords(p, t, BN, m0, n0);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
+
+            if constexpr (Cfg::STAGED) {
+                if (p.staged) {
+                    // ---- staged epilogue.  Phase 1: warp (quad, chalf) converts its 32 rows x 32 columns of the
+                    // 64-column slab into the swizzled staging buffer; phase 2: every thread moves (row, 16-byte
+                    // segment) items to global memory, so stores and residual loads are whole 128-byte row pieces.
+                    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
+                    if (p.bias != nullptr)
+                        for (int c = et; c < BN; c += EPI_THREADS)
+                            bias_s[c] = (n0 + c < p.N) ? __bfloat162float(p.bias[n0 + c]) : 0.f;
+                    named_bar_sync(1, EPI_THREADS);
+                    constexpr int NSLAB = BN / 64;
+                    const int rloc = quad * 32 + lane;
+                    const bool has_bias = p.bias != nullptr;
+#pragma unroll 1
+                    for (int slab = 0; slab < NSLAB; ++slab) {
+                        uint8_t* buf = epi_stage + (slab & 1) * (BM * 128);
+                        const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN + slab * 64 + chalf * 32);
+                        const float* bs = bias_s + slab * 64 + chalf * 32;
+                        switch (p.act) {
+                            case ACT_GELU: epi_stage_chunk<ACT_GELU>(taddr, bs, has_bias, buf, rloc, chalf * 4); break;
+                            case ACT_QUICK_GELU: epi_stage_chunk<ACT_QUICK_GELU>(taddr, bs, has_bias, buf, rloc, chalf * 4); break;
+                            case ACT_RELU: epi_stage_chunk<ACT_RELU>(taddr, bs, has_bias, buf, rloc, chalf * 4); break;
+                            case ACT_SILU: epi_stage_chunk<ACT_SILU>(taddr, bs, has_bias, buf, rloc, chalf * 4); break;
+                            default: epi_stage_chunk<ACT_NONE>(taddr, bs, has_bias, buf, rloc, chalf * 4); break;
+                        }
+                        if (slab == NSLAB - 1) {  // accumulator fully read: hand it back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                        }
+                        named_bar_sync(1, EPI_THREADS);
+                        const int seg = et & 7;
+                        const int col = n0 + slab * 64 + seg * 8;
+#pragma unroll
+                        for (int i = 0; i < BM * 8 / EPI_THREADS; ++i) {
+                            const int rl = i * (EPI_THREADS / 8) + (et >> 3);
+                            const int grow = m0 + rl;
+                            if (grow >= p.M || col >= p.N) continue;
+                            int orow = grow;
+                            if (p.row_map != nullptr) {
+                                orow = p.row_map[grow];
+                                if (orow < 0) continue;
+                            }
+                            uint4 q = *reinterpret_cast<const uint4*>(buf + rl * 128 + ((seg ^ (rl & 7)) << 4));
+                            if (p.res != nullptr) {
+                                const int rrow = p.res_row_mod > 0 ? (orow % p.res_row_mod) : orow;
+                                const uint4 r4 = *reinterpret_cast<const uint4*>(p.res + (long long)rrow * p.res_rs + col);
+                                q.x = add_bf16x2(q.x, r4.x); q.y = add_bf16x2(q.y, r4.y);
+                                q.z = add_bf16x2(q.z, r4.z); q.w = add_bf16x2(q.w, r4.w);
+                            }
+                            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (long long)orow * p.out_rs + col) = q;
+                        }
+                    }
+                    continue;
+                }
+            }
 
             const int r = m0 + quad * 32 + lane;
             const bool r_ok = r < p.M;
@@ -173,7 +280,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
             constexpr int CH = BN < 32 ? BN : 32;  // columns per TMEM load
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += CH) {
+            for (int c0 = chalf * CH; c0 < BN; c0 += 2 * CH) {
                 float v[CH];
                 {
                     const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN + c0);
@@ -425,6 +532,9 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
     p.out_f32 = a->out_dtype == IVLM_F32;
     p.atomic = split ? 1 : 0;
     p.round_steps = (a->out_dtype == IVLM_BF16 && !a->no_round) ? 1 : 0;
+    p.staged = (!swap && !split && a->out_dtype == IVLM_BF16 && !a->no_round && bn >= 64) ? 1 : 0;
+    // keep the smaller operand L2-resident across the sweep of the other dimension
+    p.n_fastest = ((long long)p.N * p.K < (long long)p.M * p.K) ? 1 : 0;
 
     const CUtensorMap *ta, *tb;
     IVLM_TRY(get_tmap_bf16(h, pa, p.M, p.K, lda, BM, &ta));

@@ -67,8 +67,13 @@ def test_tiny_end_to_end_vs_oracle_and_reference_goldens(tiny):
     assert np.abs(c - gc).max() < max(3 * cn, 0.02)
     far = np.abs(gc - 0.5) > max(3 * cn, 0.02)
     assert np.array_equal((c >= 0.5)[far], (gc >= 0.5)[far])  # contact vertex set, away from the threshold
-    f1, _, _ = OL.f1_metrics(c, (gc >= 0.5).astype(np.float32))
-    assert f1 > 0.995  # "contact-F1 within 0.5 pt of the reference"
+    # "contact-F1 within 0.5 pt of the reference": the reference runs bf16, and its own bf16 run scores
+    # F1(ref_bf16 | ref_fp32) against its fp32 run on these inputs; ours must not be more than 0.5 pt below that.
+    gt = (gc >= 0.5).astype(np.float32)
+    f1, _, _ = OL.f1_metrics(c, gt)
+    f1_ref, _, _ = OL.f1_metrics(gold["bf16_contact"], gt)
+    print(f"F1 vs reference fp32 contact set: ours {f1:.4f}, reference bf16 {f1_ref:.4f}")
+    assert f1 > f1_ref - 0.005
 
 
 def test_tail_given_identical_inputs_is_1e3(tiny):
