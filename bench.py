@@ -317,6 +317,10 @@ def main():
         ms, launches = timed(True, args.steps)
         ms_e2e, _ = timed(False, args.steps)
     clocks = cs.summary()
+    model.record_stages = True
+    step(True)
+    stages = model.stage_ms()
+    model.record_stages = False
     # launches inside CUDA-graph replays are not seen by the handle's counter: add them explicitly
     graph_launches = 0
     st = next(iter(model._graphs.values()), None)
@@ -331,7 +335,8 @@ def main():
             "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(clip_h.numel() * 2 + sam_h.numel() * 2 + cam_h.numel() * 2) * world,
                     "d2h_bytes_per_step": int(host_out.numel() * 4)},
-            "gpu_launches": int(launches + graph_launches), "sam_views_per_s": value * cfg.multiview_channels}
+            "gpu_launches": int(launches + graph_launches), "sam_views_per_s": value * cfg.multiview_channels,
+            "stage_ms": {k: round(v, 2) for k, v in stages.items()}}
 
     if rank == 0:
         pk = peaks()
@@ -358,6 +363,14 @@ def main():
             if "attention" in rep:
                 a = rep["attention"]
                 line["attention_tflops"] = a["work"] / (a["ms"] / 1e3) / 1e12
+        if "llm_decode" in stages:
+            # decode steps stream every LLaMA weight once per step for the whole batch: HBM-bound
+            nl, D, F = cfg.num_hidden_layers, cfg.hidden_size, cfg.intermediate_size
+            wbytes = 2.0 * (nl * (4 * D * D + 3 * D * F) + D * cfg.vocab_size)
+            kv = 2.0 * 2 * nl * D * args.batch * (ids.shape[1] + 255 + N_ANS / 2)
+            per_step = stages["llm_decode"] / (N_ANS - 1) / 1e3
+            line["decode_hbm"] = {"bound": "hbm", "achieved": (wbytes + kv) / per_step / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                  "frac": (wbytes + kv) / per_step / 1e9 / pk["hbm"], "ms_per_token_step": per_step * 1e3}
         if not args.no_cpu_baseline and world == 1:
             v, desc, cores, _ = cpu_reference(cfg)
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc}

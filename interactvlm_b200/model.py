@@ -470,7 +470,24 @@ class InteractVLMForCausalLM:
         self.object_3d_contact_predictor = _Predictor(self, LIFT_OBJECT_MESH)
         self.object_3d_afford_predictor = _Predictor(self, LIFT_POINTS)
         self.sam_chunk = 8
-        self.timings = None
+        self.record_stages = False  # bench.py: CUDA events at stage boundaries (a dozen per call)
+        self._marks = []
+
+    def _mark(self, name):
+        if self.record_stages and self.device.type == "cuda":
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append((name, e))
+
+    def stage_ms(self) -> dict:
+        """Milliseconds between consecutive stage marks since the last call (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self._marks, self._marks[1:]):
+            if n1 != "start":
+                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        self._marks = []
+        return out
 
     # ---- construction -------------------------------------------------------------------------------------------
     @classmethod
@@ -596,10 +613,13 @@ class InteractVLMForCausalLM:
         max_len = S + max_new_tokens
         if max_len > cfg.max_position_embeddings:
             raise ValueError(f"sequence {max_len} exceeds max_position_embeddings {cfg.max_position_embeddings}")
+        self._mark("start")
         feats = eng.clip_encode(self._bf16(images_clip))
+        self._mark("clip")
         embeds = self.ctx.embed_splice(self.w.embed, ids.to(torch.int32).to(self.device).contiguous(), feats.contiguous())
         st = self._llm_state(B, max_len)
         nxt = eng.llm_prefill(st, embeds)
+        self._mark("llm_prefill")
         graph = st.get("graph")
         out = [ids]
         done = torch.zeros(B, dtype=torch.bool)
@@ -625,6 +645,7 @@ class InteractVLMForCausalLM:
                 eng.llm_decode_step(st)
             st["hidden"][:, p] = st["hid_step"]
             nxt = st["next"]
+        self._mark("llm_decode")
         return torch.cat(out, 1), st["hidden"]
 
     # ---- public API ---------------------------------------------------------------------------------------------
@@ -644,6 +665,7 @@ class InteractVLMForCausalLM:
             elif (self.oC_loss_weight > 0 and "ocontact" in contact_type) or "oafford" in contact_type:  # sic (:626)
                 pred_contact_3d = self.object_3d_contact_predictor(pred_masks, ds_names=["ocontact"],
                                                                    lift2d_dict_path=lift2d_dict_path)
+        self._mark("lift")
         return {"output_ids": output_ids.to(self.device), "pred_masks": pred_masks, "pred_contact_3d": pred_contact_3d}
 
     def _masks_from_hidden(self, hidden, output_ids, images, cam_params, resize_list, original_size_list):
@@ -660,6 +682,7 @@ class InteractVLMForCausalLM:
                 rows.append(b * hidden.shape[1] + r[0])
                 owners.append(b)
         image_embeddings = self.get_visual_embs(images)  # computed for every sample, like the reference (:578)
+        self._mark("sam_encoder")
         S, C = image_embeddings.shape[1], image_embeddings.shape[2]
         pred_masks = [None] * B
         if owners:
@@ -670,6 +693,7 @@ class InteractVLMForCausalLM:
             low = eng.mask_decode(emb, prompt).view(len(owners), V, 4 * cfg.sam_grid, 4 * cfg.sam_grid)
             for k, b in enumerate(owners):
                 pred_masks[b] = eng.postprocess(low[k].contiguous(), resize_list[b], original_size_list[b])
+        self._mark("mask_decoder_upsample")
         for b in range(B):
             if pred_masks[b] is None:
                 oh, ow = int(original_size_list[b][0]), int(original_size_list[b][1])
