@@ -125,6 +125,12 @@ IVLM_API int ivlm_attention_bf16(ivlm_handle h, const ivlm_attn_args* args, void
  * rel_w[b,h,q,kw] = q . Rw[qx-kw+W-1]; q read from the packed qkv rows [B*S, 3*heads*hd]. */
 IVLM_API int ivlm_sam_relpos(ivlm_handle h, const void* qkv, const void* rel_pos_h, const void* rel_pos_w, float* rel_h,
                     float* rel_w, int32_t B, int32_t heads, int32_t Hq, int32_t Wq, int32_t hd, void* stream);
+/* SAM ViT attention with the decomposed relative-position bias computed in-kernel (image_encoder.py:235-260, :354-392)
+ * on the tcgen05 tensor cores: qkv [B*S, 3*heads*80] packed rows (S = Hq*Wq tokens per image or window),
+ * rel_pos_h [2*Hq-1, 80], rel_pos_w [2*Wq-1, 80] bf16 -> out rows [B*S] with pitch out_ld, columns head*80 + c.
+ * Token grids 64x64 (global blocks) and 14x14 (windows). */
+IVLM_API int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out,
+                            int32_t B, int32_t heads, int32_t Hq, int32_t Wq, int32_t hd, int64_t out_ld, void* stream);
 /* Attention with few queries or few keys and small head_dim (SAM TwoWayTransformer, transformer.py:185-242):
  * q [B,Nq,heads*hd], k/v [B,Nk,heads*hd], out [B,Nq,heads*hd]; hd in {16,32}. q batch may be 1 (broadcast). */
 IVLM_API int ivlm_attn_small_bf16(ivlm_handle h, const void* q, const void* k, const void* v, void* out, int32_t B,

@@ -1,0 +1,415 @@
+// SAM ViT attention (head_dim 80, decomposed relative-position bias) on the 5th-gen tensor cores.
+//
+//   out = softmax(q k^T * scale + rel_h[q, ky] + rel_w[q, kx]) v          image_encoder.py:235-260, :354-392
+//
+// One CTA per (128-query tile, head, image-or-window).  Everything GEMM-shaped runs as tcgen05.mma with fp32
+// accumulators in TMEM, operands staged by TMA:
+//   prologue  T_h = Q Rh_all^T, T_w = Q Rw_all^T   (the two rel-pos einsums for the whole tile: 2 x 5 UMMAs instead of a
+//             separate kernel and a 1 GB/block fp32 round trip through HBM); rounded to bf16 like the reference's einsum
+//             outputs and kept in shared memory, transposed ([table index][query row]) so that lookups are conflict-free;
+//   per 128-key tile   S = Q K^T (5 UMMAs, K = 64 + 16) -> softmax warps read S with tcgen05.ld (one query row per
+//             thread, no shuffles), add the bias, online softmax with lazy rescaling (O in TMEM is only touched when the
+//             running max moves by more than 2^8), P (bf16) -> 128B-swizzled shared memory -> O += P V (V is the
+//             MN-major operand straight from its row-major [key, 80] layout; N = 64 + 16).
+// head_dim 80 is split 64 + 16: the 64-column part uses 128B-swizzled tiles, the 16-column part 32B-swizzled tiles.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = softmax / correction / epilogue.
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "runtime.h"
+
+namespace ivlm {
+
+constexpr int AT_BQ = 128, AT_BK = 128, AT_HD = 80, AT_NS = 2, AT_THREADS = 256;
+constexpr int AT_QA = AT_BQ * 128, AT_QB = AT_BQ * 32;                // Q tile: 64-col part, 16-col part (bytes)
+constexpr int AT_STAGE = 2 * (AT_BK * 128 + AT_BK * 32);              // K (a,b) + V (a,b)
+constexpr int AT_P = AT_BQ * AT_BK * 2;                               // P tile, two 64-key chunks
+constexpr int AT_TAB = 128 * AT_BQ * 2;                               // transposed bias table [<=128 idx][128 rows] bf16
+constexpr int AT_SMEM = AT_QA + AT_QB + AT_NS * AT_STAGE + AT_P + 2 * AT_TAB + 1024 + 256;
+constexpr int AT_TMEM_COLS = 512;
+constexpr int AT_O_COL = 256;
+constexpr float AT_LOG2E = 1.4426950408889634f;
+
+struct SamAttnParams {
+    bf16* out;
+    long long out_ld;  // elements between consecutive tokens of `out`
+    int S;             // tokens per image / window
+    int heads;
+    int KH;            // key grid height (== query grid height)
+    float scale_log2;  // head_dim^-0.5 * log2(e)
+};
+
+// K-major 32B-swizzled operand ([rows][16 bf16], rows 32 B apart, 8-row groups 256 B apart).
+IVLM_DEVINL uint64_t umma_desc_sw32_kmajor(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
+// MN-major operand whose rows are K (keys): [k rows][64 bf16] 128B-swizzled; 8-row groups 1024 B apart (SBO).
+IVLM_DEVINL uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 16;  // LBO: next 64-element MN block (unused: one block)
+    d |= (uint64_t)(1024 >> 4) << 32;  // SBO: next group of 8 K rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// MN-major, [k rows][16 bf16] 32B-swizzled; 8-row groups 256 B apart.
+IVLM_DEVINL uint64_t umma_desc_sw32_mnmajor(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(256 >> 4) << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {  // B operand MN-major
+    return umma_idesc_bf16(M, N) | (1u << 16);
+}
+
+IVLM_DEVINL void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+IVLM_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+IVLM_DEVINL float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// S / T tile (128 x 128 fp32 in TMEM) = A[128 x 80] . B[128 x 80]^T, both K-major, split 64 + 16.
+IVLM_DEVINL void issue_qk(uint32_t d_tmem, const uint8_t* a64, const uint8_t* a16, const uint8_t* b64, const uint8_t* b16) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    const uint64_t da = umma_desc_sw128_kmajor(smem_u32(a64)), db = umma_desc_sw128_kmajor(smem_u32(b64));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : 0u);
+    umma_bf16(d_tmem, umma_desc_sw32_kmajor(smem_u32(a16)), umma_desc_sw32_kmajor(smem_u32(b16)), idesc, 1u);
+}
+
+// KW = key grid width: 64 (global attention over the 64x64 token grid) or 14 (14x14 windows).
+template <int KW>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+sam_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKVa, const __grid_constant__ CUtensorMap tmQKVb,
+                        const __grid_constant__ CUtensorMap tmRHa, const __grid_constant__ CUtensorMap tmRHb,
+                        const __grid_constant__ CUtensorMap tmRWa, const __grid_constant__ CUtensorMap tmRWb,
+                        const SamAttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_a = smem;
+    uint8_t* q_b = q_a + AT_QA;
+    uint8_t* stage0 = q_b + AT_QB;
+    auto k_a = [&](int s) { return stage0 + s * AT_STAGE; };
+    auto k_b = [&](int s) { return stage0 + s * AT_STAGE + AT_BK * 128; };
+    auto v_a = [&](int s) { return stage0 + s * AT_STAGE + AT_BK * 160; };
+    auto v_b = [&](int s) { return stage0 + s * AT_STAGE + AT_BK * 288; };
+    uint8_t* p_s = stage0 + AT_NS * AT_STAGE;
+    bf16* th_s = reinterpret_cast<bf16*>(p_s + AT_P);  // [idx][128 rows]
+    bf16* tw_s = th_s + 128 * AT_BQ;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tw_s) + AT_TAB);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* tab_full = bars + 1;      // 1
+    uint64_t* t_full = bars + 2;        // 1
+    uint64_t* kv_full = bars + 3;       // AT_NS
+    uint64_t* kv_empty = bars + 5;      // AT_NS
+    uint64_t* s_full = bars + 7;        // 2
+    uint64_t* s_empty = bars + 9;       // 2
+    uint64_t* p_full = bars + 11;       // 1
+    uint64_t* pv_done = bars + 12;      // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+    const int E = p.heads * AT_HD;
+    const int n_tiles = (p.S + AT_BK - 1) / AT_BK;
+    const int row_base = b * p.S;  // first token row of this image / window in the packed qkv matrix
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKVa); tma_prefetch_desc(&tmQKVb);
+        tma_prefetch_desc(&tmRHa); tma_prefetch_desc(&tmRHb);
+        tma_prefetch_desc(&tmRWa); tma_prefetch_desc(&tmRWb);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1); mbar_init(tab_full, 1); mbar_init(t_full, 1);
+        for (int s = 0; s < AT_NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
+        mbar_init(p_full, 4);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, AT_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, AT_QA + AT_QB);
+            tma_load_2d(q_a, &tmQKVa, q_full, h * AT_HD, row_base + q0);
+            tma_load_2d(q_b, &tmQKVb, q_full, h * AT_HD + 64, row_base + q0);
+            // rel-pos tables ride in the K slots of stages 0 and 1 until the prologue MMAs have consumed them
+            mbar_arrive_expect_tx(tab_full, 2 * (AT_BK * 128 + AT_BK * 32));
+            tma_load_2d(k_a(0), &tmRHa, tab_full, 0, 0);
+            tma_load_2d(k_b(0), &tmRHb, tab_full, 64, 0);
+            tma_load_2d(k_a(1), &tmRWa, tab_full, 0, 0);
+            tma_load_2d(k_b(1), &tmRWb, tab_full, 64, 0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % AT_NS;
+                mbar_wait(&kv_empty[s], (j / AT_NS) & 1);  // completion 0 = prologue MMAs done with the tables
+                mbar_arrive_expect_tx(&kv_full[s], AT_STAGE);
+                const int r = row_base + j * AT_BK;
+                tma_load_2d(k_a(s), &tmQKVa, &kv_full[s], E + h * AT_HD, r);
+                tma_load_2d(k_b(s), &tmQKVb, &kv_full[s], E + h * AT_HD + 64, r);
+                tma_load_2d(v_a(s), &tmQKVa, &kv_full[s], 2 * E + h * AT_HD, r);
+                tma_load_2d(v_b(s), &tmQKVb, &kv_full[s], 2 * E + h * AT_HD + 64, r);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            mbar_wait(q_full, 0);
+            mbar_wait(tab_full, 0);
+            tc_fence_after();
+            issue_qk(tmem_base + 0, q_a, q_b, k_a(0), k_b(0));        // T_h -> S buffer 0
+            issue_qk(tmem_base + AT_BK, q_a, q_b, k_a(1), k_b(1));    // T_w -> S buffer 1
+            umma_commit(t_full);
+            for (int s = 0; s < AT_NS; ++s) umma_commit(&kv_empty[s]);
+            auto issue_s = [&](int j) {
+                const int s = j % AT_NS, sb = j & 1;
+                mbar_wait(&kv_full[s], (j / AT_NS) & 1);
+                mbar_wait(&s_empty[sb], (j >> 1) & 1);  // completion 0 = the prologue's read of T_h / T_w
+                tc_fence_after();
+                issue_qk(tmem_base + sb * AT_BK, q_a, q_b, k_a(s), k_b(s));
+                umma_commit(&s_full[sb]);
+            };
+            issue_s(0);
+            constexpr uint32_t idesc64 = umma_idesc_bf16_bmn(128, 64), idesc16 = umma_idesc_bf16_bmn(128, 16);
+            for (int j = 0; j < n_tiles; ++j) {
+                if (j + 1 < n_tiles) issue_s(j + 1);
+                const int s = j % AT_NS;
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < AT_BK / 16; ++ks) {
+                    const uint64_t dp = umma_desc_sw128_kmajor(smem_u32(p_s + (ks >> 2) * (AT_BQ * 128))) + 2 * (ks & 3);
+                    const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+                    umma_bf16(tmem_base + AT_O_COL, dp, umma_desc_sw128_mnmajor(smem_u32(v_a(s) + ks * 2048)), idesc64, acc);
+                    umma_bf16(tmem_base + AT_O_COL + 64, dp, umma_desc_sw32_mnmajor(smem_u32(v_b(s) + ks * 512)), idesc16, acc);
+                }
+                umma_commit(&kv_empty[s]);
+                umma_commit(pv_done);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ softmax / correction / epilogue
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;  // query row inside the tile == TMEM lane
+        const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16);
+        const int qtok = q0 + r;
+        const int qy = qtok / KW, qx = qtok - qy * KW;
+        const int KH = p.KH;
+        // ---- prologue: bias tables for this tile
+        mbar_wait(t_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+            bf16* dst = t == 0 ? th_s : tw_s;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(lane_addr + t * AT_BK + c0, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dst[(c0 + i) * AT_BQ + r] = __float2bfloat16_rn(__uint_as_float(raw[i]));
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&s_empty[0]); mbar_arrive(&s_empty[1]); }
+        // each thread only ever reads column r of the tables, which it wrote itself: no CTA-level sync needed
+        const bf16* th_r = th_s + (qy + KH - 1) * AT_BQ + r;  // rel_h[ky] = th_r[-ky * 128]
+        const bf16* tw_r = tw_s + (qx + KW - 1) * AT_BQ + r;  // rel_w[kx] = tw_r[-kx * 128]
+
+        float m_ref = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int sb = j & 1;
+            mbar_wait(&s_full[sb], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t xr[AT_BK];  // tcgen05.ld results: not to be touched before tcgen05.wait::ld
+#pragma unroll
+            for (int c0 = 0; c0 < AT_BK; c0 += 32)
+                tmem_ld_32x32(lane_addr + sb * AT_BK + c0, reinterpret_cast<uint32_t(&)[32]>(xr[c0]));
+            tmem_ld_wait();
+            float x[AT_BK];
+#pragma unroll
+            for (int c = 0; c < AT_BK; ++c) x[c] = __uint_as_float(xr[c]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[sb]);
+            // ---- scale + decomposed rel-pos bias, in the log2 domain
+            float mx = -INFINITY;
+            if constexpr (KW == 64) {
+                // tile j covers key rows 2j and 2j+1 completely; rel_w is shared by both
+                const float rh0 = __bfloat162float(th_r[-(2 * j) * AT_BQ]) * AT_LOG2E;
+                const float rh1 = __bfloat162float(th_r[-(2 * j + 1) * AT_BQ]) * AT_LOG2E;
+#pragma unroll
+                for (int kx = 0; kx < 64; ++kx) {
+                    const float rw = __bfloat162float(tw_r[-kx * AT_BQ]) * AT_LOG2E;
+                    x[kx] = fmaf(x[kx], p.scale_log2, rw + rh0);
+                    x[64 + kx] = fmaf(x[64 + kx], p.scale_log2, rw + rh1);
+                    mx = fmaxf(mx, fmaxf(x[kx], x[64 + kx]));
+                }
+            } else {
+                const int kbase = j * AT_BK;
+#pragma unroll
+                for (int c = 0; c < AT_BK; ++c) {
+                    const int k = kbase + c;
+                    const int ky = k / KW, kx = k - ky * KW;
+                    if (k < p.S) {
+                        const float bias = __bfloat162float(th_r[-ky * AT_BQ]) + __bfloat162float(tw_r[-kx * AT_BQ]);
+                        x[c] = fmaf(x[c], p.scale_log2, bias * AT_LOG2E);
+                        mx = fmaxf(mx, x[c]);
+                    } else {
+                        x[c] = -INFINITY;
+                    }
+                }
+            }
+            // ---- online softmax with lazy rescaling: the reference point m_ref only moves when the row max grew by > 2^8
+            float corr = 1.f;
+            bool moved = false;
+            if (j == 0) {
+                m_ref = mx;
+            } else if (mx > m_ref + 8.f) {
+                corr = ex2_approx(m_ref - mx);
+                m_ref = mx;
+                moved = true;
+            }
+            float sum = 0.f;
+            uint32_t pk[AT_BK / 2];
+#pragma unroll
+            for (int c = 0; c < AT_BK; c += 2) {
+                const float p0 = ex2_approx(x[c] - m_ref), p1 = ex2_approx(x[c + 1] - m_ref);
+                sum += p0 + p1;
+                pk[c >> 1] = pack_bf16x2(p0, p1);
+            }
+            l_run = l_run * corr + sum;
+            // ---- P and (rarely) the O correction may only touch shared / tensor memory once PV_{j-1} has retired
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, moved)) {
+#pragma unroll
+                    for (int c0 = 0; c0 < AT_HD; c0 += 16) {
+                        uint32_t o[16];
+                        tmem_ld_32x16(lane_addr + AT_O_COL + c0, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                        tmem_st_32x16(lane_addr + AT_O_COL + c0, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint8_t* row = p_s + ch * (AT_BQ * 128) + r * 128;
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {
+                    const int i = ch * 32 + c16 * 4;
+                    *reinterpret_cast<uint4*>(row + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l -> bf16 -> out[token, head*80 ...]
+        mbar_wait(pv_done, (n_tiles - 1) & 1);
+        tc_fence_after();
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        bf16* orow = p.out + (long long)(row_base + qtok) * p.out_ld + h * AT_HD;
+#pragma unroll
+        for (int c0 = 0; c0 < AT_HD; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld_32x16(lane_addr + AT_O_COL + c0, o);
+            tmem_ld_wait();
+            if (qtok < p.S) {
+                uint4 u0, u1;
+                u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+                u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+                u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+                u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+                u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+                reinterpret_cast<uint4*>(orow + c0)[0] = u0;
+                reinterpret_cast<uint4*>(orow + c0)[1] = u1;
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, AT_TMEM_COLS);
+    }
+}
+
+}  // namespace ivlm
+
+using namespace ivlm;
+
+extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const void* rel_pos_h, const void* rel_pos_w,
+                                       void* out, int32_t B, int32_t heads, int32_t Hq, int32_t Wq, int32_t hd,
+                                       int64_t out_ld, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    IVLM_REQUIRE(h && qkv && rel_pos_h && rel_pos_w && out && B > 0 && heads > 0, "sam_attention: bad arguments");
+    IVLM_REQUIRE(hd == AT_HD, "sam_attention: head_dim %d not instantiated (80)", hd);
+    IVLM_REQUIRE((Hq == 64 && Wq == 64) || (Hq == 14 && Wq == 14), "sam_attention: token grid %dx%d not instantiated (64x64, 14x14)",
+                 Hq, Wq);
+    IVLM_REQUIRE(out_ld % 8 == 0, "sam_attention: out pitch must be a multiple of 8 elements");
+    const int S = Hq * Wq, E = heads * hd;
+    const uint64_t rows = (uint64_t)B * S;
+    const CUtensorMap *qa, *qb, *rha, *rhb, *rwa, *rwb;
+    IVLM_TRY(get_tmap_bf16_ex(h, qkv, rows, 3 * (uint64_t)E, 3 * (uint64_t)E, AT_BQ, 64, 128, &qa));
+    IVLM_TRY(get_tmap_bf16_ex(h, qkv, rows, 3 * (uint64_t)E, 3 * (uint64_t)E, AT_BQ, 16, 32, &qb));
+    IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_h, 2 * Hq - 1, hd, hd, AT_BK, 64, 128, &rha));
+    IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_h, 2 * Hq - 1, hd, hd, AT_BK, 16, 32, &rhb));
+    IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_w, 2 * Wq - 1, hd, hd, AT_BK, 64, 128, &rwa));
+    IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_w, 2 * Wq - 1, hd, hd, AT_BK, 16, 32, &rwb));
+    SamAttnParams p;
+    p.out = reinterpret_cast<bf16*>(out);
+    p.out_ld = out_ld;
+    p.S = S;
+    p.heads = heads;
+    p.KH = Hq;
+    p.scale_log2 = (1.0f / sqrtf((float)hd)) * AT_LOG2E;
+    dim3 grid((S + AT_BQ - 1) / AT_BQ, heads, B);
+    static bool attr_set = false;
+    if (!attr_set) {
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        attr_set = true;
+    }
+    if (Wq == 64)
+        sam_attn_tcgen05_kernel<64><<<grid, AT_THREADS, AT_SMEM, stream>>>(*qa, *qb, *rha, *rhb, *rwa, *rwb, p);
+    else
+        sam_attn_tcgen05_kernel<14><<<grid, AT_THREADS, AT_SMEM, stream>>>(*qa, *qb, *rha, *rhb, *rwa, *rwb, p);
+    h->launches++;
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    return IVLM_OK;
+}

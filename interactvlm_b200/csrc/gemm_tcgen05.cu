@@ -418,9 +418,9 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-int get_tmap_bf16(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                  const CUtensorMap** out) {
-    TmapKey key{ptr, rows, cols, ld, box_rows};
+int get_tmap_bf16_ex(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols, uint32_t swizzle_bytes, const CUtensorMap** out) {
+    TmapKey key{ptr, rows, cols, ld, box_rows, box_cols, swizzle_bytes};
     auto it = h->tmaps.find(key);
     if (it != h->tmaps.end()) {
         *out = &it->second;
@@ -434,23 +434,34 @@ int get_tmap_bf16(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, ui
     IVLM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand base %p is not 16-byte aligned", ptr);
     IVLM_REQUIRE((ld * 2) % 16 == 0, "TMA operand row pitch %llu elements is not a multiple of 8",
                  (unsigned long long)ld);
+    IVLM_REQUIRE(box_cols * 2 <= swizzle_bytes && box_rows <= 256, "TMA box %ux%u does not fit swizzle %u", box_rows,
+                 box_cols, swizzle_bytes);
+    const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                         : CU_TENSOR_MAP_SWIZZLE_32B;
     CUtensorMap m;
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstr[1] = {ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
-                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u swizzle=%u", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols,
+                  swizzle_bytes);
         return IVLM_ERR_CUDA;
     }
     if (h->tmaps.size() > 4096) h->tmaps.clear();  // activations churn pointers; keep the cache bounded
     auto ins = h->tmaps.emplace(key, m);
     *out = &ins.first->second;
     return IVLM_OK;
+}
+
+int get_tmap_bf16(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                  const CUtensorMap** out) {
+    return get_tmap_bf16_ex(h, ptr, rows, cols, ld, box_rows, BK, 128, out);
 }
 
 template <int BN>

@@ -43,8 +43,11 @@ struct TmapKey {
     const void* ptr;
     uint64_t rows, cols, ld;
     uint32_t box_rows;
+    uint32_t box_cols = 64;
+    uint32_t swizzle = 128;
     bool operator==(const TmapKey& o) const {
-        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+               box_cols == o.box_cols && swizzle == o.swizzle;
     }
 };
 struct TmapKeyHash {
@@ -54,6 +57,7 @@ struct TmapKeyHash {
         h = h * 1000003u ^ k.cols;
         h = h * 1000003u ^ k.ld;
         h = h * 1000003u ^ k.box_rows;
+        h = h * 1000003u ^ (k.box_cols * 131u + k.swizzle);
         return h;
     }
 };
@@ -91,4 +95,7 @@ namespace ivlm {
 // box = box_rows x 64 elements, 128B swizzle, zero OOB fill.
 int get_tmap_bf16(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                   const CUtensorMap** out);
+// General form: box = box_rows x box_cols elements, swizzle_bytes in {128, 64, 32} (box_cols * 2 must not exceed it).
+int get_tmap_bf16_ex(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols, uint32_t swizzle_bytes, const CUtensorMap** out);
 }  // namespace ivlm

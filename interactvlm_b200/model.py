@@ -164,6 +164,7 @@ class _Engine:
         self.ctx, self.cfg, self.w = ctx, cfg, w
         self.device = w.device
         self._win_maps = {}
+        self.fused_sam_attention = True
 
     # ------------------------------------------------------------------ CLIP + projector (a4)
     def clip_encode(self, images_clip):
@@ -202,6 +203,18 @@ class _Engine:
             self._win_maps[N] = (_i32(src.reshape(-1), self.device), nw)
         return self._win_maps[N]
 
+    def _sam_attention(self, qkv, bw, B, nh, side, hd):
+        """softmax(q k^T / sqrt(hd) + decomposed rel-pos) v for B images/windows of side x side tokens -> [B*S, nh*hd]."""
+        ctx = self.ctx
+        if self.fused_sam_attention and hd == 80 and side in (14, 64):
+            return ctx.sam_attention(qkv, bw["rph"], bw["rpw"], B, nh, side, side, hd)
+        # general shapes: separate rel-pos kernel + flash attention on the legacy tensor path
+        S = side * side
+        rel_h, rel_w = ctx.sam_relpos(qkv, bw["rph"], bw["rpw"], B, nh, side, side, hd)
+        t = qkv.view(B, S, 3, nh, hd)
+        o = ctx.attention(t[:, :, 0], t[:, :, 1], t[:, :, 2], hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=side, kw=side)
+        return o.view(B * S, nh * hd)
+
     def sam_encode(self, images):
         """[N,3,1024,1024] bf16 -> token-major embeddings [N, 4096, 256] (image_encoder.py:110-125)."""
         ctx, cfg, w = self.ctx, self.cfg, self.w.sam
@@ -217,21 +230,17 @@ class _Engine:
             if i in cfg.sam_global_attn_indexes:
                 y = ctx.layernorm(x, bw["n1g"], bw["n1b"], 1e-6)
                 qkv = ctx.gemm(y, bw["wqkv"], bias=bw["bqkv"], force_swap=-1)
-                rel_h, rel_w = ctx.sam_relpos(qkv, bw["rph"], bw["rpw"], N, nh, g, g, hd)
-                t = qkv.view(N, S, 3, nh, hd)
-                o = ctx.attention(t[:, :, 0], t[:, :, 1], t[:, :, 2], hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=g, kw=g)
-                x = ctx.gemm(o.view(N * S, E), bw["wo"], bias=bw["bo"], residual=x, force_swap=-1)
+                o = self._sam_attention(qkv, bw, N, nh, g, hd)
+                x = ctx.gemm(o, bw["wo"], bias=bw["bo"], residual=x, force_swap=-1)
             else:
                 Bw, Sw = N * nw * nw, ws * ws
                 y = ctx.layernorm(x, bw["n1g"], bw["n1b"], 1e-6, row_map=wmap)
                 qkv = ctx.gemm(y, bw["wqkv"], bias=bw["bqkv"], force_swap=-1)
-                rel_h, rel_w = ctx.sam_relpos(qkv, bw["rph"], bw["rpw"], Bw, nh, ws, ws, hd)
-                t = qkv.view(Bw, Sw, 3, nh, hd)
-                o = ctx.attention(t[:, :, 0], t[:, :, 1], t[:, :, 2], hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=ws, kw=ws)
+                o = self._sam_attention(qkv, bw, Bw, nh, ws, hd)
                 xn = torch.empty_like(x)
-                ctx.gemm(o.view(Bw * Sw, E), bw["wo"], bias=bw["bo"], residual=x, row_map=wmap, out=xn, force_swap=-1)
+                ctx.gemm(o, bw["wo"], bias=bw["bo"], residual=x, row_map=wmap, out=xn, force_swap=-1)
                 x = xn
-            del qkv, rel_h, rel_w, t, o
+            del qkv, o
             y = ctx.layernorm(x, bw["n2g"], bw["n2b"], 1e-6)
             y = ctx.gemm(y, bw["w1"], bias=bw["b1"], act=ACT_GELU, force_swap=-1)
             x = ctx.gemm(y, bw["w2"], bias=bw["b2"], residual=x, force_swap=-1)

@@ -59,7 +59,7 @@ class Context:
 
     # ------------------------------------------------------------------ per-kernel timing (bench.py roofline pass)
     _PROFILED = ("gemm", "attention", "layernorm", "rmsnorm", "add_bcast", "silu_mul", "im2col_patch", "im2col_3x3",
-                 "sam_relpos", "attn_small", "embed_splice", "embed_gather", "gather_rows", "rope_kv_store",
+                 "sam_relpos", "sam_attention", "attn_small", "embed_splice", "embed_gather", "gather_rows", "rope_kv_store",
                  "decode_attention", "argmax", "cam_gate", "upscale_hyper_dot", "bilinear", "finalize")
 
     def enable_profile(self):
@@ -77,6 +77,9 @@ class Context:
                 work = 0.0
                 if _name == "gemm":
                     work = 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0]
+                elif _name == "sam_attention":
+                    Bq, nh, S_, hd_ = a[3], a[4], a[5] * a[6], a[7]
+                    work = 4.0 * Bq * nh * S_ * S_ * hd_
                 elif _name == "attention":
                     B, Sq, H, D = a[0].shape
                     work = 4.0 * B * H * Sq * a[1].shape[1] * D * (0.5 if k.get("causal") else 1.0)
@@ -254,6 +257,17 @@ class Context:
         L.check(self.lib.ivlm_sam_relpos(self.h, P(qkv), P(rel_pos_h), P(rel_pos_w), P(rel_h), P(rel_w), i32(B),
                                          i32(heads), i32(Hq), i32(Wq), i32(hd), self.stream), "sam_relpos")
         return rel_h, rel_w
+
+    def sam_attention(self, qkv, rel_pos_h, rel_pos_w, B, heads, Hq, Wq, hd, out=None):
+        """Fused SAM attention (tcgen05): qkv [B*Hq*Wq, 3*heads*hd] -> [B*Hq*Wq, heads*hd]."""
+        _bf16(qkv); _bf16(rel_pos_h); _bf16(rel_pos_w)
+        assert qkv.is_contiguous() and rel_pos_h.is_contiguous() and rel_pos_w.is_contiguous()
+        assert qkv.shape == (B * Hq * Wq, 3 * heads * hd), (qkv.shape, B, Hq, Wq, heads, hd)
+        if out is None:
+            out = torch.empty((B * Hq * Wq, heads * hd), device=qkv.device, dtype=torch.bfloat16)
+        L.check(self.lib.ivlm_sam_attention_bf16(self.h, P(qkv), P(rel_pos_h), P(rel_pos_w), P(out), i32(B), i32(heads),
+                                                 i32(Hq), i32(Wq), i32(hd), i64(out.stride(0)), self.stream), "sam_attention")
+        return out
 
     def attn_small(self, q, k, v, heads):
         """q [Bq,Nq,C] (Bq == 1 broadcasts), k/v [B,Nk,C] -> [B,Nq,C]."""

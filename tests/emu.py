@@ -174,6 +174,12 @@ class EmuContext:
         rel_w = _r(torch.einsum("bnhwc,wkc->bnhwk", q, Rw)).reshape(B, heads, S, Wq)
         return rel_h.contiguous(), rel_w.contiguous()
 
+    def sam_attention(self, qkv, rel_pos_h, rel_pos_w, B, heads, Hq, Wq, hd, out=None):
+        rel_h, rel_w = self.sam_relpos(qkv, rel_pos_h, rel_pos_w, B, heads, Hq, Wq, hd)
+        t = qkv.view(B, Hq * Wq, 3, heads, hd)
+        o = self.attention(t[:, :, 0], t[:, :, 1], t[:, :, 2], hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=Hq, kw=Wq)
+        return o.reshape(B * Hq * Wq, heads * hd)
+
     def attn_small(self, q, k, v, heads):
         self.launches += 1
         B, Nk, C = k.shape

@@ -195,6 +195,37 @@ def test_sam_relpos_attention(ctx, Hq, Wq, B):
     assert rel_err(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("Hq,Wq,B,heads", [(64, 64, 2, 2), (14, 14, 5, 2), (14, 14, 50, 16)])
+def test_sam_attention_tcgen05(ctx, Hq, Wq, B, heads):
+    """Fused tcgen05 attention with in-kernel rel-pos tables vs the fp32 statement of image_encoder.py:235-260/:354-392."""
+    hd = 80
+    S = Hq * Wq
+    qkv = rnd(B * S, 3 * heads * hd, seed=60, scale=0.5)
+    rph, rpw = rnd(2 * Hq - 1, hd, seed=61, scale=0.3), rnd(2 * Wq - 1, hd, seed=62, scale=0.3)
+    out = ctx.sam_attention(qkv, rph, rpw, B, heads, Hq, Wq, hd)
+    torch.cuda.synchronize()
+    t = qkv.view(B, S, 3, heads, hd)
+    q, k, v = t[:, :, 0], t[:, :, 1], t[:, :, 2]
+    qf = q.float().permute(0, 2, 1, 3).reshape(B * heads, S, hd)
+    kf = k.float().permute(0, 2, 1, 3).reshape(B * heads, S, hd)
+    vf = v.float().permute(0, 2, 1, 3).reshape(B * heads, S, hd)
+    idx_h = (torch.arange(Hq)[:, None] - torch.arange(Hq)[None, :] + Hq - 1).to(DEV)
+    idx_w = (torch.arange(Wq)[:, None] - torch.arange(Wq)[None, :] + Wq - 1).to(DEV)
+    rq = qf.view(B * heads, Hq, Wq, hd)
+    rh = torch.einsum("bhwc,hkc->bhwk", rq, rph.float()[idx_h]).bfloat16().float()
+    rw = torch.einsum("bhwc,wkc->bhwk", rq, rpw.float()[idx_w]).bfloat16().float()
+    attn = (qf * hd ** -0.5) @ kf.transpose(-1, -2)
+    attn = (attn.view(B * heads, Hq, Wq, Hq, Wq) + rh[..., None] + rw[..., None, :]).view(B * heads, S, S)
+    ref = (attn.softmax(-1) @ vf).view(B, heads, S, hd).permute(0, 2, 1, 3).reshape(B * S, heads * hd)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
+    assert (out.float() - ref).abs().max().item() < 3e-2
+    # and against the first-generation path (separate rel-pos kernel + mma.sync flash attention)
+    rel_h, rel_w = ctx.sam_relpos(qkv, rph, rpw, B, heads, Hq, Wq, hd)
+    old = ctx.attention(q, k, v, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=Hq, kw=Wq).reshape(B * S, heads * hd)
+    assert rel_err(out, old) < 1e-2
+
+
 def test_attn_small(ctx):
     heads = 8
     for (Bq, B, Nq, Nk, Cc) in [(1, 4, 9, 4096, 128), (4, 4, 9, 9, 256), (4, 4, 4096, 9, 128), (2, 2, 9, 4096, 128)]:

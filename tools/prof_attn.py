@@ -1,0 +1,49 @@
+"""GPU-box helper: SAM attention shapes at the bench's chunk size (8 views): fused tcgen05 kernel vs the first-generation
+path (rel-pos kernel + mma.sync flash attention).  Prints ms and TFLOP/s."""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from interactvlm_b200.ops import Context  # noqa: E402
+
+ctx = Context(0)
+heads, hd = 16, 80
+g = torch.Generator(device="cuda").manual_seed(0)
+rnd = lambda *s, sc=1.0: (torch.randn(*s, device="cuda", generator=g) * sc).bfloat16()
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+which = sys.argv[2] if len(sys.argv) > 2 else "both"
+
+
+def timeit(fn):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+for name, B, side in (("global_8views", 8, 64), ("window_8views", 200, 14)):
+    S = side * side
+    qkv = rnd(B * S, 3 * heads * hd, sc=0.5)
+    rph, rpw = rnd(2 * side - 1, hd, sc=0.3), rnd(2 * side - 1, hd, sc=0.3)
+    fl = 4.0 * B * heads * S * S * hd
+    if which in ("both", "new"):
+        ms = timeit(lambda: ctx.sam_attention(qkv, rph, rpw, B, heads, side, side, hd))
+        print(f"{name} fused tcgen05: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    if which in ("both", "old"):
+        t = qkv.view(B, S, 3, heads, hd)
+
+        def old():
+            rel_h, rel_w = ctx.sam_relpos(qkv, rph, rpw, B, heads, side, side, hd)
+            return ctx.attention(t[:, :, 0], t[:, :, 1], t[:, :, 2], hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=side, kw=side)
+
+        ms = timeit(old)
+        print(f"{name} relpos + mma.sync flash: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
