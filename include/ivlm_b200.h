@@ -36,6 +36,8 @@ IVLM_API int ivlm_create(ivlm_handle* out, int device);
 IVLM_API int ivlm_destroy(ivlm_handle h);
 IVLM_API const char* ivlm_last_error(void);
 IVLM_API int ivlm_abi_version(void);
+/* Tuning / A-B switches (integer options): "window_attn_variant" 0 = single-tile window kernel (default), 1 = tiled kernel. */
+IVLM_API int ivlm_set_option(ivlm_handle h, const char* name, int32_t value);
 /* kernels launched through this handle so far (bench.py's "gpu_launches") */
 IVLM_API uint64_t ivlm_launch_count(ivlm_handle h);
 

@@ -39,3 +39,13 @@ extern "C" int ivlm_destroy(ivlm_handle h) {
 }
 
 extern "C" uint64_t ivlm_launch_count(ivlm_handle h) { return h ? h->launches : 0; }
+
+extern "C" int ivlm_set_option(ivlm_handle h, const char* name, int32_t value) {
+    IVLM_REQUIRE(h && name, "set_option: null");
+    if (std::string(name) == "window_attn_variant") {
+        h->window_attn_variant = value;
+        return IVLM_OK;
+    }
+    ivlm::set_error("set_option: unknown option %s", name);
+    return IVLM_ERR_ARG;
+}

@@ -80,6 +80,16 @@ IVLM_DEVINL void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+IVLM_DEVINL void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
 IVLM_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 IVLM_DEVINL float ex2_approx(float x) {
     float y;
@@ -369,6 +379,264 @@ sam_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKVa, const __grid
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ 14x14 windows
+// Window attention has 196 keys: ONE key tile (UMMA N = 208), no online softmax, and so little work per (window, head,
+// query tile) that latency dominates.  This variant is sized for TWO resident CTAs per SM (112 KB shared memory, 256
+// TMEM columns, 160 threads) so that one CTA's TMA / MMA / barrier latencies hide under the other's softmax:
+//   TMEM  [0,32) T_h, [32,64) T_w  ->  [0,208) S (bias-added scores are written back in place)  ->  [0,80) O
+//   smem  Q (20 KB) + K (33 KB) are dead once S is committed: P (52 KB, three 64-key chunks + one 16-key chunk) aliases them.
+constexpr int WN_KEYS = 208, WN_S = 196, WN_KW = 14, WN_THREADS = 160;
+constexpr int WN_KA = WN_KEYS * 128, WN_KB = WN_KEYS * 32;                 // 26624, 6656
+constexpr int WN_OFF_QA = 0, WN_OFF_QB = 16384, WN_OFF_KA = 20480, WN_OFF_KB = WN_OFF_KA + WN_KA;       // 47104
+constexpr int WN_OFF_VA = 54272, WN_OFF_VB = WN_OFF_VA + WN_KA;                                         // 80896
+constexpr int WN_OFF_RHA = 88064, WN_OFF_RHB = WN_OFF_RHA + 4096, WN_OFF_RWA = 93184, WN_OFF_RWB = WN_OFF_RWA + 4096;
+constexpr int WN_OFF_TH = 98304, WN_OFF_TW = WN_OFF_TH + 28 * 256, WN_OFF_BAR = WN_OFF_TW + 28 * 256;  // 112640
+constexpr int WN_OFF_P3 = 49152;                                           // 16-key P chunk (32B-swizzled)
+constexpr int WN_SMEM = WN_OFF_BAR + 256 + 1024;
+static_assert(WN_OFF_KB + WN_KB <= WN_OFF_VA && WN_OFF_VB + WN_KB <= WN_OFF_RHA && WN_OFF_P3 + 4096 <= WN_OFF_VA, "smem map");
+
+template <int C0, int N>
+IVLM_DEVINL float win_scores(uint32_t (&raw)[N], const float (&rh)[WN_KW], const float (&rw)[WN_KW], float scale_log2, float mx) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int k = C0 + i;  // compile-time after unrolling
+        float x;
+        if (k < WN_S) {
+            x = fmaf(__uint_as_float(raw[i]), scale_log2, rh[k / WN_KW] + rw[k % WN_KW]);
+            mx = fmaxf(mx, x);
+        } else {
+            x = -INFINITY;
+        }
+        raw[i] = __float_as_uint(x);
+    }
+    return mx;
+}
+
+__global__ void __launch_bounds__(WN_THREADS, 2)
+sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+                               const __grid_constant__ CUtensorMap tmKVa, const __grid_constant__ CUtensorMap tmKVb,
+                               const __grid_constant__ CUtensorMap tmRHa, const __grid_constant__ CUtensorMap tmRHb,
+                               const __grid_constant__ CUtensorMap tmRWa, const __grid_constant__ CUtensorMap tmRWb,
+                               const SamAttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    bf16* th_s = reinterpret_cast<bf16*>(smem + WN_OFF_TH);  // [28 idx][128 rows]
+    bf16* tw_s = reinterpret_cast<bf16*>(smem + WN_OFF_TW);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WN_OFF_BAR);
+    uint64_t *qt_full = bars, *k_full = bars + 1, *v_full = bars + 2, *t_full = bars + 3, *t_read = bars + 4,
+             *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+    const int E = p.heads * AT_HD;
+    const int row_base = b * WN_S;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_init(qt_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(t_full, 1);
+            mbar_init(t_read, 4); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ control: TMA + MMA issue
+        if (lane == 0) {
+            mbar_arrive_expect_tx(qt_full, 20480 + 2 * (4096 + 1024));
+            tma_load_2d(smem + WN_OFF_QA, &tmQa, qt_full, h * AT_HD, row_base + q0);
+            tma_load_2d(smem + WN_OFF_QB, &tmQb, qt_full, h * AT_HD + 64, row_base + q0);
+            tma_load_2d(smem + WN_OFF_RHA, &tmRHa, qt_full, 0, 0);
+            tma_load_2d(smem + WN_OFF_RHB, &tmRHb, qt_full, 64, 0);
+            tma_load_2d(smem + WN_OFF_RWA, &tmRWa, qt_full, 0, 0);
+            tma_load_2d(smem + WN_OFF_RWB, &tmRWb, qt_full, 64, 0);
+            mbar_arrive_expect_tx(k_full, WN_KA + WN_KB);
+            tma_load_2d(smem + WN_OFF_KA, &tmKVa, k_full, E + h * AT_HD, row_base);
+            tma_load_2d(smem + WN_OFF_KB, &tmKVb, k_full, E + h * AT_HD + 64, row_base);
+            mbar_arrive_expect_tx(v_full, WN_KA + WN_KB);
+            tma_load_2d(smem + WN_OFF_VA, &tmKVa, v_full, 2 * E + h * AT_HD, row_base);
+            tma_load_2d(smem + WN_OFF_VB, &tmKVb, v_full, 2 * E + h * AT_HD + 64, row_base);
+
+            const uint64_t dqa = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_QA));
+            const uint64_t dqb = umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_QB));
+            mbar_wait(qt_full, 0);
+            tc_fence_after();
+            {   // T_h -> cols [0,32), T_w -> cols [32,64): Q . table^T, N = 32 (27 table rows + zero fill)
+                constexpr uint32_t idesc = umma_idesc_bf16(128, 32);
+                const uint64_t dh = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_RHA));
+                const uint64_t dw = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_RWA));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dqa + 2 * k, dh + 2 * k, idesc, k > 0 ? 1u : 0u);
+                umma_bf16(tmem_base, dqb, umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_RHB)), idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 32, dqa + 2 * k, dw + 2 * k, idesc, k > 0 ? 1u : 0u);
+                umma_bf16(tmem_base + 32, dqb, umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_RWB)), idesc, 1u);
+                umma_commit(t_full);
+            }
+            mbar_wait(k_full, 0);
+            mbar_wait(t_read, 0);  // the softmax warps have taken T_h / T_w out of the columns S overwrites
+            tc_fence_after();
+            {   // S = Q K^T, N = 208
+                constexpr uint32_t idesc = umma_idesc_bf16(128, WN_KEYS);
+                const uint64_t dk = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_KA));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dqa + 2 * k, dk + 2 * k, idesc, k > 0 ? 1u : 0u);
+                umma_bf16(tmem_base, dqb, umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_KB)), idesc, 1u);
+                umma_commit(s_full);
+            }
+            mbar_wait(v_full, 0);
+            mbar_wait(p_full, 0);
+            tc_fence_after();
+            {   // O = P V over 13 key steps of 16
+                constexpr uint32_t idesc64 = umma_idesc_bf16_bmn(128, 64), idesc16 = umma_idesc_bf16_bmn(128, 16);
+#pragma unroll
+                for (int ks = 0; ks < WN_KEYS / 16; ++ks) {
+                    const uint64_t dp = ks < 12 ? umma_desc_sw128_kmajor(smem_u32(smem + (ks >> 2) * 16384)) + 2 * (ks & 3)
+                                                : umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_P3));
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
+                    umma_bf16(tmem_base, dp, umma_desc_sw128_mnmajor(smem_u32(smem + WN_OFF_VA + ks * 2048)), idesc64, acc);
+                    umma_bf16(tmem_base + 64, dp, umma_desc_sw32_mnmajor(smem_u32(smem + WN_OFF_VB + ks * 512)), idesc16, acc);
+                }
+                umma_commit(o_full);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps (quadrant == warp)
+        const int r = warp * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+        const int qtok = q0 + r;
+        const bool q_ok = qtok < WN_S;
+        const int qy = q_ok ? qtok / WN_KW : 0, qx = q_ok ? qtok - (qtok / WN_KW) * WN_KW : 0;
+        mbar_wait(t_full, 0);
+        tc_fence_after();
+        {
+            uint32_t th[32], tw[32];
+            tmem_ld_32x32(lane_addr, th);
+            tmem_ld_32x32(lane_addr + 32, tw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 28; ++i) {
+                th_s[i * AT_BQ + r] = __float2bfloat16_rn(__uint_as_float(th[i]));
+                tw_s[i * AT_BQ + r] = __float2bfloat16_rn(__uint_as_float(tw[i]));
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_read);
+        float rh[WN_KW], rw[WN_KW];  // this row's rel_h[ky], rel_w[kx] (bf16 values), pre-multiplied by log2(e)
+#pragma unroll
+        for (int i = 0; i < WN_KW; ++i) {
+            rh[i] = __bfloat162float(th_s[(qy - i + WN_KW - 1) * AT_BQ + r]) * AT_LOG2E;
+            rw[i] = __bfloat162float(tw_s[(qx - i + WN_KW - 1) * AT_BQ + r]) * AT_LOG2E;
+        }
+        mbar_wait(s_full, 0);
+        tc_fence_after();
+        // ---- pass 1: x = s*scale + bias (log2 domain) written back in place, row max
+        float mx = -INFINITY;
+#define WIN_PASS1(C0)                                                               \
+        {                                                                           \
+            uint32_t raw[32];                                                       \
+            tmem_ld_32x32(lane_addr + C0, raw);                                     \
+            tmem_ld_wait();                                                         \
+            mx = win_scores<C0, 32>(raw, rh, rw, p.scale_log2, mx);                 \
+            tmem_st_32x32(lane_addr + C0, raw);                                     \
+        }
+        WIN_PASS1(0) WIN_PASS1(32) WIN_PASS1(64) WIN_PASS1(96) WIN_PASS1(128) WIN_PASS1(160)
+#undef WIN_PASS1
+        {
+            uint32_t raw[16];
+            tmem_ld_32x16(lane_addr + 192, raw);
+            tmem_ld_wait();
+            mx = win_scores<192, 16>(raw, rh, rw, p.scale_log2, mx);
+            tmem_st_32x16(lane_addr + 192, raw);
+        }
+        tmem_st_wait();
+        // ---- pass 2: p = 2^(x - max) -> bf16 -> swizzled P (aliases the dead Q / K tiles)
+        float sum = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < 192; c0 += 32) {
+            uint32_t raw[32];
+            tmem_ld_32x32(lane_addr + c0, raw);
+            tmem_ld_wait();
+            uint8_t* row = smem + (c0 >> 6) * 16384 + r * 128;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e]) - mx);
+                    const float p1 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e + 1]) - mx);
+                    sum += p0 + p1;
+                    pk[e] = pack_bf16x2(p0, p1);
+                }
+                const int c16 = ((c0 & 63) >> 3) + j8;
+                *reinterpret_cast<uint4*>(row + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+        {
+            uint32_t raw[16];
+            tmem_ld_32x16(lane_addr + 192, raw);
+            tmem_ld_wait();
+            uint8_t* row = smem + WN_OFF_P3 + r * 32;
+#pragma unroll
+            for (int j8 = 0; j8 < 2; ++j8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e]) - mx);
+                    const float p1 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e + 1]) - mx);
+                    sum += p0 + p1;
+                    pk[e] = pack_bf16x2(p0, p1);
+                }
+                *reinterpret_cast<uint4*>(row + ((j8 ^ ((r >> 2) & 1)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // ---- epilogue
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        bf16* orow = p.out + (long long)(row_base + qtok) * p.out_ld + h * AT_HD;
+#pragma unroll
+        for (int c0 = 0; c0 < AT_HD; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld_32x16(lane_addr + c0, o);
+            tmem_ld_wait();
+            if (q_ok) {
+                uint4 u0, u1;
+                u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+                u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+                u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+                u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+                u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+                reinterpret_cast<uint4*>(orow + c0)[0] = u0;
+                reinterpret_cast<uint4*>(orow + c0)[1] = u1;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
 }  // namespace ivlm
 
 using namespace ivlm;
@@ -403,12 +671,23 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
     if (!attr_set) {
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_window_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WN_SMEM));
         attr_set = true;
     }
-    if (Wq == 64)
+    if (Wq == 64) {
         sam_attn_tcgen05_kernel<64><<<grid, AT_THREADS, AT_SMEM, stream>>>(*qa, *qb, *rha, *rhb, *rwa, *rwb, p);
-    else
+    } else if (h->window_attn_variant == 0) {
+        const CUtensorMap *kva, *kvb, *wha, *whb, *wwa, *wwb;
+        IVLM_TRY(get_tmap_bf16_ex(h, qkv, rows, 3 * (uint64_t)E, 3 * (uint64_t)E, WN_KEYS, 64, 128, &kva));
+        IVLM_TRY(get_tmap_bf16_ex(h, qkv, rows, 3 * (uint64_t)E, 3 * (uint64_t)E, WN_KEYS, 16, 32, &kvb));
+        IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_h, 2 * Hq - 1, hd, hd, 32, 64, 128, &wha));
+        IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_h, 2 * Hq - 1, hd, hd, 32, 16, 32, &whb));
+        IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_w, 2 * Wq - 1, hd, hd, 32, 64, 128, &wwa));
+        IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_w, 2 * Wq - 1, hd, hd, 32, 16, 32, &wwb));
+        sam_attn_window_tcgen05_kernel<<<grid, WN_THREADS, WN_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *wha, *whb, *wwa, *wwb, p);
+    } else {
         sam_attn_tcgen05_kernel<14><<<grid, AT_THREADS, AT_SMEM, stream>>>(*qa, *qb, *rha, *rhb, *rwa, *rwb, p);
+    }
     h->launches++;
     IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;

@@ -75,6 +75,7 @@ struct ivlm_ctx {
     int device = 0;
     int num_sms = 148;
     uint64_t launches = 0;  // kernels launched through this handle (bench "gpu_launches")
+    int window_attn_variant = 0;  // 0: single-tile 2-CTA/SM window kernel, 1: the general tiled kernel (A/B switch)
     std::unordered_map<ivlm::TmapKey, CUtensorMap, ivlm::TmapKeyHash> tmaps;
     std::unordered_map<std::string, ivlm::Weight> weights;
     // caller-provided scratch (bump allocated inside stage drivers)

@@ -54,6 +54,9 @@ class Context:
     def stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_option(self, name: str, value: int):
+        L.check(self.lib.ivlm_set_option(self.h, name.encode(), i32(value)), "set_option")
+
     def launch_count(self) -> int:
         return int(self.lib.ivlm_launch_count(self.h))
 
