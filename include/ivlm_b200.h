@@ -36,6 +36,9 @@ IVLM_API int ivlm_create(ivlm_handle* out, int device);
 IVLM_API int ivlm_destroy(ivlm_handle h);
 IVLM_API const char* ivlm_last_error(void);
 IVLM_API int ivlm_abi_version(void);
+/* Caller-owned scratch in device memory (>= 1 MiB; 32 MiB covers every shape on the path).  With a workspace bound,
+ * weight-streaming GEMMs (small token counts) split K across CTAs and reduce the partials in-kernel, deterministically. */
+IVLM_API int ivlm_set_workspace(ivlm_handle h, void* ptr, size_t bytes, void* stream);
 /* Tuning / A-B switches (integer options): "window_attn_variant" 0 = single-tile window kernel (default), 1 = tiled kernel. */
 IVLM_API int ivlm_set_option(ivlm_handle h, const char* name, int32_t value);
 /* kernels launched through this handle so far (bench.py's "gpu_launches") */
@@ -65,7 +68,8 @@ typedef struct ivlm_gemm_args {
     int32_t M, N, K;
     int32_t act;          /* ivlm_act */
     int32_t out_dtype;    /* IVLM_BF16 or IVLM_F32 */
-    int32_t k_splits;     /* >1: split-K, atomically accumulates raw fp32 into a pre-zeroed `out` */
+    int32_t k_splits;     /* >1: split-K, atomically accumulates raw fp32 into a pre-zeroed `out`; 0: let the library decide
+                             (fused deterministic split-K when a workspace is bound); 1: never split */
     int32_t force_swap;   /* 0 auto, 1 weights-as-128-row-operand, -1 never */
     int32_t no_round;     /* 1: skip the intermediate bf16 roundings */
     int32_t res_row_mod;  /* >0: residual row = out_row % res_row_mod (broadcast tables, e.g. pos_embed) */

@@ -49,3 +49,12 @@ extern "C" int ivlm_set_option(ivlm_handle h, const char* name, int32_t value) {
     ivlm::set_error("set_option: unknown option %s", name);
     return IVLM_ERR_ARG;
 }
+
+extern "C" int ivlm_set_workspace(ivlm_handle h, void* ptr, size_t bytes, void* stream) {
+    IVLM_REQUIRE(h, "set_workspace: null handle");
+    IVLM_REQUIRE(ptr == nullptr || bytes >= (1u << 20), "set_workspace: need at least 1 MiB");
+    h->ws = reinterpret_cast<char*>(ptr);
+    h->ws_bytes = ptr ? bytes : 0;
+    if (ptr) IVLM_CHECK_CUDA(cudaMemsetAsync(ptr, 0, ivlm::IVLM_WS_COUNTER_BYTES, reinterpret_cast<cudaStream_t>(stream)));
+    return IVLM_OK;
+}

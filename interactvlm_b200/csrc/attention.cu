@@ -257,10 +257,10 @@ __global__ void sam_relpos_kernel(const bf16* __restrict__ qkv, const bf16* __re
 
 // ------------------------------------------------------------------------------------------------ paged decode
 // CTA per (b, head), 8 warps. HF LlamaAttention eager numerics (transformers 4.31): scores = bf16(bf16(q.k)/sqrt(hd)),
-// softmax in fp32 cast to bf16, bf16 P.V.  HBM-bound: every K/V row of the head (HD*2 bytes, contiguous) is read
-// once by one warp with 8-byte (HD=128) loads; keys are dealt to warps in groups of 4 so that four independent row
-// loads are in flight per warp before the first shuffle reduction.
-constexpr int DEC_WARPS = 8;
+// softmax in fp32 cast to bf16, bf16 P.V.  HBM-bound: every K/V row of the head (HD*2 bytes, contiguous) is read once.
+// A row is covered by HD/8 lanes with 16-byte loads, so one warp-wide load instruction fetches 32/(HD/8) rows and each
+// warp keeps DEC_UNROLL such instructions in flight before the first shuffle (>= 2 KB outstanding per warp).
+constexpr int DEC_WARPS = 8, DEC_UNROLL = 8, DEC_MAX_PAGES = 256;
 template <int HD>
 __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const bf16* __restrict__ q,
                                                                           const bf16* __restrict__ k_cache,
@@ -271,65 +271,58 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
                                                                           int max_pages, float inv_scale) {
     extern __shared__ float sc[];  // [seq_len] scores, then probabilities
     __shared__ float red[DEC_WARPS];
-    __shared__ float part[DEC_WARPS][HD];
+    constexpr int LPR = HD / 8;        // lanes per row (16 for HD=128, 8 for HD=64)
+    constexpr int RPI = 32 / LPR;      // rows per warp-wide load instruction
+    constexpr int GROUP = RPI * DEC_UNROLL;  // rows per warp iteration
+    __shared__ float part[DEC_WARPS * RPI][HD];
     const int h = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / LPR, li = lane % LPR;  // which row of the instruction, which 8-element slice of the row
     const int len = seq_lens[b];
-    const int* bt = block_table + (long long)b * max_pages;
-    constexpr int EPL = HD / 32;  // elements per lane (4 -> 8-byte loads, 2 -> 4-byte loads)
-    float qr[EPL];
+    __shared__ int bt[DEC_MAX_PAGES];  // this sample's block table: keeps the page lookup off the global-load latency chain
+    for (int i = threadIdx.x; i < max_pages; i += DEC_WARPS * 32) bt[i] = block_table[(long long)b * max_pages + i];
+    __syncthreads();
+    float qr[8];
     {
-        const bf16* qp = q + ((long long)b * H + h) * HD + lane * EPL;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) qr[e] = __bfloat162float(qp[e]);
+        const uint4 u = *reinterpret_cast<const uint4*>(q + ((long long)b * H + h) * HD + li * 8);
+        const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y), d = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+        qr[0] = a.x; qr[1] = a.y; qr[2] = c.x; qr[3] = c.y; qr[4] = d.x; qr[5] = d.y; qr[6] = e.x; qr[7] = e.y;
     }
     auto row_ptr = [&](const bf16* cache, int kpos) {
         const long long slot = (long long)bt[kpos / page] * page + (kpos % page);
-        return cache + (slot * H + h) * HD + lane * EPL;
-    };
-    auto load_row = [&](const bf16* p, float (&v)[EPL]) {
-        if constexpr (EPL == 4) {
-            const uint2 u = *reinterpret_cast<const uint2*>(p);
-            const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
-            v[0] = a.x; v[1] = a.y; v[2] = c.x; v[3] = c.y;
-        } else {
-            const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p));
-            v[0] = a.x; v[1] = a.y;
-        }
+        return reinterpret_cast<const uint4*>(cache + (slot * H + h) * HD + li * 8);
     };
     // ---- phase 1: scores
     float lmax = -INFINITY;
-    for (int k0 = warp * 4; k0 < len; k0 += DEC_WARPS * 4) {
-        float kv[4][EPL];
+    for (int k0 = warp * GROUP; k0 < len; k0 += DEC_WARPS * GROUP) {
+        uint4 kv[DEC_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (k0 + u < len) load_row(row_ptr(k_cache, k0 + u), kv[u]);
-            else {
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) kv[u][e] = 0.f;
-            }
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const int kpos = k0 + u * RPI + sub;
+            kv[u] = kpos < len ? *row_ptr(k_cache, kpos) : make_uint4(0, 0, 0, 0);
         }
-        float d[4];
+        float d[DEC_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            d[u] = 0.f;
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) d[u] += qr[e] * kv[u][e];
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const float2 a = unpack_bf16x2(kv[u].x), c = unpack_bf16x2(kv[u].y), e = unpack_bf16x2(kv[u].z), f = unpack_bf16x2(kv[u].w);
+            d[u] = qr[0] * a.x + qr[1] * a.y + qr[2] * c.x + qr[3] * c.y + qr[4] * e.x + qr[5] * e.y + qr[6] * f.x + qr[7] * f.y;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = LPR / 2; o > 0; o >>= 1) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+            for (int u = 0; u < DEC_UNROLL; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (k0 + u < len) {
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const int kpos = k0 + u * RPI + sub;
+            if (kpos < len) {
                 const float x = bf16_round(bf16_round(d[u]) / inv_scale);
-                if (lane == 0) sc[k0 + u] = x;
+                if (li == 0) sc[kpos] = x;
                 lmax = fmaxf(lmax, x);
             }
         }
     }
+    lmax = warp_max(lmax);
     if (lane == 0) red[warp] = lmax;
     __syncthreads();
     float gmax = red[0];
@@ -350,36 +343,34 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
 #pragma unroll
     for (int w = 0; w < DEC_WARPS; ++w) tot += red[w];
     const float inv = 1.f / tot;
-    // ---- phase 3: P.V, each warp accumulates its keys, partials reduced through shared memory
-    float acc[EPL];
+    // ---- phase 3: P.V; every (warp, sub-row) slot accumulates its keys, partials reduced through shared memory
+    float acc[8];
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-    for (int k0 = warp * 4; k0 < len; k0 += DEC_WARPS * 4) {
-        float vv[4][EPL];
-        float pr[4];
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int k0 = warp * GROUP; k0 < len; k0 += DEC_WARPS * GROUP) {
+        uint4 vv[DEC_UNROLL];
+        float pr[DEC_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (k0 + u < len) {
-                load_row(row_ptr(v_cache, k0 + u), vv[u]);
-                pr[u] = bf16_round(sc[k0 + u] * inv);
-            } else {
-                pr[u] = 0.f;
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) vv[u][e] = 0.f;
-            }
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const int kpos = k0 + u * RPI + sub;
+            const bool ok = kpos < len;
+            vv[u] = ok ? *row_ptr(v_cache, kpos) : make_uint4(0, 0, 0, 0);
+            pr[u] = ok ? bf16_round(sc[kpos] * inv) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) acc[e] += pr[u] * vv[u][e];
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const float2 a = unpack_bf16x2(vv[u].x), c = unpack_bf16x2(vv[u].y), e = unpack_bf16x2(vv[u].z), f = unpack_bf16x2(vv[u].w);
+            acc[0] += pr[u] * a.x; acc[1] += pr[u] * a.y; acc[2] += pr[u] * c.x; acc[3] += pr[u] * c.y;
+            acc[4] += pr[u] * e.x; acc[5] += pr[u] * e.y; acc[6] += pr[u] * f.x; acc[7] += pr[u] * f.y;
+        }
     }
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) part[warp][lane * EPL + e] = acc[e];
+    for (int e = 0; e < 8; ++e) part[warp * RPI + sub][li * 8 + e] = acc[e];
     __syncthreads();
     for (int d = threadIdx.x; d < HD; d += DEC_WARPS * 32) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < DEC_WARPS; ++w) s += part[w][d];
+        for (int w = 0; w < DEC_WARPS * RPI; ++w) s += part[w][d];
         out[((long long)b * H + h) * HD + d] = __float2bfloat16_rn(s);
     }
 }
@@ -628,6 +619,7 @@ extern "C" int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, co
     const size_t smem = (size_t)page_size * max_pages * sizeof(float);
     IVLM_REQUIRE(smem <= 160 * 1024, "decode_attention: max context %d too long for the score buffer",
                  page_size * max_pages);
+    IVLM_REQUIRE(max_pages <= DEC_MAX_PAGES, "decode_attention: more than %d pages per sequence", DEC_MAX_PAGES);
     const float inv_scale = 1.0f / scale;  // reference divides by sqrt(hd)
     dim3 grid(H, B);
     if (hd == 128) {

@@ -44,6 +44,9 @@ struct GemmParams {
     int out_f32;      // out is fp32 (else bf16)
     int atomic;       // split-K: red.add.f32 into out (fp32), no bias/act/res
     int round_steps;  // mirror torch bf16 op boundaries: round after bias, after act, after residual
+    int fused_split;  // split-K with in-kernel reduction: partial tiles -> workspace, the last CTA of a tile sums them
+    float* ws_partial;  // [tiles * k_splits][BM][BN] fp32
+    int* ws_counter;    // [tiles], zero between launches (the reducing CTA resets its counter)
     int n_fastest;    // tile order (see tile_coords)
     int staged;       // bf16 row-major output through the shared-memory staged epilogue
 };
@@ -119,6 +122,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint64_t* tfull_bar = bars + 2 * STAGES;
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    volatile int* split_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -279,28 +283,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (p.bias != nullptr && p.bias_on_rows && r_ok) bias_r = __bfloat162float(p.bias[r]);
 
             constexpr int CH = BN < 32 ? BN : 32;  // columns per TMEM load
-#pragma unroll 1
-            for (int c0 = chalf * CH; c0 < BN; c0 += 2 * CH) {
-                float v[CH];
-                {
-                    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN + c0);
-                    if constexpr (CH == 32) {
-                        uint32_t raw[32];
-                        tmem_ld_32x32(taddr, raw);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                    } else {
-                        uint32_t raw[16];
-                        tmem_ld_32x16(taddr, raw);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-                    }
-                }
+            // bias -> act -> residual -> store for one chunk of CH accumulator columns held in v
+            auto finish_chunk = [&](float (&v)[CH], int c0) {
                 const int cbase = n0 + c0;
-                if (!row_live || cbase >= p.N) continue;
-
+                if (!row_live || cbase >= p.N) return;
                 if (p.atomic) {
                     float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
@@ -308,7 +294,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         const int c = cbase + j;
                         if (c < p.N) atomicAdd(o + (long long)orow * p.out_rs + (long long)c * p.out_cs, v[j]);
                     }
-                    continue;
+                    return;
                 }
                 // bias -> act -> residual, rounding like the eager bf16 reference at each op boundary
 #pragma unroll
@@ -389,10 +375,73 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         else reinterpret_cast<bf16*>(p.out)[oi] = __float2bfloat16_rn(x);
                     }
                 }
+            };
+            const int ks_unit = u % p.k_splits;
+            float* my_part = p.ws_partial + ((size_t)(t * p.k_splits + ks_unit) * BM + quad * 32 + lane) * BN;
+#pragma unroll 1
+            for (int c0 = chalf * CH; c0 < BN; c0 += 2 * CH) {
+                float v[CH];
+                {
+                    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN + c0);
+                    if constexpr (CH == 32) {
+                        uint32_t raw[32];
+                        tmem_ld_32x32(taddr, raw);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                    } else {
+                        uint32_t raw[16];
+                        tmem_ld_32x16(taddr, raw);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+                    }
+                }
+                if (p.fused_split) {
+                    // raw fp32 partial of this K split (64 contiguous bytes or more per thread)
+#pragma unroll
+                    for (int j = 0; j < CH; j += 4)
+                        *reinterpret_cast<float4*>(my_part + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    continue;
+                }
+                finish_chunk(v, c0);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (p.fused_split) {
+                // publish the partial, count arrivals; the CTA that completes the tile reduces all splits in split
+                // order (deterministic) and runs the normal epilogue on the sum
+                __threadfence();
+                named_bar_sync(1, EPI_THREADS);
+                if (threadIdx.x == EPI_WARP0 * 32) {
+                    const int old = atomicAdd(p.ws_counter + t, 1);
+                    const int last = old == p.k_splits - 1;
+                    if (last) p.ws_counter[t] = 0;
+                    *split_flag = last;
+                }
+                named_bar_sync(1, EPI_THREADS);
+                if (*split_flag) {
+                    __threadfence();
+                    const float* base = p.ws_partial + ((size_t)t * p.k_splits * BM + quad * 32 + lane) * BN;
+#pragma unroll 1
+                    for (int c0 = chalf * CH; c0 < BN; c0 += 2 * CH) {
+                        float v[CH];
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = 0.f;
+                        for (int sp = 0; sp < p.k_splits; ++sp) {
+                            const float* src = base + (size_t)sp * BM * BN + c0;
+#pragma unroll
+                            for (int j = 0; j < CH; j += 4) {
+                                const float4 f = __ldcg(reinterpret_cast<const float4*>(src + j));
+                                v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+                            }
+                        }
+                        finish_chunk(v, c0);
+                    }
+                }
+                named_bar_sync(1, EPI_THREADS);  // split_flag is reused by the next unit
+            }
         }
     }
 
@@ -499,6 +548,9 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
     IVLM_REQUIRE(h && a, "null handle/args");
     IVLM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
     IVLM_REQUIRE(a->K % 8 == 0, "gemm: K=%d must be a multiple of 8", a->K);
+    // k_splits > 1: caller-managed split-K (atomic fp32 accumulation into a pre-zeroed `out`, finalize separately).
+    // k_splits == 0/1 with a workspace bound: the library may split K itself (fused, deterministic) for
+    // weight-streaming shapes that would otherwise occupy only a fraction of the SMs.
     const bool split = a->k_splits > 1;
     IVLM_REQUIRE(!split || (a->out_dtype == IVLM_F32 && !a->bias && !a->residual && a->act == 0),
                  "gemm: split-K accumulates raw fp32 (no bias/act/residual)");
@@ -530,6 +582,28 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
     p.num_n_tiles = (p.N + bn - 1) / bn;
     p.k_blocks = (p.K + BK - 1) / BK;
     p.k_splits = split ? a->k_splits : 1;
+    p.fused_split = 0;
+    if (!split && swap && h->ws != nullptr && a->k_splits == 0) {
+        const int tiles = p.num_m_tiles * p.num_n_tiles;
+        // cost in k-block units: waves x (k-blocks per unit + ~6 k-blocks of pipeline fill / drain / reduce per unit)
+        int best = 1;
+        auto cost_of = [&](int sp) {
+            return (double)((tiles * sp + h->num_sms - 1) / h->num_sms) * ((double)p.k_blocks / sp + 6.0);
+        };
+        double best_cost = cost_of(1);
+        for (int sp = 2; sp <= 8; ++sp) {
+            if (p.k_blocks / sp < 8) break;
+            const double cost = cost_of(sp);
+            if (cost < best_cost * 0.9) { best_cost = cost; best = sp; }
+        }
+        const size_t need = (size_t)tiles * best * BM * bn * sizeof(float) + (size_t)tiles * sizeof(int) + 256;
+        if (best > 1 && need <= h->ws_bytes - IVLM_WS_COUNTER_BYTES && (size_t)tiles * sizeof(int) <= IVLM_WS_COUNTER_BYTES) {
+            p.k_splits = best;
+            p.fused_split = 1;
+            p.ws_counter = reinterpret_cast<int*>(h->ws);
+            p.ws_partial = reinterpret_cast<float*>(h->ws + IVLM_WS_COUNTER_BYTES);
+        }
+    }
     if (p.k_splits > p.k_blocks) p.k_splits = p.k_blocks;
     p.k_blocks_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
     p.k_splits = (p.k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;  // no empty splits

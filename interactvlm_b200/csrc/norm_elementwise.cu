@@ -91,6 +91,48 @@ __global__ void rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
     }
 }
 
+// Few rows (decode steps: one row per sample): one CTA of 256 threads per row instead of one warp, so the row is
+// covered by a single pass of 16-byte loads per thread and the kernel sits at the launch floor.
+__global__ void __launch_bounds__(256) rmsnorm_row_cta_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                              const bf16* __restrict__ gamma, int D, float eps) {
+    __shared__ float red[8];
+    const long long row = blockIdx.x;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
+    const int nvec = D >> 3;
+    constexpr int MAXV = 4;  // D <= 8192
+    uint4 q[MAXV];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int i = threadIdx.x + k * 256;
+        q[k] = i < nvec ? xr[i] : make_uint4(0, 0, 0, 0);
+        float2 a = unpack_bf16x2(q[k].x), b = unpack_bf16x2(q[k].y), c = unpack_bf16x2(q[k].z), d = unpack_bf16x2(q[k].w);
+        ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float rstd = rsqrtf(tot / (float)D + eps);
+    const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
+    uint4* yr = reinterpret_cast<uint4*>(y + row * D);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i >= nvec) break;
+        const uint4 g = g4[i];
+        uint32_t xi[4] = {q[k].x, q[k].y, q[k].z, q[k].w}, gi[4] = {g.x, g.y, g.z, g.w}, o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 xv = unpack_bf16x2(xi[j]), gv = unpack_bf16x2(gi[j]);
+            o[j] = pack_bf16x2(gv.x * bf16_round(xv.x * rstd), gv.y * bf16_round(xv.y * rstd));
+        }
+        yr[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ elementwise
 __global__ void add_bcast_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
                                  long long nvec, long long pvec) {
@@ -355,9 +397,13 @@ extern "C" int ivlm_layernorm_bf16(ivlm_handle h, const void* x, void* y, const 
 extern "C" int ivlm_rmsnorm_bf16(ivlm_handle h, const void* x, void* y, const void* gamma, int64_t rows, int32_t D,
                                  float eps, void* stream) {
     IVLM_REQUIRE(h && D % 8 == 0 && rows > 0, "rmsnorm: D=%d must be a multiple of 8, rows>0", D);
-    const int wpb = 8;
-    rmsnorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, STREAM>>>((const bf16*)x, (bf16*)y,
-                                                                                (const bf16*)gamma, rows, D, eps);
+    if (rows <= 4 * h->num_sms && D <= 8192) {
+        rmsnorm_row_cta_kernel<<<(unsigned)rows, 256, 0, STREAM>>>((const bf16*)x, (bf16*)y, (const bf16*)gamma, D, eps);
+    } else {
+        const int wpb = 8;
+        rmsnorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, STREAM>>>((const bf16*)x, (bf16*)y,
+                                                                                    (const bf16*)gamma, rows, D, eps);
+    }
     DONE();
 }
 extern "C" int ivlm_add_bcast_bf16(ivlm_handle h, const void* a, const void* b, void* out, int64_t n, int64_t period,

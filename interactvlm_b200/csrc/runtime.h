@@ -39,6 +39,10 @@ void set_error(const char* fmt, ...);
         if (_s != IVLM_OK) return _s;                                                         \
     } while (0)
 
+// Layout of the caller-provided workspace: [0, IVLM_WS_COUNTER_BYTES) int tile counters (zeroed by ivlm_set_workspace,
+// self-resetting), then fp32 split-K partial tiles.
+constexpr size_t IVLM_WS_COUNTER_BYTES = 65536;
+
 struct TmapKey {
     const void* ptr;
     uint64_t rows, cols, ld;

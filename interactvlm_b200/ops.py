@@ -38,6 +38,9 @@ class Context:
         torch.cuda.set_device(self.device)
         L.check(self.lib.ivlm_create(C.byref(h), i32(self.device.index)), "ivlm_create")
         self.h = h
+        self.workspace = torch.empty(32 << 20, device=self.device, dtype=torch.uint8)
+        L.check(self.lib.ivlm_set_workspace(self.h, P(self.workspace), C.c_size_t(self.workspace.numel()), self.stream),
+                "set_workspace")
 
     def close(self):
         if getattr(self, "h", None):
@@ -110,7 +113,7 @@ class Context:
 
     # ------------------------------------------------------------------ dense
     def gemm(self, a, w, bias=None, act=ACT_NONE, residual=None, out=None, out_dtype=torch.bfloat16, row_map=None,
-             out_rows=None, k_splits=1, force_swap=0, no_round=False, res_row_mod=0):
+             out_rows=None, k_splits=0, force_swap=0, no_round=False, res_row_mod=0):
         """out = act(a @ w.T + bias) + residual.  a [M,K], w [N,K] bf16 (last dim contiguous)."""
         _bf16(a, "a"); _bf16(w, "w")
         assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)

@@ -1,0 +1,76 @@
+"""GPU-box helper: per-op time of one LLaMA-13B decode layer at batch 8 inside CUDA graphs (no launch gaps from Python),
+weights rotated over 4 copies so that L2 cannot hold them.  Prints us per op and the achieved HBM GB/s."""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from interactvlm_b200.ops import Context  # noqa: E402
+
+ctx = Context(0)
+B, D, F, H, hd, L = 8, 5120, 13824, 40, 128, 340
+g = torch.Generator(device="cuda").manual_seed(0)
+rnd = lambda *s, sc=1.0: (torch.randn(*s, device="cuda", generator=g) * sc).bfloat16()
+NW = 4
+wqkv = [rnd(3 * D, D, sc=0.02) for _ in range(NW)]
+wo = [rnd(D, D, sc=0.02) for _ in range(NW)]
+wgu = [rnd(2 * F, D, sc=0.02) for _ in range(NW)]
+wd = [rnd(D, F, sc=0.02) for _ in range(NW)]
+x, xf, gam = rnd(B, D), rnd(B, F), rnd(D)
+gu = rnd(B, 2 * F)
+qkv = rnd(B, 3 * D)
+page, pages = 16, 24
+kc = [rnd(B * pages * page, H, hd) for _ in range(NW)]
+vc = [rnd(B * pages * page, H, hd) for _ in range(NW)]
+bt = torch.arange(B * pages, dtype=torch.int32, device="cuda").view(B, pages)
+sl = torch.full((B,), L, dtype=torch.int32, device="cuda")
+pos = torch.full((B,), L - 1, dtype=torch.int32, device="cuda")
+slot = (torch.arange(B, dtype=torch.int32, device="cuda") * pages * page + L - 1).contiguous()
+inv = 1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))
+fr = torch.outer(torch.arange(1024).float(), inv)
+emb = torch.cat((fr, fr), -1)
+cos_t, sin_t = emb.cos().bfloat16().cuda(), emb.sin().bfloat16().cuda()
+q = rnd(B, D)
+REP = 40
+
+
+def graph_time(fn):
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for i in range(REP):
+            fn(i)
+    gr.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(5):
+        gr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 5 / REP * 1e3  # us per op
+
+
+ops = {
+    "gemm_qkv": (lambda i: ctx.gemm(x, wqkv[i % NW]), 3 * D * D * 2),
+    "gemm_o": (lambda i: ctx.gemm(x, wo[i % NW], residual=x), D * D * 2),
+    "gemm_gateup": (lambda i: ctx.gemm(x, wgu[i % NW]), 2 * F * D * 2),
+    "gemm_down": (lambda i: ctx.gemm(xf, wd[i % NW], residual=x), F * D * 2),
+    "gemm_o_nosplit": (lambda i: ctx.gemm(x, wo[i % NW], residual=x, k_splits=1), D * D * 2),
+    "gemm_down_nosplit": (lambda i: ctx.gemm(xf, wd[i % NW], residual=x, k_splits=1), F * D * 2),
+    "rmsnorm": (lambda i: ctx.rmsnorm(x, gam, 1e-5), 0),
+    "rope_kv_store": (lambda i: ctx.rope_kv_store(qkv, pos, slot, cos_t, sin_t, H, hd, kc[i % NW], vc[i % NW], want_kv=False), 0),
+    "decode_attention": (lambda i: ctx.decode_attention(q, kc[i % NW], vc[i % NW], bt, sl, H, hd, page), 2 * B * L * D * 2),
+    "silu_mul": (lambda i: ctx.silu_mul(gu), 0),
+}
+tot = 0.0
+for name, (fn, nbytes) in ops.items():
+    us = graph_time(fn)
+    print(f"{name:>20}: {us:8.2f} us" + (f"   {nbytes / us / 1e3:8.1f} GB/s" if nbytes else ""), flush=True)
+    if "nosplit" not in name:
+        tot += us * (2 if name == "rmsnorm" else 1)
+print(f"layer total {tot:.1f} us -> x40 = {tot * 40 / 1e3:.2f} ms per decode step (ideal weights-only at 6551 GB/s: {12 * D * D * 2 / 6551e3 * 40 / 1e3 + 0:.2f} ms)")
