@@ -1,0 +1,7 @@
+timeout 900 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench_quick.log 2>&1; tail -1 gpurun_out/bench_quick.log | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+print({k: d[k] for k in ('value','ms_per_step','gpu_launches')}, 'e2e', d['e2e']['value'])
+print(d.get('stage_ms'), d.get('decode_hbm'))
+print(d.get('roofline'))
+print(d.get('kernel_time_shares'))"
