@@ -324,7 +324,7 @@ def main():
     # launches inside CUDA-graph replays are not seen by the handle's counter: add them explicitly
     graph_launches = 0
     st = next(iter(model._graphs.values()), None)
-    if st is not None and st.get("graph") is not None:
+    if st is not None and st.get("graph_scripted") is not None:
         graph_launches = st.get("graph_launches", 0) * (N_ANS - 1) * args.steps
     images = args.batch * world * args.steps
     value = images / (ms / 1e3)

@@ -154,12 +154,24 @@ IVLM_API int ivlm_embed_gather_bf16(ivlm_handle h, const void* embed, const int3
                            int32_t vocab, void* stream);
 /* HF apply_rotary_pos_emb (rotate_half, bf16 cos/sin tables [max_pos, hd]) on the packed qkv rows
  * [T, 3*H*hd]; writes rotated q [T,H*hd], and k/v both contiguous [T,H*hd] (may be NULL) and into the paged
- * KV cache at slot_map[t] (cache layout [slots, H, hd]). */
+ * KV cache at slot_map[t] = physical_page * page_size + offset (cache layout [pages, H, page_size, hd]: the tokens
+ * of one head inside a page are contiguous). */
 IVLM_API int ivlm_rope_kv_store_bf16(ivlm_handle h, const void* qkv, const int32_t* positions, const int32_t* slot_map,
                             const void* cos_t, const void* sin_t, void* q_out, void* k_out, void* v_out,
-                            void* k_cache, void* v_cache, int32_t T, int32_t H, int32_t hd, void* stream);
+                            void* k_cache, void* v_cache, int32_t T, int32_t H, int32_t hd, int32_t page_size,
+                            void* stream);
+/* Decode-loop bookkeeping on the device (HF greedy search, transformers 4.31 generation/utils.py, as driven by
+ * InteractVLM.py:524-531), so that one decode step is a pure CUDA-graph replay:
+ * prepare: step = state[0]++ (also copied to state[1]); token fed at this step = scripted[b,step] or next[b]
+ * (pad_token once the sample has emitted eos); records it in out_tokens[b,step]; sets tok/pos/slot/seq_lens for
+ * position S+step.  finish: hidden[b, S+step, :] = hid_step[b, :]. */
+IVLM_API int ivlm_decode_prepare(ivlm_handle h, int32_t* state, int32_t S, const int32_t* scripted, int32_t G, const int32_t* next,
+                        int32_t* done, int32_t* out_tokens, int32_t* tok, int32_t* pos, int32_t* slot, int32_t* seq_lens,
+                        const int32_t* slot_base, int32_t eos, int32_t pad, int32_t B, void* stream);
+IVLM_API int ivlm_decode_finish(ivlm_handle h, const int32_t* state, int32_t S, const void* hid_step, void* hidden, int32_t B,
+                       int32_t D, int32_t max_len, void* stream);
 /* One-token attention over the paged KV cache: q [B,H*hd], block_table [B,max_pages], seq_lens [B]
- * (keys 0..seq_len-1, the current token already stored). */
+ * (keys 0..seq_len-1, the current token already stored); caches laid out [pages, H, page_size, hd]. */
 IVLM_API int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, const void* k_cache, const void* v_cache,
                                      const int32_t* block_table, const int32_t* seq_lens, void* out, int32_t B,
                                      int32_t H, int32_t hd, int32_t page_size, int32_t max_pages, float scale,
@@ -192,6 +204,9 @@ IVLM_API int ivlm_upscale_hyper_dot(ivlm_handle h, const void* up1, const void* 
  * src [N,sh,sw] fp32, only the top-left (crop_h,crop_w) window is read -> dst [N,dh,dw]. */
 IVLM_API int ivlm_bilinear_f32(ivlm_handle h, const float* src, float* dst, int32_t N, int32_t sh, int32_t sw, int32_t crop_h,
                       int32_t crop_w, int32_t dh, int32_t dw, void* stream);
+
+/* x[i] = sigmoid(x[i]) where gt == NULL or gt[i] != ignore_value (InteractVLM.py:452-456, 'oafford' with HM view types). */
+IVLM_API int ivlm_sigmoid_where_f32(ivlm_handle h, float* x, const float* gt, float ignore_value, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Render-Localise-Lift: 2D masks -> per-vertex contact. */

@@ -288,9 +288,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
         const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y), d = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
         qr[0] = a.x; qr[1] = a.y; qr[2] = c.x; qr[3] = c.y; qr[4] = d.x; qr[5] = d.y; qr[6] = e.x; qr[7] = e.y;
     }
-    auto row_ptr = [&](const bf16* cache, int kpos) {
-        const long long slot = (long long)bt[kpos / page] * page + (kpos % page);
-        return reinterpret_cast<const uint4*>(cache + (slot * H + h) * HD + li * 8);
+    auto row_ptr = [&](const bf16* cache, int kpos) {  // cache layout [pages, H, page, HD]
+        const long long base = ((long long)bt[kpos / page] * H + h) * page + (kpos % page);
+        return reinterpret_cast<const uint4*>(cache + base * HD + li * 8);
     };
     // ---- phase 1: scores
     float lmax = -INFINITY;

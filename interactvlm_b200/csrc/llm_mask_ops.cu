@@ -12,10 +12,14 @@ __global__ void rope_kv_store_kernel(const bf16* __restrict__ qkv, const int* __
                                      const int* __restrict__ slot_map, const bf16* __restrict__ cos_t,
                                      const bf16* __restrict__ sin_t, bf16* __restrict__ q_out, bf16* __restrict__ k_out,
                                      bf16* __restrict__ v_out, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
-                                     int H, int hd) {
+                                     int H, int hd, int page) {
     const long long tkn = blockIdx.x;
     const int pos = positions[tkn];
     const long long slot = slot_map ? slot_map[tkn] : -1;
+    // paged cache layout [pages, H, page, hd]: the `page` tokens of one head are contiguous, so a decode CTA streams
+    // page*hd*2-byte runs instead of hd*2-byte pieces strided by H*hd
+    const long long pg = slot >= 0 ? slot / page : 0, off = slot >= 0 ? slot % page : 0;
+    auto cidx = [&](int hh, int j) { return ((pg * H + hh) * page + off) * hd + j; };
     const int half = hd >> 1;
     const int D = H * hd;
     const bf16* qr = qkv + tkn * 3LL * D;
@@ -36,13 +40,13 @@ __global__ void rope_kv_store_kernel(const bf16* __restrict__ qkv, const int* __
             const bf16 o1 = __float2bfloat16_rn(bf16_round(x1 * c) + bf16_round(-x2 * s));
             const bf16 o2 = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * s));
             if (k_out) { k_out[tkn * D + i1] = o1; k_out[tkn * D + i2] = o2; }
-            if (slot >= 0) { k_cache[slot * D + i1] = o1; k_cache[slot * D + i2] = o2; }
+            if (slot >= 0) { k_cache[cidx(hh, j)] = o1; k_cache[cidx(hh, j + half)] = o2; }
         }
     }
     for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) {
         const uint4 u = reinterpret_cast<const uint4*>(vr)[i];
         if (v_out) reinterpret_cast<uint4*>(v_out + tkn * D)[i] = u;
-        if (slot >= 0) reinterpret_cast<uint4*>(v_cache + slot * D)[i] = u;
+        if (slot >= 0) *reinterpret_cast<uint4*>(v_cache + cidx((i * 8) / hd, (i * 8) % hd)) = u;
     }
 }
 
@@ -96,18 +100,76 @@ __global__ void __launch_bounds__(128) upscale_hyper_dot_kernel(const bf16* __re
     lowres[((long long)bv * LR + Y) * LR + X] = bf16_round(m);
 }
 
+// Device-side bookkeeping of the greedy / scripted decode loop, so that a decode step is a pure graph replay.
+// state[0] = number of tokens fed so far (advanced here), state[1] = the step the rest of this replay works on.
+__global__ void decode_prepare_kernel(int* __restrict__ state, int S, const int* __restrict__ scripted, int G,
+                                      const int* __restrict__ next, int* __restrict__ done, int* __restrict__ out_tokens,
+                                      int* __restrict__ tok, int* __restrict__ pos, int* __restrict__ slot,
+                                      int* __restrict__ seq_lens, const int* __restrict__ slot_base, int eos, int pad, int B) {
+    const int step = state[0];
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int t = scripted != nullptr ? scripted[b * G + step] : next[b];
+        if (done[b]) t = pad;
+        out_tokens[b * G + step] = t;
+        if (t == eos) done[b] = 1;
+        const int p = S + step;
+        tok[b] = t;
+        pos[b] = p;
+        slot[b] = slot_base[b] + p;
+        seq_lens[b] = p + 1;
+    }
+    if (threadIdx.x == 0) {
+        state[1] = step;
+        state[0] = step + 1;
+    }
+}
+// hidden[b, S + step, :] = hid_step[b, :]
+__global__ void decode_finish_kernel(const int* __restrict__ state, int S, const bf16* __restrict__ hid_step,
+                                     bf16* __restrict__ hidden, int D, int max_len) {
+    const int b = blockIdx.x, p = S + state[1];
+    const uint4* src = reinterpret_cast<const uint4*>(hid_step + (long long)b * D);
+    uint4* dst = reinterpret_cast<uint4*>(hidden + ((long long)b * max_len + p) * D);
+    for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) dst[i] = src[i];
+}
+
 }  // namespace ivlm
 
 using namespace ivlm;
 
+extern "C" int ivlm_decode_prepare(ivlm_handle h, int32_t* state, int32_t S, const int32_t* scripted, int32_t G,
+                                   const int32_t* next, int32_t* done, int32_t* out_tokens, int32_t* tok, int32_t* pos,
+                                   int32_t* slot, int32_t* seq_lens, const int32_t* slot_base, int32_t eos, int32_t pad,
+                                   int32_t B, void* stream) {
+    IVLM_REQUIRE(h && state && next && done && out_tokens && tok && pos && slot && seq_lens && slot_base && B > 0 && G > 0,
+                 "decode_prepare: bad arguments");
+    decode_prepare_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(state, S, scripted, G, next, done, out_tokens,
+                                                                                 tok, pos, slot, seq_lens, slot_base, eos, pad, B);
+    h->launches++;
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    return IVLM_OK;
+}
+
+extern "C" int ivlm_decode_finish(ivlm_handle h, const int32_t* state, int32_t S, const void* hid_step, void* hidden,
+                                  int32_t B, int32_t D, int32_t max_len, void* stream) {
+    IVLM_REQUIRE(h && state && hid_step && hidden && B > 0 && D % 8 == 0, "decode_finish: bad arguments");
+    decode_finish_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(state, S, (const bf16*)hid_step, (bf16*)hidden,
+                                                                                D, max_len);
+    h->launches++;
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    return IVLM_OK;
+}
+
 extern "C" int ivlm_rope_kv_store_bf16(ivlm_handle h, const void* qkv, const int32_t* positions, const int32_t* slot_map,
                                        const void* cos_t, const void* sin_t, void* q_out, void* k_out, void* v_out,
-                                       void* k_cache, void* v_cache, int32_t T, int32_t H, int32_t hd, void* stream) {
-    IVLM_REQUIRE(h && T > 0 && (H * hd) % 8 == 0 && hd % 2 == 0, "rope: bad shape");
+                                       void* k_cache, void* v_cache, int32_t T, int32_t H, int32_t hd, int32_t page_size,
+                                       void* stream) {
+    IVLM_REQUIRE(h && T > 0 && (H * hd) % 8 == 0 && hd % 8 == 0, "rope: bad shape");
+    IVLM_REQUIRE(slot_map == nullptr || page_size > 0, "rope: page_size must be positive when a cache is written");
     IVLM_REQUIRE(slot_map == nullptr || (k_cache && v_cache), "rope: slot_map given without caches");
     rope_kv_store_kernel<<<T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         (const bf16*)qkv, positions, slot_map, (const bf16*)cos_t, (const bf16*)sin_t, (bf16*)q_out, (bf16*)k_out,
-        (bf16*)v_out, (bf16*)k_cache, (bf16*)v_cache, H, hd);
+        (bf16*)v_out, (bf16*)k_cache, (bf16*)v_cache, H, hd, page_size > 0 ? page_size : 1);
     h->launches++;
     IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;

@@ -370,6 +370,13 @@ __global__ void cam_gate_kernel(const bf16* __restrict__ cam, const bf16* __rest
     }
 }
 
+// In-place sigmoid of mask logits wherever the ground-truth mask is not the ignore label (InteractVLM.py:452-456:
+// heat-map view types feed sigmoid-ed maps to the point-cloud affordance lift).
+__global__ void sigmoid_where_kernel(float* __restrict__ x, const float* __restrict__ gt, float ignore, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        if (gt == nullptr || gt[i] != ignore) x[i] = 1.f / (1.f + expf(-x[i]));
+}
+
 static inline int grid_for(long long work, int block, int sms) {
     long long g = (work + block - 1) / block;
     long long cap = (long long)sms * 16;
@@ -491,5 +498,11 @@ extern "C" int ivlm_cam_gate_bf16(ivlm_handle h, const void* cam, const void* em
     cam_gate_kernel<<<B * V, 256, 0, STREAM>>>((const bf16*)cam, (const bf16*)emb, (const bf16*)w1, (const bf16*)b1,
                                                (const bf16*)w2, (const bf16*)b2, (const bf16*)wv, (const bf16*)bv,
                                                (bf16*)out, V);
+    DONE();
+}
+
+extern "C" int ivlm_sigmoid_where_f32(ivlm_handle h, float* x, const float* gt, float ignore_value, int64_t n, void* stream) {
+    IVLM_REQUIRE(h && x && n > 0, "sigmoid_where: bad arguments");
+    sigmoid_where_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, STREAM>>>(x, gt, ignore_value, n);
     DONE();
 }

@@ -257,9 +257,9 @@ class _Engine:
         pages_per = (max_len + PAGE - 1) // PAGE
         st = dict(B=B, max_len=max_len, pages_per=pages_per)
         st["block_table"] = torch.arange(B * pages_per, dtype=torch.int32, device=self.device).view(B, pages_per).contiguous()
-        slots = B * pages_per * PAGE
-        st["k"] = [torch.empty((slots, cfg.num_attention_heads, cfg.head_dim), device=self.device, dtype=torch.bfloat16)
-                   for _ in range(cfg.num_hidden_layers)]
+        # paged cache, [pages, heads, PAGE, head_dim] per layer (slot = page * PAGE + offset)
+        st["k"] = [torch.empty((B * pages_per, cfg.num_attention_heads, PAGE, cfg.head_dim), device=self.device,
+                               dtype=torch.bfloat16) for _ in range(cfg.num_hidden_layers)]
         st["v"] = [torch.empty_like(k) for k in st["k"]]
         st["hidden"] = torch.zeros((B, max_len, cfg.hidden_size), device=self.device, dtype=torch.bfloat16)
         return st
@@ -277,7 +277,8 @@ class _Engine:
         for i, lw in enumerate(W.llm):
             y = ctx.rmsnorm(x, lw["ln1"], cfg.rms_norm_eps)
             qkv = ctx.gemm(y, lw["wqkv"])
-            q, k, v = ctx.rope_kv_store(qkv, pos, slot, W.rope_cos, W.rope_sin, nh, hd, st["k"][i], st["v"][i])
+            q, k, v = ctx.rope_kv_store(qkv, pos, slot, W.rope_cos, W.rope_sin, nh, hd, st["k"][i], st["v"][i],
+                                        page_size=PAGE)
             o = ctx.attention(q.view(B, S, nh, hd), k.view(B, S, nh, hd), v.view(B, S, nh, hd), 1.0 / math.sqrt(hd), causal=True)
             x = ctx.gemm(o.view(B * S, D), lw["wo"], residual=x)
             y = ctx.rmsnorm(x, lw["ln2"], cfg.rms_norm_eps)
@@ -286,7 +287,7 @@ class _Engine:
         hn = ctx.rmsnorm(x, W.norm, cfg.rms_norm_eps).view(B, S, D)
         st["hidden"][:, :S] = hn
         st["len"] = S
-        return self._greedy(hn[:, S - 1].contiguous())
+        return self._greedy(hn[:, S - 1].contiguous(), out=st.get("next"))
 
     def _greedy(self, h, out=None):
         """lm_head + argmax.  Rows go through the swapped-operand GEMM in chunks of <= 64 (the vocabulary size of the
@@ -308,26 +309,32 @@ class _Engine:
         st["seq_lens"] = torch.zeros((B,), dtype=torch.int32, device=self.device)
         st["next"] = torch.zeros((B,), dtype=torch.int32, device=self.device)
         st["hid_step"] = torch.zeros((B, self.cfg.hidden_size), dtype=torch.bfloat16, device=self.device)
+        st["state"] = torch.zeros((2,), dtype=torch.int32, device=self.device)   # [tokens fed, current step]
+        st["done"] = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        st["max_new"] = 0
         st["slot_base"] = (torch.arange(B, dtype=torch.int32, device=self.device) * (st["pages_per"] * PAGE)).contiguous()
 
     def llm_decode_step(self, st):
-        """One token per sample through the paged KV cache.  Reads st['tok'|'pos'|'slot'|'seq_lens'] (device),
-        writes st['next'] (greedy token) and st['hid_step'] (normed hidden of the fed token).  Fixed launch sequence
-        with fixed buffers -> CUDA-graph capturable."""
+        """One token per sample through the paged KV cache.  All bookkeeping is on the device: `decode_prepare` picks the
+        token to feed (st['next'] from the previous step or the scripted answer), records it and advances positions;
+        the layers run; `decode_finish` files the normed hidden state under its position; the greedy token for the next
+        step lands in st['next'].  Fixed launch sequence over fixed buffers -> one CUDA graph, replayed per step."""
         ctx, cfg, W = self.ctx, self.cfg, self.w
         nh, hd = cfg.num_attention_heads, cfg.head_dim
+        ctx.decode_prepare(st, st["S"], st["G"], cfg.eos_token_id, cfg.pad_token_id)
         x = ctx.embed_gather(W.embed, st["tok"])
         for i, lw in enumerate(W.llm):
             y = ctx.rmsnorm(x, lw["ln1"], cfg.rms_norm_eps)
             qkv = ctx.gemm(y, lw["wqkv"])
             q, _, _ = ctx.rope_kv_store(qkv, st["pos"], st["slot"], W.rope_cos, W.rope_sin, nh, hd, st["k"][i], st["v"][i],
-                                        want_kv=False)
+                                        want_kv=False, page_size=PAGE)
             o = ctx.decode_attention(q, st["k"][i], st["v"][i], st["block_table"], st["seq_lens"], nh, hd, PAGE)
             x = ctx.gemm(o, lw["wo"], residual=x)
             y = ctx.rmsnorm(x, lw["ln2"], cfg.rms_norm_eps)
             y = ctx.silu_mul(ctx.gemm(y, lw["wgu"]))
             x = ctx.gemm(y, lw["wd"], residual=x)
         ctx.rmsnorm(x, W.norm, cfg.rms_norm_eps, out=st["hid_step"])
+        ctx.decode_finish(st, st["S"])
         self._greedy(st["hid_step"], out=st["next"])
 
     # ------------------------------------------------------------------ [SEG] head (a7, a10)
@@ -407,26 +414,93 @@ class _Engine:
 
 class _Predictor:
     """Callable attribute mirroring HumanContact3DPredictor / ObjectMeshContact3DPredictor / ObjectPCAfford3DPredictor
-    (model/components.py:195-489): list of [V,H,W] fp32 maps -> [B,n] fp32."""
+    (model/components.py:195-489): list of [V,H,W] fp32 maps -> [B,n] fp32.  The reference re-reads its maps from
+    disk (and copies them to the GPU) on every call; here every distinct map set is converted ONCE into the device CSR
+    of ops.LiftMap and cached by its source path(s)."""
+
+    N_POINTS = 2048  # ObjectPCAfford3DPredictor(num_points=2048), components.py:280
 
     def __init__(self, model, mode):
         self.model, self.mode = model, mode
         self.map = None
+        self._cache = {}
 
-    def set_maps(self, p2v, bary, n_verts):
+    def _make(self, p2v, bary, n):
+        if self.model._emulated:
+            return self.model.ctx.LiftMap(p2v, bary, n)
         from .ops import LiftMap
 
-        self.map = LiftMap(self.model.ctx, p2v, bary, n_verts) if not self.model._emulated else self.model.ctx.LiftMap(p2v, bary, n_verts)
+        return LiftMap(self.model.ctx, p2v, bary, n)
+
+    def set_maps(self, p2v, bary, n_verts):
+        self.map = self._make(p2v, bary, n_verts)
         return self
 
+    def _from_pickle(self, path):
+        """lift2d_dict.pkl written by generate_sam_inp_objs (utils/demo_utils.py:171-257; read at components.py:392-424)."""
+        if path not in self._cache:
+            import joblib
+
+            d = joblib.load(path)
+            self._cache[path] = self._make(np.stack([np.asarray(a) for a in d["pixel_to_vertices_map"]]),
+                                           np.stack([np.asarray(a) for a in d["bary_coords_map"]]), int(d["num_vertices"]))
+        return self._cache[path]
+
+    def _from_mask_paths(self, mask_paths):
+        """Per-view map files next to the mask images: '...mask...png' -> '...p2vmap....npz' (mesh, components.py:363-375)
+        or '...p2pmap....npz' (point cloud, components.py:309)."""
+        key = tuple(mask_paths)
+        if key not in self._cache:
+            V = self.model.config.multiview_channels
+            if self.mode == LIFT_POINTS:
+                maps = [np.load(mask_paths[v].replace("mask", "p2pmap")[:-4] + ".npz")["mapping"] for v in range(V)]
+                self._cache[key] = self._make(np.stack(maps), None, self.N_POINTS)
+            else:
+                files = [np.load(mask_paths[v].replace("mask", "p2vmap").replace(".png", ".npz")) for v in range(V)]
+                self._cache[key] = self._make(np.stack([f["pixel_to_vertices_map"] for f in files]),
+                                              np.stack([f["bary_coords_map"] for f in files]), int(files[0]["num_vertices"]))
+        return self._cache[key]
+
     def __call__(self, seg_maps, ds_names=None, mask_paths_list=None, lift2d_dict_path=None):
-        m = self.map
-        if lift2d_dict_path is not None:
-            m = self.model._lift_map_from_pickle(lift2d_dict_path)
-        if m is None:
-            raise RuntimeError("lifting maps not loaded: call set_maps(p2v, bary, n_verts) or pass lift2d_dict_path")
-        masks = torch.stack([s.float() for s in seg_maps], 0).contiguous()
-        return m(masks, self.mode, 0.3)
+        B = len(seg_maps)
+        dev = seg_maps[0].device
+        if self.mode == LIFT_HUMAN:
+            names = ds_names if ds_names is not None else ["hcontact"] * B
+            if self.map is None:
+                raise RuntimeError("human lifting maps not loaded: call model.load_human_lift_maps(data_root) or "
+                                   "model.set_human_lift_maps(p2v, bary)")
+            masks = torch.stack([s.float() for s in seg_maps], 0).contiguous()
+            out = self.map(masks, LIFT_HUMAN, 0.3)
+            for b, n in enumerate(names):  # samples of other datasets contribute zeros (components.py:231-233)
+                if "hcontact" not in n:
+                    out[b] = 0
+            return out
+        if self.mode == LIFT_OBJECT_MESH:
+            names = ds_names if ds_names is not None else ["ocontact"] * B
+            if "ocontact" not in names[0]:
+                return torch.zeros((1, 0), device=dev, dtype=torch.float32)  # components.py:430-431
+            if B != 1:
+                raise AssertionError("Batch size should be 1 since different objects have different number of vertices")
+            if lift2d_dict_path is not None:
+                m = self._from_pickle(lift2d_dict_path)
+            elif mask_paths_list is not None:
+                m = self._from_mask_paths(mask_paths_list[0])
+            elif self.map is not None:
+                m = self.map
+            else:
+                raise ValueError("Either lift2d_dict_path or mask_paths_list must be provided for ObjectMeshContact3DPredictor")
+            return m(seg_maps[0].float()[None].contiguous(), LIFT_OBJECT_MESH, 0.3)
+        # point-cloud affordance: a different pixel->point map per sample
+        names = ds_names if ds_names is not None else ["oafford"] * B
+        out = torch.zeros((B, self.N_POINTS), device=dev, dtype=torch.float32)
+        for b in range(B):
+            if "oafford" not in names[b]:
+                continue
+            m = self._from_mask_paths(mask_paths_list[b]) if mask_paths_list is not None and mask_paths_list[b] else self.map
+            if m is None:
+                raise ValueError("mask_paths_list is required for ObjectPCAfford3DPredictor")
+            out[b] = m(seg_maps[b].float()[None].contiguous(), LIFT_POINTS, 0.3)[0]
+        return out
 
 
 class _GetModel:
@@ -469,7 +543,6 @@ class InteractVLMForCausalLM:
         self.eng = _Engine(ctx, config, self.w)
         self.use_cuda_graph = use_cuda_graph and self.device.type == "cuda"
         self._graphs = {}
-        self._lift_cache = {}
         self.seg_token_idx = config.seg_token_idx
         self.img_emb_len = config.img_emb_len
         self.multiview_channels = config.multiview_channels
@@ -560,20 +633,6 @@ class InteractVLMForCausalLM:
         bary = np.load(d / "bary_coords_map_1024.npz")
         self.set_human_lift_maps(np.stack([p2v[v] for v in HUMAN_VIEWS]), np.stack([bary[v] for v in HUMAN_VIEWS]))
 
-    def _lift_map_from_pickle(self, path):
-        """lift2d_dict.pkl written by generate_sam_inp_objs (utils/demo_utils.py:171-257)."""
-        if path not in self._lift_cache:
-            import joblib
-
-            from .ops import LiftMap
-
-            d = joblib.load(path)
-            p2v = np.stack([np.asarray(a) for a in d["pixel_to_vertices_map"]])
-            bary = np.stack([np.asarray(a) for a in d["bary_coords_map"]])
-            mk = self.ctx.LiftMap if self._emulated else (lambda *a: LiftMap(self.ctx, *a))
-            self._lift_cache[path] = mk(p2v, bary, int(d["num_vertices"]))
-        return self._lift_cache[path]
-
     # ---- stages -------------------------------------------------------------------------------------------------
     def get_visual_embs(self, images):
         """[B,V,3,1024,1024] -> [B*V, 4096, 256] token-major (InteractVLM.py:251-261)."""
@@ -586,22 +645,30 @@ class InteractVLMForCausalLM:
         t = t.to(self.device)
         return t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
 
-    def _llm_state(self, B, max_len):
-        """KV pages, decode buffers and the captured decode graph, kept across calls per (batch, page count)."""
-        key = (B, (max_len + PAGE - 1) // PAGE)
+    def _llm_state(self, B, max_len, S, G):
+        """KV pages, decode buffers and the captured decode graphs, kept across calls per (batch, pages, prompt rows,
+        max_new_tokens) -- S and G are baked into the captured kernels' arguments."""
+        key = (B, (max_len + PAGE - 1) // PAGE, S, G)
         if key not in self._graphs:
             st = self.eng.llm_alloc(B, key[1] * PAGE)
             self.eng.llm_decode_buffers(st)
+            st["S"], st["G"] = S, G
+            st["out_tokens"] = torch.zeros((B, G), dtype=torch.int32, device=self.device)
+            st["scripted_buf"] = torch.zeros((B, G), dtype=torch.int32, device=self.device)
             self._graphs = {key: st}  # one resident configuration: a new shape releases the previous pages
         return self._graphs[key]
 
     def _decode_graph(self, st):
         if not self.use_cuda_graph:
             return None
-        for _ in range(2):  # warm-up outside capture: lazy function attributes, allocator pools
+        # warm-up outside capture (lazy function attributes, allocator pools), then rewind the bookkeeping it advanced
+        keep = {k: st[k].clone() for k in ("state", "done", "out_tokens", "next")}
+        for _ in range(2):
             n0 = self.ctx.launch_count()
             self.eng.llm_decode_step(st)
             st["graph_launches"] = self.ctx.launch_count() - n0  # kernels per replay (the handle cannot see replays)
+        for k, v in keep.items():
+            st[k].copy_(v)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -626,36 +693,55 @@ class InteractVLMForCausalLM:
         feats = eng.clip_encode(self._bf16(images_clip))
         self._mark("clip")
         embeds = self.ctx.embed_splice(self.w.embed, ids.to(torch.int32).to(self.device).contiguous(), feats.contiguous())
-        st = self._llm_state(B, max_len)
-        nxt = eng.llm_prefill(st, embeds)
+        st = self._llm_state(B, max_len, S, max_new_tokens)
+        G = max_new_tokens
+        st["state"].zero_()
+        st["done"].zero_()
+        st["out_tokens"].fill_(cfg.pad_token_id)
+        if scripted is not None:
+            scr = torch.as_tensor(scripted).to(torch.int32)
+            if scr.shape != (B, G):
+                raise ValueError(f"scripted tokens must be [B, max_new_tokens] = {(B, G)}, got {tuple(scr.shape)}")
+            st["scripted_buf"].copy_(scr)
+            st["scripted"] = st["scripted_buf"]
+        else:
+            st["scripted"] = None
+        key = "graph_scripted" if scripted is not None else "graph_greedy"
+        eng.llm_prefill(st, embeds)
         self._mark("llm_prefill")
-        graph = st.get("graph")
-        out = [ids]
-        done = torch.zeros(B, dtype=torch.bool)
-        scripted = None if scripted is None else torch.as_tensor(scripted).cpu().to(torch.int64)
-        for step in range(max_new_tokens):
-            tok = nxt.cpu().to(torch.int64) if scripted is None else scripted[:, step]
-            tok = torch.where(done, torch.full_like(tok, cfg.pad_token_id), tok)
-            out.append(tok[:, None])
-            done |= tok == cfg.eos_token_id
-            if bool(done.all()) or step == max_new_tokens - 1:
+        graph = st.get(key)
+        if self.use_cuda_graph and graph is None and G > 1:
+            graph = st[key] = self._decode_graph(st)
+        # the graph is replayed without any host work in between; greedy decoding looks at the EOS flags every few steps
+        fed = 0
+        check_every = 4
+        while fed < G - 1:
+            n = (G - 1 - fed) if scripted is not None else min(check_every, G - 1 - fed)
+            for _ in range(n):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    eng.llm_decode_step(st)
+            fed += n
+            if scripted is None and bool(st["done"].all().item()):
                 break
-            # feed `tok` at position S+step
-            p = S + step
-            st["tok"].copy_(tok.to(torch.int32), non_blocking=False)
-            st["pos"].fill_(p)
-            st["slot"].copy_(st["slot_base"] + p)
-            st["seq_lens"].fill_(p + 1)
-            if self.use_cuda_graph and graph is None:
-                graph = st["graph"] = self._decode_graph(st)
-            if graph is not None:
-                graph.replay()
-            else:
-                eng.llm_decode_step(st)
-            st["hidden"][:, p] = st["hid_step"]
-            nxt = st["next"]
+        toks = st["out_tokens"].cpu().to(torch.int64)[:, :G]           # tokens fed so far: columns [0, fed)
+        done = st["done"].cpu().bool()
+        last = (torch.as_tensor(scripted).cpu().to(torch.int64)[:, fed] if scripted is not None
+                else st["next"].cpu().to(torch.int64))                    # the token that ends the sequence (never fed)
+        fed_done = torch.zeros(B, dtype=torch.bool)
+        if fed > 0:
+            fed_done = (toks[:, :fed] == cfg.eos_token_id).any(1)
+        toks[:, fed] = torch.where(fed_done, torch.full_like(last, cfg.pad_token_id), last)
+        n_new = fed + 1
+        # HF stops as soon as every sequence has produced EOS: drop the all-pad tail a late EOS check may have added
+        eos_pos = torch.where(toks[:, :n_new] == cfg.eos_token_id, torch.arange(n_new)[None], torch.full((1, n_new), n_new))
+        first_eos = eos_pos.min(1).values
+        if bool((first_eos < n_new).all()):
+            n_new = int(first_eos.max().item()) + 1
+        del done
         self._mark("llm_decode")
-        return torch.cat(out, 1), st["hidden"]
+        return torch.cat([ids, toks[:, :n_new]], 1), st["hidden"]
 
     # ---- public API ---------------------------------------------------------------------------------------------
     def evaluate(self, images_clip, images, input_ids, cam_params, resize_list, original_size_list,
@@ -736,7 +822,12 @@ class InteractVLMForCausalLM:
         ds = ds_name_list or ["hcontact"] * B
         for i, name in enumerate(ds):  # HM view types feed sigmoid-ed maps to the affordance lift (:452-456)
             if "oafford" in name and cfg.oC_sam_view_type and "HM" in cfg.oC_sam_view_type:
-                pred_masks[i] = torch.sigmoid(pred_masks[i])
+                gt = None
+                if masks_list is not None and masks_list[i] is not None:
+                    gt = torch.as_tensor(masks_list[i])[:, 0].to(self.device, torch.float32).contiguous()
+                    if gt.shape != pred_masks[i].shape:
+                        gt = None
+                self.ctx.sigmoid_where(pred_masks[i], gt, -1.0)  # IGNORE_LABEL = -1 (utils/utils.py:19)
         result = {"gt_masks": [m[:, 0] for m in masks_list] if masks_list is not None else None, "pred_masks": pred_masks}
         if self.hC_loss_weight > 0:
             result["pred_human_3d_contact"] = self.human_3d_contact_predictor(pred_masks, ds)

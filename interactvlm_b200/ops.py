@@ -66,7 +66,7 @@ class Context:
     # ------------------------------------------------------------------ per-kernel timing (bench.py roofline pass)
     _PROFILED = ("gemm", "attention", "layernorm", "rmsnorm", "add_bcast", "silu_mul", "im2col_patch", "im2col_3x3",
                  "sam_relpos", "sam_attention", "attn_small", "embed_splice", "embed_gather", "gather_rows", "rope_kv_store",
-                 "decode_attention", "argmax", "cam_gate", "upscale_hyper_dot", "bilinear", "finalize")
+                 "decode_attention", "decode_prepare", "decode_finish", "argmax", "cam_gate", "upscale_hyper_dot", "bilinear", "finalize")
 
     def enable_profile(self):
         """Bracket every launch with CUDA events on the launching stream (no synchronisation until profile_report()).
@@ -316,7 +316,7 @@ class Context:
         return out
 
     def rope_kv_store(self, qkv, positions, slot_map, cos_t, sin_t, H, hd, k_cache=None, v_cache=None, want_kv=True,
-                      q_out=None):
+                      q_out=None, page_size=16):
         _bf16(qkv)
         T = qkv.shape[0]
         D = H * hd
@@ -326,7 +326,7 @@ class Context:
         v_out = torch.empty((T, D), device=qkv.device, dtype=torch.bfloat16) if want_kv else None
         L.check(self.lib.ivlm_rope_kv_store_bf16(self.h, P(qkv), P(positions), P(slot_map), P(cos_t), P(sin_t), P(q_out),
                                                  P(k_out), P(v_out), P(k_cache), P(v_cache), i32(T), i32(H), i32(hd),
-                                                 self.stream), "rope_kv_store")
+                                                 i32(page_size), self.stream), "rope_kv_store")
         return q_out, k_out, v_out
 
     def decode_attention(self, q, k_cache, v_cache, block_table, seq_lens, H, hd, page_size, out=None):
@@ -339,6 +339,19 @@ class Context:
                                                           i32(block_table.shape[1]), f32c(1.0 / math.sqrt(hd)),
                                                           self.stream), "decode_attention")
         return out
+
+    def decode_prepare(self, st, S, G, eos, pad):
+        """Device-side token / position bookkeeping of one decode step (st: the model's decode-state dict)."""
+        B = st["tok"].numel()
+        L.check(self.lib.ivlm_decode_prepare(self.h, P(st["state"]), i32(S), P(st.get("scripted")), i32(G), P(st["next"]),
+                                             P(st["done"]), P(st["out_tokens"]), P(st["tok"]), P(st["pos"]), P(st["slot"]),
+                                             P(st["seq_lens"]), P(st["slot_base"]), i32(eos), i32(pad), i32(B), self.stream),
+                "decode_prepare")
+
+    def decode_finish(self, st, S):
+        hid = st["hidden"]
+        L.check(self.lib.ivlm_decode_finish(self.h, P(st["state"]), i32(S), P(st["hid_step"]), P(hid), i32(hid.shape[0]),
+                                            i32(hid.shape[2]), i32(hid.shape[1]), self.stream), "decode_finish")
 
     def argmax(self, logits, vocab=None, out=None):
         assert logits.dtype == torch.float32 and logits.stride(1) == 1
@@ -365,6 +378,15 @@ class Context:
         L.check(self.lib.ivlm_upscale_hyper_dot(self.h, P(up1), P(w2), P(b2), P(hyper.contiguous()), P(out), i32(Bv),
                                                 i32(grid), self.stream), "upscale_hyper_dot")
         return out
+
+    def sigmoid_where(self, x, gt=None, ignore_value=-1.0):
+        """In place: x = sigmoid(x) where gt != ignore_value (everywhere when gt is None)."""
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        if gt is not None:
+            assert gt.dtype == torch.float32 and gt.is_contiguous() and gt.numel() == x.numel()
+        L.check(self.lib.ivlm_sigmoid_where_f32(self.h, P(x), P(gt), f32c(ignore_value), i64(x.numel()), self.stream),
+                "sigmoid_where")
+        return x
 
     def bilinear(self, src, dh, dw, crop_h=None, crop_w=None, out=None):
         assert src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 3

@@ -211,7 +211,7 @@ class EmuContext:
         return x[idx.long()]
 
     def rope_kv_store(self, qkv, positions, slot_map, cos_t, sin_t, H, hd, k_cache=None, v_cache=None, want_kv=True,
-                      q_out=None):
+                      q_out=None, page_size=16):
         self.launches += 1
         T = qkv.shape[0]
         D = H * hd
@@ -224,9 +224,10 @@ class EmuContext:
             return (x * c) + (rot * s)
 
         qo, ko = rope(q), rope(k)
-        if slot_map is not None:
-            k_cache[slot_map.long()] = ko
-            v_cache[slot_map.long()] = v
+        if slot_map is not None:  # cache layout [pages, H, page, hd]
+            sl = slot_map.long()
+            k_cache[sl // page_size, :, sl % page_size] = ko
+            v_cache[sl // page_size, :, sl % page_size] = v
         return qo.reshape(T, D), (ko.reshape(T, D) if want_kv else None), (v.reshape(T, D).contiguous() if want_kv else None)
 
     def decode_attention(self, q, k_cache, v_cache, block_table, seq_lens, H, hd, page_size, out=None):
@@ -236,12 +237,32 @@ class EmuContext:
         for b in range(B):
             n = int(seq_lens[b])
             pos = torch.arange(n)
-            slots = block_table[b].long()[pos // page_size] * page_size + pos % page_size
-            kf, vf = k_cache[slots].float(), v_cache[slots].float()  # [n,H,hd]
+            pg, off = block_table[b].long()[pos // page_size], pos % page_size
+            kf, vf = k_cache[pg, :, off].float(), v_cache[pg, :, off].float()  # [n,H,hd]
             sc = _r(_r(torch.einsum("hd,nhd->hn", q[b].view(H, hd).float(), kf)) / math.sqrt(hd))
             p = _r(sc.softmax(-1))
             res[b] = torch.einsum("hn,nhd->hd", p, vf).reshape(-1).to(BF)
         return res
+
+    def decode_prepare(self, st, S, G, eos, pad):
+        self.launches += 1
+        step = int(st["state"][0])
+        scripted = st.get("scripted")
+        t = (scripted[:, step] if scripted is not None else st["next"]).clone().to(torch.int32)
+        t[st["done"].bool()] = pad
+        st["out_tokens"][:, step] = t
+        st["done"][t == eos] = 1
+        p = S + step
+        st["tok"].copy_(t)
+        st["pos"].fill_(p)
+        st["slot"].copy_(st["slot_base"] + p)
+        st["seq_lens"].fill_(p + 1)
+        st["state"][1] = step
+        st["state"][0] = step + 1
+
+    def decode_finish(self, st, S):
+        self.launches += 1
+        st["hidden"][:, S + int(st["state"][1])] = st["hid_step"]
 
     def argmax(self, logits, vocab=None, out=None):
         self.launches += 1
@@ -268,6 +289,12 @@ class EmuContext:
         m = torch.einsum("btpqc,bc->btpq", z, hyper.float())
         m = m.view(Bv, G, G, 2, 2, 2, 2).permute(0, 1, 3, 5, 2, 4, 6).reshape(Bv, G * 4, G * 4)
         return _r(m)
+
+    def sigmoid_where(self, x, gt=None, ignore_value=-1.0):
+        self.launches += 1
+        keep = torch.ones_like(x, dtype=torch.bool) if gt is None else gt != ignore_value
+        x[keep] = torch.sigmoid(x[keep])
+        return x
 
     def bilinear(self, src, dh, dw, crop_h=None, crop_w=None, out=None):
         self.launches += 1

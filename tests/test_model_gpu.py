@@ -190,3 +190,40 @@ def test_full_size_layers_vs_torch_fp32(ctx):
         model.eng.llm_prefill(st, embeds)
         print("LLaMA-13B layer: rel err", rel(st["hidden"][:, :embeds.shape[1]], hid_ref))
         assert rel(st["hidden"][:, :embeds.shape[1]], hid_ref) < 2e-2
+
+
+def test_object_mesh_and_pointcloud_paths(tiny, tmp_path):
+    """Rows a15/a16 through the model API on the GPU: evaluate(contact_type='oafford', lift2d_dict_path=pkl) and
+    model_forward with the object predictors on, maps read from files like the reference does."""
+    import joblib
+
+    cfg, sd, model, _ = tiny
+    nv = 3000
+    op2v, obary = S.make_mesh_lift_maps(n_verts=nv, seed=3, coverage=0.25)
+    pkl = tmp_path / "lift2d_dict.pkl"
+    joblib.dump({"pixel_to_vertices_map": [op2v[v] for v in range(4)], "bary_coords_map": [obary[v] for v in range(4)],
+                 "num_vertices": nv}, pkl)
+    p2p = S.make_point_lift_maps(seed=2)
+    mask_paths = []
+    for v in range(4):
+        np.savez(tmp_path / f"obj_p2pmap_{v}.npz", mapping=p2p[v])
+        mask_paths.append(str(tmp_path / f"obj_mask_{v}.png"))
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 1)
+    out = model.evaluate(clip, sam, ids, cam, [SIZE], [SIZE], lift2d_dict_path=str(pkl), contact_type="oafford",
+                         max_new_tokens=ans.shape[1], scripted=ans)
+    pm = torch.stack(out["pred_masks"], 0).cpu().numpy()
+    want = OL.lift_object_mesh(pm, op2v, obary, nv, thr=0.3)
+    got = out["pred_contact_3d"].cpu().numpy()
+    assert got.shape == (1, nv) and np.abs(got - want).max() < 1e-5
+    full = torch.cat([ids, ans], 1)
+    model.oC_loss_weight = 3.0
+    try:
+        res = model(images=sam, images_clip=clip, input_ids=full, labels=full, attention_masks=torch.ones_like(full),
+                    offset=torch.tensor([0, 1]), masks_list=[torch.zeros(4, 1, *SIZE)], label_list=[torch.zeros(SIZE)],
+                    gt_contact_3d_list=[None], cam_params=cam, resize_list=[SIZE], ds_name_list=["piad_oafford"],
+                    mask_paths_list=[mask_paths], inference=True)
+    finally:
+        model.oC_loss_weight = 0.0
+    pm = torch.stack(res["pred_masks"], 0).cpu().numpy()
+    assert 0.0 <= pm.min() and pm.max() <= 1.0   # sigmoid-ed heat maps (InteractVLM.py:452-456)
+    assert np.abs(res["pred_object_3d_afford"].cpu().numpy() - OL.lift_points(pm, p2p, 2048)).max() < 1e-5

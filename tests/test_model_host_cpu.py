@@ -105,3 +105,54 @@ def test_checkpoint_roundtrip_and_api_surface(tmp_path, setup):
         model.resize_token_embeddings(cfg.vocab_size + 1)
     with pytest.raises(RuntimeError):
         model.float()
+
+
+def _write_object_maps(tmp_path, n_verts=3000):
+    import joblib
+    op2v, obary = S.make_mesh_lift_maps(n_verts=n_verts, seed=3, coverage=0.25)
+    pkl = tmp_path / "lift2d_dict.pkl"
+    joblib.dump({"pixel_to_vertices_map": [op2v[v] for v in range(4)], "bary_coords_map": [obary[v] for v in range(4)],
+                 "num_vertices": n_verts}, pkl)
+    p2p = S.make_point_lift_maps(seed=2)
+    mask_paths = []
+    for v in range(4):
+        np.savez(tmp_path / f"obj_p2pmap_{v}.npz", mapping=p2p[v])
+        np.savez(tmp_path / f"obj_p2vmap_{v}.npz", pixel_to_vertices_map=op2v[v], bary_coords_map=obary[v], num_vertices=n_verts)
+        mask_paths.append(str(tmp_path / f"obj_mask_{v}.png"))
+    return pkl, mask_paths, (op2v, obary, n_verts), p2p
+
+
+def test_object_paths_evaluate_and_forward(tmp_path, setup):
+    """Rows a15 / a16 at model level: evaluate(contact_type='oafford', lift2d_dict_path=...) lifts through the object-mesh
+    predictor (InteractVLM.py:624-628, sic precedence), model_forward with oC_loss_weight > 0 returns both object outputs
+    with maps read from the files next to the mask paths (components.py:309, :363-375)."""
+    from oracle import lift as OL
+    cfg, sd, model, _ = setup
+    pkl, mask_paths, (op2v, obary, nv), p2p = _write_object_maps(tmp_path)
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 1)
+    out = model.evaluate(clip, sam, ids, cam, [SIZE], [SIZE], lift2d_dict_path=str(pkl), contact_type="oafford",
+                         max_new_tokens=ans.shape[1], scripted=ans)
+    pm = torch.stack(out["pred_masks"], 0).cpu().numpy()
+    want = OL.lift_object_mesh(pm, op2v, obary, nv, thr=0.3)
+    assert out["pred_contact_3d"].shape == (1, nv)
+    assert np.abs(out["pred_contact_3d"].cpu().numpy() - want).max() < 1e-5
+    # teacher-forced path with object predictors switched on
+    full = torch.cat([ids, ans], 1)
+    model.oC_loss_weight, old = 3.0, model.oC_loss_weight
+    try:
+        for ds, key in (("piad_oafford", "pred_object_3d_afford"), ("pico_ocontact", "pred_object_3d_contact")):
+            res = model(images=sam, images_clip=clip, input_ids=full, labels=full, attention_masks=torch.ones_like(full),
+                        offset=torch.tensor([0, 1]), masks_list=[torch.zeros(4, 1, *SIZE)], label_list=[torch.zeros(SIZE)],
+                        gt_contact_3d_list=[None], cam_params=cam, resize_list=[SIZE], ds_name_list=[ds],
+                        mask_paths_list=[mask_paths], inference=True)
+            pm = torch.stack(res["pred_masks"], 0).cpu().numpy()
+            if "oafford" in ds:   # HM view type: the maps were sigmoid-ed before lifting (InteractVLM.py:452-456)
+                assert pm.min() >= 0 and pm.max() <= 1
+                assert np.abs(res[key].cpu().numpy() - OL.lift_points(pm, p2p, 2048)).max() < 1e-5
+                assert res["pred_object_3d_contact"].shape == (1, 0)   # 'ocontact' not in ds_name (components.py:430)
+            else:
+                assert np.abs(res[key].cpu().numpy() - OL.lift_object_mesh(pm, op2v, obary, nv)).max() < 1e-5
+                assert res["pred_object_3d_afford"].abs().max().item() == 0
+            assert res["pred_human_3d_contact"].abs().max().item() == 0  # not an hcontact sample
+    finally:
+        model.oC_loss_weight = old

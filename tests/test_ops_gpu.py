@@ -276,15 +276,16 @@ def test_rope_paged_decode(ctx):
     positions = torch.arange(T, dtype=torch.int32, device=DEV)
     pages = torch.tensor([2, 0, 1], dtype=torch.int32)
     slot = (pages[(positions.cpu() // page).long()] * page + positions.cpu() % page).to(torch.int32).to(DEV)
-    kc = torch.zeros(3 * page, H, hd, device=DEV, dtype=torch.bfloat16)
+    kc = torch.zeros(3, H, page, hd, device=DEV, dtype=torch.bfloat16)  # [pages, H, page, hd]
     vc = torch.zeros_like(kc)
-    q_out, k_out, v_out = ctx.rope_kv_store(qkv, positions, slot, cos_t, sin_t, H, hd, kc, vc)
+    q_out, k_out, v_out = ctx.rope_kv_store(qkv, positions, slot, cos_t, sin_t, H, hd, kc, vc, page_size=page)
     q, k, v = (qkv[:, i * D:(i + 1) * D].view(T, H, hd) for i in range(3))
     c, s = cos_t[:T, None, :], sin_t[:T, None, :]
     assert torch.equal(q_out.view(T, H, hd), _rope_ref(q, c, s))
     assert torch.equal(k_out.view(T, H, hd), _rope_ref(k, c, s))
     assert torch.equal(v_out.view(T, H, hd), v)
-    assert torch.equal(kc[slot.long()], k_out.view(T, H, hd)) and torch.equal(vc[slot.long()], v)
+    sl = slot.long()
+    assert torch.equal(kc[sl // page, :, sl % page], k_out.view(T, H, hd)) and torch.equal(vc[sl // page, :, sl % page], v)
     # decode attention for a "next token" query over those T keys
     qd = rnd(1, D, seed=45)
     bt = pages.view(1, 3).to(DEV)

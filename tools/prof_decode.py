@@ -22,8 +22,8 @@ x, xf, gam = rnd(B, D), rnd(B, F), rnd(D)
 gu = rnd(B, 2 * F)
 qkv = rnd(B, 3 * D)
 page, pages = 16, 24
-kc = [rnd(B * pages * page, H, hd) for _ in range(NW)]
-vc = [rnd(B * pages * page, H, hd) for _ in range(NW)]
+kc = [rnd(B * pages, H, page, hd) for _ in range(NW)]
+vc = [rnd(B * pages, H, page, hd) for _ in range(NW)]
 bt = torch.arange(B * pages, dtype=torch.int32, device="cuda").view(B, pages)
 sl = torch.full((B,), L, dtype=torch.int32, device="cuda")
 pos = torch.full((B,), L - 1, dtype=torch.int32, device="cuda")
@@ -63,7 +63,7 @@ ops = {
     "gemm_o_nosplit": (lambda i: ctx.gemm(x, wo[i % NW], residual=x, k_splits=1), D * D * 2),
     "gemm_down_nosplit": (lambda i: ctx.gemm(xf, wd[i % NW], residual=x, k_splits=1), F * D * 2),
     "rmsnorm": (lambda i: ctx.rmsnorm(x, gam, 1e-5), 0),
-    "rope_kv_store": (lambda i: ctx.rope_kv_store(qkv, pos, slot, cos_t, sin_t, H, hd, kc[i % NW], vc[i % NW], want_kv=False), 0),
+    "rope_kv_store": (lambda i: ctx.rope_kv_store(qkv, pos, slot, cos_t, sin_t, H, hd, kc[i % NW], vc[i % NW], want_kv=False, page_size=page), 0),
     "decode_attention": (lambda i: ctx.decode_attention(q, kc[i % NW], vc[i % NW], bt, sl, H, hd, page), 2 * B * L * D * 2),
     "silu_mul": (lambda i: ctx.silu_mul(gu), 0),
 }
