@@ -257,63 +257,61 @@ __global__ void sam_relpos_kernel(const bf16* __restrict__ qkv, const bf16* __re
 
 // ------------------------------------------------------------------------------------------------ paged decode
 // CTA per (b, head), 8 warps. HF LlamaAttention eager numerics (transformers 4.31): scores = bf16(bf16(q.k)/sqrt(hd)),
-// softmax in fp32 cast to bf16, bf16 P.V.  HBM-bound: every K/V row of the head (HD*2 bytes, contiguous) is read once.
-// A row is covered by HD/8 lanes with 16-byte loads, so one warp-wide load instruction fetches 32/(HD/8) rows and each
-// warp keeps DEC_UNROLL such instructions in flight before the first shuffle (>= 2 KB outstanding per warp).
-constexpr int DEC_WARPS = 8, DEC_UNROLL = 8, DEC_MAX_PAGES = 256;
+// softmax in fp32 cast to bf16, bf16 P.V.  HBM-bound.  The cache is [pages, H, 16, HD]: one (page, head) is a contiguous
+// 16*HD*2-byte run, and one warp iteration consumes exactly one page with 16/RPI independent 16-byte loads per lane
+// (a single block-table lookup, no per-row index arithmetic).
+constexpr int DEC_WARPS = 8, DEC_PAGE = 16, DEC_MAX_PAGES = 256;
 template <int HD>
 __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const bf16* __restrict__ q,
                                                                           const bf16* __restrict__ k_cache,
                                                                           const bf16* __restrict__ v_cache,
                                                                           const int* __restrict__ block_table,
                                                                           const int* __restrict__ seq_lens,
-                                                                          bf16* __restrict__ out, int H, int page,
-                                                                          int max_pages, float inv_scale) {
+                                                                          bf16* __restrict__ out, int H, int max_pages,
+                                                                          float inv_scale) {
     extern __shared__ float sc[];  // [seq_len] scores, then probabilities
     __shared__ float red[DEC_WARPS];
-    constexpr int LPR = HD / 8;        // lanes per row (16 for HD=128, 8 for HD=64)
-    constexpr int RPI = 32 / LPR;      // rows per warp-wide load instruction
-    constexpr int GROUP = RPI * DEC_UNROLL;  // rows per warp iteration
+    constexpr int LPR = HD / 8;            // lanes per row (16 for HD=128, 8 for HD=64)
+    constexpr int RPI = 32 / LPR;          // rows per warp-wide load instruction
+    constexpr int NLD = DEC_PAGE / RPI;    // load instructions per page
     __shared__ float part[DEC_WARPS * RPI][HD];
+    __shared__ int bt[DEC_MAX_PAGES];
     const int h = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = lane / LPR, li = lane % LPR;  // which row of the instruction, which 8-element slice of the row
+    const int sub = lane / LPR, li = lane % LPR;
     const int len = seq_lens[b];
-    __shared__ int bt[DEC_MAX_PAGES];  // this sample's block table: keeps the page lookup off the global-load latency chain
-    for (int i = threadIdx.x; i < max_pages; i += DEC_WARPS * 32) bt[i] = block_table[(long long)b * max_pages + i];
-    __syncthreads();
+    const int n_pages = (len + DEC_PAGE - 1) / DEC_PAGE;
+    for (int i = threadIdx.x; i < n_pages; i += DEC_WARPS * 32) bt[i] = block_table[(long long)b * max_pages + i];
     float qr[8];
     {
         const uint4 u = *reinterpret_cast<const uint4*>(q + ((long long)b * H + h) * HD + li * 8);
         const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y), d = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
         qr[0] = a.x; qr[1] = a.y; qr[2] = c.x; qr[3] = c.y; qr[4] = d.x; qr[5] = d.y; qr[6] = e.x; qr[7] = e.y;
     }
-    auto row_ptr = [&](const bf16* cache, int kpos) {  // cache layout [pages, H, page, HD]
-        const long long base = ((long long)bt[kpos / page] * H + h) * page + (kpos % page);
-        return reinterpret_cast<const uint4*>(cache + base * HD + li * 8);
-    };
+    __syncthreads();
+    const long long lane_off = (long long)sub * HD + li * 8;  // this lane's element offset inside a (page, head) run
     // ---- phase 1: scores
     float lmax = -INFINITY;
-    for (int k0 = warp * GROUP; k0 < len; k0 += DEC_WARPS * GROUP) {
-        uint4 kv[DEC_UNROLL];
+    for (int pg = warp; pg < n_pages; pg += DEC_WARPS) {
+        const bf16* base = k_cache + ((long long)bt[pg] * H + h) * (DEC_PAGE * HD) + lane_off;
+        const int k0 = pg * DEC_PAGE;
+        uint4 kv[NLD];
 #pragma unroll
-        for (int u = 0; u < DEC_UNROLL; ++u) {
-            const int kpos = k0 + u * RPI + sub;
-            kv[u] = kpos < len ? *row_ptr(k_cache, kpos) : make_uint4(0, 0, 0, 0);
-        }
-        float d[DEC_UNROLL];
+        for (int u = 0; u < NLD; ++u)
+            kv[u] = (k0 + u * RPI + sub < len) ? *reinterpret_cast<const uint4*>(base + u * RPI * HD) : make_uint4(0, 0, 0, 0);
+        float d[NLD];
 #pragma unroll
-        for (int u = 0; u < DEC_UNROLL; ++u) {
+        for (int u = 0; u < NLD; ++u) {
             const float2 a = unpack_bf16x2(kv[u].x), c = unpack_bf16x2(kv[u].y), e = unpack_bf16x2(kv[u].z), f = unpack_bf16x2(kv[u].w);
             d[u] = qr[0] * a.x + qr[1] * a.y + qr[2] * c.x + qr[3] * c.y + qr[4] * e.x + qr[5] * e.y + qr[6] * f.x + qr[7] * f.y;
         }
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) {
 #pragma unroll
-            for (int u = 0; u < DEC_UNROLL; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+            for (int u = 0; u < NLD; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
         }
 #pragma unroll
-        for (int u = 0; u < DEC_UNROLL; ++u) {
+        for (int u = 0; u < NLD; ++u) {
             const int kpos = k0 + u * RPI + sub;
             if (kpos < len) {
                 const float x = bf16_round(bf16_round(d[u]) / inv_scale);
@@ -347,18 +345,20 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int k0 = warp * GROUP; k0 < len; k0 += DEC_WARPS * GROUP) {
-        uint4 vv[DEC_UNROLL];
-        float pr[DEC_UNROLL];
+    for (int pg = warp; pg < n_pages; pg += DEC_WARPS) {
+        const bf16* base = v_cache + ((long long)bt[pg] * H + h) * (DEC_PAGE * HD) + lane_off;
+        const int k0 = pg * DEC_PAGE;
+        uint4 vv[NLD];
+        float pr[NLD];
 #pragma unroll
-        for (int u = 0; u < DEC_UNROLL; ++u) {
+        for (int u = 0; u < NLD; ++u) {
             const int kpos = k0 + u * RPI + sub;
             const bool ok = kpos < len;
-            vv[u] = ok ? *row_ptr(v_cache, kpos) : make_uint4(0, 0, 0, 0);
+            vv[u] = ok ? *reinterpret_cast<const uint4*>(base + u * RPI * HD) : make_uint4(0, 0, 0, 0);
             pr[u] = ok ? bf16_round(sc[kpos] * inv) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < DEC_UNROLL; ++u) {
+        for (int u = 0; u < NLD; ++u) {
             const float2 a = unpack_bf16x2(vv[u].x), c = unpack_bf16x2(vv[u].y), e = unpack_bf16x2(vv[u].z), f = unpack_bf16x2(vv[u].w);
             acc[0] += pr[u] * a.x; acc[1] += pr[u] * a.y; acc[2] += pr[u] * c.x; acc[3] += pr[u] * c.y;
             acc[4] += pr[u] * e.x; acc[5] += pr[u] * e.y; acc[6] += pr[u] * f.x; acc[7] += pr[u] * f.y;
@@ -620,6 +620,7 @@ extern "C" int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, co
     IVLM_REQUIRE(smem <= 160 * 1024, "decode_attention: max context %d too long for the score buffer",
                  page_size * max_pages);
     IVLM_REQUIRE(max_pages <= DEC_MAX_PAGES, "decode_attention: more than %d pages per sequence", DEC_MAX_PAGES);
+    IVLM_REQUIRE(page_size == DEC_PAGE, "decode_attention: page_size %d not instantiated (%d)", page_size, DEC_PAGE);
     const float inv_scale = 1.0f / scale;  // reference divides by sqrt(hd)
     dim3 grid(H, B);
     if (hd == 128) {
@@ -627,13 +628,13 @@ extern "C" int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, co
                                              (int)smem));
         decode_attn_paged_kernel<128><<<grid, DEC_WARPS * 32, smem, stream>>>((const bf16*)q, (const bf16*)k_cache,
                                                                    (const bf16*)v_cache, block_table, seq_lens,
-                                                                   (bf16*)out, H, page_size, max_pages, inv_scale);
+                                                                   (bf16*)out, H, max_pages, inv_scale);
     } else if (hd == 64) {
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_paged_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
         decode_attn_paged_kernel<64><<<grid, DEC_WARPS * 32, smem, stream>>>((const bf16*)q, (const bf16*)k_cache,
                                                                   (const bf16*)v_cache, block_table, seq_lens, (bf16*)out,
-                                                                  H, page_size, max_pages, inv_scale);
+                                                                  H, max_pages, inv_scale);
     } else {
         set_error("decode_attention: head_dim %d not instantiated (64, 128)", hd);
         return IVLM_ERR_ARG;

@@ -13,6 +13,8 @@ __global__ void rope_kv_store_kernel(const bf16* __restrict__ qkv, const int* __
                                      const bf16* __restrict__ sin_t, bf16* __restrict__ q_out, bf16* __restrict__ k_out,
                                      bf16* __restrict__ v_out, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
                                      int H, int hd, int page) {
+    // grid (tokens, chunks): every thread owns one (head, rotary pair) and one 16-byte piece of the V row, so a
+    // decode step (8 tokens) spreads over ~100 CTAs instead of serialising ten dependent loads per thread in 8
     const long long tkn = blockIdx.x;
     const int pos = positions[tkn];
     const long long slot = slot_map ? slot_map[tkn] : -1;
@@ -25,7 +27,7 @@ __global__ void rope_kv_store_kernel(const bf16* __restrict__ qkv, const int* __
     const bf16* qr = qkv + tkn * 3LL * D;
     const bf16* kr = qr + D;
     const bf16* vr = kr + D;
-    for (int i = threadIdx.x; i < H * half; i += blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < H * half; i += gridDim.y * blockDim.x) {
         const int hh = i / half, j = i % half;
         const float c = __bfloat162float(cos_t[(long long)pos * hd + j]);
         const float s = __bfloat162float(sin_t[(long long)pos * hd + j]);
@@ -43,7 +45,7 @@ __global__ void rope_kv_store_kernel(const bf16* __restrict__ qkv, const int* __
             if (slot >= 0) { k_cache[cidx(hh, j)] = o1; k_cache[cidx(hh, j + half)] = o2; }
         }
     }
-    for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < (D >> 3); i += gridDim.y * blockDim.x) {
         const uint4 u = reinterpret_cast<const uint4*>(vr)[i];
         if (v_out) reinterpret_cast<uint4*>(v_out + tkn * D)[i] = u;
         if (slot >= 0) *reinterpret_cast<uint4*>(v_cache + cidx((i * 8) / hd, (i * 8) % hd)) = u;
@@ -167,7 +169,11 @@ extern "C" int ivlm_rope_kv_store_bf16(ivlm_handle h, const void* qkv, const int
     IVLM_REQUIRE(h && T > 0 && (H * hd) % 8 == 0 && hd % 8 == 0, "rope: bad shape");
     IVLM_REQUIRE(slot_map == nullptr || page_size > 0, "rope: page_size must be positive when a cache is written");
     IVLM_REQUIRE(slot_map == nullptr || (k_cache && v_cache), "rope: slot_map given without caches");
-    rope_kv_store_kernel<<<T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    const int items = H * (hd / 2);
+    int chunks = (items + 255) / 256;
+    if ((long long)T * chunks > 4LL * h->num_sms) chunks = (int)((4LL * h->num_sms + T - 1) / T);  // prefill: fewer, looping CTAs
+    if (chunks < 1) chunks = 1;
+    rope_kv_store_kernel<<<dim3(T, chunks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         (const bf16*)qkv, positions, slot_map, (const bf16*)cos_t, (const bf16*)sin_t, (bf16*)q_out, (bf16*)k_out,
         (bf16*)v_out, (bf16*)k_cache, (bf16*)v_cache, H, hd, page_size > 0 ? page_size : 1);
     h->launches++;

@@ -83,6 +83,9 @@ class Context:
                 work = 0.0
                 if _name == "gemm":
                     work = 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0]
+                    if a[0].shape[0] <= 64:  # swapped-operand weight streaming (decode, decoder tokens): HBM-bound
+                        _name = "gemm_small_m"
+                        work = 2.0 * a[1].shape[0] * a[1].shape[1]  # bytes of weights read
                 elif _name == "sam_attention":
                     Bq, nh, S_, hd_ = a[3], a[4], a[5] * a[6], a[7]
                     work = 4.0 * Bq * nh * S_ * S_ * hd_
