@@ -39,7 +39,9 @@ IVLM_API int ivlm_abi_version(void);
 /* Caller-owned scratch in device memory (>= 1 MiB; 32 MiB covers every shape on the path).  With a workspace bound,
  * weight-streaming GEMMs (small token counts) split K across CTAs and reduce the partials in-kernel, deterministically. */
 IVLM_API int ivlm_set_workspace(ivlm_handle h, void* ptr, size_t bytes, void* stream);
-/* Tuning / A-B switches (integer options): "window_attn_variant" 0 = single-tile window kernel (default), 1 = tiled kernel. */
+/* Tuning / A-B switches (integer options): "window_attn_variant" 0 = single-tile window kernel (default), 1 = tiled kernel;
+ * "pdl" 1 = launch the LLaMA decode-chain kernels with programmatic dependent launch (prologues overlap the predecessor's
+ * tail; every such kernel executes griddepcontrol.wait before reading its inputs). */
 IVLM_API int ivlm_set_option(ivlm_handle h, const char* name, int32_t value);
 /* kernels launched through this handle so far (bench.py's "gpu_launches") */
 IVLM_API uint64_t ivlm_launch_count(ivlm_handle h);

@@ -42,6 +42,10 @@ extern "C" uint64_t ivlm_launch_count(ivlm_handle h) { return h ? h->launches : 
 
 extern "C" int ivlm_set_option(ivlm_handle h, const char* name, int32_t value) {
     IVLM_REQUIRE(h && name, "set_option: null");
+    if (std::string(name) == "pdl") {
+        h->pdl = value ? 1 : 0;
+        return IVLM_OK;
+    }
     if (std::string(name) == "window_attn_variant") {
         h->window_attn_variant = value;
         return IVLM_OK;

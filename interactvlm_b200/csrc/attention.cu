@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
     constexpr int NLD = DEC_PAGE / RPI;    // load instructions per page
     __shared__ float part[DEC_WARPS * RPI][HD];
     __shared__ int bt[DEC_MAX_PAGES];
+    pdl_wait();
     const int h = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane / LPR, li = lane % LPR;
@@ -626,15 +627,15 @@ extern "C" int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, co
     if (hd == 128) {
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_paged_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
-        decode_attn_paged_kernel<128><<<grid, DEC_WARPS * 32, smem, stream>>>((const bf16*)q, (const bf16*)k_cache,
-                                                                   (const bf16*)v_cache, block_table, seq_lens,
-                                                                   (bf16*)out, H, max_pages, inv_scale);
+        IVLM_CHECK_CUDA(launch_k(h, decode_attn_paged_kernel<128>, grid, dim3(DEC_WARPS * 32), smem, stream, (const bf16*)q,
+                                 (const bf16*)k_cache, (const bf16*)v_cache, (const int*)block_table, (const int*)seq_lens,
+                                 (bf16*)out, (int)H, (int)max_pages, inv_scale));
     } else if (hd == 64) {
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_paged_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
-        decode_attn_paged_kernel<64><<<grid, DEC_WARPS * 32, smem, stream>>>((const bf16*)q, (const bf16*)k_cache,
-                                                                  (const bf16*)v_cache, block_table, seq_lens, (bf16*)out,
-                                                                  H, max_pages, inv_scale);
+        IVLM_CHECK_CUDA(launch_k(h, decode_attn_paged_kernel<64>, grid, dim3(DEC_WARPS * 32), smem, stream, (const bf16*)q,
+                                 (const bf16*)k_cache, (const bf16*)v_cache, (const int*)block_table, (const int*)seq_lens,
+                                 (bf16*)out, (int)H, (int)max_pages, inv_scale));
     } else {
         set_error("decode_attention: head_dim %d not instantiated (64, 128)", hd);
         return IVLM_ERR_ARG;

@@ -87,6 +87,11 @@ IVLM_DEVINL void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// (prologue, barrier / TMEM setup, prefetch of static operands) while its predecessor drains; it must execute this
+// wait before touching anything the predecessor wrote.  Without the attribute the instruction returns immediately.
+IVLM_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 IVLM_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -47,6 +47,7 @@ struct GemmParams {
     int fused_split;  // split-K with in-kernel reduction: partial tiles -> workspace, the last CTA of a tile sums them
     float* ws_partial;  // [tiles * k_splits][BM][BN] fp32
     int* ws_counter;    // [tiles], zero between launches (the reducing CTA resets its counter)
+    int a_static;     // operand A is a weight matrix (swapped form): safe to prefetch before griddepcontrol.wait
     int n_fastest;    // tile order (see tile_coords)
     int staged;       // bf16 row-major output through the shared-memory staged epilogue
 };
@@ -155,6 +156,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            // Programmatic dependent launch: operand A of the swapped form is a static weight matrix, so the first
+            // pipeline stages of this CTA's first unit can start streaming before the predecessor kernel has finished.
+            int prefetched = 0;
+            if (p.a_static && blockIdx.x < total_units) {
+                const int u = blockIdx.x;
+                const int ks = u % p.k_splits;
+                int m0, n0;
+                tile_coords(p, u / p.k_splits, BN, m0, n0);
+                const int kb0 = ks * p.k_blocks_per_split;
+                const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+                for (int kb = kb0; kb < kb1 && prefetched < STAGES; ++kb, ++prefetched) {
+                    mbar_arrive_expect_tx(&full_bar[prefetched], Cfg::STAGE_BYTES);
+                    tma_load_2d(smem_a + prefetched * Cfg::A_BYTES, &tmA, &full_bar[prefetched], kb * BK, m0);
+                }
+            }
+            pdl_wait();
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int ks = u % p.k_splits;
                 const int t = u / p.k_splits;
@@ -163,10 +180,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const int kb0 = ks * p.k_blocks_per_split;
                 const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
-                    tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+                    if (prefetched > 0) {  // weights of this stage are already in flight: add the activation tile
+                        --prefetched;
+                        tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+                    } else {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
+                        tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -205,6 +227,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
     } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------ epilogue
+        pdl_wait();  // bias / residual / row_map / split-K workspace may come from the predecessor
         const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
         const int chalf = (warp - EPI_WARP0) >> 2;  // which half of the columns this warp of the quadrant takes
         int it = 0;
@@ -525,9 +548,8 @@ static int launch_gemm(ivlm_ctx* h, const CUtensorMap* ta, const CUtensorMap* tb
     }
     const int units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
     const int grid = units < h->num_sms ? units : h->num_sms;
-    gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, p);
+    IVLM_CHECK_CUDA(launch_k(h, gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, *ta, *tb, p));
     h->launches++;
-    IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;
 }
 
@@ -620,6 +642,7 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
     p.staged = (!swap && !split && a->out_dtype == IVLM_BF16 && !a->no_round && bn >= 64) ? 1 : 0;
     // keep the smaller operand L2-resident across the sweep of the other dimension
     p.n_fastest = ((long long)p.N * p.K < (long long)p.M * p.K) ? 1 : 0;
+    p.a_static = swap ? 1 : 0;
 
     const CUtensorMap *ta, *tb;
     IVLM_TRY(get_tmap_bf16(h, pa, p.M, p.K, lda, BM, &ta));

@@ -13,6 +13,7 @@ __global__ void rope_kv_store_kernel(const bf16* __restrict__ qkv, const int* __
                                      const bf16* __restrict__ sin_t, bf16* __restrict__ q_out, bf16* __restrict__ k_out,
                                      bf16* __restrict__ v_out, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
                                      int H, int hd, int page) {
+    pdl_wait();
     // grid (tokens, chunks): every thread owns one (head, rotary pair) and one 16-byte piece of the V row, so a
     // decode step (8 tokens) spreads over ~100 CTAs instead of serialising ten dependent loads per thread in 8
     const long long tkn = blockIdx.x;
@@ -108,6 +109,7 @@ __global__ void decode_prepare_kernel(int* __restrict__ state, int S, const int*
                                       const int* __restrict__ next, int* __restrict__ done, int* __restrict__ out_tokens,
                                       int* __restrict__ tok, int* __restrict__ pos, int* __restrict__ slot,
                                       int* __restrict__ seq_lens, const int* __restrict__ slot_base, int eos, int pad, int B) {
+    pdl_wait();
     const int step = state[0];
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -129,6 +131,7 @@ __global__ void decode_prepare_kernel(int* __restrict__ state, int S, const int*
 // hidden[b, S + step, :] = hid_step[b, :]
 __global__ void decode_finish_kernel(const int* __restrict__ state, int S, const bf16* __restrict__ hid_step,
                                      bf16* __restrict__ hidden, int D, int max_len) {
+    pdl_wait();
     const int b = blockIdx.x, p = S + state[1];
     const uint4* src = reinterpret_cast<const uint4*>(hid_step + (long long)b * D);
     uint4* dst = reinterpret_cast<uint4*>(hidden + ((long long)b * max_len + p) * D);
@@ -145,8 +148,9 @@ extern "C" int ivlm_decode_prepare(ivlm_handle h, int32_t* state, int32_t S, con
                                    int32_t B, void* stream) {
     IVLM_REQUIRE(h && state && next && done && out_tokens && tok && pos && slot && seq_lens && slot_base && B > 0 && G > 0,
                  "decode_prepare: bad arguments");
-    decode_prepare_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(state, S, scripted, G, next, done, out_tokens,
-                                                                                 tok, pos, slot, seq_lens, slot_base, eos, pad, B);
+    IVLM_CHECK_CUDA(launch_k(h, decode_prepare_kernel, dim3(1), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), (int*)state,
+                             (int)S, (const int*)scripted, (int)G, (const int*)next, (int*)done, (int*)out_tokens, (int*)tok,
+                             (int*)pos, (int*)slot, (int*)seq_lens, (const int*)slot_base, (int)eos, (int)pad, (int)B));
     h->launches++;
     IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;
@@ -155,8 +159,8 @@ extern "C" int ivlm_decode_prepare(ivlm_handle h, int32_t* state, int32_t S, con
 extern "C" int ivlm_decode_finish(ivlm_handle h, const int32_t* state, int32_t S, const void* hid_step, void* hidden,
                                   int32_t B, int32_t D, int32_t max_len, void* stream) {
     IVLM_REQUIRE(h && state && hid_step && hidden && B > 0 && D % 8 == 0, "decode_finish: bad arguments");
-    decode_finish_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(state, S, (const bf16*)hid_step, (bf16*)hidden,
-                                                                                D, max_len);
+    IVLM_CHECK_CUDA(launch_k(h, decode_finish_kernel, dim3(B), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                             (const int*)state, (int)S, (const bf16*)hid_step, (bf16*)hidden, (int)D, (int)max_len));
     h->launches++;
     IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;
@@ -173,9 +177,10 @@ extern "C" int ivlm_rope_kv_store_bf16(ivlm_handle h, const void* qkv, const int
     int chunks = (items + 255) / 256;
     if ((long long)T * chunks > 4LL * h->num_sms) chunks = (int)((4LL * h->num_sms + T - 1) / T);  // prefill: fewer, looping CTAs
     if (chunks < 1) chunks = 1;
-    rope_kv_store_kernel<<<dim3(T, chunks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        (const bf16*)qkv, positions, slot_map, (const bf16*)cos_t, (const bf16*)sin_t, (bf16*)q_out, (bf16*)k_out,
-        (bf16*)v_out, (bf16*)k_cache, (bf16*)v_cache, H, hd, page_size > 0 ? page_size : 1);
+    IVLM_CHECK_CUDA(launch_k(h, rope_kv_store_kernel, dim3(T, chunks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                             (const bf16*)qkv, (const int*)positions, (const int*)slot_map, (const bf16*)cos_t, (const bf16*)sin_t,
+                             (bf16*)q_out, (bf16*)k_out, (bf16*)v_out, (bf16*)k_cache, (bf16*)v_cache, (int)H, (int)hd,
+                             (int)(page_size > 0 ? page_size : 1)));
     h->launches++;
     IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;

@@ -96,6 +96,7 @@ __global__ void rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
 __global__ void __launch_bounds__(256) rmsnorm_row_cta_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                                               const bf16* __restrict__ gamma, int D, float eps) {
     __shared__ float red[8];
+    pdl_wait();
     const long long row = blockIdx.x;
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
     const int nvec = D >> 3;
@@ -150,6 +151,7 @@ __global__ void add_bcast_kernel(const uint4* __restrict__ a, const uint4* __res
 }
 
 __global__ void silu_mul_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, long long rows, int F) {
+    pdl_wait();
     const int fvec = F >> 3;
     const long long total = rows * fvec;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -270,6 +272,7 @@ __global__ void embed_splice_kernel(const bf16* __restrict__ embed, const int* _
 
 __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int* __restrict__ idx, bf16* __restrict__ out, int n,
                                    int D, int max_row) {
+    pdl_wait();
     const int r = blockIdx.x;
     int s = idx[r];
     if (max_row > 0) s = s < 0 ? 0 : (s >= max_row ? max_row - 1 : s);
@@ -280,6 +283,7 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int* __rest
 
 // torch.argmax semantics: first maximal index. One CTA per row.
 __global__ void argmax_kernel(const float* __restrict__ logits, int* __restrict__ out, int vocab, long long ld) {
+    pdl_wait();
     const float* row = logits + (long long)blockIdx.x * ld;
     float best = -INFINITY;
     int bi = 0x7fffffff;
@@ -405,7 +409,8 @@ extern "C" int ivlm_rmsnorm_bf16(ivlm_handle h, const void* x, void* y, const vo
                                  float eps, void* stream) {
     IVLM_REQUIRE(h && D % 8 == 0 && rows > 0, "rmsnorm: D=%d must be a multiple of 8, rows>0", D);
     if (rows <= 4 * h->num_sms && D <= 8192) {
-        rmsnorm_row_cta_kernel<<<(unsigned)rows, 256, 0, STREAM>>>((const bf16*)x, (bf16*)y, (const bf16*)gamma, D, eps);
+        IVLM_CHECK_CUDA(launch_k(h, rmsnorm_row_cta_kernel, dim3((unsigned)rows), dim3(256), 0, STREAM, (const bf16*)x, (bf16*)y,
+                                 (const bf16*)gamma, D, eps));
     } else {
         const int wpb = 8;
         rmsnorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, STREAM>>>((const bf16*)x, (bf16*)y,
@@ -422,8 +427,8 @@ extern "C" int ivlm_add_bcast_bf16(ivlm_handle h, const void* a, const void* b, 
 }
 extern "C" int ivlm_silu_mul_bf16(ivlm_handle h, const void* gate_up, void* out, int64_t rows, int32_t F, void* stream) {
     IVLM_REQUIRE(h && F % 8 == 0, "silu_mul: F must be a multiple of 8");
-    silu_mul_kernel<<<grid_for(rows * (F / 8), 256, h->num_sms), 256, 0, STREAM>>>((const bf16*)gate_up, (bf16*)out, rows,
-                                                                                  F);
+    IVLM_CHECK_CUDA(launch_k(h, silu_mul_kernel, dim3(grid_for(rows * (F / 8), 256, h->num_sms)), dim3(256), 0, STREAM,
+                             (const bf16*)gate_up, (bf16*)out, (long long)rows, F));
     DONE();
 }
 extern "C" int ivlm_finalize_f32_bf16(ivlm_handle h, const float* acc, void* out, const void* bias, const void* residual,
@@ -469,19 +474,21 @@ extern "C" int ivlm_embed_splice_bf16(ivlm_handle h, const void* embed, const in
 extern "C" int ivlm_embed_gather_bf16(ivlm_handle h, const void* embed, const int32_t* ids, void* out, int32_t n,
                                       int32_t D, int32_t vocab, void* stream) {
     IVLM_REQUIRE(h && D % 8 == 0 && n > 0, "embed_gather: bad shape");
-    gather_rows_kernel<<<n, 128, 0, STREAM>>>((const bf16*)embed, ids, (bf16*)out, n, D, vocab);
+    IVLM_CHECK_CUDA(launch_k(h, gather_rows_kernel, dim3(n), dim3(128), 0, STREAM, (const bf16*)embed, (const int*)ids,
+                             (bf16*)out, (int)n, (int)D, (int)vocab));
     DONE();
 }
 extern "C" int ivlm_gather_rows_bf16(ivlm_handle h, const void* x, const int32_t* idx, void* out, int32_t n, int32_t D,
                                      void* stream) {
     IVLM_REQUIRE(h && D % 8 == 0 && n > 0, "gather_rows: bad shape");
-    gather_rows_kernel<<<n, 128, 0, STREAM>>>((const bf16*)x, idx, (bf16*)out, n, D, 0);
+    IVLM_CHECK_CUDA(launch_k(h, gather_rows_kernel, dim3(n), dim3(128), 0, STREAM, (const bf16*)x, (const int*)idx,
+                             (bf16*)out, (int)n, (int)D, 0));
     DONE();
 }
 extern "C" int ivlm_argmax_f32(ivlm_handle h, const float* logits, int32_t* out, int32_t B, int32_t vocab, int64_t ld,
                                void* stream) {
     IVLM_REQUIRE(h && B > 0 && vocab > 0, "argmax: empty");
-    argmax_kernel<<<B, 1024, 0, STREAM>>>(logits, out, vocab, ld);
+    IVLM_CHECK_CUDA(launch_k(h, argmax_kernel, dim3(B), dim3(1024), 0, STREAM, logits, (int*)out, (int)vocab, (long long)ld));
     DONE();
 }
 extern "C" int ivlm_bilinear_f32(ivlm_handle h, const float* src, float* dst, int32_t N, int32_t sh, int32_t sw,

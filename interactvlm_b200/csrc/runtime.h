@@ -79,6 +79,7 @@ struct ivlm_ctx {
     int device = 0;
     int num_sms = 148;
     uint64_t launches = 0;  // kernels launched through this handle (bench "gpu_launches")
+    int pdl = 0;                  // 1: launch the decode-chain kernels with programmatic dependent launch
     int window_attn_variant = 0;  // 0: single-tile 2-CTA/SM window kernel, 1: the general tiled kernel (A/B switch)
     std::unordered_map<ivlm::TmapKey, CUtensorMap, ivlm::TmapKeyHash> tmaps;
     std::unordered_map<std::string, ivlm::Weight> weights;
@@ -96,6 +97,24 @@ struct ivlm_ctx {
 };
 
 namespace ivlm {
+// Kernel launch with (optionally) the programmatic-stream-serialization attribute.  Only for kernels that execute
+// pdl_wait() before reading their inputs.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(const ivlm_ctx* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Returns (creating and caching if needed) a 2D bf16 tensor map: rows x cols, row pitch ld elements,
 // box = box_rows x 64 elements, 128B swizzle, zero OOB fill.
 int get_tmap_bf16(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
