@@ -361,6 +361,7 @@ def main():
                                 "peak_source": pk["source"] + " sustained cuBLAS bf16 (kernel timed inside a long step)",
                                 "launches_per_step": g["launches"], "share_of_kernel_time": g["ms"] / tot}
             line["kernel_time_shares"] = {k: round(r["ms"] / tot, 4) for k, r in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
+            line["kernel_ms_eager_pass"] = {k: round(r["ms"], 2) for k, r in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
             if "sam_attention" in rep:
                 a = rep["sam_attention"]
                 line["sam_attention_tflops"] = a["work"] / (a["ms"] / 1e3) / 1e12

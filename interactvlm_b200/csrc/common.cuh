@@ -56,25 +56,36 @@ IVLM_DEVINL float apply_act(float x, int act) {
     }
 }
 
+// Raw SFU approximations (no range fix-up code: the arguments below are always well inside the valid range).
+IVLM_DEVINL float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+IVLM_DEVINL float ex2_approx_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // GELU (erf form) with the Abramowitz-Stegun 7.1.26 rational erf (|err| <= 1.5e-7, far below bf16 resolution):
 // 0.5*x*(1+erf(x/sqrt2)); the negative branch uses 1+erf(-z) = poly*exp(-z^2) directly (no cancellation).
 IVLM_DEVINL float gelu_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(t, poly, 1.421413741f);
-    poly = fmaf(t, poly, -0.284496736f);
-    poly = fmaf(t, poly, 0.254829592f);
-    const float pe = poly * t * __expf(-z * z);
-    return 0.5f * x * (x < 0.f ? pe : 2.0f - pe);
+    // with z = |x|/sqrt2: t = 1/(1 + p z), half_pe = 0.5 * poly(t) * t * exp(-z^2); constants pre-folded
+    const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+    float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+    poly = fmaf(t, poly, 0.5f * 1.421413741f);
+    poly = fmaf(t, poly, 0.5f * -0.284496736f);
+    poly = fmaf(t, poly, 0.5f * 0.254829592f);
+    const float half_pe = poly * t * ex2_approx_ftz((x * x) * (-0.5f * 1.4426950408889634f));
+    return x * (x < 0.f ? half_pe : 1.0f - half_pe);
 }
 // act followed by the bf16 rounding the eager reference applies to the activation output
 IVLM_DEVINL float apply_act_fast(float x, int act) {
     switch (act) {
         case ACT_GELU: return gelu_fast(x);
-        case ACT_QUICK_GELU: return __fdividef(x, 1.0f + __expf(-1.702f * x));
+        case ACT_QUICK_GELU: return x * rcp_approx(1.0f + ex2_approx_ftz(x * (-1.702f * 1.4426950408889634f)));
         case ACT_RELU: return fmaxf(x, 0.0f);
-        case ACT_SILU: return __fdividef(x, 1.0f + __expf(-x));
+        case ACT_SILU: return x * rcp_approx(1.0f + ex2_approx_ftz(x * -1.4426950408889634f));
         default: return x;
     }
 }

@@ -4,4 +4,4 @@ d = json.loads(sys.stdin.read())
 print({k: d[k] for k in ('value','ms_per_step','gpu_launches')}, 'e2e', d['e2e']['value'])
 print(d.get('stage_ms'), d.get('decode_hbm'))
 print(d.get('roofline'))
-print(d.get('kernel_time_shares'))"
+print(d.get('kernel_ms_eager_pass'))"
