@@ -111,6 +111,12 @@ IVLM_API int ivlm_im2col_patch_bf16(ivlm_handle h, const void* img, void* cols, 
 IVLM_API int ivlm_im2col_3x3_bf16(ivlm_handle h, const void* x, void* cols, int32_t N, int32_t H, int32_t W, int32_t C,
                          void* stream);
 
+/* Input pipeline (run_demo.py:65-79 `preprocess`, CLIPImageProcessor rescale + normalise): uint8 HWC images [N,H,W,3]
+ * (already resized on the host like the reference does) -> bf16 CHW [N,3,S,S], (x*pre_scale - mean[c]) / std[c], zero
+ * padded to S x S.  mean3_h / std3_h are HOST arrays of 3 floats. */
+IVLM_API int ivlm_preprocess_u8_bf16(ivlm_handle h, const uint8_t* img, void* out, int32_t N, int32_t H, int32_t W, int32_t S,
+                            float pre_scale, const float* mean3_h, const float* std3_h, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Attention. */
 typedef struct ivlm_attn_args {

@@ -381,6 +381,31 @@ __global__ void sigmoid_where_kernel(float* __restrict__ x, const float* __restr
         if (gt == nullptr || gt[i] != ignore) x[i] = 1.f / (1.f + expf(-x[i]));
 }
 
+// uint8 HWC image -> normalised, zero-padded bf16 CHW: out[n,c,y,x] = bf16((img[n,y,x,c] * pre - mean[c]) / std[c]) for
+// y < H, x < W, else 0.  SAM: pre = 1, mean/std in 0..255 units, S = 1024 (run_demo.py:65-79); CLIP: pre = 1/255
+// (CLIPImageProcessor rescale) and S = H = W = 224.  One thread per 8 output pixels of a row (16-byte store).
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int N, int H, int W, int S,
+                                     float pre, float m0, float m1, float m2, float s0, float s1, float s2) {
+    const long long total = (long long)N * 3 * S * (S / 8);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xv = (int)(i % (S / 8));
+        long long r = i / (S / 8);
+        const int y = (int)(r % S);
+        r /= S;
+        const int c = (int)(r % 3), n = (int)(r / 3);
+        const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int x = xv * 8 + j;
+            v[j] = (y < H && x < W) ? ((float)img[(((long long)n * H + y) * W + x) * 3 + c] * pre - mean) / sd : 0.f;
+        }
+        uint4 q;
+        q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(out + (((long long)n * 3 + c) * S + y) * S + xv * 8) = q;
+    }
+}
+
 static inline int grid_for(long long work, int block, int sms) {
     long long g = (work + block - 1) / block;
     long long cap = (long long)sms * 16;
@@ -511,5 +536,15 @@ extern "C" int ivlm_cam_gate_bf16(ivlm_handle h, const void* cam, const void* em
 extern "C" int ivlm_sigmoid_where_f32(ivlm_handle h, float* x, const float* gt, float ignore_value, int64_t n, void* stream) {
     IVLM_REQUIRE(h && x && n > 0, "sigmoid_where: bad arguments");
     sigmoid_where_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, STREAM>>>(x, gt, ignore_value, n);
+    DONE();
+}
+
+extern "C" int ivlm_preprocess_u8_bf16(ivlm_handle h, const uint8_t* img, void* out, int32_t N, int32_t H, int32_t W, int32_t S,
+                                       float pre_scale, const float* mean3_h, const float* std3_h, void* stream) {
+    IVLM_REQUIRE(h && img && out && mean3_h && std3_h && N > 0 && H > 0 && W > 0 && H <= S && W <= S && S % 8 == 0,
+                 "preprocess: bad arguments (N=%d H=%d W=%d S=%d)", N, H, W, S);
+    const long long total = (long long)N * 3 * S * (S / 8);
+    preprocess_u8_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, STREAM>>>(img, (bf16*)out, N, H, W, S, pre_scale, mean3_h[0],
+                                                                             mean3_h[1], mean3_h[2], std3_h[0], std3_h[1], std3_h[2]);
     DONE();
 }

@@ -1,0 +1,116 @@
+"""Caller-side pieces of the reference's harnesses that sit directly on either side of the hot path:
+
+  * input preparation of `run_demo.py:330-379` with the normalise / pad / cast fused on the GPU (`ops.preprocess_u8`);
+  * `convert_contacts` (utils/utils.py:428-443) as a CSR SpMV, and the on-disk result formats of `run_demo.py:438-463`
+    (`*_hcontact_vertices.npz` with `pred_contact_3d_smplh` / `pred_contact_3d_smplx`, `*_oafford_vertices.npz` with
+    `pred_contact_3d`);
+  * a batched `validate()` in the shape of `evaluate.py:41-302`: per-rank shard of the samples, `model.evaluate()` on
+    batches (the reference is batch 1), `get_h_contact_metrics` (utils/eval_utils.py:63-94) and ONE all-gather of the
+    predictions instead of all_gather(list) + all_gather_object + per-meter all_reduce (evaluate.py:185-222).
+
+Dataset classes, tokenisation and image decoding stay with the caller (they need the downloaded datasets).
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .parallel import gather_contacts, shard_range
+
+
+def prepare_inputs(model, image_u8, sam_views_u8):
+    """uint8 HWC images (already resized like the reference: CLIP 224x224 crop, SAM longest side 1024) ->
+    (images_clip [B,3,224,224] bf16, images [B,V,3,1024,1024] bf16, resize_list).
+    image_u8 [B,224,224,3]; sam_views_u8 [B,V,h,w,3] with h,w <= 1024 (zero padded to 1024 like `preprocess`)."""
+    cfg, ctx, dev = model.config, model.ctx, model.device
+    image_u8 = torch.as_tensor(image_u8).to(dev).contiguous()
+    sam_views_u8 = torch.as_tensor(sam_views_u8).to(dev).contiguous()
+    B, V, h, w, _ = sam_views_u8.shape
+    clip = ctx.preprocess_u8(image_u8, cfg.clip_image_size, kind="clip")
+    sam = ctx.preprocess_u8(sam_views_u8.view(B * V, h, w, 3), cfg.sam_img_size, kind="sam")
+    return clip, sam.view(B, V, 3, cfg.sam_img_size, cfg.sam_img_size), [(h, w)] * B
+
+
+class ContactConverter:
+    """convert_contacts(contact, mapping): dense [n_out, n_in] mapping applied as a CSR SpMV (the SMPL->SMPL-X matrix has
+    ~3 non-zeros per row; the reference streams the 289 MB dense matrix through bmm on every call)."""
+
+    def __init__(self, model, mapping: np.ndarray):
+        self.model = model
+        if getattr(model, "_emulated", False):
+            self._dense = torch.as_tensor(np.asarray(mapping, dtype=np.float32))
+            self._csr = None
+        else:
+            from .ops import CsrMatrix
+
+            self._csr = CsrMatrix(model.ctx, np.asarray(mapping, dtype=np.float32))
+
+    def __call__(self, contact: torch.Tensor) -> torch.Tensor:
+        x = contact.float().contiguous()
+        y = self._csr(x) if self._csr is not None else (self._dense @ x.T).T
+        return y.squeeze()  # the reference's .squeeze(): [10475] for a single sample
+
+
+def save_hcontact(path_prefix, pred_contact_3d, pred_contact_3d_smplx):
+    """`{dir}/{fname}_hcontact_vertices.npz` (run_demo.py:449-452)."""
+    out = Path(f"{path_prefix}_hcontact_vertices.npz")
+    np.savez(out, pred_contact_3d_smplh=pred_contact_3d.detach().cpu().numpy(),
+             pred_contact_3d_smplx=pred_contact_3d_smplx.detach().cpu().numpy())
+    return out
+
+
+def save_ocontact(path_prefix, pred_contact_3d):
+    """`{dir}/{fname}_oafford_vertices.npz` (run_demo.py:463)."""
+    out = Path(f"{path_prefix}_oafford_vertices.npz")
+    np.savez(out, pred_contact_3d=pred_contact_3d.detach().cpu().numpy())
+    return out
+
+
+def h_contact_metrics(contact_gt: torch.Tensor, contact_pred: torch.Tensor, threshold: float = 0.5):
+    """get_h_contact_metrics (utils/eval_utils.py:63-94): batch means of F1 / precision / recall."""
+    gt = (contact_gt.float() > 0).float()
+    pr = (contact_pred.float() >= threshold).float()
+    tp = (pr * gt).sum(-1)
+    precision = tp / (pr.sum(-1) + 1e-10)
+    recall = tp / (gt.sum(-1) + 1e-10)
+    f1 = 2 * precision * recall / (precision + recall + 1e-10)
+    return f1.mean().item(), precision.mean().item(), recall.mean().item()
+
+
+def validate(model, samples, batch_size=8, dist=None, max_new_tokens=32, contact_type="hcontact"):
+    """Batched evaluation over `samples` (a sequence of dicts with the keys evaluate() takes: images_clip, images,
+    input_ids, cam_params, resize, original_size, and optionally gt_contact_3d / scripted).  Samples are sharded
+    contiguously over the ranks of `dist` (torch.distributed or None); every rank returns the predictions of ALL samples
+    (one all-gather) and the metrics over those that carry a ground truth.  Prompts inside one batch must have equal
+    length (batches are formed from consecutive samples of equal prompt length)."""
+    n = len(samples)
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    lo, hi = shard_range(n, rank, world)
+    preds = []
+    i = lo
+    while i < hi:
+        j = i + 1
+        L = samples[i]["input_ids"].shape[-1]
+        while j < hi and j - i < batch_size and samples[j]["input_ids"].shape[-1] == L:
+            j += 1
+        chunk = samples[i:j]
+        cat = lambda k: torch.stack([torch.as_tensor(s[k]) for s in chunk], 0)
+        scripted = cat("scripted") if all("scripted" in s for s in chunk) else None
+        out = model.evaluate(cat("images_clip"), cat("images"), cat("input_ids"), cat("cam_params"),
+                             [tuple(s["resize"]) for s in chunk], [tuple(s["original_size"]) for s in chunk],
+                             contact_type=contact_type, max_new_tokens=max_new_tokens, scripted=scripted)
+        preds.append(out["pred_contact_3d"])
+        i = j
+    n_out = preds[0].shape[1] if preds else 6890
+    local = torch.cat(preds, 0) if preds else torch.zeros((0, n_out), device=model.device)
+    allp = gather_contacts(local, dist, n_samples=n) if world > 1 else local
+    gts = [s.get("gt_contact_3d") for s in samples]
+    metrics = None
+    if all(g is not None for g in gts) and n > 0:
+        gt = torch.stack([torch.as_tensor(g) for g in gts], 0).to(allp.device)
+        f1, p, r = h_contact_metrics(gt, allp)
+        metrics = {"f1": f1, "precision": p, "recall": r, "n": n}
+    return allp, metrics

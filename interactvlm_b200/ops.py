@@ -382,6 +382,20 @@ class Context:
                                                 i32(grid), self.stream), "upscale_hyper_dot")
         return out
 
+    SAM_MEAN, SAM_STD = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+    CLIP_MEAN, CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+
+    def preprocess_u8(self, img_u8, size, kind="sam"):
+        """uint8 [N,H,W,3] device tensor -> normalised bf16 [N,3,size,size] (zero padded).  kind: 'sam' | 'clip'."""
+        assert img_u8.dtype == torch.uint8 and img_u8.is_cuda and img_u8.is_contiguous() and img_u8.shape[-1] == 3
+        N, H, W, _ = img_u8.shape
+        mean, std, pre = (self.SAM_MEAN, self.SAM_STD, 1.0) if kind == "sam" else (self.CLIP_MEAN, self.CLIP_STD, 1.0 / 255.0)
+        out = torch.empty((N, 3, size, size), device=img_u8.device, dtype=torch.bfloat16)
+        m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+        L.check(self.lib.ivlm_preprocess_u8_bf16(self.h, P(img_u8), P(out), i32(N), i32(H), i32(W), i32(size), f32c(pre), m3, s3,
+                                                 self.stream), "preprocess_u8")
+        return out
+
     def sigmoid_where(self, x, gt=None, ignore_value=-1.0):
         """In place: x = sigmoid(x) where gt != ignore_value (everywhere when gt is None)."""
         assert x.dtype == torch.float32 and x.is_contiguous()

@@ -290,6 +290,15 @@ class EmuContext:
         m = m.view(Bv, G, G, 2, 2, 2, 2).permute(0, 1, 3, 5, 2, 4, 6).reshape(Bv, G * 4, G * 4)
         return _r(m)
 
+    def preprocess_u8(self, img_u8, size, kind="sam"):
+        self.launches += 1
+        from interactvlm_b200.ops import Context as _C
+        mean, std, pre = (_C.SAM_MEAN, _C.SAM_STD, 1.0) if kind == "sam" else (_C.CLIP_MEAN, _C.CLIP_STD, 1.0 / 255.0)
+        x = img_u8.float().permute(0, 3, 1, 2) * pre
+        x = (x - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+        N, _, H, W = x.shape
+        return F.pad(x, (0, size - W, 0, size - H)).to(BF)
+
     def sigmoid_where(self, x, gt=None, ignore_value=-1.0):
         self.launches += 1
         keep = torch.ones_like(x, dtype=torch.bool) if gt is None else gt != ignore_value

@@ -1,0 +1,58 @@
+"""GPU: input-preparation kernel (bit-exact vs the reference's preprocess formula in fp32 -> bf16), SMPL->SMPL-X SpMV and the
+batched validate loop through the CUDA path."""
+import numpy as np
+import pytest
+import torch
+
+from interactvlm_b200 import harness as Hn
+from interactvlm_b200 import synthetic as S
+from interactvlm_b200.config import IVLMConfig
+from oracle import lift as OL
+from oracle.make_goldens_model import TINY_SEED, tiny_inputs
+
+pytestmark = pytest.mark.gpu
+SIZE = (1024, 1024)
+
+
+@pytest.fixture(scope="module")
+def model(ctx):
+    from interactvlm_b200.model import InteractVLMForCausalLM
+
+    cfg = IVLMConfig.tiny()
+    sd = S.make_state_dict(cfg, seed=TINY_SEED["weights"])
+    m = InteractVLMForCausalLM(cfg, sd, ctx=ctx)
+    p2v, bary = S.make_mesh_lift_maps(seed=TINY_SEED["maps"])
+    m.set_human_lift_maps(p2v, bary)
+    return m
+
+
+def test_preprocess_kernel_bit_exact(model):
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (2, 224, 224, 3), dtype=np.uint8)
+    views = rng.integers(0, 256, (2, 4, 683, 1024, 3), dtype=np.uint8)   # padded at the bottom
+    clip, sam, resize = Hn.prepare_inputs(model, img, views)
+    assert resize == [(683, 1024)] * 2
+    x = torch.from_numpy(views).permute(0, 1, 4, 2, 3).float().cuda()
+    ref = (x - torch.tensor([123.675, 116.28, 103.53], device="cuda").view(1, 1, 3, 1, 1)) / \
+        torch.tensor([58.395, 57.12, 57.375], device="cuda").view(1, 1, 3, 1, 1)
+    ref = torch.nn.functional.pad(ref, (0, 0, 0, 1024 - 683)).bfloat16()
+    assert torch.equal(sam, ref)
+    c = torch.from_numpy(img).permute(0, 3, 1, 2).float().cuda() * (1.0 / 255.0)
+    cref = ((c - torch.tensor([0.48145466, 0.4578275, 0.40821073], device="cuda").view(1, 3, 1, 1))
+            / torch.tensor([0.26862954, 0.26130258, 0.27577711], device="cuda").view(1, 3, 1, 1)).bfloat16()
+    assert (clip.float() - cref.float()).abs().max().item() <= 2 ** -6  # <= 1 bf16 ulp at |x| < 4 (x/255 vs x*(1/255))
+
+
+def test_convert_contacts_spmv_and_validate(model):
+    mapping = S.make_smplx_matrix(seed=0)
+    conv = Hn.ContactConverter(model, mapping)
+    cfg = model.config
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
+    ref = model.evaluate(clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, max_new_tokens=ans.shape[1], scripted=ans)
+    smplx = conv(ref["pred_contact_3d"])
+    want = OL.convert_contacts(ref["pred_contact_3d"].cpu().numpy(), mapping)
+    assert smplx.shape == (2, S.N_SMPLX) and np.abs(smplx.cpu().numpy() - want).max() < 1e-5
+    samples = [dict(images_clip=clip[b], images=sam[b], input_ids=ids[b], cam_params=cam[b], resize=SIZE, original_size=SIZE,
+                    scripted=ans[b], gt_contact_3d=(ref["pred_contact_3d"][b] >= 0.5).float()) for b in range(2)]
+    preds, metrics = Hn.validate(model, samples, batch_size=2, max_new_tokens=ans.shape[1])
+    assert torch.equal(preds, ref["pred_contact_3d"]) and metrics["f1"] > 0.999
