@@ -355,9 +355,15 @@ def main():
             tot = sum(r["ms"] for r in rep.values())
             g = rep["gemm"]
             ach = g["work"] / (g["ms"] / 1e3) / 1e12
+            traffic = None
+            tp = ROOT / "profiles" / "r1_traffic.json"
+            if tp.exists():  # DRAM bytes of one representative launch (SAM MLP-1) from the committed ncu --set full capture
+                t = json.loads(tp.read_text())["launches"]["sam_mlp1 M=32768 N=5120 K=1280"]
+                traffic = {"dram_bytes_per_launch": t["dram_bytes"], "algorithmic_bytes_per_launch": t["algorithmic_bytes"],
+                           "launch": "sam_mlp1 M=32768 N=5120 K=1280", "source": "profiles/r1_traffic.json (ncu --set full)"}
             line["roofline"] = {"kernel": "gemm_bf16_tcgen05_kernel (token count > 64: SAM, CLIP, LLaMA prefill)", "bound": "tensor",
                                 "achieved": ach, "peak": pk["tf_sustained"],
-                                "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None,
+                                "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": traffic,
                                 "peak_source": pk["source"] + " sustained cuBLAS bf16 (kernel timed inside a long step)",
                                 "launches_per_step": g["launches"], "share_of_kernel_time": g["ms"] / tot}
             line["kernel_time_shares"] = {k: round(r["ms"] / tot, 4) for k, r in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
