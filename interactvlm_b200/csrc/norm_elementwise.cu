@@ -61,6 +61,67 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
     }
 }
 
+// Register-resident variant for D = 256 * VPL (SAM 1280, CLIP 1024, decoder 256): the row is read from HBM exactly once
+// (VPL 16-byte vectors per lane), statistics and the normalised output come from registers.
+template <int VPL>
+__global__ void __launch_bounds__(256) layernorm_reg_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                            const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                                                            long long out_rows, float eps, const int* __restrict__ row_map,
+                                                            int act) {
+    constexpr int D = VPL * 256;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= out_rows) return;
+    const int lane = threadIdx.x & 31;
+    long long src = row;
+    if (row_map != nullptr) src = row_map[row];
+    uint4* yr = reinterpret_cast<uint4*>(y + row * D);
+    if (src < 0) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) yr[lane + 32 * k] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const uint4* xr = reinterpret_cast<const uint4*>(x + src * D);
+    float v[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const uint4 q = xr[lane + 32 * k];
+        const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+        v[k][0] = a.x; v[k][1] = a.y; v[k][2] = b.x; v[k][3] = b.y; v[k][4] = c.x; v[k][5] = c.y; v[k][6] = d.x; v[k][7] = d.y;
+        s += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = v[k][j] - mean;
+            ss += t * t;
+        }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
+    const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
+    const uint4* b4 = reinterpret_cast<const uint4*>(beta);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const uint4 g = g4[lane + 32 * k], b = b4[lane + 32 * k];
+        const uint32_t gi[4] = {g.x, g.y, g.z, g.w}, bi[4] = {b.x, b.y, b.z, b.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 gv = unpack_bf16x2(gi[j]), bv = unpack_bf16x2(bi[j]);
+            float r0 = (v[k][2 * j] - mean) * rstd * gv.x + bv.x;
+            float r1 = (v[k][2 * j + 1] - mean) * rstd * gv.y + bv.y;
+            if (act != ACT_NONE) {
+                r0 = apply_act(bf16_round(r0), act);
+                r1 = apply_act(bf16_round(r1), act);
+            }
+            o[j] = pack_bf16x2(r0, r1);
+        }
+        yr[lane + 32 * k] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // HF LlamaRMSNorm (transformers 4.31 modeling_llama.py): variance in fp32, normalised value cast to bf16,
 // then multiplied by the bf16 weight.
 __global__ void rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ gamma,
@@ -426,8 +487,17 @@ extern "C" int ivlm_layernorm_bf16(ivlm_handle h, const void* x, void* y, const 
                                    void* stream) {
     IVLM_REQUIRE(h && D % 8 == 0 && out_rows > 0, "layernorm: D=%d must be a multiple of 8, rows>0", D);
     const int wpb = 8;
-    layernorm_kernel<<<(unsigned)((out_rows + wpb - 1) / wpb), wpb * 32, 0, STREAM>>>(
-        (const bf16*)x, (bf16*)y, (const bf16*)gamma, (const bf16*)beta, out_rows, D, eps, row_map, act);
+    const unsigned grid = (unsigned)((out_rows + wpb - 1) / wpb);
+#define IVLM_LN_REG(V)                                                                                                  \
+    layernorm_reg_kernel<V><<<grid, wpb * 32, 0, STREAM>>>((const bf16*)x, (bf16*)y, (const bf16*)gamma, (const bf16*)beta, \
+                                                           out_rows, eps, row_map, act)
+    if (D == 1280) IVLM_LN_REG(5);
+    else if (D == 1024) IVLM_LN_REG(4);
+    else if (D == 256) IVLM_LN_REG(1);
+    else
+        layernorm_kernel<<<grid, wpb * 32, 0, STREAM>>>((const bf16*)x, (bf16*)y, (const bf16*)gamma, (const bf16*)beta,
+                                                        out_rows, D, eps, row_map, act);
+#undef IVLM_LN_REG
     DONE();
 }
 extern "C" int ivlm_rmsnorm_bf16(ivlm_handle h, const void* x, void* y, const void* gamma, int64_t rows, int32_t D,
