@@ -46,6 +46,10 @@ extern "C" int ivlm_set_option(ivlm_handle h, const char* name, int32_t value) {
         h->pdl = value ? 1 : 0;
         return IVLM_OK;
     }
+    if (std::string(name) == "global_attn_variant") {
+        h->global_attn_variant = value;
+        return IVLM_OK;
+    }
     if (std::string(name) == "window_attn_variant") {
         h->window_attn_variant = value;
         return IVLM_OK;

@@ -80,6 +80,7 @@ struct ivlm_ctx {
     int num_sms = 148;
     uint64_t launches = 0;  // kernels launched through this handle (bench "gpu_launches")
     int pdl = 0;                  // 1: launch the decode-chain kernels with programmatic dependent launch
+    int global_attn_variant = 0;  // 0: 64-key tiles, 2 CTAs/SM; 1: 128-key tiles, 1 CTA/SM (A/B switch)
     int window_attn_variant = 0;  // 0: single-tile 2-CTA/SM window kernel, 1: the general tiled kernel (A/B switch)
     std::unordered_map<ivlm::TmapKey, CUtensorMap, ivlm::TmapKeyHash> tmaps;
     std::unordered_map<std::string, ivlm::Weight> weights;

@@ -220,6 +220,11 @@ def test_sam_attention_tcgen05(ctx, Hq, Wq, B, heads):
     assert torch.isfinite(out.float()).all()
     assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
     assert (out.float() - ref).abs().max().item() < 3e-2
+    if Hq == 64:  # the 128-key-tile, one-CTA-per-SM variant must agree with the default 64-key-tile kernel
+        ctx.set_option("global_attn_variant", 1)
+        alt = ctx.sam_attention(qkv, rph, rpw, B, heads, Hq, Wq, hd)
+        ctx.set_option("global_attn_variant", 0)
+        assert rel_err(alt, ref) < 1e-2 and rel_err(alt, out) < 5e-3
     # and against the first-generation path (separate rel-pos kernel + mma.sync flash attention)
     rel_h, rel_w = ctx.sam_relpos(qkv, rph, rpw, B, heads, Hq, Wq, hd)
     old = ctx.attention(q, k, v, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=Hq, kw=Wq).reshape(B * S, heads * hd)

@@ -38,6 +38,11 @@ for name, B, side in (("global_8views", 8, 64), ("window_8views", 200, 14)):
     if which in ("both", "new"):
         ms = timeit(lambda: ctx.sam_attention(qkv, rph, rpw, B, heads, side, side, hd))
         print(f"{name} fused tcgen05: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+        if side == 64:
+            ctx.set_option("global_attn_variant", 1)
+            ms = timeit(lambda: ctx.sam_attention(qkv, rph, rpw, B, heads, side, side, hd))
+            ctx.set_option("global_attn_variant", 0)
+            print(f"{name} fused tcgen05, 128-key tiles / 1 CTA per SM: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
     if which in ("both", "old"):
         t = qkv.view(B, S, 3, heads, hd)
 
