@@ -355,16 +355,18 @@ def main():
             tot = sum(r["ms"] for r in rep.values())
             g = rep["gemm"]
             ach = g["work"] / (g["ms"] / 1e3) / 1e12
-            traffic = None
+            traffic, traffic_note = None, None
             tp = ROOT / "profiles" / "r1_traffic.json"
             if tp.exists():  # DRAM bytes of one representative launch (SAM MLP-1) from the committed ncu --set full capture
                 t = json.loads(tp.read_text())["launches"]["sam_mlp1 M=32768 N=5120 K=1280"]
-                traffic = {"dram_bytes_per_launch": t["dram_bytes"], "algorithmic_bytes_per_launch": t["algorithmic_bytes"],
-                           "launch": "sam_mlp1 M=32768 N=5120 K=1280", "source": "profiles/r1_traffic.json (ncu --set full)"}
+                traffic = t["dram_bytes"]
+                traffic_note = {"launch": "sam_mlp1 M=32768 N=5120 K=1280", "algorithmic_bytes_per_launch": t["algorithmic_bytes"],
+                                "source": "profiles/r1_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
             line["roofline"] = {"kernel": "gemm_bf16_tcgen05_kernel (token count > 64: SAM, CLIP, LLaMA prefill)", "bound": "tensor",
                                 "achieved": ach, "peak": pk["tf_sustained"],
                                 "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": traffic,
                                 "peak_source": pk["source"] + " sustained cuBLAS bf16 (kernel timed inside a long step)",
+                                "traffic_note": traffic_note,
                                 "launches_per_step": g["launches"], "share_of_kernel_time": g["ms"] / tot}
             line["kernel_time_shares"] = {k: round(r["ms"] / tot, 4) for k, r in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
             line["kernel_ms_eager_pass"] = {k: round(r["ms"], 2) for k, r in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}

@@ -598,7 +598,11 @@ class InteractVLMForCausalLM:
         elif vision_tower is not None and Path(str(vision_tower)).is_dir():
             for k, v in load_checkpoint_dir(Path(vision_tower)).items():
                 sd[k if k.startswith("model.vision_tower.") else "model.vision_tower.vision_tower." + k] = v
-        return cls(cfg, sd, device=device)
+        model = cls(cfg, sd, device=device)
+        data_root = Path(kwargs.get("data_root", "./data"))
+        if (data_root / "hcontact_vitruvian" / "pixel_to_vertex_map_1024.npz").exists():
+            model.load_human_lift_maps(data_root)  # what HumanContact3DPredictor.__init__ reads (components.py:203-218)
+        return model
 
     def get_model(self):
         return _GetModel(self)
