@@ -40,6 +40,8 @@ IVLM_API int ivlm_abi_version(void);
  * weight-streaming GEMMs (small token counts) split K across CTAs and reduce the partials in-kernel, deterministically. */
 IVLM_API int ivlm_set_workspace(ivlm_handle h, void* ptr, size_t bytes, void* stream);
 /* Tuning / A-B switches (integer options): "window_attn_variant" 0 = single-tile window kernel (default), 1 = tiled kernel;
+ * "global_attn_variant" 0 = 64-key tiles, 2 CTAs/SM (default), 1 = 128-key tiles; "small_m_variant" 0 = weight-streaming
+ * kernel for token counts <= 64 (default), 1 = swapped-operand tcgen05 kernel with fused split-K;
  * "pdl" 1 = launch the LLaMA decode-chain kernels with programmatic dependent launch (prologues overlap the predecessor's
  * tail; every such kernel executes griddepcontrol.wait before reading its inputs). */
 IVLM_API int ivlm_set_option(ivlm_handle h, const char* name, int32_t value);

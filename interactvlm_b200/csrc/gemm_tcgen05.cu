@@ -577,6 +577,11 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
     IVLM_REQUIRE(!split || (a->out_dtype == IVLM_F32 && !a->bias && !a->residual && a->act == 0),
                  "gemm: split-K accumulates raw fp32 (no bias/act/residual)");
 
+    // Small token counts are weight streaming (HBM-bound): dedicated kernel built around the weight stream.
+    if (h->small_m_variant == 0 && a->M <= 64 && a->N <= h->gv_max_n && a->force_swap >= 0 && a->row_map == nullptr && a->k_splits <= 1 &&
+        a->K % 32 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0 && a->res_row_mod == 0 &&
+        (reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0)
+        return launch_gemv_small_m(h, a, stream);
     // Swap operands when the token count is small: the weight rows fill the 128-row UMMA operand.
     const bool swap = a->force_swap == 1 || (a->force_swap == 0 && a->M <= 64 && a->row_map == nullptr);
     GemmParams p{};

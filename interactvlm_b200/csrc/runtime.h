@@ -80,6 +80,14 @@ struct ivlm_ctx {
     int num_sms = 148;
     uint64_t launches = 0;  // kernels launched through this handle (bench "gpu_launches")
     int pdl = 0;                  // 1: launch the decode-chain kernels with programmatic dependent launch
+    // Weight-streaming kernel for token counts <= 64 (gemv_small_m.cu).  Measured on B200 at 8 tokens (tools/prof_decode.py
+    // sweep): for N = 5120 layers 16 rows x 10 warps per CTA gives o_proj 12.7 us / down_proj 30.8 us against 18.5 / 35.8
+    // for the swapped tcgen05 kernel with fused split-K; for the wide layers (qkv 15360, gate-up 27648, lm_head) the
+    // tcgen05 kernel is as fast or faster, so those keep it.
+    int gv_rows8_max_n = 0;       // layers with N <= this use 8 rows per CTA (A/B knob; 16 rows measured better)
+    int gv_warps = 10;            // warps per CTA (0: heuristic)
+    int gv_max_n = 8192;          // layers wider than this go to the swapped tcgen05 kernel instead
+    int small_m_variant = 0;      // 0: weight-streaming mma.sync kernel for token counts <= 64; 1: swapped-operand tcgen05 path
     int global_attn_variant = 0;  // 0: 64-key tiles, 2 CTAs/SM; 1: 128-key tiles, 1 CTA/SM (A/B switch)
     int window_attn_variant = 0;  // 0: single-tile 2-CTA/SM window kernel, 1: the general tiled kernel (A/B switch)
     std::unordered_map<ivlm::TmapKey, CUtensorMap, ivlm::TmapKeyHash> tmaps;
@@ -120,6 +128,8 @@ inline cudaError_t launch_k(const ivlm_ctx* h, void (*kernel)(KArgs...), dim3 gr
 // box = box_rows x 64 elements, 128B swizzle, zero OOB fill.
 int get_tmap_bf16(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                   const CUtensorMap** out);
+// Weight-streaming small-token GEMM (gemv_small_m.cu); arguments as ivlm_gemm_bf16.
+int launch_gemv_small_m(ivlm_ctx* h, const ivlm_gemm_args* a, cudaStream_t stream);
 // General form: box = box_rows x box_cols elements, swizzle_bytes in {128, 64, 32} (box_cols * 2 must not exceed it).
 int get_tmap_bf16_ex(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols, uint32_t swizzle_bytes, const CUtensorMap** out);

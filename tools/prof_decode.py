@@ -67,6 +67,17 @@ ops = {
     "decode_attention": (lambda i: ctx.decode_attention(q, kc[i % NW], vc[i % NW], bt, sl, H, hd, page), 2 * B * L * D * 2),
     "silu_mul": (lambda i: ctx.silu_mul(gu), 0),
 }
+if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+    gemms = {k: v for k, v in ops.items() if k.startswith("gemm") and "nosplit" not in k}
+    cfgs = [("tcgen05 swapped + split-K", dict(small_m_variant=1))]
+    for rows8 in (0, 1):
+        for wv in (3, 5, 6, 7, 10, 12, 16):
+            cfgs.append((f"gemv rows{8 if rows8 else 16} warps{wv}", dict(small_m_variant=0, gv_rows8_max_n=(1 << 30) if rows8 else 0, gv_warps=wv)))
+    for label, opts in cfgs:
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        print(label + ": " + "  ".join(f"{n[5:]} {graph_time(fn):6.2f}us" for n, (fn, _) in gemms.items()), flush=True)
+    sys.exit(0)
 tot = 0.0
 for name, (fn, nbytes) in ops.items():
     us = graph_time(fn)
