@@ -348,7 +348,11 @@ def main():
             model.use_cuda_graph = False
             model._graphs = {}
             model.ctx.enable_profile()
+            # park the GPU (~100 ms spin) at the start of the CLIP/prefill stage and of every SAM chunk so that the host
+            # is hundreds of launches ahead: the event pairs then bracket pure GPU time, not host launch latency
+            model.stage_delay = lambda: torch.cuda._sleep(200_000_000)
             step(True)
+            model.stage_delay = None
             rep = model.ctx.profile_report()
             model.ctx.disable_profile()
             model.use_cuda_graph = True

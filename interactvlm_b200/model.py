@@ -560,6 +560,7 @@ class InteractVLMForCausalLM:
         self.sam_chunk = 8
         self.record_stages = False  # bench.py: CUDA events at stage boundaries (a dozen per call)
         self._marks = []
+        self.stage_delay = None     # bench.py per-kernel timing pass: callable that parks the GPU so the host runs ahead
 
     def _mark(self, name):
         if self.record_stages and self.device.type == "cuda":
@@ -648,7 +649,11 @@ class InteractVLMForCausalLM:
         """[B,V,3,1024,1024] -> [B*V, 4096, 256] token-major (InteractVLM.py:251-261)."""
         B, V = images.shape[:2]
         flat = images.reshape(B * V, *images.shape[2:])
-        outs = [self.eng.sam_encode(self._bf16(flat[i:i + self.sam_chunk])) for i in range(0, B * V, self.sam_chunk)]
+        outs = []
+        for i in range(0, B * V, self.sam_chunk):
+            if self.stage_delay is not None:
+                self.stage_delay()
+            outs.append(self.eng.sam_encode(self._bf16(flat[i:i + self.sam_chunk])))
         return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
 
     def _bf16(self, t):
@@ -700,6 +705,8 @@ class InteractVLMForCausalLM:
         if max_len > cfg.max_position_embeddings:
             raise ValueError(f"sequence {max_len} exceeds max_position_embeddings {cfg.max_position_embeddings}")
         self._mark("start")
+        if self.stage_delay is not None:
+            self.stage_delay()
         feats = eng.clip_encode(self._bf16(images_clip))
         self._mark("clip")
         embeds = self.ctx.embed_splice(self.w.embed, ids.to(torch.int32).to(self.device).contiguous(), feats.contiguous())
