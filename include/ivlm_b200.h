@@ -119,6 +119,13 @@ IVLM_API int ivlm_im2col_3x3_bf16(ivlm_handle h, const void* x, void* cols, int3
 IVLM_API int ivlm_preprocess_u8_bf16(ivlm_handle h, const uint8_t* img, void* out, int32_t N, int32_t H, int32_t W, int32_t S,
                             float pre_scale, const float* mean3_h, const float* std3_h, void* stream);
 
+/* One pass (vertical = 0: along x, 1: along y) of Pillow's antialiased 8-bit resize -- the arithmetic of the reference's
+ * ResizeLongestSide.apply_image (segment_anything/utils/transforms.py:27-34, bilinear) and CLIPImageProcessor resize
+ * (bicubic): src [N,H,W,3] uint8 -> dst [N,OH,OW,3]; bounds [out,2] (first input index, count) and coeffs [out,ksize]
+ * (22-bit fixed point) are DEVICE arrays built by the host (interactvlm_b200/resample.py).  Bit-exact vs Pillow. */
+IVLM_API int ivlm_resample_u8(ivlm_handle h, const uint8_t* src, uint8_t* dst, const int32_t* bounds, const int32_t* coeffs,
+                     int32_t ksize, int32_t N, int32_t H, int32_t W, int32_t OH, int32_t OW, int32_t vertical, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Attention. */
 typedef struct ivlm_attn_args {

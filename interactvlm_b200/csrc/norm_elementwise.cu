@@ -467,6 +467,33 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ img, bf16* __re
     }
 }
 
+// Pillow's separable antialiased resize on uint8 HWC images (libImaging/Resample.c, 8bpc): one pass along x or y.
+// out[o] = clip8((2^21 + sum_j in[first[o] + j] * k[o][j]) >> 22); coefficient windows come from the host
+// (interactvlm_b200/resample.py).  One thread per output pixel (3 channels), consecutive threads along x.
+__global__ void resample_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int* __restrict__ bounds,
+                                   const int* __restrict__ kk, int ksize, int N, int H, int W, int OH, int OW, int vertical) {
+    const long long total = (long long)N * OH * OW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % OW);
+        const int oy = (int)((i / OW) % OH);
+        const int n = (int)(i / ((long long)OW * OH));
+        const int o = vertical ? oy : ox;
+        const int first = bounds[2 * o], cnt = bounds[2 * o + 1];
+        const int* k = kk + (long long)o * ksize;
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+        for (int j = 0; j < cnt; ++j) {
+            const int y = vertical ? first + j : oy, x = vertical ? ox : first + j;
+            const uint8_t* px = src + (((long long)n * H + y) * W + x) * 3;
+            const int c = k[j];
+            a0 += px[0] * c; a1 += px[1] * c; a2 += px[2] * c;
+        }
+        uint8_t* q = dst + (((long long)n * OH + oy) * OW + ox) * 3;
+        q[0] = (uint8_t)min(max(a0 >> 22, 0), 255);
+        q[1] = (uint8_t)min(max(a1 >> 22, 0), 255);
+        q[2] = (uint8_t)min(max(a2 >> 22, 0), 255);
+    }
+}
+
 static inline int grid_for(long long work, int block, int sms) {
     long long g = (work + block - 1) / block;
     long long cap = (long long)sms * 16;
@@ -616,5 +643,17 @@ extern "C" int ivlm_preprocess_u8_bf16(ivlm_handle h, const uint8_t* img, void* 
     const long long total = (long long)N * 3 * S * (S / 8);
     preprocess_u8_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, STREAM>>>(img, (bf16*)out, N, H, W, S, pre_scale, mean3_h[0],
                                                                              mean3_h[1], mean3_h[2], std3_h[0], std3_h[1], std3_h[2]);
+    DONE();
+}
+
+extern "C" int ivlm_resample_u8(ivlm_handle h, const uint8_t* src, uint8_t* dst, const int32_t* bounds, const int32_t* coeffs,
+                                int32_t ksize, int32_t N, int32_t H, int32_t W, int32_t OH, int32_t OW, int32_t vertical,
+                                void* stream) {
+    IVLM_REQUIRE(h && src && dst && bounds && coeffs && N > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && ksize > 0,
+                 "resample: bad arguments");
+    IVLM_REQUIRE(vertical ? (OW == W) : (OH == H), "resample: a pass changes one dimension only");
+    const long long total = (long long)N * OH * OW;
+    resample_u8_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, STREAM>>>(src, dst, bounds, coeffs, ksize, N, H, W, OH, OW,
+                                                                           vertical);
     DONE();
 }

@@ -33,6 +33,29 @@ def prepare_inputs(model, image_u8, sam_views_u8):
     return clip, sam.view(B, V, 3, cfg.sam_img_size, cfg.sam_img_size), [(h, w)] * B
 
 
+def prepare_inputs_from_raw(model, image_u8, sam_views_u8):
+    """Same as prepare_inputs but starting from UN-resized uint8 images, with the reference's CPU/Pillow resizes done on the
+    GPU bit-exactly: CLIP = bicubic to shortest edge 224 + centre crop (CLIPImageProcessor, run_demo.py:330-346), SAM =
+    bilinear to longest side 1024 (ResizeLongestSide.apply_image, run_demo.py:359-366).
+    image_u8 [B,H,W,3]; sam_views_u8 [B,V,h,w,3] (all views of a call share one size)."""
+    from . import resample as R
+
+    cfg, ctx, dev = model.config, model.ctx, model.device
+    image_u8 = torch.as_tensor(image_u8).to(dev).contiguous()
+    sam_views_u8 = torch.as_tensor(sam_views_u8).to(dev).contiguous()
+    B, H, W, _ = image_u8.shape
+    ch, cw = R.clip_target_size(H, W, cfg.clip_image_size)
+    small = ctx.resize_u8(image_u8, ch, cw, "bicubic")
+    top, left = (ch - cfg.clip_image_size) // 2, (cw - cfg.clip_image_size) // 2
+    crop = small[:, top:top + cfg.clip_image_size, left:left + cfg.clip_image_size].contiguous()
+    clip = ctx.preprocess_u8(crop, cfg.clip_image_size, kind="clip")
+    _, V, h, w, _ = sam_views_u8.shape
+    sh, sw = R.sam_target_size(h, w, cfg.sam_img_size)
+    views = ctx.resize_u8(sam_views_u8.view(B * V, h, w, 3), sh, sw, "bilinear")
+    sam = ctx.preprocess_u8(views, cfg.sam_img_size, kind="sam")
+    return clip, sam.view(B, V, 3, cfg.sam_img_size, cfg.sam_img_size), [(sh, sw)] * B
+
+
 class ContactConverter:
     """convert_contacts(contact, mapping): dense [n_out, n_in] mapping applied as a CSR SpMV (the SMPL->SMPL-X matrix has
     ~3 non-zeros per row; the reference streams the 289 MB dense matrix through bmm on every call)."""

@@ -396,6 +396,36 @@ class Context:
                                                  self.stream), "preprocess_u8")
         return out
 
+    def resize_u8(self, img_u8, out_h, out_w, filt="bilinear"):
+        """Pillow-exact antialiased resize of uint8 [N,H,W,3] device images (horizontal pass, then vertical)."""
+        from . import resample as R
+
+        assert img_u8.dtype == torch.uint8 and img_u8.is_cuda and img_u8.is_contiguous() and img_u8.shape[-1] == 3
+        N, H, W, _ = img_u8.shape
+        cache = self.__dict__.setdefault("_resample_tables", {})
+
+        def tables(n_in, n_out):
+            key = (n_in, n_out, filt)
+            if key not in cache:
+                b, k, ks = R.precompute_coeffs(n_in, n_out, filt)
+                cache[key] = (torch.from_numpy(b).to(self.device), torch.from_numpy(k).to(self.device), ks)
+            return cache[key]
+
+        x = img_u8
+        if out_w != W:
+            b, k, ks = tables(W, out_w)
+            y = torch.empty((N, H, out_w, 3), device=x.device, dtype=torch.uint8)
+            L.check(self.lib.ivlm_resample_u8(self.h, P(x), P(y), P(b), P(k), i32(ks), i32(N), i32(H), i32(W), i32(H), i32(out_w),
+                                              i32(0), self.stream), "resample_u8")
+            x = y
+        if out_h != H:
+            b, k, ks = tables(H, out_h)
+            y = torch.empty((N, out_h, out_w, 3), device=x.device, dtype=torch.uint8)
+            L.check(self.lib.ivlm_resample_u8(self.h, P(x), P(y), P(b), P(k), i32(ks), i32(N), i32(H), i32(out_w), i32(out_h),
+                                              i32(out_w), i32(1), self.stream), "resample_u8")
+            x = y
+        return x
+
     def sigmoid_where(self, x, gt=None, ignore_value=-1.0):
         """In place: x = sigmoid(x) where gt != ignore_value (everywhere when gt is None)."""
         assert x.dtype == torch.float32 and x.is_contiguous()

@@ -299,6 +299,11 @@ class EmuContext:
         N, _, H, W = x.shape
         return F.pad(x, (0, size - W, 0, size - H)).to(BF)
 
+    def resize_u8(self, img_u8, out_h, out_w, filt="bilinear"):
+        self.launches += 1
+        from oracle import resize as OR
+        return torch.stack([torch.from_numpy(OR.resize_u8(i.numpy(), out_h, out_w, filt)) for i in img_u8], 0)
+
     def sigmoid_where(self, x, gt=None, ignore_value=-1.0):
         self.launches += 1
         keep = torch.ones_like(x, dtype=torch.bool) if gt is None else gt != ignore_value

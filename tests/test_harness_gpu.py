@@ -56,3 +56,36 @@ def test_convert_contacts_spmv_and_validate(model):
                     scripted=ans[b], gt_contact_3d=(ref["pred_contact_3d"][b] >= 0.5).float()) for b in range(2)]
     preds, metrics = Hn.validate(model, samples, batch_size=2, max_new_tokens=ans.shape[1])
     assert torch.equal(preds, ref["pred_contact_3d"]) and metrics["f1"] > 0.999
+
+
+@pytest.mark.parametrize("h,w,oh,ow,filt", [(480, 640, 768, 1024, "bilinear"), (1365, 2048, 683, 1024, "bilinear"),
+                                           (480, 640, 224, 298, "bicubic"), (100, 37, 224, 82, "bicubic")])
+def test_resize_kernel_bit_exact_vs_pillow(model, h, w, oh, ow, filt):
+    from PIL import Image
+
+    rng = np.random.default_rng(h + w)
+    img = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    got = model.ctx.resize_u8(torch.from_numpy(img).cuda(), oh, ow, filt).cpu().numpy()
+    for i in range(2):
+        want = np.asarray(Image.fromarray(img[i]).resize((ow, oh), Image.BILINEAR if filt == "bilinear" else Image.BICUBIC))
+        assert np.array_equal(got[i], want)
+
+
+def test_prepare_inputs_from_raw_matches_reference_pipeline(model):
+    """Raw uint8 images -> GPU resize + normalise == the reference's CPU pipeline (Pillow resize, preprocess, bf16 cast)."""
+    from PIL import Image
+
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (1, 480, 640, 3), dtype=np.uint8)
+    views = rng.integers(0, 256, (1, 4, 600, 800, 3), dtype=np.uint8)
+    clip, sam, resize = Hn.prepare_inputs_from_raw(model, img, views)
+    assert resize == [(768, 1024)] and sam.shape == (1, 4, 3, 1024, 1024) and clip.shape == (1, 3, 224, 224)
+    v = np.array(Image.fromarray(views[0, 1]).resize((1024, 768), Image.BILINEAR))
+    x = torch.from_numpy(v).permute(2, 0, 1).float()
+    ref = (x - torch.tensor([123.675, 116.28, 103.53]).view(-1, 1, 1)) / torch.tensor([58.395, 57.12, 57.375]).view(-1, 1, 1)
+    ref = torch.nn.functional.pad(ref, (0, 0, 0, 1024 - 768)).bfloat16()
+    assert torch.equal(sam[0, 1].cpu(), ref)
+    c = np.asarray(Image.fromarray(img[0]).resize((298, 224), Image.BICUBIC))[:, 37:37 + 224]
+    cref = ((torch.from_numpy(c.copy()).permute(2, 0, 1).float() * (1 / 255.0) - torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(-1, 1, 1))
+            / torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(-1, 1, 1)).bfloat16()
+    assert (clip[0].float().cpu() - cref.float()).abs().max().item() <= 2 ** -6
