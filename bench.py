@@ -218,6 +218,11 @@ def main():
     ap.add_argument("--config", default="full", choices=["full", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--overlap", type=int, default=0, help="1: SAM encoder on a second stream next to the decode steps "
+                    "(measured slower on B200, profiles/r1_overlap_timeline.txt; kept as an option)")
+    ap.add_argument("--sm-limit", type=int, default=104, help="SMs the encoder GEMMs keep to while decode steps are in flight")
+    ap.add_argument("--limited-chunks", type=int, default=-1, help="encoder chunks launched SM-limited (-1: estimate)")
+    ap.add_argument("--sam-chunk", type=int, default=4, help="views per encoder chunk")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -228,7 +233,9 @@ def main():
                 f"prompt {N_PRE + N_POST + 4} ids (+255 image rows), {N_ANS} scripted answer tokens, V=4 views 1024^2")
     config = {"workload": workload, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
               "views": cfg.multiview_channels, "parallelism": f"dp{world} (batch-sharded, one NCCL all-gather of [B,6890])",
-              "l2": "inputs (201 MB/step) and weights (28 GB) exceed the 126 MB L2; no explicit flush"}
+              "l2": "inputs (201 MB/step) and weights (28 GB) exceed the 126 MB L2; no explicit flush",
+              "overlap": ({"sam_encoder_next_to_decode": True, "sm_limit": args.sm_limit, "limited_chunks": args.limited_chunks,
+                           "sam_chunk": args.sam_chunk} if args.overlap else None)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -269,6 +276,11 @@ def main():
     sd = S.make_state_dict(cfg, seed=0, device=dev, gain=0.5)
     model = InteractVLMForCausalLM(cfg, sd, device=local_rank)
     del sd
+    if args.overlap:
+        model.enable_overlap(sm_limit=args.sm_limit, limited_chunks=None if args.limited_chunks < 0 else args.limited_chunks,
+                             sam_chunk=args.sam_chunk)
+    else:
+        model.sam_chunk = args.sam_chunk if args.sam_chunk != 4 else 8
     p2v, bary = S.make_mesh_lift_maps(seed=0)
     model.set_human_lift_maps(p2v, bary)
     del p2v, bary
@@ -294,7 +306,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = model.ctx.launch_count()
+        n0 = model.launch_count()
         e0.record()
         for _ in range(steps):
             step(resident)
@@ -307,7 +319,7 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
-        return ms, model.ctx.launch_count() - n0
+        return ms, model.launch_count() - n0
 
     for _ in range(args.warmup):
         last = step(True)

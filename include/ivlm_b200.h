@@ -43,7 +43,9 @@ IVLM_API int ivlm_set_workspace(ivlm_handle h, void* ptr, size_t bytes, void* st
  * "global_attn_variant" 0 = 64-key tiles, 2 CTAs/SM (default), 1 = 128-key tiles; "small_m_variant" 0 = weight-streaming
  * kernel for token counts <= 64 (default), 1 = swapped-operand tcgen05 kernel with fused split-K;
  * "pdl" 1 = launch the LLaMA decode-chain kernels with programmatic dependent launch (prologues overlap the predecessor's
- * tail; every such kernel executes griddepcontrol.wait before reading its inputs). */
+ * tail; every such kernel executes griddepcontrol.wait before reading its inputs);
+ * "sm_limit" n > 0 = persistent token-major GEMMs launched through this handle use at most n CTAs (one per SM), leaving
+ * the other SMs to a second handle/stream (SAM encoder next to the weight-streaming decode chain); 0 = all SMs. */
 IVLM_API int ivlm_set_option(ivlm_handle h, const char* name, int32_t value);
 /* kernels launched through this handle so far (bench.py's "gpu_launches") */
 IVLM_API uint64_t ivlm_launch_count(ivlm_handle h);

@@ -46,6 +46,7 @@ extern "C" int ivlm_set_option(ivlm_handle h, const char* name, int32_t value) {
         h->pdl = value ? 1 : 0;
         return IVLM_OK;
     }
+    if (std::string(name) == "sm_limit") { h->sm_limit = value; return IVLM_OK; }
     if (std::string(name) == "gv_rows8_max_n") { h->gv_rows8_max_n = value; return IVLM_OK; }
     if (std::string(name) == "gv_warps") { h->gv_warps = value; return IVLM_OK; }
     if (std::string(name) == "gv_max_n") { h->gv_max_n = value; return IVLM_OK; }

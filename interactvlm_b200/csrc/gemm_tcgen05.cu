@@ -547,7 +547,10 @@ static int launch_gemm(ivlm_ctx* h, const CUtensorMap* ta, const CUtensorMap* tb
         attr_set = true;
     }
     const int units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
-    const int grid = units < h->num_sms ? units : h->num_sms;
+    // SM partitioning (option "sm_limit"): a token-major GEMM of a low-priority stream keeps to a subset of the SMs so
+    // that the weight-streaming decode chain of another stream always finds free ones
+    const int cap = (h->sm_limit > 0 && h->sm_limit < h->num_sms && !p.a_static) ? h->sm_limit : h->num_sms;
+    const int grid = units < cap ? units : cap;
     IVLM_CHECK_CUDA(launch_k(h, gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, *ta, *tb, p));
     h->launches++;
     return IVLM_OK;

@@ -79,6 +79,7 @@ struct ivlm_ctx {
     int device = 0;
     int num_sms = 148;
     uint64_t launches = 0;  // kernels launched through this handle (bench "gpu_launches")
+    int sm_limit = 0;             // > 0: persistent token-major GEMMs launch at most this many CTAs (leaves SMs to a concurrent stream)
     int pdl = 0;                  // 1: launch the decode-chain kernels with programmatic dependent launch
     // Weight-streaming kernel for token counts <= 64 (gemv_small_m.cu).  Measured on B200 at 8 tokens (tools/prof_decode.py
     // sweep): for N = 5120 layers 16 rows x 10 warps per CTA gives o_proj 12.7 us / down_proj 30.8 us against 18.5 / 35.8

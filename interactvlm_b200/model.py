@@ -558,6 +558,8 @@ class InteractVLMForCausalLM:
         self.object_3d_contact_predictor = _Predictor(self, LIFT_OBJECT_MESH)
         self.object_3d_afford_predictor = _Predictor(self, LIFT_POINTS)
         self.sam_chunk = 8
+        # SAM encoder (tensor-bound) next to the LLaMA decode chain (HBM-bound): see enable_overlap()
+        self.overlap = None
         self.record_stages = False  # bench.py: CUDA events at stage boundaries (a dozen per call)
         self._marks = []
         self.stage_delay = None     # bench.py per-kernel timing pass: callable that parks the GPU so the host runs ahead
@@ -686,11 +688,18 @@ class InteractVLMForCausalLM:
             st[k].copy_(v)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.eng.llm_decode_step(st)
+        cur = torch.cuda.current_stream(self.device)
+        if self.overlap is not None and cur == self.overlap["hi"]:
+            # kernel nodes inherit the capturing stream's priority: capture on a high-priority stream of our own
+            cap = torch.cuda.Stream(self.device, priority=-1)
+            with torch.cuda.graph(g, stream=cap):
+                self.eng.llm_decode_step(st)
+        else:
+            with torch.cuda.graph(g):
+                self.eng.llm_decode_step(st)
         return g
 
-    def generate(self, images_clip, input_ids, max_new_tokens=32, scripted=None):
+    def generate(self, images_clip, input_ids, max_new_tokens=32, scripted=None, after_prefill=None):
         """Greedy decoding with a paged KV cache.  Returns (output_ids [B,L'] int64 on host, hidden [B,max_len,D] device
         buffer holding the normed last-layer state of every position of output_ids[:, :-1]).  `scripted` [B,G] forces
         the generated tokens (teacher forcing: same arithmetic, known [SEG] position)."""
@@ -726,6 +735,8 @@ class InteractVLMForCausalLM:
         key = "graph_scripted" if scripted is not None else "graph_greedy"
         eng.llm_prefill(st, embeds)
         self._mark("llm_prefill")
+        if after_prefill is not None:
+            after_prefill(G - 1)  # the caller queues independent work (SAM encoder) next to the decode steps
         graph = st.get(key)
         if self.use_cuda_graph and graph is None and G > 1:
             graph = st[key] = self._decode_graph(st)
@@ -768,8 +779,13 @@ class InteractVLMForCausalLM:
         cfg = self.config
         if cfg.token_type != "Gen":
             raise NotImplementedError("token_type != 'Gen' (AttentionSplitter variants) is outside the hot path")
-        output_ids, hidden = self.generate(images_clip, input_ids, max_new_tokens, scripted)
-        pred_masks = self._masks_from_hidden(hidden, output_ids, images, cam_params, resize_list, original_size_list)
+        emb = None
+        if self.overlap is not None and not self.record_stages and self.stage_delay is None:
+            output_ids, hidden, emb = self._generate_and_encode(images_clip, images, input_ids, max_new_tokens, scripted)
+        else:
+            output_ids, hidden = self.generate(images_clip, input_ids, max_new_tokens, scripted)
+        pred_masks = self._masks_from_hidden(hidden, output_ids, images, cam_params, resize_list, original_size_list,
+                                             image_embeddings=emb)
         pred_contact_3d = None
         if pred_masks[0].shape[0] > 0:
             if self.hC_loss_weight > 0 and "hcontact" in contact_type:
@@ -780,7 +796,102 @@ class InteractVLMForCausalLM:
         self._mark("lift")
         return {"output_ids": output_ids.to(self.device), "pred_masks": pred_masks, "pred_contact_3d": pred_contact_3d}
 
-    def _masks_from_hidden(self, hidden, output_ids, images, cam_params, resize_list, original_size_list):
+    def enable_overlap(self, sm_limit=104, limited_chunks=None, sam_chunk=4, decode_ms_per_step=None):
+        """Run the SAM ViT-H encoder (tensor-bound) on a second handle + low-priority stream NEXT TO the LLaMA decode
+        steps (weight streaming, HBM-bound, leaves the tensor pipes idle) instead of after them.  The two stages are
+        independent until the mask decoder (the reference runs them back to back, InteractVLM.py:524-531 then :578).
+        While decode steps are in flight the encoder's persistent GEMMs keep to `sm_limit` SMs (ivlm option "sm_limit")
+        so that the decode kernels -- on a high-priority stream -- always find free SMs; the first `limited_chunks`
+        chunks of `sam_chunk` views are launched that way (None: estimated from the decode length), the rest use the
+        whole chip.  Results are bit-identical to the serial order (same kernels, same operands)."""
+        if self._emulated or self.device.type != "cuda":
+            return self
+        from .ops import Context
+
+        if self.overlap is None:
+            ctx2 = Context(self.device)
+            self.overlap = dict(ctx=ctx2, eng=_Engine(ctx2, self.config, self.w),
+                                hi=torch.cuda.Stream(self.device, priority=-1), lo=torch.cuda.Stream(self.device, priority=0))
+            self._graphs = {}  # decode graphs are re-captured on the high-priority stream
+        self.overlap.update(sm_limit=int(sm_limit), limited_chunks=limited_chunks, sam_chunk=int(sam_chunk),
+                            decode_ms_per_step=decode_ms_per_step)
+        return self
+
+    def disable_overlap(self):
+        self.overlap = None
+        self._graphs = {}
+
+    def launch_count(self) -> int:
+        return self.ctx.launch_count() + (self.overlap["ctx"].launch_count() if self.overlap is not None else 0)
+
+    def _limited_chunks(self, n_chunks, views_per_chunk, decode_steps):
+        """How many encoder chunks fit next to `decode_steps` decode steps: decode time from the weight bytes at ~0.55 of
+        the HBM copy rate (what the chain reaches when it shares the chip), chunk time from the encoder FLOPs at ~1.1
+        PFLOP/s scaled by the SM share."""
+        ov, cfg = self.overlap, self.config
+        if ov["limited_chunks"] is not None:
+            return min(int(ov["limited_chunks"]), n_chunks)
+        if ov["decode_ms_per_step"] is not None:
+            step_ms = float(ov["decode_ms_per_step"])
+        else:
+            D, F = cfg.hidden_size, cfg.intermediate_size
+            wbytes = 2.0 * (cfg.num_hidden_layers * (4 * D * D + 3 * D * F) + D * cfg.vocab_size)
+            step_ms = max(wbytes / 3.6e12 * 1e3, 0.012 * 9 * cfg.num_hidden_layers * 0.25)
+        E, T = cfg.sam_embed_dim, cfg.sam_grid ** 2
+        view_flop = cfg.sam_depth * 2 * T * 12 * E * E * 1.25
+        chunk_ms = views_per_chunk * view_flop / 1.1e15 * 1e3 * self.ctx_num_sms / max(ov["sm_limit"], 1)
+        return max(0, min(n_chunks, int(round(decode_steps * step_ms / max(chunk_ms, 1e-3)))))
+
+    @property
+    def ctx_num_sms(self):
+        return torch.cuda.get_device_properties(self.device).multi_processor_count
+
+    def _generate_and_encode(self, images_clip, images, input_ids, max_new_tokens, scripted):
+        ov = self.overlap
+        cur = torch.cuda.current_stream(self.device)
+        hi, lo = ov["hi"], ov["lo"]
+        fork = cur.record_event()
+        hi.wait_event(fork)
+        lo.wait_event(fork)
+        box = {}
+
+        tr = ov.get("trace")
+        if tr is not None:
+            tr.append(("fork", cur.record_event(torch.cuda.Event(enable_timing=True))))
+
+        def after_prefill(decode_steps):
+            ev = hi.record_event()
+            if tr is not None:
+                tr.append(("prefill_end", hi.record_event(torch.cuda.Event(enable_timing=True))))
+            B, V = images.shape[:2]
+            flat = images.reshape(B * V, *images.shape[2:])
+            chunk = ov["sam_chunk"]
+            n_chunks = (B * V + chunk - 1) // chunk
+            n_lim = self._limited_chunks(n_chunks, chunk, decode_steps)
+            with torch.cuda.stream(lo):
+                lo.wait_event(ev)
+                outs = []
+                for c in range(n_chunks):
+                    ov["ctx"].set_option("sm_limit", ov["sm_limit"] if c < n_lim else 0)
+                    outs.append(ov["eng"].sam_encode(self._bf16(flat[c * chunk:(c + 1) * chunk])))
+                    if ov.get("trace") is not None:
+                        ov["trace"].append((f"sam_chunk{c}{'L' if c < n_lim else ''}", lo.record_event(torch.cuda.Event(enable_timing=True))))
+                ov["ctx"].set_option("sm_limit", 0)
+                box["emb"] = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+                box["ev"] = lo.record_event()
+
+        with torch.cuda.stream(hi):
+            output_ids, hidden = self.generate(images_clip, input_ids, max_new_tokens, scripted, after_prefill=after_prefill)
+            ev_llm = hi.record_event()
+            if tr is not None:
+                tr.append(("decode_end", hi.record_event(torch.cuda.Event(enable_timing=True))))
+        cur.wait_event(ev_llm)
+        cur.wait_event(box["ev"])
+        box["emb"].record_stream(cur)
+        return output_ids, hidden, box["emb"]
+
+    def _masks_from_hidden(self, hidden, output_ids, images, cam_params, resize_list, original_size_list,
+                           image_embeddings=None):
         cfg, eng = self.config, self.eng
         B = output_ids.shape[0]
         V = cfg.multiview_channels
@@ -793,7 +904,8 @@ class InteractVLMForCausalLM:
             if r:
                 rows.append(b * hidden.shape[1] + r[0])
                 owners.append(b)
-        image_embeddings = self.get_visual_embs(images)  # computed for every sample, like the reference (:578)
+        if image_embeddings is None:
+            image_embeddings = self.get_visual_embs(images)  # computed for every sample, like the reference (:578)
         self._mark("sam_encoder")
         S, C = image_embeddings.shape[1], image_embeddings.shape[2]
         pred_masks = [None] * B

@@ -159,6 +159,34 @@ def test_batched_evaluate_equals_per_sample(tiny):
         assert d < 2e-2, d  # tile shapes differ with batch size -> bf16-level differences only
 
 
+def test_overlapped_encoder_is_bit_identical_to_serial(tiny):
+    """SAM encoder on a second handle + low-priority stream next to the decode steps (SM-limited GEMM grids, chunked
+    views): same kernels on the same operands -> bit-identical masks, contacts and tokens, scripted and greedy."""
+    cfg, sd, model, _ = tiny
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
+    args = (clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2)
+    serial = model.evaluate(*args, max_new_tokens=ans.shape[1], scripted=ans)
+    serial_g = model.evaluate(*args, max_new_tokens=6)
+    try:
+        for lim, nlim, chunk in ((100, None, 4), (64, 1, 3), (0, 0, 8)):
+            model.enable_overlap(sm_limit=lim, limited_chunks=nlim, sam_chunk=chunk)
+            n0 = model.launch_count()
+            for _ in range(2):  # second call replays the decode graph captured on the high-priority stream
+                ov = model.evaluate(*args, max_new_tokens=ans.shape[1], scripted=ans)
+            assert model.overlap["ctx"].launch_count() > 0 and model.launch_count() > n0
+            assert torch.equal(ov["output_ids"], serial["output_ids"])
+            assert torch.equal(ov["pred_contact_3d"], serial["pred_contact_3d"])
+            for a, b in zip(ov["pred_masks"], serial["pred_masks"]):
+                assert torch.equal(a, b)
+            ov_g = model.evaluate(*args, max_new_tokens=6)
+            assert torch.equal(ov_g["output_ids"], serial_g["output_ids"])
+            assert (ov_g["pred_contact_3d"] is None) == (serial_g["pred_contact_3d"] is None)
+            if serial_g["pred_contact_3d"] is not None:
+                assert torch.equal(ov_g["pred_contact_3d"], serial_g["pred_contact_3d"])
+    finally:
+        model.disable_overlap()
+
+
 def test_full_size_layers_vs_torch_fp32(ctx):
     """One SAM ViT-H block pair (window + global), one LLaMA-13B layer and the CLIP-L stack at their REAL widths:
     the oracle restatement evaluated with stock torch fp32 CUDA ops is the checker (CPU would take minutes)."""
