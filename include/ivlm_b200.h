@@ -246,6 +246,37 @@ IVLM_API int64_t ivlm_lift_nnz(const ivlm_lift_map* m);
  * thr = 0.3), ObjectPCAfford3DPredictor (components.py:289-347). Deterministic gather, no atomics. */
 IVLM_API int ivlm_lift(ivlm_handle h, const ivlm_lift_map* m, const float* masks, float* contact, int32_t B, int32_t mode,
               float thr, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * "Render" of Render-Localise-Lift: mesh -> per-pixel (face, barycentrics) -> lift maps and SAM input views.
+ * Replaces pytorch3d's MeshRasterizer / HardPhongShader as the reference drives them (get_rasterizer,
+ * project_vertices_and_create_mask, render_mesh: preprocess_data/render_mesh_utils.py:115-198; generate_sam_inp_objs:
+ * utils/demo_utils.py:171-256): FoV perspective camera, blur_radius 0, faces_per_pixel 1, perspective-correct
+ * barycentrics, z_clip = znear/2.  One-time preprocessing calls: they use the stream-ordered allocator for scratch and
+ * synchronise `stream` once. */
+#define IVLM_RASTER_MAX_VIEWS 8
+typedef struct ivlm_raster_cam {
+    float R[9];   /* row-major world->view rotation, row-vector convention: X_view = X_world R + T (look_at_view_transform) */
+    float T[3];
+    float C[3];   /* camera centre in world space (specular term of the shader) */
+    float s;      /* 1 / tan(fov / 2): x_ndc = s * x_view / z_view (aspect 1) */
+    float z_clip; /* znear / 2 */
+} ivlm_raster_cam;
+/* verts [Nv,3] fp32, faces [Nf,3] int32 (device) -> pix_to_face [V,H,W] int32 (-1 background), bary [V,H,W,3] fp32 (-1
+ * background), optional zbuf [V,H,W] fp32 (-1 background) and pixel_to_vertices_map p2v [V,H,W,3] int64 (-1 background;
+ * render_mesh_utils.py:140-163).  NDC +X left / +Y up, pixel centres, nearest depth wins, ties to the lower face index.
+ * Faces entirely behind z_clip are culled, faces crossing it are kept where the interpolated depth is >= z_clip; faces
+ * with a vertex at z <= 0 that are not culled are skipped and counted in *n_skipped_h (host, optional). */
+IVLM_API int ivlm_rasterize_mesh(ivlm_handle h, const float* verts, const int32_t* faces, int32_t n_verts, int32_t n_faces,
+                        const ivlm_raster_cam* cams_h, int32_t V, int32_t H, int32_t W, int32_t* pix_to_face, float* bary,
+                        float* zbuf, int64_t* p2v, int32_t* n_skipped_h, void* stream);
+/* HardPhongShader with one point light per view (lights_h [V,3] host) and default materials over the rasteriser output:
+ * rgb [V,H,W,3] uint8 = trunc(255 * ((ambient + diffuse * max(n.l,0)) * colour + specular * max(v.r,0)^shininess)),
+ * white background (render_mesh_utils.py:177-198).  colors [Nv,3] fp32 vertex colours (TexturesVertex). */
+IVLM_API int ivlm_shade_phong(ivlm_handle h, const float* verts, const int32_t* faces, int32_t n_verts, int32_t n_faces,
+                     const float* colors, const ivlm_raster_cam* cams_h, const float* lights_h, int32_t V, int32_t H, int32_t W,
+                     const int32_t* pix_to_face, const float* bary, float ambient, float diffuse, float specular,
+                     float shininess, uint8_t* rgb, void* stream);
+
 /* convert_contacts (utils/utils.py:428-443): SMPL->SMPL-X dense [R,C] matrix applied as CSR SpMV.
  * csr built once from the host dense matrix. */
 typedef struct ivlm_csr ivlm_csr;

@@ -46,6 +46,14 @@ class AttnArgs(C.Structure):
     ]
 
 
+class RasterCam(C.Structure):
+    """ivlm_raster_cam (include/ivlm_b200.h)."""
+    _fields_ = [("R", C.c_float * 9), ("T", C.c_float * 3), ("C", C.c_float * 3), ("s", C.c_float), ("z_clip", C.c_float)]
+
+
+RASTER_MAX_VIEWS = 8
+
+
 def declared_symbols() -> list[str]:
     """Every function the public header declares (used by the CPU-side ABI test)."""
     txt = HEADER.read_text()

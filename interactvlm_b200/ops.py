@@ -446,6 +446,49 @@ class Context:
         return out
 
 
+def _cam_array(cams):
+    """list of dict(R [3,3], T [3], C [3], s, z_clip) -> ctypes array of ivlm_raster_cam."""
+    assert 1 <= len(cams) <= L.RASTER_MAX_VIEWS, f"1..{L.RASTER_MAX_VIEWS} cameras per call"
+    arr = (L.RasterCam * len(cams))()
+    for a, c in zip(arr, cams):
+        a.R[:] = [float(x) for x in np.asarray(c["R"], dtype=np.float32).reshape(9)]
+        a.T[:] = [float(x) for x in np.asarray(c["T"], dtype=np.float32).reshape(3)]
+        a.C[:] = [float(x) for x in np.asarray(c["C"], dtype=np.float32).reshape(3)]
+        a.s, a.z_clip = float(c["s"]), float(c["z_clip"])
+    return arr
+
+
+def rasterize_mesh(ctx: Context, verts, faces, cams, H, W, want_p2v=True, want_zbuf=False):
+    """verts [Nv,3] fp32, faces [Nf,3] int32 (CUDA) -> dict(pix_to_face [V,H,W] i32, bary [V,H,W,3] f32,
+    p2v [V,H,W,3] i64 | None, zbuf | None, skipped).  pytorch3d MeshRasterizer semantics (include/ivlm_b200.h)."""
+    assert verts.is_cuda and verts.dtype == torch.float32 and verts.is_contiguous() and verts.shape[1] == 3
+    assert faces.is_cuda and faces.dtype == torch.int32 and faces.is_contiguous() and faces.shape[1] == 3
+    V, dev = len(cams), verts.device
+    pix = torch.empty((V, H, W), device=dev, dtype=torch.int32)
+    bary = torch.empty((V, H, W, 3), device=dev, dtype=torch.float32)
+    zbuf = torch.empty((V, H, W), device=dev, dtype=torch.float32) if want_zbuf else None
+    p2v = torch.empty((V, H, W, 3), device=dev, dtype=torch.int64) if want_p2v else None
+    skipped = i32(0)
+    L.check(ctx.lib.ivlm_rasterize_mesh(ctx.h, P(verts), P(faces), i32(verts.shape[0]), i32(faces.shape[0]), _cam_array(cams),
+                                        i32(V), i32(H), i32(W), P(pix), P(bary), P(zbuf), P(p2v), C.byref(skipped), ctx.stream),
+            "rasterize_mesh")
+    return dict(pix_to_face=pix, bary=bary, zbuf=zbuf, p2v=p2v, skipped=int(skipped.value))
+
+
+def shade_phong(ctx: Context, verts, faces, colors, cams, lights, pix_to_face, bary, ambient=0.5, diffuse=0.3, specular=0.2,
+                shininess=64.0):
+    """HardPhongShader over the rasteriser output -> uint8 [V,H,W,3] (white background)."""
+    assert colors.is_cuda and colors.dtype == torch.float32 and colors.is_contiguous() and colors.shape == verts.shape
+    V, H, W = pix_to_face.shape
+    lights = np.ascontiguousarray(lights, dtype=np.float32).reshape(V, 3)
+    rgb = torch.empty((V, H, W, 3), device=verts.device, dtype=torch.uint8)
+    L.check(ctx.lib.ivlm_shade_phong(ctx.h, P(verts), P(faces), i32(verts.shape[0]), i32(faces.shape[0]), P(colors),
+                                     _cam_array(cams), lights.ctypes.data_as(C.c_void_p), i32(V), i32(H), i32(W),
+                                     P(pix_to_face), P(bary), f32c(ambient), f32c(diffuse), f32c(specular), f32c(shininess),
+                                     P(rgb), ctx.stream), "shade_phong")
+    return rgb
+
+
 class LiftMap:
     """Per-(view, vertex) CSR built once from the reference's pixel->vertex / barycentric maps."""
 

@@ -108,6 +108,57 @@ def make_smplx_matrix(n_smplx: int = N_SMPLX, n_smpl: int = N_SMPL, seed: int = 
 
 
 # ---------------------------------------------------------------------------------------------- model weights
+def make_test_mesh(kind: str = "blob", n_lat: int = 24, n_lon: int = 48, seed: int = 0):
+    """Closed triangle meshes for the rasteriser tests / bench: `blob` = UV sphere with smooth radial noise (self-occluding
+    from most views), `torus`, `adversarial` = blob + coplanar overlapping quads (depth ties), degenerate faces, a face
+    behind the camera plane, a large face crossing the clip plane and faces leaving the view.  -> (verts f32 [Nv,3], faces
+    i64 [Nf,3]); extents ~[-0.5, 0.5] like normalize_mesh output."""
+    rng = np.random.default_rng(seed)
+    th = np.linspace(0, np.pi, n_lat + 1)[1:-1]
+    ph = np.linspace(0, 2 * np.pi, n_lon, endpoint=False)
+    T, Pp = np.meshgrid(th, ph, indexing="ij")
+    if kind == "torus":
+        th = np.linspace(0, 2 * np.pi, n_lat, endpoint=False)
+        T, Pp = np.meshgrid(th, ph, indexing="ij")
+        r = 0.33 + 0.14 * np.cos(T)
+        grid = np.stack([r * np.cos(Pp), 0.14 * np.sin(T), r * np.sin(Pp)], -1)
+        verts = grid.reshape(-1, 3)
+        idx = np.arange(n_lat * n_lon).reshape(n_lat, n_lon)
+        a, b = idx, np.roll(idx, -1, 1)
+        c, d = np.roll(idx, -1, 0), np.roll(np.roll(idx, -1, 0), -1, 1)
+        faces = np.concatenate([np.stack([a, c, b], -1).reshape(-1, 3), np.stack([b, c, d], -1).reshape(-1, 3)])
+        return verts.astype(np.float32), faces.astype(np.int64)
+    k = rng.normal(size=(4, 3))
+    dirs = np.stack([np.sin(T) * np.cos(Pp), np.cos(T), np.sin(T) * np.sin(Pp)], -1)
+    rad = 0.38 + 0.1 * np.sin(dirs @ k[0] * 3) * np.cos(dirs @ k[1] * 2) + 0.04 * np.sin(dirs @ k[2] * 7)
+    body = (dirs * rad[..., None]).reshape(-1, 3)
+    north, south = np.array([[0, 0.4, 0]]), np.array([[0, -0.4, 0]])
+    verts = np.concatenate([body, north, south])
+    n_body = body.shape[0]
+    idx = np.arange(n_body).reshape(n_lat - 1, n_lon)
+    a, b = idx[:-1], np.roll(idx[:-1], -1, 1)
+    c, d = idx[1:], np.roll(idx[1:], -1, 1)
+    faces = [np.stack([a, b, c], -1).reshape(-1, 3), np.stack([b, d, c], -1).reshape(-1, 3)]
+    top, bot = idx[0], idx[-1]
+    faces.append(np.stack([np.full(n_lon, n_body), np.roll(top, -1), top], -1))
+    faces.append(np.stack([np.full(n_lon, n_body + 1), bot, np.roll(bot, -1)], -1))
+    faces = np.concatenate(faces)
+    if kind == "adversarial":
+        n0 = verts.shape[0]
+        extra = np.array([
+            [-0.3, -0.3, 0.45], [0.3, -0.3, 0.45], [0.3, 0.3, 0.45], [-0.3, 0.3, 0.45],      # quad A (z = 0.45)
+            [-0.2, -0.35, 0.45], [0.35, -0.2, 0.45], [0.2, 0.35, 0.45], [-0.35, 0.2, 0.45],   # quad B, coplanar with A
+            [0.1, 0.1, 0.1], [0.1, 0.1, 0.1], [0.2, 0.2, 0.2],                                  # degenerate (two equal verts)
+            [0.0, 0.0, 5.0], [0.1, 0.0, 5.0], [0.0, 0.1, 5.0],                                  # behind a camera at z = 2
+            [-0.6, -0.2, 0.2], [0.6, -0.2, 0.2], [0.0, 0.1, 1.7],                               # crosses z_clip for that camera
+            [0.4, 0.4, 0.0], [3.0, 0.5, 0.0], [0.5, 3.0, 0.0],                                  # leaves the view
+        ])
+        verts = np.concatenate([verts, extra])
+        ef = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7], [8, 9, 10], [11, 12, 13], [14, 15, 16], [17, 18, 19]]) + n0
+        faces = np.concatenate([faces, ef, ef[:2]])  # the last two duplicate quad A exactly (identical depth everywhere)
+    return verts.astype(np.float32), faces.astype(np.int64)
+
+
 CLIP_PREFIX = "model.vision_tower.vision_tower.vision_model."
 SAM_PREFIX = "model.visual_model."
 

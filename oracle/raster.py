@@ -1,0 +1,197 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy, float32 arithmetic, no FMA contraction) of the "Render" step of
+Render-Localise-Lift: the reference's `get_rasterizer` + `project_vertices_and_create_mask`
+(preprocess_data/render_mesh_utils.py:115-174) and `normalize_mesh` (utils/demo_utils.py:130-145), which run
+pytorch3d's `look_at_view_transform`, `FoVPerspectiveCameras` and `MeshRasterizer` (blur_radius 0, faces_per_pixel 1).
+
+PARITY UNPINNED: pytorch3d (`git+https://github.com/facebookresearch/pytorch3d.git@stable`, requirements.txt:28, no
+version pin) is neither under /root/reference nor installed here, and the reference holds no test or golden vector for
+this step.  What follows restates pytorch3d's published algorithm:
+  * look_at_view_transform(dist, elev, azim) in degrees: camera centre C = dist*(cos(el)sin(az), sin(el), cos(el)cos(az)),
+    z = normalize(at - C), x = normalize(up x z), y = normalize(z x x) (x re-derived from y x z when degenerate), R has
+    the axes as COLUMNS, T = -R^T C, row-vector convention X_view = X_world R + T;
+  * FoVPerspectiveCameras defaults fov 60 deg, aspect 1, znear 1, zfar 100: x_ndc = x / (z tan(fov/2)), same for y; the
+    rasteriser keeps view-space z as depth (MeshRasterizer.transform);
+  * NDC has +X left and +Y up; pixel (row i, col j) samples y = 1 - (2i+1)/H, x = 1 - (2j+1)/W;
+  * per pixel and face: signed-area barycentrics with area + 1e-8, perspective correction w_k' ~ w_k * prod(z_other)
+    / max(sum, 1e-8), depth pz = sum w_k' z_k, a pixel is covered when all three corrected coordinates are > 0;
+    faces with |area| <= 1e-8, max z < 0 or pz < 0 are skipped; nearest pz wins, ties go to the lower face index;
+  * z_clip_value = znear / 2 for perspective cameras: triangles entirely behind it are culled; pytorch3d clips triangles
+    that straddle the plane into sub-triangles -- restated here as "covered only where pz >= z_clip" (identical coverage
+    while every vertex has z > 0; faces with a vertex at z <= 0 that straddle the plane are skipped and counted).
+Only tests/, __graft_entry__.smoke() and bench.py's CPU arm may import this module."""
+from __future__ import annotations
+
+import numpy as np
+
+F = np.float32
+K_EPS = F(1e-8)
+
+
+def normalize_mesh(verts, scale_factor=1.0):
+    """utils/demo_utils.py:130-145."""
+    v = np.asarray(verts, dtype=F)
+    c = v - v.mean(0, dtype=F)
+    size = (c.max(0) - c.min(0)).max()
+    return (c / size * F(scale_factor)).astype(F)
+
+
+def look_at_view_transform(dist, elev, azim):
+    """pytorch3d.renderer.cameras.look_at_view_transform (degrees, at = origin, up = +Y) -> R [3,3], T [3], C [3]."""
+    d, el, az = F(dist), F(np.deg2rad(F(elev))), F(np.deg2rad(F(azim)))
+    C = np.array([d * np.cos(el) * np.sin(az), d * np.sin(el), d * np.cos(el) * np.cos(az)], dtype=F)
+
+    def nrm(v):
+        return (v / max(np.sqrt((v * v).sum(dtype=F)), F(1e-5))).astype(F)  # F.normalize eps = 1e-5 in look_at_rotation
+
+    up = np.array([0, 1, 0], dtype=F)
+    z = nrm(-C)
+    x = nrm(np.cross(up, z).astype(F))
+    y = nrm(np.cross(z, x).astype(F))
+    if np.all(np.abs(x) <= 5e-3):
+        x = nrm(np.cross(y, z).astype(F))
+    R = np.stack([x, y, z], axis=1).astype(F)  # axes as columns
+    T = (-(R.T @ C)).astype(F)
+    return R, T, C
+
+
+def camera(cam_params, fov_deg=60.0, znear=1.0):
+    """render_mesh_utils.py:115-121: (distance, elevation, azimuth, x_trans, y_trans) -> dict(R, T, C, s, z_clip)."""
+    dist, elev, azim, xt, yt = [float(c) for c in cam_params]
+    R, T, C = look_at_view_transform(dist, elev, azim)
+    T = T.copy()
+    T[1] += F(yt)
+    T[0] += F(xt)
+    s = F(1.0) / F(np.tan(F(np.deg2rad(F(fov_deg))) / F(2)))
+    return dict(R=R, T=T, C=C, s=F(s), z_clip=F(znear / 2.0))
+
+
+def project(verts, cam):
+    """[Nv,3] world -> [Nv,3] (x_ndc, y_ndc, z_view), float32, fixed operation order (matches the CUDA kernel)."""
+    v = np.asarray(verts, dtype=F)
+    R, T = cam["R"], cam["T"]
+    out = np.empty_like(v)
+    view = np.empty_like(v)
+    for k in range(3):
+        view[:, k] = ((v[:, 0] * R[0, k] + v[:, 1] * R[1, k]) + v[:, 2] * R[2, k]) + T[k]
+    out[:, 0] = (view[:, 0] * cam["s"]) / view[:, 2]
+    out[:, 1] = (view[:, 1] * cam["s"]) / view[:, 2]
+    out[:, 2] = view[:, 2]
+    return out
+
+
+def _edge(px, py, ax, ay, bx, by):
+    return (px - ax) * (by - ay) - (py - ay) * (bx - ax)
+
+
+def rasterize(verts, faces, cam, H, W):
+    """pytorch3d rasterize_meshes (naive path), K=1, blur 0, perspective_correct.  Returns pix_to_face [H,W] int32 (-1 =
+    background), bary [H,W,3] f32 (-1 on background, like pytorch3d), zbuf [H,W] f32 (-1 on background), n_skipped."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = project(verts, cam)
+    faces = np.asarray(faces, dtype=np.int64)
+    pix = np.full((H, W), -1, dtype=np.int32)
+    bary = np.full((H, W, 3), -1, dtype=F)
+    zbuf = np.full((H, W), -1, dtype=F)
+    best = np.full((H, W), np.inf, dtype=F)
+    # PixToNonSquareNdc on the flipped index (square images): -1 + (2 i' + 1) / S with i' = S - 1 - i
+    ys = (F(-1) + (F(2) * (H - 1 - np.arange(H)).astype(F) + F(1)) / F(H)).astype(F)
+    xs = (F(-1) + (F(2) * (W - 1 - np.arange(W)).astype(F) + F(1)) / F(W)).astype(F)
+    zc = cam["z_clip"]
+    skipped = 0
+    for f, (i0, i1, i2) in enumerate(faces):
+        (x0, y0, z0), (x1, y1, z1), (x2, y2, z2) = p[i0], p[i1], p[i2]
+        zmin, zmax = min(z0, z1, z2), max(z0, z1, z2)
+        if zmax < zc:
+            continue  # entirely behind the clip plane (clip_faces case 1) / behind the camera
+        if zmin <= 0:
+            skipped += 1  # straddles the camera plane: pytorch3d clips it; not restated
+            continue
+        area = _edge(x2, y2, x0, y0, x1, y1)
+        if -K_EPS <= area <= K_EPS:
+            continue
+        xmin, xmax, ymin, ymax = min(x0, x1, x2), max(x0, x1, x2), min(y0, y1, y2), max(y0, y1, y2)
+        # pixel rows/cols whose centre lies inside the bounding box (x decreases with the column index)
+        cols = np.nonzero((xs >= xmin) & (xs <= xmax))[0]
+        rows = np.nonzero((ys >= ymin) & (ys <= ymax))[0]
+        if len(cols) == 0 or len(rows) == 0:
+            continue
+        px = xs[cols][None, :]
+        py = ys[rows][:, None]
+        den = area + K_EPS
+        w0 = _edge(px, py, x1, y1, x2, y2) / den
+        w1 = _edge(px, py, x2, y2, x0, y0) / den
+        w2 = _edge(px, py, x0, y0, x1, y1) / den
+        t0 = (w0 * z1) * z2
+        t1 = (z0 * w1) * z2
+        t2 = (z0 * z1) * w2
+        d = np.maximum((t0 + t1) + t2, K_EPS)
+        b0, b1, b2 = t0 / d, t1 / d, t2 / d
+        pz = (b0 * z0 + b1 * z1) + b2 * z2
+        inside = (b0 > 0) & (b1 > 0) & (b2 > 0) & (pz >= 0)
+        if zmin < zc:
+            inside &= pz >= zc  # the part of a straddling triangle that pytorch3d's clip_faces keeps
+        r = rows[:, None].repeat(len(cols), 1)
+        c = cols[None, :].repeat(len(rows), 0)
+        cur = best[r, c]
+        take = inside & (pz < cur)  # faces visited in ascending order: ties keep the lower index
+        rr, cc = r[take], c[take]
+        best[rr, cc] = pz[take]
+        pix[rr, cc] = f
+        zbuf[rr, cc] = pz[take]
+        bary[rr, cc, 0], bary[rr, cc, 1], bary[rr, cc, 2] = b0[take], b1[take], b2[take]
+    return pix, bary, zbuf, skipped
+
+
+def project_vertices_and_create_mask(verts, faces, cam_params, contact_vertices, image_size, min_vertices=3):
+    """render_mesh_utils.py:123-174 -> (mask uint8 [H,W] in {0,255}, pixel_to_vertices_map int64 [H,W,3] (-1 background),
+    bary f32 [H,W,3])."""
+    H, W = image_size
+    faces = np.asarray(faces, dtype=np.int64)
+    pix, bary, _, _ = rasterize(verts, faces, camera(cam_params), H, W)
+    cnt = np.isin(faces, list(set(int(v) for v in contact_vertices))).sum(1)
+    hot = cnt >= min_vertices
+    mask = ((pix >= 0) & hot[np.maximum(pix, 0)]).astype(np.uint8) * 255
+    p2v = np.full((H, W, 3), -1, dtype=np.int64)
+    p2v[pix >= 0] = faces[pix[pix >= 0]]
+    return mask, p2v, bary
+
+
+def vertex_normals(verts, faces):
+    """pytorch3d Meshes.verts_normals_packed(): area-weighted sum of the face normals, normalised (eps 1e-6)."""
+    v = np.asarray(verts, dtype=F)
+    f = np.asarray(faces, dtype=np.int64)
+    n = np.zeros_like(v)
+    v0, v1, v2 = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    np.add.at(n, f[:, 1], np.cross(v2 - v1, v0 - v1))
+    np.add.at(n, f[:, 2], np.cross(v0 - v2, v1 - v2))
+    np.add.at(n, f[:, 0], np.cross(v1 - v0, v2 - v0))
+    return (n / np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-6)).astype(F)
+
+
+def render_phong(verts, faces, colors, cam, light_location, H, W, ambient=0.5, diffuse=0.3, specular=0.2, shininess=64.0):
+    """render_mesh (render_mesh_utils.py:177-198): MeshRenderer(MeshRasterizer, HardPhongShader) with one PointLights
+    (ambient .5, diffuse .3, specular .2), default Materials (shininess 64), white background, `(image*255).astype(uint8)`.
+    Returns uint8 [H,W,3]."""
+    v = np.asarray(verts, dtype=F)
+    f = np.asarray(faces, dtype=np.int64)
+    col = np.asarray(colors, dtype=F)
+    pix, bary, _, _ = rasterize(v, f, cam, H, W)
+    nrm = vertex_normals(v, f)
+    fg = pix >= 0
+    fi = f[pix[fg]]
+    b = bary[fg]
+    interp = lambda a: (b[:, 0:1] * a[fi[:, 0]] + b[:, 1:2] * a[fi[:, 1]]) + b[:, 2:3] * a[fi[:, 2]]
+    pts, nn, tex = interp(v), interp(nrm), interp(col)
+    unit = lambda a: a / np.maximum(np.linalg.norm(a, axis=1, keepdims=True), 1e-6)
+    nn = unit(nn)
+    L = unit(np.asarray(light_location, dtype=F)[None] - pts)
+    cosang = (nn * L).sum(1)
+    diff = F(diffuse) * np.maximum(cosang, 0)
+    view = unit(cam["C"][None] - pts)
+    refl = -L + 2 * (cosang[:, None] * nn)
+    alpha = np.maximum((view * refl).sum(1), 0) * (cosang > 0)
+    spec = F(specular) * np.power(alpha, F(shininess))
+    rgb = (F(ambient) + diff)[:, None] * tex + spec[:, None]
+    img = np.ones((H, W, 3), dtype=F)
+    img[fg] = rgb
+    return (img * 255).astype(np.uint8)
