@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--sm-limit", type=int, default=104, help="SMs the encoder GEMMs keep to while decode steps are in flight")
     ap.add_argument("--limited-chunks", type=int, default=-1, help="encoder chunks launched SM-limited (-1: estimate)")
     ap.add_argument("--sam-chunk", type=int, default=4, help="views per encoder chunk")
+    ap.add_argument("--pdl", type=int, default=1, help="1: programmatic dependent launch for the decode chain")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -235,7 +236,8 @@ def main():
               "views": cfg.multiview_channels, "parallelism": f"dp{world} (batch-sharded, one NCCL all-gather of [B,6890])",
               "l2": "inputs (201 MB/step) and weights (28 GB) exceed the 126 MB L2; no explicit flush",
               "overlap": ({"sam_encoder_next_to_decode": True, "sm_limit": args.sm_limit, "limited_chunks": args.limited_chunks,
-                           "sam_chunk": args.sam_chunk} if args.overlap else None)}
+                           "sam_chunk": args.sam_chunk} if args.overlap else None),
+              "pdl_decode_chain": bool(args.pdl)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -274,7 +276,7 @@ def main():
 
     dev = torch.device("cuda", local_rank)
     sd = S.make_state_dict(cfg, seed=0, device=dev, gain=0.5)
-    model = InteractVLMForCausalLM(cfg, sd, device=local_rank)
+    model = InteractVLMForCausalLM(cfg, sd, device=local_rank, use_pdl=bool(args.pdl))
     del sd
     if args.overlap:
         model.enable_overlap(sm_limit=args.sm_limit, limited_chunks=None if args.limited_chunks < 0 else args.limited_chunks,
@@ -359,6 +361,7 @@ def main():
             # roofline of the dominant kernel (tcgen05 GEMM), timed per launch with CUDA events on the launching stream
             model.use_cuda_graph = False
             model._graphs = {}
+            model.ctx.set_option("pdl", 0)  # per-launch event pairs need serialised kernels
             model.ctx.enable_profile()
             # park the GPU (~100 ms spin) at the start of the CLIP/prefill stage and of every SAM chunk so that the host
             # is hundreds of launches ahead: the event pairs then bracket pure GPU time, not host launch latency
@@ -367,6 +370,7 @@ def main():
             model.stage_delay = None
             rep = model.ctx.profile_report()
             model.ctx.disable_profile()
+            model.ctx.set_option("pdl", int(bool(args.pdl)))
             model.use_cuda_graph = True
             tot = sum(r["ms"] for r in rep.values())
             g = rep["gemm"]

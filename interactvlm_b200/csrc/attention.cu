@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
     constexpr int NLD = DEC_PAGE / RPI;    // load instructions per page
     __shared__ float part[DEC_WARPS * RPI][HD];
     __shared__ int bt[DEC_MAX_PAGES];
-    pdl_wait();
+    pdl_wait_then_launch();
     const int h = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane / LPR, li = lane % LPR;

@@ -102,6 +102,11 @@ IVLM_DEVINL void named_bar_sync(int id, int nthreads) {
 // (prologue, barrier / TMEM setup, prefetch of static operands) while its predecessor drains; it must execute this
 // wait before touching anything the predecessor wrote.  Without the attribute the instruction returns immediately.
 IVLM_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the NEXT kernel of the stream (if it was launched with the attribute) become resident now instead of when this grid
+// has drained: its launch latency, prologue and static-operand prefetch then overlap this kernel's execution.  Takes
+// effect once every CTA of this grid has executed it (or exited).  No-op without a programmatic dependent.
+IVLM_DEVINL void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+IVLM_DEVINL void pdl_wait_then_launch() { pdl_wait(); pdl_launch(); }
 
 // ---------------------------------------------------------------- mbarrier
 IVLM_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {

@@ -150,6 +150,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
+    pdl_launch();  // the successor's launch + prologue (and weight prefetch, if it is a swapped GEMM) overlap this kernel
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer

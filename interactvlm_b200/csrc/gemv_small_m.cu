@@ -38,7 +38,6 @@ template <int NT, int ROWS>
 __global__ void __launch_bounds__(GV_MAX_WARPS * 32) gemv_small_m_kernel(const GemvParams p) {
     extern __shared__ float part[];  // [warps][GV_ROWS][8*NT + 1]
     constexpr int PLD = 8 * NT + 1;
-    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;  // the k-steps of this CTA's 16 rows are dealt round-robin to its warps
     const int g = lane >> 2, t = lane & 3;
@@ -46,6 +45,29 @@ __global__ void __launch_bounds__(GV_MAX_WARPS * 32) gemv_small_m_kernel(const G
     const int r_lo = min(row0 + g, p.N - 1), r_hi = min(row0 + g + 8, p.N - 1);
     const bf16* w_lo = p.w + (long long)r_lo * p.ldw + 8 * t;
     const bf16* w_hi = p.w + (long long)r_hi * p.ldw + 8 * t;
+    const int steps = p.K >> 5;  // 32 k per step
+    const int stride = nwarps * GV_UNROLL;
+
+    // a warp iteration covers GV_UNROLL ADJACENT k-steps (GV_UNROLL * 64 contiguous bytes of every row); the chunks of
+    // one round are dealt to consecutive warps, so a round reads nwarps * GV_UNROLL * 64 contiguous bytes per row.
+    // The FIRST round is issued before griddepcontrol.wait -- weights are static, so under programmatic dependent launch
+    // they stream while the predecessor kernel is still running.  (Double buffering the weight registers costs 30
+    // registers and the third resident CTA per SM: 320 CTAs would no longer fit one wave.)
+    uint4 wl[GV_UNROLL], wh[GV_UNROLL];
+    auto load_round = [&](uint4(&l)[GV_UNROLL], uint4(&h)[GV_UNROLL], int s0) {
+#pragma unroll
+        for (int u = 0; u < GV_UNROLL; ++u) {
+            const int s = s0 + u;
+            if (s < steps) {
+                l[u] = __ldcs(reinterpret_cast<const uint4*>(w_lo + (s << 5)));  // streamed once: evict-first
+                h[u] = ROWS == 16 ? __ldcs(reinterpret_cast<const uint4*>(w_hi + (s << 5))) : make_uint4(0, 0, 0, 0);
+            }
+        }
+    };
+    load_round(wl, wh, warp * GV_UNROLL);
+    pdl_launch();
+    pdl_wait();
+
     const bf16* x_row[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) x_row[nt] = p.a + (long long)min(nt * 8 + g, p.M - 1) * p.lda + 8 * t;
@@ -54,19 +76,7 @@ __global__ void __launch_bounds__(GV_MAX_WARPS * 32) gemv_small_m_kernel(const G
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
 
-    const int steps = p.K >> 5;  // 32 k per step
-    // a warp iteration covers GV_UNROLL ADJACENT k-steps (GV_UNROLL * 64 contiguous bytes of every row); the chunks of
-    // one round are dealt to consecutive warps, so a round reads nwarps * GV_UNROLL * 64 contiguous bytes per row
-    for (int s0 = warp * GV_UNROLL; s0 < steps; s0 += nwarps * GV_UNROLL) {
-        uint4 wl[GV_UNROLL], wh[GV_UNROLL];
-#pragma unroll
-        for (int u = 0; u < GV_UNROLL; ++u) {
-            const int s = s0 + u;
-            if (s < steps) {
-                wl[u] = __ldcs(reinterpret_cast<const uint4*>(w_lo + (s << 5)));  // streamed once: evict-first
-                wh[u] = ROWS == 16 ? __ldcs(reinterpret_cast<const uint4*>(w_hi + (s << 5))) : make_uint4(0, 0, 0, 0);
-            }
-        }
+    for (int s0 = warp * GV_UNROLL; s0 < steps; s0 += stride) {
 #pragma unroll
         for (int u = 0; u < GV_UNROLL; ++u) {
             const int s = s0 + u;
@@ -81,6 +91,7 @@ __global__ void __launch_bounds__(GV_MAX_WARPS * 32) gemv_small_m_kernel(const G
                 }
             }
         }
+        load_round(wl, wh, s0 + stride);
     }
     // c[nt][0,1] = (row g, tokens nt*8 + 2t, 2t+1); c[nt][2,3] = (row g+8, same tokens)
 #pragma unroll

@@ -13,7 +13,7 @@ __global__ void rope_kv_store_kernel(const bf16* __restrict__ qkv, const int* __
                                      const bf16* __restrict__ sin_t, bf16* __restrict__ q_out, bf16* __restrict__ k_out,
                                      bf16* __restrict__ v_out, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
                                      int H, int hd, int page) {
-    pdl_wait();
+    pdl_wait_then_launch();
     // grid (tokens, chunks): every thread owns one (head, rotary pair) and one 16-byte piece of the V row, so a
     // decode step (8 tokens) spreads over ~100 CTAs instead of serialising ten dependent loads per thread in 8
     const long long tkn = blockIdx.x;
@@ -109,7 +109,7 @@ __global__ void decode_prepare_kernel(int* __restrict__ state, int S, const int*
                                       const int* __restrict__ next, int* __restrict__ done, int* __restrict__ out_tokens,
                                       int* __restrict__ tok, int* __restrict__ pos, int* __restrict__ slot,
                                       int* __restrict__ seq_lens, const int* __restrict__ slot_base, int eos, int pad, int B) {
-    pdl_wait();
+    pdl_wait_then_launch();
     const int step = state[0];
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -131,7 +131,7 @@ __global__ void decode_prepare_kernel(int* __restrict__ state, int S, const int*
 // hidden[b, S + step, :] = hid_step[b, :]
 __global__ void decode_finish_kernel(const int* __restrict__ state, int S, const bf16* __restrict__ hid_step,
                                      bf16* __restrict__ hidden, int D, int max_len) {
-    pdl_wait();
+    pdl_wait_then_launch();
     const int b = blockIdx.x, p = S + state[1];
     const uint4* src = reinterpret_cast<const uint4*>(hid_step + (long long)b * D);
     uint4* dst = reinterpret_cast<uint4*>(hidden + ((long long)b * max_len + p) * D);

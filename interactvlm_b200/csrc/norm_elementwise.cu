@@ -157,7 +157,7 @@ __global__ void rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
 __global__ void __launch_bounds__(256) rmsnorm_row_cta_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                                               const bf16* __restrict__ gamma, int D, float eps) {
     __shared__ float red[8];
-    pdl_wait();
+    pdl_wait_then_launch();
     const long long row = blockIdx.x;
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
     const int nvec = D >> 3;
@@ -212,7 +212,7 @@ __global__ void add_bcast_kernel(const uint4* __restrict__ a, const uint4* __res
 }
 
 __global__ void silu_mul_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, long long rows, int F) {
-    pdl_wait();
+    pdl_wait_then_launch();
     const int fvec = F >> 3;
     const long long total = rows * fvec;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -333,7 +333,7 @@ __global__ void embed_splice_kernel(const bf16* __restrict__ embed, const int* _
 
 __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int* __restrict__ idx, bf16* __restrict__ out, int n,
                                    int D, int max_row) {
-    pdl_wait();
+    pdl_wait_then_launch();
     const int r = blockIdx.x;
     int s = idx[r];
     if (max_row > 0) s = s < 0 ? 0 : (s >= max_row ? max_row - 1 : s);
@@ -344,7 +344,7 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int* __rest
 
 // torch.argmax semantics: first maximal index. One CTA per row.
 __global__ void argmax_kernel(const float* __restrict__ logits, int* __restrict__ out, int vocab, long long ld) {
-    pdl_wait();
+    pdl_wait_then_launch();
     const float* row = logits + (long long)blockIdx.x * ld;
     float best = -INFINITY;
     int bi = 0x7fffffff;

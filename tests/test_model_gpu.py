@@ -187,6 +187,36 @@ def test_overlapped_encoder_is_bit_identical_to_serial(tiny):
         model.disable_overlap()
 
 
+def test_programmatic_dependent_launch_is_bit_identical(tiny, ctx):
+    """Option "pdl": decode-chain kernels launched with programmatic stream serialisation (early launch_dependents
+    trigger, static-weight prefetch before griddepcontrol.wait) -> same kernels, same operands, same bits; eager and
+    under CUDA-graph replay, scripted and greedy."""
+    cfg, sd, model, _ = tiny
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
+    args = (clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2)
+    ctx.set_option("pdl", 0)
+    model._graphs = {}
+    base = model.evaluate(*args, max_new_tokens=ans.shape[1], scripted=ans)
+    base_g = model.evaluate(*args, max_new_tokens=6)
+    try:
+        ctx.set_option("pdl", 1)
+        model._graphs = {}
+        for graphs in (True, False):
+            model.use_cuda_graph = graphs
+            model._graphs = {}
+            for _ in range(2):
+                out = model.evaluate(*args, max_new_tokens=ans.shape[1], scripted=ans)
+            assert torch.equal(out["output_ids"], base["output_ids"])
+            assert torch.equal(out["pred_contact_3d"], base["pred_contact_3d"])
+            for a, b in zip(out["pred_masks"], base["pred_masks"]):
+                assert torch.equal(a, b)
+            assert torch.equal(model.evaluate(*args, max_new_tokens=6)["output_ids"], base_g["output_ids"])
+    finally:
+        ctx.set_option("pdl", 1)  # the model's default
+        model.use_cuda_graph = True
+        model._graphs = {}
+
+
 def test_full_size_layers_vs_torch_fp32(ctx):
     """One SAM ViT-H block pair (window + global), one LLaMA-13B layer and the CLIP-L stack at their REAL widths:
     the oracle restatement evaluated with stock torch fp32 CUDA ops is the checker (CPU would take minutes)."""

@@ -78,6 +78,30 @@ if len(sys.argv) > 1 and sys.argv[1] == "sweep":
             ctx.set_option(k, v)
         print(label + ": " + "  ".join(f"{n[5:]} {graph_time(fn):6.2f}us" for n, (fn, _) in gemms.items()), flush=True)
     sys.exit(0)
+def layer_chain(i):
+    """the 9 launches of one decode layer, in order, on rotating weights (what the captured decode graph replays)"""
+    y = ctx.rmsnorm(x, gam, 1e-5)
+    qkv_ = ctx.gemm(y, wqkv[i % NW])
+    q_, _, _ = ctx.rope_kv_store(qkv_, pos, slot, cos_t, sin_t, H, hd, kc[i % NW], vc[i % NW], want_kv=False, page_size=page)
+    o_ = ctx.decode_attention(q_, kc[i % NW], vc[i % NW], bt, sl, H, hd, page)
+    x1 = ctx.gemm(o_, wo[i % NW], residual=x)
+    y = ctx.rmsnorm(x1, gam, 1e-5)
+    y = ctx.silu_mul(ctx.gemm(y, wgu[i % NW]))
+    return ctx.gemm(y, wd[i % NW], residual=x1)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "chain":
+    ref = None
+    for pdl in (0, 1, 0, 1):
+        ctx.set_option("pdl", pdl)
+        us = graph_time(layer_chain)
+        out = layer_chain(0).float()
+        torch.cuda.synchronize()
+        same = True if ref is None else bool(torch.equal(out, ref))
+        ref = out if ref is None else ref
+        print(f"layer chain in a graph, pdl={pdl}: {us:7.2f} us per layer -> {us * 40 / 1e3:.2f} ms per 40-layer step; identical output: {same}", flush=True)
+    ctx.set_option("pdl", 0)
+    sys.exit(0)
 tot = 0.0
 for name, (fn, nbytes) in ops.items():
     us = graph_time(fn)
