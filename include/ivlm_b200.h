@@ -277,6 +277,15 @@ IVLM_API int ivlm_shade_phong(ivlm_handle h, const float* verts, const int32_t* 
                      const int32_t* pix_to_face, const float* bary, float ambient, float diffuse, float specular,
                      float shininess, uint8_t* rgb, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pose refinement (optim/), contact term: ObjPose_Opt.contact_loss (optim/optimizer.py:80-96),
+ *   loss = sum_ij p_i q_j |o_i - h_j| / (sum p * sum q)
+ * and, when grad_obj != NULL, d loss / d obj_verts [n_obj,3] in the same pass (the reference builds the [n_obj, n_hum]
+ * cdist and outer-product matrices and differentiates through them).  fp32; deterministic; uses the handle's workspace
+ * (16 bytes x n_obj x splits). */
+IVLM_API int ivlm_contact_loss(ivlm_handle h, const float* obj_verts, const float* obj_prob, const float* hum_verts,
+                      const float* hum_prob, int32_t n_obj, int32_t n_hum, float* loss, float* grad_obj, void* stream);
+
 /* convert_contacts (utils/utils.py:428-443): SMPL->SMPL-X dense [R,C] matrix applied as CSR SpMV.
  * csr built once from the host dense matrix. */
 typedef struct ivlm_csr ivlm_csr;
