@@ -126,3 +126,28 @@ def test_generate_sam_inp_objs_and_lift_from_pickle(ctx, tmp_path):
     got = LiftMap(ctx, p2v, bary, len(v))(logits, LIFT_OBJECT_MESH).cpu().numpy()
     want = OL.lift_object_mesh(logits.cpu().numpy(), p2v, bary, len(v))
     assert np.abs(got - want).max() < 1e-6
+
+
+def test_object_demo_flow_mesh_to_vertex_contact(ctx, tmp_path):
+    """run_demo.py's object path end to end on the tiny configuration: .obj -> rendered views + lift2d_dict.pkl (GPU
+    rasteriser) -> evaluate(contact_type='oafford') -> per-vertex contact == oracle lift of the predicted masks."""
+    import importlib.util
+    import joblib
+
+    from interactvlm_b200.config import IVLMConfig
+    from interactvlm_b200.model import InteractVLMForCausalLM
+
+    spec = importlib.util.spec_from_file_location("demo_obj", str(R.Path(__file__).resolve().parents[1] / "examples" / "demo_synthetic_object.py"))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    cfg = IVLMConfig.tiny()
+    model = InteractVLMForCausalLM(cfg, S.make_state_dict(cfg, seed=0), ctx=ctx)
+    _, res, f, obj_dir = demo.run(tmp_path, "tiny", model=model)
+    d = joblib.load(obj_dir / "lift2d_dict.pkl")
+    p2v, bary = np.stack(d["pixel_to_vertices_map"]), np.stack(d["bary_coords_map"])
+    masks = res["pred_masks"][0].cpu().numpy()[None]
+    assert masks.shape == (1, 4, 1024, 1024)
+    want = OL.lift_object_mesh(masks, p2v, bary, d["num_vertices"])
+    got = np.load(f)["pred_contact_3d"]
+    assert got.shape == (1, d["num_vertices"]) and np.abs(got - want).max() < 1e-6
+    assert np.array_equal(got > 0.5, want > 0.5)
