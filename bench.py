@@ -222,7 +222,7 @@ def main():
                     "(measured slower on B200, profiles/r1_overlap_timeline.txt; kept as an option)")
     ap.add_argument("--sm-limit", type=int, default=104, help="SMs the encoder GEMMs keep to while decode steps are in flight")
     ap.add_argument("--limited-chunks", type=int, default=-1, help="encoder chunks launched SM-limited (-1: estimate)")
-    ap.add_argument("--sam-chunk", type=int, default=4, help="views per encoder chunk")
+    ap.add_argument("--sam-chunk", type=int, default=0, help="views per encoder chunk (0: model default, 16; 4 with --overlap)")
     ap.add_argument("--pdl", type=int, default=1, help="1: programmatic dependent launch for the decode chain")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -280,9 +280,9 @@ def main():
     del sd
     if args.overlap:
         model.enable_overlap(sm_limit=args.sm_limit, limited_chunks=None if args.limited_chunks < 0 else args.limited_chunks,
-                             sam_chunk=args.sam_chunk)
-    else:
-        model.sam_chunk = args.sam_chunk if args.sam_chunk != 4 else 8
+                             sam_chunk=args.sam_chunk or 4)
+    elif args.sam_chunk:
+        model.sam_chunk = args.sam_chunk
     p2v, bary = S.make_mesh_lift_maps(seed=0)
     model.set_human_lift_maps(p2v, bary)
     del p2v, bary

@@ -557,7 +557,7 @@ class InteractVLMForCausalLM:
         self.human_3d_contact_predictor = _Predictor(self, LIFT_HUMAN)
         self.object_3d_contact_predictor = _Predictor(self, LIFT_OBJECT_MESH)
         self.object_3d_afford_predictor = _Predictor(self, LIFT_POINTS)
-        self.sam_chunk = 8
+        self.sam_chunk = 16  # views per encoder pass: 16 x 4096 rows keep the last partial wave of the N=1280 GEMMs small
         # SAM encoder (tensor-bound) next to the LLaMA decode chain (HBM-bound): see enable_overlap()
         self.overlap = None
         self.record_stages = False  # bench.py: CUDA events at stage boundaries (a dozen per call)
