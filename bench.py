@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--sm-limit", type=int, default=104, help="SMs the encoder GEMMs keep to while decode steps are in flight")
     ap.add_argument("--limited-chunks", type=int, default=-1, help="encoder chunks launched SM-limited (-1: estimate)")
     ap.add_argument("--sam-chunk", type=int, default=0, help="views per encoder chunk (0: model default, 16; 4 with --overlap)")
+    ap.add_argument("--no-view-cache-pass", action="store_true", help="skip the separately reported constant-views measurement")
     ap.add_argument("--pdl", type=int, default=1, help="1: programmatic dependent launch for the decode chain")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -351,6 +352,33 @@ def main():
                     "d2h_bytes_per_step": int(host_out.numel() * 4)},
             "gpu_launches": int(launches + graph_launches), "sam_views_per_s": value * cfg.multiview_channels,
             "stage_ms": {k: round(v, 2) for k, v in stages.items()}}
+
+    if world == 1 and not args.no_view_cache_pass:
+        # NOT the headline: the real hcontact harness feeds the SAME four body renders with every image (run_demo.py:279-281);
+        # with the exact-match view cache the encoder runs once per distinct view instead of once per sample.
+        model.enable_view_cache()
+        same = sam_d[:1].expand(args.batch, *sam_d.shape[1:]).contiguous()
+
+        def cstep():
+            out = model.evaluate(clip_d, same, ids, cam_d, sizes, sizes, contact_type="hcontact", max_new_tokens=N_ANS, scripted=ans)
+            return out["pred_contact_3d"]
+
+        for _ in range(2):
+            cstep()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            cstep()
+        e1.record()
+        torch.cuda.synchronize()
+        cms = e0.elapsed_time(e1) / args.steps
+        line["hcontact_constant_views"] = {
+            "value": args.batch / (cms / 1e3), "unit": "images/s", "ms_per_step": cms,
+            "cache": {k: model._view_cache[k] for k in ("hits", "misses")},
+            "note": "separate from the headline: all samples share the same 4 SAM views (as run_demo.py hcontact does), exact-match "
+                    "view cache on (model.enable_view_cache): bit-identical outputs, encoder skipped for views seen before"}
+        model._view_cache = None
 
     if rank == 0:
         pk = peaks()

@@ -199,6 +199,12 @@ IVLM_API int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, cons
 IVLM_API int ivlm_argmax_f32(ivlm_handle h, const float* logits, int32_t* out, int32_t B, int32_t vocab, int64_t ld,
                     void* stream);
 /* rows gather: out[i,:] = x[idx[i],:] (bf16), e.g. the [SEG]-1 hidden rows (InteractVLM.py:545-556). */
+/* neq[i*K + k] = 1 when row i of x [n rows] and row k of ref [K rows] differ in any bit, else 0 (rows of row_bytes bytes,
+ * a multiple of 16; 16-byte aligned).  Exact-match test of the encoder's view cache: the hcontact harness feeds the same
+ * four body renders with every image (run_demo.py:279-281), whose embeddings the reference recomputes each time
+ * (InteractVLM.py:578). */
+IVLM_API int ivlm_rows_differ(ivlm_handle h, const void* x, int32_t n, const void* ref, int32_t K, int64_t row_bytes,
+                     int32_t* neq, void* stream);
 IVLM_API int ivlm_gather_rows_bf16(ivlm_handle h, const void* x, const int32_t* idx, void* out, int32_t n, int32_t D,
                           void* stream);
 

@@ -1,6 +1,8 @@
 // HBM-bound row-wise and elementwise kernels: LayerNorm / RMSNorm (warp per row, 16-byte loads, warp-shuffle
 // reductions, fp32 statistics), broadcast add, SwiGLU gate, split-K finalize, casts, im2col lowering,
 // embedding gather / image splice, greedy argmax, bilinear resize, camera gate.
+#include <algorithm>
+
 #include "common.cuh"
 #include "runtime.h"
 
@@ -342,6 +344,34 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int* __rest
     for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) dst[i] = src[i];
 }
 
+// neq[i * K + k] = 1 when row i of x and row k of ref differ in any bit.  grid (segments, n * K): every CTA compares one
+// segment of one pair with 16-byte loads and leaves at the first mismatch it (or another CTA of the pair) has seen.
+__global__ void __launch_bounds__(256) rows_differ_kernel(const uint4* __restrict__ x, const uint4* __restrict__ ref, int K,
+                                                          long long row_vecs, long long seg_vecs, int* __restrict__ neq) {
+    const int pair = blockIdx.y;
+    const int i = pair / K, k = pair % K;
+    const uint4* a = x + (long long)i * row_vecs;
+    const uint4* b = ref + (long long)k * row_vecs;
+    const long long v0 = (long long)blockIdx.x * seg_vecs, v1 = min(v0 + seg_vecs, row_vecs);
+    volatile int* flag = neq + pair;
+    for (long long base = v0; base < v1; base += 256 * 4) {
+        bool diff = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long v = base + u * 256 + threadIdx.x;
+            if (v < v1) {
+                const uint4 p = __ldg(a + v), q = __ldg(b + v);
+                diff |= (p.x != q.x) | (p.y != q.y) | (p.z != q.z) | (p.w != q.w);
+            }
+        }
+        if (__syncthreads_or(diff)) {
+            if (threadIdx.x == 0) *flag = 1;
+            return;
+        }
+        if (*flag) return;  // another segment of this pair already differs
+    }
+}
+
 // torch.argmax semantics: first maximal index. One CTA per row.
 __global__ void argmax_kernel(const float* __restrict__ logits, int* __restrict__ out, int vocab, long long ld) {
     pdl_wait_then_launch();
@@ -605,6 +635,19 @@ extern "C" int ivlm_gather_rows_bf16(ivlm_handle h, const void* x, const int32_t
     IVLM_REQUIRE(h && D % 8 == 0 && n > 0, "gather_rows: bad shape");
     IVLM_CHECK_CUDA(launch_k(h, gather_rows_kernel, dim3(n), dim3(128), 0, STREAM, (const bf16*)x, (const int*)idx,
                              (bf16*)out, (int)n, (int)D, 0));
+    DONE();
+}
+extern "C" int ivlm_rows_differ(ivlm_handle h, const void* x, int32_t n, const void* ref, int32_t K, int64_t row_bytes,
+                                int32_t* neq, void* stream) {
+    IVLM_REQUIRE(h && x && ref && neq && n > 0 && K > 0 && row_bytes > 0 && row_bytes % 16 == 0,
+                 "rows_differ: need n, K > 0 and a row size that is a multiple of 16 bytes");
+    IVLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(ref) & 15) == 0,
+                 "rows_differ: 16-byte aligned rows");
+    const long long row_vecs = row_bytes / 16;
+    int segs = (int)std::min<long long>(64, (row_vecs + 4095) / 4096);
+    const long long seg_vecs = (row_vecs + segs - 1) / segs;
+    IVLM_CHECK_CUDA(cudaMemsetAsync(neq, 0, sizeof(int) * (size_t)n * K, STREAM));
+    rows_differ_kernel<<<dim3(segs, n * K), 256, 0, STREAM>>>((const uint4*)x, (const uint4*)ref, K, row_vecs, seg_vecs, neq);
     DONE();
 }
 extern "C" int ivlm_argmax_f32(ivlm_handle h, const float* logits, int32_t* out, int32_t B, int32_t vocab, int64_t ld,

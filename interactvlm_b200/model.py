@@ -560,6 +560,7 @@ class InteractVLMForCausalLM:
         self.sam_chunk = 16  # views per encoder pass: 16 x 4096 rows keep the last partial wave of the N=1280 GEMMs small
         # SAM encoder (tensor-bound) next to the LLaMA decode chain (HBM-bound): see enable_overlap()
         self.overlap = None
+        self._view_cache = None  # exact-match cache of encoder outputs for repeated views: enable_view_cache()
         self.record_stages = False  # bench.py: CUDA events at stage boundaries (a dozen per call)
         self._marks = []
         self.stage_delay = None     # bench.py per-kernel timing pass: callable that parks the GPU so the host runs ahead
@@ -647,16 +648,73 @@ class InteractVLMForCausalLM:
         self.set_human_lift_maps(np.stack([p2v[v] for v in HUMAN_VIEWS]), np.stack([bary[v] for v in HUMAN_VIEWS]))
 
     # ---- stages -------------------------------------------------------------------------------------------------
+    def enable_view_cache(self, max_entries: int = 8):
+        """Exact-match cache of SAM-encoder outputs, off by default.  The hcontact harnesses feed the SAME four body renders
+        with every image (run_demo.py:279-281; `HumanContact` datasets alike) and the reference re-encodes them every time
+        (InteractVLM.py:578).  With the cache, every incoming view is compared bit for bit with the cached inputs
+        (`ivlm_rows_differ`) and with the other views of the call; only unseen views go through the encoder, and their
+        embeddings are the ones the encoder would produce anyway (its rows do not depend on the batch composition), so
+        results are bit-identical.  Costs one small device->host read per call; entries are never evicted."""
+        if not self._emulated:
+            self._view_cache = dict(max=int(max_entries), inputs=None, embs=None, hits=0, misses=0)
+        return self
+
+    def clear_view_cache(self):
+        if self._view_cache is not None:
+            self._view_cache.update(inputs=None, embs=None, hits=0, misses=0)
+
+    def _encode_views(self, flat):
+        outs = []
+        for i in range(0, flat.shape[0], self.sam_chunk):
+            if self.stage_delay is not None:
+                self.stage_delay()
+            outs.append(self.eng.sam_encode(flat[i:i + self.sam_chunk]))
+        return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+
     def get_visual_embs(self, images):
         """[B,V,3,1024,1024] -> [B*V, 4096, 256] token-major (InteractVLM.py:251-261)."""
         B, V = images.shape[:2]
-        flat = images.reshape(B * V, *images.shape[2:])
-        outs = []
-        for i in range(0, B * V, self.sam_chunk):
-            if self.stage_delay is not None:
-                self.stage_delay()
-            outs.append(self.eng.sam_encode(self._bf16(flat[i:i + self.sam_chunk])))
-        return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+        flat = self._bf16(images.reshape(B * V, *images.shape[2:])).contiguous()
+        vc = self._view_cache
+        if vc is None:
+            return self._encode_views(flat)
+        n = B * V
+        src = [-1] * n                                   # row of the embedding table that serves view i
+        K = 0 if vc["inputs"] is None else vc["inputs"].shape[0]
+        if K:
+            neq = self.ctx.rows_differ(flat, vc["inputs"]).cpu()
+            for i in range(n):
+                hit = (neq[i] == 0).nonzero()
+                if hit.numel():
+                    src[i] = int(hit[0])
+        miss = [i for i in range(n) if src[i] < 0]
+        vc["hits"] += n - len(miss)
+        vc["misses"] += len(miss)
+        table = vc["embs"]
+        if miss:
+            mt = flat if len(miss) == n else flat[torch.as_tensor(miss, device=self.device)]
+            rep = list(range(len(miss)))                 # views repeated inside this call are encoded once
+            if len(miss) > 1:
+                neq2 = self.ctx.rows_differ(mt, mt).cpu()
+                for j in range(len(miss)):
+                    rep[j] = int((neq2[j, :j + 1] == 0).nonzero()[0])
+            uniq = [j for j in range(len(miss)) if rep[j] == j]
+            ut = mt if len(uniq) == len(miss) else mt[torch.as_tensor(uniq, device=self.device)]
+            enc = self._encode_views(ut.contiguous())
+            pos = {j: K + u for u, j in enumerate(uniq)}
+            for j, i in enumerate(miss):
+                src[i] = pos[rep[j]]
+            table = enc if table is None else torch.cat([table, enc], 0)
+            room = vc["max"] - K
+            if room > 0:                                 # the table's first rows stay the cache, in insertion order
+                keep = min(room, len(uniq))
+                vc["inputs"] = ut[:keep].clone() if vc["inputs"] is None else torch.cat([vc["inputs"], ut[:keep]], 0)
+                vc["embs"] = table[:K + keep].clone() if keep < len(uniq) or K else table
+        S, C = table.shape[1], table.shape[2]
+        if src == list(range(n)) and table.shape[0] == n:
+            return table
+        out = self.ctx.gather_rows(table.view(table.shape[0], S * C), _i32(src, self.device))
+        return out.view(n, S, C)
 
     def _bf16(self, t):
         t = t.to(self.device)
@@ -780,7 +838,7 @@ class InteractVLMForCausalLM:
         if cfg.token_type != "Gen":
             raise NotImplementedError("token_type != 'Gen' (AttentionSplitter variants) is outside the hot path")
         emb = None
-        if self.overlap is not None and not self.record_stages and self.stage_delay is None:
+        if self.overlap is not None and self._view_cache is None and not self.record_stages and self.stage_delay is None:
             output_ids, hidden, emb = self._generate_and_encode(images_clip, images, input_ids, max_new_tokens, scripted)
         else:
             output_ids, hidden = self.generate(images_clip, input_ids, max_new_tokens, scripted)

@@ -310,6 +310,16 @@ class Context:
                                                 self.stream), "embed_gather")
         return out
 
+    def rows_differ(self, x, ref):
+        """x [n, ...], ref [K, ...] (same row shape and dtype, contiguous) -> int32 [n, K], 1 where the rows differ bitwise."""
+        assert x.is_cuda and ref.is_cuda and x.dtype == ref.dtype and x.shape[1:] == ref.shape[1:]
+        assert x.is_contiguous() and ref.is_contiguous()
+        n, K = x.shape[0], ref.shape[0]
+        row_bytes = x[0].numel() * x.element_size()
+        neq = torch.empty((n, K), device=x.device, dtype=torch.int32)
+        L.check(self.lib.ivlm_rows_differ(self.h, P(x), i32(n), P(ref), i32(K), i64(row_bytes), P(neq), self.stream), "rows_differ")
+        return neq
+
     def gather_rows(self, x, idx):
         _bf16(x)
         assert idx.dtype == torch.int32 and x.is_contiguous()

@@ -217,6 +217,45 @@ def test_programmatic_dependent_launch_is_bit_identical(tiny, ctx):
         model._graphs = {}
 
 
+def test_view_cache_is_bit_identical(tiny, ctx):
+    """Exact-match cache of encoder outputs (model.enable_view_cache): all-new views, all-repeated views and a mix give the
+    bits of the uncached path; repeated views are not re-encoded."""
+    cfg, sd, model, _ = tiny
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 3)
+    sam = sam.clone()
+    sam[1] = sam[0]                      # sample 1 sees the same four views as sample 0
+    sam[2, 0] = sam[0, 2]                # sample 2 repeats one of them in another slot
+    x = torch.arange(32, dtype=torch.float32).view(4, 8).bfloat16().cuda()
+    y = x.clone()
+    y[2, 5] += 1
+    assert ctx.rows_differ(x, y).cpu().tolist() == [[int(i != k or i == 2) for k in range(4)] for i in range(4)]
+    args = (clip, sam, ids, cam, [SIZE] * 3, [SIZE] * 3)
+    base = model.evaluate(*args, max_new_tokens=ans.shape[1], scripted=ans)
+    try:
+        model.enable_view_cache(max_entries=6)
+        for call in range(2):
+            n0 = model.ctx.launch_count()
+            out = model.evaluate(*args, max_new_tokens=ans.shape[1], scripted=ans)
+            launches = model.ctx.launch_count() - n0
+            assert torch.equal(out["pred_contact_3d"], base["pred_contact_3d"])
+            for a, b in zip(out["pred_masks"], base["pred_masks"]):
+                assert torch.equal(a, b)
+            if call == 0:
+                assert model._view_cache["misses"] == 12 and model._view_cache["inputs"].shape[0] == 6  # 7 distinct, room for 6
+            else:
+                assert model._view_cache["hits"] == 11   # 6 cached views serve 11 of the 12 slots; the 7th is re-encoded
+        model.enable_view_cache(max_entries=8)           # room for all 7: the second call does not run the encoder at all
+        counts = []
+        for call in range(2):
+            n0 = model.ctx.launch_count()
+            out = model.evaluate(*args, max_new_tokens=ans.shape[1], scripted=ans)
+            counts.append(model.ctx.launch_count() - n0)
+            assert torch.equal(out["pred_contact_3d"], base["pred_contact_3d"])
+        assert counts[1] < counts[0] - 20 and model._view_cache["hits"] == 12 and model._view_cache["inputs"].shape[0] == 7
+    finally:
+        model._view_cache = None
+
+
 def test_full_size_layers_vs_torch_fp32(ctx):
     """One SAM ViT-H block pair (window + global), one LLaMA-13B layer and the CLIP-L stack at their REAL widths:
     the oracle restatement evaluated with stock torch fp32 CUDA ops is the checker (CPU would take minutes)."""
