@@ -292,6 +292,12 @@ IVLM_API int ivlm_shade_phong(ivlm_handle h, const float* verts, const int32_t* 
 IVLM_API int ivlm_contact_loss(ivlm_handle h, const float* obj_verts, const float* obj_prob, const float* hum_verts,
                       const float* hum_prob, int32_t n_obj, int32_t n_hum, float* loss, float* grad_obj, void* stream);
 
+/* Nearest neighbour (K = 1) of each of the n rows of x [n,D] among the m rows of y [m,D], 1 <= D <= 8, squared Euclidean
+ * distance, ties to the lowest index: the knn_points(K=1) call of the contact ICP (optim/icp/icp.py:187-196, points ++ normals,
+ * D = 6).  idx [n] int32, dist2 [n] fp32 (optional). */
+IVLM_API int ivlm_knn1(ivlm_handle h, const float* x, const float* y, int32_t n, int32_t m, int32_t D, int32_t* idx, float* dist2,
+              void* stream);
+
 /* convert_contacts (utils/utils.py:428-443): SMPL->SMPL-X dense [R,C] matrix applied as CSR SpMV.
  * csr built once from the host dense matrix. */
 typedef struct ivlm_csr ivlm_csr;

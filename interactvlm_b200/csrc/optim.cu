@@ -83,9 +83,62 @@ contact_finalize_kernel(const float4* __restrict__ partial, const float* __restr
     }
 }
 
+// Nearest neighbour (K = 1) of every query row in a target set, D <= 8 coordinates per point (ICP over points ++ normals,
+// optim/icp/icp.py:187-196 -> pytorch3d knn_points).  One thread per query, targets staged through shared memory, squared
+// Euclidean distance summed coordinate by coordinate; ties keep the lowest target index.
+constexpr int KNN_THREADS = 128, KNN_CHUNK = 512, KNN_MAX_D = 8;
+
+template <int D>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn1_kernel(const float* __restrict__ x, const float* __restrict__ y, int n, int m, int* __restrict__ idx,
+            float* __restrict__ dist2) {
+    __shared__ float sh[KNN_CHUNK * D];
+    const int i = blockIdx.x * KNN_THREADS + threadIdx.x;
+    float q[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[d] = i < n ? x[(size_t)i * D + d] : 0.f;
+    float best = INFINITY;
+    int best_j = 0;
+    for (int base = 0; base < m; base += KNN_CHUNK) {
+        const int c = min(KNN_CHUNK, m - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < c * D; k += KNN_THREADS) sh[k] = y[(size_t)base * D + k];
+        __syncthreads();
+        for (int k = 0; k < c; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float t = q[d] - sh[k * D + d];
+                acc = __fadd_rn(acc, __fmul_rn(t, t));
+            }
+            if (acc < best) { best = acc; best_j = base + k; }
+        }
+    }
+    if (i < n) {
+        idx[i] = best_j;
+        if (dist2) dist2[i] = best;
+    }
+}
+
 }  // namespace ivlm
 
 using namespace ivlm;
+
+extern "C" int ivlm_knn1(ivlm_handle h, const float* x, const float* y, int32_t n, int32_t m, int32_t D, int32_t* idx,
+                         float* dist2, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    IVLM_REQUIRE(h && x && y && idx, "knn1: null argument");
+    IVLM_REQUIRE(n > 0 && m > 0 && D >= 1 && D <= KNN_MAX_D, "knn1: need n, m > 0 and 1 <= D <= %d (got %d, %d, %d)", KNN_MAX_D, n, m, D);
+    const dim3 grid((n + KNN_THREADS - 1) / KNN_THREADS);
+#define IVLM_KNN(D_) case D_: knn1_kernel<D_><<<grid, KNN_THREADS, 0, stream>>>(x, y, n, m, idx, dist2); break;
+    switch (D) {
+        IVLM_KNN(1) IVLM_KNN(2) IVLM_KNN(3) IVLM_KNN(4) IVLM_KNN(5) IVLM_KNN(6) IVLM_KNN(7) IVLM_KNN(8)
+    }
+#undef IVLM_KNN
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return IVLM_OK;
+}
 
 extern "C" int ivlm_contact_loss(ivlm_handle h, const float* obj_verts, const float* obj_prob, const float* hum_verts,
                                  const float* hum_prob, int32_t n_obj, int32_t n_hum, float* loss, float* grad_obj,

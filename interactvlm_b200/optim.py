@@ -55,3 +55,114 @@ def contact_loss(obj_verts, human_verts, object_contact_probs, human_contact_pro
     differentiable w.r.t. `obj_verts`."""
     ctx = ctx or _ctx(obj_verts.device)
     return _ContactLoss.apply(obj_verts, human_verts, object_contact_probs, human_contact_probs, ctx)
+
+
+# ------------------------------------------------------------------------------------------------ contact ICP
+from typing import NamedTuple, List, Optional  # noqa: E402
+
+
+class SimilarityTransform(NamedTuple):   # optim/icp/icp.py:24-27
+    R: torch.Tensor
+    T: torch.Tensor
+    s: torch.Tensor
+
+
+class ICPSolution(NamedTuple):           # optim/icp/icp.py:30-35
+    converged: bool
+    rmse: Optional[torch.Tensor]
+    Xt: torch.Tensor
+    RTs: SimilarityTransform
+    t_history: List[SimilarityTransform]
+
+
+def knn1(x, y, ctx: Context | None = None):
+    """Index (int64 [n]) and squared distance (fp32 [n]) of the nearest row of y [m,D] for every row of x [n,D], D <= 8:
+    pytorch3d `knn_points(..., K=1)` as the contact ICP uses it (optim/icp/icp.py:187-196)."""
+    ctx = ctx or _ctx(x.device)
+    x, y = _f32(x, "x"), _f32(y, "y")
+    if x.dim() != 2 or y.dim() != 2 or x.shape[1] != y.shape[1]:
+        raise ValueError(f"knn1: expected [n,D] and [m,D], got {tuple(x.shape)} and {tuple(y.shape)}")
+    idx = torch.empty((x.shape[0],), device=x.device, dtype=torch.int32)
+    d2 = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32)
+    L.check(ctx.lib.ivlm_knn1(ctx.h, P(x), P(y), C.c_int32(x.shape[0]), C.c_int32(y.shape[0]), C.c_int32(x.shape[1]), P(idx),
+                              P(d2), ctx.stream), "knn1")
+    return idx.long(), d2
+
+
+def corresponding_points_alignment(X, Y, weights=None, estimate_scale=False, allow_reflection=False, eps=1e-9):
+    """optim/icp/icp.py:274-417 (Umeyama) for batched [b,n,d] tensors: s X R + T ~ Y.  A handful of O(n) reductions and a
+    d x d SVD -- host-side glue around the nearest-neighbour kernel, written with torch ops."""
+    b, n, dim = X.shape
+    w = X.new_ones(b, n) if weights is None else weights.to(X.dtype)
+    wsum = w.sum(1).clamp(eps)
+    Xmu = (X * w[..., None]).sum(1, keepdim=True) / wsum[:, None, None]
+    Ymu = (Y * w[..., None]).sum(1, keepdim=True) / wsum[:, None, None]
+    Xc, Yc = (X - Xmu) * w[..., None], (Y - Ymu) * w[..., None]
+    cov = torch.bmm(Xc.transpose(2, 1), Yc) / wsum[:, None, None]
+    U, S, Vh = torch.linalg.svd(cov)
+    E = torch.eye(dim, dtype=X.dtype, device=X.device)[None].repeat(b, 1, 1)
+    if not allow_reflection:
+        E[:, -1, -1] = torch.det(torch.bmm(U, Vh))
+    R = torch.bmm(torch.bmm(U, E), Vh)
+    if estimate_scale:
+        s = (torch.diagonal(E, dim1=1, dim2=2) * S).sum(1) / ((Xc * Xc).sum((1, 2)) / wsum).clamp(eps)
+        T = Ymu[:, 0, :] - s[:, None] * torch.bmm(Xmu, R)[:, 0, :]
+    else:
+        T = Ymu[:, 0, :] - torch.bmm(Xmu, R)[:, 0, :]
+        s = T.new_ones(b)
+    return SimilarityTransform(R, T, s)
+
+
+def _apply_similarity_transform(X, R, T, s):
+    return s[:, None, None] * torch.bmm(X, R) + T[:, None, :]
+
+
+def ICP(obj_contact_pcd, hum_contact_pcd, init_transform: Optional[SimilarityTransform] = None, max_iterations: int = 100,
+        relative_rmse_thr: float = 1e-6, estimate_scale: bool = False, allow_reflection: bool = False, verbose: bool = False,
+        obj_contact_normals=None, hum_contact_normals=None, min_scale: float = None, scale_penalty: float = 10.0,
+        ctx: Context | None = None) -> ICPSolution:
+    """Drop-in for optim/icp/icp.py:38-268 with [b,n,3] CUDA tensors (the reference's `Pointclouds` inputs hold one cloud
+    each: pass `pcd.points_padded()`).  Same loop, same outputs; the per-iteration `knn_points` over points ++ normals is the
+    `ivlm_knn1` kernel.  Like the reference, the query cloud is assembled once before the loop (icp.py:176-185)."""
+    Xt0, Y = obj_contact_pcd.float(), hum_contact_pcd.float()
+    if Xt0.dim() != 3 or Y.dim() != 3 or Xt0.shape[0] != Y.shape[0] or Xt0.shape[2] != Y.shape[2]:
+        raise ValueError("Point sets X and Y have to have the same number of batches and data dimensions.")
+    b, n, dim = Xt0.shape
+    mask = Xt0.new_ones(b, n)
+    obj_init = Xt0.clone()
+    if init_transform is not None:
+        R, T, s = init_transform
+        if R.shape != (b, dim, dim) or T.shape != (b, dim) or s.shape != (b,):
+            raise ValueError("The initial transformation init_transform has to be a named tuple SimilarityTransform with "
+                             "elements (R, T, s) of shapes (minibatch, dim, dim), (minibatch, dim) and (minibatch,).")
+        R, T, s = R.float(), T.float(), s.float()
+        Xt = _apply_similarity_transform(Xt0, R, T, s)
+    else:
+        R = torch.eye(dim, device=Xt0.device)[None].repeat(b, 1, 1)
+        T, s, Xt = Xt0.new_zeros((b, dim)), Xt0.new_ones(b), Xt0
+    q = torch.cat([Xt, obj_contact_normals.float()], -1) if obj_contact_normals is not None else Xt
+    t = torch.cat([Y, -hum_contact_normals.float()], -1) if hum_contact_normals is not None else Y
+    q, t = q.contiguous(), t.contiguous()
+    prev, rmse, converged, history = None, None, False, []
+    for iteration in range(max_iterations):
+        nn = torch.stack([t[k][knn1(q[k], t[k], ctx)[0]] for k in range(b)])
+        nn_pts, nn_normals = nn[..., :3], -nn[..., 3:]
+        R, T, s = corresponding_points_alignment(obj_init, nn_pts, mask, estimate_scale, allow_reflection)
+        Xt = _apply_similarity_transform(obj_init, R, T, s)
+        history.append(SimilarityTransform(R, T, s))
+        sq = ((Xt - nn_pts) ** 2).sum(2)
+        rmse = ((sq * mask).sum(1) / mask.sum(1).clamp(1e-9)).sqrt()
+        combined = rmse
+        if nn_normals.shape[-1]:
+            nt = _apply_similarity_transform(nn_normals, R, torch.zeros_like(T), s)
+            combined = rmse + (1 - (nt * nn_normals).sum(2))          # [b,n] + [b] broadcast exactly as icp.py:219-224 does
+        if min_scale is not None:
+            combined = combined + scale_penalty * torch.clamp_min(s - min_scale, 0)
+        rel = torch.ones_like(combined) if prev is None else (combined - prev) / prev
+        if verbose:
+            print(f"ICP iteration {iteration}: mean/max rmse = {rmse.mean():1.2e}/{rmse.max():1.2e}; mean relative rmse = {rel.mean():1.2e}")
+        if bool((rel <= relative_rmse_thr).all()):
+            converged = True
+            break
+        prev = combined
+    return ICPSolution(converged, rmse, Xt, SimilarityTransform(R, T, s), history)

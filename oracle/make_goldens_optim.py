@@ -35,7 +35,88 @@ def inputs(seed, n_obj, n_hum):
 CASES = {"small": (0, 257, 300), "smplx": (1, 3000, 10475), "coincident": (2, 64, 64)}
 
 
+def reference_icp():
+    """Imports the reference's optim/icp/icp.py UNMODIFIED.  Its only pytorch3d dependencies are `knn_points` (stubbed by a
+    brute-force K = 1 search with pytorch3d's return convention) and `pytorch3d.structures.utils` (only touched for list
+    weights, unused here); optim/icp/utils.py vendors the rest."""
+    import collections
+    import sys
+    import types
+
+    KNN = collections.namedtuple("KNN", "dists idx knn")
+
+    def knn_points(p1, p2, lengths1=None, lengths2=None, K=1, return_nn=False, **kw):
+        assert K == 1
+        d = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)
+        dist, idx = d.min(-1)
+        nn = torch.gather(p2, 1, idx[..., None].expand(-1, -1, p2.shape[-1]))
+        return KNN(dist[..., None], idx[..., None], nn[:, :, None, :] if return_nn else None)
+
+    mods = {n: types.ModuleType(n) for n in ("pytorch3d", "pytorch3d.ops", "pytorch3d.ops.knn", "pytorch3d.structures",
+                                             "pytorch3d.structures.utils")}
+    mods["pytorch3d.ops"].knn_points = knn_points
+    mods["pytorch3d.ops.knn"].knn_points = knn_points
+    mods["pytorch3d.structures"].utils = mods["pytorch3d.structures.utils"]
+    saved = {n: sys.modules.get(n) for n in list(mods) + ["optim", "optim.icp", "optim.icp.icp", "optim.icp.utils"]}
+    sys.modules.update(mods)
+    sys.path.insert(0, "/root/reference")
+    try:
+        for n in ("optim", "optim.icp", "optim.icp.icp", "optim.icp.utils"):
+            sys.modules.pop(n, None)
+        import importlib
+
+        icp = importlib.import_module("optim.icp.icp")
+    finally:
+        sys.path.remove("/root/reference")
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
+    return icp
+
+
+def icp_inputs(seed, n_obj, n_hum):
+    """Two contact patches that roughly face each other, with unit normals, and an initial similarity transform."""
+    g = np.random.default_rng(seed)
+    hum = np.stack([g.uniform(-0.3, 0.3, n_hum), g.uniform(-0.3, 0.3, n_hum), np.zeros(n_hum)], -1)
+    hum[:, 2] = 0.15 * np.sin(4 * hum[:, 0]) * np.cos(3 * hum[:, 1])
+    hn = np.stack([-0.6 * np.cos(4 * hum[:, 0]) * np.cos(3 * hum[:, 1]), 0.45 * np.sin(4 * hum[:, 0]) * np.sin(3 * hum[:, 1]), np.ones(n_hum)], -1)
+    hn /= np.linalg.norm(hn, axis=1, keepdims=True)
+    sel = g.choice(n_hum, n_obj, replace=n_obj > n_hum)
+    ang = 0.35
+    Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    obj = (hum[sel] + g.normal(size=(n_obj, 3)) * 0.01) @ Rz.T * 1.15 + np.array([0.05, -0.08, 0.12])
+    on = (-hn[sel]) @ Rz.T + g.normal(size=(n_obj, 3)) * 0.05
+    on /= np.linalg.norm(on, axis=1, keepdims=True)
+    R0 = np.eye(3)[None]
+    T0 = np.array([[0.01, 0.02, -0.03]])
+    s0 = np.array([1.0])
+    f = lambda a: a.astype(np.float32)
+    return f(obj)[None], f(on)[None], f(hum)[None], f(hn)[None], f(R0), f(T0), f(s0)
+
+
+ICP_CASES = {"patch": (3, 400, 700, False), "patch_scale": (4, 900, 600, True)}
+
+
 def main():
+    icp = reference_icp()
+    out_icp = {}
+    for name, (seed, n_obj, n_hum, est_scale) in ICP_CASES.items():
+        obj, on, hum, hn, R0, T0, s0 = icp_inputs(seed, n_obj, n_hum)
+        for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            t = lambda a: torch.from_numpy(a).to(dt)
+            sol = icp.ICP(t(obj), t(hum), init_transform=icp.SimilarityTransform(t(R0), t(T0), t(s0)), max_iterations=30,
+                          estimate_scale=est_scale, obj_contact_normals=t(on), hum_contact_normals=t(hn))
+            out_icp[f"{name}_{tag}_R"] = sol.RTs.R.numpy()
+            out_icp[f"{name}_{tag}_T"] = sol.RTs.T.numpy()
+            out_icp[f"{name}_{tag}_s"] = sol.RTs.s.numpy()
+            out_icp[f"{name}_{tag}_Xt"] = sol.Xt.numpy()
+            out_icp[f"{name}_{tag}_rmse"] = sol.rmse.numpy()
+            out_icp[f"{name}_{tag}_iters"] = np.array(len(sol.t_history))
+            out_icp[f"{name}_{tag}_converged"] = np.array(bool(sol.converged))
+    np.savez_compressed(OUT.with_name("icp.npz"), **out_icp)
+    print({k: (v.shape, float(np.abs(v).max())) for k, v in out_icp.items() if k.endswith(("_s", "_rmse", "_iters", "_T"))})
     fn = reference_contact_loss()
     out = {}
     for name, (seed, n_obj, n_hum) in CASES.items():

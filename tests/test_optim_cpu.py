@@ -31,6 +31,22 @@ def test_oracle_matches_reference_goldens(name):
     assert np.isfinite(grad).all()
 
 
+def test_icp_oracle_matches_reference_goldens():
+    """oracle/optim.py icp() against outputs of the reference's own ICP (optim/icp/icp.py imported unmodified with a
+    brute-force stand-in for pytorch3d's knn_points; oracle/make_goldens_optim.py)."""
+    from oracle.make_goldens_optim import ICP_CASES, icp_inputs
+
+    G = np.load(Path(__file__).parent / "golden" / "icp.npz")
+    for name, (seed, n_obj, n_hum, est) in ICP_CASES.items():
+        obj, on, hum, hn, R0, T0, s0 = icp_inputs(seed, n_obj, n_hum)
+        r = OO.icp(obj[0], hum[0], (R0[0], T0[0], s0[0]), 30, estimate_scale=est, obj_normals=on[0], hum_normals=hn[0])
+        assert r["iters"] == int(G[f"{name}_f64_iters"]) and r["converged"] == bool(G[f"{name}_f64_converged"])
+        for k in ("R", "T", "Xt"):
+            assert np.abs(r[k] - G[f"{name}_f64_{k}"][0]).max() < 1e-12
+        assert abs(r["s"] - G[f"{name}_f64_s"][0]) < 1e-12 and abs(r["rmse"] - G[f"{name}_f64_rmse"][0]) < 1e-12
+        assert abs(np.linalg.det(r["R"]) - 1) < 1e-9
+
+
 def test_product_wrapper_refuses_cpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")

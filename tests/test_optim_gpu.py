@@ -76,3 +76,36 @@ def test_full_size_properties(ctx):
     got = PO.contact_loss(os_, h, p[sub], q, ctx=ctx)
     got.backward()
     assert abs(got.item() - want) < 2e-6 and np.abs(os_.grad.cpu().numpy() - gw).max() < 2e-6 * np.abs(gw).max() + 1e-10
+
+
+def test_knn1_exact_vs_brute_force(ctx):
+    g = torch.Generator().manual_seed(5)
+    for n, m, D in ((1000, 777, 6), (513, 4000, 3), (7, 1, 8), (300, 300, 1)):
+        x, y = torch.randn(n, D, generator=g).cuda(), torch.randn(m, D, generator=g).cuda()
+        y[m // 2] = y[0]                                     # an exact duplicate: ties go to the lower index
+        idx, d2 = PO.knn1(x, y, ctx)
+        full = ((x.double()[:, None, :] - y.double()[None, :, :]) ** 2).sum(-1)
+        want_d, want_i = full.min(1)
+        assert (d2.double() - want_d).abs().max().item() < 1e-5
+        picked = full.gather(1, idx[:, None])[:, 0]
+        assert (picked - want_d).abs().max().item() < 1e-5   # the chosen neighbour is a nearest one (fp32 near-ties aside)
+        assert (idx != m // 2).all() or m == 1
+
+
+def test_icp_vs_reference_goldens(ctx):
+    from oracle.make_goldens_optim import ICP_CASES, icp_inputs
+
+    G = np.load(Path(__file__).parent / "golden" / "icp.npz")
+    for name, (seed, n_obj, n_hum, est) in ICP_CASES.items():
+        obj, on, hum, hn, R0, T0, s0 = icp_inputs(seed, n_obj, n_hum)
+        t = lambda a: torch.from_numpy(a).cuda()
+        sol = PO.ICP(t(obj), t(hum), init_transform=PO.SimilarityTransform(t(R0), t(T0), t(s0)), max_iterations=30,
+                     estimate_scale=est, obj_contact_normals=t(on), hum_contact_normals=t(hn), ctx=ctx)
+        assert sol.converged == bool(G[f"{name}_f64_converged"]) and len(sol.t_history) == int(G[f"{name}_f64_iters"])
+        assert np.abs(sol.RTs.R.cpu().numpy() - G[f"{name}_f64_R"]).max() < 2e-5
+        assert np.abs(sol.RTs.T.cpu().numpy() - G[f"{name}_f64_T"]).max() < 2e-5
+        assert np.abs(sol.RTs.s.cpu().numpy() - G[f"{name}_f64_s"]).max() < 2e-5
+        assert np.abs(sol.Xt.cpu().numpy() - G[f"{name}_f64_Xt"]).max() < 2e-5
+        assert np.abs(sol.rmse.cpu().numpy() - G[f"{name}_f64_rmse"]).max() < 2e-5
+        # the reference's own fp32 run is this far from its fp64 run:
+        assert np.abs(G[f"{name}_f32_Xt"] - G[f"{name}_f64_Xt"]).max() < 2e-5
