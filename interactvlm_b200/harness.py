@@ -137,3 +137,71 @@ def validate(model, samples, batch_size=8, dist=None, max_new_tokens=32, contact
         f1, p, r = h_contact_metrics(gt, allp)
         metrics = {"f1": f1, "precision": p, "recall": r, "n": n}
     return allp, metrics
+
+
+# ------------------------------------------------------------------------------------------------ prompt / camera helpers
+# Host-side input preparation of both harnesses: plain Python, no device work.
+IMAGE_TOKEN_INDEX = -200                       # utils/utils.py:18-23
+DEFAULT_IMAGE_TOKEN = "<image>"
+DEFAULT_IM_START_TOKEN = "<im_start>"
+DEFAULT_IM_END_TOKEN = "<im_end>"
+HCONTACT_PROMPT = "Which body parts are in contact with the {object}? Segment these contact areas."   # run_demo.py:282
+
+# preprocess_data/constants.py:315-382: (distance, elevation, azimuth, x_translation, y_translation) per body render
+HUMAN_VIEW_CAM_PARAMS = {
+    view_type: {"topfront": [2., 45., 315., 0., 0.], "bottomfront": [2., 315., 315., 0., 0.3],
+                "topback": [2., 45., 135., 0., 0.], "bottomback": [2., 315., 135., 0., 0.3]}
+    for view_type in ("4MV-Z_Vitru", "4MV-Z_Vitru_mv2", "4MV-Z_Vitru_FootGround")}
+
+_SYSTEM = {
+    "llava_v1": "A chat between a curious human and an artificial intelligence assistant. "
+                "The assistant gives helpful, detailed, and polite answers to the human's questions.",
+    "llava_llama_2": "You are a helpful language and vision assistant. You are able to understand the visual content that "
+                     "the user provides, and assist the user with a variety of tasks using natural language.",
+}
+
+
+def normalize_cam_params(cam_params):
+    """datasets/base_contact_dataset.py:37-50 -> float32 tensor [5]; None -> zeros."""
+    if cam_params is None:
+        return torch.tensor([0.0, 0.0, 0.0, 0.0, 0.0])
+    distance, elevation, azimuth, x_translation, y_translation = cam_params
+    return torch.tensor([distance / 10.0, elevation / 360.0, azimuth / 360.0, (x_translation + 1.0) / 2.0,
+                         (y_translation + 1.0) / 2.0])
+
+
+def human_cam_params(view_type="4MV-Z_Vitru"):
+    """run_demo.py:275-278: the [1,V,5] camera conditioning of the hcontact path."""
+    views = HUMAN_VIEW_CAM_PARAMS[view_type]
+    return torch.stack([normalize_cam_params(views[v]) for v in views]).unsqueeze(0)
+
+
+def build_prompt(question, conv_type="llava_v1", use_mm_start_end=True):
+    """run_demo.py:313-323: `<image>\\n` + question, image token wrapped in <im_start>/<im_end>, one user turn and an empty
+    assistant turn in the `llava_v1` (SeparatorStyle.TWO) or `llava_llama_2` template (model/llava/conversation.py)."""
+    prompt = DEFAULT_IMAGE_TOKEN + "\n" + question
+    if use_mm_start_end:
+        prompt = prompt.replace(DEFAULT_IMAGE_TOKEN, DEFAULT_IM_START_TOKEN + DEFAULT_IMAGE_TOKEN + DEFAULT_IM_END_TOKEN)
+    if conv_type == "llava_v1":
+        return _SYSTEM[conv_type] + " " + "USER: " + prompt + " " + "ASSISTANT:"
+    if conv_type == "llava_llama_2":
+        return "[INST] " + f"<<SYS>>\n{_SYSTEM[conv_type]}\n<</SYS>>\n\n" + prompt + " [/INST]"
+    raise ValueError(f"unknown conv_type {conv_type!r} (run_demo.py accepts llava_v1 and llava_llama_2)")
+
+
+def tokenizer_image_token(prompt, tokenizer, image_token_index=IMAGE_TOKEN_INDEX, return_tensors=None):
+    """model/llava/mm_utils.py:19-44: tokenise the text around every `<image>` and put `image_token_index` in between; a
+    leading BOS is kept once."""
+    chunks = [tokenizer(chunk).input_ids for chunk in prompt.split(DEFAULT_IMAGE_TOKEN)]
+    has_bos = len(chunks) > 0 and len(chunks[0]) > 0 and chunks[0][0] == tokenizer.bos_token_id
+    input_ids = [chunks[0][0]] if has_bos else []
+    skip = 1 if has_bos else 0
+    for k, chunk in enumerate(chunks):
+        if k > 0:
+            input_ids.append(image_token_index)   # the reference inserts [idx] * (offset + 1) and drops `offset` of them
+        input_ids.extend(chunk[skip:])
+    if return_tensors is not None:
+        if return_tensors == "pt":
+            return torch.tensor(input_ids, dtype=torch.long)
+        raise ValueError(f"Unsupported tensor type: {return_tensors}")
+    return input_ids

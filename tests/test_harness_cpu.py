@@ -78,3 +78,29 @@ def test_validate_batches_and_scores(model):
     assert metrics["n"] == 2 and metrics["f1"] > 0.999
     preds1, _ = Hn.validate(model, samples, batch_size=1, max_new_tokens=ans.shape[1])
     assert (preds1 - preds).abs().max().item() < 2e-2
+
+
+def test_prompt_and_camera_helpers_match_reference_goldens():
+    """build_prompt / tokenizer_image_token / normalize_cam_params against outputs of the reference's own functions
+    (tests/golden/prompt.json, written by oracle/make_goldens_prompt.py)."""
+    import json
+    from pathlib import Path
+
+    import torch
+
+    from interactvlm_b200 import harness as Hn
+    from oracle.make_goldens_prompt import CAMS, NoBosTokenizer, WordTokenizer
+
+    gold = json.loads((Path(__file__).parent / "golden" / "prompt.json").read_text())
+    assert len(gold["prompts"]) == 8
+    for g in gold["prompts"]:
+        text = Hn.build_prompt(g["question"], g["conv_type"], g["use_mm_start_end"])
+        assert text == g["prompt"]
+        assert Hn.tokenizer_image_token(text, WordTokenizer()) == g["ids_bos"]
+        ids = Hn.tokenizer_image_token(text, NoBosTokenizer(), return_tensors="pt")
+        assert ids.dtype == torch.long and ids.tolist() == g["ids_nobos"]
+    for cam, want in zip(CAMS, gold["cams"]):
+        assert Hn.normalize_cam_params(cam).tolist() == want
+    from interactvlm_b200 import synthetic as S
+
+    assert torch.allclose(Hn.human_cam_params("4MV-Z_Vitru")[0], torch.from_numpy(S.HCONTACT_CAM_PARAMS).float(), atol=1e-7)
