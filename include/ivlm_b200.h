@@ -264,12 +264,14 @@ typedef struct ivlm_raster_cam {
     float R[9];   /* row-major world->view rotation, row-vector convention: X_view = X_world R + T (look_at_view_transform) */
     float T[3];
     float C[3];   /* camera centre in world space (specular term of the shader) */
-    float s;      /* 1 / tan(fov / 2): x_ndc = s * x_view / z_view (aspect 1) */
-    float z_clip; /* znear / 2 */
+    float fx, fy; /* NDC focal lengths: x_ndc = fx * x_view / z_view + cx (FoV cameras: fx = fy = 1 / tan(fov / 2)) */
+    float cx, cy; /* NDC principal point (0 for FoV cameras) */
+    float z_clip; /* znear / 2; <= 0 disables clipping (PerspectiveCameras have no znear) */
 } ivlm_raster_cam;
 /* verts [Nv,3] fp32, faces [Nf,3] int32 (device) -> pix_to_face [V,H,W] int32 (-1 background), bary [V,H,W,3] fp32 (-1
  * background), optional zbuf [V,H,W] fp32 (-1 background) and pixel_to_vertices_map p2v [V,H,W,3] int64 (-1 background;
- * render_mesh_utils.py:140-163).  NDC +X left / +Y up, pixel centres, nearest depth wins, ties to the lower face index.
+ * render_mesh_utils.py:140-163).  NDC +X left / +Y up (the longer image side spans [-L/S, L/S], the shorter [-1, 1]), pixel
+ * centres, nearest depth wins, ties to the lower face index.
  * Faces entirely behind z_clip are culled, faces crossing it are kept where the interpolated depth is >= z_clip; faces
  * with a vertex at z <= 0 that are not culled are skipped and counted in *n_skipped_h (host, optional). */
 IVLM_API int ivlm_rasterize_mesh(ivlm_handle h, const float* verts, const int32_t* faces, int32_t n_verts, int32_t n_faces,
@@ -291,6 +293,22 @@ IVLM_API int ivlm_shade_phong(ivlm_handle h, const float* verts, const int32_t* 
  * (16 bytes x n_obj x splits). */
 IVLM_API int ivlm_contact_loss(ivlm_handle h, const float* obj_verts, const float* obj_prob, const float* hum_verts,
                       const float* hum_prob, int32_t n_obj, int32_t n_hum, float* loss, float* grad_obj, void* stream);
+
+/* Differentiable soft silhouette of the pose refinement: SSRenderer.render (optim/renderer.py:64-104) = pytorch3d
+ * MeshRasterizer(blur_radius, faces_per_pixel = K, perspective-correct, clipped barycentrics) + SoftSilhouetteShader(sigma), one
+ * camera.  Forward: alpha [H,W] = 1 - prod_k (1 - sigmoid(-d_k / sigma)) over the K fragments nearest in depth among the faces
+ * within sqrt(blur_radius) of the pixel centre (signed squared NDC distance d_k, negative inside), zbuf0 [H,W] = depth of the
+ * nearest fragment (-1 if none); the fragment lists n_frag [H,W], frag_face / frag_sd / frag_z [K,H,W] are kept for the
+ * backward pass.  Backward: grad_verts [n_verts,3] = d(sum(grad_alpha * alpha)) / d verts, through the distance to the closest
+ * edge and the projection (float atomics on the per-vertex NDC gradient).  One-time scratch from the stream-ordered allocator;
+ * the forward synchronises `stream` once. */
+IVLM_API int ivlm_soft_silhouette(ivlm_handle h, const float* verts, const int32_t* faces, int32_t n_verts, int32_t n_faces,
+                         const ivlm_raster_cam* cam_h, int32_t H, int32_t W, float sigma, float blur_radius, int32_t K, float* alpha,
+                         float* zbuf0, int32_t* n_frag, int32_t* frag_face, float* frag_sd, float* frag_z, void* stream);
+IVLM_API int ivlm_soft_silhouette_backward(ivlm_handle h, const float* verts, const int32_t* faces, int32_t n_verts, int32_t n_faces,
+                                  const ivlm_raster_cam* cam_h, int32_t H, int32_t W, float sigma, const float* grad_alpha,
+                                  const int32_t* n_frag, const int32_t* frag_face, const float* frag_sd, float* grad_verts,
+                                  void* stream);
 
 /* Nearest neighbour (K = 1) of each of the n rows of x [n,D] among the m rows of y [m,D], 1 <= D <= 8, squared Euclidean
  * distance, ties to the lowest index: the knn_points(K=1) call of the contact ICP (optim/icp/icp.py:187-196, points ++ normals,

@@ -48,7 +48,8 @@ class AttnArgs(C.Structure):
 
 class RasterCam(C.Structure):
     """ivlm_raster_cam (include/ivlm_b200.h)."""
-    _fields_ = [("R", C.c_float * 9), ("T", C.c_float * 3), ("C", C.c_float * 3), ("s", C.c_float), ("z_clip", C.c_float)]
+    _fields_ = [("R", C.c_float * 9), ("T", C.c_float * 3), ("C", C.c_float * 3), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("z_clip", C.c_float)]
 
 
 RASTER_MAX_VIEWS = 8

@@ -32,10 +32,14 @@ __device__ __forceinline__ float dvd(float a, float b) { return __fdiv_rn(a, b);
 __device__ __forceinline__ float edge(float px, float py, float ax, float ay, float bx, float by) {
     return sub(mul(sub(px, ax), sub(by, ay)), mul(sub(py, ay), sub(bx, ax)));
 }
-// PixToNonSquareNdc on the flipped pixel index (square aspect): -1 + (2 i' + 1) / S, i' = S - 1 - i
-__device__ __forceinline__ float pix_to_ndc(int i, int S) {
-    return add(-1.f, dvd(add(mul(2.f, (float)(S - 1 - i)), 1.f), (float)S));
+// PixToNonSquareNdc on the flipped pixel index: -offset + (range i' + offset) / S1 with i' = S1 - 1 - i, range = 2 (S1/S2 when
+// S1 is the longer side), offset = range / 2
+__device__ __forceinline__ float pix_to_ndc(int i, int S1, int S2) {
+    const float range = S1 > S2 ? mul(dvd((float)S1, (float)S2), 2.f) : 2.f;
+    const float offset = dvd(range, 2.f);
+    return add(-offset, dvd(add(mul(range, (float)(S1 - 1 - i)), offset), (float)S1));
 }
+__host__ __device__ __forceinline__ float ndc_half_range(int S1, int S2) { return S1 > S2 ? (float)S1 / (float)S2 : 1.f; }
 
 __global__ void raster_project_kernel(const float* __restrict__ verts, int n_verts, DevCams cams, int V,
                                       float4* __restrict__ out) {
@@ -48,7 +52,7 @@ __global__ void raster_project_kernel(const float* __restrict__ verts, int n_ver
 #pragma unroll
     for (int k = 0; k < 3; ++k)
         w[k] = add(add(add(mul(x, c.R[k]), mul(y, c.R[3 + k])), mul(z, c.R[6 + k])), c.T[k]);
-    out[(size_t)v * n_verts + i] = make_float4(dvd(mul(w[0], c.s), w[2]), dvd(mul(w[1], c.s), w[2]), w[2], 0.f);
+    out[(size_t)v * n_verts + i] = make_float4(add(dvd(mul(w[0], c.fx), w[2]), c.cx), add(dvd(mul(w[1], c.fy), w[2]), c.cy), w[2], 0.f);
 }
 
 struct FaceBox {
@@ -56,23 +60,25 @@ struct FaceBox {
 };
 
 // status: 0 = rasterise, 1 = culled, 2 = skipped (straddles the camera plane)
+// `pad` widens the box in NDC (sqrt(blur_radius) for the soft rasteriser, 0 otherwise)
 __device__ __forceinline__ int face_box(const float4 a, const float4 b, const float4 c, float z_clip, int H, int W,
-                                        FaceBox& box) {
+                                        FaceBox& box, float pad = 0.f) {
     box = {1, 0, 1, 0};
     const float zmin = fminf(a.z, fminf(b.z, c.z)), zmax = fmaxf(a.z, fmaxf(b.z, c.z));
-    if (!(zmax >= z_clip)) return 1;  // entirely behind the clip plane (or NaN)
+    if (!(zmax >= fmaxf(z_clip, 0.f))) return 1;  // entirely behind the clip plane / the camera (or NaN)
     if (!(zmin > 0.f)) return 2;
     const float area = edge(c.x, c.y, a.x, a.y, b.x, b.y);
     if (area <= R_EPS && area >= -R_EPS) return 1;
-    const float xmin = fminf(a.x, fminf(b.x, c.x)), xmax = fmaxf(a.x, fmaxf(b.x, c.x));
-    const float ymin = fminf(a.y, fminf(b.y, c.y)), ymax = fmaxf(a.y, fmaxf(b.y, c.y));
-    if (!(xmax >= -1.f && xmin <= 1.f && ymax >= -1.f && ymin <= 1.f)) return 1;
+    const float xmin = fminf(a.x, fminf(b.x, c.x)) - pad, xmax = fmaxf(a.x, fmaxf(b.x, c.x)) + pad;
+    const float ymin = fminf(a.y, fminf(b.y, c.y)) - pad, ymax = fmaxf(a.y, fmaxf(b.y, c.y)) + pad;
+    const float rx = ndc_half_range(W, H), ry = ndc_half_range(H, W);
+    if (!(xmax >= -rx && xmin <= rx && ymax >= -ry && ymin <= ry)) return 1;
     // conservative pixel range (x decreases with the column, y with the row); the per-pixel test is exact
-    const float fw = 0.5f * W, fh = 0.5f * H;
-    const int j0 = (int)fmaxf(floorf((1.f - fminf(xmax, 1.f)) * fw - 0.5f) - 1.f, 0.f);
-    const int j1 = (int)fminf(ceilf((1.f - fmaxf(xmin, -1.f)) * fw - 0.5f) + 1.f, (float)(W - 1));
-    const int i0 = (int)fmaxf(floorf((1.f - fminf(ymax, 1.f)) * fh - 0.5f) - 1.f, 0.f);
-    const int i1 = (int)fminf(ceilf((1.f - fmaxf(ymin, -1.f)) * fh - 0.5f) + 1.f, (float)(H - 1));
+    const float fw = 0.5f * W / rx, fh = 0.5f * H / ry;
+    const int j0 = (int)fmaxf(floorf((rx - fminf(xmax, rx)) * fw - 0.5f) - 1.f, 0.f);
+    const int j1 = (int)fminf(ceilf((rx - fmaxf(xmin, -rx)) * fw - 0.5f) + 1.f, (float)(W - 1));
+    const int i0 = (int)fmaxf(floorf((ry - fminf(ymax, ry)) * fh - 0.5f) - 1.f, 0.f);
+    const int i1 = (int)fminf(ceilf((ry - fmaxf(ymin, -ry)) * fh - 0.5f) + 1.f, (float)(H - 1));
     if (j0 > j1 || i0 > i1) return 1;
     box = {j0 / RT, j1 / RT, i0 / RT, i1 / RT};
     return 0;
@@ -82,7 +88,8 @@ __device__ __forceinline__ int face_box(const float4 a, const float4 b, const fl
 template <int PASS>
 __global__ void raster_bin_kernel(const float4* __restrict__ proj, const int* __restrict__ faces, int n_verts, int n_faces,
                                   DevCams cams, int H, int W, int tiles_x, int tiles_y, int* __restrict__ tile_cnt,
-                                  const int* __restrict__ tile_off, int* __restrict__ tile_faces, int* __restrict__ n_skipped) {
+                                  const int* __restrict__ tile_off, int* __restrict__ tile_faces, int* __restrict__ n_skipped,
+                                  float pad) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
     if (f >= n_faces) return;
@@ -90,7 +97,7 @@ __global__ void raster_bin_kernel(const float4* __restrict__ proj, const int* __
     if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) return;
     const float4* p = proj + (size_t)v * n_verts;
     FaceBox box;
-    const int st = face_box(p[i0], p[i1], p[i2], cams.c[v].z_clip, H, W, box);
+    const int st = face_box(p[i0], p[i1], p[i2], cams.c[v].z_clip, H, W, box, pad);
     if (st == 2 && PASS == 0) atomicAdd(n_skipped, 1);
     if (st != 0) return;
     for (int ty = box.ty0; ty <= box.ty1; ++ty)
@@ -145,7 +152,7 @@ raster_tile_kernel(const float4* __restrict__ proj, const int* __restrict__ face
     const int lx = threadIdx.x % RT, ly = threadIdx.x / RT;
     const int col = tx * RT + lx, row = ty * RT + ly;
     const bool live = col < W && row < H;
-    const float px = pix_to_ndc(col, W), py = pix_to_ndc(row, H);
+    const float px = pix_to_ndc(col, W, H), py = pix_to_ndc(row, H, W);
     const float z_clip = cams.c[v].z_clip;
     const float4* p = proj + (size_t)v * n_verts;
     const int beg = tile_off[t], end = tile_off[t + 1];
@@ -165,7 +172,7 @@ raster_tile_kernel(const float4* __restrict__ proj, const int* __restrict__ face
             r.xmin = fminf(a.x, fminf(b.x, c.x)); r.xmax = fmaxf(a.x, fmaxf(b.x, c.x));
             r.ymin = fminf(a.y, fminf(b.y, c.y)); r.ymax = fmaxf(a.y, fmaxf(b.y, c.y));
             r.id = f;
-            r.straddle = fminf(a.z, fminf(b.z, c.z)) < z_clip;
+            r.straddle = z_clip > 0.f && fminf(a.z, fminf(b.z, c.z)) < z_clip;
             rec[k] = r;
         }
         __syncthreads();
@@ -277,6 +284,179 @@ __global__ void raster_phong_kernel(const float* __restrict__ verts, const int* 
     for (int d = 0; d < 3; ++d) rgb[3 * g + d] = (uint8_t)(int)fminf(fmaxf(out[d] * 255.f, 0.f), 255.f);
 }
 
+
+// ------------------------------------------------------------------------------------------------ soft silhouette (optim/)
+// SSRenderer (optim/renderer.py:64-104): MeshRasterizer(blur_radius, faces_per_pixel = K, perspective-correct, clipped
+// barycentrics) + SoftSilhouetteShader(sigma).  Per pixel every face within sqrt(blur_radius) (squared NDC distance) is a
+// fragment with a signed distance; the K fragments nearest in depth are kept (sorted insertion into [K][H*W] arrays, pixel
+// index fastest so that neighbouring threads touch neighbouring words); alpha = 1 - prod(1 - sigmoid(-d / sigma)).
+
+// pytorch3d PointLineDistanceForward: squared distance to the segment a-b and the clamped parameter t
+__device__ __forceinline__ float seg_dist2(float px, float py, float ax, float ay, float bx, float by, float& t) {
+    const float dx = bx - ax, dy = by - ay;
+    const float l2 = dx * dx + dy * dy;
+    if (l2 <= R_EPS) {
+        t = 1.f;
+        return (px - bx) * (px - bx) + (py - by) * (py - by);
+    }
+    t = fminf(fmaxf((dx * (px - ax) + dy * (py - ay)) / l2, 0.f), 1.f);
+    const float qx = ax + t * dx - px, qy = ay + t * dy - py;
+    return qx * qx + qy * qy;
+}
+
+struct SoftFrag {
+    float z, sd;
+    int face;
+};
+
+// evaluates one face at one pixel; false when the face contributes no fragment.  `edge_t` returns the closest edge and its t.
+__device__ __forceinline__ bool soft_eval(const float4 a, const float4 b, const float4 c, float px, float py, float blur,
+                                          SoftFrag& out, int& edge_id, float& edge_t) {
+    const float area = edge(c.x, c.y, a.x, a.y, b.x, b.y);
+    if (area <= R_EPS && area >= -R_EPS) return false;
+    const float den = area + R_EPS;
+    const float w0 = edge(px, py, b.x, b.y, c.x, c.y) / den, w1 = edge(px, py, c.x, c.y, a.x, a.y) / den,
+                w2 = edge(px, py, a.x, a.y, b.x, b.y) / den;
+    const float t0 = w0 * b.z * c.z, t1 = a.z * w1 * c.z, t2 = a.z * b.z * w2;
+    const float d = fmaxf(t0 + t1 + t2, R_EPS);
+    const float b0 = t0 / d, b1 = t1 / d, b2 = t2 / d;
+    float c0 = fminf(fmaxf(b0, 0.f), 1.f), c1 = fminf(fmaxf(b1, 0.f), 1.f), c2 = fminf(fmaxf(b2, 0.f), 1.f);
+    const float cs = fmaxf(c0 + c1 + c2, 1e-5f);
+    c0 /= cs; c1 /= cs; c2 /= cs;
+    const float pz = c0 * a.z + c1 * b.z + c2 * c.z;
+    if (!(pz >= 0.f)) return false;
+    float ta, tb, tc;
+    const float d0 = seg_dist2(px, py, a.x, a.y, b.x, b.y, ta), d1 = seg_dist2(px, py, b.x, b.y, c.x, c.y, tb),
+                d2 = seg_dist2(px, py, c.x, c.y, a.x, a.y, tc);
+    float dist = d0;
+    edge_id = 0; edge_t = ta;
+    if (d1 < dist) { dist = d1; edge_id = 1; edge_t = tb; }
+    if (d2 < dist) { dist = d2; edge_id = 2; edge_t = tc; }
+    const bool inside = b0 > 0.f && b1 > 0.f && b2 > 0.f;
+    if (!inside && dist >= blur) return false;
+    out.z = pz;
+    out.sd = inside ? -dist : dist;
+    return true;
+}
+
+__global__ void __launch_bounds__(RT* RT)
+soft_tile_kernel(const float4* __restrict__ proj, const int* __restrict__ faces, int n_verts, int H, int W, int tiles_x,
+                 const int* __restrict__ tile_off, const int* __restrict__ tile_faces, float sigma, float blur, int K,
+                 float* __restrict__ alpha, float* __restrict__ zbuf0, int* __restrict__ n_frag, int* __restrict__ frag_face,
+                 float* __restrict__ frag_sd, float* __restrict__ frag_z) {
+    __shared__ float4 sa[RCHUNK], sb[RCHUNK], sc[RCHUNK];
+    __shared__ int sid[RCHUNK];
+    const int ty = blockIdx.y, tx = blockIdx.x;
+    const int t = ty * tiles_x + tx;
+    const int col = tx * RT + threadIdx.x % RT, row = ty * RT + threadIdx.x / RT;
+    const bool live = col < W && row < H;
+    const float px = pix_to_ndc(col, W, H), py = pix_to_ndc(row, H, W);
+    const size_t hw = (size_t)H * W, o = (size_t)row * W + col;
+    const int beg = tile_off[t], end = tile_off[t + 1];
+    int n = 0;
+    for (int base = beg; base < end; base += RCHUNK) {
+        const int cnt = min(RCHUNK, end - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+            const int f = tile_faces[base + k];
+            sa[k] = proj[faces[3 * f]]; sb[k] = proj[faces[3 * f + 1]]; sc[k] = proj[faces[3 * f + 2]];
+            sid[k] = f;
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int k = 0; k < cnt; ++k) {
+            const float4 a = sa[k], b = sb[k], c = sc[k];
+            const float pad = sqrtf(blur);
+            if (px > fmaxf(a.x, fmaxf(b.x, c.x)) + pad || px < fminf(a.x, fminf(b.x, c.x)) - pad ||
+                py > fmaxf(a.y, fmaxf(b.y, c.y)) + pad || py < fminf(a.y, fminf(b.y, c.y)) - pad)
+                continue;
+            SoftFrag fr;
+            int e;
+            float et;
+            if (!soft_eval(a, b, c, px, py, blur, fr, e, et)) continue;
+            fr.face = sid[k];
+            // sorted insertion by (z, face) into the K nearest; the list lives in [k][pixel] global arrays
+            int pos = n < K ? n : K;
+            while (pos > 0) {
+                const float zp = frag_z[(size_t)(pos - 1) * hw + o];
+                const int fp = frag_face[(size_t)(pos - 1) * hw + o];
+                if (zp < fr.z || (zp == fr.z && fp < fr.face)) break;
+                if (pos < K) {
+                    frag_z[(size_t)pos * hw + o] = zp;
+                    frag_face[(size_t)pos * hw + o] = fp;
+                    frag_sd[(size_t)pos * hw + o] = frag_sd[(size_t)(pos - 1) * hw + o];
+                }
+                --pos;
+            }
+            if (pos < K) {
+                frag_z[(size_t)pos * hw + o] = fr.z;
+                frag_face[(size_t)pos * hw + o] = fr.face;
+                frag_sd[(size_t)pos * hw + o] = fr.sd;
+                if (n < K) ++n;
+            }
+        }
+    }
+    if (!live) return;
+    float keep = 1.f;
+    for (int k = 0; k < n; ++k) keep *= 1.f / (1.f + __expf(-frag_sd[(size_t)k * hw + o] / sigma));  // 1 - sigmoid(-d/sigma)
+    alpha[o] = 1.f - keep;
+    zbuf0[o] = n > 0 ? frag_z[o] : -1.f;
+    n_frag[o] = n;
+}
+
+__global__ void soft_backward_pixels_kernel(const float4* __restrict__ proj, const int* __restrict__ faces, int H, int W,
+                                            float sigma, float blur, const float* __restrict__ grad_alpha,
+                                            const int* __restrict__ n_frag, const int* __restrict__ frag_face,
+                                            const float* __restrict__ frag_sd, float* __restrict__ g_ndc /*[Nv,2]*/) {
+    const size_t hw = (size_t)H * W;
+    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= hw) return;
+    const float g = grad_alpha[o];
+    const int n = n_frag[o];
+    if (n == 0 || g == 0.f) return;
+    const int row = (int)(o / W), col = (int)(o % W);
+    const float px = pix_to_ndc(col, W, H), py = pix_to_ndc(row, H, W);
+    float keep = 1.f;
+    for (int k = 0; k < n; ++k) keep *= 1.f / (1.f + __expf(-frag_sd[(size_t)k * hw + o] / sigma));
+    if (keep == 0.f) return;
+    for (int k = 0; k < n; ++k) {
+        const float sd = frag_sd[(size_t)k * hw + o];
+        const float p = 1.f / (1.f + __expf(sd / sigma));
+        // d alpha / d sd = -(prod_{j != k} (1 - p_j)) p_k (1 - p_k) / sigma = -keep p_k / sigma
+        const float g_d = -g * keep * p / sigma * (sd < 0.f ? -1.f : 1.f);
+        if (g_d == 0.f) continue;
+        const int f = frag_face[(size_t)k * hw + o];
+        const int iv[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
+        const float4 a = proj[iv[0]], b = proj[iv[1]], c = proj[iv[2]];
+        SoftFrag fr;
+        int e;
+        float t;
+        if (!soft_eval(a, b, c, px, py, INFINITY, fr, e, t)) continue;
+        const int ia = iv[e], ib = iv[(e + 1) % 3];
+        const float4 va = e == 0 ? a : (e == 1 ? b : c), vb = e == 0 ? b : (e == 1 ? c : a);
+        const float qx = va.x + t * (vb.x - va.x) - px, qy = va.y + t * (vb.y - va.y) - py;
+        const float gx = g_d * 2.f * qx, gy = g_d * 2.f * qy;
+        atomicAdd(g_ndc + 2 * ia, (1.f - t) * gx); atomicAdd(g_ndc + 2 * ia + 1, (1.f - t) * gy);
+        atomicAdd(g_ndc + 2 * ib, t * gx); atomicAdd(g_ndc + 2 * ib + 1, t * gy);
+    }
+}
+
+// NDC gradient -> view space (x_ndc = fx x / z + cx) -> world space (X_view = X_world R + T)
+__global__ void soft_backward_verts_kernel(const float* __restrict__ verts, int n_verts, DevCams cams,
+                                           const float* __restrict__ g_ndc, float* __restrict__ grad_verts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_verts) return;
+    const ivlm_raster_cam& c = cams.c[0];
+    const float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
+    float w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w[k] = x * c.R[k] + y * c.R[3 + k] + z * c.R[6 + k] + c.T[k];
+    const float gx = g_ndc[2 * i], gy = g_ndc[2 * i + 1];
+    const float gv[3] = {gx * c.fx / w[2], gy * c.fy / w[2], -(gx * c.fx * w[0] + gy * c.fy * w[1]) / (w[2] * w[2])};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) grad_verts[3 * i + r] = gv[0] * c.R[3 * r] + gv[1] * c.R[3 * r + 1] + gv[2] * c.R[3 * r + 2];
+}
+
 static int load_cams(const ivlm_raster_cam* cams_h, int V, DevCams& dc) {
     IVLM_REQUIRE(cams_h && V >= 1 && V <= IVLM_RASTER_MAX_VIEWS, "raster: need 1..%d cameras, got %d", IVLM_RASTER_MAX_VIEWS, V);
     for (int v = 0; v < V; ++v) dc.c[v] = cams_h[v];
@@ -294,7 +474,6 @@ extern "C" int ivlm_rasterize_mesh(ivlm_handle h, const float* verts, const int3
     IVLM_REQUIRE(h && verts && faces && pix_to_face && bary, "rasterize_mesh: null argument");
     IVLM_REQUIRE(n_verts > 0 && n_faces > 0 && H > 0 && W > 0, "rasterize_mesh: empty mesh or image (%d verts, %d faces, %dx%d)",
                  n_verts, n_faces, H, W);
-    IVLM_REQUIRE(H == W, "rasterize_mesh: square images only (the reference renders 512^2 / 1024^2), got %dx%d", H, W);
     DevCams dc{};
     IVLM_TRY(load_cams(cams_h, V, dc));
     const int tiles_x = (W + RT - 1) / RT, tiles_y = (H + RT - 1) / RT;
@@ -310,7 +489,7 @@ extern "C" int ivlm_rasterize_mesh(ivlm_handle h, const float* verts, const int3
     raster_project_kernel<<<dim3((n_verts + 255) / 256, V), 256, 0, stream>>>(verts, n_verts, dc, V, proj);
     const dim3 fgrid((n_faces + 127) / 128, V);
     raster_bin_kernel<0><<<fgrid, 128, 0, stream>>>(proj, faces, n_verts, n_faces, dc, H, W, tiles_x, tiles_y, tile_cnt,
-                                                    nullptr, nullptr, skipped);
+                                                    nullptr, nullptr, skipped, 0.f);
     raster_scan_kernel<<<1, 1024, 0, stream>>>(tile_cnt, tile_off, n_tiles);
     int total = 0, n_skip = 0;
     IVLM_CHECK_CUDA(cudaMemcpyAsync(&total, tile_off + n_tiles, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -320,7 +499,7 @@ extern "C" int ivlm_rasterize_mesh(ivlm_handle h, const float* verts, const int3
     IVLM_CHECK_CUDA(cudaMallocAsync(&tile_faces, sizeof(int) * (size_t)(total > 0 ? total : 1), stream));
     IVLM_CHECK_CUDA(cudaMemsetAsync(tile_cnt, 0, sizeof(int) * (size_t)n_tiles, stream));
     raster_bin_kernel<1><<<fgrid, 128, 0, stream>>>(proj, faces, n_verts, n_faces, dc, H, W, tiles_x, tiles_y, tile_cnt,
-                                                    tile_off, tile_faces, skipped);
+                                                    tile_off, tile_faces, skipped, 0.f);
     raster_tile_kernel<<<dim3(tiles_x, tiles_y, V), RT * RT, 0, stream>>>(
         proj, faces, n_verts, dc, H, W, tiles_x, tiles_y, tile_off, tile_faces, pix_to_face, bary, zbuf,
         reinterpret_cast<long long*>(p2v));
@@ -356,5 +535,71 @@ extern "C" int ivlm_shade_phong(ivlm_handle h, const float* verts, const int32_t
     h->launches += 2;
     IVLM_CHECK_CUDA(cudaFreeAsync(lights, stream));
     IVLM_CHECK_CUDA(cudaFreeAsync(nrm, stream));
+    return IVLM_OK;
+}
+
+extern "C" int ivlm_soft_silhouette(ivlm_handle h, const float* verts, const int32_t* faces, int32_t n_verts, int32_t n_faces,
+                                    const ivlm_raster_cam* cam_h, int32_t H, int32_t W, float sigma, float blur_radius, int32_t K,
+                                    float* alpha, float* zbuf0, int32_t* n_frag, int32_t* frag_face, float* frag_sd, float* frag_z,
+                                    void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    IVLM_REQUIRE(h && verts && faces && alpha && zbuf0 && n_frag && frag_face && frag_sd && frag_z, "soft_silhouette: null argument");
+    IVLM_REQUIRE(n_verts > 0 && n_faces > 0 && H > 0 && W > 0 && K >= 1 && sigma > 0.f && blur_radius >= 0.f,
+                 "soft_silhouette: bad sizes (%d verts, %d faces, %dx%d, K=%d, sigma=%g)", n_verts, n_faces, H, W, K, sigma);
+    DevCams dc{};
+    IVLM_TRY(load_cams(cam_h, 1, dc));
+    const int tiles_x = (W + RT - 1) / RT, tiles_y = (H + RT - 1) / RT, n_tiles = tiles_x * tiles_y;
+    float4* proj = nullptr;
+    int *tile_cnt = nullptr, *tile_off = nullptr, *tile_faces = nullptr;
+    IVLM_CHECK_CUDA(cudaMallocAsync(&proj, sizeof(float4) * (size_t)n_verts, stream));
+    IVLM_CHECK_CUDA(cudaMallocAsync(&tile_cnt, sizeof(int) * (size_t)(n_tiles + 1), stream));
+    IVLM_CHECK_CUDA(cudaMallocAsync(&tile_off, sizeof(int) * (size_t)(n_tiles + 1), stream));
+    IVLM_CHECK_CUDA(cudaMemsetAsync(tile_cnt, 0, sizeof(int) * (size_t)(n_tiles + 1), stream));
+    const float pad = sqrtf(blur_radius);
+    raster_project_kernel<<<dim3((n_verts + 255) / 256, 1), 256, 0, stream>>>(verts, n_verts, dc, 1, proj);
+    const dim3 fgrid((n_faces + 127) / 128, 1);
+    raster_bin_kernel<0><<<fgrid, 128, 0, stream>>>(proj, faces, n_verts, n_faces, dc, H, W, tiles_x, tiles_y, tile_cnt, nullptr,
+                                                    nullptr, tile_cnt + n_tiles, pad);
+    raster_scan_kernel<<<1, 1024, 0, stream>>>(tile_cnt, tile_off, n_tiles);
+    int total = 0;
+    IVLM_CHECK_CUDA(cudaMemcpyAsync(&total, tile_off + n_tiles, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    IVLM_CHECK_CUDA(cudaStreamSynchronize(stream));
+    IVLM_CHECK_CUDA(cudaMallocAsync(&tile_faces, sizeof(int) * (size_t)(total > 0 ? total : 1), stream));
+    IVLM_CHECK_CUDA(cudaMemsetAsync(tile_cnt, 0, sizeof(int) * (size_t)n_tiles, stream));
+    raster_bin_kernel<1><<<fgrid, 128, 0, stream>>>(proj, faces, n_verts, n_faces, dc, H, W, tiles_x, tiles_y, tile_cnt, tile_off,
+                                                    tile_faces, tile_cnt + n_tiles, pad);
+    soft_tile_kernel<<<dim3(tiles_x, tiles_y), RT * RT, 0, stream>>>(proj, faces, n_verts, H, W, tiles_x, tile_off, tile_faces, sigma,
+                                                                     blur_radius, K, alpha, zbuf0, n_frag, frag_face, frag_sd, frag_z);
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    h->launches += 6;
+    IVLM_CHECK_CUDA(cudaFreeAsync(tile_faces, stream));
+    IVLM_CHECK_CUDA(cudaFreeAsync(tile_off, stream));
+    IVLM_CHECK_CUDA(cudaFreeAsync(tile_cnt, stream));
+    IVLM_CHECK_CUDA(cudaFreeAsync(proj, stream));
+    return IVLM_OK;
+}
+
+extern "C" int ivlm_soft_silhouette_backward(ivlm_handle h, const float* verts, const int32_t* faces, int32_t n_verts,
+                                             int32_t n_faces, const ivlm_raster_cam* cam_h, int32_t H, int32_t W, float sigma,
+                                             const float* grad_alpha, const int32_t* n_frag, const int32_t* frag_face,
+                                             const float* frag_sd, float* grad_verts, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    IVLM_REQUIRE(h && verts && faces && grad_alpha && n_frag && frag_face && frag_sd && grad_verts, "soft_silhouette_backward: null argument");
+    IVLM_REQUIRE(n_verts > 0 && n_faces > 0 && H > 0 && W > 0 && sigma > 0.f, "soft_silhouette_backward: bad sizes");
+    DevCams dc{};
+    IVLM_TRY(load_cams(cam_h, 1, dc));
+    float4* proj = nullptr;
+    float* g_ndc = nullptr;
+    IVLM_CHECK_CUDA(cudaMallocAsync(&proj, sizeof(float4) * (size_t)n_verts, stream));
+    IVLM_CHECK_CUDA(cudaMallocAsync(&g_ndc, sizeof(float) * 2 * (size_t)n_verts, stream));
+    IVLM_CHECK_CUDA(cudaMemsetAsync(g_ndc, 0, sizeof(float) * 2 * (size_t)n_verts, stream));
+    raster_project_kernel<<<dim3((n_verts + 255) / 256, 1), 256, 0, stream>>>(verts, n_verts, dc, 1, proj);
+    soft_backward_pixels_kernel<<<(unsigned)(((size_t)H * W + 127) / 128), 128, 0, stream>>>(proj, faces, H, W, sigma, 0.f, grad_alpha,
+                                                                                            n_frag, frag_face, frag_sd, g_ndc);
+    soft_backward_verts_kernel<<<(n_verts + 255) / 256, 256, 0, stream>>>(verts, n_verts, dc, g_ndc, grad_verts);
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    h->launches += 3;
+    IVLM_CHECK_CUDA(cudaFreeAsync(g_ndc, stream));
+    IVLM_CHECK_CUDA(cudaFreeAsync(proj, stream));
     return IVLM_OK;
 }

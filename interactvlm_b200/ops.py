@@ -457,14 +457,15 @@ class Context:
 
 
 def _cam_array(cams):
-    """list of dict(R [3,3], T [3], C [3], s, z_clip) -> ctypes array of ivlm_raster_cam."""
+    """list of dict(R [3,3], T [3], C [3], s | (fx, fy, cx, cy), z_clip) -> ctypes array of ivlm_raster_cam."""
     assert 1 <= len(cams) <= L.RASTER_MAX_VIEWS, f"1..{L.RASTER_MAX_VIEWS} cameras per call"
     arr = (L.RasterCam * len(cams))()
     for a, c in zip(arr, cams):
         a.R[:] = [float(x) for x in np.asarray(c["R"], dtype=np.float32).reshape(9)]
         a.T[:] = [float(x) for x in np.asarray(c["T"], dtype=np.float32).reshape(3)]
         a.C[:] = [float(x) for x in np.asarray(c["C"], dtype=np.float32).reshape(3)]
-        a.s, a.z_clip = float(c["s"]), float(c["z_clip"])
+        a.fx, a.fy = float(c.get("fx", c.get("s", 1.0))), float(c.get("fy", c.get("s", 1.0)))
+        a.cx, a.cy, a.z_clip = float(c.get("cx", 0.0)), float(c.get("cy", 0.0)), float(c["z_clip"])
     return arr
 
 

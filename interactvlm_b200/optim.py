@@ -166,3 +166,103 @@ def ICP(obj_contact_pcd, hum_contact_pcd, init_transform: Optional[SimilarityTra
             break
         prev = combined
     return ICPSolution(converged, rmse, Xt, SimilarityTransform(R, T, s), history)
+
+
+# ------------------------------------------------------------------------------------------------ soft silhouette renderer
+import math  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+from . import ops as _ops  # noqa: E402
+
+
+def perspective_camera(focal_length, principal_point, image_size):
+    """The camera of optim/renderer.py:29-46 -- pytorch3d PerspectiveCameras(in_ndc=False, R = diag(-1,-1,1), T = 0) -- as
+    the dict ops.rasterize_mesh / soft_silhouette take: pixel focal lengths and principal point are converted to NDC with
+    s = min(H, W) / 2 (f / s, -(c - size / 2) / s); no znear, so no z clipping."""
+    H, W = int(image_size[0]), int(image_size[1])
+    fl = torch.as_tensor(focal_length, dtype=torch.float64).reshape(-1)
+    fl = fl.repeat(2) if fl.numel() == 1 else fl
+    pp = torch.as_tensor(principal_point, dtype=torch.float64).reshape(2)
+    s = min(H, W) / 2.0
+    return dict(R=np.diag([-1.0, -1.0, 1.0]).astype(np.float32), T=np.zeros(3, np.float32), C=np.zeros(3, np.float32),
+                fx=float(fl[0]) / s, fy=float(fl[1]) / s, cx=-(float(pp[0]) - W / 2.0) / s, cy=-(float(pp[1]) - H / 2.0) / s,
+                z_clip=0.0)
+
+
+class _SoftSilhouette(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, verts, faces, cam, H, W, sigma, blur_radius, K, ctx):
+        v, f = _f32(verts, "verts"), faces.contiguous()
+        if f.dtype != torch.int32 or not f.is_cuda or f.dim() != 2 or f.shape[1] != 3 or v.dim() != 2 or v.shape[1] != 3:
+            raise ValueError("soft_silhouette: verts [Nv,3] float32 and faces [Nf,3] int32 CUDA tensors expected")
+        dev = v.device
+        alpha = torch.empty((H, W), device=dev, dtype=torch.float32)
+        zbuf0 = torch.empty((H, W), device=dev, dtype=torch.float32)
+        n_frag = torch.empty((H, W), device=dev, dtype=torch.int32)
+        frag_face = torch.empty((K, H, W), device=dev, dtype=torch.int32)
+        frag_sd = torch.empty((K, H, W), device=dev, dtype=torch.float32)
+        frag_z = torch.empty((K, H, W), device=dev, dtype=torch.float32)
+        cams = _ops._cam_array([cam])
+        L.check(ctx.lib.ivlm_soft_silhouette(ctx.h, P(v), P(f), C.c_int32(v.shape[0]), C.c_int32(f.shape[0]), cams, C.c_int32(H),
+                                             C.c_int32(W), C.c_float(sigma), C.c_float(blur_radius), C.c_int32(K), P(alpha), P(zbuf0),
+                                             P(n_frag), P(frag_face), P(frag_sd), P(frag_z), ctx.stream), "soft_silhouette")
+        del frag_z
+        fctx.save_for_backward(v, f, n_frag, frag_face, frag_sd)
+        fctx.meta = (cam, H, W, sigma, ctx)
+        fctx.mark_non_differentiable(zbuf0)
+        return alpha, zbuf0
+
+    @staticmethod
+    def backward(fctx, g_alpha, _g_z):
+        v, f, n_frag, frag_face, frag_sd = fctx.saved_tensors
+        cam, H, W, sigma, ctx = fctx.meta
+        grad = torch.empty_like(v)
+        L.check(ctx.lib.ivlm_soft_silhouette_backward(ctx.h, P(v), P(f), C.c_int32(v.shape[0]), C.c_int32(f.shape[0]),
+                                                      _ops._cam_array([cam]), C.c_int32(H), C.c_int32(W), C.c_float(sigma),
+                                                      P(g_alpha.float().contiguous()), P(n_frag), P(frag_face), P(frag_sd), P(grad),
+                                                      ctx.stream), "soft_silhouette_backward")
+        return grad, None, None, None, None, None, None, None, None
+
+
+def soft_silhouette(verts, faces, cam, image_size, sigma=1e-4, blur_radius=None, faces_per_pixel=100, ctx: Context | None = None):
+    """-> (alpha [H,W] differentiable w.r.t. verts, zbuf0 [H,W]).  pytorch3d MeshRasterizer(blur_radius, faces_per_pixel) +
+    SoftSilhouetteShader(BlendParams(sigma)) for one camera (include/ivlm_b200.h: ivlm_soft_silhouette)."""
+    ctx = ctx or _ctx(verts.device)
+    if blur_radius is None:
+        blur_radius = math.log(1.0 / 1e-4 - 1.0) * sigma          # optim/renderer.py:71
+    H, W = int(image_size[0]), int(image_size[1])
+    return _SoftSilhouette.apply(verts, faces, cam, H, W, float(sigma), float(blur_radius), int(faces_per_pixel), ctx)
+
+
+class SSRenderer:
+    """optim/renderer.py:64-104 with the same constructor arguments and `render` returns: `silhouette_image [1,H,W,4]` (rgb =
+    1, alpha = soft silhouette, differentiable w.r.t. the vertices) and `depth [1,H,W,1]` (nearest fragment depth normalised
+    to [0,1] over the valid pixels, -1 elsewhere)."""
+
+    def __init__(self, img_shape, h_faces, o_faces, camera_params, device="cuda", ctx: Context | None = None):
+        self.img_shape = (int(img_shape[0]), int(img_shape[1]))
+        self.h_faces = None if h_faces is None else torch.as_tensor(h_faces).to(device)
+        self.o_faces = torch.as_tensor(o_faces).to(device)
+        fl = camera_params["focal_length"] if isinstance(camera_params, dict) else camera_params.focal_length
+        pp = camera_params["principal_point"] if isinstance(camera_params, dict) else camera_params.principal_point
+        self.cam = perspective_camera(torch.as_tensor(fl).detach().cpu(), torch.as_tensor(pp).detach().cpu(), self.img_shape)
+        self.sigma = 1e-4
+        self.blur_radius = math.log(1.0 / 1e-4 - 1.0) * self.sigma
+        self.faces_per_pixel = 100
+        self.ctx = ctx
+
+    def render(self, vertices, **kwargs):
+        verts, faces = vertices, self.o_faces
+        if kwargs.get("h_vertices") is not None:        # join_meshes_as_scene([o_mesh, h_mesh]) (renderer.py:48-61)
+            verts = torch.cat([vertices, kwargs["h_vertices"]], 0)
+            faces = torch.cat([self.o_faces, self.h_faces + vertices.shape[0]], 0)
+        alpha, z = soft_silhouette(verts.float(), faces.to(torch.int32), self.cam, self.img_shape, self.sigma, self.blur_radius,
+                                   self.faces_per_pixel, self.ctx)
+        depth = z.clone()[None, ..., None]
+        valid = depth != -1
+        if bool(valid.any()):
+            d = depth[valid]
+            depth[valid] = (d - d.min()) / (d.max() - d.min())
+        image = torch.cat([torch.ones((*alpha.shape, 3), device=alpha.device), alpha[..., None]], -1)[None]
+        return image, depth

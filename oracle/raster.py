@@ -73,10 +73,31 @@ def project(verts, cam):
     view = np.empty_like(v)
     for k in range(3):
         view[:, k] = ((v[:, 0] * R[0, k] + v[:, 1] * R[1, k]) + v[:, 2] * R[2, k]) + T[k]
-    out[:, 0] = (view[:, 0] * cam["s"]) / view[:, 2]
-    out[:, 1] = (view[:, 1] * cam["s"]) / view[:, 2]
+    fx, fy = F(cam.get("fx", cam.get("s", 1.0))), F(cam.get("fy", cam.get("s", 1.0)))
+    out[:, 0] = (view[:, 0] * fx) / view[:, 2] + F(cam.get("cx", 0.0))
+    out[:, 1] = (view[:, 1] * fy) / view[:, 2] + F(cam.get("cy", 0.0))
     out[:, 2] = view[:, 2]
     return out
+
+
+def pixel_ndc(S1, S2, dtype=F):
+    """pytorch3d PixToNonSquareNdc on the flipped index for every pixel of a side of S1 pixels (other side S2): the longer
+    side spans [-S1/S2, S1/S2], the shorter [-1, 1]."""
+    rng = dtype(S1) / dtype(S2) * dtype(2) if S1 > S2 else dtype(2)
+    off = rng / dtype(2)
+    return (-off + (rng * (S1 - 1 - np.arange(S1)).astype(dtype) + off) / dtype(S1)).astype(dtype)
+
+
+def perspective_camera(focal_length, principal_point, image_size):
+    """optim/renderer.py:29-46: pytorch3d PerspectiveCameras(in_ndc=False) with R = diag(-1,-1,1), T = 0; focal length and
+    principal point in pixels are converted to NDC with s = min(H, W) / 2: f_ndc = f / s, c_ndc = -(c - size/2) / s.
+    No znear -> no z clipping."""
+    H, W = image_size
+    fl = np.broadcast_to(np.asarray(focal_length, dtype=np.float64).reshape(-1), (2,)) if np.ndim(focal_length) else np.array([focal_length] * 2, dtype=np.float64)
+    pp = np.asarray(principal_point, dtype=np.float64).reshape(2)
+    s = min(H, W) / 2.0
+    return dict(R=np.diag([-1.0, -1.0, 1.0]).astype(F), T=np.zeros(3, F), C=np.zeros(3, F), fx=F(fl[0] / s), fy=F(fl[1] / s),
+                cx=F(-(pp[0] - W / 2.0) / s), cy=F(-(pp[1] - H / 2.0) / s), z_clip=F(0.0))
 
 
 def _edge(px, py, ax, ay, bx, by):
@@ -93,15 +114,13 @@ def rasterize(verts, faces, cam, H, W):
     bary = np.full((H, W, 3), -1, dtype=F)
     zbuf = np.full((H, W), -1, dtype=F)
     best = np.full((H, W), np.inf, dtype=F)
-    # PixToNonSquareNdc on the flipped index (square images): -1 + (2 i' + 1) / S with i' = S - 1 - i
-    ys = (F(-1) + (F(2) * (H - 1 - np.arange(H)).astype(F) + F(1)) / F(H)).astype(F)
-    xs = (F(-1) + (F(2) * (W - 1 - np.arange(W)).astype(F) + F(1)) / F(W)).astype(F)
+    ys, xs = pixel_ndc(H, W), pixel_ndc(W, H)
     zc = cam["z_clip"]
     skipped = 0
     for f, (i0, i1, i2) in enumerate(faces):
         (x0, y0, z0), (x1, y1, z1), (x2, y2, z2) = p[i0], p[i1], p[i2]
         zmin, zmax = min(z0, z1, z2), max(z0, z1, z2)
-        if zmax < zc:
+        if zmax < max(zc, F(0)):
             continue  # entirely behind the clip plane (clip_faces case 1) / behind the camera
         if zmin <= 0:
             skipped += 1  # straddles the camera plane: pytorch3d clips it; not restated
@@ -128,7 +147,7 @@ def rasterize(verts, faces, cam, H, W):
         b0, b1, b2 = t0 / d, t1 / d, t2 / d
         pz = (b0 * z0 + b1 * z1) + b2 * z2
         inside = (b0 > 0) & (b1 > 0) & (b2 > 0) & (pz >= 0)
-        if zmin < zc:
+        if zc > 0 and zmin < zc:
             inside &= pz >= zc  # the part of a straddling triangle that pytorch3d's clip_faces keeps
         r = rows[:, None].repeat(len(cols), 1)
         c = cols[None, :].repeat(len(rows), 0)
@@ -195,3 +214,100 @@ def render_phong(verts, faces, colors, cam, light_location, H, W, ambient=0.5, d
     img = np.ones((H, W, 3), dtype=F)
     img[fg] = rgb
     return (img * 255).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------ soft silhouette (optim/)
+def _seg_dist2(px, py, ax, ay, bx, by, eps=1e-8):
+    """pytorch3d PointLineDistanceForward: squared distance from p to the segment a-b (+ the clamped parameter)."""
+    dx, dy = bx - ax, by - ay
+    l2 = dx * dx + dy * dy
+    if l2 <= eps:
+        return (px - bx) ** 2 + (py - by) ** 2, 1.0
+    t = min(max((dx * (px - ax) + dy * (py - ay)) / l2, 0.0), 1.0)
+    qx, qy = ax + t * dx, ay + t * dy
+    return (px - qx) ** 2 + (py - qy) ** 2, t
+
+
+def soft_silhouette(verts, faces, cam, H, W, sigma=1e-4, blur_radius=None, K=100, grad_alpha=None):
+    """SSRenderer.render (optim/renderer.py:64-104): pytorch3d MeshRasterizer(blur_radius = log(1/1e-4 - 1) sigma,
+    faces_per_pixel = 100, perspective-correct, clipped barycentrics) + SoftSilhouetteShader(sigma):
+      per pixel, every face whose squared NDC distance to the pixel centre is < blur_radius (or that covers it) is a candidate
+      with signed distance d (negative inside); the K candidates nearest in depth are kept;
+      alpha = 1 - prod_k (1 - sigmoid(-d_k / sigma)).
+    float64, brute force.  Returns alpha [H,W], zbuf0 [H,W] (depth of the nearest kept candidate, -1 if none) and, when
+    `grad_alpha` [H,W] is given, d(sum(grad_alpha * alpha)) / d verts [Nv,3] (pytorch3d's backward: through the distance to
+    the closest edge with the clamped segment parameter held fixed, through the projection, not through depth ordering).
+    PARITY UNPINNED (pytorch3d absent), see the module header."""
+    v = np.asarray(verts, dtype=np.float64)
+    f = np.asarray(faces, dtype=np.int64)
+    if blur_radius is None:
+        blur_radius = np.log(1.0 / 1e-4 - 1.0) * sigma
+    R, T = np.asarray(cam["R"], np.float64), np.asarray(cam["T"], np.float64)
+    fx, fy = float(cam.get("fx", cam.get("s", 1.0))), float(cam.get("fy", cam.get("s", 1.0)))
+    cx, cy = float(cam.get("cx", 0.0)), float(cam.get("cy", 0.0))
+    view = v @ R + T
+    ndc = np.stack([fx * view[:, 0] / view[:, 2] + cx, fy * view[:, 1] / view[:, 2] + cy, view[:, 2]], -1)
+    ys, xs = pixel_ndc(H, W, np.float64), pixel_ndc(W, H, np.float64)
+    alpha = np.zeros((H, W))
+    zbuf0 = np.full((H, W), -1.0)
+    g_ndc = np.zeros((len(v), 2))
+    pad = np.sqrt(blur_radius)
+    tri = ndc[f]                                   # [Nf,3,3]
+    lo, hi = tri[:, :, :2].min(1) - pad, tri[:, :, :2].max(1) + pad
+    zmax, zmin = tri[:, :, 2].max(1), tri[:, :, 2].min(1)
+    for r in range(H):
+        py = ys[r]
+        row_faces = np.nonzero((lo[:, 1] <= py) & (hi[:, 1] >= py) & (zmax >= 0) & (zmin > 0))[0]
+        for c in range(W):
+            px = xs[c]
+            cand = []
+            for fi in row_faces[(lo[row_faces, 0] <= px) & (hi[row_faces, 0] >= px)]:
+                (x0, y0, z0), (x1, y1, z1), (x2, y2, z2) = tri[fi]
+                area = _edge(x2, y2, x0, y0, x1, y1)
+                if abs(area) <= 1e-8:
+                    continue
+                den = area + 1e-8
+                w = np.array([_edge(px, py, x1, y1, x2, y2), _edge(px, py, x2, y2, x0, y0), _edge(px, py, x0, y0, x1, y1)]) / den
+                top = np.array([w[0] * z1 * z2, z0 * w[1] * z2, z0 * z1 * w[2]])
+                b = top / max(top.sum(), 1e-8)
+                bc = np.clip(b, 0.0, 1.0)
+                bc = bc / max(bc.sum(), 1e-5)
+                pz = bc[0] * z0 + bc[1] * z1 + bc[2] * z2
+                if pz < 0:
+                    continue
+                segs = [_seg_dist2(px, py, x0, y0, x1, y1), _seg_dist2(px, py, x1, y1, x2, y2), _seg_dist2(px, py, x2, y2, x0, y0)]
+                e = int(np.argmin([s_[0] for s_ in segs]))
+                dist = segs[e][0]
+                inside = bool((b > 0).all())
+                if not inside and dist >= blur_radius:
+                    continue
+                cand.append((pz, fi, -dist if inside else dist, e, segs[e][1]))
+            if not cand:
+                continue
+            cand.sort(key=lambda t: (t[0], t[1]))
+            cand = cand[:K]
+            prob = np.array([1.0 / (1.0 + np.exp(c_[2] / sigma)) if c_[2] / sigma < 700 else 0.0 for c_ in cand])
+            keep = np.prod(1.0 - prob)
+            alpha[r, c] = 1.0 - keep
+            zbuf0[r, c] = cand[0][0]
+            if grad_alpha is not None and grad_alpha[r, c] != 0.0:
+                for (pz, fi, sd, e, t), p_k in zip(cand, prob):
+                    # d alpha / d sd = -(prod_{j != k}(1 - p_j)) p_k (1 - p_k) / sigma
+                    others = np.prod([1.0 - q for j, q in enumerate(prob) if not (cand[j][1] == fi)]) if p_k >= 1.0 else keep / (1.0 - p_k)
+                    g_sd = -grad_alpha[r, c] * others * p_k * (1.0 - p_k) / sigma
+                    g_d = g_sd * (-1.0 if sd < 0 else 1.0)
+                    ia, ib = f[fi][e], f[fi][(e + 1) % 3]
+                    ax, ay = ndc[ia, 0], ndc[ia, 1]
+                    bx, by = ndc[ib, 0], ndc[ib, 1]
+                    qx, qy = ax + t * (bx - ax), ay + t * (by - ay)
+                    gq = g_d * 2.0 * np.array([qx - px, qy - py])       # d dist / d q, the closest point on the segment
+                    g_ndc[ia] += (1.0 - t) * gq
+                    g_ndc[ib] += t * gq
+    if grad_alpha is None:
+        return alpha, zbuf0
+    g_view = np.zeros_like(v)
+    z = view[:, 2]
+    g_view[:, 0] = g_ndc[:, 0] * fx / z
+    g_view[:, 1] = g_ndc[:, 1] * fy / z
+    g_view[:, 2] = -(g_ndc[:, 0] * fx * view[:, 0] + g_ndc[:, 1] * fy * view[:, 1]) / (z * z)
+    return alpha, zbuf0, g_view @ R.T

@@ -127,3 +127,28 @@ def test_render_module_has_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError):
         R.rasterize_views(S.make_test_mesh("blob"), VIEWS, (64, 64))
+
+
+def test_soft_silhouette_oracle_gradient_is_the_numerical_one():
+    """The oracle's analytic backward of the soft silhouette (pytorch3d's formulas) against central finite differences of its
+    own forward, on a non-square image with an off-centre principal point."""
+    v, f = S.make_test_mesh("blob", n_lat=8, n_lon=12)
+    v = (v * 0.6 + np.array([0.1, -0.05, 2.0])).astype(np.float64)
+    cam = O.perspective_camera((60.0, 60.0), (24.0, 16.0), (32, 48))
+    G = np.random.default_rng(0).normal(size=(32, 48))
+    alpha, z, g = O.soft_silhouette(v, f, cam, 32, 48, grad_alpha=G)
+    assert alpha.min() >= 0 and alpha.max() <= 1 and 0.05 < (alpha > 0.5).mean() < 0.5
+    assert ((alpha > 0.01) & (alpha < 0.99)).sum() > 30              # a soft boundary band exists
+    assert (z[alpha > 0.5] > 1.5).all() and (z[alpha == 0] == -1).all()
+    loss = lambda vv: (O.soft_silhouette(vv, f, cam, 32, 48)[0] * G).sum()
+    for k in np.argsort(-np.abs(g).reshape(-1))[:5]:
+        i, d = divmod(int(k), 3)
+        vp, vm = v.copy(), v.copy()
+        vp[i, d] += 1e-6
+        vm[i, d] -= 1e-6
+        num = (loss(vp) - loss(vm)) / 2e-6
+        assert abs(num - g[i, d]) < 1e-5 * max(1.0, abs(num))
+    # hard limit: with a tiny sigma the silhouette is the rasteriser's coverage
+    hard, _ = O.soft_silhouette(v, f, cam, 32, 48, sigma=1e-7, blur_radius=0.0)
+    pix, _, _, _ = O.rasterize(v.astype(np.float32), f, cam, 32, 48)
+    assert ((hard > 0.5) == (pix >= 0)).mean() > 0.995
