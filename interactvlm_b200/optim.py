@@ -266,3 +266,126 @@ class SSRenderer:
             depth[valid] = (d - d.min()) / (d.max() - d.min())
         image = torch.cat([torch.ones((*alpha.shape, 3), device=alpha.device), alpha[..., None]], -1)[None]
         return image, depth
+
+
+# ------------------------------------------------------------------------------------------------ pose refinement loop
+import torch.nn.functional as _F  # noqa: E402
+
+
+def matrix_to_rot6d(matrix):
+    """optim/utils.py:22-27."""
+    matrix = matrix.view(-1, 3, 3)
+    return torch.stack((matrix[:, :, 0], matrix[:, :, 1]), dim=-1).view(-1, 6)
+
+
+def rot6d_to_matrix(rot_6d):
+    """optim/utils.py:30-37 (Gram-Schmidt on the two stored columns)."""
+    rot_6d = rot_6d.view(-1, 3, 2)
+    a1, a2 = rot_6d[:, :, 0], rot_6d[:, :, 1]
+    b1 = _F.normalize(a1)
+    b2 = _F.normalize(a2 - torch.einsum("bi,bi->b", b1, a2).unsqueeze(-1) * b1)
+    b3 = torch.linalg.cross(b1, b2)
+    return torch.stack((b1, b2, b3), dim=-1)
+
+
+def apply_transformation(vertices, rot6d, translation, scaling=1.0):
+    """optim/utils.py:56-62: (vertices * scaling) @ R(rot6d) + translation."""
+    rot_matrix = rot6d_to_matrix(rot6d).view(1, 3, 3)
+    return torch.matmul((vertices * scaling).unsqueeze(1), rot_matrix).squeeze(1) + translation
+
+
+def calculate_centroid(mask):
+    """optim/utils.py:46-53: intensity-weighted (row, col) centroid of the non-zero pixels."""
+    coords = torch.nonzero(mask, as_tuple=False)
+    if coords.nelement() == 0:
+        return torch.tensor([mask.shape[0] / 2, mask.shape[1] / 2], device=mask.device)
+    weights = mask[coords[:, 0], coords[:, 1]]
+    return torch.sum(coords * weights.unsqueeze(1), dim=0) / torch.sum(weights)
+
+
+def normalized_distance(point1, point2, img_shape):
+    """optim/utils.py:40-43."""
+    shape = torch.tensor(img_shape, device=point1.device)
+    return torch.sqrt(torch.sum((point1 / shape - point2 / shape) ** 2)).item()
+
+
+class ObjPose_Opt(torch.nn.Module):
+    """The optimisation model of optim/optimizer.py:14-175 without its logging side (tensorboard writer, Phong overlay):
+    parameters rotation (6-D), translation and optionally scale of the object; `forward(loss_weights)` renders the soft
+    silhouette of the transformed object (SSRenderer -> sm_100a kernels) and sums mask (1 - soft "IoU"), centroid and
+    contact terms with the reference's weights / kick-in steps.  `human_params` / `object_params` are mappings with
+    `vertices`, `contact_verts` (+ `centroid_offset` for the human, `mask` [H,W] for the object)."""
+
+    def __init__(self, rotation_init, translation_init, scaling_init, human_params, object_params, silhouette_renderer,
+                 vars=("pose",), ctx: Context | None = None):
+        super().__init__()
+        g = lambda d, k: d[k] if isinstance(d, dict) else getattr(d, k)
+        self.step = 0
+        self.ctx = ctx
+        self.silhouette_renderer = silhouette_renderer
+        self.rotation = torch.nn.Parameter(rotation_init.clone().float(), requires_grad="pose" in vars)
+        self.translation = torch.nn.Parameter(translation_init.clone().float(), requires_grad="pose" in vars)
+        if "scale" in vars:
+            self.scale = torch.nn.Parameter(torch.as_tensor(scaling_init).float(), requires_grad=True)
+        else:
+            self.register_buffer("scale", torch.as_tensor(scaling_init).float())
+        self.register_buffer("human_contact_probs", g(human_params, "contact_verts").float())
+        self.register_buffer("object_contact_probs", g(object_params, "contact_verts").float())
+        mask = g(object_params, "mask")
+        bbox = torch.nonzero(mask)
+        lo, hi = bbox.min(dim=0)[0], bbox.max(dim=0)[0]
+        self.register_buffer("target_mask_centroid", torch.stack([(hi[0] + lo[0]) / 2, (hi[1] + lo[1]) / 2]).float())
+        self.register_buffer("human_vertices", g(human_params, "vertices").float())
+        self.register_buffer("hum_centroid_offset", g(human_params, "centroid_offset").float())
+        self.register_buffer("obj_vertices", g(object_params, "vertices").float())
+        self.register_buffer("target_mask", mask.bool().float())
+
+    def contact_loss(self, obj_verts, human_verts):
+        return contact_loss(obj_verts, human_verts, self.object_contact_probs, self.human_contact_probs, self.ctx)
+
+    def mask_loss_iou(self, current_mask):
+        """optimizer.py:171-174 (the 'union' is the plain sum of both masks, as in the reference)."""
+        return 1 - torch.sum(current_mask * self.target_mask) / torch.sum(current_mask + self.target_mask)
+
+    def forward(self, loss_weights: dict):
+        obj_vertices = apply_transformation(self.obj_vertices, self.rotation, self.translation, self.scale)
+        sil_img, depth_img = self.silhouette_renderer.render(obj_vertices + self.hum_centroid_offset, h_vertices=None)
+        current_mask = sil_img[0, ..., 3]
+        active = lambda k: k in loss_weights and self.step >= loss_weights[k]["kick_in"]
+        loss_dict = {}
+        if active("mask_loss"):
+            loss_dict["mask_loss"] = self.mask_loss_iou(current_mask)
+        current_mask_centroid = calculate_centroid(current_mask)
+        if active("centroid_loss"):
+            loss_dict["centroid_loss"] = torch.sum((current_mask_centroid - self.target_mask_centroid) ** 2)
+        if active("contact_loss"):
+            loss_dict["contact_loss"] = self.contact_loss(obj_vertices, self.human_vertices)
+        weighted = {k: v * loss_weights[k]["w"] for k, v in loss_dict.items() if loss_weights[k]["kick_in"] >= 0}
+        total = sum(weighted.values())
+        self.step += 1
+        output = {"object_vertices": obj_vertices.detach(), "current_mask": current_mask, "current_depth": depth_img[0, ..., 0],
+                  "current_mask_centroid": current_mask_centroid,
+                  "centroid_distance": normalized_distance(current_mask_centroid, self.target_mask_centroid, self.target_mask.shape),
+                  "losses": {k: float(v.detach()) for k, v in weighted.items()}}
+        return total, output
+
+
+def fit(model: ObjPose_Opt, loss_weights: dict, max_iter: int = 250, lr_rotation: float = 5.0e-2, lr_translation: float = 1.0e-2,
+        lr_scale: float = 1.0e-2, early_stop: bool = False):
+    """The Adam loop of optim/fit.py:216-290 (per-parameter learning rates of :218-224, optional early stop of :279-283).
+    -> list of per-iteration dicts (loss, weighted terms, centroid distance)."""
+    groups = [{"params": [model.rotation], "lr": lr_rotation}, {"params": [model.translation], "lr": lr_translation}]
+    if isinstance(model.scale, torch.nn.Parameter):
+        groups.append({"params": [model.scale], "lr": lr_scale})
+    optimizer = torch.optim.Adam(groups)
+    history, prev = [], 1e10
+    for _ in range(max_iter):
+        optimizer.zero_grad()
+        loss, out = model(loss_weights)
+        loss.backward()
+        optimizer.step()
+        history.append({"loss": loss.item(), "centroid_distance": out["centroid_distance"], **out["losses"]})
+        if early_stop and abs(prev - loss.item()) < 1e-6:
+            break
+        prev = loss.item()
+    return history

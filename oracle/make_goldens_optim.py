@@ -96,6 +96,28 @@ def icp_inputs(seed, n_obj, n_hum):
     return f(obj)[None], f(on)[None], f(hum)[None], f(hn)[None], f(R0), f(T0), f(s0)
 
 
+def reference_utils():
+    """rot6d_to_matrix, matrix_to_rot6d, apply_transformation, calculate_centroid out of optim/utils.py (the module imports
+    trimesh / matplotlib, absent here) and mask_loss_iou out of optim/optimizer.py, executed as they are."""
+    ns = {"torch": torch, "F": torch.nn.functional}
+    src = (REF.parent / "utils.py").read_text()
+    for n in ast.parse(src).body:
+        if isinstance(n, ast.FunctionDef) and n.name in ("rot6d_to_matrix", "matrix_to_rot6d", "apply_transformation", "calculate_centroid"):
+            exec(textwrap.dedent(ast.get_source_segment(src, n)), ns)
+    src = REF.read_text()
+    cls = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "ObjPose_Opt")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "mask_loss_iou")
+    exec(textwrap.dedent(ast.get_source_segment(src, fn)), ns)
+    return ns
+
+
+def utils_inputs():
+    g = torch.Generator().manual_seed(11)
+    return dict(rot6d=torch.randn(6, generator=g), verts=torch.randn(50, 3, generator=g), trans=torch.randn(3, generator=g),
+                scale=torch.tensor(1.3), mask=(torch.rand(20, 30, generator=g) > 0.6).float() * torch.rand(20, 30, generator=g),
+                target=(torch.rand(20, 30, generator=g) > 0.5).float(), mat=torch.linalg.qr(torch.randn(3, 3, generator=g))[0])
+
+
 ICP_CASES = {"patch": (3, 400, 700, False), "patch_scale": (4, 900, 600, True)}
 
 
@@ -115,6 +137,16 @@ def main():
             out_icp[f"{name}_{tag}_rmse"] = sol.rmse.numpy()
             out_icp[f"{name}_{tag}_iters"] = np.array(len(sol.t_history))
             out_icp[f"{name}_{tag}_converged"] = np.array(bool(sol.converged))
+    ns, u = reference_utils(), utils_inputs()
+
+    class Self:
+        target_mask = u["target"]
+    out_icp["utils_rot"] = ns["rot6d_to_matrix"](u["rot6d"]).numpy()
+    out_icp["utils_rot6d"] = ns["matrix_to_rot6d"](u["mat"]).numpy()
+    out_icp["utils_transformed"] = ns["apply_transformation"](u["verts"], u["rot6d"], u["trans"], u["scale"]).numpy()
+    out_icp["utils_centroid"] = ns["calculate_centroid"](u["mask"]).numpy()
+    out_icp["utils_centroid_empty"] = ns["calculate_centroid"](torch.zeros(6, 8)).numpy()
+    out_icp["utils_mask_loss"] = ns["mask_loss_iou"](Self, u["mask"]).numpy()
     np.savez_compressed(OUT.with_name("icp.npz"), **out_icp)
     print({k: (v.shape, float(np.abs(v).max())) for k, v in out_icp.items() if k.endswith(("_s", "_rmse", "_iters", "_T"))})
     fn = reference_contact_loss()

@@ -54,3 +54,22 @@ def test_product_wrapper_refuses_cpu():
 
     with pytest.raises((RuntimeError, ValueError)):
         PO.contact_loss(torch.zeros(4, 3), torch.zeros(5, 3), torch.ones(4), torch.ones(5))
+
+
+def test_pose_utils_match_reference_goldens():
+    """rot6d / transformation / centroid / mask-loss helpers of interactvlm_b200.optim (plain torch, run on CPU here) against
+    outputs of the reference's own functions (optim/utils.py, optim/optimizer.py:171-174)."""
+    from interactvlm_b200 import optim as PO
+    from oracle.make_goldens_optim import utils_inputs
+
+    G = np.load(Path(__file__).parent / "golden" / "icp.npz")
+    u = utils_inputs()
+    assert np.abs(PO.rot6d_to_matrix(u["rot6d"]).numpy() - G["utils_rot"]).max() < 1e-6
+    assert np.abs(PO.matrix_to_rot6d(u["mat"]).numpy() - G["utils_rot6d"]).max() == 0
+    assert np.abs(PO.apply_transformation(u["verts"], u["rot6d"], u["trans"], u["scale"]).numpy() - G["utils_transformed"]).max() < 1e-6
+    assert np.abs(PO.calculate_centroid(u["mask"]).numpy() - G["utils_centroid"]).max() < 1e-5
+    assert np.abs(PO.calculate_centroid(torch.zeros(6, 8)).numpy() - G["utils_centroid_empty"]).max() == 0
+
+    class M:
+        target_mask = u["target"]
+    assert abs(PO.ObjPose_Opt.mask_loss_iou(M, u["mask"]).item() - float(G["utils_mask_loss"])) < 1e-6

@@ -176,3 +176,21 @@ def test_ssrenderer_mask_loss_drives_translation(ctx):
         loss.backward()
         opt.step()
     assert loss.item() < first - 0.05 and t.detach().abs().max().item() < 0.06, (first, loss.item(), t)
+
+
+def test_pose_refinement_end_to_end(ctx):
+    """optim/fit.py's flow on a synthetic scene (examples/demo_synthetic_fit.py): contact ICP initialisation, then Adam on
+    rotation / translation with the mask + centroid + contact terms; the loss falls and the object moves towards the pose
+    that produced the target mask."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("demo_fit", str(Path(__file__).resolve().parents[1] / "examples" / "demo_synthetic_fit.py"))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    model, hist, info = demo.run(iters=100, size=96)
+    assert len(hist) == 100 and all(np.isfinite(h["loss"]) for h in hist)
+    # the reference's mask term is 1 - I / (A + B) >= 0.5 and the contact term is a mean distance: both have a floor
+    assert hist[-1]["loss"] < 0.8 * hist[0]["loss"], (hist[0], hist[-1])
+    assert hist[-1]["mask_loss"] < hist[0]["mask_loss"] and hist[-1]["contact_loss"] < hist[0]["contact_loss"]
+    assert hist[-1]["centroid_distance"] < 0.3 * hist[0]["centroid_distance"]
+    assert info["t_err_end"] < 0.25 * info["t_err_start"] and info["t_err_end"] < 0.04, info
