@@ -39,6 +39,27 @@ def test_rasteriser_bit_exact_vs_oracle(ctx, kind, size, views):
     assert np.array_equal(r["p2v"].cpu().numpy(), want_p2v)
 
 
+def test_rasteriser_non_square_and_pinhole_camera_bit_exact(ctx):
+    """Non-square image + the PerspectiveCameras set-up of optim/renderer.py (pixel focal length, off-centre principal
+    point): the longer side spans [-W/H, W/H] in NDC; same bit-exact agreement with the oracle."""
+    from interactvlm_b200 import ops
+    from interactvlm_b200 import optim as PO
+
+    v, f = S.make_test_mesh("torus")
+    v = (v * 1.2 + np.array([0.1, -0.05, 2.5])).astype(np.float32)
+    H, W = 120, 200
+    cam = PO.perspective_camera((150.0, 140.0), (W / 2 + 7.0, H / 2 - 5.0), (H, W))
+    vt, ft = torch.from_numpy(v).cuda(), torch.from_numpy(f.astype(np.int32)).cuda()
+    r = ops.rasterize_mesh(ctx, vt, ft, [cam], H, W, want_zbuf=True)
+    pix, bary, zb, skipped = O.rasterize(v, f, cam, H, W)
+    assert (pix >= 0).mean() > 0.05 and np.array_equal(r["pix_to_face"][0].cpu().numpy(), pix)
+    assert np.array_equal(r["bary"][0].cpu().numpy(), bary) and np.array_equal(r["zbuf"][0].cpu().numpy(), zb)
+    rows, cols = np.nonzero(pix >= 0)
+    # OpenCV-style image axes (R = diag(-1,-1,1) undoes pytorch3d's +X-left / +Y-up): world +x and a principal point right of
+    # the centre move the object right, world -y and a principal point above the centre move it up
+    assert cols.mean() > W / 2 and rows.mean() < H / 2
+
+
 def test_reference_api_project_vertices_and_create_mask(ctx):
     v, f = S.make_test_mesh("blob")
     v = O.normalize_mesh(v)
