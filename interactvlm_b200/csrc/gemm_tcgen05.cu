@@ -582,7 +582,7 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
                  "gemm: split-K accumulates raw fp32 (no bias/act/residual)");
 
     // Small token counts are weight streaming (HBM-bound): dedicated kernel built around the weight stream.
-    if (h->small_m_variant == 0 && a->M <= 64 && a->N <= h->gv_max_n && a->force_swap >= 0 && a->row_map == nullptr && a->k_splits <= 1 &&
+    if (h->small_m_variant == 0 && a->M <= h->gv_max_m && a->N <= h->gv_max_n && a->force_swap >= 0 && a->row_map == nullptr && a->k_splits <= 1 &&
         a->K % 32 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0 && a->res_row_mod == 0 &&
         (reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0)
         return launch_gemv_small_m(h, a, stream);

@@ -10,7 +10,9 @@ sys.path.insert(0, str(ROOT))
 from interactvlm_b200.ops import Context  # noqa: E402
 
 ctx = Context(0)
-B, D, F, H, hd, L = 8, 5120, 13824, 40, 128, 340
+import os  # noqa: E402
+
+B, D, F, H, hd, L = int(os.environ.get("PROF_B", "8")), 5120, 13824, 40, 128, 340
 g = torch.Generator(device="cuda").manual_seed(0)
 rnd = lambda *s, sc=1.0: (torch.randn(*s, device="cuda", generator=g) * sc).bfloat16()
 NW = 4
@@ -90,6 +92,15 @@ def layer_chain(i):
     return ctx.gemm(y, wd[i % NW], residual=x1)
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "variants":
+    gemms = {k: v for k, v in ops.items() if k.startswith("gemm") and "nosplit" not in k}
+    for label, v in (("gemv (N <= 8192) + swapped tcgen05", 0), ("swapped tcgen05 + split-K everywhere", 1)):
+        ctx.set_option("small_m_variant", v)
+        print(f"B={B} {label}: " + "  ".join(f"{n[5:]} {graph_time(fn):6.2f}us" for n, (fn, _) in gemms.items()), flush=True)
+    ctx.set_option("small_m_variant", 0)
+    print(f"B={B} decode_attention {graph_time(ops['decode_attention'][0]):6.2f}us rmsnorm {graph_time(ops['rmsnorm'][0]):5.2f}us "
+          f"rope {graph_time(ops['rope_kv_store'][0]):5.2f}us silu {graph_time(ops['silu_mul'][0]):5.2f}us", flush=True)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "chain":
     ref = None
     for pdl in (0, 1, 0, 1):
