@@ -50,6 +50,7 @@ extern "C" int ivlm_set_option(ivlm_handle h, const char* name, int32_t value) {
     if (std::string(name) == "gv_rows8_max_n") { h->gv_rows8_max_n = value; return IVLM_OK; }
     if (std::string(name) == "gv_warps") { h->gv_warps = value; return IVLM_OK; }
     if (std::string(name) == "gv_max_n") { h->gv_max_n = value; return IVLM_OK; }
+    if (std::string(name) == "fused_split_force") { h->fused_split_force = value; return IVLM_OK; }
     if (std::string(name) == "gv_max_m") { h->gv_max_m = value; return IVLM_OK; }
     if (std::string(name) == "small_m_variant") {
         h->small_m_variant = value;

@@ -616,10 +616,14 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
     p.fused_split = 0;
     if (!split && swap && h->ws != nullptr && a->k_splits == 0) {
         const int tiles = p.num_m_tiles * p.num_n_tiles;
-        // cost in k-block units: waves x (k-blocks per unit + ~6 k-blocks of pipeline fill / drain / reduce per unit)
+        // cost in k-block units: waves x (k-blocks per unit + pipeline fill / drain / partial-tile exchange per unit).  The
+        // exchange grows with the token tile: ~6 k-blocks at 16 tokens, 4x / 16x that at 32 / 64 (measured with
+        // tools/prof_decode.py splits: at 32 / 64 tokens splitting gate-up in two costs 73 / 87 us against 60 / 61 unsplit,
+        // while the 40-tile o / down projections still gain from a 3-way split)
         int best = 1;
+        const double per_unit = bn <= 16 ? 6.0 : 6.0 * (bn / 16.0) * (bn / 16.0);
         auto cost_of = [&](int sp) {
-            return (double)((tiles * sp + h->num_sms - 1) / h->num_sms) * ((double)p.k_blocks / sp + 6.0);
+            return (double)((tiles * sp + h->num_sms - 1) / h->num_sms) * ((double)p.k_blocks / sp + per_unit);
         };
         double best_cost = cost_of(1);
         for (int sp = 2; sp <= 8; ++sp) {
@@ -627,6 +631,7 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
             const double cost = cost_of(sp);
             if (cost < best_cost * 0.9) { best_cost = cost; best = sp; }
         }
+        if (h->fused_split_force > 0) best = h->fused_split_force;  // A/B knob (tools/prof_decode.py splits)
         const size_t need = (size_t)tiles * best * BM * bn * sizeof(float) + (size_t)tiles * sizeof(int) + 256;
         if (best > 1 && need <= h->ws_bytes - IVLM_WS_COUNTER_BYTES && (size_t)tiles * sizeof(int) <= IVLM_WS_COUNTER_BYTES) {
             p.k_splits = best;

@@ -88,6 +88,7 @@ struct ivlm_ctx {
     int gv_rows8_max_n = 0;       // layers with N <= this use 8 rows per CTA (A/B knob; 16 rows measured better)
     int gv_warps = 10;            // warps per CTA (0: heuristic)
     int gv_max_n = 8192;          // layers wider than this go to the swapped tcgen05 kernel instead
+    int fused_split_force = 0;    // > 0: fused split-K factor of the swapped GEMM instead of the cost model's choice (A/B knob)
     int gv_max_m = 8;             // token counts above this too: at 16 / 32 / 64 tokens the swapped tcgen05 kernel wins (o_proj 20 / 29 / 33 us
                                   // against 23 / 48 / 52, down_proj 40 / 57 / 62 against 56 / 136 / 130; tools/prof_decode.py variants)
     int small_m_variant = 0;      // 0: weight-streaming mma.sync kernel for token counts <= 64; 1: swapped-operand tcgen05 path

@@ -92,6 +92,16 @@ def layer_chain(i):
     return ctx.gemm(y, wd[i % NW], residual=x1)
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "splits":
+    ctx.set_option("small_m_variant", 1)
+    for name, wl, xin in (("qkv", wqkv, x), ("o", wo, x), ("gateup", wgu, x), ("down", wd, xf)):
+        row = []
+        for ks in (0, 1, 2, 3, 4, 6):
+            ctx.set_option("fused_split_force", ks)   # 0: the cost model's choice
+            row.append(f"split {ks or 'auto'}: {graph_time(lambda i, wl=wl, xin=xin: ctx.gemm(xin, wl[i % NW])):6.2f}us")
+        ctx.set_option("fused_split_force", 0)
+        print(f"B={B} {name}: " + "  ".join(row), flush=True)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "variants":
     gemms = {k: v for k, v in ops.items() if k.startswith("gemm") and "nosplit" not in k}
     for label, v in (("gemv (N <= 8192) + swapped tcgen05", 0), ("swapped tcgen05 + split-K everywhere", 1)):
