@@ -1,23 +1,21 @@
 """GPU-box helper: time of the rasteriser (4 views x 1024^2, the reference's RENDER_IMG_SIZE) for meshes of growing size,
 CUDA events around the whole ivlm_rasterize_mesh call (it contains one stream synchronisation), plus the Phong shader,
-against the algorithmic output bytes (40 B per pixel: face id, 3 barycentrics, 3 int64 vertex ids)."""
+against the algorithmic output bytes (40 B per pixel: face id, 3 barycentrics, 3 int64 vertex ids).  (The CPU-oracle times quoted
+in profiles/r1_raster.txt were taken with tests-only code: tools/ does not import oracle/.)"""
 import sys
-import time
 from pathlib import Path
 
-import numpy as np
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from interactvlm_b200 import ops, render as R, synthetic as S  # noqa: E402
-from oracle import raster as O  # noqa: E402
 
 ctx = ops.Context(0)
 views = list(R.OBJECT_VIEWS_4.values())
 size = 1024
 for n_lat, n_lon in ((24, 48), (96, 192), (256, 512), (512, 1024)):
     v, f = S.make_test_mesh("blob", n_lat=n_lat, n_lon=n_lon)
-    v = O.normalize_mesh(v)
+    v = R.normalize_mesh(torch.from_numpy(v)).numpy()
     r = R.rasterize_views((v, f), views, (size, size), ctx=ctx)
     vt, ft, cams = r["verts"], r["faces"], r["cams"]
     col = torch.full_like(vt, 0.8)
@@ -37,8 +35,4 @@ for n_lat, n_lon in ((24, 48), (96, 192), (256, 512), (512, 1024)):
     ms, ms_sh = e0.elapsed_time(e1) / n, e1.elapsed_time(e2) / n
     nbytes = 4 * size * size * 40
     line = f"{len(f):8d} faces: rasterise 4x{size}^2 {ms:7.3f} ms ({nbytes / ms / 1e6:7.1f} GB/s of output), phong {ms_sh:6.3f} ms, coverage {(out['pix_to_face'] >= 0).float().mean().item():.3f}"
-    if len(f) < 40000:
-        t0 = time.perf_counter()
-        O.rasterize(v, f, cams[0], size, size)
-        line += f" | CPU oracle (numpy, 1 thread) {4 * (time.perf_counter() - t0) * 1e3:8.0f} ms for 4 views"
     print(line, flush=True)
