@@ -274,24 +274,36 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         named_bar_sync(1, EPI_THREADS);
                         const int seg = et & 7;
                         const int col = n0 + slab * 64 + seg * 8;
+                        // all row-map lookups first, then all residual loads, then add + store: the loads of the four rows a
+                        // thread moves are in flight together instead of one dependent chain per row
+                        constexpr int NIT = BM * 8 / EPI_THREADS;
+                        int orow_[NIT];
+                        uint4 r4_[NIT];
 #pragma unroll
-                        for (int i = 0; i < BM * 8 / EPI_THREADS; ++i) {
-                            const int rl = i * (EPI_THREADS / 8) + (et >> 3);
-                            const int grow = m0 + rl;
-                            if (grow >= p.M || col >= p.N) continue;
-                            int orow = grow;
-                            if (p.row_map != nullptr) {
-                                orow = p.row_map[grow];
-                                if (orow < 0) continue;
+                        for (int i = 0; i < NIT; ++i) {
+                            const int grow = m0 + i * (EPI_THREADS / 8) + (et >> 3);
+                            int orow = (grow < p.M && col < p.N) ? grow : -1;
+                            if (orow >= 0 && p.row_map != nullptr) orow = p.row_map[grow];
+                            orow_[i] = orow;
+                        }
+                        if (p.res != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < NIT; ++i) {
+                                if (orow_[i] < 0) continue;
+                                const int rrow = p.res_row_mod > 0 ? (orow_[i] % p.res_row_mod) : orow_[i];
+                                r4_[i] = *reinterpret_cast<const uint4*>(p.res + (long long)rrow * p.res_rs + col);
                             }
+                        }
+#pragma unroll
+                        for (int i = 0; i < NIT; ++i) {
+                            if (orow_[i] < 0) continue;
+                            const int rl = i * (EPI_THREADS / 8) + (et >> 3);
                             uint4 q = *reinterpret_cast<const uint4*>(buf + rl * 128 + ((seg ^ (rl & 7)) << 4));
                             if (p.res != nullptr) {
-                                const int rrow = p.res_row_mod > 0 ? (orow % p.res_row_mod) : orow;
-                                const uint4 r4 = *reinterpret_cast<const uint4*>(p.res + (long long)rrow * p.res_rs + col);
-                                q.x = add_bf16x2(q.x, r4.x); q.y = add_bf16x2(q.y, r4.y);
-                                q.z = add_bf16x2(q.z, r4.z); q.w = add_bf16x2(q.w, r4.w);
+                                q.x = add_bf16x2(q.x, r4_[i].x); q.y = add_bf16x2(q.y, r4_[i].y);
+                                q.z = add_bf16x2(q.z, r4_[i].z); q.w = add_bf16x2(q.w, r4_[i].w);
                             }
-                            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (long long)orow * p.out_rs + col) = q;
+                            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (long long)orow_[i] * p.out_rs + col) = q;
                         }
                     }
                     continue;
