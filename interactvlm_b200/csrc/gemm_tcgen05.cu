@@ -82,11 +82,8 @@ struct GemmCfg {
 
 // Phase 1 of the staged epilogue for one warp: 32 accumulator rows x 32 columns -> bf16 -> swizzled slab.
 template <int ACT>
-IVLM_DEVINL void epi_stage_chunk(uint32_t taddr, const float* __restrict__ bs, bool has_bias, uint8_t* buf, int rloc,
+IVLM_DEVINL void epi_stage_chunk(const uint32_t (&raw)[32], const float* __restrict__ bs, bool has_bias, uint8_t* buf, int rloc,
                                  int seg0) {
-    uint32_t raw[32];
-    tmem_ld_32x32(taddr, raw);
-    tmem_ld_wait();
     float x[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -254,19 +251,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     constexpr int NSLAB = BN / 64;
                     const int rloc = quad * 32 + lane;
                     const bool has_bias = p.bias != nullptr;
+                    // the TMEM read of slab s+1 is issued as soon as slab s has been converted, so its latency runs under
+                    // the barrier and the global stores of slab s
+                    const uint32_t taddr0 = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN + chalf * 32);
+                    uint32_t raw[32];
+                    tmem_ld_32x32(taddr0, raw);
 #pragma unroll 1
                     for (int slab = 0; slab < NSLAB; ++slab) {
                         uint8_t* buf = epi_stage + (slab & 1) * (BM * 128);
-                        const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN + slab * 64 + chalf * 32);
                         const float* bs = bias_s + slab * 64 + chalf * 32;
+                        tmem_ld_wait();
                         switch (p.act) {
-                            case ACT_GELU: epi_stage_chunk<ACT_GELU>(taddr, bs, has_bias, buf, rloc, chalf * 4); break;
-                            case ACT_QUICK_GELU: epi_stage_chunk<ACT_QUICK_GELU>(taddr, bs, has_bias, buf, rloc, chalf * 4); break;
-                            case ACT_RELU: epi_stage_chunk<ACT_RELU>(taddr, bs, has_bias, buf, rloc, chalf * 4); break;
-                            case ACT_SILU: epi_stage_chunk<ACT_SILU>(taddr, bs, has_bias, buf, rloc, chalf * 4); break;
-                            default: epi_stage_chunk<ACT_NONE>(taddr, bs, has_bias, buf, rloc, chalf * 4); break;
+                            case ACT_GELU: epi_stage_chunk<ACT_GELU>(raw, bs, has_bias, buf, rloc, chalf * 4); break;
+                            case ACT_QUICK_GELU: epi_stage_chunk<ACT_QUICK_GELU>(raw, bs, has_bias, buf, rloc, chalf * 4); break;
+                            case ACT_RELU: epi_stage_chunk<ACT_RELU>(raw, bs, has_bias, buf, rloc, chalf * 4); break;
+                            case ACT_SILU: epi_stage_chunk<ACT_SILU>(raw, bs, has_bias, buf, rloc, chalf * 4); break;
+                            default: epi_stage_chunk<ACT_NONE>(raw, bs, has_bias, buf, rloc, chalf * 4); break;
                         }
-                        if (slab == NSLAB - 1) {  // accumulator fully read: hand it back to the MMA warp
+                        if (slab + 1 < NSLAB) {
+                            tmem_ld_32x32(taddr0 + uint32_t((slab + 1) * 64), raw);
+                        } else {  // accumulator fully read: hand it back to the MMA warp
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&tempty_bar[as]);
