@@ -787,33 +787,34 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
         }
         mbar_wait(s_full, 0);
         tc_fence_after();
-        // ---- pass 1: x = s*scale + bias (log2 domain) written back in place, row max
+        // ---- pass 1: x = s*scale + bias (log2 domain) written back in place, row max.  Both passes are software
+        // pipelined over two register buffers: the TMEM read of chunk c+1 is issued before chunk c is processed, so its
+        // latency hides under the arithmetic (two softmax warps per scheduler do not hide it otherwise).
         float mx = -INFINITY;
-#define WIN_PASS1(C0)                                                               \
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(lane_addr, ra);
+#define WIN_PASS1(C0, CUR, NXT, NEXT_LD)                                            \
         {                                                                           \
-            uint32_t raw[32];                                                       \
-            tmem_ld_32x32(lane_addr + C0, raw);                                     \
             tmem_ld_wait();                                                         \
-            mx = win_scores<C0, 32>(raw, rh, rw, p.scale_log2, mx);                 \
-            tmem_st_32x32(lane_addr + C0, raw);                                     \
+            NEXT_LD;                                                                \
+            mx = win_scores<C0, 32>(CUR, rh, rw, p.scale_log2, mx);                 \
+            tmem_st_32x32(lane_addr + C0, CUR);                                     \
         }
-        WIN_PASS1(0) WIN_PASS1(32) WIN_PASS1(64) WIN_PASS1(96) WIN_PASS1(128) WIN_PASS1(160)
+        WIN_PASS1(0, ra, rb, tmem_ld_32x32(lane_addr + 32, rb))
+        WIN_PASS1(32, rb, ra, tmem_ld_32x32(lane_addr + 64, ra))
+        WIN_PASS1(64, ra, rb, tmem_ld_32x32(lane_addr + 96, rb))
+        WIN_PASS1(96, rb, ra, tmem_ld_32x32(lane_addr + 128, ra))
+        WIN_PASS1(128, ra, rb, tmem_ld_32x32(lane_addr + 160, rb))
+        uint32_t rc[16];
+        WIN_PASS1(160, rb, ra, tmem_ld_32x16(lane_addr + 192, rc))
 #undef WIN_PASS1
-        {
-            uint32_t raw[16];
-            tmem_ld_32x16(lane_addr + 192, raw);
-            tmem_ld_wait();
-            mx = win_scores<192, 16>(raw, rh, rw, p.scale_log2, mx);
-            tmem_st_32x16(lane_addr + 192, raw);
-        }
+        tmem_ld_wait();
+        mx = win_scores<192, 16>(rc, rh, rw, p.scale_log2, mx);
+        tmem_st_32x16(lane_addr + 192, rc);
         tmem_st_wait();
         // ---- pass 2: p = 2^(x - max) -> bf16 -> swizzled P (aliases the dead Q / K tiles)
         float sum = 0.f;
-#pragma unroll
-        for (int c0 = 0; c0 < 192; c0 += 32) {
-            uint32_t raw[32];
-            tmem_ld_32x32(lane_addr + c0, raw);
-            tmem_ld_wait();
+        auto exp_chunk = [&](const uint32_t(&raw)[32], int c0) {
             uint8_t* row = smem + (c0 >> 6) * 16384 + r * 128;
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
@@ -828,10 +829,15 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
                 const int c16 = ((c0 & 63) >> 3) + j8;
                 *reinterpret_cast<uint4*>(row + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-        }
+        };
+        tmem_ld_32x32(lane_addr, ra);
+        tmem_ld_wait(); tmem_ld_32x32(lane_addr + 32, rb);  exp_chunk(ra, 0);
+        tmem_ld_wait(); tmem_ld_32x32(lane_addr + 64, ra);  exp_chunk(rb, 32);
+        tmem_ld_wait(); tmem_ld_32x32(lane_addr + 96, rb);  exp_chunk(ra, 64);
+        tmem_ld_wait(); tmem_ld_32x32(lane_addr + 128, ra); exp_chunk(rb, 96);
+        tmem_ld_wait(); tmem_ld_32x32(lane_addr + 160, rb); exp_chunk(ra, 128);
+        tmem_ld_wait(); tmem_ld_32x16(lane_addr + 192, rc); exp_chunk(rb, 160);
         {
-            uint32_t raw[16];
-            tmem_ld_32x16(lane_addr + 192, raw);
             tmem_ld_wait();
             uint8_t* row = smem + WN_OFF_P3 + r * 32;
 #pragma unroll
@@ -839,8 +845,8 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
                 uint32_t pk[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float p0 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e]) - mx);
-                    const float p1 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e + 1]) - mx);
+                    const float p0 = ex2_approx(__uint_as_float(rc[j8 * 8 + 2 * e]) - mx);
+                    const float p1 = ex2_approx(__uint_as_float(rc[j8 * 8 + 2 * e + 1]) - mx);
                     sum += p0 + p1;
                     pk[e] = pack_bf16x2(p0, p1);
                 }
