@@ -66,7 +66,7 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
 // Register-resident variant for D = 256 * VPL (SAM 1280, CLIP 1024, decoder 256): the row is read from HBM exactly once
 // (VPL 16-byte vectors per lane), statistics and the normalised output come from registers.
 template <int VPL>
-__global__ void __launch_bounds__(256) layernorm_reg_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+__global__ void __launch_bounds__(256, 6) layernorm_reg_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                                             const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
                                                             long long out_rows, float eps, const int* __restrict__ row_map,
                                                             int act) {
@@ -83,37 +83,50 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const bf16* __restri
         return;
     }
     const uint4* xr = reinterpret_cast<const uint4*>(x + src * D);
-    float v[VPL][8];
+    // the row stays PACKED in registers (VPL x 4 instead of VPL x 8 words) and is unpacked in each of the three passes: the
+    // kernel is HBM-bound and 40 instead of 70 registers double the resident warps (loads in flight per SM)
+    uint4 q[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) q[k] = xr[lane + 32 * k];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-        const uint4 q = xr[lane + 32 * k];
-        const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
-        v[k][0] = a.x; v[k][1] = a.y; v[k][2] = b.x; v[k][3] = b.y; v[k][4] = c.x; v[k][5] = c.y; v[k][6] = d.x; v[k][7] = d.y;
+        const float2 a = unpack_bf16x2(q[k].x), b = unpack_bf16x2(q[k].y), c = unpack_bf16x2(q[k].z), d = unpack_bf16x2(q[k].w);
         s += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
     }
     const float mean = warp_sum(s) / (float)D;
+    // opaque to the optimiser: without it the unpacked floats of the first pass are kept live for the next two
+#define IVLM_LN_REPACK()                                                                                   \
+    _Pragma("unroll") for (int k = 0; k < VPL; ++k)                                                        \
+        asm volatile("" : "+r"(q[k].x), "+r"(q[k].y), "+r"(q[k].z), "+r"(q[k].w))
+    IVLM_LN_REPACK();
     float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < VPL; ++k)
+    for (int k = 0; k < VPL; ++k) {
+        const uint32_t w4[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float t = v[k][j] - mean;
-            ss += t * t;
+        for (int j = 0; j < 4; ++j) {
+            const float2 t2 = unpack_bf16x2(w4[j]);
+            const float t0 = t2.x - mean, t1 = t2.y - mean;
+            ss += t0 * t0;
+            ss += t1 * t1;
         }
+    }
     const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
+    IVLM_LN_REPACK();
+#undef IVLM_LN_REPACK
     const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
     const uint4* b4 = reinterpret_cast<const uint4*>(beta);
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
         const uint4 g = g4[lane + 32 * k], b = b4[lane + 32 * k];
-        const uint32_t gi[4] = {g.x, g.y, g.z, g.w}, bi[4] = {b.x, b.y, b.z, b.w};
+        const uint32_t xi[4] = {q[k].x, q[k].y, q[k].z, q[k].w}, gi[4] = {g.x, g.y, g.z, g.w}, bi[4] = {b.x, b.y, b.z, b.w};
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float2 gv = unpack_bf16x2(gi[j]), bv = unpack_bf16x2(bi[j]);
-            float r0 = (v[k][2 * j] - mean) * rstd * gv.x + bv.x;
-            float r1 = (v[k][2 * j + 1] - mean) * rstd * gv.y + bv.y;
+            const float2 xv = unpack_bf16x2(xi[j]), gv = unpack_bf16x2(gi[j]), bv = unpack_bf16x2(bi[j]);
+            float r0 = (xv.x - mean) * rstd * gv.x + bv.x;
+            float r1 = (xv.y - mean) * rstd * gv.y + bv.y;
             if (act != ACT_NONE) {
                 r0 = apply_act(bf16_round(r0), act);
                 r1 = apply_act(bf16_round(r1), act);
