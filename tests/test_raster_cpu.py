@@ -152,3 +152,43 @@ def test_soft_silhouette_oracle_gradient_is_the_numerical_one():
     hard, _ = O.soft_silhouette(v, f, cam, 32, 48, sigma=1e-7, blur_radius=0.0)
     pix, _, _, _ = O.rasterize(v.astype(np.float32), f, cam, 32, 48)
     assert ((hard > 0.5) == (pix >= 0)).mean() > 0.995
+
+
+def test_rasteriser_oracle_agrees_with_independent_ray_casting():
+    """pytorch3d is absent, so the oracle cannot be pinned to it; as an independent derivation, cast a ray through every
+    pixel centre (float64 Moller-Trumbore against the view-space triangles): the nearest hit must be the oracle's face, its
+    3-D barycentrics the oracle's perspective-corrected ones, its depth the oracle's zbuf."""
+    v, f = S.make_test_mesh("blob", n_lat=10, n_lon=16)
+    v = O.normalize_mesh(v)
+    H = W = 64
+    for params in (VIEWS[0], VIEWS[2], (2.0, 315.0, 135.0, 0.0, 0.3)):
+        cam = O.camera(params)
+        pix, bary, zbuf, _ = O.rasterize(v, f, cam, H, W)
+        view = v.astype(np.float64) @ cam["R"].astype(np.float64) + cam["T"].astype(np.float64)
+        tri = view[f]                                              # [Nf,3,3]
+        ys, xs = O.pixel_ndc(H, W, np.float64), O.pixel_ndc(W, H, np.float64)
+        s = float(cam["s"])
+        d = np.stack(np.broadcast_arrays(xs[None, :] / s, ys[:, None] / s, np.ones((H, W))), -1).reshape(-1, 3)   # rays from the origin
+        e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+        pv = np.cross(d[:, None, :], e2[None])                     # [P,Nf,3]
+        det = (pv * e1[None]).sum(-1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / det
+            tv = -tri[None, :, 0, :]                                # origin - v0
+            u = (tv * pv).sum(-1) * inv
+            qv = np.cross(tv, e1[None])
+            w = (d[:, None, :] * qv).sum(-1) * inv
+            t = (e2[None] * qv).sum(-1) * inv
+        hit = (np.abs(det) > 1e-14) & (u > 0) & (w > 0) & (u + w < 1) & (t > 0)
+        t_hit = np.where(hit, t, np.inf)
+        best = t_hit.argmin(1)
+        any_hit = np.isfinite(t_hit.min(1))
+        ray_face = np.where(any_hit, best, -1).reshape(H, W)
+        agree = ray_face == pix
+        assert agree.mean() > 0.995, agree.mean()                   # pixel centres on an edge may go either way
+        sel = agree & (pix >= 0)
+        idx = np.nonzero(sel.reshape(-1))[0]
+        bu, bw = u[idx, best[idx]], w[idx, best[idx]]
+        ray_bary = np.stack([1 - bu - bw, bu, bw], -1)
+        assert np.abs(ray_bary - bary[sel]).max() < 2e-4
+        assert np.abs(t[idx, best[idx]] - zbuf[sel]).max() < 2e-5   # ray direction has unit z: t is the view-space depth
