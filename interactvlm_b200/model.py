@@ -655,8 +655,7 @@ class InteractVLMForCausalLM:
         (`ivlm_rows_differ`) and with the other views of the call; only unseen views go through the encoder, and their
         embeddings are the ones the encoder would produce anyway (its rows do not depend on the batch composition), so
         results are bit-identical.  Costs one small device->host read per call; entries are never evicted."""
-        if not self._emulated:
-            self._view_cache = dict(max=int(max_entries), inputs=None, embs=None, hits=0, misses=0)
+        self._view_cache = dict(max=int(max_entries), inputs=None, embs=None, hits=0, misses=0)
         return self
 
     def clear_view_cache(self):

@@ -210,6 +210,11 @@ class EmuContext:
         self.launches += 1
         return x[idx.long()]
 
+    def rows_differ(self, x, ref):
+        self.launches += 1
+        a, b = x.reshape(x.shape[0], -1), ref.reshape(ref.shape[0], -1)
+        return (a.view(torch.int16)[:, None, :] != b.view(torch.int16)[None, :, :]).any(-1).to(torch.int32)
+
     def rope_kv_store(self, qkv, positions, slot_map, cos_t, sin_t, H, hd, k_cache=None, v_cache=None, want_kv=True,
                       q_out=None, page_size=16):
         self.launches += 1

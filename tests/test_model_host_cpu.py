@@ -73,6 +73,34 @@ def test_batch_of_two_and_missing_seg(setup):
     assert np.abs(out["pred_contact_3d"].numpy() - ref["pred_contact_3d"].numpy()).max() < 0.08
 
 
+def test_view_cache_bookkeeping(setup):
+    """Host logic of the encoder view cache (which views are encoded, where their embeddings are filed, how the batch is
+    re-assembled) with the emulated kernels: identical outputs, repeated views encoded once."""
+    cfg, sd, model, _ = setup
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 3)
+    sam = sam.clone()
+    sam[1] = sam[0]
+    sam[2, 0] = sam[0, 2]
+    args = (clip, sam, ids, cam, [SIZE] * 3, [SIZE] * 3)
+    base = model.evaluate(*args, max_new_tokens=ans.shape[1], scripted=ans)
+    encoded = []
+    orig = model.eng.sam_encode
+    model.eng.sam_encode = lambda x: (encoded.append(x.shape[0]), orig(x))[1]
+    try:
+        model.enable_view_cache(max_entries=6)
+        for call in range(2):
+            out = model.evaluate(*args, max_new_tokens=ans.shape[1], scripted=ans)
+            assert torch.equal(out["pred_contact_3d"], base["pred_contact_3d"])
+            assert all(torch.equal(a, b) for a, b in zip(out["pred_masks"], base["pred_masks"]))
+        assert sum(encoded) == 7 + 1                       # 7 distinct views, 6 cached, the 7th re-encoded on the second call
+        assert model._view_cache["hits"] == 11 and model._view_cache["inputs"].shape[0] == 6
+        model.clear_view_cache()
+        assert model._view_cache["inputs"] is None and model._view_cache["hits"] == 0
+    finally:
+        model.eng.sam_encode = orig
+        model._view_cache = None
+
+
 def test_model_forward_teacher_forced(setup):
     cfg, sd, model, (p2v, bary) = setup
     ids, ans, clip, sam, cam = tiny_inputs(cfg, 1)
