@@ -131,15 +131,37 @@ class _Weights:
         # [SEG] projection, camera gate
         self.fc = (g("model.text_hidden_fcs.0.0.weight"), g("model.text_hidden_fcs.0.0.bias"),
                    g("model.text_hidden_fcs.0.2.weight"), g("model.text_hidden_fcs.0.2.bias"))
-        self.cam = None
+        # camera conditioning (components.py:491-572).  Linear(5, .) layers are stored with K zero-padded to 64 so that they
+        # run through the same GEMM kernels as everything else.
+        self.cam, self.cam_type = None, None
+        V = cfg.multiview_channels
+
+        def pad_k(wt):
+            out = torch.zeros((wt.shape[0], 64), device=wt.device, dtype=wt.dtype)
+            out[:, :wt.shape[1]] = wt
+            return out.contiguous()
+
         if cfg.multiview_cam_cond:
-            if cfg.cam_encoder_type != "vi_v1":
-                raise NotImplementedError("only cam_encoder_type='vi_v1' (the released checkpoints) is on the hot path")
-            V = cfg.multiview_channels
-            self.cam = (g("cam_pose_encoder.spatial_encoder.0.weight"), g("cam_pose_encoder.spatial_encoder.0.bias"),
-                        g("cam_pose_encoder.spatial_encoder.2.weight"), g("cam_pose_encoder.spatial_encoder.2.bias"),
-                        torch.stack([g(f"cam_pose_encoder.view_transforms.{v}.weight") for v in range(V)], 0).contiguous(),
-                        torch.stack([g(f"cam_pose_encoder.view_transforms.{v}.bias") for v in range(V)], 0).contiguous())
+            self.cam_type = cfg.cam_encoder_type
+            cpe = "cam_pose_encoder."
+            if cfg.cam_encoder_type == "vi_v1":
+                self.cam = (g(cpe + "spatial_encoder.0.weight"), g(cpe + "spatial_encoder.0.bias"),
+                            g(cpe + "spatial_encoder.2.weight"), g(cpe + "spatial_encoder.2.bias"),
+                            torch.stack([g(cpe + f"view_transforms.{v}.weight") for v in range(V)], 0).contiguous(),
+                            torch.stack([g(cpe + f"view_transforms.{v}.bias") for v in range(V)], 0).contiguous())
+            elif cfg.cam_encoder_type == "view_index":
+                self.cam = (pad_k(g(cpe + "spatial_encoder.0.weight")), g(cpe + "spatial_encoder.0.bias"),
+                            g(cpe + "spatial_encoder.2.weight"), g(cpe + "spatial_encoder.2.bias"),
+                            [g(cpe + f"view_transforms.{v}.weight") for v in range(V)],
+                            [g(cpe + f"view_transforms.{v}.bias") for v in range(V)])
+            elif cfg.cam_encoder_type == "simple":
+                self.cam = (pad_k(g(cpe + "linear1.weight")), g(cpe + "linear1.bias"))
+            else:
+                raise NotImplementedError(f"cam_encoder_type {cfg.cam_encoder_type!r} (components.py knows simple, view_index, vi_v1)")
+        self.splitter = None
+        if cfg.token_type.replace("-DifDe", "") in ("Gen-Hu-Obj", "Gen-Int"):   # AttentionSplitter (components.py:155-193)
+            self.splitter = {n: (g(f"attention_splitter.{n}.weight"), g(f"attention_splitter.{n}.bias"))
+                             for n in ("input_proj", "query_human", "query_object", "key", "value", "output_proj")}
         del self.g
 
     @staticmethod
@@ -338,14 +360,47 @@ class _Engine:
         self._greedy(st["hid_step"], out=st["next"])
 
     # ------------------------------------------------------------------ [SEG] head (a7, a10)
-    def seg_prompt(self, hidden_rows, cam_params):
-        """hidden_rows [n,D] bf16, cam_params [n,V,5] bf16 -> view-gated prompt tokens [n,V,256]."""
-        ctx, w = self.ctx, self.w
+    def seg_prompt(self, hidden_rows, cam_params, tokens=None):
+        """hidden_rows [n,D] bf16, cam_params [n,V,5] bf16, tokens [n] (which of [SEG]/[HSEG]/[OSEG] each row predicts)
+        -> prompt tokens [n,V,256]: text_hidden_fcs, camera conditioning, AttentionSplitter branch
+        (InteractVLM.py:268-294,551-556)."""
+        ctx, w, cfg = self.ctx, self.w, self.cfg
+        V = cfg.multiview_channels
         y = ctx.gemm(hidden_rows, w.fc[0], bias=w.fc[1], act=ACT_RELU)
         emb = ctx.gemm(y, w.fc[2], bias=w.fc[3])
+        n = emb.shape[0]
         if w.cam is None:
-            return emb[:, None, :].repeat(1, self.cfg.multiview_channels, 1).contiguous(), emb
-        return ctx.cam_gate(cam_params, emb, *w.cam), emb
+            prompt = emb[:, None, :].repeat(1, V, 1).contiguous()
+        elif w.cam_type == "vi_v1":
+            prompt = ctx.cam_gate(cam_params, emb, *w.cam)
+        else:
+            cam = torch.zeros((n * V, 64), device=emb.device, dtype=torch.bfloat16)
+            cam[:, :5] = cam_params.reshape(n * V, 5)
+            if w.cam_type == "simple":      # emb + relu(W cam)
+                enc = ctx.gemm(cam, w.cam[0], bias=w.cam[1], act=ACT_RELU).view(n, V, -1)
+                prompt = torch.stack([ctx.add_bcast(enc[i].contiguous(), emb[i].contiguous()) for i in range(n)])
+            else:                            # view_index: emb * W_v sigmoid(W2 relu(W1 cam))
+                h = ctx.gemm(cam, w.cam[0], bias=w.cam[1], act=ACT_RELU)
+                base = torch.sigmoid(ctx.gemm(h, w.cam[2], bias=w.cam[3])).view(n, V, -1)
+                enc = torch.stack([ctx.gemm(base[:, v].contiguous(), w.cam[4][v], bias=w.cam[5][v]) for v in range(V)], 1)
+                prompt = emb[:, None, :] * enc
+        if w.splitter is not None and tokens is not None:
+            prompt = prompt.clone()
+            for i, tok in enumerate(tokens):
+                if tok is not None and tok in (cfg.hseg_token_idx, cfg.oseg_token_idx):
+                    prompt[i] = self._attention_split(prompt[i].contiguous(), "query_human" if tok == cfg.hseg_token_idx else "query_object")
+        return prompt.contiguous(), emb
+
+    def _attention_split(self, x, query):
+        """AttentionSplitter.forward on one sample's V view tokens x [V,256] (components.py:173-193).  The six Linear layers
+        are GEMM launches; the V x V attention in between (16 scores) is a handful of torch ops on the device."""
+        ctx, sp = self.ctx, self.w.splitter
+        lin = lambda t, name: ctx.gemm(t.contiguous(), sp[name][0], bias=sp[name][1])
+        xp = lin(x, "input_proj")
+        k, v, q = lin(xp, "key"), lin(xp, "value"), lin(xp, query)
+        scores = torch.matmul(q, k.transpose(-2, -1)) / (k.shape[-1] ** 0.5)
+        attn = torch.softmax(scores.float(), dim=-1).to(torch.bfloat16)
+        return lin(torch.matmul(attn, v), "output_proj")
 
     # ------------------------------------------------------------------ prompt encoder + mask decoder (a11, a12)
     def _dec_attn(self, aw, q, k, v, heads, residual=None):
@@ -834,8 +889,8 @@ class InteractVLMForCausalLM:
         """model/InteractVLM.py:510-638.  Returns {"output_ids", "pred_masks" (list of [V,H,W] fp32 logits),
         "pred_contact_3d" ([B,6890] / [1,Nv] fp32 or None)}."""
         cfg = self.config
-        if cfg.token_type != "Gen":
-            raise NotImplementedError("token_type != 'Gen' (AttentionSplitter variants) is outside the hot path")
+        if "DifDe" in cfg.token_type:
+            raise NotImplementedError("token_type '*-DifDe' (separate human / object mask decoders) is outside the hot path")
         emb = None
         if self.overlap is not None and self._view_cache is None and not self.record_stages and self.stage_delay is None:
             output_ids, hidden, emb = self._generate_and_encode(images_clip, images, input_ids, max_new_tokens, scripted)
@@ -952,15 +1007,20 @@ class InteractVLMForCausalLM:
         cfg, eng = self.config, self.eng
         B = output_ids.shape[0]
         V = cfg.multiview_channels
-        rows, owners = [], []
+        rows, owners, tokens = [], [], []
+        seg_ids = [cfg.seg_token_idx]
+        if cfg.token_type.replace("-DifDe", "") in ("Gen-Hu-Obj", "Gen-Int"):   # InteractVLM.py:535-543
+            seg_ids += [t for t in (cfg.hseg_token_idx, cfg.oseg_token_idx) if t is not None]
+        seg_ids_t = torch.tensor(seg_ids)
         for b in range(B):
-            js = (output_ids[b] == cfg.seg_token_idx).nonzero().flatten().tolist()
-            r = [j - 1 + cfg.img_emb_len for j in js if j >= 1]
+            js = [j for j in torch.isin(output_ids[b].cpu(), seg_ids_t).nonzero().flatten().tolist() if j >= 1]
+            r = [j - 1 + cfg.img_emb_len for j in js]
             if len(r) > 1:
                 raise NotImplementedError("multi-view decoding supports one [SEG] per sample (SURVEY.md section 0.5)")
             if r:
                 rows.append(b * hidden.shape[1] + r[0])
                 owners.append(b)
+                tokens.append(int(output_ids[b, js[0]]))
         if image_embeddings is None:
             image_embeddings = self.get_visual_embs(images)  # computed for every sample, like the reference (:578)
         self._mark("sam_encoder")
@@ -969,7 +1029,7 @@ class InteractVLMForCausalLM:
         if owners:
             hrows = self.ctx.gather_rows(hidden.view(-1, hidden.shape[-1]), _i32(rows, self.device))
             cam = self._bf16(torch.as_tensor(cam_params))[owners].contiguous()
-            prompt, _ = eng.seg_prompt(hrows, cam)
+            prompt, _ = eng.seg_prompt(hrows, cam, tokens)
             emb = image_embeddings.view(B, V, S, C)[owners].reshape(len(owners) * V, S, C)
             low = eng.mask_decode(emb, prompt).view(len(owners), V, 4 * cfg.sam_grid, 4 * cfg.sam_grid)
             for k, b in enumerate(owners):

@@ -259,12 +259,25 @@ def state_dict_spec(cfg) -> dict:
     # [SEG] projection and camera gate
     s["model.text_hidden_fcs.0.0.weight"] = ((D, D), "w"); s["model.text_hidden_fcs.0.0.bias"] = ((D,), "b")
     s["model.text_hidden_fcs.0.2.weight"] = ((cfg.out_dim, D), "w"); s["model.text_hidden_fcs.0.2.bias"] = ((cfg.out_dim,), "b")
-    if cfg.multiview_cam_cond and cfg.cam_encoder_type == "vi_v1":
+    O_ = cfg.out_dim
+    if cfg.multiview_cam_cond and cfg.cam_encoder_type == "vi_v1":       # components.py:541-572
         s["cam_pose_encoder.spatial_encoder.0.weight"] = ((128, 5), "w"); s["cam_pose_encoder.spatial_encoder.0.bias"] = ((128,), "b")
         s["cam_pose_encoder.spatial_encoder.2.weight"] = ((128, 128), "w"); s["cam_pose_encoder.spatial_encoder.2.bias"] = ((128,), "b")
         for v in range(cfg.multiview_channels):
-            s[f"cam_pose_encoder.view_transforms.{v}.weight"] = ((cfg.out_dim, 128), "w")
-            s[f"cam_pose_encoder.view_transforms.{v}.bias"] = ((cfg.out_dim,), "b")
+            s[f"cam_pose_encoder.view_transforms.{v}.weight"] = ((O_, 128), "w")
+            s[f"cam_pose_encoder.view_transforms.{v}.bias"] = ((O_,), "b")
+    elif cfg.multiview_cam_cond and cfg.cam_encoder_type == "view_index":  # components.py:510-539
+        s["cam_pose_encoder.spatial_encoder.0.weight"] = ((O_, 5), "w"); s["cam_pose_encoder.spatial_encoder.0.bias"] = ((O_,), "b")
+        s["cam_pose_encoder.spatial_encoder.2.weight"] = ((O_, O_), "w"); s["cam_pose_encoder.spatial_encoder.2.bias"] = ((O_,), "b")
+        for v in range(cfg.multiview_channels):
+            s[f"cam_pose_encoder.view_transforms.{v}.weight"] = ((O_, O_), "w")
+            s[f"cam_pose_encoder.view_transforms.{v}.bias"] = ((O_,), "b")
+    elif cfg.multiview_cam_cond and cfg.cam_encoder_type == "simple":      # components.py:491-508
+        s["cam_pose_encoder.linear1.weight"] = ((O_, 5), "w"); s["cam_pose_encoder.linear1.bias"] = ((O_,), "b")
+    if cfg.token_type.replace("-DifDe", "") in ("Gen-Hu-Obj", "Gen-Int"):  # AttentionSplitter, components.py:155-193
+        for name, shape in (("input_proj", (128, O_)), ("query_human", (128, 128)), ("query_object", (128, 128)), ("key", (128, 128)),
+                            ("value", (128, 128)), ("output_proj", (O_, 128))):
+            s[f"attention_splitter.{name}.weight"] = (shape, "w"); s[f"attention_splitter.{name}.bias"] = ((shape[0],), "b")
     return s
 
 

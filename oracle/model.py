@@ -160,14 +160,25 @@ def lm_logits(w: W, hidden):
     return F.linear(hidden, w("lm_head.weight"))
 
 
-def seg_rows(cfg, output_ids):
-    """Hidden-state row that predicts each [SEG]: token j sits at row j + img_emb_len, its predictor at
-    j - 1 + img_emb_len (InteractVLM.py:535-549).  Returns a list (per sample) of row indices."""
-    out = []
+def seg_token_ids(cfg):
+    """[SEG] alone, or [SEG] / [HSEG] / [OSEG] for the Gen-Hu-Obj / Gen-Int token types (InteractVLM.py:535-543)."""
+    ids = [cfg.seg_token_idx]
+    if cfg.token_type.replace("-DifDe", "") in ("Gen-Hu-Obj", "Gen-Int"):
+        ids += [t for t in (cfg.hseg_token_idx, cfg.oseg_token_idx) if t is not None]
+    return ids
+
+
+def seg_rows(cfg, output_ids, with_tokens=False):
+    """Hidden-state row that predicts each segmentation token: token j sits at row j + img_emb_len, its predictor at
+    j - 1 + img_emb_len (InteractVLM.py:535-549).  Returns a list (per sample) of row indices; with_tokens also the
+    token id the reference files per sample (the first one, :566-575)."""
+    out, toks = [], []
+    ids = torch.tensor(seg_token_ids(cfg))
     for b in range(output_ids.shape[0]):
-        js = (output_ids[b] == cfg.seg_token_idx).nonzero().flatten().tolist()
-        out.append([j - 1 + cfg.img_emb_len for j in js if j >= 1])
-    return out
+        js = [j for j in torch.isin(output_ids[b].cpu(), ids).nonzero().flatten().tolist() if j >= 1]
+        out.append([j - 1 + cfg.img_emb_len for j in js])
+        toks.append(int(output_ids[b, js[0]]) if js else None)
+    return (out, toks) if with_tokens else out
 
 
 def text_hidden_fcs(w: W, x):
@@ -176,21 +187,52 @@ def text_hidden_fcs(w: W, x):
 
 
 def cam_gate(w: W, cfg, pred_emb, cam_params):
-    """pred_emb [N,256], cam_params [V,5] -> [N,V,256] (vi_v1: emb * sigmoid(W_v relu(W2 relu(W1 cam))))."""
+    """pred_emb [N,256], cam_params [V,5] -> [N,V,256]: the camera conditioning of process_embeddings
+    (InteractVLM.py:268-283) for the three encoder types of components.py:491-572 --
+    simple: emb + relu(W cam); view_index: emb * W_v sigmoid(W2 relu(W1 cam)); vi_v1: emb * sigmoid(W_v relu(W2 relu(W1 cam)))."""
     V = cfg.multiview_channels
     emb = pred_emb[:, None, :].repeat(1, V, 1)
     if not cfg.multiview_cam_cond:
         return emb
-    assert cfg.cam_encoder_type == "vi_v1"
+    lin = lambda x, name: F.linear(x, w(f"cam_pose_encoder.{name}.weight"), w(f"cam_pose_encoder.{name}.bias"))
+    cam = cam_params.to(w.device, w.dtype)
+    if cfg.cam_encoder_type == "simple":
+        return emb + F.relu(lin(cam, "linear1"))
+    assert cfg.cam_encoder_type in ("view_index", "vi_v1"), cfg.cam_encoder_type
     encs = []
     for v in range(V):
-        c = cam_params[[v]].to(w.device, w.dtype)
-        y = F.relu(F.linear(c, w("cam_pose_encoder.spatial_encoder.0.weight"), w("cam_pose_encoder.spatial_encoder.0.bias")))
-        y = F.relu(F.linear(y, w("cam_pose_encoder.spatial_encoder.2.weight"), w("cam_pose_encoder.spatial_encoder.2.bias")))
-        y = torch.sigmoid(F.linear(y, w(f"cam_pose_encoder.view_transforms.{v}.weight"),
-                                   w(f"cam_pose_encoder.view_transforms.{v}.bias")))
+        c = cam[[v]]
+        if cfg.cam_encoder_type == "view_index":
+            y = torch.sigmoid(lin(F.relu(lin(c, "spatial_encoder.0")), "spatial_encoder.2"))
+            y = lin(y, f"view_transforms.{v}")
+        else:
+            y = F.relu(lin(F.relu(lin(c, "spatial_encoder.0")), "spatial_encoder.2"))
+            y = torch.sigmoid(lin(y, f"view_transforms.{v}"))
         encs.append(y)
     return emb * torch.stack(encs, 1)
+
+
+def attention_split(w: W, x, which):
+    """AttentionSplitter.forward (components.py:173-193) on x [N,V,256]: the V view tokens attend to each other with a
+    human or an object query projection.  which: 'human' | 'object'."""
+    lin = lambda t, name: F.linear(t, w(f"attention_splitter.{name}.weight"), w(f"attention_splitter.{name}.bias"))
+    xp = lin(x, "input_proj")
+    k, v = lin(xp, "key"), lin(xp, "value")
+    q = lin(xp, "query_human" if which == "human" else "query_object")
+    attn = F.softmax(torch.matmul(q, k.transpose(-2, -1)) / (k.size(-1) ** 0.5), dim=-1)
+    return lin(torch.matmul(attn, v), "output_proj")
+
+
+def process_embeddings(w: W, cfg, pred_emb, cam_params, token):
+    """InteractVLM.py:268-294: camera conditioning, then (Gen-Hu-Obj / Gen-Int only) the splitter branch the token selects."""
+    e = cam_gate(w, cfg, pred_emb, cam_params)
+    if cfg.token_type.replace("-DifDe", "") == "Gen":
+        return e
+    if token is not None and token == cfg.hseg_token_idx:
+        return attention_split(w, e, "human")
+    if token is not None and token == cfg.oseg_token_idx:
+        return attention_split(w, e, "object")
+    return e
 
 
 # ---------------------------------------------------------------------------------------------- SAM encoder
@@ -375,7 +417,7 @@ def greedy_generate(w: W, cfg, images_clip, input_ids, max_new_tokens, scripted=
 
 def masks_from_hidden(w: W, cfg, hidden, output_ids, images, cam_params, resize_list, original_size_list, stages=None):
     """Everything downstream of the language model (InteractVLM.py:535-612): per sample a [V,H,W] fp32 logit map."""
-    rows = seg_rows(cfg, output_ids)
+    rows, tokens = seg_rows(cfg, output_ids, with_tokens=True)
     pred_masks = []
     for b in range(hidden.shape[0]):
         emb_img = sam_image_encoder(w, cfg, images[b])
@@ -387,7 +429,7 @@ def masks_from_hidden(w: W, cfg, hidden, output_ids, images, cam_params, resize_
             pred_masks.append(torch.zeros((0,) + tuple(original_size_list[b]), dtype=torch.float32))
             continue
         assert pe.shape[0] == 1, "multi-view decoding broadcasts only for one [SEG] per sample (SURVEY.md 0.5)"
-        prompt = cam_gate(w, cfg, pe, cam_params[b])
+        prompt = process_embeddings(w, cfg, pe, cam_params[b], tokens[b])
         low = mask_decoder(w, cfg, emb_img, prompt)
         pm = postprocess_masks(cfg, low, resize_list[b], original_size_list[b])
         if stages is not None:

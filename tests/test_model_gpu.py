@@ -256,6 +256,39 @@ def test_view_cache_is_bit_identical(tiny, ctx):
         model._view_cache = None
 
 
+@pytest.mark.parametrize("cam_type,token_type,tok_name", [("simple", "Gen-Hu-Obj", "hseg"), ("view_index", "Gen-Int", "oseg"),
+                                                          ("view_index", "Gen", "seg")])
+def test_camera_encoder_and_token_type_variants(ctx, cam_type, token_type, tok_name):
+    """The other camera encoders and the AttentionSplitter token types on the CUDA path against the oracle (pinned to the
+    reference's own classes): the prompt stage-wise, and the whole evaluate() call for the splitter variant."""
+    from interactvlm_b200.model import InteractVLMForCausalLM
+
+    cfg = IVLMConfig.tiny()
+    cfg.cam_encoder_type, cfg.token_type, cfg.hseg_token_idx, cfg.oseg_token_idx = cam_type, token_type, 323, 324
+    sd = S.make_state_dict(cfg, seed=5)
+    for k in [k for k in sd if k.startswith(("attention_splitter.", "cam_pose_encoder.")) and k.endswith("weight")]:
+        sd[k] = sd[k] * 1.5
+    model = InteractVLMForCausalLM(cfg, sd, ctx=ctx)
+    w = OM.W(sd, torch.float32)
+    tok = {"seg": cfg.seg_token_idx, "hseg": cfg.hseg_token_idx, "oseg": cfg.oseg_token_idx}[tok_name]
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
+    hrow = torch.randn(2, cfg.hidden_size, generator=torch.Generator().manual_seed(3)).bfloat16()
+    got, _ = model.eng.seg_prompt(hrow.cuda(), cam.bfloat16().cuda(), [tok, cfg.seg_token_idx])
+    for i, t in enumerate((tok, cfg.seg_token_idx)):
+        want = OM.process_embeddings(w, cfg, OM.text_hidden_fcs(w, hrow[i:i + 1].float()), cam[i], t)
+        assert (got[i].float().cpu() - want[0]).abs().max().item() < 0.03 * max(1.0, want.abs().max().item())
+    if tok_name == "hseg":
+        p2v, bary = S.make_mesh_lift_maps(seed=TINY_SEED["maps"])
+        model.set_human_lift_maps(p2v, bary)
+        ans = ans.clone()
+        ans[ans == cfg.seg_token_idx] = tok
+        out = model.evaluate(clip[:1], sam[:1], ids[:1], cam[:1], [SIZE], [SIZE], max_new_tokens=ans.shape[1], scripted=ans[:1])
+        ref = OM.evaluate(sd, cfg, clip[:1], sam[:1], ids[:1], cam[:1], [SIZE], [SIZE], lift_maps=(p2v, bary, S.N_SMPL),
+                          max_new_tokens=ans.shape[1], scripted=ans[:1], dtype=torch.float32)
+        assert torch.equal(out["output_ids"].cpu(), ref["output_ids"])
+        assert (out["pred_contact_3d"].cpu() - ref["pred_contact_3d"]).abs().max().item() < 0.1
+
+
 def test_full_size_layers_vs_torch_fp32(ctx):
     """One SAM ViT-H block pair (window + global), one LLaMA-13B layer and the CLIP-L stack at their REAL widths:
     the oracle restatement evaluated with stock torch fp32 CUDA ops is the checker (CPU would take minutes)."""

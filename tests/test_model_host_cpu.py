@@ -184,3 +184,42 @@ def test_object_paths_evaluate_and_forward(tmp_path, setup):
             assert res["pred_human_3d_contact"].abs().max().item() == 0  # not an hcontact sample
     finally:
         model.oC_loss_weight = old
+
+
+@pytest.mark.parametrize("cam_type,token_type,tok_name", [("simple", "Gen-Hu-Obj", "hseg"), ("view_index", "Gen-Int", "oseg"),
+                                                          ("view_index", "Gen", "seg"), ("vi_v1", "Gen-Hu-Obj", "seg")])
+def test_camera_encoder_and_token_type_variants(cam_type, token_type, tok_name):
+    """The other camera encoders (components.py:491-539) and the AttentionSplitter token types (Gen-Hu-Obj / Gen-Int,
+    InteractVLM.py:268-294,535-543): host logic with emulated kernels against the oracle (itself pinned to the reference's
+    own classes, tests/test_oracle_components_golden.py), through the whole evaluate() call."""
+    cfg = IVLMConfig.tiny()
+    cfg.cam_encoder_type, cfg.token_type = cam_type, token_type
+    cfg.hseg_token_idx, cfg.oseg_token_idx = 323, 324
+    sd = S.make_state_dict(cfg, seed=5)
+    for k in [k for k in sd if k.startswith(("attention_splitter.", "cam_pose_encoder.")) and k.endswith("weight")]:
+        sd[k] = sd[k] * 1.5                      # a non-flat softmax (score spread ~2.4) without saturating it
+    model = InteractVLMForCausalLM(cfg, sd, ctx=EmuContext())
+    p2v, bary = S.make_mesh_lift_maps(seed=TINY_SEED["maps"])
+    model.set_human_lift_maps(p2v, bary)
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 1)
+    ans = ans.clone()
+    tok = {"seg": cfg.seg_token_idx, "hseg": cfg.hseg_token_idx, "oseg": cfg.oseg_token_idx}[tok_name]
+    ans[ans == cfg.seg_token_idx] = tok
+    out = model.evaluate(clip, sam, ids, cam, [SIZE], [SIZE], max_new_tokens=ans.shape[1], scripted=ans)
+    st = {}
+    ref = OM.evaluate(sd, cfg, clip, sam, ids, cam, [SIZE], [SIZE], lift_maps=(p2v, bary, S.N_SMPL),
+                      max_new_tokens=ans.shape[1], scripted=ans, dtype=torch.float32, stages=st)
+    assert torch.equal(out["output_ids"].cpu(), ref["output_ids"]) and out["pred_masks"][0].shape == (4, 1024, 1024)
+    rm = ref["pred_masks"][0]
+    assert (out["pred_masks"][0] - rm).abs().max().item() < 0.08 * rm.abs().max().item()
+    assert (out["pred_contact_3d"] - ref["pred_contact_3d"]).abs().max().item() < 0.1   # bf16 storage vs the fp32 oracle
+    # the prompt itself, stage-wise: bf16 storage only
+    hid = OM.lm_hidden(OM.W(sd, torch.float32), cfg, clip.float(), ref["output_ids"][:, :-1])
+    rows, toks = OM.seg_rows(cfg, ref["output_ids"], with_tokens=True)
+    assert toks == [tok]
+    prompt, _ = model.eng.seg_prompt(hid[0, rows[0]].bfloat16(), cam.bfloat16(), toks)
+    want = st["prompt"][0]
+    assert (prompt.float() - want).abs().max().item() < 0.03 * max(1.0, want.abs().max().item())
+    if token_type != "Gen" and tok_name != "seg":   # the splitter branch changed the prompt
+        plain, _ = model.eng.seg_prompt(hid[0, rows[0]].bfloat16(), cam.bfloat16(), [cfg.seg_token_idx])
+        assert (plain.float() - prompt.float()).abs().max().item() > 0.05
