@@ -192,3 +192,20 @@ def test_rasteriser_oracle_agrees_with_independent_ray_casting():
         ray_bary = np.stack([1 - bu - bw, bu, bw], -1)
         assert np.abs(ray_bary - bary[sel]).max() < 2e-4
         assert np.abs(t[idx, best[idx]] - zbuf[sel]).max() < 2e-5   # ray direction has unit z: t is the view-space depth
+
+
+def test_phong_oracle_analytic_pixel():
+    """HardPhong with one point light on a fronto-parallel triangle: at the pixel on the optical axis the light, view and
+    normal directions coincide, so colour = (ambient + diffuse) * texture + specular (front side) or ambient * texture (the
+    lighting is one-sided: a triangle wound the other way gets neither diffuse nor specular light)."""
+    cam = O.camera((2.0, 0, 0, 0, 0))
+    v = np.array([[-0.5, -0.5, 0], [0.5, -0.5, 0], [0, 0.6, 0]], dtype=np.float32)
+    col = np.full((3, 3), 0.5, np.float32)
+    H = 65                                                           # odd: pixel (32, 32) is on the optical axis
+    front = O.render_phong(v, np.array([[0, 1, 2]]), col, cam, [0, 0, 3], H, H)   # normal +z, towards camera and light
+    back = O.render_phong(v, np.array([[0, 2, 1]]), col, cam, [0, 0, 3], H, H)
+    assert (front[0, 0] == 255).all() and (back[0, 0] == 255).all()               # white background
+    assert (front[32, 32] == int((0.5 + 0.3) * 0.5 * 255 + 0.2 * 255)).all()      # 153
+    assert (back[32, 32] == int(0.5 * 0.5 * 255)).all()                           # 63
+    n = O.vertex_normals(v, np.array([[0, 1, 2]]))
+    assert np.allclose(n, [[0, 0, 1]] * 3, atol=1e-6)
