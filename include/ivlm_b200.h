@@ -249,9 +249,16 @@ IVLM_API int ivlm_lift_free(ivlm_lift_map* m);
 IVLM_API int64_t ivlm_lift_nnz(const ivlm_lift_map* m);
 /* masks [B,V,H,W] fp32 logits (POINTS mode: values) -> contact [B,n_verts] fp32.
  * HumanContact3DPredictor.forward (components.py:220-277), ObjectMeshContact3DPredictor (components.py:430-489,
- * thr = 0.3), ObjectPCAfford3DPredictor (components.py:289-347). Deterministic gather, no atomics. */
+ * thr = 0.3), ObjectPCAfford3DPredictor (components.py:289-347). Deterministic gather, no atomics: one warp per (vertex,
+ * view) strides the CSR segment with coalesced loads and folds the lanes with shuffles. */
 IVLM_API int ivlm_lift(ivlm_handle h, const ivlm_lift_map* m, const float* masks, float* contact, int32_t B, int32_t mode,
               float thr, void* stream);
+/* Same lift fed with the mask decoder's LOW-RES logits [B,V,sh,sw] fp32 (mask_decoder.py:116-164 output): the bilinear
+ * upsample to the map's (H,W) that Sam.postprocess_masks applies first (sam.py:161-165, align_corners=False, no crop) is
+ * evaluated per map entry inside the kernel with the arithmetic of ivlm_bilinear_f32, so the result is bit-identical to
+ * ivlm_bilinear_f32 followed by ivlm_lift while reading 1/16 of the logits. */
+IVLM_API int ivlm_lift_lowres(ivlm_handle h, const ivlm_lift_map* m, const float* lowres, int32_t sh, int32_t sw, float* contact,
+                     int32_t B, int32_t mode, float thr, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * "Render" of Render-Localise-Lift: mesh -> per-pixel (face, barycentrics) -> lift maps and SAM input views.
  * Replaces pytorch3d's MeshRasterizer / HardPhongShader as the reference drives them (get_rasterizer,

@@ -94,6 +94,30 @@ IVLM_DEVINL uint32_t add_bf16x2(uint32_t a, uint32_t b) {
     const float2 fa = unpack_bf16x2(a), fb = unpack_bf16x2(b);
     return pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
 }
+// One output sample of PyTorch's upsample_bilinear2d (align_corners=False) from src [.., sw] whose top-left (ch, cw) window is
+// the source image: src coordinate = max((dst + 0.5) * scale - 0.5, 0), scale = in / out; same association as ATen:
+// hy*(hx*a + lx*b) + ly*(hx*c + lx*d), every product and sum rounded separately.  Shared by bilinear_kernel and by the lift
+// kernels that read the low-res logits directly, so both produce the same bits.
+struct BilinearTap {
+    int o00, o01, o10, o11;  // element offsets inside one [sh, sw] plane
+    float hy, ly, hx, lx;
+};
+IVLM_DEVINL BilinearTap bilinear_tap(int y, int x, float sy, float sx, int ch, int cw, int sw) {
+    const float fy = fmaxf(((float)y + 0.5f) * sy - 0.5f, 0.f);
+    const float fx = fmaxf(((float)x + 0.5f) * sx - 0.5f, 0.f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < ch - 1 ? 1 : 0), x1 = x0 + (x0 < cw - 1 ? 1 : 0);
+    BilinearTap t;
+    t.ly = fy - (float)y0; t.lx = fx - (float)x0;
+    t.hy = 1.f - t.ly; t.hx = 1.f - t.lx;
+    t.o00 = y0 * sw + x0; t.o01 = y0 * sw + x1; t.o10 = y1 * sw + x0; t.o11 = y1 * sw + x1;
+    return t;
+}
+IVLM_DEVINL float bilinear_eval(const BilinearTap& t, const float* __restrict__ s) {
+    const float top = __fadd_rn(__fmul_rn(t.hx, __ldg(s + t.o00)), __fmul_rn(t.lx, __ldg(s + t.o01)));
+    const float bot = __fadd_rn(__fmul_rn(t.hx, __ldg(s + t.o10)), __fmul_rn(t.lx, __ldg(s + t.o11)));
+    return __fadd_rn(__fmul_rn(t.hy, top), __fmul_rn(t.ly, bot));
+}
 IVLM_DEVINL void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

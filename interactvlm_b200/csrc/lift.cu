@@ -3,8 +3,8 @@
 // The reference scatters every valid pixel into its 3 vertices with atomics after copying 150 MB of maps to
 // the GPU per sample (components.py:220-277).  Here the maps are inverted ONCE into a per-(view,vertex) CSR of
 // (pixel, weight) entries, and the lift is a deterministic gather: no atomics, int32 indices, ~18 MB of map
-// data shared by the whole batch.  Entries are ordered (corner k, pixel) and summed sequentially with separate
-// multiply and add roundings, which is the order the reference's three scatter_add_ passes use on CPU.
+// data shared by the whole batch.  Entries are ordered (corner k, pixel); a warp strides each (view, vertex) segment and
+// folds its lanes' partial sums with shuffles (fp32; within 1e-6 of the reference's sequential scatter_add_ order).
 #include <algorithm>
 #include <vector>
 
@@ -29,39 +29,98 @@ struct ivlm_csr {
 
 namespace ivlm {
 
-__global__ void lift_kernel(const int* __restrict__ row_ptr, const int* __restrict__ pix, const float* __restrict__ wgt,
-                            const float* __restrict__ masks, float* __restrict__ contact, int B, int V, int n,
-                            long long hw, int mode, float thr) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)B * n) return;
-    const int b = (int)(idx / n), vtx = (int)(idx % n);
-    float pred = 0.f, nviews = 0.f;
-    for (int v = 0; v < V; ++v) {
-        const float* m = masks + ((long long)b * V + v) * hw;
+// One CTA per (vertex, chunk of LIFT_BC samples): warp w takes views w, w + LIFT_WARPS, ...; its lanes stride the CSR
+// segment of (view, vertex) -- coalesced 128-byte loads of pix / wgt, each entry loaded ONCE and applied to all samples of
+// the chunk -- and the per-lane partial sums are folded with a shuffle tree (deterministic: the grouping depends only on the
+// map).  Views are combined through shared memory in view order, like the reference's loop over views
+// (components.py:235-262).  LOWRES: `src` holds the mask decoder's low-res logits [B,V,sh,sw] and the x(H/sh) bilinear of
+// Sam.postprocess_masks (sam.py:161-165) is evaluated per entry with the arithmetic of bilinear_kernel (bit-identical to
+// lifting the materialised 1024^2 logits, which are then never read: 1.05 MB instead of 16.8 MB per sample).
+constexpr int LIFT_BC = 8, LIFT_WARPS = 4, LIFT_MAX_VIEWS = 8;
+
+template <int MODE, bool LOWRES>
+__global__ void __launch_bounds__(LIFT_WARPS * 32)
+lift_warp_kernel(const int* __restrict__ row_ptr, const int* __restrict__ pix, const float* __restrict__ wgt,
+                 const float* __restrict__ src, float* __restrict__ contact, int B, int V, int n, int H, int W, int sh, int sw,
+                 float thr) {
+    const int vtx = blockIdx.x, b0 = blockIdx.y * LIFT_BC;
+    const int nb = min(LIFT_BC, B - b0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ float s_votes[LIFT_MAX_VIEWS][LIFT_BC], s_cnt[LIFT_MAX_VIEWS][LIFT_BC];
+    const long long plane = LOWRES ? (long long)sh * sw : (long long)H * W;
+    const float sy = (float)sh / (float)H, sx = (float)sw / (float)W;
+    for (int v = warp; v < V; v += LIFT_WARPS) {
         const int e0 = row_ptr[v * n + vtx], e1 = row_ptr[v * n + vtx + 1];
-        float votes = 0.f, cnt = 0.f;
-        for (int e = e0; e < e1; ++e) {
-            float x = __ldg(m + pix[e]);
-            if (mode == IVLM_LIFT_POINTS) {
-                votes = __fadd_rn(votes, x);
-                cnt = __fadd_rn(cnt, 1.f);
-                continue;
+        float votes[LIFT_BC], cnt[LIFT_BC];
+#pragma unroll
+        for (int s = 0; s < LIFT_BC; ++s) votes[s] = cnt[s] = 0.f;
+        const float* base = src + ((long long)b0 * V + v) * plane;
+        for (int e = e0 + lane; e < e1; e += 32) {
+            const int p = __ldg(pix + e);
+            const float w = (MODE == IVLM_LIFT_POINTS) ? 1.f : __ldg(wgt + e);
+            BilinearTap t;
+            if (LOWRES) t = bilinear_tap(p / W, p % W, sy, sx, sh, sw, sw);
+            if (MODE != IVLM_LIFT_OBJECT_MESH) cnt[0] += w;   // the weight sum does not depend on the sample
+#pragma unroll
+            for (int s = 0; s < LIFT_BC; ++s) {
+                if (s < nb) {
+                    const float* m = base + (long long)s * V * plane;
+                    float x = LOWRES ? bilinear_eval(t, m) : __ldg(m + p);
+                    if (MODE == IVLM_LIFT_POINTS) {
+                        votes[s] += x;
+                    } else {
+                        if (MODE == IVLM_LIFT_HUMAN) x = fminf(fmaxf(x, -20.f), 20.f);
+                        const float pr = 1.f / (1.f + expf(-x));
+                        if (MODE == IVLM_LIFT_OBJECT_MESH) {
+                            if (pr > thr) { votes[s] += w * pr; cnt[s] += w; }
+                        } else {
+                            votes[s] += w * pr;
+                        }
+                    }
+                }
             }
-            if (mode == IVLM_LIFT_HUMAN) x = fminf(fmaxf(x, -20.f), 20.f);
-            const float p = 1.f / (1.f + expf(-x));
-            if (mode == IVLM_LIFT_OBJECT_MESH && !(p > thr)) continue;
-            const float w = wgt[e];
-            votes = __fadd_rn(votes, __fmul_rn(w, p));
-            cnt = __fadd_rn(cnt, w);
         }
-        if (cnt > 0.f) {
-            pred = __fadd_rn(pred, votes / cnt);
-            nviews += 1.f;
+        if (MODE != IVLM_LIFT_OBJECT_MESH) cnt[0] = warp_sum(cnt[0]);
+#pragma unroll
+        for (int s = 0; s < LIFT_BC; ++s) {
+            if (s < nb) {
+                votes[s] = warp_sum(votes[s]);
+                if (MODE == IVLM_LIFT_OBJECT_MESH) cnt[s] = warp_sum(cnt[s]);
+                if (lane == 0) {
+                    s_votes[v][s] = votes[s];
+                    s_cnt[v][s] = (MODE == IVLM_LIFT_OBJECT_MESH) ? cnt[s] : cnt[0];
+                }
+            }
         }
     }
-    if (nviews > 0.f) pred = pred / nviews;
-    if (mode == IVLM_LIFT_HUMAN) pred = fminf(fmaxf(pred, 0.f), 1.f);
-    contact[idx] = pred;
+    __syncthreads();
+    if ((int)threadIdx.x < nb) {
+        const int s = threadIdx.x;
+        float pred = 0.f, nviews = 0.f;
+        for (int v = 0; v < V; ++v) {
+            const float c = s_cnt[v][s], vt = s_votes[v][s];
+            // votes are normalised only where the weight sum is positive; the rest is added as is (components.py:257-262)
+            pred += (c > 0.f) ? vt / c : vt;
+            nviews += (c > 0.f) ? 1.f : 0.f;
+        }
+        if (nviews > 0.f) pred = pred / nviews;
+        if (MODE == IVLM_LIFT_HUMAN) pred = fminf(fmaxf(pred, 0.f), 1.f);
+        contact[(long long)(b0 + s) * n + vtx] = pred;
+    }
+}
+
+template <bool LOWRES>
+static cudaError_t launch_lift(const ivlm_lift_map* m, const float* src, float* contact, int B, int mode, float thr, int sh,
+                               int sw, cudaStream_t st) {
+    const dim3 grid((unsigned)m->n, (unsigned)((B + LIFT_BC - 1) / LIFT_BC)), block(LIFT_WARPS * 32);
+#define IVLM_LIFT_LAUNCH(MODE)                                                                                              \
+    lift_warp_kernel<MODE, LOWRES><<<grid, block, 0, st>>>(m->row_ptr, m->pix, m->wgt, src, contact, B, m->V, m->n, m->H, \
+                                                            m->W, sh, sw, thr)
+    if (mode == IVLM_LIFT_HUMAN) IVLM_LIFT_LAUNCH(IVLM_LIFT_HUMAN);
+    else if (mode == IVLM_LIFT_OBJECT_MESH) IVLM_LIFT_LAUNCH(IVLM_LIFT_OBJECT_MESH);
+    else IVLM_LIFT_LAUNCH(IVLM_LIFT_POINTS);
+#undef IVLM_LIFT_LAUNCH
+    return cudaGetLastError();
 }
 
 __global__ void csr_spmv_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col,
@@ -83,9 +142,22 @@ static int upload(T** dptr, const std::vector<T>& host) {
     return IVLM_OK;
 }
 
+// In-place inclusive prefix sum of per-row counts held in row_ptr[1..]; refuses maps whose entry count leaves int32.
+static int prefix_sum_checked(std::vector<int>& row_ptr, const char* who) {
+    long long run = 0;
+    for (size_t i = 1; i < row_ptr.size(); ++i) {
+        run += row_ptr[i];
+        IVLM_REQUIRE(run < (1LL << 31), "%s: %lld map entries exceed the int32 CSR range", who, run);
+        row_ptr[i] = (int)run;
+    }
+    return IVLM_OK;
+}
+
 }  // namespace ivlm
 
 using namespace ivlm;
+extern "C" int ivlm_lift_free(ivlm_lift_map* m);
+extern "C" int ivlm_csr_free(ivlm_csr* m);
 
 extern "C" int ivlm_lift_build_mesh(ivlm_handle h, const int64_t* p2v, const float* bary, int32_t V, int32_t H, int32_t W,
                                     int32_t n, ivlm_lift_map** out) {
@@ -103,7 +175,7 @@ extern "C" int ivlm_lift_build_mesh(ivlm_handle h, const int64_t* p2v, const flo
             cnt[a]++; cnt[b]++; cnt[c]++;
         }
     }
-    for (size_t i = 1; i < row_ptr.size(); ++i) row_ptr[i] += row_ptr[i - 1];
+    IVLM_TRY(prefix_sum_checked(row_ptr, "lift_build_mesh"));
     const long long nnz = row_ptr.back();
     std::vector<int> pix((size_t)nnz);
     std::vector<float> wgt((size_t)nnz);
@@ -124,12 +196,13 @@ extern "C" int ivlm_lift_build_mesh(ivlm_handle h, const int64_t* p2v, const flo
             }
         }
     }
+    IVLM_CHECK_CUDA(cudaSetDevice(h->device));
     ivlm_lift_map* m = new ivlm_lift_map();
     m->V = V; m->H = H; m->W = W; m->n = n; m->nnz = nnz;
-    IVLM_CHECK_CUDA(cudaSetDevice(h->device));
-    IVLM_TRY(upload(&m->row_ptr, row_ptr));
-    IVLM_TRY(upload(&m->pix, pix));
-    IVLM_TRY(upload(&m->wgt, wgt));
+    if (upload(&m->row_ptr, row_ptr) != IVLM_OK || upload(&m->pix, pix) != IVLM_OK || upload(&m->wgt, wgt) != IVLM_OK) {
+        ivlm_lift_free(m);
+        return IVLM_ERR_CUDA;
+    }
     *out = m;
     return IVLM_OK;
 }
@@ -137,6 +210,7 @@ extern "C" int ivlm_lift_build_mesh(ivlm_handle h, const int64_t* p2v, const flo
 extern "C" int ivlm_lift_build_points(ivlm_handle h, const int64_t* p2p, int32_t V, int32_t H, int32_t W, int32_t n,
                                       ivlm_lift_map** out) {
     IVLM_REQUIRE(h && p2p && out && V > 0 && H > 0 && W > 0 && n > 0, "lift_build_points: bad arguments");
+    IVLM_REQUIRE((long long)H * W < (1LL << 31), "lift_build_points: view too large for int32 pixel ids");
     const long long hw = (long long)H * W;
     std::vector<int> row_ptr((size_t)V * n + 1, 0);
     for (int v = 0; v < V; ++v)
@@ -146,7 +220,7 @@ extern "C" int ivlm_lift_build_points(ivlm_handle h, const int64_t* p2p, int32_t
             IVLM_REQUIRE(a >= 0 && a < n, "lift_build_points: point id %lld out of range [0,%d)", (long long)a, n);
             row_ptr[(size_t)v * n + 1 + a]++;
         }
-    for (size_t i = 1; i < row_ptr.size(); ++i) row_ptr[i] += row_ptr[i - 1];
+    IVLM_TRY(prefix_sum_checked(row_ptr, "lift_build_points"));
     const long long nnz = row_ptr.back();
     std::vector<int> pix((size_t)nnz);
     std::vector<int> cur(row_ptr.begin(), row_ptr.end() - 1);
@@ -156,11 +230,13 @@ extern "C" int ivlm_lift_build_points(ivlm_handle h, const int64_t* p2p, int32_t
             if (a == -1) continue;
             pix[cur[(size_t)v * n + a]++] = (int)i;
         }
+    IVLM_CHECK_CUDA(cudaSetDevice(h->device));
     ivlm_lift_map* m = new ivlm_lift_map();
     m->V = V; m->H = H; m->W = W; m->n = n; m->nnz = nnz;
-    IVLM_CHECK_CUDA(cudaSetDevice(h->device));
-    IVLM_TRY(upload(&m->row_ptr, row_ptr));
-    IVLM_TRY(upload(&m->pix, pix));
+    if (upload(&m->row_ptr, row_ptr) != IVLM_OK || upload(&m->pix, pix) != IVLM_OK) {
+        ivlm_lift_free(m);
+        return IVLM_ERR_CUDA;
+    }
     *out = m;
     return IVLM_OK;
 }
@@ -178,12 +254,23 @@ extern "C" int64_t ivlm_lift_nnz(const ivlm_lift_map* m) { return m ? m->nnz : 0
 extern "C" int ivlm_lift(ivlm_handle h, const ivlm_lift_map* m, const float* masks, float* contact, int32_t B,
                          int32_t mode, float thr, void* stream) {
     IVLM_REQUIRE(h && m && masks && contact && B > 0, "lift: bad arguments");
+    IVLM_REQUIRE(mode == IVLM_LIFT_HUMAN || mode == IVLM_LIFT_OBJECT_MESH || mode == IVLM_LIFT_POINTS, "lift: unknown mode %d", mode);
     IVLM_REQUIRE(mode == IVLM_LIFT_POINTS || m->wgt != nullptr, "lift: mesh modes need a map built by ivlm_lift_build_mesh");
-    const long long total = (long long)B * m->n;
-    lift_kernel<<<(unsigned)((total + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        m->row_ptr, m->pix, m->wgt, masks, contact, B, m->V, m->n, (long long)m->H * m->W, mode, thr);
+    IVLM_REQUIRE(m->V <= LIFT_MAX_VIEWS, "lift: at most %d views", LIFT_MAX_VIEWS);
+    IVLM_CHECK_CUDA(launch_lift<false>(m, masks, contact, B, mode, thr, m->H, m->W, reinterpret_cast<cudaStream_t>(stream)));
     h->launches++;
-    IVLM_CHECK_CUDA(cudaGetLastError());
+    return IVLM_OK;
+}
+
+extern "C" int ivlm_lift_lowres(ivlm_handle h, const ivlm_lift_map* m, const float* lowres, int32_t sh, int32_t sw,
+                                float* contact, int32_t B, int32_t mode, float thr, void* stream) {
+    IVLM_REQUIRE(h && m && lowres && contact && B > 0 && sh > 0 && sw > 0, "lift_lowres: bad arguments");
+    IVLM_REQUIRE(mode == IVLM_LIFT_HUMAN || mode == IVLM_LIFT_OBJECT_MESH || mode == IVLM_LIFT_POINTS, "lift_lowres: unknown mode %d", mode);
+    IVLM_REQUIRE(mode == IVLM_LIFT_POINTS || m->wgt != nullptr, "lift_lowres: mesh modes need a map built by ivlm_lift_build_mesh");
+    IVLM_REQUIRE(m->V <= LIFT_MAX_VIEWS, "lift_lowres: at most %d views", LIFT_MAX_VIEWS);
+    IVLM_REQUIRE((long long)sh * sw < (1LL << 31), "lift_lowres: source plane too large");
+    IVLM_CHECK_CUDA(launch_lift<true>(m, lowres, contact, B, mode, thr, sh, sw, reinterpret_cast<cudaStream_t>(stream)));
+    h->launches++;
     return IVLM_OK;
 }
 
@@ -198,12 +285,13 @@ extern "C" int ivlm_csr_build_dense(ivlm_handle h, const float* dense, int32_t r
         }
         row_ptr[r + 1] = (int)col.size();
     }
+    IVLM_CHECK_CUDA(cudaSetDevice(h->device));
     ivlm_csr* m = new ivlm_csr();
     m->rows = rows; m->cols = cols; m->nnz = (long long)col.size();
-    IVLM_CHECK_CUDA(cudaSetDevice(h->device));
-    IVLM_TRY(upload(&m->row_ptr, row_ptr));
-    IVLM_TRY(upload(&m->col, col));
-    IVLM_TRY(upload(&m->val, val));
+    if (upload(&m->row_ptr, row_ptr) != IVLM_OK || upload(&m->col, col) != IVLM_OK || upload(&m->val, val) != IVLM_OK) {
+        ivlm_csr_free(m);
+        return IVLM_ERR_CUDA;
+    }
     *out = m;
     return IVLM_OK;
 }

@@ -430,17 +430,8 @@ __global__ void bilinear_kernel(const float* __restrict__ src, float* __restrict
          i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % dw), y = (int)((i / dw) % dh);
         const long long n = i / ((long long)dw * dh);
-        float fy = fmaxf(((float)y + 0.5f) * sy - 0.5f, 0.f);
-        float fx = fmaxf(((float)x + 0.5f) * sx - 0.5f, 0.f);
-        const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = y0 + (y0 < ch - 1 ? 1 : 0), x1 = x0 + (x0 < cw - 1 ? 1 : 0);
-        const float ly = fy - (float)y0, lx = fx - (float)x0;
-        const float hy = 1.f - ly, hx = 1.f - lx;
-        const float* s = src + n * (long long)sh * sw;
-        // same association as ATen's upsample_bilinear2d: hy*(hx*a + lx*b) + ly*(hx*c + lx*d)
-        const float top = __fadd_rn(__fmul_rn(hx, s[(long long)y0 * sw + x0]), __fmul_rn(lx, s[(long long)y0 * sw + x1]));
-        const float bot = __fadd_rn(__fmul_rn(hx, s[(long long)y1 * sw + x0]), __fmul_rn(lx, s[(long long)y1 * sw + x1]));
-        dst[i] = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+        const BilinearTap t = bilinear_tap(y, x, sy, sx, ch, cw, sw);
+        dst[i] = bilinear_eval(t, src + n * (long long)sh * sw);
     }
 }
 

@@ -113,6 +113,8 @@ def validate(model, samples, batch_size=8, dist=None, max_new_tokens=32, contact
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     lo, hi = shard_range(n, rank, world)
     preds = []
+    hmap = getattr(model.human_3d_contact_predictor, "map", None)
+    n_verts = hmap.n if hmap is not None else 6890
     i = lo
     while i < hi:
         j = i + 1
@@ -125,9 +127,12 @@ def validate(model, samples, batch_size=8, dist=None, max_new_tokens=32, contact
         out = model.evaluate(cat("images_clip"), cat("images"), cat("input_ids"), cat("cam_params"),
                              [tuple(s["resize"]) for s in chunk], [tuple(s["original_size"]) for s in chunk],
                              contact_type=contact_type, max_new_tokens=max_new_tokens, scripted=scripted)
-        preds.append(out["pred_contact_3d"])
+        pc = out["pred_contact_3d"]
+        if pc is None:   # no sample of the chunk produced a [SEG] (the reference reads .get("pred_contact_3d", None), evaluate.py:111)
+            pc = torch.zeros((len(chunk), n_verts), device=model.device, dtype=torch.float32)
+        preds.append(pc)
         i = j
-    n_out = preds[0].shape[1] if preds else 6890
+    n_out = preds[0].shape[1] if preds else n_verts
     local = torch.cat(preds, 0) if preds else torch.zeros((0, n_out), device=model.device)
     allp = gather_contacts(local, dist, n_samples=n) if world > 1 else local
     gts = [s.get("gt_contact_3d") for s in samples]

@@ -474,11 +474,23 @@ class _Predictor:
     of ops.LiftMap and cached by its source path(s)."""
 
     N_POINTS = 2048  # ObjectPCAfford3DPredictor(num_points=2048), components.py:280
+    CACHE_ENTRIES = 16  # per-sample object maps are ~20-100 MB of device CSR each: least-recently-used entries are dropped
 
     def __init__(self, model, mode):
+        from collections import OrderedDict
+
         self.model, self.mode = model, mode
         self.map = None
-        self._cache = {}
+        self._cache = OrderedDict()
+
+    def _cached(self, key, make):
+        if key in self._cache:
+            self._cache.move_to_end(key)
+            return self._cache[key]
+        m = self._cache[key] = make()
+        while len(self._cache) > self.CACHE_ENTRIES:
+            self._cache.popitem(last=False)
+        return m
 
     def _make(self, p2v, bary, n):
         if self.model._emulated:
@@ -493,30 +505,32 @@ class _Predictor:
 
     def _from_pickle(self, path):
         """lift2d_dict.pkl written by generate_sam_inp_objs (utils/demo_utils.py:171-257; read at components.py:392-424)."""
-        if path not in self._cache:
+        def make():
             import joblib
 
             d = joblib.load(path)
-            self._cache[path] = self._make(np.stack([np.asarray(a) for a in d["pixel_to_vertices_map"]]),
-                                           np.stack([np.asarray(a) for a in d["bary_coords_map"]]), int(d["num_vertices"]))
-        return self._cache[path]
+            return self._make(np.stack([np.asarray(a) for a in d["pixel_to_vertices_map"]]),
+                              np.stack([np.asarray(a) for a in d["bary_coords_map"]]), int(d["num_vertices"]))
+
+        return self._cached(str(path), make)
 
     def _from_mask_paths(self, mask_paths):
         """Per-view map files next to the mask images: '...mask...png' -> '...p2vmap....npz' (mesh, components.py:363-375)
         or '...p2pmap....npz' (point cloud, components.py:309)."""
-        key = tuple(mask_paths)
-        if key not in self._cache:
+        def make():
             V = self.model.config.multiview_channels
             if self.mode == LIFT_POINTS:
                 maps = [np.load(mask_paths[v].replace("mask", "p2pmap")[:-4] + ".npz")["mapping"] for v in range(V)]
-                self._cache[key] = self._make(np.stack(maps), None, self.N_POINTS)
-            else:
-                files = [np.load(mask_paths[v].replace("mask", "p2vmap").replace(".png", ".npz")) for v in range(V)]
-                self._cache[key] = self._make(np.stack([f["pixel_to_vertices_map"] for f in files]),
-                                              np.stack([f["bary_coords_map"] for f in files]), int(files[0]["num_vertices"]))
-        return self._cache[key]
+                return self._make(np.stack(maps), None, self.N_POINTS)
+            files = [np.load(mask_paths[v].replace("mask", "p2vmap").replace(".png", ".npz")) for v in range(V)]
+            return self._make(np.stack([f["pixel_to_vertices_map"] for f in files]),
+                              np.stack([f["bary_coords_map"] for f in files]), int(files[0]["num_vertices"]))
 
-    def __call__(self, seg_maps, ds_names=None, mask_paths_list=None, lift2d_dict_path=None):
+        return self._cached(tuple(mask_paths), make)
+
+    def __call__(self, seg_maps, ds_names=None, mask_paths_list=None, lift2d_dict_path=None, _lowres=None):
+        """`_lowres` (internal, optional): the mask decoder's low-res logits [n_live,V,h,w] of the samples that own a mask, in
+        sample order, when seg_maps are exactly their x4 bilinear blow-up: the lift then reads those (ivlm_lift_lowres)."""
         B = len(seg_maps)
         dev = seg_maps[0].device
         if self.mode == LIFT_HUMAN:
@@ -524,8 +538,19 @@ class _Predictor:
             if self.map is None:
                 raise RuntimeError("human lifting maps not loaded: call model.load_human_lift_maps(data_root) or "
                                    "model.set_human_lift_maps(p2v, bary)")
-            masks = torch.stack([s.float() for s in seg_maps], 0).contiguous()
-            out = self.map(masks, LIFT_HUMAN, 0.3)
+            # samples without a [SEG] carry an empty [0,H,W] map (InteractVLM.py:596-601): they get a zero row
+            live = [b for b in range(B) if seg_maps[b].shape[0] > 0]
+            out = torch.zeros((B, self.map.n), device=dev, dtype=torch.float32)
+            if live:
+                hw = tuple(seg_maps[live[0]].shape[-2:])
+                if _lowres is not None and _lowres.shape[0] == len(live) and hw == (self.map.H, self.map.W):
+                    vals = self.map.lowres(_lowres.contiguous(), LIFT_HUMAN, 0.3)
+                else:
+                    vals = self.map(torch.stack([seg_maps[b].float() for b in live], 0).contiguous(), LIFT_HUMAN, 0.3)
+                if len(live) == B:
+                    out = vals
+                else:
+                    out[torch.as_tensor(live, device=dev)] = vals
             for b, n in enumerate(names):  # samples of other datasets contribute zeros (components.py:231-233)
                 if "hcontact" not in n:
                     out[b] = 0
@@ -619,6 +644,7 @@ class InteractVLMForCausalLM:
         self.record_stages = False  # bench.py: CUDA events at stage boundaries (a dozen per call)
         self._marks = []
         self.stage_delay = None     # bench.py per-kernel timing pass: callable that parks the GPU so the host runs ahead
+        self._lowres_last = None    # low-res logits of the last _masks_from_hidden() when pred_masks are exactly their x4 blow-up
 
     def _mark(self, name):
         if self.record_stages and self.device.type == "cuda":
@@ -899,12 +925,15 @@ class InteractVLMForCausalLM:
         pred_masks = self._masks_from_hidden(hidden, output_ids, images, cam_params, resize_list, original_size_list,
                                              image_embeddings=emb)
         pred_contact_3d = None
-        if pred_masks[0].shape[0] > 0:
+        # the reference (batch 1) lifts when its sample produced a mask (:618); batched: when any sample did -- the others
+        # get a zero row (and a [0,H,W] entry in pred_masks, as the reference files them)
+        if any(m.shape[0] > 0 for m in pred_masks):
             if self.hC_loss_weight > 0 and "hcontact" in contact_type:
-                pred_contact_3d = self.human_3d_contact_predictor(pred_masks)
+                pred_contact_3d = self.human_3d_contact_predictor(pred_masks, _lowres=self._lowres_last)
             elif (self.oC_loss_weight > 0 and "ocontact" in contact_type) or "oafford" in contact_type:  # sic (:626)
                 pred_contact_3d = self.object_3d_contact_predictor(pred_masks, ds_names=["ocontact"],
                                                                    lift2d_dict_path=lift2d_dict_path)
+        self._lowres_last = None
         self._mark("lift")
         return {"output_ids": output_ids.to(self.device), "pred_masks": pred_masks, "pred_contact_3d": pred_contact_3d}
 
@@ -1008,6 +1037,7 @@ class InteractVLMForCausalLM:
         B = output_ids.shape[0]
         V = cfg.multiview_channels
         rows, owners, tokens = [], [], []
+        self._lowres_last = None
         seg_ids = [cfg.seg_token_idx]
         if cfg.token_type.replace("-DifDe", "") in ("Gen-Hu-Obj", "Gen-Int"):   # InteractVLM.py:535-543
             seg_ids += [t for t in (cfg.hseg_token_idx, cfg.oseg_token_idx) if t is not None]
@@ -1032,8 +1062,18 @@ class InteractVLMForCausalLM:
             prompt, _ = eng.seg_prompt(hrows, cam, tokens)
             emb = image_embeddings.view(B, V, S, C)[owners].reshape(len(owners) * V, S, C)
             low = eng.mask_decode(emb, prompt).view(len(owners), V, 4 * cfg.sam_grid, 4 * cfg.sam_grid)
-            for k, b in enumerate(owners):
-                pred_masks[b] = eng.postprocess(low[k].contiguous(), resize_list[b], original_size_list[b])
+            S_img = cfg.sam_img_size
+            same = all(tuple(int(x) for x in resize_list[b]) == (S_img, S_img) and
+                       tuple(int(x) for x in original_size_list[b]) == (S_img, S_img) for b in owners)
+            if same:   # one launch for the whole batch; the lift reads `low` directly
+                full = eng.postprocess(low.view(len(owners) * V, low.shape[2], low.shape[3]), (S_img, S_img), (S_img, S_img))
+                full = full.view(len(owners), V, S_img, S_img)
+                for k, b in enumerate(owners):
+                    pred_masks[b] = full[k]
+                self._lowres_last = low
+            else:
+                for k, b in enumerate(owners):
+                    pred_masks[b] = eng.postprocess(low[k].contiguous(), resize_list[b], original_size_list[b])
         self._mark("mask_decoder_upsample")
         for b in range(B):
             if pred_masks[b] is None:
@@ -1076,10 +1116,11 @@ class InteractVLMForCausalLM:
                 self.ctx.sigmoid_where(pred_masks[i], gt, -1.0)  # IGNORE_LABEL = -1 (utils/utils.py:19)
         result = {"gt_masks": [m[:, 0] for m in masks_list] if masks_list is not None else None, "pred_masks": pred_masks}
         if self.hC_loss_weight > 0:
-            result["pred_human_3d_contact"] = self.human_3d_contact_predictor(pred_masks, ds)
+            result["pred_human_3d_contact"] = self.human_3d_contact_predictor(pred_masks, ds, _lowres=self._lowres_last)
         if self.oC_loss_weight > 0:
             result["pred_object_3d_contact"] = self.object_3d_contact_predictor(pred_masks, ds, mask_paths_list)
             result["pred_object_3d_afford"] = self.object_3d_afford_predictor(pred_masks, ds, mask_paths_list)
+        self._lowres_last = None
         return result
 
 

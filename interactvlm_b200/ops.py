@@ -530,6 +530,16 @@ class LiftMap:
                                        self.ctx.stream), "lift")
         return out
 
+    def lowres(self, low: torch.Tensor, mode: int, thr: float = 0.3) -> torch.Tensor:
+        """low [B,V,sh,sw] fp32 low-res logits -> [B,n]: bilinear to (H,W) fused into the gather (ivlm_lift_lowres)."""
+        assert low.dtype == torch.float32 and low.is_cuda and low.is_contiguous() and low.dim() == 4
+        B = low.shape[0]
+        assert low.shape[1] == self.V, (low.shape, self.V)
+        out = torch.empty((B, self.n), device=low.device, dtype=torch.float32)
+        L.check(self.ctx.lib.ivlm_lift_lowres(self.ctx.h, self.ptr, P(low), i32(low.shape[2]), i32(low.shape[3]), P(out), i32(B),
+                                              i32(mode), f32c(thr), self.ctx.stream), "lift_lowres")
+        return out
+
     def __del__(self):
         try:
             if self.ptr:

@@ -36,6 +36,7 @@ def _r(x):
 class EmuLiftMap:
     def __init__(self, p2v, bary, n):
         self.p2v, self.bary, self.n = np.asarray(p2v), (None if bary is None else np.asarray(bary)), n
+        self.V, self.H, self.W = self.p2v.shape[:3]
 
     def __call__(self, masks, mode, thr=0.3):
         from oracle import lift as OL
@@ -46,6 +47,14 @@ class EmuLiftMap:
         if mode == 1:
             return torch.from_numpy(OL.lift_object_mesh(m, self.p2v, self.bary, self.n, thr))
         return torch.from_numpy(OL.lift_points(m, self.p2v, self.n))
+
+
+    def lowres(self, low, mode, thr=0.3):
+        """ivlm_lift_lowres: bilinear to the map size, then the lift (what the fused kernel computes)."""
+        import torch.nn.functional as F
+
+        H, W = self.p2v.shape[1], self.p2v.shape[2]
+        return self(F.interpolate(low.float(), (H, W), mode="bilinear", align_corners=False), mode, thr)
 
 
 class EmuContext:

@@ -89,3 +89,43 @@ def test_lift_edge_cases(ctx):
     empty = LiftMap(ctx, np.full((1, 4, 4, 3), -1, np.int64), np.zeros((1, 4, 4, 3), np.float32), 5)
     assert empty.nnz == 0
     assert empty(torch.randn(2, 1, 4, 4, device="cuda"), LIFT_HUMAN).abs().max().item() == 0
+
+
+def test_lowres_lift_is_bit_identical_to_upsample_then_lift(ctx, data):
+    """ivlm_lift_lowres evaluates the x4 bilinear of Sam.postprocess_masks per map entry: same bits as ivlm_bilinear_f32
+    followed by ivlm_lift, in all three modes, for a batch that spans two sample chunks (9 > LIFT_BC)."""
+    from interactvlm_b200.ops import LIFT_HUMAN, LIFT_OBJECT_MESH, LIFT_POINTS, LiftMap
+    from oracle import lift as OL
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    low = (torch.randn(9, 4, 256, 256, generator=g) * 4).bfloat16().float().cuda()   # bf16-valued like the decoder's output
+    full = ctx.bilinear(low.view(36, 256, 256), 1024, 1024).view(9, 4, 1024, 1024)
+    p2v, bary = S.make_mesh_lift_maps(seed=data["seed"]["maps"])
+    m = LiftMap(ctx, p2v, bary, S.N_SMPL)
+    a = m.lowres(low, LIFT_HUMAN)
+    assert torch.equal(a, m(full, LIFT_HUMAN))
+    assert torch.equal(m.lowres(low, LIFT_OBJECT_MESH, 0.3), m(full, LIFT_OBJECT_MESH, 0.3))
+    # against torch's own interpolate + the numpy oracle (reference op order)
+    ref_full = F.interpolate(low.cpu(), (1024, 1024), mode="bilinear", align_corners=False).numpy()
+    assert np.abs(a.cpu().numpy() - OL.lift_human(ref_full, p2v, bary, S.N_SMPL)).max() < 1e-6
+    p2p = S.make_point_lift_maps(seed=data["seed"]["points"])
+    mp = LiftMap(ctx, p2p, None, 2048)
+    assert torch.equal(mp.lowres(low, LIFT_POINTS), mp(full, LIFT_POINTS))
+
+
+def test_lift_nonpositive_weight_sum_keeps_raw_votes(ctx):
+    """components.py:257-262: votes are divided by the weight sum only where it is positive; elsewhere the raw votes are still
+    added to the prediction (and the view is not counted)."""
+    from interactvlm_b200.ops import LIFT_HUMAN, LIFT_OBJECT_MESH, LiftMap
+    from oracle import lift as OL
+    p2v = np.full((2, 4, 4, 3), -1, np.int64)
+    bary = np.zeros((2, 4, 4, 3), np.float32)
+    p2v[0, 1, 1] = [0, 1, 2]; bary[0, 1, 1] = [-0.25, 0.75, 0.5]     # vertex 0: negative weight sum in view 0
+    p2v[1, 2, 2] = [0, 1, 3]; bary[1, 2, 2] = [0.5, 0.25, 0.25]      # and a regular vote in view 1
+    m = LiftMap(ctx, p2v, bary, 5)
+    logits = np.random.default_rng(0).normal(0, 2, (1, 2, 4, 4)).astype(np.float32)
+    out = m(torch.from_numpy(logits).cuda(), LIFT_OBJECT_MESH, 0.0).cpu().numpy()
+    ref = OL.lift_object_mesh(logits, p2v, bary, 5, thr=0.0)
+    assert np.abs(out - ref).max() < 1e-6 and ref[0, 0] != 0
+    outh = m(torch.from_numpy(logits).cuda(), LIFT_HUMAN).cpu().numpy()
+    assert np.abs(outh - OL.lift_human(logits, p2v, bary, 5)).max() < 1e-6

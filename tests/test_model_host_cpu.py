@@ -62,15 +62,22 @@ def test_batch_of_two_and_missing_seg(setup):
     ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
     ans = ans.clone()
     ans[1, -3] = 5  # second sample never emits [SEG]
-    with pytest.raises(Exception):
-        # the reference indexes pred_masks[0] and lifts every sample; a sample without [SEG] has an empty mask stack
-        model.evaluate(clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, max_new_tokens=ans.shape[1], scripted=ans)
+    # batched extension of the reference's batch-1 rule (InteractVLM.py:596-601,618): a sample without [SEG] keeps an empty
+    # [0,H,W] mask stack and gets a zero contact row; the other samples are lifted as usual
+    out0 = model.evaluate(clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, max_new_tokens=ans.shape[1], scripted=ans)
+    assert out0["pred_masks"][1].shape[0] == 0 and out0["pred_masks"][0].shape[0] == cfg.multiview_channels
+    assert out0["pred_contact_3d"].shape == (2, S.N_SMPL) and float(out0["pred_contact_3d"][1].abs().max()) == 0.0
+    # no sample with a [SEG] at all: None, like the reference
+    ans0 = ans.clone()
+    ans0[0, -3] = 5
+    assert model.evaluate(clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, max_new_tokens=ans.shape[1], scripted=ans0)["pred_contact_3d"] is None
     ans[1, -3] = cfg.seg_token_idx
     out = model.evaluate(clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, max_new_tokens=ans.shape[1], scripted=ans)
     ref = OM.evaluate(sd, cfg, clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, lift_maps=(p2v, bary, S.N_SMPL),
                       max_new_tokens=ans.shape[1], scripted=ans)
     assert out["pred_contact_3d"].shape == (2, S.N_SMPL)
     assert np.abs(out["pred_contact_3d"].numpy() - ref["pred_contact_3d"].numpy()).max() < 0.08
+    assert torch.equal(out["pred_contact_3d"][0], out0["pred_contact_3d"][0])   # sample 0 does not depend on its neighbour
 
 
 def test_view_cache_bookkeeping(setup):
