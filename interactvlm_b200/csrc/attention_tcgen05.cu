@@ -920,13 +920,12 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
     p.KH = Hq;
     p.scale_log2 = (1.0f / sqrtf((float)hd)) * AT_LOG2E;
     dim3 grid((S + AT_BQ - 1) / AT_BQ, heads, B);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(h->attr_done & (1ull << 16))) {   // per handle = per device
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_window_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WN_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_global64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
-        attr_set = true;
+        h->attr_done |= 1ull << 16;
     }
     if (Wq == 64 && h->global_attn_variant == 0) {
         const CUtensorMap *kva, *kvb;

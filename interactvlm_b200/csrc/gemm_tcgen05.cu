@@ -515,6 +515,11 @@ int get_tmap_bf16_ex(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols,
         *out = &it->second;
         return IVLM_OK;
     }
+    it = h->tmaps_old.find(key);
+    if (it != h->tmaps_old.end()) {
+        *out = &it->second;
+        return IVLM_OK;
+    }
     auto enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -542,7 +547,10 @@ int get_tmap_bf16_ex(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols,
                   swizzle_bytes);
         return IVLM_ERR_CUDA;
     }
-    if (h->tmaps.size() > 4096) h->tmaps.clear();  // activations churn pointers; keep the cache bounded
+    if (h->tmaps.size() >= IVLM_TMAP_GEN) {  // retire a generation (see runtime.h): earlier pointers stay valid
+        h->tmaps_old.swap(h->tmaps);
+        h->tmaps.clear();
+    }
     auto ins = h->tmaps.emplace(key, m);
     *out = &ins.first->second;
     return IVLM_OK;
@@ -557,11 +565,12 @@ template <int BN>
 static int launch_gemm(ivlm_ctx* h, const CUtensorMap* ta, const CUtensorMap* tb, const GemmParams& p,
                        cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device: remembered per handle (a handle is bound to one device), bit = log2(BN)
+    const uint64_t attr_bit = 1ull << (BN == 256 ? 8 : BN == 128 ? 7 : BN == 64 ? 6 : BN == 32 ? 5 : 4);
+    if (!(h->attr_done & attr_bit)) {
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES));
-        attr_set = true;
+        h->attr_done |= attr_bit;
     }
     const int units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
     // SM partitioning (option "sm_limit"): a token-major GEMM of a low-priority stream keeps to a subset of the SMs so

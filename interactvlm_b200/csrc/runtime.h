@@ -42,6 +42,7 @@ void set_error(const char* fmt, ...);
 // Layout of the caller-provided workspace: [0, IVLM_WS_COUNTER_BYTES) int tile counters (zeroed by ivlm_set_workspace,
 // self-resetting), then fp32 split-K partial tiles.
 constexpr size_t IVLM_WS_COUNTER_BYTES = 65536;
+constexpr size_t IVLM_TMAP_GEN = 2048;
 
 struct TmapKey {
     const void* ptr;
@@ -94,7 +95,12 @@ struct ivlm_ctx {
     int small_m_variant = 0;      // 0: weight-streaming mma.sync kernel for token counts <= 64; 1: swapped-operand tcgen05 path
     int global_attn_variant = 0;  // 0: 64-key tiles, 2 CTAs/SM; 1: 128-key tiles, 1 CTA/SM (A/B switch)
     int window_attn_variant = 0;  // 0: single-tile 2-CTA/SM window kernel, 1: the general tiled kernel (A/B switch)
-    std::unordered_map<ivlm::TmapKey, CUtensorMap, ivlm::TmapKeyHash> tmaps;
+    // TMA descriptor cache in two generations: lookups see both, inserts go to `tmaps`; when it holds IVLM_TMAP_GEN entries it
+    // becomes `tmaps_old` (whose previous content is dropped).  A pointer handed out therefore stays valid for at least
+    // IVLM_TMAP_GEN further insertions -- one call fetches at most a handful -- while activations that churn addresses cannot
+    // grow the cache without bound.  (unordered_map never moves its nodes on insert.)
+    std::unordered_map<ivlm::TmapKey, CUtensorMap, ivlm::TmapKeyHash> tmaps, tmaps_old;
+    uint64_t attr_done = 0;       // bit i: cudaFuncSetAttribute done on this handle's device for kernel variant i (per handle = per device)
     std::unordered_map<std::string, ivlm::Weight> weights;
     // caller-provided scratch (bump allocated inside stage drivers)
     char* ws = nullptr;

@@ -187,6 +187,7 @@ class _Engine:
         self.device = w.device
         self._win_maps = {}
         self.fused_sam_attention = True
+        self.trace = None  # tests: dict of lists receiving the residual stream after every SAM block / LLaMA prefill layer
 
     # ------------------------------------------------------------------ CLIP + projector (a4)
     def clip_encode(self, images_clip):
@@ -267,6 +268,8 @@ class _Engine:
             y = ctx.gemm(y, bw["w1"], bias=bw["b1"], act=ACT_GELU, force_swap=-1)
             x = ctx.gemm(y, bw["w2"], bias=bw["b2"], residual=x, force_swap=-1)
             del y
+            if self.trace is not None:
+                self.trace.setdefault("sam", []).append(x)
         y = ctx.gemm(x, w["neck0"], force_swap=-1)
         y = ctx.layernorm(y, w["n1g"], w["n1b"], 1e-6)
         cols = ctx.im2col_3x3(y, N, g, g)
@@ -306,6 +309,8 @@ class _Engine:
             y = ctx.rmsnorm(x, lw["ln2"], cfg.rms_norm_eps)
             y = ctx.silu_mul(ctx.gemm(y, lw["wgu"]))
             x = ctx.gemm(y, lw["wd"], residual=x)
+            if self.trace is not None:
+                self.trace.setdefault("llm", []).append(x)
         hn = ctx.rmsnorm(x, W.norm, cfg.rms_norm_eps).view(B, S, D)
         st["hidden"][:, :S] = hn
         st["len"] = S

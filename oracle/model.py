@@ -128,8 +128,9 @@ def _rmsnorm(x, g, eps):
     return g * xf.to(x.dtype)
 
 
-def llama_forward(w: W, cfg, embeds):
-    """embeds [B,S,D] -> last hidden state after the final RMSNorm [B,S,D] (causal, no padding)."""
+def llama_forward(w: W, cfg, embeds, trace=None):
+    """embeds [B,S,D] -> last hidden state after the final RMSNorm [B,S,D] (causal, no padding).
+    trace (optional list): receives the residual stream after every layer (tests: per-layer error curves)."""
     B, S, D = embeds.shape
     nh, hd = cfg.num_attention_heads, cfg.head_dim
     cos, sin = (t.to(embeds.device) for t in _rope_tables(cfg, S, embeds.dtype))
@@ -153,6 +154,8 @@ def llama_forward(w: W, cfg, embeds):
         y = _rmsnorm(h, w("post_attention_layernorm.weight", p), cfg.rms_norm_eps)
         y = F.silu(F.linear(y, w("mlp.gate_proj.weight", p))) * F.linear(y, w("mlp.up_proj.weight", p))
         h = r + F.linear(y, w("mlp.down_proj.weight", p))
+        if trace is not None:
+            trace.append(h)
     return _rmsnorm(h, w("model.norm.weight"), cfg.rms_norm_eps)
 
 
@@ -264,8 +267,8 @@ def _ln2d(x, g, b, eps=1e-6):
     return g[:, None, None] * x + b[:, None, None]
 
 
-def sam_image_encoder(w: W, cfg, images):
-    """images [N,3,1024,1024] -> [N,256,64,64]."""
+def sam_image_encoder(w: W, cfg, images, trace=None):
+    """images [N,3,1024,1024] -> [N,256,64,64].  trace (optional list): the token grid after every block."""
     e = SAM_PREFIX + "image_encoder."
     x = F.conv2d(images.to(w.device, w.dtype), w("patch_embed.proj.weight", e), w("patch_embed.proj.bias", e),
                  stride=cfg.sam_patch_size).permute(0, 2, 3, 1)
@@ -291,6 +294,8 @@ def sam_image_encoder(w: W, cfg, images):
         y = F.linear(F.gelu(F.linear(y, w("mlp.lin1.weight", p), w("mlp.lin1.bias", p))), w("mlp.lin2.weight", p),
                      w("mlp.lin2.bias", p))
         x = x + y
+        if trace is not None:
+            trace.append(x)
     x = x.permute(0, 3, 1, 2)
     x = F.conv2d(x, w("neck.0.weight", e))
     x = _ln2d(x, w("neck.1.weight", e), w("neck.1.bias", e))

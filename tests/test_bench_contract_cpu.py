@@ -19,7 +19,7 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"].startswith("images/sec") and line["unit"] == "images/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "no KV cache" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "WITHOUT KV cache" in cb["sample"] and "not extrapolated" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and "workload" in line["config"]
 
