@@ -46,6 +46,25 @@ class AttnArgs(C.Structure):
     ]
 
 
+class DecodeLinearArgs(C.Structure):
+    """ivlm_decode_linear_args (include/ivlm_b200.h)."""
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_int64),
+        ("w", C.c_void_p), ("ldw", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("norm_gamma", C.c_void_p), ("norm_eps", C.c_float),
+        ("epilogue", C.c_int32), ("act", C.c_int32),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("out_dtype", C.c_int32),
+        ("positions", C.c_void_p), ("slot_map", C.c_void_p), ("cos_t", C.c_void_p), ("sin_t", C.c_void_p),
+        ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
+        ("H", C.c_int32), ("hd", C.c_int32), ("page_size", C.c_int32),
+    ]
+
+
+EPI_PLAIN, EPI_SWIGLU, EPI_ROPE_KV = 0, 1, 2
+
+
 class RasterCam(C.Structure):
     """ivlm_raster_cam (include/ivlm_b200.h)."""
     _fields_ = [("R", C.c_float * 9), ("T", C.c_float * 3), ("C", C.c_float * 3), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),

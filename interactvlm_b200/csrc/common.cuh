@@ -113,10 +113,13 @@ IVLM_DEVINL BilinearTap bilinear_tap(int y, int x, float sy, float sx, int ch, i
     t.o00 = y0 * sw + x0; t.o01 = y0 * sw + x1; t.o10 = y1 * sw + x0; t.o11 = y1 * sw + x1;
     return t;
 }
-IVLM_DEVINL float bilinear_eval(const BilinearTap& t, const float* __restrict__ s) {
-    const float top = __fadd_rn(__fmul_rn(t.hx, __ldg(s + t.o00)), __fmul_rn(t.lx, __ldg(s + t.o01)));
-    const float bot = __fadd_rn(__fmul_rn(t.hx, __ldg(s + t.o10)), __fmul_rn(t.lx, __ldg(s + t.o11)));
+IVLM_DEVINL float bilinear_combine(const BilinearTap& t, float v00, float v01, float v10, float v11) {
+    const float top = __fadd_rn(__fmul_rn(t.hx, v00), __fmul_rn(t.lx, v01));
+    const float bot = __fadd_rn(__fmul_rn(t.hx, v10), __fmul_rn(t.lx, v11));
     return __fadd_rn(__fmul_rn(t.hy, top), __fmul_rn(t.ly, bot));
+}
+IVLM_DEVINL float bilinear_eval(const BilinearTap& t, const float* __restrict__ s) {
+    return bilinear_combine(t, __ldg(s + t.o00), __ldg(s + t.o01), __ldg(s + t.o10), __ldg(s + t.o11));
 }
 IVLM_DEVINL void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -1,0 +1,368 @@
+// Weight-streaming linear layer for LLaMA decode steps (token count M <= 8) with the neighbouring row-wise work fused in:
+//
+//   out[M,N] = epilogue( rmsnorm?(A)[M,K] . W[N,K]^T )
+//
+//   prologue (optional)  HF LlamaRMSNorm of the activation rows (transformers 4.31 modeling_llama.py: variance in fp32, value
+//                        cast to bf16, times the bf16 weight) -- every CTA normalises the M x K activation into shared memory
+//                        itself (80 KB read from L2), so the separate rmsnorm launch and its round trip disappear;
+//   epilogue PLAIN       bias / activation / residual with the rounding points of the other GEMM kernels (o_proj, down_proj,
+//                        lm_head);
+//            SWIGLU      HF LlamaMLP gate: out[m,f] = bf16(bf16(silu(gate[m,f])) * up[m,f]); the weight rows are stored
+//                        INTERLEAVED (8 gate rows, then the 8 up rows of the same features) so one 16-row tile holds both;
+//            ROPE_KV     HF apply_rotary_pos_emb on q and k (bf16 products and sum, bf16 cos/sin tables) + the write of k, v
+//                        into the paged cache and of q into its buffer; q/k weight rows are stored PAIRED (8 rows j, then
+//                        the 8 rows j + hd/2 of the same head) so the two halves of a rotation meet in one tile.
+//
+// A decode step reads every weight once for <= 8 tokens: the launch is HBM-bound and built around the byte stream.
+//   * persistent: one CTA per SM; the (16-row tile) x (512-column stage) grid of the weight matrix is cut into equal CONTIGUOUS
+//     stage ranges, one per CTA (no wave quantisation: 320 or 960 tiles never divide by 148 SMs);
+//   * one producer thread per CTA keeps an 8-deep ring of 16 KB stages full with cp.async.bulk (1 KB per weight row, completion
+//     on an mbarrier), >= 128 KB in flight per SM whatever the consumers do; the first ring of weights is requested BEFORE
+//     griddepcontrol.wait (weights are static), so under programmatic dependent launch it streams under the predecessor's tail;
+//   * eight consumer warps split the 32 k16-steps of a stage (ldmatrix + mma.sync m16n8k16: 16 weight rows x 8 tokens), keep
+//     their partial tile in registers across the stages of a tile and fold it through shared memory in warp order;
+//   * a tile cut by a range boundary is finished by the CTA that holds its first stages: the CTA holding the rest computes that
+//     part FIRST, parks it in the workspace and raises a flag (self-resetting; fixed summation order -> deterministic).
+// No tensor-core tile shape drives this kernel (tcgen05 needs 128-row operands and buys nothing at 16 FLOP per byte).
+#include "common.cuh"
+#include "runtime.h"
+
+namespace ivlm {
+
+constexpr int DS_ROWS = 16, DS_KW = 512, DS_PITCH = DS_KW + 8, DS_STAGES = 8, DS_CONSUMERS = 8, DS_MAX_M = 8;
+constexpr int DS_THREADS = (DS_CONSUMERS + 1) * 32;
+constexpr int DS_FLAG_OFFSET_BYTES = (int)IVLM_WS_COUNTER_BYTES - 4096;  // last 1024 ints of the counter region
+
+enum { DS_EPI_PLAIN = 0, DS_EPI_SWIGLU = 1, DS_EPI_ROPE_KV = 2 };
+
+struct DecodeStreamParams {
+    const bf16* a;  long long lda;   // [M,K] activations (un-normalised when gamma != nullptr)
+    const bf16* w;  long long ldw;   // [N,K] weights (row layout as the epilogue requires)
+    int M, N, K;
+    const bf16* gamma; float eps;    // fused RMSNorm or nullptr
+    int epi, act, out_f32, round_steps;
+    const bf16* bias; const bf16* res; long long ldr;
+    void* out; long long ldo;
+    // ROPE_KV
+    const int* positions; const int* slot_map; const bf16* cos_t; const bf16* sin_t;
+    bf16* k_cache; bf16* v_cache; int H, hd, page;
+    // decomposition
+    int tiles, spt, total_stages;    // spt = stages per tile
+    int resident;                    // 1: the whole activation sits in shared memory (required with gamma)
+    float* partial; int* flags;
+};
+
+IVLM_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+IVLM_DEVINL void ldmatrix_x2(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(smem_row)));
+}
+IVLM_DEVINL int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+IVLM_DEVINL void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const DecodeStreamParams p) {
+    extern __shared__ __align__(128) uint8_t ds_smem[];
+    // [full bars | empty bars] [red: 8 warps x 16 x 8 fp32] [fin: 16 x 8 fp32] [resident activation] [ring]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ds_smem);
+    uint64_t* empty = full + DS_STAGES;
+    float* red = reinterpret_cast<float*>(ds_smem + 128);
+    float* fin = red + DS_CONSUMERS * 128;
+    bf16* act = reinterpret_cast<bf16*>(fin + 128);
+    const int act_pitch = p.K + 8;
+    const int stage_rows = DS_ROWS + (p.resident ? 0 : DS_MAX_M);
+    bf16* ring = act + (p.resident ? (size_t)DS_MAX_M * act_pitch : 0);
+    const size_t stage_elems = (size_t)stage_rows * DS_PITCH;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int s_begin = (int)((long long)p.total_stages * cta / G), s_end = (int)((long long)p.total_stages * (cta + 1) / G);
+    const int n_my = s_end - s_begin;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < DS_STAGES; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, DS_CONSUMERS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == DS_CONSUMERS) {
+        // ------------------------------------------------------------------ producer (one thread)
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();   // every weight byte is used once per step
+            auto issue_weights = [&](int it) {
+                const int s = s_begin + it, slot = it % DS_STAGES;
+                const int tile = s / p.spt, k0 = (s % p.spt) * DS_KW;
+                const int kw = min(DS_KW, p.K - k0), rows = min(DS_ROWS, p.N - tile * DS_ROWS);
+                const uint32_t bytes = (uint32_t)(rows * kw * 2 + (p.resident ? 0 : p.M * kw * 2));
+                mbar_arrive_expect_tx(full + slot, bytes);
+                bf16* dst = ring + slot * stage_elems;
+                const bf16* src = p.w + (long long)tile * DS_ROWS * p.ldw + k0;
+                for (int r = 0; r < rows; ++r) bulk_g2s(dst + r * DS_PITCH, src + (long long)r * p.ldw, (uint32_t)kw * 2, full + slot, pol);
+            };
+            auto issue_acts = [&](int it) {
+                const int s = s_begin + it, slot = it % DS_STAGES;
+                const int k0 = (s % p.spt) * DS_KW, kw = min(DS_KW, p.K - k0);
+                bf16* dst = ring + slot * stage_elems + DS_ROWS * DS_PITCH;
+                const uint64_t keep = l2_policy_evict_last();
+                for (int m = 0; m < p.M; ++m) bulk_g2s(dst + m * DS_PITCH, p.a + (long long)m * p.lda + k0, (uint32_t)kw * 2, full + slot, keep);
+            };
+            const int n_pre = min(DS_STAGES, n_my);
+            for (int it = 0; it < n_pre; ++it) issue_weights(it);   // static operands: before the dependency wait
+            pdl_launch();
+            pdl_wait();
+            if (!p.resident)
+                for (int it = 0; it < n_pre; ++it) issue_acts(it);
+            for (int it = n_pre; it < n_my; ++it) {
+                mbar_wait(empty + it % DS_STAGES, ((it / DS_STAGES) - 1) & 1);
+                issue_weights(it);
+                if (!p.resident) issue_acts(it);
+            }
+        } else {
+            pdl_launch();
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers (8 warps)
+    pdl_launch();
+    pdl_wait();
+    const int g = lane >> 2, t = lane & 3;
+    if (p.resident) {
+        // warp m stages token m: raw copy + sum of squares (the association of rmsnorm_kernel), then normalise in place
+        const int nvec = p.K >> 3;
+        for (int m = warp; m < DS_MAX_M; m += DS_CONSUMERS) {
+            uint4* dst = reinterpret_cast<uint4*>(act + (size_t)m * act_pitch);
+            if (m >= p.M) {
+                for (int i = lane; i < nvec; i += 32) dst[i] = make_uint4(0, 0, 0, 0);
+                continue;
+            }
+            const uint4* xr = reinterpret_cast<const uint4*>(p.a + (long long)m * p.lda);
+            float ss = 0.f;
+            for (int i = lane; i < nvec; i += 32) {
+                const uint4 q = xr[i];
+                dst[i] = q;
+                const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+                ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+            }
+            if (p.gamma != nullptr) {
+                const float rstd = rsqrtf(warp_sum(ss) / (float)p.K + p.eps);
+                const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma);
+                for (int i = lane; i < nvec; i += 32) {
+                    const uint4 q = dst[i], gm = g4[i];
+                    const uint32_t xi[4] = {q.x, q.y, q.z, q.w}, gi[4] = {gm.x, gm.y, gm.z, gm.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 xv = unpack_bf16x2(xi[j]), gv = unpack_bf16x2(gi[j]);
+                        o[j] = pack_bf16x2(gv.x * bf16_round(xv.x * rstd), gv.y * bf16_round(xv.y * rstd));
+                    }
+                    dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        named_bar_sync(1, DS_CONSUMERS * 32);
+    }
+
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    // ldmatrix lane addressing. A (weights): matrices (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15)
+    const int a_row = ((lane >> 3) & 1) * 8 + (lane & 7), a_kofs = (lane >> 4) * 8;
+    // B (tokens, stored [token][k]): matrices (tokens 0-7, k 0-7), (tokens 0-7, k 8-15); lanes 16-31 repeat valid addresses
+    const int b_row = lane & 7, b_kofs = ((lane >> 3) & 1) * 8;
+
+    for (int it = 0; it < n_my; ++it) {
+        const int s = s_begin + it, slot = it % DS_STAGES;
+        const int tile = s / p.spt, ks = s % p.spt, k0 = ks * DS_KW;
+        const int kw = min(DS_KW, p.K - k0);
+        mbar_wait(full + slot, (it / DS_STAGES) & 1);
+        const bf16* st = ring + slot * stage_elems;
+        const bf16* a_base = st + a_row * DS_PITCH + a_kofs;
+        const bf16* b_base = p.resident ? act + (size_t)b_row * act_pitch + k0 + b_kofs
+                                        : st + (DS_ROWS + b_row) * DS_PITCH + b_kofs;
+        const int n16 = kw >> 4;
+        for (int j = warp; j < n16; j += DS_CONSUMERS) {
+            uint32_t af[4], b0, b1;
+            ldmatrix_x4(af[0], af[1], af[2], af[3], a_base + j * 16);
+            ldmatrix_x2(b0, b1, b_base + j * 16);
+            mma_bf16_16816(c, af, b0, b1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+
+        const bool tile_end = (ks == p.spt - 1), range_end = (it == n_my - 1);
+        if (!tile_end && !range_end) continue;
+        // ---- fold the eight partial tiles (warp order), then finish or hand over the tile
+        float* pw = red + warp * 128;
+        pw[g * 8 + 2 * t] = c[0];
+        pw[g * 8 + 2 * t + 1] = c[1];
+        pw[(g + 8) * 8 + 2 * t] = c[2];
+        pw[(g + 8) * 8 + 2 * t + 1] = c[3];
+        c[0] = c[1] = c[2] = c[3] = 0.f;
+        named_bar_sync(1, DS_CONSUMERS * 32);
+        const int e = threadIdx.x;                       // 0..255; the first 128 threads own one (row, token) each
+        const int rl = e & 15, tok = (e >> 4) & 7;
+        const bool head_part = (tile * p.spt < s_begin);          // this CTA does not hold the tile's first stage: contributor
+        const bool cut_tail = (!tile_end);                        // the tile continues in the next CTA: this CTA finishes it
+        float x = 0.f;
+        if (e < 128) {
+#pragma unroll
+            for (int w = 0; w < DS_CONSUMERS; ++w) x += red[w * 128 + rl * 8 + tok];
+        }
+        if (head_part) {
+            if (e < 128) p.partial[(size_t)cta * 128 + e] = x;
+            __threadfence();
+            named_bar_sync(1, DS_CONSUMERS * 32);
+            if (e == 0) st_release(p.flags + cta, 1);
+            continue;
+        }
+        if (cut_tail) {
+            if (e == 0) {
+                const uint64_t t0 = global_timer_ns();
+                while (ld_acquire(p.flags + cta + 1) == 0) {
+                    if (global_timer_ns() - t0 > 5000000000ull) {
+                        printf("ivlm: decode_stream partial-tile wait timeout cta=%d\n", cta);
+                        __trap();
+                    }
+                }
+            }
+            named_bar_sync(1, DS_CONSUMERS * 32);
+            if (e < 128) x += __ldcg(p.partial + (size_t)(cta + 1) * 128 + e);
+            named_bar_sync(1, DS_CONSUMERS * 32);
+            if (e == 0) p.flags[cta + 1] = 0;   // self-resetting: the next launch finds it clear (stream order)
+        }
+        // ---- epilogue
+        const int row0 = tile * DS_ROWS;
+        if (p.epi == DS_EPI_PLAIN) {
+            const int row = row0 + rl;
+            if (e < 128 && row < p.N && tok < p.M) {
+                if (p.bias != nullptr) x += __bfloat162float(p.bias[row]);
+                if (p.round_steps) x = bf16_round(x);
+                if (p.act != ACT_NONE) {
+                    x = apply_act(x, p.act);
+                    if (p.round_steps) x = bf16_round(x);
+                }
+                if (p.res != nullptr) x += __bfloat162float(p.res[(long long)tok * p.ldr + row]);
+                const long long oi = (long long)tok * p.ldo + row;
+                if (p.out_f32) reinterpret_cast<float*>(p.out)[oi] = x;
+                else reinterpret_cast<bf16*>(p.out)[oi] = __float2bfloat16_rn(x);
+            }
+        } else {
+            if (e < 128) fin[rl * 8 + tok] = bf16_round(x);   // the Linear output as the reference holds it (bf16)
+            named_bar_sync(1, DS_CONSUMERS * 32);
+            if (e < 64 && (e >> 3) < p.M) {
+                const int j8 = e & 7, tk = e >> 3;            // 8 features x 8 tokens
+                const float lo = fin[j8 * 8 + tk], hi = fin[(j8 + 8) * 8 + tk];
+                if (p.epi == DS_EPI_SWIGLU) {
+                    // rows 0-7: gate of features 8*tile + j8, rows 8-15: up of the same features
+                    const float v = bf16_round(apply_act(lo, ACT_SILU)) * hi;
+                    reinterpret_cast<bf16*>(p.out)[(long long)tk * p.ldo + tile * 8 + j8] = __float2bfloat16_rn(v);
+                } else {
+                    const int D = p.H * p.hd, half = p.hd >> 1;
+                    const int sec = row0 / D, r = row0 - sec * D;
+                    const long long slot_i = p.slot_map[tk];
+                    const long long pg = slot_i / p.page, off = slot_i % p.page;
+                    if (sec < 2) {
+                        const int hh = r / p.hd, j = ((r % p.hd) >> 4) * 8 + j8;   // rotary pair (j, j + half) of head hh
+                        const int pos = p.positions[tk];
+                        const float cs = __bfloat162float(p.cos_t[(long long)pos * p.hd + j]);
+                        const float sn = __bfloat162float(p.sin_t[(long long)pos * p.hd + j]);
+                        const bf16 o1 = __float2bfloat16_rn(bf16_round(lo * cs) + bf16_round(-hi * sn));
+                        const bf16 o2 = __float2bfloat16_rn(bf16_round(hi * cs) + bf16_round(lo * sn));
+                        if (sec == 0) {
+                            bf16* q = reinterpret_cast<bf16*>(p.out) + (long long)tk * p.ldo + hh * p.hd;
+                            q[j] = o1;
+                            q[j + half] = o2;
+                        } else {
+                            bf16* kc = p.k_cache + ((pg * p.H + hh) * p.page + off) * p.hd;
+                            kc[j] = o1;
+                            kc[j + half] = o2;
+                        }
+                    } else {
+                        // v rows are in natural order: 16 consecutive features of one head
+                        const int f0 = r + j8;
+                        bf16* vc0 = p.v_cache + ((pg * p.H + f0 / p.hd) * p.page + off) * p.hd;
+                        vc0[f0 % p.hd] = __float2bfloat16_rn(lo);
+                        const int f1 = f0 + 8;
+                        bf16* vc1 = p.v_cache + ((pg * p.H + f1 / p.hd) * p.page + off) * p.hd;
+                        vc1[f1 % p.hd] = __float2bfloat16_rn(hi);
+                    }
+                }
+            }
+        }
+        named_bar_sync(1, DS_CONSUMERS * 32);   // red / fin are free again
+    }
+}
+
+}  // namespace ivlm
+
+using namespace ivlm;
+
+extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    IVLM_REQUIRE(h && a && a->a && a->w && a->out, "decode_linear: null argument");
+    IVLM_REQUIRE(a->M >= 1 && a->M <= DS_MAX_M, "decode_linear: token count %d outside 1..%d", a->M, DS_MAX_M);
+    IVLM_REQUIRE(a->N > 0 && a->K >= 16 && a->K % 16 == 0, "decode_linear: N=%d K=%d (K must be a multiple of 16)", a->N, a->K);
+    IVLM_REQUIRE((a->lda * 2) % 16 == 0 && (a->ldw * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->a) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
+                 "decode_linear: operands must be 16-byte aligned with 16-byte row pitches");
+    IVLM_REQUIRE(a->epilogue >= DS_EPI_PLAIN && a->epilogue <= DS_EPI_ROPE_KV, "decode_linear: unknown epilogue %d", a->epilogue);
+    IVLM_REQUIRE(h->ws != nullptr && h->ws_bytes >= IVLM_WS_COUNTER_BYTES + (size_t)(h->num_sms + 1) * 512,
+                 "decode_linear: bind a workspace first (ivlm_set_workspace)");
+    DecodeStreamParams p = {};
+    p.a = reinterpret_cast<const bf16*>(a->a); p.lda = a->lda;
+    p.w = reinterpret_cast<const bf16*>(a->w); p.ldw = a->ldw;
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.gamma = reinterpret_cast<const bf16*>(a->norm_gamma); p.eps = a->norm_eps;
+    p.epi = a->epilogue; p.act = a->act;
+    p.out_f32 = a->out_dtype == IVLM_F32;
+    p.round_steps = a->out_dtype == IVLM_BF16 ? 1 : 0;
+    p.bias = reinterpret_cast<const bf16*>(a->bias);
+    p.res = reinterpret_cast<const bf16*>(a->residual); p.ldr = a->ldr;
+    p.out = a->out; p.ldo = a->ldo;
+    if (a->epilogue == DS_EPI_SWIGLU) {
+        IVLM_REQUIRE(a->N % 16 == 0 && !a->bias && !a->residual && a->out_dtype == IVLM_BF16,
+                     "decode_linear: SWIGLU needs interleaved gate/up rows (N %% 16 == 0), bf16 output, no bias/residual");
+    }
+    if (a->epilogue == DS_EPI_ROPE_KV) {
+        IVLM_REQUIRE(a->positions && a->slot_map && a->cos_t && a->sin_t && a->k_cache && a->v_cache && a->H > 0 && a->hd > 0 &&
+                         a->hd % 16 == 0 && a->N == 3 * a->H * a->hd && a->page_size > 0 && a->out_dtype == IVLM_BF16 && !a->bias &&
+                         !a->residual,
+                     "decode_linear: ROPE_KV needs N == 3*H*hd, hd %% 16 == 0, tables, cache and slot map, bf16 q output");
+        p.positions = a->positions; p.slot_map = a->slot_map;
+        p.cos_t = reinterpret_cast<const bf16*>(a->cos_t); p.sin_t = reinterpret_cast<const bf16*>(a->sin_t);
+        p.k_cache = reinterpret_cast<bf16*>(a->k_cache); p.v_cache = reinterpret_cast<bf16*>(a->v_cache);
+        p.H = a->H; p.hd = a->hd; p.page = a->page_size;
+    }
+    p.tiles = (a->N + DS_ROWS - 1) / DS_ROWS;
+    p.spt = (a->K + DS_KW - 1) / DS_KW;
+    p.total_stages = p.tiles * p.spt;
+    // shared memory: barriers + fold buffers, the resident activation (when it fits next to a useful ring), the ring
+    const size_t fixed = 128 + (DS_CONSUMERS + 1) * 128 * sizeof(float);
+    const size_t act_bytes = (size_t)DS_MAX_M * (a->K + 8) * 2;
+    const size_t ring_res = (size_t)DS_STAGES * DS_ROWS * DS_PITCH * 2, ring_str = (size_t)DS_STAGES * (DS_ROWS + DS_MAX_M) * DS_PITCH * 2;
+    const size_t cap = 227 * 1024;
+    p.resident = (fixed + act_bytes + ring_res <= cap) ? 1 : 0;
+    IVLM_REQUIRE(p.resident || a->norm_gamma == nullptr, "decode_linear: fused RMSNorm needs K <= %d (activation resident in shared memory)",
+                 (int)((cap - fixed - ring_res) / (2 * DS_MAX_M) - 8));
+    const size_t smem = fixed + (p.resident ? act_bytes + ring_res : ring_str);
+    // one CTA per SM, but never more CTAs than whole tiles: a range then always reaches the end of the tile it starts in
+    int grid = h->num_sms < p.tiles ? h->num_sms : p.tiles;
+    p.partial = reinterpret_cast<float*>(h->ws + IVLM_WS_COUNTER_BYTES);
+    p.flags = reinterpret_cast<int*>(h->ws + DS_FLAG_OFFSET_BYTES);
+    if (!(h->attr_done & (1ull << 20))) {
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        h->attr_done |= 1ull << 20;
+    }
+    IVLM_CHECK_CUDA(launch_k(h, decode_stream_kernel, dim3(grid), dim3(DS_THREADS), smem, stream, p));
+    h->launches++;
+    return IVLM_OK;
+}

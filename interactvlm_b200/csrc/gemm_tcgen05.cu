@@ -658,7 +658,7 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
         }
         if (h->fused_split_force > 0) best = h->fused_split_force;  // A/B knob (tools/prof_decode.py splits)
         const size_t need = (size_t)tiles * best * BM * bn * sizeof(float) + (size_t)tiles * sizeof(int) + 256;
-        if (best > 1 && need <= h->ws_bytes - IVLM_WS_COUNTER_BYTES && (size_t)tiles * sizeof(int) <= IVLM_WS_COUNTER_BYTES) {
+        if (best > 1 && need <= h->ws_bytes - IVLM_WS_COUNTER_BYTES && (size_t)tiles * sizeof(int) <= IVLM_WS_COUNTER_BYTES - 4096 /* the last 4 KB are decode_stream's flags */) {
             p.k_splits = best;
             p.fused_split = 1;
             p.ws_counter = reinterpret_cast<int*>(h->ws);

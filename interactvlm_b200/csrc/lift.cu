@@ -38,58 +38,71 @@ namespace ivlm {
 // lifting the materialised 1024^2 logits, which are then never read: 1.05 MB instead of 16.8 MB per sample).
 constexpr int LIFT_BC = 8, LIFT_WARPS = 4, LIFT_MAX_VIEWS = 8;
 
-template <int MODE, bool LOWRES>
+template <int MODE, bool LOWRES, int BC>
 __global__ void __launch_bounds__(LIFT_WARPS * 32)
 lift_warp_kernel(const int* __restrict__ row_ptr, const int* __restrict__ pix, const float* __restrict__ wgt,
                  const float* __restrict__ src, float* __restrict__ contact, int B, int V, int n, int H, int W, int sh, int sw,
                  float thr) {
-    const int vtx = blockIdx.x, b0 = blockIdx.y * LIFT_BC;
-    const int nb = min(LIFT_BC, B - b0);
+    const int vtx = blockIdx.x, b0 = blockIdx.y * BC;
+    const int nb = min(BC, B - b0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ float s_votes[LIFT_MAX_VIEWS][LIFT_BC], s_cnt[LIFT_MAX_VIEWS][LIFT_BC];
+    __shared__ float s_votes[LIFT_MAX_VIEWS][BC], s_cnt[LIFT_MAX_VIEWS][BC];
     const long long plane = LOWRES ? (long long)sh * sw : (long long)H * W;
     const float sy = (float)sh / (float)H, sx = (float)sw / (float)W;
     for (int v = warp; v < V; v += LIFT_WARPS) {
         const int e0 = row_ptr[v * n + vtx], e1 = row_ptr[v * n + vtx + 1];
-        float votes[LIFT_BC], cnt[LIFT_BC];
+        float votes[BC], cnt[BC];
 #pragma unroll
-        for (int s = 0; s < LIFT_BC; ++s) votes[s] = cnt[s] = 0.f;
-        const float* base = src + ((long long)b0 * V + v) * plane;
+        for (int s = 0; s < BC; ++s) votes[s] = cnt[s] = 0.f;
+        // sample slots past the batch end alias the last valid sample: every load below is unconditional, so all BC (x4 taps)
+        // gathers of an entry are in flight together instead of one L2 round trip after the other
+        const float* ms[BC];
+#pragma unroll
+        for (int s = 0; s < BC; ++s) ms[s] = src + ((long long)(b0 + min(s, nb - 1)) * V + v) * plane;
         for (int e = e0 + lane; e < e1; e += 32) {
             const int p = __ldg(pix + e);
             const float w = (MODE == IVLM_LIFT_POINTS) ? 1.f : __ldg(wgt + e);
-            BilinearTap t;
-            if (LOWRES) t = bilinear_tap(p / W, p % W, sy, sx, sh, sw, sw);
+            float x[BC];
+            if (LOWRES) {
+                const BilinearTap t = bilinear_tap(p / W, p % W, sy, sx, sh, sw, sw);
+                float a[BC], b[BC], c[BC], d[BC];
+#pragma unroll
+                for (int s = 0; s < BC; ++s) {
+                    a[s] = __ldg(ms[s] + t.o00); b[s] = __ldg(ms[s] + t.o01);
+                    c[s] = __ldg(ms[s] + t.o10); d[s] = __ldg(ms[s] + t.o11);
+                }
+#pragma unroll
+                for (int s = 0; s < BC; ++s) x[s] = bilinear_combine(t, a[s], b[s], c[s], d[s]);
+            } else {
+#pragma unroll
+                for (int s = 0; s < BC; ++s) x[s] = __ldg(ms[s] + p);
+            }
             if (MODE != IVLM_LIFT_OBJECT_MESH) cnt[0] += w;   // the weight sum does not depend on the sample
 #pragma unroll
-            for (int s = 0; s < LIFT_BC; ++s) {
-                if (s < nb) {
-                    const float* m = base + (long long)s * V * plane;
-                    float x = LOWRES ? bilinear_eval(t, m) : __ldg(m + p);
-                    if (MODE == IVLM_LIFT_POINTS) {
-                        votes[s] += x;
+            for (int s = 0; s < BC; ++s) {
+                if (MODE == IVLM_LIFT_POINTS) {
+                    votes[s] += x[s];
+                } else {
+                    const float xc = (MODE == IVLM_LIFT_HUMAN) ? fminf(fmaxf(x[s], -20.f), 20.f) : x[s];
+                    const float pr = 1.f / (1.f + expf(-xc));
+                    if (MODE == IVLM_LIFT_OBJECT_MESH) {
+                        const bool on = pr > thr;
+                        votes[s] += on ? w * pr : 0.f;
+                        cnt[s] += on ? w : 0.f;
                     } else {
-                        if (MODE == IVLM_LIFT_HUMAN) x = fminf(fmaxf(x, -20.f), 20.f);
-                        const float pr = 1.f / (1.f + expf(-x));
-                        if (MODE == IVLM_LIFT_OBJECT_MESH) {
-                            if (pr > thr) { votes[s] += w * pr; cnt[s] += w; }
-                        } else {
-                            votes[s] += w * pr;
-                        }
+                        votes[s] += w * pr;
                     }
                 }
             }
         }
         if (MODE != IVLM_LIFT_OBJECT_MESH) cnt[0] = warp_sum(cnt[0]);
 #pragma unroll
-        for (int s = 0; s < LIFT_BC; ++s) {
-            if (s < nb) {
-                votes[s] = warp_sum(votes[s]);
-                if (MODE == IVLM_LIFT_OBJECT_MESH) cnt[s] = warp_sum(cnt[s]);
-                if (lane == 0) {
-                    s_votes[v][s] = votes[s];
-                    s_cnt[v][s] = (MODE == IVLM_LIFT_OBJECT_MESH) ? cnt[s] : cnt[0];
-                }
+        for (int s = 0; s < BC; ++s) {
+            votes[s] = warp_sum(votes[s]);
+            if (MODE == IVLM_LIFT_OBJECT_MESH) cnt[s] = warp_sum(cnt[s]);
+            if (lane == 0) {
+                s_votes[v][s] = votes[s];
+                s_cnt[v][s] = (MODE == IVLM_LIFT_OBJECT_MESH) ? cnt[s] : cnt[0];
             }
         }
     }
@@ -109,18 +122,28 @@ lift_warp_kernel(const int* __restrict__ row_ptr, const int* __restrict__ pix, c
     }
 }
 
-template <bool LOWRES>
-static cudaError_t launch_lift(const ivlm_lift_map* m, const float* src, float* contact, int B, int mode, float thr, int sh,
-                               int sw, cudaStream_t st) {
-    const dim3 grid((unsigned)m->n, (unsigned)((B + LIFT_BC - 1) / LIFT_BC)), block(LIFT_WARPS * 32);
-#define IVLM_LIFT_LAUNCH(MODE)                                                                                              \
-    lift_warp_kernel<MODE, LOWRES><<<grid, block, 0, st>>>(m->row_ptr, m->pix, m->wgt, src, contact, B, m->V, m->n, m->H, \
-                                                            m->W, sh, sw, thr)
+template <bool LOWRES, int BC>
+static cudaError_t launch_lift_bc(const ivlm_lift_map* m, const float* src, float* contact, int B, int mode, float thr, int sh,
+                                  int sw, cudaStream_t st) {
+    const dim3 grid((unsigned)m->n, (unsigned)((B + BC - 1) / BC)), block(LIFT_WARPS * 32);
+#define IVLM_LIFT_LAUNCH(MODE)                                                                                                  \
+    lift_warp_kernel<MODE, LOWRES, BC><<<grid, block, 0, st>>>(m->row_ptr, m->pix, m->wgt, src, contact, B, m->V, m->n, m->H, \
+                                                                m->W, sh, sw, thr)
     if (mode == IVLM_LIFT_HUMAN) IVLM_LIFT_LAUNCH(IVLM_LIFT_HUMAN);
     else if (mode == IVLM_LIFT_OBJECT_MESH) IVLM_LIFT_LAUNCH(IVLM_LIFT_OBJECT_MESH);
     else IVLM_LIFT_LAUNCH(IVLM_LIFT_POINTS);
 #undef IVLM_LIFT_LAUNCH
     return cudaGetLastError();
+}
+
+// samples per CTA pass: the smallest of 1 / 2 / 4 / 8 that covers the batch (a map entry is loaded once per pass)
+template <bool LOWRES>
+static cudaError_t launch_lift(const ivlm_lift_map* m, const float* src, float* contact, int B, int mode, float thr, int sh,
+                               int sw, cudaStream_t st) {
+    if (B <= 1) return launch_lift_bc<LOWRES, 1>(m, src, contact, B, mode, thr, sh, sw, st);
+    if (B <= 2) return launch_lift_bc<LOWRES, 2>(m, src, contact, B, mode, thr, sh, sw, st);
+    if (B <= 4) return launch_lift_bc<LOWRES, 4>(m, src, contact, B, mode, thr, sh, sw, st);
+    return launch_lift_bc<LOWRES, LIFT_BC>(m, src, contact, B, mode, thr, sh, sw, st);
 }
 
 __global__ void csr_spmv_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col,

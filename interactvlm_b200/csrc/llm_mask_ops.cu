@@ -12,7 +12,7 @@ __global__ void rope_kv_store_kernel(const bf16* __restrict__ qkv, const int* __
                                      const int* __restrict__ slot_map, const bf16* __restrict__ cos_t,
                                      const bf16* __restrict__ sin_t, bf16* __restrict__ q_out, bf16* __restrict__ k_out,
                                      bf16* __restrict__ v_out, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
-                                     int H, int hd, int page) {
+                                     int H, int hd, int page, int paired) {
     pdl_wait_then_launch();
     // grid (tokens, chunks): every thread owns one (head, rotary pair) and one 16-byte piece of the V row, so a
     // decode step (8 tokens) spreads over ~100 CTAs instead of serialising ten dependent loads per thread in 8
@@ -33,13 +33,16 @@ __global__ void rope_kv_store_kernel(const bf16* __restrict__ qkv, const int* __
         const float c = __bfloat162float(cos_t[(long long)pos * hd + j]);
         const float s = __bfloat162float(sin_t[(long long)pos * hd + j]);
         const int i1 = hh * hd + j, i2 = i1 + half;
+        // `paired` input columns (the row order ivlm_decode_linear's ROPE_KV epilogue needs, used for q and k by every path so
+        // that the weights exist once): feature j of a head sits at (j / 8) * 16 + j % 8, its partner j + half 8 columns later
+        const int s1 = paired ? hh * hd + (j >> 3) * 16 + (j & 7) : i1, s2 = paired ? s1 + 8 : i2;
         {
-            const float x1 = __bfloat162float(qr[i1]), x2 = __bfloat162float(qr[i2]);
+            const float x1 = __bfloat162float(qr[s1]), x2 = __bfloat162float(qr[s2]);
             q_out[tkn * D + i1] = __float2bfloat16_rn(bf16_round(x1 * c) + bf16_round(-x2 * s));
             q_out[tkn * D + i2] = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * s));
         }
         {
-            const float x1 = __bfloat162float(kr[i1]), x2 = __bfloat162float(kr[i2]);
+            const float x1 = __bfloat162float(kr[s1]), x2 = __bfloat162float(kr[s2]);
             const bf16 o1 = __float2bfloat16_rn(bf16_round(x1 * c) + bf16_round(-x2 * s));
             const bf16 o2 = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * s));
             if (k_out) { k_out[tkn * D + i1] = o1; k_out[tkn * D + i2] = o2; }
@@ -169,8 +172,9 @@ extern "C" int ivlm_decode_finish(ivlm_handle h, const int32_t* state, int32_t S
 extern "C" int ivlm_rope_kv_store_bf16(ivlm_handle h, const void* qkv, const int32_t* positions, const int32_t* slot_map,
                                        const void* cos_t, const void* sin_t, void* q_out, void* k_out, void* v_out,
                                        void* k_cache, void* v_cache, int32_t T, int32_t H, int32_t hd, int32_t page_size,
-                                       void* stream) {
+                                       int32_t paired, void* stream) {
     IVLM_REQUIRE(h && T > 0 && (H * hd) % 8 == 0 && hd % 8 == 0, "rope: bad shape");
+    IVLM_REQUIRE(!paired || hd % 16 == 0, "rope: the paired column layout needs head_dim %% 16 == 0");
     IVLM_REQUIRE(slot_map == nullptr || page_size > 0, "rope: page_size must be positive when a cache is written");
     IVLM_REQUIRE(slot_map == nullptr || (k_cache && v_cache), "rope: slot_map given without caches");
     const int items = H * (hd / 2);
@@ -180,7 +184,7 @@ extern "C" int ivlm_rope_kv_store_bf16(ivlm_handle h, const void* qkv, const int
     IVLM_CHECK_CUDA(launch_k(h, rope_kv_store_kernel, dim3(T, chunks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
                              (const bf16*)qkv, (const int*)positions, (const int*)slot_map, (const bf16*)cos_t, (const bf16*)sin_t,
                              (bf16*)q_out, (bf16*)k_out, (bf16*)v_out, (bf16*)k_cache, (bf16*)v_cache, (int)H, (int)hd,
-                             (int)(page_size > 0 ? page_size : 1)));
+                             (int)(page_size > 0 ? page_size : 1), (int)(paired ? 1 : 0)));
     h->launches++;
     IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;

@@ -226,7 +226,7 @@ __global__ void add_bcast_kernel(const uint4* __restrict__ a, const uint4* __res
     }
 }
 
-__global__ void silu_mul_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, long long rows, int F) {
+__global__ void silu_mul_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, long long rows, int F, int interleaved) {
     pdl_wait_then_launch();
     const int fvec = F >> 3;
     const long long total = rows * fvec;
@@ -234,8 +234,10 @@ __global__ void silu_mul_kernel(const bf16* __restrict__ gu, bf16* __restrict__ 
          i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / fvec;
         const int c = (int)(i % fvec);
-        uint4 g = reinterpret_cast<const uint4*>(gu + r * 2 * F)[c];
-        uint4 u = reinterpret_cast<const uint4*>(gu + r * 2 * F + F)[c];
+        // interleaved: gate / up columns alternate in blocks of 8 (the row order of ivlm_decode_linear's SWIGLU epilogue)
+        uint4 g = reinterpret_cast<const uint4*>(gu + r * 2 * F)[interleaved ? 2 * c : c];
+        uint4 u = interleaved ? reinterpret_cast<const uint4*>(gu + r * 2 * F)[2 * c + 1]
+                              : reinterpret_cast<const uint4*>(gu + r * 2 * F + F)[c];
         uint32_t gi[4] = {g.x, g.y, g.z, g.w}, ui[4] = {u.x, u.y, u.z, u.w}, o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -581,10 +583,11 @@ extern "C" int ivlm_add_bcast_bf16(ivlm_handle h, const void* a, const void* b, 
                                                                            n / 8, period / 8);
     DONE();
 }
-extern "C" int ivlm_silu_mul_bf16(ivlm_handle h, const void* gate_up, void* out, int64_t rows, int32_t F, void* stream) {
+extern "C" int ivlm_silu_mul_bf16(ivlm_handle h, const void* gate_up, void* out, int64_t rows, int32_t F, int32_t interleaved,
+                                  void* stream) {
     IVLM_REQUIRE(h && F % 8 == 0, "silu_mul: F must be a multiple of 8");
     IVLM_CHECK_CUDA(launch_k(h, silu_mul_kernel, dim3(grid_for(rows * (F / 8), 256, h->num_sms)), dim3(256), 0, STREAM,
-                             (const bf16*)gate_up, (bf16*)out, (long long)rows, F));
+                             (const bf16*)gate_up, (bf16*)out, (long long)rows, F, (int)(interleaved ? 1 : 0)));
     DONE();
 }
 extern "C" int ivlm_finalize_f32_bf16(ivlm_handle h, const float* acc, void* out, const void* bias, const void* residual,

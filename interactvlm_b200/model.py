@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from .config import IVLMConfig
+from .layout import interleave_gate_up, pair_rows
 from .synthetic import CLIP_PREFIX, SAM_PREFIX
 
 IMAGE_TOKEN_INDEX = -200
@@ -47,14 +48,23 @@ class _Weights:
 
         self.g = g
         L = self.llm = []
+        nh, hd_ = cfg.num_attention_heads, cfg.head_dim
+        # q / k rows PAIRED per head and gate / up rows INTERLEAVED (layout.py): the row orders the fused decode kernel's
+        # RoPE and SwiGLU epilogues need; the prefill kernels read the same single copy through their layout flags
+        self.paired_qk = hd_ % 16 == 0 and cfg.intermediate_size % 8 == 0
         for i in range(cfg.num_hidden_layers):
             p = f"model.layers.{i}."
+            q, k, v = (g(p + f"self_attn.{n}_proj.weight") for n in "qkv")
+            gate, up = g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")
+            if self.paired_qk:
+                wqkv = torch.cat([pair_rows(q, nh, hd_), pair_rows(k, nh, hd_), v], 0).contiguous()
+                wgu = interleave_gate_up(gate, up)
+            else:
+                wqkv, wgu = torch.cat([q, k, v], 0).contiguous(), torch.cat([gate, up], 0).contiguous()
+            del q, k, v, gate, up
             L.append(dict(
                 ln1=g(p + "input_layernorm.weight"), ln2=g(p + "post_attention_layernorm.weight"),
-                wqkv=torch.cat([g(p + f"self_attn.{n}_proj.weight") for n in "qkv"], 0).contiguous(),
-                wo=g(p + "self_attn.o_proj.weight"),
-                wgu=torch.cat([g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")], 0).contiguous(),
-                wd=g(p + "mlp.down_proj.weight")))
+                wqkv=wqkv, wo=g(p + "self_attn.o_proj.weight"), wgu=wgu, wd=g(p + "mlp.down_proj.weight")))
         self.embed = g("model.embed_tokens.weight")
         self.norm = g("model.norm.weight")
         self.lm_head = g("lm_head.weight")
@@ -187,6 +197,7 @@ class _Engine:
         self.device = w.device
         self._win_maps = {}
         self.fused_sam_attention = True
+        self.fused_decode = True   # decode steps of <= 8 tokens through ivlm_decode_linear (5 launches per layer instead of 9)
         self.trace = None  # tests: dict of lists receiving the residual stream after every SAM block / LLaMA prefill layer
 
     # ------------------------------------------------------------------ CLIP + projector (a4)
@@ -303,11 +314,11 @@ class _Engine:
             y = ctx.rmsnorm(x, lw["ln1"], cfg.rms_norm_eps)
             qkv = ctx.gemm(y, lw["wqkv"])
             q, k, v = ctx.rope_kv_store(qkv, pos, slot, W.rope_cos, W.rope_sin, nh, hd, st["k"][i], st["v"][i],
-                                        page_size=PAGE)
+                                        page_size=PAGE, paired=W.paired_qk)
             o = ctx.attention(q.view(B, S, nh, hd), k.view(B, S, nh, hd), v.view(B, S, nh, hd), 1.0 / math.sqrt(hd), causal=True)
             x = ctx.gemm(o.view(B * S, D), lw["wo"], residual=x)
             y = ctx.rmsnorm(x, lw["ln2"], cfg.rms_norm_eps)
-            y = ctx.silu_mul(ctx.gemm(y, lw["wgu"]))
+            y = ctx.silu_mul(ctx.gemm(y, lw["wgu"]), interleaved=W.paired_qk)
             x = ctx.gemm(y, lw["wd"], residual=x)
             if self.trace is not None:
                 self.trace.setdefault("llm", []).append(x)
@@ -316,13 +327,18 @@ class _Engine:
         st["len"] = S
         return self._greedy(hn[:, S - 1].contiguous(), out=st.get("next"))
 
-    def _greedy(self, h, out=None):
+    def _greedy(self, h, out=None, stream_kernel=False):
         """lm_head + argmax.  Rows go through the swapped-operand GEMM in chunks of <= 64 (the vocabulary size of the
-        released checkpoints, 32004, is not a multiple of 8, which the row-major epilogue would need)."""
+        released checkpoints, 32004, is not a multiple of 8, which the row-major epilogue would need); decode steps of <= 8
+        tokens stream the matrix through ivlm_decode_linear."""
         ctx, cfg = self.ctx, self.cfg
         B = h.shape[0]
         if out is None:
             out = torch.empty((B,), device=self.device, dtype=torch.int32)
+        if stream_kernel and B <= 8:
+            logits = ctx.decode_linear(h, self.w.lm_head, out_dtype=torch.float32)
+            ctx.argmax(logits, vocab=cfg.vocab_size, out=out)
+            return out
         for b0 in range(0, B, 64):
             logits = ctx.gemm(h[b0:b0 + 64], self.w.lm_head, out_dtype=torch.float32, force_swap=1)
             ctx.argmax(logits, vocab=cfg.vocab_size, out=out[b0:b0 + 64])
@@ -350,19 +366,33 @@ class _Engine:
         nh, hd = cfg.num_attention_heads, cfg.head_dim
         ctx.decode_prepare(st, st["S"], st["G"], cfg.eos_token_id, cfg.pad_token_id)
         x = ctx.embed_gather(W.embed, st["tok"])
-        for i, lw in enumerate(W.llm):
-            y = ctx.rmsnorm(x, lw["ln1"], cfg.rms_norm_eps)
-            qkv = ctx.gemm(y, lw["wqkv"])
-            q, _, _ = ctx.rope_kv_store(qkv, st["pos"], st["slot"], W.rope_cos, W.rope_sin, nh, hd, st["k"][i], st["v"][i],
-                                        want_kv=False, page_size=PAGE)
-            o = ctx.decode_attention(q, st["k"][i], st["v"][i], st["block_table"], st["seq_lens"], nh, hd, PAGE)
-            x = ctx.gemm(o, lw["wo"], residual=x)
-            y = ctx.rmsnorm(x, lw["ln2"], cfg.rms_norm_eps)
-            y = ctx.silu_mul(ctx.gemm(y, lw["wgu"]))
-            x = ctx.gemm(y, lw["wd"], residual=x)
+        fused = self.fused_decode and W.paired_qk and x.shape[0] <= 8 and cfg.hidden_size % 16 == 0
+        if fused:
+            # 5 launches per layer (ivlm_decode_linear): [RMSNorm + qkv + RoPE + KV store] -> attention -> [o_proj + residual]
+            # -> [RMSNorm + gate/up + SwiGLU] -> [down_proj + residual]
+            EPI_SWIGLU, EPI_ROPE_KV = 1, 2
+            for i, lw in enumerate(W.llm):
+                rope = dict(positions=st["pos"], slot_map=st["slot"], cos=W.rope_cos, sin=W.rope_sin, k_cache=st["k"][i],
+                            v_cache=st["v"][i], H=nh, hd=hd, page_size=PAGE)
+                q = ctx.decode_linear(x, lw["wqkv"], gamma=lw["ln1"], eps=cfg.rms_norm_eps, epilogue=EPI_ROPE_KV, rope=rope)
+                o = ctx.decode_attention(q, st["k"][i], st["v"][i], st["block_table"], st["seq_lens"], nh, hd, PAGE)
+                x = ctx.decode_linear(o, lw["wo"], residual=x)
+                y = ctx.decode_linear(x, lw["wgu"], gamma=lw["ln2"], eps=cfg.rms_norm_eps, epilogue=EPI_SWIGLU)
+                x = ctx.decode_linear(y, lw["wd"], residual=x)
+        else:
+            for i, lw in enumerate(W.llm):
+                y = ctx.rmsnorm(x, lw["ln1"], cfg.rms_norm_eps)
+                qkv = ctx.gemm(y, lw["wqkv"])
+                q, _, _ = ctx.rope_kv_store(qkv, st["pos"], st["slot"], W.rope_cos, W.rope_sin, nh, hd, st["k"][i], st["v"][i],
+                                            want_kv=False, page_size=PAGE, paired=W.paired_qk)
+                o = ctx.decode_attention(q, st["k"][i], st["v"][i], st["block_table"], st["seq_lens"], nh, hd, PAGE)
+                x = ctx.gemm(o, lw["wo"], residual=x)
+                y = ctx.rmsnorm(x, lw["ln2"], cfg.rms_norm_eps)
+                y = ctx.silu_mul(ctx.gemm(y, lw["wgu"]), interleaved=W.paired_qk)
+                x = ctx.gemm(y, lw["wd"], residual=x)
         ctx.rmsnorm(x, W.norm, cfg.rms_norm_eps, out=st["hid_step"])
         ctx.decode_finish(st, st["S"])
-        self._greedy(st["hid_step"], out=st["next"])
+        self._greedy(st["hid_step"], out=st["next"], stream_kernel=fused)
 
     # ------------------------------------------------------------------ [SEG] head (a7, a10)
     def seg_prompt(self, hidden_rows, cam_params, tokens=None):

@@ -65,7 +65,7 @@ class Context:
 
     # ------------------------------------------------------------------ per-kernel timing (bench.py roofline pass)
     _PROFILED = ("gemm", "attention", "layernorm", "rmsnorm", "add_bcast", "silu_mul", "im2col_patch", "im2col_3x3",
-                 "sam_relpos", "sam_attention", "attn_small", "embed_splice", "embed_gather", "gather_rows", "rope_kv_store",
+                 "sam_relpos", "sam_attention", "attn_small", "embed_splice", "embed_gather", "gather_rows", "rope_kv_store", "decode_linear",
                  "decode_attention", "decode_prepare", "decode_finish", "argmax", "cam_gate", "upscale_hyper_dot", "bilinear", "finalize")
 
     def enable_profile(self):
@@ -86,6 +86,8 @@ class Context:
                     if a[0].shape[0] <= 64:  # swapped-operand weight streaming (decode, decoder tokens): HBM-bound
                         _name = "gemm_small_m"
                         work = 2.0 * a[1].shape[0] * a[1].shape[1]  # bytes of weights read
+                elif _name == "decode_linear":
+                    work = 2.0 * a[1].shape[0] * a[1].shape[1]  # bytes of weights streamed
                 elif _name == "sam_attention":
                     Bq, nh, S_, hd_ = a[3], a[4], a[5] * a[6], a[7]
                     work = 4.0 * Bq * nh * S_ * S_ * hd_
@@ -183,12 +185,46 @@ class Context:
                 "add_bcast")
         return out
 
-    def silu_mul(self, gate_up, out=None):
+    def silu_mul(self, gate_up, out=None, interleaved=False):
         _bf16(gate_up)
         rows, F2 = gate_up.shape
         if out is None:
             out = torch.empty((rows, F2 // 2), device=gate_up.device, dtype=torch.bfloat16)
-        L.check(self.lib.ivlm_silu_mul_bf16(self.h, P(gate_up), P(out), i64(rows), i32(F2 // 2), self.stream), "silu_mul")
+        L.check(self.lib.ivlm_silu_mul_bf16(self.h, P(gate_up), P(out), i64(rows), i32(F2 // 2), i32(1 if interleaved else 0),
+                                            self.stream), "silu_mul")
+        return out
+
+    def decode_linear(self, a, w, gamma=None, eps=0.0, epilogue=L.EPI_PLAIN, act=ACT_NONE, bias=None, residual=None, out=None,
+                      out_dtype=torch.bfloat16, rope=None):
+        """Weight-streaming linear layer of a decode step, M <= 8 tokens (ivlm_decode_linear): optional fused RMSNorm of `a`,
+        epilogue PLAIN / SWIGLU (w rows interleaved) / ROPE_KV (w q,k rows paired; rope = dict(positions, slot_map, cos, sin,
+        k_cache, v_cache, H, hd, page_size))."""
+        _bf16(a, "a"); _bf16(w, "w")
+        M, K = a.shape
+        N = w.shape[0]
+        assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+        width = N // 2 if epilogue == L.EPI_SWIGLU else (N // 3 if epilogue == L.EPI_ROPE_KV else N)
+        if out is None:
+            out = torch.empty((M, width), device=a.device, dtype=out_dtype)
+        assert out.shape == (M, width) and out.stride(1) == 1
+        g = L.DecodeLinearArgs()
+        g.a, g.lda, g.w, g.ldw = a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0)
+        g.M, g.N, g.K = M, N, K
+        g.norm_gamma, g.norm_eps = (_bf16(gamma, "gamma").data_ptr() if gamma is not None else None), float(eps)
+        g.epilogue, g.act = epilogue, act
+        g.bias = _bf16(bias, "bias").data_ptr() if bias is not None else None
+        if residual is not None:
+            _bf16(residual, "residual")
+            g.residual, g.ldr = residual.data_ptr(), residual.stride(0)
+        g.out, g.ldo = out.data_ptr(), out.stride(0)
+        g.out_dtype = BF16 if out.dtype == torch.bfloat16 else F32
+        if epilogue == L.EPI_ROPE_KV:
+            assert rope["positions"].dtype == torch.int32 and rope["slot_map"].dtype == torch.int32
+            g.positions, g.slot_map = rope["positions"].data_ptr(), rope["slot_map"].data_ptr()
+            g.cos_t, g.sin_t = rope["cos"].data_ptr(), rope["sin"].data_ptr()
+            g.k_cache, g.v_cache = rope["k_cache"].data_ptr(), rope["v_cache"].data_ptr()
+            g.H, g.hd, g.page_size = rope["H"], rope["hd"], rope["page_size"]
+        L.check(self.lib.ivlm_decode_linear(self.h, C.byref(g), self.stream), "decode_linear")
         return out
 
     def finalize(self, acc, bias=None, residual=None, act=ACT_NONE, out=None):
@@ -329,7 +365,7 @@ class Context:
         return out
 
     def rope_kv_store(self, qkv, positions, slot_map, cos_t, sin_t, H, hd, k_cache=None, v_cache=None, want_kv=True,
-                      q_out=None, page_size=16):
+                      q_out=None, page_size=16, paired=False):
         _bf16(qkv)
         T = qkv.shape[0]
         D = H * hd
@@ -339,7 +375,7 @@ class Context:
         v_out = torch.empty((T, D), device=qkv.device, dtype=torch.bfloat16) if want_kv else None
         L.check(self.lib.ivlm_rope_kv_store_bf16(self.h, P(qkv), P(positions), P(slot_map), P(cos_t), P(sin_t), P(q_out),
                                                  P(k_out), P(v_out), P(k_cache), P(v_cache), i32(T), i32(H), i32(hd),
-                                                 i32(page_size), self.stream), "rope_kv_store")
+                                                 i32(page_size), i32(1 if paired else 0), self.stream), "rope_kv_store")
         return q_out, k_out, v_out
 
     def decode_attention(self, q, k_cache, v_cache, block_table, seq_lens, H, hd, page_size, out=None):

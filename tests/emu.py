@@ -136,10 +136,33 @@ class EmuContext:
         assert a.is_contiguous() and b.is_contiguous() and a.numel() % b.numel() == 0
         return (a.float().view(-1, b.numel()) + b.float().view(1, -1)).to(BF).view(a.shape)
 
-    def silu_mul(self, gate_up, out=None):
+    def silu_mul(self, gate_up, out=None, interleaved=False):
         self.launches += 1
         Fh = gate_up.shape[1] // 2
-        return (_r(F.silu(gate_up[:, :Fh].float())) * gate_up[:, Fh:].float()).to(BF)
+        if interleaved:
+            from interactvlm_b200.layout import split_interleaved
+            gate, up = split_interleaved(gate_up)
+        else:
+            gate, up = gate_up[:, :Fh], gate_up[:, Fh:]
+        return (_r(F.silu(gate.float())) * up.float()).to(BF)
+
+    def decode_linear(self, a, w, gamma=None, eps=0.0, epilogue=0, act=ACT_NONE, bias=None, residual=None, out=None, out_dtype=BF,
+                      rope=None):
+        """ivlm_decode_linear: rmsnorm? -> linear -> PLAIN / SWIGLU (interleaved rows) / ROPE_KV (paired q, k rows)."""
+        assert a.shape[0] <= 8 and a.shape[1] % 16 == 0
+        x = self.rmsnorm(a, gamma, eps) if gamma is not None else a
+        if epilogue == 0:
+            y = self.gemm(x, w, bias=bias, act=act, residual=residual, out_dtype=out_dtype, force_swap=1)
+        elif epilogue == 1:
+            y = self.silu_mul(self.gemm(x, w, force_swap=1), interleaved=True)
+        else:
+            qkv = self.gemm(x, w, force_swap=1)
+            y, _, _ = self.rope_kv_store(qkv, rope["positions"], rope["slot_map"], rope["cos"], rope["sin"], rope["H"], rope["hd"],
+                                         rope["k_cache"], rope["v_cache"], want_kv=False, page_size=rope["page_size"], paired=True)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
 
     # ---- lowering
     def im2col_patch(self, img, p, ldk=None):
@@ -225,11 +248,14 @@ class EmuContext:
         return (a.view(torch.int16)[:, None, :] != b.view(torch.int16)[None, :, :]).any(-1).to(torch.int32)
 
     def rope_kv_store(self, qkv, positions, slot_map, cos_t, sin_t, H, hd, k_cache=None, v_cache=None, want_kv=True,
-                      q_out=None, page_size=16):
+                      q_out=None, page_size=16, paired=False):
         self.launches += 1
         T = qkv.shape[0]
         D = H * hd
-        q, k, v = (qkv[:, i * D:(i + 1) * D].view(T, H, hd) for i in range(3))
+        if paired:   # q and k columns arrive in the paired order of layout.py
+            from interactvlm_b200.layout import unpair_cols
+            qkv = torch.cat([unpair_cols(qkv[:, :D], H, hd), unpair_cols(qkv[:, D:2 * D], H, hd), qkv[:, 2 * D:]], 1)
+        q, k, v = (qkv[:, i * D:(i + 1) * D].reshape(T, H, hd) for i in range(3))
         c, s = cos_t[positions.long()][:, None, :], sin_t[positions.long()][:, None, :]
 
         def rope(x):  # bf16 ops like HF apply_rotary_pos_emb

@@ -103,7 +103,9 @@ def test_full_size_properties_and_lift_round_trip(ctx):
     lm = R.lift_map_from_mesh((v, f), VIEWS, (1024, 1024), ctx=ctx)
     got = lm(logits, LIFT_OBJECT_MESH).cpu().numpy()[0]
     want = OL.lift_object_mesh(logits.cpu().numpy(), p2v.cpu().numpy(), bary.cpu().numpy(), len(v))[0]
-    assert np.abs(got - want).max() < 1e-6
+    # vertices of this coarse mesh collect thousands of pixels: the oracle's sequential fp32 sum (the reference's scatter order)
+    # and the kernel's lane-strided + shuffle-tree sum differ by a few 1e-7 per thousand terms
+    assert np.abs(got - want).max() < 5e-6
     visible = np.zeros(len(v), bool)
     visible[np.unique(p2v[fg].cpu().numpy())] = True
     interior = np.zeros(len(v), bool)

@@ -92,6 +92,33 @@ def layer_chain(i):
     return ctx.gemm(y, wd[i % NW], residual=x1)
 
 
+def fused_chain(i):
+    """the 5 launches of one decode layer with ivlm_decode_linear (RMSNorm / RoPE + KV store / SwiGLU fused)"""
+    rope = dict(positions=pos, slot_map=slot, cos=cos_t, sin=sin_t, k_cache=kc[i % NW], v_cache=vc[i % NW], H=H, hd=hd, page_size=page)
+    q_ = ctx.decode_linear(x, wqkv[i % NW], gamma=gam, eps=1e-5, epilogue=2, rope=rope)
+    o_ = ctx.decode_attention(q_, kc[i % NW], vc[i % NW], bt, sl, H, hd, page)
+    x1 = ctx.decode_linear(o_, wo[i % NW], residual=x)
+    y = ctx.decode_linear(x1, wgu[i % NW], gamma=gam, eps=1e-5, epilogue=1)
+    return ctx.decode_linear(y, wd[i % NW], residual=x1)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "fused":
+    fops = {
+        "norm+qkv+rope+kv": (lambda i: ctx.decode_linear(x, wqkv[i % NW], gamma=gam, eps=1e-5, epilogue=2, rope=dict(
+            positions=pos, slot_map=slot, cos=cos_t, sin=sin_t, k_cache=kc[i % NW], v_cache=vc[i % NW], H=H, hd=hd, page_size=page)), 3 * D * D * 2),
+        "o_proj+res": (lambda i: ctx.decode_linear(x, wo[i % NW], residual=x), D * D * 2),
+        "norm+gateup+swiglu": (lambda i: ctx.decode_linear(x, wgu[i % NW], gamma=gam, eps=1e-5, epilogue=1), 2 * F * D * 2),
+        "down+res": (lambda i: ctx.decode_linear(xf, wd[i % NW], residual=x), F * D * 2),
+        "decode_attention": (lambda i: ctx.decode_attention(q, kc[i % NW], vc[i % NW], bt, sl, H, hd, page), 2 * B * L * D * 2),
+    }
+    for name, (fn, nbytes) in fops.items():
+        us = graph_time(fn)
+        print(f"{name:>20}: {us:8.2f} us   {nbytes / us / 1e3:8.1f} GB/s", flush=True)
+    for pdl in (0, 1):
+        ctx.set_option("pdl", pdl)
+        print(f"fused layer chain in a graph, pdl={pdl}: {graph_time(fused_chain):7.2f} us per layer;   9-launch chain: {graph_time(layer_chain):7.2f} us", flush=True)
+    ctx.set_option("pdl", 0)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "splits":
     ctx.set_option("small_m_variant", 1)
     for name, wl, xin in (("qkv", wqkv, x), ("o", wo, x), ("gateup", wgu, x), ("down", wd, xf)):
