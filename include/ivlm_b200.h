@@ -201,7 +201,8 @@ IVLM_API int ivlm_decode_finish(ivlm_handle h, const int32_t* state, int32_t S, 
  *                     (rows h*hd+16b..+7 = features h*hd+8b..+7, rows +8..+15 = the same features + hd/2), v rows natural;
  *                     rotated q -> out [M, H*hd] (natural order), rotated k and v -> paged cache at slot_map[m]
  *                     (layout of ivlm_rope_kv_store_bf16).
- * Replaces, per decoder layer, the separate rmsnorm / rope_kv_store / silu_mul launches of the chain.  Needs a bound workspace. */
+ * Replaces, per decoder layer, the separate rmsnorm / rope_kv_store / silu_mul launches of the chain.  Needs a bound workspace;
+ * K must be a multiple of 64 and all operands 16-byte aligned (the weights arrive through a rank-3 TMA tensor map). */
 enum ivlm_decode_epilogue { IVLM_EPI_PLAIN = 0, IVLM_EPI_SWIGLU = 1, IVLM_EPI_ROPE_KV = 2 };
 typedef struct ivlm_decode_linear_args {
     const void* a;          /* [M,K] bf16 activations (the un-normalised residual stream when norm_gamma != NULL) */

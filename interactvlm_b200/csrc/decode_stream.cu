@@ -16,9 +16,12 @@
 // A decode step reads every weight once for <= 8 tokens: the launch is HBM-bound and built around the byte stream.
 //   * persistent: one CTA per SM; the (16-row tile) x (512-column stage) grid of the weight matrix is cut into equal CONTIGUOUS
 //     stage ranges, one per CTA (no wave quantisation: 320 or 960 tiles never divide by 148 SMs);
-//   * one producer thread per CTA keeps an 8-deep ring of 16 KB stages full with cp.async.bulk (1 KB per weight row, completion
-//     on an mbarrier), >= 128 KB in flight per SM whatever the consumers do; the first ring of weights is requested BEFORE
-//     griddepcontrol.wait (weights are static), so under programmatic dependent launch it streams under the predecessor's tail;
+//   * one producer thread per CTA keeps an 8-deep ring of 16 KB stages full, ONE TMA op per stage: the weight matrix is described
+//     as a 3-D tensor (64-element k-chunk, row, chunk index) and a (64, 16, 8) box lands as eight 128B-swizzled [16 rows x 128 B]
+//     slabs -- the K-major layout ldmatrix reads without bank conflicts; >= 128 KB in flight per SM whatever the consumers do
+//     (row-wise 1 KB cp.async.bulk copies, 16 per stage, measured 2.1 TB/s: the per-op issue cost dominates); the first ring of
+//     weights is requested BEFORE griddepcontrol.wait (weights are static), so under programmatic dependent launch it streams
+//     under the predecessor's tail;
 //   * eight consumer warps split the 32 k16-steps of a stage (ldmatrix + mma.sync m16n8k16: 16 weight rows x 8 tokens), keep
 //     their partial tile in registers across the stages of a tile and fold it through shared memory in warp order;
 //   * a tile cut by a range boundary is finished by the CTA that holds its first stages: the CTA holding the rest computes that
@@ -29,7 +32,8 @@
 
 namespace ivlm {
 
-constexpr int DS_ROWS = 16, DS_KW = 512, DS_PITCH = DS_KW + 8, DS_STAGES = 8, DS_CONSUMERS = 8, DS_MAX_M = 8;
+constexpr int DS_ROWS = 16, DS_KW = 512, DS_STAGES = 8, DS_CONSUMERS = 8, DS_MAX_M = 8;
+constexpr int DS_W_BYTES = DS_ROWS * DS_KW * 2, DS_A_BYTES = DS_MAX_M * DS_KW * 2;  // per stage: weights 16 KB, streamed tokens 8 KB
 constexpr int DS_THREADS = (DS_CONSUMERS + 1) * 32;
 constexpr int DS_FLAG_OFFSET_BYTES = (int)IVLM_WS_COUNTER_BYTES - 4096;  // last 1024 ints of the counter region
 
@@ -52,10 +56,10 @@ struct DecodeStreamParams {
     float* partial; int* flags;
 };
 
-IVLM_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+IVLM_DEVINL void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
         : "memory");
 }
 IVLM_DEVINL void ldmatrix_x2(uint32_t& r0, uint32_t& r1, const void* smem_row) {
@@ -68,18 +72,19 @@ IVLM_DEVINL int ld_acquire(const int* p) {
 }
 IVLM_DEVINL void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-__global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const DecodeStreamParams p) {
+__global__ void __launch_bounds__(DS_THREADS, 1)
+decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const DecodeStreamParams p) {
     extern __shared__ __align__(128) uint8_t ds_smem[];
-    // [full bars | empty bars] [red: 8 warps x 16 x 8 fp32] [fin: 16 x 8 fp32] [resident activation] [ring]
+    // [full bars | empty bars] [red: 8 warps x 16 x 8 fp32] [fin: 16 x 8 fp32] [resident activation] [ring, 1024-byte aligned]
     uint64_t* full = reinterpret_cast<uint64_t*>(ds_smem);
     uint64_t* empty = full + DS_STAGES;
     float* red = reinterpret_cast<float*>(ds_smem + 128);
     float* fin = red + DS_CONSUMERS * 128;
     bf16* act = reinterpret_cast<bf16*>(fin + 128);
     const int act_pitch = p.K + 8;
-    const int stage_rows = DS_ROWS + (p.resident ? 0 : DS_MAX_M);
-    bf16* ring = act + (p.resident ? (size_t)DS_MAX_M * act_pitch : 0);
-    const size_t stage_elems = (size_t)stage_rows * DS_PITCH;
+    const uint32_t stage_bytes = DS_W_BYTES + (p.resident ? 0 : DS_A_BYTES);
+    uint8_t* ring = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(act) + (p.resident ? (size_t)DS_MAX_M * act_pitch * 2 : 0) + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -99,22 +104,17 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const Deco
         // ------------------------------------------------------------------ producer (one thread)
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();   // every weight byte is used once per step
+            const uint64_t keep = l2_policy_evict_last();
             auto issue_weights = [&](int it) {
                 const int s = s_begin + it, slot = it % DS_STAGES;
-                const int tile = s / p.spt, k0 = (s % p.spt) * DS_KW;
-                const int kw = min(DS_KW, p.K - k0), rows = min(DS_ROWS, p.N - tile * DS_ROWS);
-                const uint32_t bytes = (uint32_t)(rows * kw * 2 + (p.resident ? 0 : p.M * kw * 2));
-                mbar_arrive_expect_tx(full + slot, bytes);
-                bf16* dst = ring + slot * stage_elems;
-                const bf16* src = p.w + (long long)tile * DS_ROWS * p.ldw + k0;
-                for (int r = 0; r < rows; ++r) bulk_g2s(dst + r * DS_PITCH, src + (long long)r * p.ldw, (uint32_t)kw * 2, full + slot, pol);
+                const int tile = s / p.spt, ks = s % p.spt;
+                // the full box always counts: rows past N and chunks past K are zero-filled by the TMA unit
+                mbar_arrive_expect_tx(full + slot, stage_bytes);
+                tma_load_3d_hint(ring + (size_t)slot * stage_bytes, &tmW, full + slot, 0, tile * DS_ROWS, ks * (DS_KW / 64), pol);
             };
             auto issue_acts = [&](int it) {
                 const int s = s_begin + it, slot = it % DS_STAGES;
-                const int k0 = (s % p.spt) * DS_KW, kw = min(DS_KW, p.K - k0);
-                bf16* dst = ring + slot * stage_elems + DS_ROWS * DS_PITCH;
-                const uint64_t keep = l2_policy_evict_last();
-                for (int m = 0; m < p.M; ++m) bulk_g2s(dst + m * DS_PITCH, p.a + (long long)m * p.lda + k0, (uint32_t)kw * 2, full + slot, keep);
+                tma_load_3d_hint(ring + (size_t)slot * stage_bytes + DS_W_BYTES, &tmA, full + slot, 0, 0, (s % p.spt) * (DS_KW / 64), keep);
             };
             const int n_pre = min(DS_STAGES, n_my);
             for (int it = 0; it < n_pre; ++it) issue_weights(it);   // static operands: before the dependency wait
@@ -174,25 +174,29 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const Deco
     }
 
     float c[4] = {0.f, 0.f, 0.f, 0.f};
-    // ldmatrix lane addressing. A (weights): matrices (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15)
-    const int a_row = ((lane >> 3) & 1) * 8 + (lane & 7), a_kofs = (lane >> 4) * 8;
-    // B (tokens, stored [token][k]): matrices (tokens 0-7, k 0-7), (tokens 0-7, k 8-15); lanes 16-31 repeat valid addresses
-    const int b_row = lane & 7, b_kofs = ((lane >> 3) & 1) * 8;
+    // ldmatrix lane addressing.  A (weights): matrices (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15).
+    // A stage holds 8 slabs (one per 64-wide k-chunk) of [16 rows x 128 B] with the 128-byte swizzle: 16-byte unit u of row r
+    // sits at r * 128 + ((u ^ (r & 7)) << 4).
+    const int a_row = ((lane >> 3) & 1) * 8 + (lane & 7), a_half = lane >> 4;
+    // B (tokens, [token][k]): matrices (tokens 0-7, k 0-7), (tokens 0-7, k 8-15); lanes 16-31 repeat valid addresses
+    const int b_row = lane & 7, b_half = (lane >> 3) & 1;
 
     for (int it = 0; it < n_my; ++it) {
         const int s = s_begin + it, slot = it % DS_STAGES;
         const int tile = s / p.spt, ks = s % p.spt, k0 = ks * DS_KW;
         const int kw = min(DS_KW, p.K - k0);
         mbar_wait(full + slot, (it / DS_STAGES) & 1);
-        const bf16* st = ring + slot * stage_elems;
-        const bf16* a_base = st + a_row * DS_PITCH + a_kofs;
-        const bf16* b_base = p.resident ? act + (size_t)b_row * act_pitch + k0 + b_kofs
-                                        : st + (DS_ROWS + b_row) * DS_PITCH + b_kofs;
+        const uint8_t* st = ring + (size_t)slot * stage_bytes;
+        const uint8_t* a_base = st + a_row * 128;
+        const uint8_t* b_str = st + DS_W_BYTES + b_row * 128;
+        const bf16* b_res = act + (size_t)b_row * act_pitch + k0 + b_half * 8;
         const int n16 = kw >> 4;
         for (int j = warp; j < n16; j += DS_CONSUMERS) {
             uint32_t af[4], b0, b1;
-            ldmatrix_x4(af[0], af[1], af[2], af[3], a_base + j * 16);
-            ldmatrix_x2(b0, b1, b_base + j * 16);
+            const int chunk = j >> 2, u = (j & 3) * 2;
+            ldmatrix_x4(af[0], af[1], af[2], af[3], a_base + chunk * 2048 + (((u + a_half) ^ (a_row & 7)) << 4));
+            if (p.resident) ldmatrix_x2(b0, b1, b_res + j * 16);
+            else ldmatrix_x2(b0, b1, b_str + chunk * 1024 + (((u + b_half) ^ b_row) << 4));
             mma_bf16_16816(c, af, b0, b1);
         }
         __syncwarp();
@@ -310,7 +314,7 @@ extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* 
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     IVLM_REQUIRE(h && a && a->a && a->w && a->out, "decode_linear: null argument");
     IVLM_REQUIRE(a->M >= 1 && a->M <= DS_MAX_M, "decode_linear: token count %d outside 1..%d", a->M, DS_MAX_M);
-    IVLM_REQUIRE(a->N > 0 && a->K >= 16 && a->K % 16 == 0, "decode_linear: N=%d K=%d (K must be a multiple of 16)", a->N, a->K);
+    IVLM_REQUIRE(a->N > 0 && a->K >= 64 && a->K % 64 == 0, "decode_linear: N=%d K=%d (K must be a multiple of 64)", a->N, a->K);
     IVLM_REQUIRE((a->lda * 2) % 16 == 0 && (a->ldw * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->a) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
                  "decode_linear: operands must be 16-byte aligned with 16-byte row pitches");
@@ -345,15 +349,18 @@ extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* 
     p.tiles = (a->N + DS_ROWS - 1) / DS_ROWS;
     p.spt = (a->K + DS_KW - 1) / DS_KW;
     p.total_stages = p.tiles * p.spt;
-    // shared memory: barriers + fold buffers, the resident activation (when it fits next to a useful ring), the ring
+    // shared memory: barriers + fold buffers, the resident activation (when it fits next to the ring), the 1024-byte aligned ring
     const size_t fixed = 128 + (DS_CONSUMERS + 1) * 128 * sizeof(float);
     const size_t act_bytes = (size_t)DS_MAX_M * (a->K + 8) * 2;
-    const size_t ring_res = (size_t)DS_STAGES * DS_ROWS * DS_PITCH * 2, ring_str = (size_t)DS_STAGES * (DS_ROWS + DS_MAX_M) * DS_PITCH * 2;
+    const size_t ring_res = (size_t)DS_STAGES * DS_W_BYTES, ring_str = (size_t)DS_STAGES * (DS_W_BYTES + DS_A_BYTES);
     const size_t cap = 227 * 1024;
-    p.resident = (fixed + act_bytes + ring_res <= cap) ? 1 : 0;
+    p.resident = (fixed + act_bytes + 1024 + ring_res <= cap) ? 1 : 0;
     IVLM_REQUIRE(p.resident || a->norm_gamma == nullptr, "decode_linear: fused RMSNorm needs K <= %d (activation resident in shared memory)",
-                 (int)((cap - fixed - ring_res) / (2 * DS_MAX_M) - 8));
-    const size_t smem = fixed + (p.resident ? act_bytes + ring_res : ring_str);
+                 (int)((cap - fixed - 1024 - ring_res) / (2 * DS_MAX_M) - 8));
+    const size_t smem = fixed + 1024 + (p.resident ? act_bytes + ring_res : ring_str);
+    const CUtensorMap *tw, *ta;
+    IVLM_TRY(get_tmap_bf16_kchunk3d(h, a->w, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, DS_ROWS, &tw));
+    IVLM_TRY(get_tmap_bf16_kchunk3d(h, a->a, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, DS_MAX_M, &ta));
     // one CTA per SM, but never more CTAs than whole tiles: a range then always reaches the end of the tile it starts in
     int grid = h->num_sms < p.tiles ? h->num_sms : p.tiles;
     p.partial = reinterpret_cast<float*>(h->ws + IVLM_WS_COUNTER_BYTES);
@@ -362,7 +369,7 @@ extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* 
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
         h->attr_done |= 1ull << 20;
     }
-    IVLM_CHECK_CUDA(launch_k(h, decode_stream_kernel, dim3(grid), dim3(DS_THREADS), smem, stream, p));
+    IVLM_CHECK_CUDA(launch_k(h, decode_stream_kernel, dim3(grid), dim3(DS_THREADS), smem, stream, *tw, *ta, p));
     h->launches++;
     return IVLM_OK;
 }

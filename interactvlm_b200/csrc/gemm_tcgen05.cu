@@ -556,6 +556,44 @@ int get_tmap_bf16_ex(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols,
     return IVLM_OK;
 }
 
+// 3-D view of a row-major [rows, K] bf16 matrix for the weight-streaming decode kernel: (64-element k-chunk, row, chunk index),
+// box (64, box_rows, 8), 128-byte swizzle.  One box = 8 K-major slabs of [box_rows x 128 B] (512 columns of box_rows rows).
+int get_tmap_bf16_kchunk3d(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows,
+                           const CUtensorMap** out) {
+    TmapKey key{ptr, rows, K, ld, box_rows, 64, 128 + 3};   // swizzle tag 131: rank-3 k-chunk map
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) { *out = &it->second; return IVLM_OK; }
+    it = h->tmaps_old.find(key);
+    if (it != h->tmaps_old.end()) { *out = &it->second; return IVLM_OK; }
+    auto enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return IVLM_ERR_CUDA;
+    }
+    IVLM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0 && K % 64 == 0 && box_rows <= 256,
+                 "k-chunk tensor map: base/pitch must be 16-byte aligned and K a multiple of 64 (K=%llu)", (unsigned long long)K);
+    CUtensorMap m;
+    cuuint64_t gdim[3] = {64, rows, K / 64};
+    cuuint64_t gstr[2] = {ld * 2, 128};
+    cuuint32_t box[3] = {64, box_rows, 8};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (k-chunk 3-D) failed (%d) rows=%llu K=%llu ld=%llu", (int)r, (unsigned long long)rows,
+                  (unsigned long long)K, (unsigned long long)ld);
+        return IVLM_ERR_CUDA;
+    }
+    if (h->tmaps.size() >= IVLM_TMAP_GEN) {
+        h->tmaps_old.swap(h->tmaps);
+        h->tmaps.clear();
+    }
+    auto ins = h->tmaps.emplace(key, m);
+    *out = &ins.first->second;
+    return IVLM_OK;
+}
+
 int get_tmap_bf16(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                   const CUtensorMap** out) {
     return get_tmap_bf16_ex(h, ptr, rows, cols, ld, box_rows, BK, 128, out);

@@ -138,6 +138,9 @@ inline cudaError_t launch_k(const ivlm_ctx* h, void (*kernel)(KArgs...), dim3 gr
 // box = box_rows x 64 elements, 128B swizzle, zero OOB fill.
 int get_tmap_bf16(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                   const CUtensorMap** out);
+// Rank-3 (k-chunk, row, chunk index) map of a [rows, K] matrix, box (64, box_rows, 8), 128B swizzle (decode_stream.cu).
+int get_tmap_bf16_kchunk3d(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows,
+                           const CUtensorMap** out);
 // Weight-streaming small-token GEMM (gemv_small_m.cu); arguments as ivlm_gemm_bf16.
 int launch_gemv_small_m(ivlm_ctx* h, const ivlm_gemm_args* a, cudaStream_t stream);
 // General form: box = box_rows x box_cols elements, swizzle_bytes in {128, 64, 32} (box_cols * 2 must not exceed it).

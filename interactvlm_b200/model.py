@@ -366,7 +366,7 @@ class _Engine:
         nh, hd = cfg.num_attention_heads, cfg.head_dim
         ctx.decode_prepare(st, st["S"], st["G"], cfg.eos_token_id, cfg.pad_token_id)
         x = ctx.embed_gather(W.embed, st["tok"])
-        fused = self.fused_decode and W.paired_qk and x.shape[0] <= 8 and cfg.hidden_size % 16 == 0
+        fused = self.fused_decode and W.paired_qk and x.shape[0] <= 8 and cfg.hidden_size % 64 == 0 and cfg.intermediate_size % 64 == 0
         if fused:
             # 5 launches per layer (ivlm_decode_linear): [RMSNorm + qkv + RoPE + KV store] -> attention -> [o_proj + residual]
             # -> [RMSNorm + gate/up + SwiGLU] -> [down_proj + residual]
