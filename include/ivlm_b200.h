@@ -99,6 +99,10 @@ IVLM_API int ivlm_add_bcast_bf16(ivlm_handle h, const void* a, const void* b, vo
  * [F,2F); with interleaved != 0 gate/up alternate in blocks of 8 columns (the weight-row order of IVLM_EPI_SWIGLU). */
 IVLM_API int ivlm_silu_mul_bf16(ivlm_handle h, const void* gate_up, void* out, int64_t rows, int32_t F, int32_t interleaved,
                        void* stream);
+/* out[rows[i], 0:N] = vec[0:N] (bf16) for i < n_rows: the q/k/v rows of the SAM window padding are the qkv bias (the padded
+ * tokens are zeros after norm1, image_encoder.py:179-183), so they are written as a broadcast instead of being multiplied. */
+IVLM_API int ivlm_fill_rows_bf16(ivlm_handle h, void* out, int64_t ld, const int32_t* rows, int32_t n_rows, const void* vec, int32_t N,
+                        void* stream);
 /* fp32 split-K accumulator -> bf16 with optional bias / activation / residual. */
 IVLM_API int ivlm_finalize_f32_bf16(ivlm_handle h, const float* acc, void* out, const void* bias, const void* residual,
                            int64_t rows, int32_t N, int32_t act, void* stream);
@@ -155,9 +159,12 @@ IVLM_API int ivlm_sam_relpos(ivlm_handle h, const void* qkv, const void* rel_pos
 /* SAM ViT attention with the decomposed relative-position bias computed in-kernel (image_encoder.py:235-260, :354-392)
  * on the tcgen05 tensor cores: qkv [B*S, 3*heads*80] packed rows (S = Hq*Wq tokens per image or window),
  * rel_pos_h [2*Hq-1, 80], rel_pos_w [2*Wq-1, 80] bf16 -> out rows [B*S] with pitch out_ld, columns head*80 + c.
- * Token grids 64x64 (global blocks) and 14x14 (windows). */
+ * Token grids 64x64 (global blocks) and 14x14 (windows).  out_row_map (optional, 14x14 windows only, [B*S] int32): output row of
+ * input row r, -1 drops it -- window_unpartition (image_encoder.py:291-318) fused into the store, so the rows of the 64 -> 70
+ * zero padding are never written and the proj GEMM that follows runs on the real tokens only. */
 IVLM_API int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out,
-                            int32_t B, int32_t heads, int32_t Hq, int32_t Wq, int32_t hd, int64_t out_ld, void* stream);
+                            int32_t B, int32_t heads, int32_t Hq, int32_t Wq, int32_t hd, int64_t out_ld,
+                            const int32_t* out_row_map, void* stream);
 /* Attention with few queries or few keys and small head_dim (SAM TwoWayTransformer, transformer.py:185-242):
  * q [B,Nq,heads*hd], k/v [B,Nk,heads*hd], out [B,Nq,heads*hd]; hd in {16,32}. q batch may be 1 (broadcast). */
 IVLM_API int ivlm_attn_small_bf16(ivlm_handle h, const void* q, const void* k, const void* v, void* out, int32_t B,

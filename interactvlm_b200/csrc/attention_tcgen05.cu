@@ -37,6 +37,7 @@ struct SamAttnParams {
     int heads;
     int KH;            // key grid height (== query grid height)
     float scale_log2;  // head_dim^-0.5 * log2(e)
+    const int* out_map;  // window kernel only, optional: output row of input row r (window_unpartition fused), -1 drops the row
 };
 
 // K-major 32B-swizzled operand ([rows][16 bf16], rows 32 B apart, 8-row groups 256 B apart).
@@ -861,13 +862,18 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
         mbar_wait(o_full, 0);
         tc_fence_after();
         const float inv = sum > 0.f ? 1.f / sum : 0.f;
-        bf16* orow = p.out + (long long)(row_base + qtok) * p.out_ld + h * AT_HD;
+        // window_unpartition (image_encoder.py:291-318) folded into the store: with out_map the row goes straight to its token
+        // position and the rows of the zero padding are never written
+        long long orow_i = q_ok ? (long long)(row_base + qtok) : -1;
+        if (q_ok && p.out_map != nullptr) orow_i = p.out_map[row_base + qtok];
+        const bool st_ok = orow_i >= 0;
+        bf16* orow = p.out + (st_ok ? orow_i : 0) * p.out_ld + h * AT_HD;
 #pragma unroll
         for (int c0 = 0; c0 < AT_HD; c0 += 16) {
             uint32_t o[16];
             tmem_ld_32x16(lane_addr + c0, o);
             tmem_ld_wait();
-            if (q_ok) {
+            if (st_ok) {
                 uint4 u0, u1;
                 u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
                 u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
@@ -896,7 +902,7 @@ using namespace ivlm;
 
 extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const void* rel_pos_h, const void* rel_pos_w,
                                        void* out, int32_t B, int32_t heads, int32_t Hq, int32_t Wq, int32_t hd,
-                                       int64_t out_ld, void* stream_) {
+                                       int64_t out_ld, const int32_t* out_row_map, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     IVLM_REQUIRE(h && qkv && rel_pos_h && rel_pos_w && out && B > 0 && heads > 0, "sam_attention: bad arguments");
     IVLM_REQUIRE(hd == AT_HD, "sam_attention: head_dim %d not instantiated (80)", hd);
@@ -919,6 +925,9 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
     p.heads = heads;
     p.KH = Hq;
     p.scale_log2 = (1.0f / sqrtf((float)hd)) * AT_LOG2E;
+    p.out_map = out_row_map;
+    IVLM_REQUIRE(out_row_map == nullptr || (Wq == 14 && h->window_attn_variant == 0),
+                 "sam_attention: out_row_map is implemented by the 14x14 window kernel only");
     dim3 grid((S + AT_BQ - 1) / AT_BQ, heads, B);
     if (!(h->attr_done & (1ull << 16))) {   // per handle = per device
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));

@@ -72,6 +72,7 @@ IVLM_DEVINL int ld_acquire(const int* p) {
 }
 IVLM_DEVINL void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
+template <bool RESIDENT>
 __global__ void __launch_bounds__(DS_THREADS, 1)
 decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const DecodeStreamParams p) {
     extern __shared__ __align__(128) uint8_t ds_smem[];
@@ -82,9 +83,9 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     float* fin = red + DS_CONSUMERS * 128;
     bf16* act = reinterpret_cast<bf16*>(fin + 128);
     const int act_pitch = p.K + 8;
-    const uint32_t stage_bytes = DS_W_BYTES + (p.resident ? 0 : DS_A_BYTES);
+    constexpr uint32_t stage_bytes = DS_W_BYTES + (RESIDENT ? 0 : DS_A_BYTES);
     uint8_t* ring = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(act) + (p.resident ? (size_t)DS_MAX_M * act_pitch * 2 : 0) + 1023) & ~uintptr_t(1023));
+        (reinterpret_cast<uintptr_t>(act) + (RESIDENT ? (size_t)DS_MAX_M * act_pitch * 2 : 0) + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -120,12 +121,12 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             for (int it = 0; it < n_pre; ++it) issue_weights(it);   // static operands: before the dependency wait
             pdl_launch();
             pdl_wait();
-            if (!p.resident)
+            if (!RESIDENT)
                 for (int it = 0; it < n_pre; ++it) issue_acts(it);
             for (int it = n_pre; it < n_my; ++it) {
                 mbar_wait(empty + it % DS_STAGES, ((it / DS_STAGES) - 1) & 1);
                 issue_weights(it);
-                if (!p.resident) issue_acts(it);
+                if (!RESIDENT) issue_acts(it);
             }
         } else {
             pdl_launch();
@@ -137,8 +138,9 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     pdl_launch();
     pdl_wait();
     const int g = lane >> 2, t = lane & 3;
-    if (p.resident) {
-        // warp m stages token m: raw copy + sum of squares (the association of rmsnorm_kernel), then normalise in place
+    if (RESIDENT) {
+        // warp m stages token m: raw copy + sum of squares (the association of rmsnorm_kernel: lane-strided, in order), then
+        // normalise in place.  Loads go out in batches of 10 per lane so that a 5120-wide row costs two L2 round trips.
         const int nvec = p.K >> 3;
         for (int m = warp; m < DS_MAX_M; m += DS_CONSUMERS) {
             uint4* dst = reinterpret_cast<uint4*>(act + (size_t)m * act_pitch);
@@ -148,17 +150,22 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             }
             const uint4* xr = reinterpret_cast<const uint4*>(p.a + (long long)m * p.lda);
             float ss = 0.f;
-            for (int i = lane; i < nvec; i += 32) {
-                const uint4 q = xr[i];
-                dst[i] = q;
-                const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
-                ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+            for (int i0 = lane; i0 < nvec; i0 += 320) {
+                uint4 q[10];
+#pragma unroll
+                for (int u = 0; u < 10; ++u) q[u] = (i0 + 32 * u < nvec) ? __ldcg(xr + i0 + 32 * u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < 10; ++u) {
+                    if (i0 + 32 * u < nvec) dst[i0 + 32 * u] = q[u];
+                    const float2 a = unpack_bf16x2(q[u].x), b = unpack_bf16x2(q[u].y), c = unpack_bf16x2(q[u].z), d = unpack_bf16x2(q[u].w);
+                    ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+                }
             }
             if (p.gamma != nullptr) {
                 const float rstd = rsqrtf(warp_sum(ss) / (float)p.K + p.eps);
                 const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma);
                 for (int i = lane; i < nvec; i += 32) {
-                    const uint4 q = dst[i], gm = g4[i];
+                    const uint4 q = dst[i], gm = __ldg(g4 + i);
                     const uint32_t xi[4] = {q.x, q.y, q.z, q.w}, gi[4] = {gm.x, gm.y, gm.z, gm.w};
                     uint32_t o[4];
 #pragma unroll
@@ -173,37 +180,58 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         named_bar_sync(1, DS_CONSUMERS * 32);
     }
 
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulators: independent HMMA chains
     // ldmatrix lane addressing.  A (weights): matrices (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15).
     // A stage holds 8 slabs (one per 64-wide k-chunk) of [16 rows x 128 B] with the 128-byte swizzle: 16-byte unit u of row r
-    // sits at r * 128 + ((u ^ (r & 7)) << 4).
+    // sits at r * 128 + ((u ^ (r & 7)) << 4).  Warp w takes the k16-steps w, w + 8, w + 16, w + 24 of a stage: slab
+    // (w >> 2) + 2 i, units 2 (w & 3) and 2 (w & 3) + 1 -- the in-slab offsets are per-lane constants.
     const int a_row = ((lane >> 3) & 1) * 8 + (lane & 7), a_half = lane >> 4;
     // B (tokens, [token][k]): matrices (tokens 0-7, k 0-7), (tokens 0-7, k 8-15); lanes 16-31 repeat valid addresses
     const int b_row = lane & 7, b_half = (lane >> 3) & 1;
+    const int u_w = (warp & 3) * 2;
+    const uint32_t a_off = a_row * 128 + (((u_w + a_half) ^ (a_row & 7)) << 4) + (warp >> 2) * 2048;
+    const uint32_t b_off_str = DS_W_BYTES + b_row * 128 + (((u_w + b_half) ^ b_row) << 4) + (warp >> 2) * 1024;
+    const bf16* b_res0 = act + (size_t)b_row * act_pitch + b_half * 8 + warp * 16;
 
+    int tile = s_begin / p.spt, ks = s_begin - tile * p.spt;
     for (int it = 0; it < n_my; ++it) {
-        const int s = s_begin + it, slot = it % DS_STAGES;
-        const int tile = s / p.spt, ks = s % p.spt, k0 = ks * DS_KW;
+        const int slot = it % DS_STAGES;
+        const int k0 = ks * DS_KW;
         const int kw = min(DS_KW, p.K - k0);
         mbar_wait(full + slot, (it / DS_STAGES) & 1);
         const uint8_t* st = ring + (size_t)slot * stage_bytes;
-        const uint8_t* a_base = st + a_row * 128;
-        const uint8_t* b_str = st + DS_W_BYTES + b_row * 128;
-        const bf16* b_res = act + (size_t)b_row * act_pitch + k0 + b_half * 8;
-        const int n16 = kw >> 4;
-        for (int j = warp; j < n16; j += DS_CONSUMERS) {
-            uint32_t af[4], b0, b1;
-            const int chunk = j >> 2, u = (j & 3) * 2;
-            ldmatrix_x4(af[0], af[1], af[2], af[3], a_base + chunk * 2048 + (((u + a_half) ^ (a_row & 7)) << 4));
-            if (p.resident) ldmatrix_x2(b0, b1, b_res + j * 16);
-            else ldmatrix_x2(b0, b1, b_str + chunk * 1024 + (((u + b_half) ^ b_row) << 4));
-            mma_bf16_16816(c, af, b0, b1);
+        if (kw == DS_KW) {
+            uint32_t af[4][4], bq[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ldmatrix_x4(af[i][0], af[i][1], af[i][2], af[i][3], st + a_off + i * 4096);
+                if (RESIDENT) ldmatrix_x2(bq[i][0], bq[i][1], b_res0 + k0 + i * 128);
+                else ldmatrix_x2(bq[i][0], bq[i][1], st + b_off_str + i * 2048);
+            }
+            mma_bf16_16816(c, af[0], bq[0][0], bq[0][1]);
+            mma_bf16_16816(c2, af[1], bq[1][0], bq[1][1]);
+            mma_bf16_16816(c, af[2], bq[2][0], bq[2][1]);
+            mma_bf16_16816(c2, af[3], bq[3][0], bq[3][1]);
+        } else {
+            const int n16 = kw >> 4;
+            for (int j = warp; j < n16; j += DS_CONSUMERS) {
+                uint32_t af[4], b0, b1;
+                const int i = j >> 3;
+                ldmatrix_x4(af[0], af[1], af[2], af[3], st + a_off + i * 4096);
+                if (RESIDENT) ldmatrix_x2(b0, b1, b_res0 + k0 + i * 128);
+                else ldmatrix_x2(b0, b1, st + b_off_str + i * 2048);
+                mma_bf16_16816(c, af, b0, b1);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);
 
         const bool tile_end = (ks == p.spt - 1), range_end = (it == n_my - 1);
+        const int tile_now = tile;
+        if (++ks == p.spt) { ks = 0; ++tile; }
         if (!tile_end && !range_end) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { c[i] += c2[i]; c2[i] = 0.f; }
         // ---- fold the eight partial tiles (warp order), then finish or hand over the tile
         float* pw = red + warp * 128;
         pw[g * 8 + 2 * t] = c[0];
@@ -214,7 +242,7 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         named_bar_sync(1, DS_CONSUMERS * 32);
         const int e = threadIdx.x;                       // 0..255; the first 128 threads own one (row, token) each
         const int rl = e & 15, tok = (e >> 4) & 7;
-        const bool head_part = (tile * p.spt < s_begin);          // this CTA does not hold the tile's first stage: contributor
+        const bool head_part = (tile_now * p.spt < s_begin);          // this CTA does not hold the tile's first stage: contributor
         const bool cut_tail = (!tile_end);                        // the tile continues in the next CTA: this CTA finishes it
         float x = 0.f;
         if (e < 128) {
@@ -223,9 +251,11 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         }
         if (head_part) {
             if (e < 128) p.partial[(size_t)cta * 128 + e] = x;
-            __threadfence();
             named_bar_sync(1, DS_CONSUMERS * 32);
-            if (e == 0) st_release(p.flags + cta, 1);
+            if (e == 0) {   // the barrier made the 128 stores visible to this thread; its fence + release publishes them
+                __threadfence();
+                st_release(p.flags + cta, 1);
+            }
             continue;
         }
         if (cut_tail) {
@@ -244,7 +274,7 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             if (e == 0) p.flags[cta + 1] = 0;   // self-resetting: the next launch finds it clear (stream order)
         }
         // ---- epilogue
-        const int row0 = tile * DS_ROWS;
+        const int row0 = tile_now * DS_ROWS;
         if (p.epi == DS_EPI_PLAIN) {
             const int row = row0 + rl;
             if (e < 128 && row < p.N && tok < p.M) {
@@ -268,7 +298,7 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 if (p.epi == DS_EPI_SWIGLU) {
                     // rows 0-7: gate of features 8*tile + j8, rows 8-15: up of the same features
                     const float v = bf16_round(apply_act(lo, ACT_SILU)) * hi;
-                    reinterpret_cast<bf16*>(p.out)[(long long)tk * p.ldo + tile * 8 + j8] = __float2bfloat16_rn(v);
+                    reinterpret_cast<bf16*>(p.out)[(long long)tk * p.ldo + tile_now * 8 + j8] = __float2bfloat16_rn(v);
                 } else {
                     const int D = p.H * p.hd, half = p.hd >> 1;
                     const int sec = row0 / D, r = row0 - sec * D;
@@ -366,10 +396,12 @@ extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* 
     p.partial = reinterpret_cast<float*>(h->ws + IVLM_WS_COUNTER_BYTES);
     p.flags = reinterpret_cast<int*>(h->ws + DS_FLAG_OFFSET_BYTES);
     if (!(h->attr_done & (1ull << 20))) {
-        IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
         h->attr_done |= 1ull << 20;
     }
-    IVLM_CHECK_CUDA(launch_k(h, decode_stream_kernel, dim3(grid), dim3(DS_THREADS), smem, stream, *tw, *ta, p));
+    if (p.resident) IVLM_CHECK_CUDA(launch_k(h, decode_stream_kernel<true>, dim3(grid), dim3(DS_THREADS), smem, stream, *tw, *ta, p));
+    else IVLM_CHECK_CUDA(launch_k(h, decode_stream_kernel<false>, dim3(grid), dim3(DS_THREADS), smem, stream, *tw, *ta, p));
     h->launches++;
     return IVLM_OK;
 }

@@ -248,6 +248,15 @@ __global__ void silu_mul_kernel(const bf16* __restrict__ gu, bf16* __restrict__ 
     }
 }
 
+__global__ void fill_rows_kernel(bf16* __restrict__ out, long long ld, const int* __restrict__ rows, int n_rows,
+                                 const bf16* __restrict__ vec, int nvec) {
+    const long long total = (long long)n_rows * nvec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / nvec), c = (int)(i % nvec);
+        reinterpret_cast<uint4*>(out + (long long)rows[r] * ld)[c] = __ldg(reinterpret_cast<const uint4*>(vec) + c);
+    }
+}
+
 __global__ void finalize_kernel(const float* __restrict__ acc, bf16* __restrict__ out, const bf16* __restrict__ bias,
                                 const bf16* __restrict__ res, long long rows, int N, int act) {
     const long long total = rows * N;
@@ -588,6 +597,13 @@ extern "C" int ivlm_silu_mul_bf16(ivlm_handle h, const void* gate_up, void* out,
     IVLM_REQUIRE(h && F % 8 == 0, "silu_mul: F must be a multiple of 8");
     IVLM_CHECK_CUDA(launch_k(h, silu_mul_kernel, dim3(grid_for(rows * (F / 8), 256, h->num_sms)), dim3(256), 0, STREAM,
                              (const bf16*)gate_up, (bf16*)out, (long long)rows, F, (int)(interleaved ? 1 : 0)));
+    DONE();
+}
+extern "C" int ivlm_fill_rows_bf16(ivlm_handle h, void* out, int64_t ld, const int32_t* rows, int32_t n_rows, const void* vec,
+                                   int32_t N, void* stream) {
+    IVLM_REQUIRE(h && out && rows && vec && n_rows > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "fill_rows: bad arguments");
+    fill_rows_kernel<<<grid_for((long long)n_rows * (N / 8), 256, h->num_sms), 256, 0, STREAM>>>((bf16*)out, ld, rows, n_rows,
+                                                                                               (const bf16*)vec, N / 8);
     DONE();
 }
 extern "C" int ivlm_finalize_f32_bf16(ivlm_handle h, const float* acc, void* out, const void* bias, const void* residual,

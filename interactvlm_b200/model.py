@@ -197,6 +197,7 @@ class _Engine:
         self.device = w.device
         self._win_maps = {}
         self.fused_sam_attention = True
+        self.skip_pad_rows = True  # SAM window blocks: GEMMs on the real tokens only (the padded rows' q/k/v are the bias)
         self.fused_decode = True   # decode steps of <= 8 tokens through ivlm_decode_linear (5 launches per layer instead of 9)
         self.trace = None  # tests: dict of lists receiving the residual stream after every SAM block / LLaMA prefill layer
 
@@ -237,6 +238,18 @@ class _Engine:
             self._win_maps[N] = (_i32(src.reshape(-1), self.device), nw)
         return self._win_maps[N]
 
+    def _window_inverse(self, N):
+        """Inverse of _window_map: token -> its row in window-major order [N*g*g], and the window-major rows that are padding."""
+        key = ("inv", N)
+        if key not in self._win_maps:
+            wmap, _ = self._window_map(N)
+            w = wmap.cpu().numpy()
+            inv = np.empty(N * self.cfg.sam_grid ** 2, np.int32)
+            live = w >= 0
+            inv[w[live]] = np.nonzero(live)[0].astype(np.int32)
+            self._win_maps[key] = (_i32(inv, self.device), _i32(np.nonzero(~live)[0], self.device))
+        return self._win_maps[key]
+
     def _sam_attention(self, qkv, bw, B, nh, side, hd):
         """softmax(q k^T / sqrt(hd) + decomposed rel-pos) v for B images/windows of side x side tokens -> [B*S, nh*hd]."""
         ctx = self.ctx
@@ -265,6 +278,20 @@ class _Engine:
                 y = ctx.layernorm(x, bw["n1g"], bw["n1b"], 1e-6)
                 qkv = ctx.gemm(y, bw["wqkv"], bias=bw["bqkv"], force_swap=-1)
                 o = self._sam_attention(qkv, bw, N, nh, g, hd)
+                x = ctx.gemm(o, bw["wo"], bias=bw["bo"], residual=x, force_swap=-1)
+            elif self.fused_sam_attention and hd == 80 and ws == 14 and self.skip_pad_rows:
+                # window_partition / unpartition without multiplying the 64 -> 70 padding (804 of 4900 rows per view): norm1
+                # and both GEMMs run on the real tokens; the qkv rows scatter into window order (row map of the GEMM store),
+                # the padded tokens' q/k/v -- zeros after norm1, hence exactly the qkv bias (image_encoder.py:179-183) -- are a
+                # broadcast, and the attention kernel stores its rows straight back at their token positions
+                Bw = N * nw * nw
+                inv, pads = self._window_inverse(N)
+                y = ctx.layernorm(x, bw["n1g"], bw["n1b"], 1e-6)
+                qkv = torch.empty((Bw * ws * ws, 3 * E), device=self.device, dtype=torch.bfloat16)
+                if pads.numel():
+                    ctx.fill_rows(qkv, pads, bw["bqkv"])
+                ctx.gemm(y, bw["wqkv"], bias=bw["bqkv"], row_map=inv, out=qkv, force_swap=-1)
+                o = ctx.sam_attention(qkv, bw["rph"], bw["rpw"], Bw, nh, ws, ws, hd, out_map=wmap, out_rows=N * S)
                 x = ctx.gemm(o, bw["wo"], bias=bw["bo"], residual=x, force_swap=-1)
             else:
                 Bw, Sw = N * nw * nw, ws * ws

@@ -66,7 +66,7 @@ class Context:
     # ------------------------------------------------------------------ per-kernel timing (bench.py roofline pass)
     _PROFILED = ("gemm", "attention", "layernorm", "rmsnorm", "add_bcast", "silu_mul", "im2col_patch", "im2col_3x3",
                  "sam_relpos", "sam_attention", "attn_small", "embed_splice", "embed_gather", "gather_rows", "rope_kv_store", "decode_linear",
-                 "decode_attention", "decode_prepare", "decode_finish", "argmax", "cam_gate", "upscale_hyper_dot", "bilinear", "finalize")
+                 "decode_attention", "fill_rows", "decode_prepare", "decode_finish", "argmax", "cam_gate", "upscale_hyper_dot", "bilinear", "finalize")
 
     def enable_profile(self):
         """Bracket every launch with CUDA events on the launching stream (no synchronisation until profile_report()).
@@ -303,15 +303,28 @@ class Context:
                                          i32(heads), i32(Hq), i32(Wq), i32(hd), self.stream), "sam_relpos")
         return rel_h, rel_w
 
-    def sam_attention(self, qkv, rel_pos_h, rel_pos_w, B, heads, Hq, Wq, hd, out=None):
-        """Fused SAM attention (tcgen05): qkv [B*Hq*Wq, 3*heads*hd] -> [B*Hq*Wq, heads*hd]."""
+    def sam_attention(self, qkv, rel_pos_h, rel_pos_w, B, heads, Hq, Wq, hd, out=None, out_map=None, out_rows=None):
+        """Fused SAM attention (tcgen05): qkv [B*Hq*Wq, 3*heads*hd] -> [B*Hq*Wq, heads*hd]; with out_map ([B*Hq*Wq] int32,
+        windows only) row r is stored at out_map[r] of an [out_rows, heads*hd] output (-1: dropped)."""
         _bf16(qkv); _bf16(rel_pos_h); _bf16(rel_pos_w)
         assert qkv.is_contiguous() and rel_pos_h.is_contiguous() and rel_pos_w.is_contiguous()
         assert qkv.shape == (B * Hq * Wq, 3 * heads * hd), (qkv.shape, B, Hq, Wq, heads, hd)
         if out is None:
-            out = torch.empty((B * Hq * Wq, heads * hd), device=qkv.device, dtype=torch.bfloat16)
+            rows = B * Hq * Wq if out_map is None else out_rows
+            out = torch.empty((rows, heads * hd), device=qkv.device, dtype=torch.bfloat16)
+        if out_map is not None:
+            assert out_map.dtype == torch.int32 and out_map.numel() == B * Hq * Wq
         L.check(self.lib.ivlm_sam_attention_bf16(self.h, P(qkv), P(rel_pos_h), P(rel_pos_w), P(out), i32(B), i32(heads),
-                                                 i32(Hq), i32(Wq), i32(hd), i64(out.stride(0)), self.stream), "sam_attention")
+                                                 i32(Hq), i32(Wq), i32(hd), i64(out.stride(0)), P(out_map), self.stream),
+                "sam_attention")
+        return out
+
+    def fill_rows(self, out, rows, vec):
+        """out[rows[i], :] = vec (bf16) -- bias broadcast into the rows of the SAM window padding."""
+        _bf16(out); _bf16(vec)
+        assert rows.dtype == torch.int32 and out.stride(1) == 1 and vec.numel() == out.shape[1]
+        L.check(self.lib.ivlm_fill_rows_bf16(self.h, P(out), i64(out.stride(0)), P(rows), i32(rows.numel()), P(vec),
+                                             i32(out.shape[1]), self.stream), "fill_rows")
         return out
 
     def attn_small(self, q, k, v, heads):

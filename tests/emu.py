@@ -206,11 +206,22 @@ class EmuContext:
         rel_w = _r(torch.einsum("bnhwc,wkc->bnhwk", q, Rw)).reshape(B, heads, S, Wq)
         return rel_h.contiguous(), rel_w.contiguous()
 
-    def sam_attention(self, qkv, rel_pos_h, rel_pos_w, B, heads, Hq, Wq, hd, out=None):
+    def sam_attention(self, qkv, rel_pos_h, rel_pos_w, B, heads, Hq, Wq, hd, out=None, out_map=None, out_rows=None):
         rel_h, rel_w = self.sam_relpos(qkv, rel_pos_h, rel_pos_w, B, heads, Hq, Wq, hd)
         t = qkv.view(B, Hq * Wq, 3, heads, hd)
         o = self.attention(t[:, :, 0], t[:, :, 1], t[:, :, 2], hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=Hq, kw=Wq)
-        return o.reshape(B * Hq * Wq, heads * hd)
+        o = o.reshape(B * Hq * Wq, heads * hd)
+        if out_map is None:
+            return o
+        res = torch.zeros((out_rows, heads * hd), dtype=BF)
+        live = out_map.long() >= 0
+        res[out_map.long()[live]] = o[live]
+        return res
+
+    def fill_rows(self, out, rows, vec):
+        self.launches += 1
+        out[rows.long()] = vec
+        return out
 
     def attn_small(self, q, k, v, heads):
         self.launches += 1
