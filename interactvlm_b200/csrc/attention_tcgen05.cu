@@ -628,6 +628,273 @@ sam_attn_global64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ 64x64 global, 2 threads / row
+// sam_attn_global64_kernel with EIGHT softmax warps per CTA: every query row is shared by two threads (key columns [0,32) and
+// [32,64) of each 64-key tile; the row maximum and the final row sum are exchanged through shared memory, the rel_w values of a
+// thread's 32 columns live in 16 registers).  Still two CTAs per SM (setmaxnreg moves registers from the TMA / MMA warps to the
+// softmax warps), i.e. four softmax warps per scheduler instead of two.
+constexpr int G2H_THREADS = 384;
+constexpr int G2H_SMEM = G2_SMEM + 3 * 1024;
+
+__global__ void __launch_bounds__(G2H_THREADS, 2)
+sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+                         const __grid_constant__ CUtensorMap tmKVa, const __grid_constant__ CUtensorMap tmKVb,
+                         const __grid_constant__ CUtensorMap tmRHa, const __grid_constant__ CUtensorMap tmRHb,
+                         const __grid_constant__ CUtensorMap tmRWa, const __grid_constant__ CUtensorMap tmRWb,
+                         const SamAttnParams p) {
+    constexpr int KW = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_a = smem;
+    uint8_t* q_b = q_a + AT_QA;
+    uint8_t* stage0 = q_b + AT_QB;
+    auto k_a = [&](int s) { return stage0 + s * G2_STAGE; };
+    auto k_b = [&](int s) { return stage0 + s * G2_STAGE + G2_BK * 128; };
+    auto v_a = [&](int s) { return stage0 + s * G2_STAGE + G2_BK * 160; };
+    auto v_b = [&](int s) { return stage0 + s * G2_STAGE + G2_BK * 288; };
+    uint8_t* p_s = stage0 + G2_NS * G2_STAGE;
+    bf16* th_s = reinterpret_cast<bf16*>(p_s + G2_P);  // rel_h[ky][row]
+    bf16* tw_s = th_s + 64 * AT_BQ;                    // rel_w[kx][row]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tw_s) + G2_TAB);
+    uint64_t *q_full = bars, *tab_full = bars + 1, *t_full = bars + 2, *kv_full = bars + 3, *kv_empty = bars + 5,
+             *s_full = bars + 7, *s_empty = bars + 9, *p_full = bars + 11, *pv_done = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    float* mxbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [tile parity][half][row]
+    float* lbuf = mxbuf + 4 * AT_BQ;                                                   // [half][row]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+    const int E = p.heads * AT_HD;
+    const int n_tiles = p.S / G2_BK;
+    const int row_base = b * p.S;
+
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1); mbar_init(tab_full, 1); mbar_init(t_full, 1);
+        for (int s = 0; s < G2_NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8); }
+        mbar_init(p_full, 8);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // warps 0-3 (TMA, MMA issue, TMEM allocation) hand registers to the eight softmax warps
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, AT_QA + AT_QB);
+            tma_load_2d(q_a, &tmQa, q_full, h * AT_HD, row_base + q0);
+            tma_load_2d(q_b, &tmQb, q_full, h * AT_HD + 64, row_base + q0);
+            // the two 128-row rel-pos tables (16 KB + 4 KB each) fill the two K/V stages until the prologue MMAs are done
+            mbar_arrive_expect_tx(tab_full, 2 * (128 * 128 + 128 * 32));
+            tma_load_2d(stage0, &tmRHa, tab_full, 0, 0);
+            tma_load_2d(stage0 + 128 * 128, &tmRHb, tab_full, 64, 0);
+            tma_load_2d(stage0 + G2_STAGE, &tmRWa, tab_full, 0, 0);
+            tma_load_2d(stage0 + G2_STAGE + 128 * 128, &tmRWb, tab_full, 64, 0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % G2_NS;
+                mbar_wait(&kv_empty[s], (j / G2_NS) & 1);
+                mbar_arrive_expect_tx(&kv_full[s], G2_STAGE);
+                const int r = row_base + j * G2_BK;
+                tma_load_2d(k_a(s), &tmKVa, &kv_full[s], E + h * AT_HD, r);
+                tma_load_2d(k_b(s), &tmKVb, &kv_full[s], E + h * AT_HD + 64, r);
+                tma_load_2d(v_a(s), &tmKVa, &kv_full[s], 2 * E + h * AT_HD, r);
+                tma_load_2d(v_b(s), &tmKVb, &kv_full[s], 2 * E + h * AT_HD + 64, r);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint64_t dqa = umma_desc_sw128_kmajor(smem_u32(q_a)), dqb = umma_desc_sw32_kmajor(smem_u32(q_b));
+            mbar_wait(q_full, 0);
+            mbar_wait(tab_full, 0);
+            tc_fence_after();
+            issue_qk(tmem_base + 0, q_a, q_b, stage0, stage0 + 128 * 128);                            // T_h
+            issue_qk(tmem_base + 128, q_a, q_b, stage0 + G2_STAGE, stage0 + G2_STAGE + 128 * 128);    // T_w
+            umma_commit(t_full);
+            for (int s = 0; s < G2_NS; ++s) umma_commit(&kv_empty[s]);
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, G2_BK);
+            auto issue_s = [&](int j) {
+                const int s = j % G2_NS, sb = j & 1;
+                mbar_wait(&kv_full[s], (j / G2_NS) & 1);
+                mbar_wait(&s_empty[sb], (j >> 1) & 1);
+                tc_fence_after();
+                const uint64_t dk = umma_desc_sw128_kmajor(smem_u32(k_a(s)));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + sb * G2_BK, dqa + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                umma_bf16(tmem_base + sb * G2_BK, dqb, umma_desc_sw32_kmajor(smem_u32(k_b(s))), idesc_s, 1u);
+                umma_commit(&s_full[sb]);
+            };
+            issue_s(0);
+            constexpr uint32_t idesc64 = umma_idesc_bf16_bmn(128, 64), idesc16 = umma_idesc_bf16_bmn(128, 16);
+            for (int j = 0; j < n_tiles; ++j) {
+                if (j + 1 < n_tiles) issue_s(j + 1);
+                const int s = j % G2_NS;
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < G2_BK / 16; ++ks) {
+                    const uint64_t dp = umma_desc_sw128_kmajor(smem_u32(p_s)) + 2 * ks;
+                    const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+                    umma_bf16(tmem_base + G2_O_COL, dp, umma_desc_sw128_mnmajor(smem_u32(v_a(s) + ks * 2048)), idesc64, acc);
+                    umma_bf16(tmem_base + G2_O_COL + 64, dp, umma_desc_sw32_mnmajor(smem_u32(v_b(s) + ks * 512)), idesc16, acc);
+                }
+                umma_commit(&kv_empty[s]);
+                umma_commit(pv_done);
+            }
+        }
+    } else if (warp >= 4) {
+        // two threads per query row: warps 4-7 (half 0) take key columns [0,32) of every 64-key tile, warps 8-11 (half 1) take
+        // [32,64); warp w and w+4 share a TMEM lane quadrant.  Twice the warps per scheduler hide the TMEM / barrier latencies
+        // that left the issue slots half empty with one thread per row.
+        const int quad = warp & 3, half = (warp >> 2) - 1;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16);
+        const int qtok = q0 + r;
+        const int qy = qtok / KW, qx = qtok - qy * KW;
+        // ---- prologue: half 0 files rel_h[ky][r] = T_h[r][qy - ky + 63], half 1 files rel_w[kx][r] = T_w[r][qx - kx + 63]
+        mbar_wait(t_full, 0);
+        tc_fence_after();
+        {
+            bf16* dst = half == 0 ? th_s : tw_s;
+            const int qq = (half == 0 ? qy : qx) + KW - 1;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(lane_addr + half * 128 + c0, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int kk = qq - (c0 + i);
+                    if (kk >= 0 && kk < KW) dst[kk * AT_BQ + r] = __float2bfloat16_rn(__uint_as_float(raw[i]));
+                }
+            }
+        }
+        tc_fence_before();
+        named_bar_sync(1, 256);   // both tables complete (each half reads what the other wrote); T_h / T_w columns are free
+        if (lane == 0) { mbar_arrive(&s_empty[0]); mbar_arrive(&s_empty[1]); }
+        const bf16* th_r = th_s + r;
+        // this thread's 32 rel_w values (the same for every key row): packed bf16 pairs in 16 registers
+        uint32_t twp[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t lo = *reinterpret_cast<const uint16_t*>(tw_s + (half * 32 + 2 * i) * AT_BQ + r);
+            const uint32_t hi = *reinterpret_cast<const uint16_t*>(tw_s + (half * 32 + 2 * i + 1) * AT_BQ + r);
+            twp[i] = lo | (hi << 16);
+        }
+
+        float m_ref = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int sb = j & 1;
+            mbar_wait(&s_full[sb], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t xr[32];
+            tmem_ld_32x32(lane_addr + sb * G2_BK + half * 32, xr);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[sb]);
+            const float rh = __bfloat162float(th_r[j * AT_BQ]);   // key row ky == j
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float tw = __uint_as_float((i & 1) ? (twp[i >> 1] & 0xffff0000u) : (twp[i >> 1] << 16));
+                const float x = fmaf(__uint_as_float(xr[i]), p.scale_log2, (tw + rh) * AT_LOG2E);
+                xr[i] = __float_as_uint(x);
+                mx = fmaxf(mx, x);
+            }
+            // row maximum over both halves
+            float* mb = mxbuf + (j & 1) * 2 * AT_BQ;
+            mb[half * AT_BQ + r] = mx;
+            named_bar_sync(2 + quad, 64);
+            mx = fmaxf(mx, mb[(half ^ 1) * AT_BQ + r]);
+            float corr = 1.f;
+            bool moved = false;
+            if (j == 0) {
+                m_ref = mx;
+            } else if (mx > m_ref + 8.f) {
+                corr = ex2_approx(m_ref - mx);
+                m_ref = mx;
+                moved = true;
+            }
+            float sum = 0.f;
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                const float p0 = ex2_approx(__uint_as_float(xr[c]) - m_ref), p1 = ex2_approx(__uint_as_float(xr[c + 1]) - m_ref);
+                sum += p0 + p1;
+                pk[c >> 1] = pack_bf16x2(p0, p1);
+            }
+            l_run = l_run * corr + sum;
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, moved)) {   // the partner warp sees the same rows and takes the same branch
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        const int c0 = half * 48 + cc * 16;
+                        if (c0 < AT_HD) {
+                            uint32_t o[16];
+                            tmem_ld_32x16(lane_addr + G2_O_COL + c0, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                            tmem_st_32x16(lane_addr + G2_O_COL + c0, o);
+                        }
+                    }
+                    tmem_st_wait();
+                }
+            }
+            uint8_t* row = p_s + r * 128;
+#pragma unroll
+            for (int c16 = 0; c16 < 4; ++c16)
+                *reinterpret_cast<uint4*>(row + (((half * 4 + c16) ^ (r & 7)) << 4)) =
+                    make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        lbuf[half * AT_BQ + r] = l_run;
+        mbar_wait(pv_done, (n_tiles - 1) & 1);
+        tc_fence_after();
+        named_bar_sync(2 + quad, 64);
+        const float l_tot = lbuf[r] + lbuf[AT_BQ + r];
+        const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+        bf16* orow = p.out + (long long)(row_base + qtok) * p.out_ld + h * AT_HD;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+            const int c0 = half * 48 + cc * 16;
+            if (c0 < AT_HD) {
+                uint32_t o[16];
+                tmem_ld_32x16(lane_addr + G2_O_COL + c0, o);
+                tmem_ld_wait();
+                uint4 u0, u1;
+                u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+                u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+                u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+                u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+                u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+                reinterpret_cast<uint4*>(orow + c0)[0] = u0;
+                reinterpret_cast<uint4*>(orow + c0)[1] = u1;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ 14x14 windows
 // Window attention has 196 keys: ONE key tile (UMMA N = 208), no online softmax, and so little work per (window, head,
 // query tile) that latency dominates.  This variant is sized for TWO resident CTAs per SM (112 KB shared memory, 256
@@ -934,13 +1201,17 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_window_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WN_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_global64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_global64h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2H_SMEM));
         h->attr_done |= 1ull << 16;
     }
-    if (Wq == 64 && h->global_attn_variant == 0) {
+    if (Wq == 64 && (h->global_attn_variant == 0 || h->global_attn_variant == 2)) {
         const CUtensorMap *kva, *kvb;
         IVLM_TRY(get_tmap_bf16_ex(h, qkv, rows, 3 * (uint64_t)E, 3 * (uint64_t)E, G2_BK, 64, 128, &kva));
         IVLM_TRY(get_tmap_bf16_ex(h, qkv, rows, 3 * (uint64_t)E, 3 * (uint64_t)E, G2_BK, 16, 32, &kvb));
-        sam_attn_global64_kernel<<<grid, G2_THREADS, G2_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *rha, *rhb, *rwa, *rwb, p);
+        if (h->global_attn_variant == 0)
+            sam_attn_global64h_kernel<<<grid, G2H_THREADS, G2H_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *rha, *rhb, *rwa, *rwb, p);
+        else
+            sam_attn_global64_kernel<<<grid, G2_THREADS, G2_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *rha, *rhb, *rwa, *rwb, p);
     } else if (Wq == 64) {
         sam_attn_tcgen05_kernel<64><<<grid, AT_THREADS, AT_SMEM, stream>>>(*qa, *qb, *rha, *rhb, *rwa, *rwb, p);
     } else if (h->window_attn_variant == 0) {
