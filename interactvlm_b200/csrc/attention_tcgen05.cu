@@ -656,9 +656,13 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
     bf16* th_s = reinterpret_cast<bf16*>(p_s + G2_P);  // rel_h[ky][row]
     bf16* tw_s = th_s + 64 * AT_BQ;                    // rel_w[kx][row]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tw_s) + G2_TAB);
-    uint64_t *q_full = bars, *tab_full = bars + 1, *t_full = bars + 2, *kv_full = bars + 3, *kv_empty = bars + 5,
-             *s_full = bars + 7, *s_empty = bars + 9, *p_full = bars + 11, *pv_done = bars + 12;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    // K and V of a stage have their own barriers: a K slot is free as soon as S = Q K^T of its tile has completed (two tiles
+    // before the slot is needed again), a V slot only after P V -- with one barrier pair per stage the next K load could not
+    // start before the previous tile's P V had finished and its latency sat on the critical path of every tile
+    uint64_t *q_full = bars, *tab_full = bars + 1, *t_full = bars + 2, *k_full = bars + 3, *k_empty = bars + 5,
+             *s_full = bars + 7, *s_empty = bars + 9, *p_full = bars + 11, *pv_done = bars + 12, *v_full = bars + 13,
+             *v_empty = bars + 15;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
     float* mxbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [tile parity][half][row]
     float* lbuf = mxbuf + 4 * AT_BQ;                                                   // [half][row]
 
@@ -670,7 +674,9 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
 
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1); mbar_init(tab_full, 1); mbar_init(t_full, 1);
-        for (int s = 0; s < G2_NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < G2_NS; ++s) {
+            mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+        }
         for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8); }
         mbar_init(p_full, 8);
         mbar_init(pv_done, 1);
@@ -682,9 +688,8 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // warps 0-3 (TMA, MMA issue, TMEM allocation) hand registers to the eight softmax warps
-    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
-
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, AT_QA + AT_QB);
@@ -696,15 +701,24 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
             tma_load_2d(stage0 + 128 * 128, &tmRHb, tab_full, 64, 0);
             tma_load_2d(stage0 + G2_STAGE, &tmRWa, tab_full, 0, 0);
             tma_load_2d(stage0 + G2_STAGE + 128 * 128, &tmRWb, tab_full, 64, 0);
+            for (int j = 0; j < n_tiles; ++j) {   // K ring (warp 3 feeds the V ring)
+                const int s = j % G2_NS;
+                mbar_wait(&k_empty[s], (j / G2_NS) & 1);
+                mbar_arrive_expect_tx(&k_full[s], G2_STAGE / 2);
+                const int r = row_base + j * G2_BK;
+                tma_load_2d(k_a(s), &tmKVa, &k_full[s], E + h * AT_HD, r);
+                tma_load_2d(k_b(s), &tmKVb, &k_full[s], E + h * AT_HD + 64, r);
+            }
+        }
+    } else if (warp == 3) {
+        if (lane == 0) {
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j % G2_NS;
-                mbar_wait(&kv_empty[s], (j / G2_NS) & 1);
-                mbar_arrive_expect_tx(&kv_full[s], G2_STAGE);
+                mbar_wait(&v_empty[s], (j / G2_NS) & 1);
+                mbar_arrive_expect_tx(&v_full[s], G2_STAGE / 2);
                 const int r = row_base + j * G2_BK;
-                tma_load_2d(k_a(s), &tmKVa, &kv_full[s], E + h * AT_HD, r);
-                tma_load_2d(k_b(s), &tmKVb, &kv_full[s], E + h * AT_HD + 64, r);
-                tma_load_2d(v_a(s), &tmKVa, &kv_full[s], 2 * E + h * AT_HD, r);
-                tma_load_2d(v_b(s), &tmKVb, &kv_full[s], 2 * E + h * AT_HD + 64, r);
+                tma_load_2d(v_a(s), &tmKVa, &v_full[s], 2 * E + h * AT_HD, r);
+                tma_load_2d(v_b(s), &tmKVb, &v_full[s], 2 * E + h * AT_HD + 64, r);
             }
         }
     } else if (warp == 1) {
@@ -716,11 +730,11 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
             issue_qk(tmem_base + 0, q_a, q_b, stage0, stage0 + 128 * 128);                            // T_h
             issue_qk(tmem_base + 128, q_a, q_b, stage0 + G2_STAGE, stage0 + G2_STAGE + 128 * 128);    // T_w
             umma_commit(t_full);
-            for (int s = 0; s < G2_NS; ++s) umma_commit(&kv_empty[s]);
+            for (int s = 0; s < G2_NS; ++s) { umma_commit(&k_empty[s]); umma_commit(&v_empty[s]); }
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, G2_BK);
             auto issue_s = [&](int j) {
                 const int s = j % G2_NS, sb = j & 1;
-                mbar_wait(&kv_full[s], (j / G2_NS) & 1);
+                mbar_wait(&k_full[s], (j / G2_NS) & 1);
                 mbar_wait(&s_empty[sb], (j >> 1) & 1);
                 tc_fence_after();
                 const uint64_t dk = umma_desc_sw128_kmajor(smem_u32(k_a(s)));
@@ -728,12 +742,14 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
                 for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + sb * G2_BK, dqa + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
                 umma_bf16(tmem_base + sb * G2_BK, dqb, umma_desc_sw32_kmajor(smem_u32(k_b(s))), idesc_s, 1u);
                 umma_commit(&s_full[sb]);
+                umma_commit(&k_empty[s]);
             };
             issue_s(0);
             constexpr uint32_t idesc64 = umma_idesc_bf16_bmn(128, 64), idesc16 = umma_idesc_bf16_bmn(128, 16);
             for (int j = 0; j < n_tiles; ++j) {
                 if (j + 1 < n_tiles) issue_s(j + 1);
                 const int s = j % G2_NS;
+                mbar_wait(&v_full[s], (j / G2_NS) & 1);
                 mbar_wait(p_full, j & 1);
                 tc_fence_after();
 #pragma unroll
@@ -743,11 +759,13 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
                     umma_bf16(tmem_base + G2_O_COL, dp, umma_desc_sw128_mnmajor(smem_u32(v_a(s) + ks * 2048)), idesc64, acc);
                     umma_bf16(tmem_base + G2_O_COL + 64, dp, umma_desc_sw32_mnmajor(smem_u32(v_b(s) + ks * 512)), idesc16, acc);
                 }
-                umma_commit(&kv_empty[s]);
+                umma_commit(&v_empty[s]);
                 umma_commit(pv_done);
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         // two threads per query row: warps 4-7 (half 0) take key columns [0,32) of every 64-key tile, warps 8-11 (half 1) take
         // [32,64); warp w and w+4 share a TMEM lane quadrant.  Twice the warps per scheduler hide the TMEM / barrier latencies
         // that left the issue slots half empty with one thread per row.
@@ -1163,6 +1181,253 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
     }
 }
 
+// ------------------------------------------------------------------------------------------------ 14x14 windows, 2 threads / row
+// sam_attn_window_tcgen05_kernel with eight softmax warps (two threads per query row: key columns [0,96) and [96,208)); the
+// row maximum and row sum are exchanged through shared memory.  Still two CTAs per SM.
+constexpr int WNH_THREADS = 288;
+constexpr int WNH_SMEM = WN_SMEM;   // the exchange buffer aliases a dead tile: two CTAs still fit per SM
+
+__global__ void __launch_bounds__(WNH_THREADS, 2)
+sam_attn_window_h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+                               const __grid_constant__ CUtensorMap tmKVa, const __grid_constant__ CUtensorMap tmKVb,
+                               const __grid_constant__ CUtensorMap tmRHa, const __grid_constant__ CUtensorMap tmRHb,
+                               const __grid_constant__ CUtensorMap tmRWa, const __grid_constant__ CUtensorMap tmRWb,
+                               const SamAttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    bf16* th_s = reinterpret_cast<bf16*>(smem + WN_OFF_TH);  // [28 idx][128 rows]
+    bf16* tw_s = reinterpret_cast<bf16*>(smem + WN_OFF_TW);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WN_OFF_BAR);
+    uint64_t *qt_full = bars, *k_full = bars + 1, *v_full = bars + 2, *t_full = bars + 3, *t_read = bars + 4,
+             *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* xbuf = reinterpret_cast<float*>(smem + WN_OFF_RHA);   // [max | sum][half][row]: over the rel-pos table tile, dead once T is done
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+    const int E = p.heads * AT_HD;
+    const int row_base = b * WN_S;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_init(qt_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(t_full, 1);
+            mbar_init(t_read, 8); mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(o_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ------------------------------------------------------------------ control: TMA + MMA issue
+        if (lane == 0) {
+            mbar_arrive_expect_tx(qt_full, 20480 + 2 * (4096 + 1024));
+            tma_load_2d(smem + WN_OFF_QA, &tmQa, qt_full, h * AT_HD, row_base + q0);
+            tma_load_2d(smem + WN_OFF_QB, &tmQb, qt_full, h * AT_HD + 64, row_base + q0);
+            tma_load_2d(smem + WN_OFF_RHA, &tmRHa, qt_full, 0, 0);
+            tma_load_2d(smem + WN_OFF_RHB, &tmRHb, qt_full, 64, 0);
+            tma_load_2d(smem + WN_OFF_RWA, &tmRWa, qt_full, 0, 0);
+            tma_load_2d(smem + WN_OFF_RWB, &tmRWb, qt_full, 64, 0);
+            mbar_arrive_expect_tx(k_full, WN_KA + WN_KB);
+            tma_load_2d(smem + WN_OFF_KA, &tmKVa, k_full, E + h * AT_HD, row_base);
+            tma_load_2d(smem + WN_OFF_KB, &tmKVb, k_full, E + h * AT_HD + 64, row_base);
+            mbar_arrive_expect_tx(v_full, WN_KA + WN_KB);
+            tma_load_2d(smem + WN_OFF_VA, &tmKVa, v_full, 2 * E + h * AT_HD, row_base);
+            tma_load_2d(smem + WN_OFF_VB, &tmKVb, v_full, 2 * E + h * AT_HD + 64, row_base);
+
+            const uint64_t dqa = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_QA));
+            const uint64_t dqb = umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_QB));
+            mbar_wait(qt_full, 0);
+            tc_fence_after();
+            {   // T_h -> cols [0,32), T_w -> cols [32,64): Q . table^T, N = 32 (27 table rows + zero fill)
+                constexpr uint32_t idesc = umma_idesc_bf16(128, 32);
+                const uint64_t dh = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_RHA));
+                const uint64_t dw = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_RWA));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dqa + 2 * k, dh + 2 * k, idesc, k > 0 ? 1u : 0u);
+                umma_bf16(tmem_base, dqb, umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_RHB)), idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 32, dqa + 2 * k, dw + 2 * k, idesc, k > 0 ? 1u : 0u);
+                umma_bf16(tmem_base + 32, dqb, umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_RWB)), idesc, 1u);
+                umma_commit(t_full);
+            }
+            mbar_wait(k_full, 0);
+            mbar_wait(t_read, 0);  // the softmax warps have taken T_h / T_w out of the columns S overwrites
+            tc_fence_after();
+            {   // S = Q K^T, N = 208
+                constexpr uint32_t idesc = umma_idesc_bf16(128, WN_KEYS);
+                const uint64_t dk = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_KA));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dqa + 2 * k, dk + 2 * k, idesc, k > 0 ? 1u : 0u);
+                umma_bf16(tmem_base, dqb, umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_KB)), idesc, 1u);
+                umma_commit(s_full);
+            }
+            mbar_wait(v_full, 0);
+            mbar_wait(p_full, 0);
+            tc_fence_after();
+            {   // O = P V over 13 key steps of 16
+                constexpr uint32_t idesc64 = umma_idesc_bf16_bmn(128, 64), idesc16 = umma_idesc_bf16_bmn(128, 16);
+#pragma unroll
+                for (int ks = 0; ks < WN_KEYS / 16; ++ks) {
+                    const uint64_t dp = ks < 12 ? umma_desc_sw128_kmajor(smem_u32(smem + (ks >> 2) * 16384)) + 2 * (ks & 3)
+                                                : umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_P3));
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
+                    umma_bf16(tmem_base, dp, umma_desc_sw128_mnmajor(smem_u32(smem + WN_OFF_VA + ks * 2048)), idesc64, acc);
+                    umma_bf16(tmem_base + 64, dp, umma_desc_sw32_mnmajor(smem_u32(smem + WN_OFF_VB + ks * 512)), idesc16, acc);
+                }
+                umma_commit(o_full);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps: two threads per query row
+        // warps 0-3 (half 0) own key columns [0,96), warps 4-7 (half 1) own [96,208); warp w and w+4 share a TMEM lane quadrant.
+        const int quad = warp & 3, half = warp >> 2;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16);
+        const int qtok = q0 + r;
+        const bool q_ok = qtok < WN_S;
+        const int qy = q_ok ? qtok / WN_KW : 0, qx = q_ok ? qtok - (qtok / WN_KW) * WN_KW : 0;
+        mbar_wait(t_full, 0);
+        tc_fence_after();
+        {   // half 0 files T_h, half 1 files T_w
+            uint32_t tt[32];
+            tmem_ld_32x32(lane_addr + half * 32, tt);
+            tmem_ld_wait();
+            bf16* dst = half == 0 ? th_s : tw_s;
+#pragma unroll
+            for (int i = 0; i < 28; ++i) dst[i * AT_BQ + r] = __float2bfloat16_rn(__uint_as_float(tt[i]));
+        }
+        tc_fence_before();
+        named_bar_sync(1, 256);
+        if (lane == 0) mbar_arrive(t_read);
+        float rh[WN_KW], rw[WN_KW];  // this row's rel_h[ky], rel_w[kx] (bf16 values), pre-multiplied by log2(e)
+#pragma unroll
+        for (int i = 0; i < WN_KW; ++i) {
+            rh[i] = __bfloat162float(th_s[(qy - i + WN_KW - 1) * AT_BQ + r]) * AT_LOG2E;
+            rw[i] = __bfloat162float(tw_s[(qx - i + WN_KW - 1) * AT_BQ + r]) * AT_LOG2E;
+        }
+        mbar_wait(s_full, 0);
+        tc_fence_after();
+        // ---- pass 1: x = s*scale + bias (log2 domain) written back in place, row max over this thread's columns
+        float mx = -INFINITY;
+        uint32_t ra[32];
+        uint32_t rc[16];
+#define WINH_PASS1(C0)                                                  \
+        {                                                               \
+            tmem_ld_32x32(lane_addr + C0, ra);                          \
+            tmem_ld_wait();                                             \
+            mx = win_scores<C0, 32>(ra, rh, rw, p.scale_log2, mx);      \
+            tmem_st_32x32(lane_addr + C0, ra);                          \
+        }
+        if (half == 0) {
+            WINH_PASS1(0) WINH_PASS1(32) WINH_PASS1(64)
+        } else {
+            WINH_PASS1(96) WINH_PASS1(128) WINH_PASS1(160)
+            tmem_ld_32x16(lane_addr + 192, rc);
+            tmem_ld_wait();
+            mx = win_scores<192, 16>(rc, rh, rw, p.scale_log2, mx);
+            tmem_st_32x16(lane_addr + 192, rc);
+        }
+#undef WINH_PASS1
+        tmem_st_wait();
+        xbuf[half * AT_BQ + r] = mx;
+        named_bar_sync(2 + quad, 64);
+        mx = fmaxf(mx, xbuf[(half ^ 1) * AT_BQ + r]);
+        // ---- pass 2: p = 2^(x - max) -> bf16 -> swizzled P (aliases the dead Q / K tiles)
+        float sum = 0.f;
+        auto exp_chunk = [&](const uint32_t(&raw)[32], int c0) {
+            uint8_t* row = smem + (c0 >> 6) * 16384 + r * 128;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e]) - mx);
+                    const float p1 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e + 1]) - mx);
+                    sum += p0 + p1;
+                    pk[e] = pack_bf16x2(p0, p1);
+                }
+                const int c16 = ((c0 & 63) >> 3) + j8;
+                *reinterpret_cast<uint4*>(row + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        };
+#define WINH_PASS2(C0)                                  \
+        {                                               \
+            tmem_ld_32x32(lane_addr + C0, ra);          \
+            tmem_ld_wait();                             \
+            exp_chunk(ra, C0);                          \
+        }
+        if (half == 0) {
+            WINH_PASS2(0) WINH_PASS2(32) WINH_PASS2(64)
+        } else {
+            WINH_PASS2(96) WINH_PASS2(128) WINH_PASS2(160)
+            tmem_ld_32x16(lane_addr + 192, rc);
+            tmem_ld_wait();
+            uint8_t* row = smem + WN_OFF_P3 + r * 32;
+#pragma unroll
+            for (int j8 = 0; j8 < 2; ++j8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = ex2_approx(__uint_as_float(rc[j8 * 8 + 2 * e]) - mx);
+                    const float p1 = ex2_approx(__uint_as_float(rc[j8 * 8 + 2 * e + 1]) - mx);
+                    sum += p0 + p1;
+                    pk[e] = pack_bf16x2(p0, p1);
+                }
+                *reinterpret_cast<uint4*>(row + ((j8 ^ ((r >> 2) & 1)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+#undef WINH_PASS2
+        xbuf[(2 + half) * AT_BQ + r] = sum;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // ---- epilogue
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        named_bar_sync(2 + quad, 64);
+        const float tot = xbuf[2 * AT_BQ + r] + xbuf[3 * AT_BQ + r];
+        const float inv = tot > 0.f ? 1.f / tot : 0.f;
+        long long orow_i = q_ok ? (long long)(row_base + qtok) : -1;
+        if (q_ok && p.out_map != nullptr) orow_i = p.out_map[row_base + qtok];
+        const bool st_ok = orow_i >= 0;
+        bf16* orow = p.out + (st_ok ? orow_i : 0) * p.out_ld + h * AT_HD;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+            const int c0 = half * 48 + cc * 16;
+            if (c0 < AT_HD) {
+                uint32_t o[16];
+                tmem_ld_32x16(lane_addr + c0, o);
+                tmem_ld_wait();
+                if (st_ok) {
+                    uint4 u0, u1;
+                    u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                    u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                    u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                    u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+                    u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+                    u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+                    u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+                    u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+                    reinterpret_cast<uint4*>(orow + c0)[0] = u0;
+                    reinterpret_cast<uint4*>(orow + c0)[1] = u1;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
 }  // namespace ivlm
 
 using namespace ivlm;
@@ -1193,13 +1458,14 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
     p.KH = Hq;
     p.scale_log2 = (1.0f / sqrtf((float)hd)) * AT_LOG2E;
     p.out_map = out_row_map;
-    IVLM_REQUIRE(out_row_map == nullptr || (Wq == 14 && h->window_attn_variant == 0),
+    IVLM_REQUIRE(out_row_map == nullptr || (Wq == 14 && h->window_attn_variant != 1),
                  "sam_attention: out_row_map is implemented by the 14x14 window kernel only");
     dim3 grid((S + AT_BQ - 1) / AT_BQ, heads, B);
     if (!(h->attr_done & (1ull << 16))) {   // per handle = per device
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_window_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WN_SMEM));
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_window_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WNH_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_global64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_global64h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2H_SMEM));
         h->attr_done |= 1ull << 16;
@@ -1214,7 +1480,7 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
             sam_attn_global64_kernel<<<grid, G2_THREADS, G2_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *rha, *rhb, *rwa, *rwb, p);
     } else if (Wq == 64) {
         sam_attn_tcgen05_kernel<64><<<grid, AT_THREADS, AT_SMEM, stream>>>(*qa, *qb, *rha, *rhb, *rwa, *rwb, p);
-    } else if (h->window_attn_variant == 0) {
+    } else if (h->window_attn_variant == 0 || h->window_attn_variant == 2) {
         const CUtensorMap *kva, *kvb, *wha, *whb, *wwa, *wwb;
         IVLM_TRY(get_tmap_bf16_ex(h, qkv, rows, 3 * (uint64_t)E, 3 * (uint64_t)E, WN_KEYS, 64, 128, &kva));
         IVLM_TRY(get_tmap_bf16_ex(h, qkv, rows, 3 * (uint64_t)E, 3 * (uint64_t)E, WN_KEYS, 16, 32, &kvb));
@@ -1222,7 +1488,10 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
         IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_h, 2 * Hq - 1, hd, hd, 32, 16, 32, &whb));
         IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_w, 2 * Wq - 1, hd, hd, 32, 64, 128, &wwa));
         IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_w, 2 * Wq - 1, hd, hd, 32, 16, 32, &wwb));
-        sam_attn_window_tcgen05_kernel<<<grid, WN_THREADS, WN_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *wha, *whb, *wwa, *wwb, p);
+        if (h->window_attn_variant == 0)
+            sam_attn_window_h_kernel<<<grid, WNH_THREADS, WNH_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *wha, *whb, *wwa, *wwb, p);
+        else
+            sam_attn_window_tcgen05_kernel<<<grid, WN_THREADS, WN_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *wha, *whb, *wwa, *wwb, p);
     } else {
         sam_attn_tcgen05_kernel<14><<<grid, AT_THREADS, AT_SMEM, stream>>>(*qa, *qb, *rha, *rhb, *rwa, *rwb, p);
     }

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) upscale_hyper_dot_kernel(const bf16* __re
 
 // Device-side bookkeeping of the greedy / scripted decode loop, so that a decode step is a pure graph replay.
 // state[0] = number of tokens fed so far (advanced here), state[1] = the step the rest of this replay works on.
-__global__ void decode_prepare_kernel(int* __restrict__ state, int S, const int* __restrict__ scripted, int G,
+__global__ void decode_prepare_kernel(int* __restrict__ state, int S, const int* __restrict__ S_rows, const int* __restrict__ scripted, int G,
                                       const int* __restrict__ next, int* __restrict__ done, int* __restrict__ out_tokens,
                                       int* __restrict__ tok, int* __restrict__ pos, int* __restrict__ slot,
                                       int* __restrict__ seq_lens, const int* __restrict__ slot_base, int eos, int pad, int B) {
@@ -120,7 +120,7 @@ __global__ void decode_prepare_kernel(int* __restrict__ state, int S, const int*
         if (done[b]) t = pad;
         out_tokens[b * G + step] = t;
         if (t == eos) done[b] = 1;
-        const int p = S + step;
+        const int p = (S_rows != nullptr ? S_rows[b] : S) + step;   // per-sample prompt length (right-padded batches)
         tok[b] = t;
         pos[b] = p;
         slot[b] = slot_base[b] + p;
@@ -132,10 +132,10 @@ __global__ void decode_prepare_kernel(int* __restrict__ state, int S, const int*
     }
 }
 // hidden[b, S + step, :] = hid_step[b, :]
-__global__ void decode_finish_kernel(const int* __restrict__ state, int S, const bf16* __restrict__ hid_step,
-                                     bf16* __restrict__ hidden, int D, int max_len) {
+__global__ void decode_finish_kernel(const int* __restrict__ state, int S, const int* __restrict__ S_rows,
+                                     const bf16* __restrict__ hid_step, bf16* __restrict__ hidden, int D, int max_len) {
     pdl_wait_then_launch();
-    const int b = blockIdx.x, p = S + state[1];
+    const int b = blockIdx.x, p = (S_rows != nullptr ? S_rows[b] : S) + state[1];
     const uint4* src = reinterpret_cast<const uint4*>(hid_step + (long long)b * D);
     uint4* dst = reinterpret_cast<uint4*>(hidden + ((long long)b * max_len + p) * D);
     for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) dst[i] = src[i];
@@ -145,25 +145,25 @@ __global__ void decode_finish_kernel(const int* __restrict__ state, int S, const
 
 using namespace ivlm;
 
-extern "C" int ivlm_decode_prepare(ivlm_handle h, int32_t* state, int32_t S, const int32_t* scripted, int32_t G,
+extern "C" int ivlm_decode_prepare(ivlm_handle h, int32_t* state, int32_t S, const int32_t* S_rows, const int32_t* scripted, int32_t G,
                                    const int32_t* next, int32_t* done, int32_t* out_tokens, int32_t* tok, int32_t* pos,
                                    int32_t* slot, int32_t* seq_lens, const int32_t* slot_base, int32_t eos, int32_t pad,
                                    int32_t B, void* stream) {
     IVLM_REQUIRE(h && state && next && done && out_tokens && tok && pos && slot && seq_lens && slot_base && B > 0 && G > 0,
                  "decode_prepare: bad arguments");
     IVLM_CHECK_CUDA(launch_k(h, decode_prepare_kernel, dim3(1), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), (int*)state,
-                             (int)S, (const int*)scripted, (int)G, (const int*)next, (int*)done, (int*)out_tokens, (int*)tok,
+                             (int)S, (const int*)S_rows, (const int*)scripted, (int)G, (const int*)next, (int*)done, (int*)out_tokens, (int*)tok,
                              (int*)pos, (int*)slot, (int*)seq_lens, (const int*)slot_base, (int)eos, (int)pad, (int)B));
     h->launches++;
     IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;
 }
 
-extern "C" int ivlm_decode_finish(ivlm_handle h, const int32_t* state, int32_t S, const void* hid_step, void* hidden,
+extern "C" int ivlm_decode_finish(ivlm_handle h, const int32_t* state, int32_t S, const int32_t* S_rows, const void* hid_step, void* hidden,
                                   int32_t B, int32_t D, int32_t max_len, void* stream) {
     IVLM_REQUIRE(h && state && hid_step && hidden && B > 0 && D % 8 == 0, "decode_finish: bad arguments");
     IVLM_CHECK_CUDA(launch_k(h, decode_finish_kernel, dim3(B), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
-                             (const int*)state, (int)S, (const bf16*)hid_step, (bf16*)hidden, (int)D, (int)max_len));
+                             (const int*)state, (int)S, (const int*)S_rows, (const bf16*)hid_step, (bf16*)hidden, (int)D, (int)max_len));
     h->launches++;
     IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;

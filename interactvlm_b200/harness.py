@@ -117,14 +117,14 @@ def validate(model, samples, batch_size=8, dist=None, max_new_tokens=32, contact
     n_verts = hmap.n if hmap is not None else 6890
     i = lo
     while i < hi:
-        j = i + 1
-        L = samples[i]["input_ids"].shape[-1]
-        while j < hi and j - i < batch_size and samples[j]["input_ids"].shape[-1] == L:
-            j += 1
+        j = min(i + batch_size, hi)
         chunk = samples[i:j]
         cat = lambda k: torch.stack([torch.as_tensor(s[k]) for s in chunk], 0)
         scripted = cat("scripted") if all("scripted" in s for s in chunk) else None
-        out = model.evaluate(cat("images_clip"), cat("images"), cat("input_ids"), cat("cam_params"),
+        # prompts of different lengths (object names differ) go in as a list: generate() right-pads them like the reference's
+        # collate_fn (datasets/dataset.py:159-178) and keeps per-sample positions
+        ids = [torch.as_tensor(s["input_ids"]).reshape(-1) for s in chunk]
+        out = model.evaluate(cat("images_clip"), cat("images"), ids, cat("cam_params"),
                              [tuple(s["resize"]) for s in chunk], [tuple(s["original_size"]) for s in chunk],
                              contact_type=contact_type, max_new_tokens=max_new_tokens, scripted=scripted)
         pc = out["pred_contact_3d"]

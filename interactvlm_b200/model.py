@@ -327,9 +327,11 @@ class _Engine:
         st["hidden"] = torch.zeros((B, max_len, cfg.hidden_size), device=self.device, dtype=torch.bfloat16)
         return st
 
-    def llm_prefill(self, st, embeds):
+    def llm_prefill(self, st, embeds, last_rows=None):
         """embeds [B,S,D] -> writes K/V pages and the normed last-layer hidden states of all S positions; returns the
-        greedy next token per sample [B] int32 (HF LlamaModel + lm_head, eager 4.31 numerics)."""
+        greedy next token per sample [B] int32 (HF LlamaModel + lm_head, eager 4.31 numerics).  last_rows (int32 [B], flat row
+        b*S + S_b - 1) selects each sample's last prompt row when prompts of different lengths are right-padded to S: causal
+        attention keeps the valid rows independent of the padding behind them."""
         ctx, cfg, W = self.ctx, self.cfg, self.w
         B, S, D = embeds.shape
         nh, hd = cfg.num_attention_heads, cfg.head_dim
@@ -352,7 +354,11 @@ class _Engine:
         hn = ctx.rmsnorm(x, W.norm, cfg.rms_norm_eps).view(B, S, D)
         st["hidden"][:, :S] = hn
         st["len"] = S
-        return self._greedy(hn[:, S - 1].contiguous(), out=st.get("next"))
+        if last_rows is None:
+            last = hn[:, S - 1].contiguous()
+        else:   # right-padded batch: the row that predicts the first new token is each sample's own last prompt row
+            last = ctx.gather_rows(hn.view(B * S, D), last_rows)
+        return self._greedy(last, out=st.get("next"))
 
     def _greedy(self, h, out=None, stream_kernel=False):
         """lm_head + argmax.  Rows go through the swapped-operand GEMM in chunks of <= 64 (the vocabulary size of the
@@ -383,6 +389,7 @@ class _Engine:
         st["done"] = torch.zeros((B,), dtype=torch.int32, device=self.device)
         st["max_new"] = 0
         st["slot_base"] = (torch.arange(B, dtype=torch.int32, device=self.device) * (st["pages_per"] * PAGE)).contiguous()
+        st["S_rows"] = torch.zeros((B,), dtype=torch.int32, device=self.device)   # per-sample prompt rows (right-padded batches)
 
     def llm_decode_step(self, st):
         """One token per sample through the paged KV cache.  All bookkeeping is on the device: `decode_prepare` picks the
@@ -899,17 +906,32 @@ class InteractVLMForCausalLM:
                 self.eng.llm_decode_step(st)
         return g
 
-    def generate(self, images_clip, input_ids, max_new_tokens=32, scripted=None, after_prefill=None):
+    def generate(self, images_clip, input_ids, max_new_tokens=32, scripted=None, after_prefill=None, prompt_lens=None):
         """Greedy decoding with a paged KV cache.  Returns (output_ids [B,L'] int64 on host, hidden [B,max_len,D] device
         buffer holding the normed last-layer state of every position of output_ids[:, :-1]).  `scripted` [B,G] forces
         the generated tokens (teacher forcing: same arithmetic, known [SEG] position)."""
         cfg, eng = self.config, self.eng
-        ids = torch.as_tensor(input_ids).cpu().to(torch.int64)
+        if isinstance(input_ids, (list, tuple)):   # prompts of different lengths: right-pad like the reference's collate_fn
+            seqs = [torch.as_tensor(t).reshape(-1).cpu().to(torch.int64) for t in input_ids]
+            prompt_lens = [int(t.numel()) for t in seqs]
+            ids = torch.full((len(seqs), max(prompt_lens)), cfg.pad_token_id, dtype=torch.int64)
+            for b, t in enumerate(seqs):
+                ids[b, : t.numel()] = t
+        else:
+            ids = torch.as_tensor(input_ids).cpu().to(torch.int64)
         B, L = ids.shape
+        if prompt_lens is None:   # datasets/dataset.py:159-178 pads with pad_token_id and masks `input_ids.ne(pad)`
+            nz = (ids != cfg.pad_token_id)
+            prompt_lens = [int(nz[b].nonzero().max()) + 1 if bool(nz[b].any()) else 0 for b in range(B)]
+        lens = torch.as_tensor(prompt_lens, dtype=torch.int64)
+        if int(lens.min()) < 1 or int(lens.max()) > L:
+            raise ValueError(f"prompt lengths {lens.tolist()} do not fit input_ids of width {L}")
+        ragged = bool((lens != L).any())
         if int((ids == IMAGE_TOKEN_INDEX).sum(1).min()) != 1 or int((ids == IMAGE_TOKEN_INDEX).sum(1).max()) != 1:
             raise ValueError("every prompt must contain exactly one IMAGE_TOKEN_INDEX (-200)")
         n_img = cfg.clip_tokens - 1
         S = L - 1 + n_img
+        S_rows = (lens - 1 + n_img).to(torch.int32)
         max_len = S + max_new_tokens
         if max_len > cfg.max_position_embeddings:
             raise ValueError(f"sequence {max_len} exceeds max_position_embeddings {cfg.max_position_embeddings}")
@@ -933,7 +955,11 @@ class InteractVLMForCausalLM:
         else:
             st["scripted"] = None
         key = "graph_scripted" if scripted is not None else "graph_greedy"
-        eng.llm_prefill(st, embeds)
+        st["S_rows"].copy_(S_rows)
+        last_rows = None
+        if ragged:
+            last_rows = (torch.arange(B, dtype=torch.int32) * S + S_rows - 1).to(self.device)
+        eng.llm_prefill(st, embeds, last_rows=last_rows)
         self._mark("llm_prefill")
         if after_prefill is not None:
             after_prefill(G - 1)  # the caller queues independent work (SAM encoder) next to the decode steps
@@ -969,11 +995,20 @@ class InteractVLMForCausalLM:
             n_new = int(first_eos.max().item()) + 1
         del done
         self._mark("llm_decode")
-        return torch.cat([ids, toks[:, :n_new]], 1), st["hidden"]
+        if not ragged:
+            return torch.cat([ids, toks[:, :n_new]], 1), st["hidden"]
+        # every sample's answer follows its own prompt; the tail is padding.  hidden[b, p] is the state of position p of THAT row.
+        out = torch.full((B, L + n_new), cfg.pad_token_id, dtype=torch.int64)
+        for b in range(B):
+            n = int(lens[b])
+            out[b, :n] = ids[b, :n]
+            out[b, n:n + n_new] = toks[b, :n_new]
+        return out, st["hidden"]
 
     # ---- public API ---------------------------------------------------------------------------------------------
     def evaluate(self, images_clip, images, input_ids, cam_params, resize_list, original_size_list,
-                 lift2d_dict_path=None, contact_type="hcontact", max_new_tokens=32, tokenizer=None, scripted=None):
+                 lift2d_dict_path=None, contact_type="hcontact", max_new_tokens=32, tokenizer=None, scripted=None,
+                 prompt_lens=None):
         """model/InteractVLM.py:510-638.  Returns {"output_ids", "pred_masks" (list of [V,H,W] fp32 logits),
         "pred_contact_3d" ([B,6890] / [1,Nv] fp32 or None)}."""
         cfg = self.config
@@ -981,9 +1016,10 @@ class InteractVLMForCausalLM:
             raise NotImplementedError("token_type '*-DifDe' (separate human / object mask decoders) is outside the hot path")
         emb = None
         if self.overlap is not None and self._view_cache is None and not self.record_stages and self.stage_delay is None:
-            output_ids, hidden, emb = self._generate_and_encode(images_clip, images, input_ids, max_new_tokens, scripted)
+            output_ids, hidden, emb = self._generate_and_encode(images_clip, images, input_ids, max_new_tokens, scripted,
+                                                                prompt_lens=prompt_lens)
         else:
-            output_ids, hidden = self.generate(images_clip, input_ids, max_new_tokens, scripted)
+            output_ids, hidden = self.generate(images_clip, input_ids, max_new_tokens, scripted, prompt_lens=prompt_lens)
         pred_masks = self._masks_from_hidden(hidden, output_ids, images, cam_params, resize_list, original_size_list,
                                              image_embeddings=emb)
         pred_contact_3d = None
@@ -1049,7 +1085,7 @@ class InteractVLMForCausalLM:
     def ctx_num_sms(self):
         return torch.cuda.get_device_properties(self.device).multi_processor_count
 
-    def _generate_and_encode(self, images_clip, images, input_ids, max_new_tokens, scripted):
+    def _generate_and_encode(self, images_clip, images, input_ids, max_new_tokens, scripted, prompt_lens=None):
         ov = self.overlap
         cur = torch.cuda.current_stream(self.device)
         hi, lo = ov["hi"], ov["lo"]
@@ -1084,7 +1120,8 @@ class InteractVLMForCausalLM:
                 box["ev"] = lo.record_event()
 
         with torch.cuda.stream(hi):
-            output_ids, hidden = self.generate(images_clip, input_ids, max_new_tokens, scripted, after_prefill=after_prefill)
+            output_ids, hidden = self.generate(images_clip, input_ids, max_new_tokens, scripted, after_prefill=after_prefill,
+                                               prompt_lens=prompt_lens)
             ev_llm = hi.record_event()
             if tr is not None:
                 tr.append(("decode_end", hi.record_event(torch.cuda.Event(enable_timing=True))))

@@ -405,14 +405,14 @@ class Context:
     def decode_prepare(self, st, S, G, eos, pad):
         """Device-side token / position bookkeeping of one decode step (st: the model's decode-state dict)."""
         B = st["tok"].numel()
-        L.check(self.lib.ivlm_decode_prepare(self.h, P(st["state"]), i32(S), P(st.get("scripted")), i32(G), P(st["next"]),
+        L.check(self.lib.ivlm_decode_prepare(self.h, P(st["state"]), i32(S), P(st.get("S_rows")), P(st.get("scripted")), i32(G), P(st["next"]),
                                              P(st["done"]), P(st["out_tokens"]), P(st["tok"]), P(st["pos"]), P(st["slot"]),
                                              P(st["seq_lens"]), P(st["slot_base"]), i32(eos), i32(pad), i32(B), self.stream),
                 "decode_prepare")
 
     def decode_finish(self, st, S):
         hid = st["hidden"]
-        L.check(self.lib.ivlm_decode_finish(self.h, P(st["state"]), i32(S), P(st["hid_step"]), P(hid), i32(hid.shape[0]),
+        L.check(self.lib.ivlm_decode_finish(self.h, P(st["state"]), i32(S), P(st.get("S_rows")), P(st["hid_step"]), P(hid), i32(hid.shape[0]),
                                             i32(hid.shape[2]), i32(hid.shape[1]), self.stream), "decode_finish")
 
     def argmax(self, logits, vocab=None, out=None):

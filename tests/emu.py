@@ -303,17 +303,21 @@ class EmuContext:
         t[st["done"].bool()] = pad
         st["out_tokens"][:, step] = t
         st["done"][t == eos] = 1
-        p = S + step
+        rows = st.get("S_rows")
+        p = (rows.to(torch.int32) if rows is not None else torch.full_like(t, S)) + step
         st["tok"].copy_(t)
-        st["pos"].fill_(p)
+        st["pos"].copy_(p)
         st["slot"].copy_(st["slot_base"] + p)
-        st["seq_lens"].fill_(p + 1)
+        st["seq_lens"].copy_(p + 1)
         st["state"][1] = step
         st["state"][0] = step + 1
 
     def decode_finish(self, st, S):
         self.launches += 1
-        st["hidden"][:, S + int(st["state"][1])] = st["hid_step"]
+        rows = st.get("S_rows")
+        step = int(st["state"][1])
+        for b in range(st["hidden"].shape[0]):
+            st["hidden"][b, (int(rows[b]) if rows is not None else S) + step] = st["hid_step"][b]
 
     def argmax(self, logits, vocab=None, out=None):
         self.launches += 1

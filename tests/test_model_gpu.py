@@ -143,6 +143,7 @@ def test_greedy_decode_kv_cache_and_cuda_graph(tiny):
     assert out_e[0, L].item() == int(gold["f32_greedy4"][0, 0]) == int(seq[0, L])
     agree = (out_e[0, L:L + 4] == torch.from_numpy(gold["f32_greedy4"][0])).float().mean().item()
     print("greedy agreement with the reference over 4 tokens:", agree)
+    assert agree == 1.0   # InteractVLM.py:524-531 greedy search through the KV cache == the reference's no-cache generate
     m = min(hidden.shape[1], n)
     if out_e.tolist() == seq.tolist():
         assert rel(hid_e[:, :m], hidden[:, :m]) < 2e-2     # decode-through-cache hidden states == full re-encode
@@ -357,3 +358,33 @@ def test_object_mesh_and_pointcloud_paths(tiny, tmp_path):
     pm = torch.stack(res["pred_masks"], 0).cpu().numpy()
     assert 0.0 <= pm.min() and pm.max() <= 1.0   # sigmoid-ed heat maps (InteractVLM.py:452-456)
     assert np.abs(res["pred_object_3d_afford"].cpu().numpy() - OL.lift_points(pm, p2p, 2048)).max() < 1e-5
+
+
+def test_prompts_of_different_lengths_in_one_batch(tiny):
+    """Ragged prompts in one batch on the CUDA path (right padding, per-sample positions in the decode bookkeeping kernels,
+    per-sample last prompt rows): every sample must come out as if it had been evaluated alone, and as the fp32 oracle says
+    on the unpadded prompt (reference: llava_arch.py:98-347 pads, its evaluate() is batch 1)."""
+    cfg, sd, model, (p2v, bary) = tiny
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 3)
+    prompts = [ids[0], ids[1][:-3], ids[2][:-7]]
+    for graphs in (True, False):
+        model.use_cuda_graph = graphs
+        model._graphs = {}
+        out = model.evaluate(clip, sam, prompts, cam, [SIZE] * 3, [SIZE] * 3, max_new_tokens=ans.shape[1], scripted=ans)
+        for b in range(3):
+            one = model.evaluate(clip[b:b + 1], sam[b:b + 1], prompts[b][None], cam[b:b + 1], [SIZE], [SIZE],
+                                 max_new_tokens=ans.shape[1], scripted=ans[b:b + 1])
+            n = prompts[b].numel() + ans.shape[1]
+            assert torch.equal(out["output_ids"][b, :n], one["output_ids"][0])
+            assert bool((out["output_ids"][b, n:] == cfg.pad_token_id).all())
+            assert (out["pred_contact_3d"][b] - one["pred_contact_3d"][0]).abs().max().item() < 2e-2
+            ref = OM.evaluate(sd, cfg, clip[b:b + 1], sam[b:b + 1], prompts[b][None], cam[b:b + 1], [SIZE], [SIZE],
+                              lift_maps=(p2v, bary, S.N_SMPL), max_new_tokens=ans.shape[1], scripted=ans[b:b + 1])
+            assert (out["pred_contact_3d"][b].cpu() - ref["pred_contact_3d"][0]).abs().max().item() < 0.05
+    model.use_cuda_graph = True
+    model._graphs = {}
+    g_ids, _ = model.generate(clip, prompts, max_new_tokens=3)
+    for b in range(3):
+        one, _ = model.generate(clip[b:b + 1], prompts[b][None], max_new_tokens=3)
+        n = one.shape[1]
+        assert g_ids[b, :n].tolist() == one[0].tolist()

@@ -230,3 +230,35 @@ def test_camera_encoder_and_token_type_variants(cam_type, token_type, tok_name):
     if token_type != "Gen" and tok_name != "seg":   # the splitter branch changed the prompt
         plain, _ = model.eng.seg_prompt(hid[0, rows[0]].bfloat16(), cam.bfloat16(), [cfg.seg_token_idx])
         assert (plain.float() - prompt.float()).abs().max().item() > 0.05
+
+
+def test_prompts_of_different_lengths_in_one_batch(setup):
+    """generate() / evaluate() with ragged prompts (right-padded like the reference's collate_fn, per-sample positions and
+    last-prompt rows) against the per-sample oracle run on the UNPADDED prompts (llava_arch.py:98-347 handles the padding in
+    the reference; its evaluate() is batch 1)."""
+    cfg, sd, model, (p2v, bary) = setup
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 3)
+    prompts = [ids[0], ids[1][:-3], ids[2][:-7]]                        # 22, 19 and 15 ids, each with its image token
+    out = model.evaluate(clip, sam, prompts, cam, [SIZE] * 3, [SIZE] * 3, max_new_tokens=ans.shape[1], scripted=ans)
+    assert out["pred_contact_3d"].shape == (3, S.N_SMPL)
+    for b in range(3):
+        ref = OM.evaluate(sd, cfg, clip[b:b + 1], sam[b:b + 1], prompts[b][None], cam[b:b + 1], [SIZE], [SIZE],
+                          lift_maps=(p2v, bary, S.N_SMPL), max_new_tokens=ans.shape[1], scripted=ans[b:b + 1])
+        n = prompts[b].numel() + ans.shape[1]
+        assert out["output_ids"][b, :n].tolist() == ref["output_ids"][0].tolist()
+        assert bool((out["output_ids"][b, n:] == cfg.pad_token_id).all())
+        assert np.abs(out["pred_contact_3d"][b].numpy() - ref["pred_contact_3d"][0].numpy()).max() < 0.08
+    # the padded-tensor form with explicit lengths gives the same thing, and so does greedy decoding
+    L = max(p.numel() for p in prompts)
+    padded = torch.full((3, L), cfg.pad_token_id, dtype=torch.int64)
+    for b, p in enumerate(prompts):
+        padded[b, : p.numel()] = p
+    out2 = model.evaluate(clip, sam, padded, cam, [SIZE] * 3, [SIZE] * 3, max_new_tokens=ans.shape[1], scripted=ans)
+    assert torch.equal(out2["output_ids"], out["output_ids"]) and torch.equal(out2["pred_contact_3d"], out["pred_contact_3d"])
+    w = OM.W(sd)
+    g_ids, _ = model.generate(clip, prompts, max_new_tokens=3)
+    for b in range(3):
+        with torch.no_grad():
+            seq, _, _ = OM.greedy_generate(w, cfg, clip[b:b + 1], prompts[b][None], 3)
+        n = seq.shape[1]
+        assert g_ids[b, :n].tolist() == seq[0].tolist()

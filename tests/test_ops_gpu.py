@@ -220,11 +220,25 @@ def test_sam_attention_tcgen05(ctx, Hq, Wq, B, heads):
     assert torch.isfinite(out.float()).all()
     assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
     assert (out.float() - ref).abs().max().item() < 3e-2
-    if Hq == 64:  # the 128-key-tile, one-CTA-per-SM variant must agree with the default 64-key-tile kernel
-        ctx.set_option("global_attn_variant", 1)
+    # the other kernel variants must agree with the default (two threads per query row): 64-key tiles with one thread per
+    # row (2), 128-key tiles / one CTA per SM (global, 1); one thread per row (window, 2), tiled kernel (window, 1)
+    opt = "global_attn_variant" if Hq == 64 else "window_attn_variant"
+    for variant in (1, 2):
+        ctx.set_option(opt, variant)
         alt = ctx.sam_attention(qkv, rph, rpw, B, heads, Hq, Wq, hd)
-        ctx.set_option("global_attn_variant", 0)
+        ctx.set_option(opt, 0)
         assert rel_err(alt, ref) < 1e-2 and rel_err(alt, out) < 5e-3
+    if Hq == 14:  # window_unpartition fused into the store: rows go to their token positions, padding rows are dropped
+        gmap = torch.randperm(B * S + 40, generator=torch.Generator().manual_seed(3))[: B * S].to(torch.int32)
+        gmap[::7] = -1
+        gmap = gmap.to(DEV)
+        scat = ctx.sam_attention(qkv, rph, rpw, B, heads, Hq, Wq, hd, out_map=gmap, out_rows=B * S + 40,
+                                 out=torch.zeros(B * S + 40, heads * hd, device=DEV, dtype=torch.bfloat16))
+        live = gmap >= 0
+        assert torch.equal(scat[gmap[live].long()], out[live])
+        dead = torch.ones(B * S + 40, dtype=torch.bool, device=DEV)
+        dead[gmap[live].long()] = False
+        assert scat[dead].abs().max().item() == 0
     # and against the first-generation path (separate rel-pos kernel + mma.sync flash attention)
     rel_h, rel_w = ctx.sam_relpos(qkv, rph, rpw, B, heads, Hq, Wq, hd)
     old = ctx.attention(q, k, v, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=Hq, kw=Wq).reshape(B * S, heads * hd)

@@ -30,7 +30,7 @@ def timeit(fn):
     return e0.elapsed_time(e1) / iters
 
 
-for name, B, side in (("global_8views", 8, 64), ("window_8views", 200, 14)):
+for name, B, side in (("global_16views", 16, 64), ("window_16views", 400, 14)):
     S = side * side
     qkv = rnd(B * S, 3 * heads * hd, sc=0.5)
     rph, rpw = rnd(2 * side - 1, hd, sc=0.3), rnd(2 * side - 1, hd, sc=0.3)
@@ -38,11 +38,12 @@ for name, B, side in (("global_8views", 8, 64), ("window_8views", 200, 14)):
     if which in ("both", "new"):
         ms = timeit(lambda: ctx.sam_attention(qkv, rph, rpw, B, heads, side, side, hd))
         print(f"{name} fused tcgen05: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
-        if side == 64:
-            ctx.set_option("global_attn_variant", 1)
+        opt = "global_attn_variant" if side == 64 else "window_attn_variant"
+        for variant, label in ((2, "one thread per row (round-1 kernel)"), (1, "128-key tiles / 1 CTA per SM" if side == 64 else "tiled kernel")):
+            ctx.set_option(opt, variant)
             ms = timeit(lambda: ctx.sam_attention(qkv, rph, rpw, B, heads, side, side, hd))
-            ctx.set_option("global_attn_variant", 0)
-            print(f"{name} fused tcgen05, 128-key tiles / 1 CTA per SM: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+            ctx.set_option(opt, 0)
+            print(f"{name} fused tcgen05, {label}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
     if which in ("both", "old"):
         t = qkv.view(B, S, 3, heads, hd)
 
