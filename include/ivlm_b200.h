@@ -200,6 +200,44 @@ IVLM_API int ivlm_decode_prepare(ivlm_handle h, int32_t* state, int32_t S, const
                         int32_t* seq_lens, const int32_t* slot_base, int32_t eos, int32_t pad, int32_t B, void* stream);
 IVLM_API int ivlm_decode_finish(ivlm_handle h, const int32_t* state, int32_t S, const int32_t* S_rows, const void* hid_step,
                        void* hidden, int32_t B, int32_t D, int32_t max_len, void* stream);
+/* Weight-streaming linear layer of a LLaMA decode step (token count M <= 8) with the row-wise neighbours fused in
+ * (csrc/decode_stream.cu): optional HF LlamaRMSNorm prologue on the activation rows, and one of three epilogues --
+ *   IVLM_EPI_PLAIN    out = act(A W^T + bias) + residual (o_proj, down_proj, lm_head of HF LlamaDecoderLayer / lm_head);
+ *   IVLM_EPI_SWIGLU   HF LlamaMLP: out[m,f] = bf16(bf16(silu(gate[m,f])) * up[m,f]); `w` holds gate/up rows INTERLEAVED in blocks
+ *                     of 8 (rows 16t..16t+7 = gate features 8t..8t+7, rows 16t+8..16t+15 = up features 8t..8t+7); out [M, N/2];
+ *   IVLM_EPI_ROPE_KV  HF apply_rotary_pos_emb + cache write: `w` = [q;k;v] rows with q/k rows PAIRED per head in blocks of 8
+ *                     (rows h*hd+16b..+7 = features h*hd+8b..+7, rows +8..+15 = the same features + hd/2), v rows natural;
+ *                     rotated q -> out [M, H*hd] (natural order), rotated k and v -> paged cache at slot_map[m]
+ *                     (layout of ivlm_rope_kv_store_bf16).
+ * Replaces, per decoder layer, the separate rmsnorm / rope_kv_store / silu_mul launches of the chain.  Needs a bound workspace;
+ * K must be a multiple of 64 and all operands 16-byte aligned (the weights arrive through a rank-3 TMA tensor map). */
+enum ivlm_decode_epilogue { IVLM_EPI_PLAIN = 0, IVLM_EPI_SWIGLU = 1, IVLM_EPI_ROPE_KV = 2 };
+typedef struct ivlm_decode_linear_args {
+    const void* a;          /* [M,K] bf16 activations (the un-normalised residual stream when norm_gamma != NULL) */
+    int64_t lda;
+    const void* w;          /* [N,K] bf16, row order as the epilogue requires */
+    int64_t ldw;
+    int32_t M, N, K;
+    const void* norm_gamma; /* [K] bf16 RMSNorm weight or NULL */
+    float norm_eps;
+    int32_t epilogue;       /* ivlm_decode_epilogue */
+    int32_t act;            /* PLAIN only: ivlm_act */
+    const void* bias;       /* PLAIN only: [N] bf16 or NULL */
+    const void* residual;   /* PLAIN only: [M,N] bf16 or NULL */
+    int64_t ldr;
+    void* out;              /* PLAIN [M,N]; SWIGLU [M,N/2]; ROPE_KV q [M,H*hd] */
+    int64_t ldo;
+    int32_t out_dtype;      /* IVLM_BF16 (IVLM_F32 allowed for PLAIN: raw accumulators, e.g. lm_head logits) */
+    /* ROPE_KV only */
+    const int32_t* positions; /* [M] */
+    const int32_t* slot_map;  /* [M] physical_page * page_size + offset */
+    const void* cos_t;        /* [max_pos, hd] bf16 */
+    const void* sin_t;
+    void* k_cache;            /* [pages, H, page_size, hd] bf16 */
+    void* v_cache;
+    int32_t H, hd, page_size;
+} ivlm_decode_linear_args;
+IVLM_API int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* args, void* stream);
 /* One-token attention over the paged KV cache: q [B,H*hd], block_table [B,max_pages], seq_lens [B]
  * (keys 0..seq_len-1, the current token already stored); caches laid out [pages, H, page_size, hd]. */
 IVLM_API int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, const void* k_cache, const void* v_cache,
