@@ -39,9 +39,11 @@ IVLM_API int ivlm_abi_version(void);
 /* Caller-owned scratch in device memory (>= 1 MiB; 32 MiB covers every shape on the path).  With a workspace bound,
  * weight-streaming GEMMs (small token counts) split K across CTAs and reduce the partials in-kernel, deterministically. */
 IVLM_API int ivlm_set_workspace(ivlm_handle h, void* ptr, size_t bytes, void* stream);
-/* Tuning / A-B switches (integer options): "window_attn_variant" 0 = single-tile window kernel (default), 1 = tiled kernel;
- * "global_attn_variant" 0 = 64-key tiles, 2 CTAs/SM (default), 1 = 128-key tiles; "small_m_variant" 0 = weight-streaming
- * kernel for token counts <= 64 (default), 1 = swapped-operand tcgen05 kernel with fused split-K;
+/* Tuning / A-B switches (integer options): "window_attn_variant" 0 = single-tile window kernel, one softmax thread per query
+ * row (default), 2 = the same with two threads per row, 1 = tiled kernel; "global_attn_variant" 0 = 64-key tiles, two softmax
+ * threads per query row, single-pass softmax, separate K / V rings, 2 CTAs/SM (default), 2 = round-1 kernel (one thread per
+ * row), 1 = 128-key tiles / 1 CTA per SM; "small_m_variant" 0 = weight-streaming kernel for token counts <= 64 (default),
+ * 1 = swapped-operand tcgen05 kernel with fused split-K;
  * "pdl" 1 = launch the LLaMA decode-chain kernels with programmatic dependent launch (prologues overlap the predecessor's
  * tail; every such kernel executes griddepcontrol.wait before reading its inputs);
  * "sm_limit" n > 0 = persistent token-major GEMMs launched through this handle use at most n CTAs (one per SM), leaving

@@ -38,6 +38,7 @@ struct SamAttnParams {
     int KH;            // key grid height (== query grid height)
     float scale_log2;  // head_dim^-0.5 * log2(e)
     const int* out_map;  // window kernel only, optional: output row of input row r (window_unpartition fused), -1 drops the row
+    int prefetch_ahead;  // window kernel: distance (in CTAs of the launch order) of the L2 prefetch, 0 = off
 };
 
 // K-major 32B-swizzled operand ([rows][16 bf16], rows 32 B apart, 8-row groups 256 B apart).
@@ -805,7 +806,11 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
             twp[i] = lo | (hi << 16);
         }
 
-        float m_ref = -INFINITY, l_run = 0.f;
+        // Single pass per tile: the scores are formed directly relative to the running reference m_ref (log2 domain), exponentiated
+        // at once, and the reference only moves when a tile's maximum exceeds it by more than 2^8 (then the tile's probabilities,
+        // the row sum and O are scaled by 2^-excess -- rare after the first tiles).  About 6.5 instructions per score element
+        // instead of 12: unpack rel_w, two FMAs, max, ex2, sum, half a pack.
+        float m_ref = 0.f, l_run = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
             const int sb = j & 1;
             mbar_wait(&s_full[sb], (j >> 1) & 1);
@@ -817,33 +822,33 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[sb]);
             const float rh = __bfloat162float(th_r[j * AT_BQ]);   // key row ky == j
+            const float cbase = fmaf(rh, AT_LOG2E, -m_ref);
             float mx = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float tw = __uint_as_float((i & 1) ? (twp[i >> 1] & 0xffff0000u) : (twp[i >> 1] << 16));
-                const float x = fmaf(__uint_as_float(xr[i]), p.scale_log2, (tw + rh) * AT_LOG2E);
-                xr[i] = __float_as_uint(x);
+                const float x = fmaf(__uint_as_float(xr[i]), p.scale_log2, fmaf(tw, AT_LOG2E, cbase));
                 mx = fmaxf(mx, x);
+                xr[i] = __float_as_uint(ex2_approx(x));
             }
-            // row maximum over both halves
+            // row maximum over both halves (relative to m_ref)
             float* mb = mxbuf + (j & 1) * 2 * AT_BQ;
             mb[half * AT_BQ + r] = mx;
             named_bar_sync(2 + quad, 64);
             mx = fmaxf(mx, mb[(half ^ 1) * AT_BQ + r]);
             float corr = 1.f;
-            bool moved = false;
-            if (j == 0) {
-                m_ref = mx;
-            } else if (mx > m_ref + 8.f) {
-                corr = ex2_approx(m_ref - mx);
-                m_ref = mx;
-                moved = true;
+            const bool moved = (j == 0) || (mx > 8.f);
+            if (moved) {
+                corr = ex2_approx(-mx);
+                m_ref += mx;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xr[i] = __float_as_uint(__uint_as_float(xr[i]) * corr);
             }
             float sum = 0.f;
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
-                const float p0 = ex2_approx(__uint_as_float(xr[c]) - m_ref), p1 = ex2_approx(__uint_as_float(xr[c + 1]) - m_ref);
+                const float p0 = __uint_as_float(xr[c]), p1 = __uint_as_float(xr[c + 1]);
                 sum += p0 + p1;
                 pk[c >> 1] = pack_bf16x2(p0, p1);
             }
@@ -998,6 +1003,24 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
             mbar_arrive_expect_tx(v_full, WN_KA + WN_KB);
             tma_load_2d(smem + WN_OFF_VA, &tmKVa, v_full, 2 * E + h * AT_HD, row_base);
             tma_load_2d(smem + WN_OFF_VB, &tmKVb, v_full, 2 * E + h * AT_HD + 64, row_base);
+            // Optional (option "attn_prefetch_ahead", off by default): pull the q / k / v tiles of a CTA further down the launch
+            // order into L2.  The kernel's top stalls are barrier waits behind its TMA loads and MMAs, but the experiment was
+            // neutral -- the latency that paces a CTA is the serial chain load -> T -> S -> softmax -> P V, not the DRAM access.
+            if (p.prefetch_ahead > 0) {
+                const long long lin = (long long)blockIdx.x + 2LL * (h + (long long)p.heads * b) + p.prefetch_ahead;
+                const int nb = (int)(lin / (2LL * p.heads)), nh = (int)((lin >> 1) % p.heads), nx = (int)(lin & 1);
+                if (nb < (int)gridDim.z) {
+                    const int nrow = nb * WN_S;
+                    tma_prefetch_2d_l2(&tmQa, nh * AT_HD, nrow + nx * AT_BQ);
+                    tma_prefetch_2d_l2(&tmQb, nh * AT_HD + 64, nrow + nx * AT_BQ);
+                    if (nx == 0) {   // both query tiles of a (window, head) read the same keys / values
+                        tma_prefetch_2d_l2(&tmKVa, E + nh * AT_HD, nrow);
+                        tma_prefetch_2d_l2(&tmKVb, E + nh * AT_HD + 64, nrow);
+                        tma_prefetch_2d_l2(&tmKVa, 2 * E + nh * AT_HD, nrow);
+                        tma_prefetch_2d_l2(&tmKVb, 2 * E + nh * AT_HD + 64, nrow);
+                    }
+                }
+            }
 
             const uint64_t dqa = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_QA));
             const uint64_t dqb = umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_QB));
@@ -1458,6 +1481,7 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
     p.KH = Hq;
     p.scale_log2 = (1.0f / sqrtf((float)hd)) * AT_LOG2E;
     p.out_map = out_row_map;
+    p.prefetch_ahead = h->attn_prefetch_ahead;
     IVLM_REQUIRE(out_row_map == nullptr || (Wq == 14 && h->window_attn_variant != 1),
                  "sam_attention: out_row_map is implemented by the 14x14 window kernel only");
     dim3 grid((S + AT_BQ - 1) / AT_BQ, heads, B);
@@ -1488,7 +1512,7 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
         IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_h, 2 * Hq - 1, hd, hd, 32, 16, 32, &whb));
         IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_w, 2 * Wq - 1, hd, hd, 32, 64, 128, &wwa));
         IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_w, 2 * Wq - 1, hd, hd, 32, 16, 32, &wwb));
-        if (h->window_attn_variant == 0)
+        if (h->window_attn_variant == 2)   // measured 201 vs 213 TFLOP/s: the window kernel waits on loads, not on its softmax warps
             sam_attn_window_h_kernel<<<grid, WNH_THREADS, WNH_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *wha, *whb, *wwa, *wwb, p);
         else
             sam_attn_window_tcgen05_kernel<<<grid, WN_THREADS, WN_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *wha, *whb, *wwa, *wwb, p);

@@ -204,6 +204,12 @@ IVLM_DEVINL void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "l"(policy)
         : "memory");
 }
+// Pulls the box at (c_inner, c_outer) into L2 without a shared-memory destination or a barrier.
+IVLM_DEVINL void tma_prefetch_2d_l2(const CUtensorMap* m, int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c_inner),
+                 "r"(c_outer)
+                 : "memory");
+}
 IVLM_DEVINL uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));

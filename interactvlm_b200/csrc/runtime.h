@@ -94,6 +94,8 @@ struct ivlm_ctx {
                                   // against 23 / 48 / 52, down_proj 40 / 57 / 62 against 56 / 136 / 130; tools/prof_decode.py variants)
     int small_m_variant = 0;      // 0: weight-streaming mma.sync kernel for token counts <= 64; 1: swapped-operand tcgen05 path
     int global_attn_variant = 0;  // 0: 64-key tiles, 2 CTAs/SM; 1: 128-key tiles, 1 CTA/SM (A/B switch)
+    int attn_prefetch_ahead = 0;  // window attention: L2 prefetch of the successor CTA's tiles, distance in CTAs of the launch order
+                                  // (0 = off, the default: measured neutral at 148 .. 1184 CTAs ahead, 0.366-0.379 ms per 16 views)
     int window_attn_variant = 0;  // 0: single-tile 2-CTA/SM window kernel, 1: the general tiled kernel (A/B switch)
     // TMA descriptor cache in two generations: lookups see both, inserts go to `tmaps`; when it holds IVLM_TMAP_GEN entries it
     // becomes `tmaps_old` (whose previous content is dropped).  A pointer handed out therefore stays valid for at least

@@ -38,8 +38,15 @@ for name, B, side in (("global_16views", 16, 64), ("window_16views", 400, 14)):
     if which in ("both", "new"):
         ms = timeit(lambda: ctx.sam_attention(qkv, rph, rpw, B, heads, side, side, hd))
         print(f"{name} fused tcgen05: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+        if side == 14:
+            for ahead in (0, 148, 296, 592, 1184):
+                ctx.set_option("attn_prefetch_ahead", ahead)
+                ms = timeit(lambda: ctx.sam_attention(qkv, rph, rpw, B, heads, side, side, hd))
+                print(f"{name} fused tcgen05, L2 prefetch {ahead} CTAs ahead: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+            ctx.set_option("attn_prefetch_ahead", -1)
         opt = "global_attn_variant" if side == 64 else "window_attn_variant"
-        for variant, label in ((2, "one thread per row (round-1 kernel)"), (1, "128-key tiles / 1 CTA per SM" if side == 64 else "tiled kernel")):
+        for variant, label in ((2, "one thread per row (round-1 kernel)" if side == 64 else "two threads per row"),
+                               (1, "128-key tiles / 1 CTA per SM" if side == 64 else "tiled kernel")):
             ctx.set_option(opt, variant)
             ms = timeit(lambda: ctx.sam_attention(qkv, rph, rpw, B, heads, side, side, hd))
             ctx.set_option(opt, 0)
