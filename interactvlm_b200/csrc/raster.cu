@@ -561,10 +561,17 @@ extern "C" int ivlm_soft_silhouette(ivlm_handle h, const float* verts, const int
     raster_bin_kernel<0><<<fgrid, 128, 0, stream>>>(proj, faces, n_verts, n_faces, dc, H, W, tiles_x, tiles_y, tile_cnt, nullptr,
                                                     nullptr, tile_cnt + n_tiles, pad);
     raster_scan_kernel<<<1, 1024, 0, stream>>>(tile_cnt, tile_off, n_tiles);
-    int total = 0;
-    IVLM_CHECK_CUDA(cudaMemcpyAsync(&total, tile_off + n_tiles, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    IVLM_CHECK_CUDA(cudaStreamSynchronize(stream));
-    IVLM_CHECK_CUDA(cudaMallocAsync(&tile_faces, sizeof(int) * (size_t)(total > 0 ? total : 1), stream));
+    // the per-tile face lists hold at most n_faces x n_tiles entries: when that bound is small (fit images are a few hundred
+    // pixels wide and objects a few thousand faces) it is allocated outright from the stream-ordered pool and the iteration
+    // has no host round trip; otherwise the exact total is read back first (one synchronisation)
+    size_t cap = (size_t)n_faces * (size_t)n_tiles;
+    if (cap > ((size_t)64 << 20)) {
+        int total = 0;
+        IVLM_CHECK_CUDA(cudaMemcpyAsync(&total, tile_off + n_tiles, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        IVLM_CHECK_CUDA(cudaStreamSynchronize(stream));
+        cap = (size_t)(total > 0 ? total : 1);
+    }
+    IVLM_CHECK_CUDA(cudaMallocAsync(&tile_faces, sizeof(int) * cap, stream));
     IVLM_CHECK_CUDA(cudaMemsetAsync(tile_cnt, 0, sizeof(int) * (size_t)n_tiles, stream));
     raster_bin_kernel<1><<<fgrid, 128, 0, stream>>>(proj, faces, n_verts, n_faces, dc, H, W, tiles_x, tiles_y, tile_cnt, tile_off,
                                                     tile_faces, tile_cnt + n_tiles, pad);

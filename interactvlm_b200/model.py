@@ -628,6 +628,12 @@ class _Predictor:
             names = ds_names if ds_names is not None else ["ocontact"] * B
             if "ocontact" not in names[0]:
                 return torch.zeros((1, 0), device=dev, dtype=torch.float32)  # components.py:430-431
+            if isinstance(lift2d_dict_path, (list, tuple)):
+                # batched extension: one lift2d_dict.pkl per sample -> list of [1, Nv_b] (objects differ in vertex count, which
+                # is why the reference insists on batch 1, components.py:433)
+                assert len(lift2d_dict_path) == B
+                return [self._from_pickle(pth)(seg_maps[b].float()[None].contiguous(), LIFT_OBJECT_MESH, 0.3)
+                        for b, pth in enumerate(lift2d_dict_path)]
             if B != 1:
                 raise AssertionError("Batch size should be 1 since different objects have different number of vertices")
             if lift2d_dict_path is not None:

@@ -252,19 +252,22 @@ class SSRenderer:
         self.faces_per_pixel = 100
         self.ctx = ctx
 
-    def render(self, vertices, **kwargs):
+    def render(self, vertices, want_depth=True, **kwargs):
+        """want_depth=False skips the depth normalisation (one host synchronisation) and returns depth None."""
         verts, faces = vertices, self.o_faces
         if kwargs.get("h_vertices") is not None:        # join_meshes_as_scene([o_mesh, h_mesh]) (renderer.py:48-61)
             verts = torch.cat([vertices, kwargs["h_vertices"]], 0)
             faces = torch.cat([self.o_faces, self.h_faces + vertices.shape[0]], 0)
         alpha, z = soft_silhouette(verts.float(), faces.to(torch.int32), self.cam, self.img_shape, self.sigma, self.blur_radius,
                                    self.faces_per_pixel, self.ctx)
+        image = torch.cat([torch.ones((*alpha.shape, 3), device=alpha.device), alpha[..., None]], -1)[None]
+        if not want_depth:
+            return image, None
         depth = z.clone()[None, ..., None]
         valid = depth != -1
         if bool(valid.any()):
             d = depth[valid]
             depth[valid] = (d - d.min()) / (d.max() - d.min())
-        image = torch.cat([torch.ones((*alpha.shape, 3), device=alpha.device), alpha[..., None]], -1)[None]
         return image, depth
 
 
@@ -296,11 +299,15 @@ def apply_transformation(vertices, rot6d, translation, scaling=1.0):
 
 def calculate_centroid(mask):
     """optim/utils.py:46-53: intensity-weighted (row, col) centroid of the non-zero pixels."""
-    coords = torch.nonzero(mask, as_tuple=False)
-    if coords.nelement() == 0:
-        return torch.tensor([mask.shape[0] / 2, mask.shape[1] / 2], device=mask.device)
-    weights = mask[coords[:, 0], coords[:, 1]]
-    return torch.sum(coords * weights.unsqueeze(1), dim=0) / torch.sum(weights)
+    # same value without materialising the non-zero coordinates (a data-dependent size = a host synchronisation): zero pixels
+    # carry zero weight, and an empty mask falls back to the image centre like the reference
+    H, W = mask.shape
+    rows = torch.arange(H, device=mask.device, dtype=mask.dtype)
+    cols = torch.arange(W, device=mask.device, dtype=mask.dtype)
+    tot = mask.sum()
+    c = torch.stack([(mask.sum(1) * rows).sum(), (mask.sum(0) * cols).sum()]) / torch.where(tot != 0, tot, torch.ones_like(tot))
+    centre = torch.tensor([H / 2, W / 2], device=mask.device, dtype=mask.dtype)
+    return torch.where(tot != 0, c, centre)
 
 
 def normalized_distance(point1, point2, img_shape):
@@ -347,9 +354,11 @@ class ObjPose_Opt(torch.nn.Module):
         """optimizer.py:171-174 (the 'union' is the plain sum of both masks, as in the reference)."""
         return 1 - torch.sum(current_mask * self.target_mask) / torch.sum(current_mask + self.target_mask)
 
-    def forward(self, loss_weights: dict):
+    def forward(self, loss_weights: dict, log: bool = True):
+        """log=False leaves out what only the reference's progress bar / tensorboard read (loss floats, centroid distance,
+        normalised depth): the iteration then runs without a host synchronisation."""
         obj_vertices = apply_transformation(self.obj_vertices, self.rotation, self.translation, self.scale)
-        sil_img, depth_img = self.silhouette_renderer.render(obj_vertices + self.hum_centroid_offset, h_vertices=None)
+        sil_img, depth_img = self.silhouette_renderer.render(obj_vertices + self.hum_centroid_offset, h_vertices=None, want_depth=log)
         current_mask = sil_img[0, ..., 3]
         active = lambda k: k in loss_weights and self.step >= loss_weights[k]["kick_in"]
         loss_dict = {}
@@ -363,6 +372,8 @@ class ObjPose_Opt(torch.nn.Module):
         weighted = {k: v * loss_weights[k]["w"] for k, v in loss_dict.items() if loss_weights[k]["kick_in"] >= 0}
         total = sum(weighted.values())
         self.step += 1
+        if not log:
+            return total, {"object_vertices": obj_vertices.detach(), "current_mask": current_mask}
         output = {"object_vertices": obj_vertices.detach(), "current_mask": current_mask, "current_depth": depth_img[0, ..., 0],
                   "current_mask_centroid": current_mask_centroid,
                   "centroid_distance": normalized_distance(current_mask_centroid, self.target_mask_centroid, self.target_mask.shape),
@@ -371,14 +382,22 @@ class ObjPose_Opt(torch.nn.Module):
 
 
 def fit(model: ObjPose_Opt, loss_weights: dict, max_iter: int = 250, lr_rotation: float = 5.0e-2, lr_translation: float = 1.0e-2,
-        lr_scale: float = 1.0e-2, early_stop: bool = False):
+        lr_scale: float = 1.0e-2, early_stop: bool = False, record: bool = True):
     """The Adam loop of optim/fit.py:216-290 (per-parameter learning rates of :218-224, optional early stop of :279-283).
-    -> list of per-iteration dicts (loss, weighted terms, centroid distance)."""
+    -> list of per-iteration dicts (loss, weighted terms, centroid distance); record=False (no early stop) runs the loop
+    without reading anything back and returns an empty list."""
     groups = [{"params": [model.rotation], "lr": lr_rotation}, {"params": [model.translation], "lr": lr_translation}]
     if isinstance(model.scale, torch.nn.Parameter):
         groups.append({"params": [model.scale], "lr": lr_scale})
     optimizer = torch.optim.Adam(groups)
     history, prev = [], 1e10
+    if not record and not early_stop:
+        for _ in range(max_iter):
+            optimizer.zero_grad()
+            loss, _ = model(loss_weights, log=False)
+            loss.backward()
+            optimizer.step()
+        return history
     for _ in range(max_iter):
         optimizer.zero_grad()
         loss, out = model(loss_weights)

@@ -55,3 +55,13 @@ def test_bench_tiny_oafford_and_sweep_one_gpu():
     rows = [json.loads(l) for l in r.stdout.strip().splitlines() if l.startswith("{")]
     assert [x["config"]["batch_per_gpu"] for x in rows] == [1, 4] and all(x["value"] > 0 for x in rows)
     assert all("oafford_pc" in x["metric"] for x in rows)
+
+
+def test_bench_tiny_joint_fit_one_gpu():
+    env = dict(os.environ, IVLM_FIT_ITERS="12")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--config", "tiny", "--steps", "1", "--warmup", "1", "--batch", "2",
+                        "--workload", "joint_fit"], capture_output=True, text=True, timeout=900, cwd=str(ROOT), env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = _line(r.stdout)
+    assert d["unit"] == "samples/s" and d["value"] > 0 and d["e2e"]["value"] > 0 and d["config"]["fit_iterations"] == 12
+    assert d["gpu_launches"] > 200 and d["fit_ms_per_iteration"] > 0
