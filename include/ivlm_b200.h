@@ -335,6 +335,12 @@ typedef struct ivlm_raster_cam {
 IVLM_API int ivlm_rasterize_mesh(ivlm_handle h, const float* verts, const int32_t* faces, int32_t n_verts, int32_t n_faces,
                         const ivlm_raster_cam* cams_h, int32_t V, int32_t H, int32_t W, int32_t* pix_to_face, float* bary,
                         float* zbuf, int64_t* p2v, int32_t* n_skipped_h, void* stream);
+/* pytorch3d PointsRasterizer as preprocess_data/utils_obj_pc.py:28-42,88-113 uses it for the LEMON / PIAD point clouds
+ * (`num_point2pixel == 1`): points [n,3] fp32 (device) -> pixel_to_point map p2p [V,H,W] int64 = index of the point nearest in
+ * depth among those within `radius` (NDC units) of the pixel centre, -1 where there is none.  Same NDC / pixel-centre
+ * conventions as ivlm_rasterize_mesh; equal depths resolve to the lower index.  One-time preprocessing (stream-ordered scratch). */
+IVLM_API int ivlm_rasterize_points(ivlm_handle h, const float* points, int32_t n_points, const ivlm_raster_cam* cams_h, int32_t V,
+                          int32_t H, int32_t W, float radius, int64_t* p2p, void* stream);
 /* HardPhongShader with one point light per view (lights_h [V,3] host) and default materials over the rasteriser output:
  * rgb [V,H,W,3] uint8 = trunc(255 * ((ambient + diffuse * max(n.l,0)) * colour + specular * max(v.r,0)^shininess)),
  * white background (render_mesh_utils.py:177-198).  colors [Nv,3] fp32 vertex colours (TexturesVertex). */

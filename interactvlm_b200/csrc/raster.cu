@@ -538,6 +538,69 @@ extern "C" int ivlm_shade_phong(ivlm_handle h, const float* verts, const int32_t
     return IVLM_OK;
 }
 
+namespace ivlm {
+// ------------------------------------------------------------------------------------------------ point-cloud rasteriser
+// pytorch3d PointsRasterizer as preprocess_data/utils_obj_pc.py:88-113 reads it (`num_point2pixel == 1`): a pixel takes the
+// point nearest in depth among those whose NDC distance to the pixel centre is below `radius` (z >= 0).  Every point splats
+// a packed (depth bits, index) key into the pixels of its disc with atomicMin: positive floats order like their bit
+// patterns, ties in depth go to the lower index -- deterministic whatever the execution order.
+__global__ void points_splat_kernel(const float4* __restrict__ proj, int n_points, int H, int W, float radius,
+                                    unsigned long long* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (i >= n_points) return;
+    const float4 p = proj[(size_t)v * n_points + i];
+    if (!(p.z >= 0.f)) return;
+    const float rx = ndc_half_range(W, H), ry = ndc_half_range(H, W);
+    if (!(p.x + radius >= -rx && p.x - radius <= rx && p.y + radius >= -ry && p.y - radius <= ry)) return;
+    const float fw = 0.5f * W / rx, fh = 0.5f * H / ry;
+    const int j0 = (int)fmaxf(floorf((rx - fminf(p.x + radius, rx)) * fw - 0.5f) - 1.f, 0.f);
+    const int j1 = (int)fminf(ceilf((rx - fmaxf(p.x - radius, -rx)) * fw - 0.5f) + 1.f, (float)(W - 1));
+    const int i0 = (int)fmaxf(floorf((ry - fminf(p.y + radius, ry)) * fh - 0.5f) - 1.f, 0.f);
+    const int i1 = (int)fminf(ceilf((ry - fmaxf(p.y - radius, -ry)) * fh - 0.5f) + 1.f, (float)(H - 1));
+    const float r2 = mul(radius, radius);
+    const unsigned long long key = ((unsigned long long)__float_as_uint(p.z) << 32) | (unsigned int)i;
+    for (int y = i0; y <= i1; ++y) {
+        const float dy = sub(pix_to_ndc(y, H, W), p.y);
+        for (int x = j0; x <= j1; ++x) {
+            const float dx = sub(pix_to_ndc(x, W, H), p.x);
+            if (add(mul(dx, dx), mul(dy, dy)) < r2) atomicMin(keys + ((size_t)v * H + y) * W + x, key);
+        }
+    }
+}
+__global__ void points_resolve_kernel(const unsigned long long* __restrict__ keys, long long n, long long* __restrict__ p2p) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        p2p[i] = k == ~0ull ? -1 : (long long)(k & 0xffffffffull);
+    }
+}
+}  // namespace ivlm
+
+extern "C" int ivlm_rasterize_points(ivlm_handle h, const float* points, int32_t n_points, const ivlm_raster_cam* cams_h, int32_t V,
+                                     int32_t H, int32_t W, float radius, int64_t* p2p, void* stream_) {
+    using namespace ivlm;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    IVLM_REQUIRE(h && points && cams_h && p2p && n_points > 0 && V >= 1 && V <= IVLM_RASTER_MAX_VIEWS && H > 0 && W > 0 && radius > 0.f,
+                 "rasterize_points: bad arguments (%d points, %d views, %dx%d, radius %g)", n_points, V, H, W, radius);
+    DevCams dc{};
+    IVLM_TRY(load_cams(cams_h, V, dc));
+    float4* proj = nullptr;
+    unsigned long long* keys = nullptr;
+    const size_t npix = (size_t)V * H * W;
+    IVLM_CHECK_CUDA(cudaMallocAsync(&proj, sizeof(float4) * (size_t)V * n_points, stream));
+    IVLM_CHECK_CUDA(cudaMallocAsync(&keys, sizeof(unsigned long long) * npix, stream));
+    IVLM_CHECK_CUDA(cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * npix, stream));
+    raster_project_kernel<<<dim3((n_points + 255) / 256, V), 256, 0, stream>>>(points, n_points, dc, V, proj);
+    points_splat_kernel<<<dim3((n_points + 127) / 128, V), 128, 0, stream>>>(proj, n_points, H, W, radius, keys);
+    points_resolve_kernel<<<(unsigned)std::min<size_t>((npix + 255) / 256, 148 * 16), 256, 0, stream>>>(keys, (long long)npix,
+                                                                                                      reinterpret_cast<long long*>(p2p));
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    h->launches += 3;
+    IVLM_CHECK_CUDA(cudaFreeAsync(keys, stream));
+    IVLM_CHECK_CUDA(cudaFreeAsync(proj, stream));
+    return IVLM_OK;
+}
+
 extern "C" int ivlm_soft_silhouette(ivlm_handle h, const float* verts, const int32_t* faces, int32_t n_verts, int32_t n_faces,
                                     const ivlm_raster_cam* cam_h, int32_t H, int32_t W, float sigma, float blur_radius, int32_t K,
                                     float* alpha, float* zbuf0, int32_t* n_frag, int32_t* frag_face, float* frag_sd, float* frag_z,

@@ -535,6 +535,17 @@ def rasterize_mesh(ctx: Context, verts, faces, cams, H, W, want_p2v=True, want_z
     return dict(pix_to_face=pix, bary=bary, zbuf=zbuf, p2v=p2v, skipped=int(skipped.value))
 
 
+def rasterize_points(ctx: Context, points, cams, H, W, radius):
+    """points [n,3] fp32 CUDA -> pixel_to_point [V,H,W] int64 (-1 background): nearest point in depth within `radius` (NDC) of
+    each pixel centre (ivlm_rasterize_points)."""
+    assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.dim() == 2 and points.shape[1] == 3
+    V = len(cams)
+    p2p = torch.empty((V, H, W), device=points.device, dtype=torch.int64)
+    L.check(ctx.lib.ivlm_rasterize_points(ctx.h, P(points), i32(points.shape[0]), _cam_array(cams), i32(V), i32(H), i32(W),
+                                          f32c(float(radius)), P(p2p), ctx.stream), "rasterize_points")
+    return p2p
+
+
 def shade_phong(ctx: Context, verts, faces, colors, cams, lights, pix_to_face, bary, ambient=0.5, diffuse=0.3, specular=0.2,
                 shininess=64.0):
     """HardPhongShader over the rasteriser output -> uint8 [V,H,W,3] (white background)."""

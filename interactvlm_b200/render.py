@@ -175,3 +175,38 @@ def generate_sam_inp_objs(obj_mesh_f, image_size=RENDER_IMG_SIZE, device=0):
                  "bary_coords_map": [bary[k] for k in range(len(names))],
                  "num_vertices": int(vertices.shape[0])}, out_dir / "lift2d_dict.pkl")
     return out_dir
+
+
+# ------------------------------------------------------------------------------------------------ point clouds (LEMON / PIAD)
+def point_camera(camera_params, fov=60.0, znear=1.0):
+    """get_rasterizer of preprocess_data/utils_obj_pc.py:28-32: like `camera`, but only the y translation is applied."""
+    dist, elev, azim, _x_trans, y_trans = [float(c) for c in camera_params]
+    return camera((dist, elev, azim, 0.0, y_trans), fov, znear)
+
+
+def get_dynamic_radius(points):
+    """utils_obj_pc.py:18-26: 0.004 x the bounding-box diagonal of the cloud."""
+    p = np.asarray(points.detach().cpu() if torch.is_tensor(points) else points, dtype=np.float32).reshape(-1, 3)
+    return float(0.004 * np.linalg.norm(p.max(0) - p.min(0)))
+
+
+def project_points_to_image(points, camera_params, dynamic_radius=True, fixed_radius=0.005, image_size=(512, 512), num_point2pixel=1,
+                            device=0, ctx=None):
+    """utils_obj_pc.py:88-113 for `num_point2pixel == 1` -> pixel_to_point_map int64 [H,W] (-1 background), the `mapping` array
+    of the `p2pmap_*.npz` files ObjectPCAfford3DPredictor reads (components.py:309)."""
+    if num_point2pixel != 1:
+        raise NotImplementedError("only the single-point-per-pixel maps the released pipeline writes (num_point2pixel=1)")
+    ctx = ctx or _ctx(device)
+    pts = torch.as_tensor(points, dtype=torch.float32).to(ctx.device).reshape(-1, 3).contiguous()
+    radius = get_dynamic_radius(pts) if dynamic_radius else fixed_radius
+    p2p = ops.rasterize_points(ctx, pts, [point_camera(camera_params)], int(image_size[0]), int(image_size[1]), radius)
+    return p2p[0].cpu().numpy()
+
+
+def create_affordance_mask(points, afford_indices, camera_params, dynamic_radius=True, fixed_radius=0.005, image_size=(512, 512),
+                           device=0, ctx=None):
+    """utils_obj_pc.py:115-137 (single point per pixel): 255 where the visible point carries the affordance."""
+    p2p = project_points_to_image(points, camera_params, dynamic_radius, fixed_radius, image_size, 1, device, ctx)
+    mask = np.zeros(tuple(image_size), np.uint8)
+    mask[np.isin(p2p, list(set(int(i) for i in np.asarray(afford_indices).reshape(-1))))] = 255
+    return mask, p2p

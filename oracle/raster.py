@@ -311,3 +311,26 @@ def soft_silhouette(verts, faces, cam, H, W, sigma=1e-4, blur_radius=None, K=100
     g_view[:, 1] = g_ndc[:, 1] * fy / z
     g_view[:, 2] = -(g_ndc[:, 0] * fx * view[:, 0] + g_ndc[:, 1] * fy * view[:, 1]) / (z * z)
     return alpha, zbuf0, g_view @ R.T
+
+
+def rasterize_points(points, cam, H, W, radius):
+    """pytorch3d PointsRasterizer as utils_obj_pc.py:88-113 reads it (num_point2pixel == 1) -> pixel_to_point int64 [H,W]
+    (-1 background): per pixel the point nearest in depth with (x_pix - x)^2 + (y_pix - y)^2 < radius^2 and z >= 0, equal
+    depths to the lower index.  float32 with the operation order of the CUDA kernel.  Parity unpinned like the rest of this
+    file (pytorch3d absent): conventions as documented for ivlm_rasterize_mesh."""
+    pr = project(points, cam)
+    xs, ys = pixel_ndc(W, H), pixel_ndc(H, W)
+    best_z = np.full((H, W), np.inf, dtype=F)
+    best_i = np.full((H, W), -1, dtype=np.int64)
+    r2 = F(radius) * F(radius)
+    for i in range(pr.shape[0]):
+        x, y, z = pr[i]
+        if not z >= 0:
+            continue
+        dx = (xs - x).astype(F)
+        dy = (ys - y).astype(F)
+        d2 = (dx * dx)[None, :] + (dy * dy)[:, None]
+        hit = (d2 < r2) & (z < best_z)          # ascending index order: a later point only wins with a strictly smaller depth
+        best_z[hit] = z
+        best_i[hit] = i
+    return best_i

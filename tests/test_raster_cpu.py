@@ -209,3 +209,19 @@ def test_phong_oracle_analytic_pixel():
     assert (back[32, 32] == int(0.5 * 0.5 * 255)).all()                           # 63
     n = O.vertex_normals(v, np.array([[0, 1, 2]]))
     assert np.allclose(n, [[0, 0, 1]] * 3, atol=1e-6)
+
+
+def test_point_rasteriser_oracle_picks_the_nearest_point_in_its_disc():
+    from oracle import raster as O
+
+    cam = O.camera((2.0, 0.0, 0.0, 0.0, 0.0))
+    pts = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 0.5], [0.3, 0.2, 0.0]], np.float32)   # the second point is nearer to the camera at z = 2
+    m = O.rasterize_points(pts, cam, 64, 64, 0.05)
+    pr = O.project(pts, cam)
+    assert pr[1, 2] < pr[0, 2]
+    centre = m[31:33, 31:33]
+    assert np.all(centre == 1)                     # same pixel, smaller depth wins
+    assert (m == 2).sum() > 0 and (m == 0).sum() >= 0 and (m >= 0).sum() < 64 * 64 * 0.05
+    xs = O.pixel_ndc(64, 64)
+    yy, xx = np.nonzero(m == 2)
+    assert np.all((xs[xx] - pr[2, 0]) ** 2 + (xs[yy] - pr[2, 1]) ** 2 < 0.05 ** 2)
