@@ -14,6 +14,7 @@
  */
 #ifndef IVLM_B200_H
 #define IVLM_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -51,6 +52,75 @@ IVLM_API int ivlm_set_workspace(ivlm_handle h, void* ptr, size_t bytes, void* st
 IVLM_API int ivlm_set_option(ivlm_handle h, const char* name, int32_t value);
 /* kernels launched through this handle so far (bench.py's "gpu_launches") */
 IVLM_API uint64_t ivlm_launch_count(ivlm_handle h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage-level entry points (csrc/stages.cu): bind the checkpoint tensors once, then one call per stage.  What a reference
+ * maintainer would bind instead of the Python-level loops of InteractVLMForCausalLM: `get_visual_embs` ->
+ * ImageEncoderViT.forward (InteractVLM.py:251-261, image_encoder.py:110-125), `LlavaLlamaForCausalLM.forward` over the prompt
+ * (llava_llama.py:55-135) and one greedy-search step (transformers generation/utils.py as driven by InteractVLM.py:524-531).
+ * Each driver is the fixed launch sequence of the op-level entry points below (bit-identical results); activations live in a
+ * caller-provided arena; every launch goes to `stream`; nothing synchronises or allocates. */
+typedef struct ivlm_weight_desc {
+    const char* name;   /* "sam.w_patch", "sam.blocks.7.wqkv", "llm.3.wgu", "llm.lm_head", ... (interactvlm_b200/model.py lists them) */
+    const void* ptr;    /* device pointer, borrowed: the caller keeps the tensor alive */
+    int32_t dtype;      /* ivlm_dtype */
+    int32_t ndim;
+    int64_t shape[4];
+} ivlm_weight_desc;
+IVLM_API int ivlm_bind_weights(ivlm_handle h, const ivlm_weight_desc* descs, int32_t n);
+typedef struct ivlm_model_dims {
+    int32_t sam_img, sam_patch, sam_embed_dim, sam_depth, sam_heads, sam_window, sam_out_chans;
+    uint32_t sam_global_mask;      /* bit i set: block i uses global attention (build_sam.py global_attn_indexes) */
+    int32_t llm_hidden, llm_intermediate, llm_layers, llm_heads, llm_head_dim, llm_vocab;
+    float llm_rms_eps;
+    int32_t llm_paired_layout;     /* 1: q/k rows paired and gate/up rows interleaved (interactvlm_b200/layout.py) */
+} ivlm_model_dims;
+IVLM_API int ivlm_set_model_dims(ivlm_handle h, const ivlm_model_dims* dims);
+/* SAM ViT encoder on N views: images [N,3,S,S] bf16 -> emb [N, (S/patch)^2, out_chans] bf16 (token-major, the layout the mask
+ * decoder reads).  win_map [N*nw*nw*ws*ws]: window-major row -> token row or -1 (window_partition with zero padding,
+ * image_encoder.py:263-288); win_inv [N*(S/patch)^2]: its inverse; win_pads [n_pads]: the window-major rows that are padding. */
+typedef struct ivlm_sam_encode_args {
+    const void* images;
+    void* emb;
+    int32_t N;
+    const int32_t* win_map;
+    const int32_t* win_inv;
+    const int32_t* win_pads;
+    int32_t n_pads;
+    void* arena;
+    size_t arena_bytes;
+} ivlm_sam_encode_args;
+IVLM_API size_t ivlm_sam_encode_arena_bytes(ivlm_handle h, int32_t N);
+IVLM_API int ivlm_sam_encode(ivlm_handle h, const ivlm_sam_encode_args* args, void* stream);
+/* LLaMA prefill over B sequences of S embedded rows (right-padded): K/V pages, normed hidden states, greedy next token. */
+typedef struct ivlm_llm_prefill_args {
+    const void* embeds;         /* [B*S, D] bf16 */
+    const int32_t* positions;   /* [B*S] */
+    const int32_t* slot_map;    /* [B*S] cache slot of every row */
+    void* const* k_cache;       /* HOST array of n_layers device pointers, each [pages, H, page_size, hd] bf16 */
+    void* const* v_cache;
+    void* hidden;               /* [B, max_len, D] bf16: rows [0,S) of every sequence are written */
+    int32_t* next_tok;          /* [B] */
+    const int32_t* last_rows;   /* [B] flat row b*S + S_b - 1 of every sequence's last valid row, or NULL (row S-1) */
+    int32_t B, S, max_len, page_size;
+    void* arena;
+    size_t arena_bytes;
+} ivlm_llm_prefill_args;
+IVLM_API size_t ivlm_llm_arena_bytes(ivlm_handle h, int32_t tokens);
+IVLM_API int ivlm_llm_prefill(ivlm_handle h, const ivlm_llm_prefill_args* args, void* stream);
+/* One decode step for B <= 8 sequences (the launch sequence a CUDA graph captures): bookkeeping buffers as ivlm_decode_prepare /
+ * ivlm_decode_finish take them. */
+typedef struct ivlm_llm_decode_args {
+    int32_t* state; int32_t S; const int32_t* S_rows; const int32_t* scripted; int32_t G;
+    int32_t* next; int32_t* done; int32_t* out_tokens; int32_t* tok; int32_t* pos; int32_t* slot; int32_t* seq_lens;
+    const int32_t* slot_base; int32_t eos, pad, B;
+    void* const* k_cache; void* const* v_cache;   /* HOST arrays of n_layers device pointers */
+    const int32_t* block_table; int32_t max_pages, page_size;
+    void* hidden; int32_t max_len;                /* [B, max_len, D] */
+    void* hid_step;                               /* [B, D] */
+    void* arena; size_t arena_bytes;              /* ivlm_llm_arena_bytes(h, B) */
+} ivlm_llm_decode_args;
+IVLM_API int ivlm_llm_decode_step(ivlm_handle h, const ivlm_llm_decode_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contraction (tcgen05 / TMEM / TMA).  Replaces every nn.Linear / 1x1-or-patch Conv2d call on

@@ -26,6 +26,13 @@ extern "C" int ivlm_create(ivlm_handle* out, int device) {
     IVLM_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
     IVLM_REQUIRE(prop.major == 10, "ivlm_create: device %d is sm_%d%d; this library is built for sm_100a only",
                  device, prop.major, prop.minor);
+    // the preprocessing / pose-refinement entry points take scratch from the stream-ordered allocator: keep what it has obtained
+    // instead of handing it back to the driver at every synchronisation (the default release threshold is 0)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     ivlm_ctx* h = new ivlm_ctx();
     h->device = device;
     h->num_sms = prop.multiProcessorCount;

@@ -14,7 +14,7 @@
 struct ivlm_lift_map {
     int V = 0, H = 0, W = 0, n = 0;
     long long nnz = 0;
-    int* row_ptr = nullptr;  // device [V*n + 1]
+    int* row_ptr = nullptr;  // device [n*V + 1], vertex-major: row = vertex * V + view
     int* pix = nullptr;      // device [nnz] pixel index inside the view
     float* wgt = nullptr;    // device [nnz] barycentric weight (nullptr => unit weights)
 };
@@ -29,13 +29,16 @@ struct ivlm_csr {
 
 namespace ivlm {
 
-// One CTA per (vertex, chunk of LIFT_BC samples): warp w takes views w, w + LIFT_WARPS, ...; its lanes stride the CSR
-// segment of (view, vertex) -- coalesced 128-byte loads of pix / wgt, each entry loaded ONCE and applied to all samples of
-// the chunk -- and the per-lane partial sums are folded with a shuffle tree (deterministic: the grouping depends only on the
-// map).  Views are combined through shared memory in view order, like the reference's loop over views
-// (components.py:235-262).  LOWRES: `src` holds the mask decoder's low-res logits [B,V,sh,sw] and the x(H/sh) bilinear of
-// Sam.postprocess_masks (sam.py:161-165) is evaluated per entry with the arithmetic of bilinear_kernel (bit-identical to
-// lifting the materialised 1024^2 logits, which are then never read: 1.05 MB instead of 16.8 MB per sample).
+// One CTA (4 warps) per (vertex, chunk of BC samples).  The CSR is VERTEX-major (row = vertex * V + view), so the V segments of
+// a vertex are adjacent; the CTA walks them view by view with ALL 128 threads striding a segment -- coalesced loads of pix /
+// wgt, each entry loaded ONCE and applied to all samples of the chunk -- which keeps the four warps equally busy whatever the
+// split of a vertex's pixels over the views (one warp per view left three warps idle behind the longest segment: 6890 blocks
+// in 9 waves paced by their slowest warp).  Per-thread partial sums (registers, one set per view) are folded with shuffles and
+// then across the warps in warp order: deterministic, the grouping depends only on the map.  Views are combined in view
+// order like the reference's loop (components.py:235-262).  LOWRES: `src` holds the mask decoder's low-res logits
+// [B,V,sh,sw] and the x(H/sh) bilinear of Sam.postprocess_masks (sam.py:161-165) is evaluated per entry with the arithmetic
+// of bilinear_kernel (bit-identical to lifting the materialised 1024^2 logits, which are then never read: 1.05 MB instead of
+// 16.8 MB per sample).
 constexpr int LIFT_BC = 8, LIFT_WARPS = 4, LIFT_MAX_VIEWS = 8;
 
 template <int MODE, bool LOWRES, int BC>
@@ -46,11 +49,14 @@ lift_warp_kernel(const int* __restrict__ row_ptr, const int* __restrict__ pix, c
     const int vtx = blockIdx.x, b0 = blockIdx.y * BC;
     const int nb = min(BC, B - b0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ float s_votes[LIFT_MAX_VIEWS][BC], s_cnt[LIFT_MAX_VIEWS][BC];
+    __shared__ float s_votes[LIFT_MAX_VIEWS][LIFT_WARPS][BC], s_cnt[LIFT_MAX_VIEWS][LIFT_WARPS][BC];
+    __shared__ int s_rp[LIFT_MAX_VIEWS + 1];
+    if ((int)threadIdx.x <= V) s_rp[threadIdx.x] = row_ptr[(long long)vtx * V + threadIdx.x];
+    __syncthreads();
     const long long plane = LOWRES ? (long long)sh * sw : (long long)H * W;
     const float sy = (float)sh / (float)H, sx = (float)sw / (float)W;
-    for (int v = warp; v < V; v += LIFT_WARPS) {
-        const int e0 = row_ptr[v * n + vtx], e1 = row_ptr[v * n + vtx + 1];
+    for (int v = 0; v < V; ++v) {
+        const int e0 = s_rp[v], e1 = s_rp[v + 1];
         float votes[BC], cnt[BC];
 #pragma unroll
         for (int s = 0; s < BC; ++s) votes[s] = cnt[s] = 0.f;
@@ -59,7 +65,7 @@ lift_warp_kernel(const int* __restrict__ row_ptr, const int* __restrict__ pix, c
         const float* ms[BC];
 #pragma unroll
         for (int s = 0; s < BC; ++s) ms[s] = src + ((long long)(b0 + min(s, nb - 1)) * V + v) * plane;
-        for (int e = e0 + lane; e < e1; e += 32) {
+        for (int e = e0 + (int)threadIdx.x; e < e1; e += LIFT_WARPS * 32) {
             const int p = __ldg(pix + e);
             const float w = (MODE == IVLM_LIFT_POINTS) ? 1.f : __ldg(wgt + e);
             float x[BC];
@@ -95,14 +101,19 @@ lift_warp_kernel(const int* __restrict__ row_ptr, const int* __restrict__ pix, c
                 }
             }
         }
-        if (MODE != IVLM_LIFT_OBJECT_MESH) cnt[0] = warp_sum(cnt[0]);
+        if (e1 - e0 > 0) {   // CTA-uniform: empty segments skip the shuffles
+            if (MODE != IVLM_LIFT_OBJECT_MESH) cnt[0] = warp_sum(cnt[0]);
 #pragma unroll
-        for (int s = 0; s < BC; ++s) {
-            votes[s] = warp_sum(votes[s]);
-            if (MODE == IVLM_LIFT_OBJECT_MESH) cnt[s] = warp_sum(cnt[s]);
-            if (lane == 0) {
-                s_votes[v][s] = votes[s];
-                s_cnt[v][s] = (MODE == IVLM_LIFT_OBJECT_MESH) ? cnt[s] : cnt[0];
+            for (int s = 0; s < BC; ++s) {
+                votes[s] = warp_sum(votes[s]);
+                if (MODE == IVLM_LIFT_OBJECT_MESH) cnt[s] = warp_sum(cnt[s]);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < BC; ++s) {
+                s_votes[v][warp][s] = votes[s];
+                s_cnt[v][warp][s] = (MODE == IVLM_LIFT_OBJECT_MESH) ? cnt[s] : cnt[0];
             }
         }
     }
@@ -111,7 +122,9 @@ lift_warp_kernel(const int* __restrict__ row_ptr, const int* __restrict__ pix, c
         const int s = threadIdx.x;
         float pred = 0.f, nviews = 0.f;
         for (int v = 0; v < V; ++v) {
-            const float c = s_cnt[v][s], vt = s_votes[v][s];
+            float c = 0.f, vt = 0.f;
+#pragma unroll
+            for (int w = 0; w < LIFT_WARPS; ++w) { c += s_cnt[v][w][s]; vt += s_votes[v][w][s]; }
             // votes are normalised only where the weight sum is positive; the rest is added as is (components.py:257-262)
             pred += (c > 0.f) ? vt / c : vt;
             nviews += (c > 0.f) ? 1.f : 0.f;
@@ -189,13 +202,14 @@ extern "C" int ivlm_lift_build_mesh(ivlm_handle h, const int64_t* p2v, const flo
     const long long hw = (long long)H * W;
     std::vector<int> row_ptr((size_t)V * n + 1, 0);
     // pass 1: counts (a pixel votes only if all three ids are valid, components.py:241-245)
+    // rows are vertex-major: row = vertex * V + view (the V segments of a vertex are adjacent)
     for (int v = 0; v < V; ++v) {
         const int64_t* pv = p2v + (long long)v * hw * 3;
-        int* cnt = row_ptr.data() + (size_t)v * n + 1;
+        int* cnt = row_ptr.data() + 1 + v;
         for (long long i = 0; i < hw; ++i) {
             const int64_t a = pv[i * 3], b = pv[i * 3 + 1], c = pv[i * 3 + 2];
             if (a < 0 || a >= n || b < 0 || b >= n || c < 0 || c >= n) continue;
-            cnt[a]++; cnt[b]++; cnt[c]++;
+            cnt[a * V]++; cnt[b * V]++; cnt[c * V]++;
         }
     }
     IVLM_TRY(prefix_sum_checked(row_ptr, "lift_build_mesh"));
@@ -207,13 +221,13 @@ extern "C" int ivlm_lift_build_mesh(ivlm_handle h, const int64_t* p2v, const flo
     for (int v = 0; v < V; ++v) {
         const int64_t* pv = p2v + (long long)v * hw * 3;
         const float* bw = bary + (long long)v * hw * 3;
-        int* c = cur.data() + (size_t)v * n;
+        int* c = cur.data() + v;
         for (int k = 0; k < 3; ++k) {
             for (long long i = 0; i < hw; ++i) {
                 const int64_t a = pv[i * 3], b = pv[i * 3 + 1], d = pv[i * 3 + 2];
                 if (a < 0 || a >= n || b < 0 || b >= n || d < 0 || d >= n) continue;
                 const int64_t vid = pv[i * 3 + k];
-                const int e = c[vid]++;
+                const int e = c[vid * V]++;
                 pix[e] = (int)i;
                 wgt[e] = bw[i * 3 + k];
             }
@@ -241,7 +255,7 @@ extern "C" int ivlm_lift_build_points(ivlm_handle h, const int64_t* p2p, int32_t
             const int64_t a = p2p[(long long)v * hw + i];
             if (a == -1) continue;  // components.py:327 `pixel_to_point_map != -1`
             IVLM_REQUIRE(a >= 0 && a < n, "lift_build_points: point id %lld out of range [0,%d)", (long long)a, n);
-            row_ptr[(size_t)v * n + 1 + a]++;
+            row_ptr[(size_t)a * V + v + 1]++;
         }
     IVLM_TRY(prefix_sum_checked(row_ptr, "lift_build_points"));
     const long long nnz = row_ptr.back();
@@ -251,7 +265,7 @@ extern "C" int ivlm_lift_build_points(ivlm_handle h, const int64_t* p2p, int32_t
         for (long long i = 0; i < hw; ++i) {
             const int64_t a = p2p[(long long)v * hw + i];
             if (a == -1) continue;
-            pix[cur[(size_t)v * n + a]++] = (int)i;
+            pix[cur[(size_t)a * V + v]++] = (int)i;
         }
     IVLM_CHECK_CUDA(cudaSetDevice(h->device));
     ivlm_lift_map* m = new ivlm_lift_map();

@@ -103,7 +103,9 @@ struct ivlm_ctx {
     // grow the cache without bound.  (unordered_map never moves its nodes on insert.)
     std::unordered_map<ivlm::TmapKey, CUtensorMap, ivlm::TmapKeyHash> tmaps, tmaps_old;
     uint64_t attr_done = 0;       // bit i: cudaFuncSetAttribute done on this handle's device for kernel variant i (per handle = per device)
-    std::unordered_map<std::string, ivlm::Weight> weights;
+    std::unordered_map<std::string, ivlm::Weight> weights;   // ivlm_bind_weights: borrowed device pointers by name
+    ivlm_model_dims dims = {};                               // ivlm_set_model_dims
+    int dims_set = 0;
     // caller-provided scratch (bump allocated inside stage drivers)
     char* ws = nullptr;
     size_t ws_bytes = 0;

@@ -172,7 +172,7 @@ def test_object_demo_flow_mesh_to_vertex_contact(ctx, tmp_path):
     assert masks.shape == (1, 4, 1024, 1024)
     want = OL.lift_object_mesh(masks, p2v, bary, d["num_vertices"])
     got = np.load(f)["pred_contact_3d"]
-    assert got.shape == (1, d["num_vertices"]) and np.abs(got - want).max() < 1e-6
+    assert got.shape == (1, d["num_vertices"]) and np.abs(got - want).max() < 5e-6   # tree vs sequential fp32 sums
     assert np.array_equal(got > 0.5, want > 0.5)
 
 

@@ -58,3 +58,20 @@ hist = PO.fit(model, demo.LOSS_WEIGHTS, max_iter=60)
 e1 = ev()
 torch.cuda.synchronize()
 print(f"fit loop at 256^2: {e0.elapsed_time(e1) / 60:.2f} ms per iteration")
+
+e0 = ev()
+PO.fit(model, demo.LOSS_WEIGHTS, max_iter=60, record=False)
+e1 = ev()
+torch.cuda.synchronize()
+print(f"fit loop at 256^2 without host read-backs (record=False): {e0.elapsed_time(e1) / 60:.2f} ms per iteration")
+import time
+from interactvlm_b200 import fit as FIT
+from interactvlm_b200.bench_fit import _scene
+h_, o_, c_ = _scene(256, 0, torch.device("cuda"))
+opt = FIT.default_options()
+for it in (0, 250):
+    opt["max_iter"] = it
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    FIT.run_fit(h_, o_, c_, (256, 256), opt, record=False)
+    torch.cuda.synchronize()
+    print(f"run_fit with {it} iterations: {(time.perf_counter() - t0) * 1e3:.1f} ms wall", flush=True)
