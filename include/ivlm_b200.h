@@ -199,6 +199,12 @@ IVLM_API int ivlm_im2col_3x3_bf16(ivlm_handle h, const void* x, void* cols, int3
 IVLM_API int ivlm_preprocess_u8_bf16(ivlm_handle h, const uint8_t* img, void* out, int32_t N, int32_t H, int32_t W, int32_t S,
                             float pre_scale, const float* mean3_h, const float* std3_h, void* stream);
 
+/* JPEG decode through nvJPEG (a library call, as cuBLAS would be for a plain GEMM): the compressed file in HOST memory -> interleaved
+ * RGB uint8 [H,W,3] in DEVICE memory, the input of ivlm_resample_u8 / ivlm_preprocess_u8_bf16.  Replaces the cv2.imread of
+ * run_demo.py:330 / the dataset classes on the way to the GPU; pixel values may differ from libjpeg-turbo's by a few grey levels. */
+IVLM_API int ivlm_jpeg_info(ivlm_handle h, const uint8_t* data_h, size_t n, int32_t* height, int32_t* width);
+IVLM_API int ivlm_jpeg_decode_rgb(ivlm_handle h, const uint8_t* data_h, size_t n, uint8_t* rgb, int32_t H, int32_t W, void* stream);
+
 /* One pass (vertical = 0: along x, 1: along y) of Pillow's antialiased 8-bit resize -- the arithmetic of the reference's
  * ResizeLongestSide.apply_image (segment_anything/utils/transforms.py:27-34, bilinear) and CLIPImageProcessor resize
  * (bicubic): src [N,H,W,3] uint8 -> dst [N,OH,OW,3]; bounds [out,2] (first input index, count) and coeffs [out,ksize]

@@ -65,6 +65,43 @@ class DecodeLinearArgs(C.Structure):
 EPI_PLAIN, EPI_SWIGLU, EPI_ROPE_KV = 0, 1, 2
 
 
+class WeightDesc(C.Structure):
+    """ivlm_weight_desc."""
+    _fields_ = [("name", C.c_char_p), ("ptr", C.c_void_p), ("dtype", C.c_int32), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class ModelDims(C.Structure):
+    """ivlm_model_dims."""
+    _fields_ = [("sam_img", C.c_int32), ("sam_patch", C.c_int32), ("sam_embed_dim", C.c_int32), ("sam_depth", C.c_int32),
+                ("sam_heads", C.c_int32), ("sam_window", C.c_int32), ("sam_out_chans", C.c_int32), ("sam_global_mask", C.c_uint32),
+                ("llm_hidden", C.c_int32), ("llm_intermediate", C.c_int32), ("llm_layers", C.c_int32), ("llm_heads", C.c_int32),
+                ("llm_head_dim", C.c_int32), ("llm_vocab", C.c_int32), ("llm_rms_eps", C.c_float), ("llm_paired_layout", C.c_int32)]
+
+
+class SamEncodeArgs(C.Structure):
+    """ivlm_sam_encode_args."""
+    _fields_ = [("images", C.c_void_p), ("emb", C.c_void_p), ("N", C.c_int32), ("win_map", C.c_void_p), ("win_inv", C.c_void_p),
+                ("win_pads", C.c_void_p), ("n_pads", C.c_int32), ("arena", C.c_void_p), ("arena_bytes", C.c_size_t)]
+
+
+class LlmPrefillArgs(C.Structure):
+    """ivlm_llm_prefill_args."""
+    _fields_ = [("embeds", C.c_void_p), ("positions", C.c_void_p), ("slot_map", C.c_void_p), ("k_cache", C.POINTER(C.c_void_p)),
+                ("v_cache", C.POINTER(C.c_void_p)), ("hidden", C.c_void_p), ("next_tok", C.c_void_p), ("last_rows", C.c_void_p),
+                ("B", C.c_int32), ("S", C.c_int32), ("max_len", C.c_int32), ("page_size", C.c_int32), ("arena", C.c_void_p),
+                ("arena_bytes", C.c_size_t)]
+
+
+class LlmDecodeArgs(C.Structure):
+    """ivlm_llm_decode_args."""
+    _fields_ = [("state", C.c_void_p), ("S", C.c_int32), ("S_rows", C.c_void_p), ("scripted", C.c_void_p), ("G", C.c_int32),
+                ("next", C.c_void_p), ("done", C.c_void_p), ("out_tokens", C.c_void_p), ("tok", C.c_void_p), ("pos", C.c_void_p),
+                ("slot", C.c_void_p), ("seq_lens", C.c_void_p), ("slot_base", C.c_void_p), ("eos", C.c_int32), ("pad", C.c_int32),
+                ("B", C.c_int32), ("k_cache", C.POINTER(C.c_void_p)), ("v_cache", C.POINTER(C.c_void_p)), ("block_table", C.c_void_p),
+                ("max_pages", C.c_int32), ("page_size", C.c_int32), ("hidden", C.c_void_p), ("max_len", C.c_int32),
+                ("hid_step", C.c_void_p), ("arena", C.c_void_p), ("arena_bytes", C.c_size_t)]
+
+
 class RasterCam(C.Structure):
     """ivlm_raster_cam (include/ivlm_b200.h)."""
     _fields_ = [("R", C.c_float * 9), ("T", C.c_float * 3), ("C", C.c_float * 3), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
@@ -94,6 +131,8 @@ def lib() -> C.CDLL:
         _lib.ivlm_last_error.restype = C.c_char_p
         _lib.ivlm_launch_count.restype = C.c_uint64
         _lib.ivlm_lift_nnz.restype = C.c_int64
+        _lib.ivlm_sam_encode_arena_bytes.restype = C.c_size_t
+        _lib.ivlm_llm_arena_bytes.restype = C.c_size_t
         for name in declared_symbols():
             if not hasattr(_lib, name):
                 raise RuntimeError(f"libivlm_b200.so does not export {name}")

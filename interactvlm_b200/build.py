@@ -73,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         objs = list(ex.map(lambda s: _compile(s, verbose), sources()))
     # the visible symbols are exactly the extern "C" ABI of include/ivlm_b200.h
     cmd = [_nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC"]
+           "-Xcompiler", "-fPIC", "-lnvjpeg", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -53,6 +53,7 @@ struct DecodeStreamParams {
     // decomposition
     int tiles, spt, total_stages;    // spt = stages per tile
     int resident;                    // 1: the whole activation sits in shared memory (required with gamma)
+    int nstages;                     // ring depth in use (<= DS_STAGES; option "ds_stages")
     float* partial; int* flags;
 };
 
@@ -91,6 +92,7 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     const int G = gridDim.x, cta = blockIdx.x;
     const int s_begin = (int)((long long)p.total_stages * cta / G), s_end = (int)((long long)p.total_stages * (cta + 1) / G);
     const int n_my = s_end - s_begin;
+    const int NS = p.nstages;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < DS_STAGES; ++i) {
@@ -106,27 +108,29 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();   // every weight byte is used once per step
             const uint64_t keep = l2_policy_evict_last();
-            auto issue_weights = [&](int it) {
-                const int s = s_begin + it, slot = it % DS_STAGES;
+            auto issue_weights = [&](int it, int slot) {
+                const int s = s_begin + it;
                 const int tile = s / p.spt, ks = s % p.spt;
                 // the full box always counts: rows past N and chunks past K are zero-filled by the TMA unit
                 mbar_arrive_expect_tx(full + slot, stage_bytes);
                 tma_load_3d_hint(ring + (size_t)slot * stage_bytes, &tmW, full + slot, 0, tile * DS_ROWS, ks * (DS_KW / 64), pol);
             };
-            auto issue_acts = [&](int it) {
-                const int s = s_begin + it, slot = it % DS_STAGES;
+            auto issue_acts = [&](int it, int slot) {
+                const int s = s_begin + it;
                 tma_load_3d_hint(ring + (size_t)slot * stage_bytes + DS_W_BYTES, &tmA, full + slot, 0, 0, (s % p.spt) * (DS_KW / 64), keep);
             };
-            const int n_pre = min(DS_STAGES, n_my);
-            for (int it = 0; it < n_pre; ++it) issue_weights(it);   // static operands: before the dependency wait
+            const int n_pre = min(NS, n_my);
+            for (int it = 0; it < n_pre; ++it) issue_weights(it, it);   // static operands: before the dependency wait
             pdl_launch();
             pdl_wait();
             if (!RESIDENT)
-                for (int it = 0; it < n_pre; ++it) issue_acts(it);
+                for (int it = 0; it < n_pre; ++it) issue_acts(it, it);
+            int slot = 0, par = 0;   // ring position and wait parity, advanced incrementally (NS is a run-time value: no divisions)
             for (int it = n_pre; it < n_my; ++it) {
-                mbar_wait(empty + it % DS_STAGES, ((it / DS_STAGES) - 1) & 1);
-                issue_weights(it);
-                if (!RESIDENT) issue_acts(it);
+                mbar_wait(empty + slot, par);
+                issue_weights(it, slot);
+                if (!RESIDENT) issue_acts(it, slot);
+                if (++slot == NS) { slot = 0; par ^= 1; }
             }
         } else {
             pdl_launch();
@@ -194,11 +198,13 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     const bf16* b_res0 = act + (size_t)b_row * act_pitch + b_half * 8 + warp * 16;
 
     int tile = s_begin / p.spt, ks = s_begin - tile * p.spt;
+    int slot = -1, par = 1;
     for (int it = 0; it < n_my; ++it) {
-        const int slot = it % DS_STAGES;
+        if (++slot == NS) slot = 0;
+        if (slot == 0) par ^= 1;
         const int k0 = ks * DS_KW;
         const int kw = min(DS_KW, p.K - k0);
-        mbar_wait(full + slot, (it / DS_STAGES) & 1);
+        mbar_wait(full + slot, par);
         const uint8_t* st = ring + (size_t)slot * stage_bytes;
         if (kw == DS_KW) {
             uint32_t af[4][4], bq[4][2];
@@ -382,7 +388,9 @@ extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* 
     // shared memory: barriers + fold buffers, the resident activation (when it fits next to the ring), the 1024-byte aligned ring
     const size_t fixed = 128 + (DS_CONSUMERS + 1) * 128 * sizeof(float);
     const size_t act_bytes = (size_t)DS_MAX_M * (a->K + 8) * 2;
-    const size_t ring_res = (size_t)DS_STAGES * DS_W_BYTES, ring_str = (size_t)DS_STAGES * (DS_W_BYTES + DS_A_BYTES);
+    const int ns = (h->ds_stages >= 2 && h->ds_stages <= DS_STAGES) ? h->ds_stages : DS_STAGES;
+    p.nstages = ns;
+    const size_t ring_res = (size_t)ns * DS_W_BYTES, ring_str = (size_t)ns * (DS_W_BYTES + DS_A_BYTES);
     const size_t cap = 227 * 1024;
     p.resident = (fixed + act_bytes + 1024 + ring_res <= cap) ? 1 : 0;
     IVLM_REQUIRE(p.resident || a->norm_gamma == nullptr, "decode_linear: fused RMSNorm needs K <= %d (activation resident in shared memory)",

@@ -94,6 +94,7 @@ struct ivlm_ctx {
                                   // against 23 / 48 / 52, down_proj 40 / 57 / 62 against 56 / 136 / 130; tools/prof_decode.py variants)
     int small_m_variant = 0;      // 0: weight-streaming mma.sync kernel for token counts <= 64; 1: swapped-operand tcgen05 path
     int global_attn_variant = 0;  // 0: 64-key tiles, 2 CTAs/SM; 1: 128-key tiles, 1 CTA/SM (A/B switch)
+    int ds_stages = 0;            // decode_stream ring depth (0: 8 stages; A/B knob)
     int attn_prefetch_ahead = 0;  // window attention: L2 prefetch of the successor CTA's tiles, distance in CTAs of the launch order
                                   // (0 = off, the default: measured neutral at 148 .. 1184 CTAs ahead, 0.366-0.379 ms per 16 views)
     int window_attn_variant = 0;  // 0: single-tile 2-CTA/SM window kernel, 1: the general tiled kernel (A/B switch)
@@ -106,6 +107,7 @@ struct ivlm_ctx {
     std::unordered_map<std::string, ivlm::Weight> weights;   // ivlm_bind_weights: borrowed device pointers by name
     ivlm_model_dims dims = {};                               // ivlm_set_model_dims
     int dims_set = 0;
+    void* jpeg = nullptr;                                    // lazily created nvJPEG handle + state (jpeg.cu)
     // caller-provided scratch (bump allocated inside stage drivers)
     char* ws = nullptr;
     size_t ws_bytes = 0;

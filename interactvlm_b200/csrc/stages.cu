@@ -81,8 +81,13 @@ extern "C" size_t ivlm_sam_encode_arena_bytes(ivlm_handle h, int32_t N) {
     const size_t g = d.sam_img / d.sam_patch, S = g * g, E = d.sam_embed_dim, nw = (g + d.sam_window - 1) / d.sam_window;
     const size_t rows = (size_t)N * S, wrows = (size_t)N * nw * nw * d.sam_window * d.sam_window;
     const size_t qkv_rows = wrows > rows ? wrows : rows;
-    // x (two buffers), y, o: rows x E; qkv: qkv_rows x 3E; h: rows x 4E (also holds the im2col operands); slack for alignment
-    return 2 * (2 * rows * E + rows * E + rows * E + qkv_rows * 3 * E + rows * 4 * E) + 16 * 256;
+    // x (two buffers), y, o: rows x E; qkv: qkv_rows x 3E; h: rows x max(4E, patch operand, 3x3 operand); slack for alignment
+    size_t hw = 4 * E;
+    const size_t kk = 3 * (size_t)d.sam_patch * d.sam_patch, k9 = 9 * (size_t)d.sam_out_chans;
+    hw = hw > kk ? hw : kk;
+    hw = hw > k9 ? hw : k9;
+    const size_t Ew = E > (size_t)d.sam_out_chans ? E : (size_t)d.sam_out_chans;
+    return 2 * (2 * rows * E + 2 * rows * Ew + qkv_rows * 3 * E + rows * hw) + 16 * 256;
 }
 
 // images [N,3,S,S] bf16 -> emb [N, g*g, out_chans] bf16 token-major (image_encoder.py:110-125).  Window blocks run on the real
@@ -96,15 +101,19 @@ extern "C" int ivlm_sam_encode(ivlm_handle h, const ivlm_sam_encode_args* a, voi
     const int rows = N * S, Bw = N * nw * nw, wrows = Bw * ws * ws;
     IVLM_REQUIRE(hd == 80 && ws == 14 && a->win_map && a->win_inv, "sam_encode: the stage driver covers the ViT-H geometry (head_dim 80, 14x14 windows)");
     Arena arena(a->arena, a->arena_bytes);
+    const int kk = 3 * d.sam_patch * d.sam_patch;
+    size_t hw = 4 * (size_t)E;
+    hw = hw > (size_t)kk ? hw : (size_t)kk;
+    hw = hw > (size_t)9 * O ? hw : (size_t)9 * O;
+    const size_t Ew = E > O ? E : O;
     IVLM_TAKE(xa, uint16_t, (size_t)rows * E);
     IVLM_TAKE(xb, uint16_t, (size_t)rows * E);
-    IVLM_TAKE(y, uint16_t, (size_t)rows * E);
-    IVLM_TAKE(o, uint16_t, (size_t)rows * E);
+    IVLM_TAKE(y, uint16_t, (size_t)rows * Ew);
+    IVLM_TAKE(o, uint16_t, (size_t)rows * Ew);
     IVLM_TAKE(qkv, uint16_t, (size_t)(wrows > rows ? wrows : rows) * 3 * E);
-    IVLM_TAKE(hbuf, uint16_t, (size_t)rows * 4 * E);
+    IVLM_TAKE(hbuf, uint16_t, (size_t)rows * hw);
     IVLM_W(w_patch, "sam.w_patch"); IVLM_W(b_patch, "sam.b_patch"); IVLM_W(pos, "sam.pos");
-    const int kk = 3 * d.sam_patch * d.sam_patch;
-    IVLM_REQUIRE((size_t)rows * kk <= (size_t)rows * 4 * E && kk % 8 == 0, "sam_encode: patch operand does not fit the scratch");
+    IVLM_REQUIRE(kk % 8 == 0, "sam_encode: patch operand width %d is not a multiple of 8", kk);
     IVLM_TRY(ivlm_im2col_patch_bf16(h, a->images, hbuf, N, 3, d.sam_img, d.sam_img, d.sam_patch, kk, stream));
     IVLM_TRY(gemm(h, hbuf, kk, w_patch, kk, xa, E, rows, E, kk, b_patch, 0, pos, E, nullptr, S, -1, IVLM_BF16, stream));
     uint16_t *x = xa, *xn = xb;
@@ -134,7 +143,6 @@ extern "C" int ivlm_sam_encode(ivlm_handle h, const ivlm_sam_encode_args* a, voi
     uint16_t *t0 = y, *t1 = o;   // [rows, O] temporaries inside the dead E-wide buffers
     IVLM_TRY(gemm(h, x, E, neck0, E, t0, O, rows, O, E, nullptr, 0, nullptr, 0, nullptr, 0, -1, IVLM_BF16, stream));
     IVLM_TRY(ivlm_layernorm_bf16(h, t0, t1, n1g, n1b, rows, O, 1e-6f, nullptr, 0, stream));
-    IVLM_REQUIRE((size_t)9 * O <= (size_t)4 * E, "sam_encode: 3x3 operand does not fit the scratch");
     IVLM_TRY(ivlm_im2col_3x3_bf16(h, t1, hbuf, N, g, g, O, stream));
     IVLM_TRY(gemm(h, hbuf, 9 * O, neck2, 9 * O, t0, O, rows, O, 9 * O, nullptr, 0, nullptr, 0, nullptr, 0, -1, IVLM_BF16, stream));
     IVLM_TRY(ivlm_layernorm_bf16(h, t0, a->emb, n3g, n3b, rows, O, 1e-6f, nullptr, 0, stream));
@@ -146,7 +154,7 @@ extern "C" size_t ivlm_llm_arena_bytes(ivlm_handle h, int32_t tokens) {
     const ivlm_model_dims& d = h->dims;
     const size_t T = tokens, D = d.llm_hidden, F = d.llm_intermediate;
     // x (two), y, q, k, v, o: T x D; qkv: T x 3D; gate-up: T x 2F; act: T x F; logits: 64 x vocab fp32
-    return 2 * (7 * T * D + 3 * T * D + 2 * T * F + T * F) + 4 * (size_t)64 * (d.llm_vocab + 8) + 32 * 256;
+    return 2 * (8 * T * D + 3 * T * D + 2 * T * F + T * F) + 4 * (size_t)64 * (d.llm_vocab + 8) + 32 * 256;   // 8th T x D: the last-row gather
 }
 
 // embeds [B*S, D] bf16 (B sequences of S rows, right-padded) -> K/V pages, hidden [B, max_len, D] (rows [0,S) of every
@@ -158,6 +166,7 @@ extern "C" int ivlm_llm_prefill(ivlm_handle h, const ivlm_llm_prefill_args* a, v
     IVLM_REQUIRE(h->dims_set, "llm_prefill: call ivlm_set_model_dims first");
     const ivlm_model_dims& d = h->dims;
     const int D = d.llm_hidden, F = d.llm_intermediate, nh = d.llm_heads, hd = d.llm_head_dim, T = a->B * a->S;
+    IVLM_CHECK_CUDA(cudaGetLastError());   // a launch error left behind by earlier work on this device would otherwise surface below
     Arena arena(a->arena, a->arena_bytes);
     IVLM_TAKE(xa, uint16_t, (size_t)T * D);
     IVLM_TAKE(xb, uint16_t, (size_t)T * D);
@@ -201,9 +210,10 @@ extern "C" int ivlm_llm_prefill(ivlm_handle h, const ivlm_llm_prefill_args* a, v
     IVLM_W(norm, "llm.norm");
     // normed states of every row -> hidden[b, 0:S, :]
     IVLM_TRY(ivlm_rmsnorm_bf16(h, x, y, norm, T, D, d.llm_rms_eps, stream));
-    for (int b = 0; b < a->B; ++b)
-        IVLM_CHECK_CUDA(cudaMemcpyAsync(reinterpret_cast<uint16_t*>(a->hidden) + (size_t)b * a->max_len * D, y + (size_t)b * a->S * D,
-                                        sizeof(uint16_t) * (size_t)a->S * D, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+    IVLM_REQUIRE(a->max_len >= a->S, "llm_prefill: hidden holds %d rows per sequence, the prompt has %d", a->max_len, a->S);
+    IVLM_CHECK_CUDA(cudaMemcpy2DAsync(a->hidden, sizeof(uint16_t) * (size_t)a->max_len * D, y, sizeof(uint16_t) * (size_t)a->S * D,
+                                      sizeof(uint16_t) * (size_t)a->S * D, (size_t)a->B, cudaMemcpyDeviceToDevice,
+                                      reinterpret_cast<cudaStream_t>(stream)));
     // greedy token after each sequence's last valid row
     IVLM_W(lm_head, "llm.lm_head");
     IVLM_TAKE(last, uint16_t, (size_t)a->B * D);

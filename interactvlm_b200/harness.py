@@ -56,6 +56,15 @@ def prepare_inputs_from_raw(model, image_u8, sam_views_u8):
     return clip, sam.view(B, V, 3, cfg.sam_img_size, cfg.sam_img_size), [(sh, sw)] * B
 
 
+def prepare_inputs_from_jpeg(model, image_jpeg: bytes, sam_views_u8):
+    """run_demo.py:330-366 starting from the COMPRESSED photo: nvJPEG decode on the GPU (ivlm_jpeg_decode_rgb), then the
+    Pillow-exact resizes and the fused normalisation of prepare_inputs_from_raw.  One photo, V rendered views.  The decoded
+    pixels can differ from cv2.imread's by a few grey levels (different IDCT); everything after the decode is bit-exact."""
+    rgb = model.ctx.decode_jpeg(image_jpeg)
+    return prepare_inputs_from_raw(model, rgb[None], torch.as_tensor(sam_views_u8)[None] if torch.as_tensor(sam_views_u8).dim() == 4
+                                   else sam_views_u8)
+
+
 class ContactConverter:
     """convert_contacts(contact, mapping): dense [n_out, n_in] mapping applied as a CSR SpMV (the SMPL->SMPL-X matrix has
     ~3 non-zeros per row; the reference streams the 289 MB dense matrix through bmm on every call)."""

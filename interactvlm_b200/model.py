@@ -173,6 +173,18 @@ class _Weights:
             self.splitter = {n: (g(f"attention_splitter.{n}.weight"), g(f"attention_splitter.{n}.bias"))
                              for n in ("input_proj", "query_human", "query_object", "key", "value", "output_proj")}
         del self.g
+        # names under which the stage-level ABI (ivlm_bind_weights -> ivlm_sam_encode / ivlm_llm_prefill / ivlm_llm_decode_step)
+        # finds the tensors above
+        nm = self.named = {"llm.embed": self.embed, "llm.norm": self.norm, "llm.lm_head": self.lm_head, "llm.rope_cos": self.rope_cos,
+                           "llm.rope_sin": self.rope_sin}
+        for i, lw in enumerate(self.llm):
+            for k in ("ln1", "ln2", "wqkv", "wo", "wgu", "wd"):
+                nm[f"llm.{i}.{k}"] = lw[k]
+        for k in ("w_patch", "b_patch", "pos", "neck0", "n1g", "n1b", "neck2", "n3g", "n3b"):
+            nm["sam." + k] = self.sam[k]
+        for i, bw in enumerate(self.sam["blocks"]):
+            for k, t in bw.items():
+                nm[f"sam.blocks.{i}.{k}"] = t
 
     @staticmethod
     def _dense_pe(G, cfg):
@@ -197,9 +209,21 @@ class _Engine:
         self.device = w.device
         self._win_maps = {}
         self.fused_sam_attention = True
+        # stage-level ABI: one C call per stage (SAM encoder, LLaMA prefill, decode step) instead of the op-by-op loops below;
+        # same kernels in the same order (bit-identical).  The op-level path stays for per-op profiling and the test traces.
+        self.stage_abi = not getattr(ctx, "emulated", False)
+        self._bind()
         self.skip_pad_rows = True  # SAM window blocks: GEMMs on the real tokens only (the padded rows' q/k/v are the bias)
         self.fused_decode = True   # decode steps of <= 8 tokens through ivlm_decode_linear (5 launches per layer instead of 9)
         self.trace = None  # tests: dict of lists receiving the residual stream after every SAM block / LLaMA prefill layer
+
+    def _bind(self):
+        """The weight table and the model dimensions live in the ivlm handle: (re)bind them when another model used the handle
+        in between (tests share one handle between several models)."""
+        if self.stage_abi and getattr(self.ctx, "_bound_weights", None) is not self.w:
+            self.ctx.bind_weights(self.w.named)
+            self.ctx.set_model_dims(self.cfg, self.w.paired_qk)
+            self.ctx._bound_weights = self.w
 
     # ------------------------------------------------------------------ CLIP + projector (a4)
     def clip_encode(self, images_clip):
@@ -269,6 +293,12 @@ class _Engine:
         g, E, nh, ws = cfg.sam_grid, cfg.sam_embed_dim, cfg.sam_num_heads, cfg.sam_window_size
         hd = E // nh
         S = g * g
+        if (self.stage_abi and self.trace is None and self.fused_sam_attention and self.skip_pad_rows and hd == 80 and ws == 14
+                and not ctx.profiling and (3 * cfg.sam_patch_size ** 2) % 8 == 0):
+            wmap, _ = self._window_map(N)
+            inv, pads = self._window_inverse(N)
+            self._bind()
+            return ctx.sam_encode_stage(images.contiguous(), wmap, inv, pads)
         cols = ctx.im2col_patch(images.contiguous(), cfg.sam_patch_size)
         x = ctx.gemm(cols, w["w_patch"], bias=w["b_patch"], residual=w["pos"], res_row_mod=S, force_swap=-1)
         del cols
@@ -339,6 +369,15 @@ class _Engine:
         slot = (torch.arange(B, dtype=torch.int32)[:, None] * (st["pages_per"] * PAGE) + torch.arange(S, dtype=torch.int32)[None]).reshape(-1)
         pos, slot = pos.to(self.device), slot.to(self.device)
         x = embeds.reshape(B * S, D)
+        if self.stage_abi and self.trace is None and not ctx.profiling:
+            if "next" not in st:
+                st["next"] = torch.zeros((B,), dtype=torch.int32, device=self.device)
+            if "k_ptrs" not in st:
+                st["k_ptrs"], st["v_ptrs"] = ctx.pointer_array(st["k"]), ctx.pointer_array(st["v"])
+            self._bind()
+            ctx.llm_prefill_stage(x.contiguous(), pos, slot, st["k_ptrs"], st["v_ptrs"], st["hidden"], st["next"], last_rows, B, S, PAGE)
+            st["len"] = S
+            return st["next"]
         for i, lw in enumerate(W.llm):
             y = ctx.rmsnorm(x, lw["ln1"], cfg.rms_norm_eps)
             qkv = ctx.gemm(y, lw["wqkv"])
@@ -390,6 +429,9 @@ class _Engine:
         st["max_new"] = 0
         st["slot_base"] = (torch.arange(B, dtype=torch.int32, device=self.device) * (st["pages_per"] * PAGE)).contiguous()
         st["S_rows"] = torch.zeros((B,), dtype=torch.int32, device=self.device)   # per-sample prompt rows (right-padded batches)
+        if self.stage_abi:
+            st["k_ptrs"], st["v_ptrs"] = self.ctx.pointer_array(st["k"]), self.ctx.pointer_array(st["v"])
+            st["decode_arena"] = self.ctx.llm_arena(B, self.device)
 
     def llm_decode_step(self, st):
         """One token per sample through the paged KV cache.  All bookkeeping is on the device: `decode_prepare` picks the
@@ -398,9 +440,14 @@ class _Engine:
         step lands in st['next'].  Fixed launch sequence over fixed buffers -> one CUDA graph, replayed per step."""
         ctx, cfg, W = self.ctx, self.cfg, self.w
         nh, hd = cfg.num_attention_heads, cfg.head_dim
+        fused = (self.fused_decode and W.paired_qk and st["tok"].numel() <= 8 and cfg.hidden_size % 64 == 0 and
+                 cfg.intermediate_size % 64 == 0)
+        if fused and self.stage_abi and not ctx.profiling and "decode_arena" in st:
+            self._bind()
+            ctx.llm_decode_stage(st, st["S"], st["G"], cfg.eos_token_id, cfg.pad_token_id, PAGE)
+            return
         ctx.decode_prepare(st, st["S"], st["G"], cfg.eos_token_id, cfg.pad_token_id)
         x = ctx.embed_gather(W.embed, st["tok"])
-        fused = self.fused_decode and W.paired_qk and x.shape[0] <= 8 and cfg.hidden_size % 64 == 0 and cfg.intermediate_size % 64 == 0
         if fused:
             # 5 launches per layer (ivlm_decode_linear): [RMSNorm + qkv + RoPE + KV store] -> attention -> [o_proj + residual]
             # -> [RMSNorm + gate/up + SwiGLU] -> [down_proj + residual]

@@ -38,6 +38,7 @@ class Context:
         torch.cuda.set_device(self.device)
         L.check(self.lib.ivlm_create(C.byref(h), i32(self.device.index)), "ivlm_create")
         self.h = h
+        self.profiling = False   # per-op event brackets on (enable_profile): stage-level calls are then bypassed by the model
         self.workspace = torch.empty(32 << 20, device=self.device, dtype=torch.uint8)
         L.check(self.lib.ivlm_set_workspace(self.h, P(self.workspace), C.c_size_t(self.workspace.numel()), self.stream),
                 "set_workspace")
@@ -72,6 +73,7 @@ class Context:
         """Bracket every launch with CUDA events on the launching stream (no synchronisation until profile_report()).
         Adds a few microseconds of host time per launch, so bench.py uses it in a separate pass from the headline timing."""
         self._prof = []
+        self.profiling = True
         for name in self._PROFILED:
             fn = getattr(type(self), name)
 
@@ -100,6 +102,7 @@ class Context:
             setattr(self, name, wrapped)
 
     def disable_profile(self):
+        self.profiling = False
         for name in self._PROFILED:
             if name in self.__dict__:
                 delattr(self, name)
@@ -115,6 +118,87 @@ class Context:
             r["work"] += work
         self._prof = []
         return rep
+
+    # ------------------------------------------------------------------ stage-level ABI (csrc/stages.cu)
+    def bind_weights(self, named: dict):
+        """name -> CUDA tensor; pointers are borrowed (the caller keeps the tensors alive)."""
+        arr = (L.WeightDesc * len(named))()
+        keep = []
+        for d, (name, t) in zip(arr, named.items()):
+            assert t.is_cuda and t.is_contiguous() and t.dim() >= 1 and t.dim() <= 4, name
+            nb = name.encode()
+            keep.append(nb)
+            d.name, d.ptr, d.ndim = nb, t.data_ptr(), t.dim()
+            d.dtype = BF16 if t.dtype == torch.bfloat16 else (F32 if t.dtype == torch.float32 else 2)
+            for k, sz in enumerate(t.shape):
+                d.shape[k] = sz
+        L.check(self.lib.ivlm_bind_weights(self.h, arr, i32(len(named))), "bind_weights")
+
+    def set_model_dims(self, cfg, paired_layout: bool):
+        d = L.ModelDims()
+        d.sam_img, d.sam_patch, d.sam_embed_dim, d.sam_depth = cfg.sam_img_size, cfg.sam_patch_size, cfg.sam_embed_dim, cfg.sam_depth
+        d.sam_heads, d.sam_window, d.sam_out_chans = cfg.sam_num_heads, cfg.sam_window_size, cfg.sam_out_chans
+        d.sam_global_mask = sum(1 << i for i in cfg.sam_global_attn_indexes)
+        d.llm_hidden, d.llm_intermediate, d.llm_layers = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+        d.llm_heads, d.llm_head_dim, d.llm_vocab = cfg.num_attention_heads, cfg.head_dim, cfg.vocab_size
+        d.llm_rms_eps, d.llm_paired_layout = cfg.rms_norm_eps, 1 if paired_layout else 0
+        L.check(self.lib.ivlm_set_model_dims(self.h, C.byref(d)), "set_model_dims")
+        self._dims = d
+
+    def sam_encode_stage(self, images, win_map, win_inv, win_pads):
+        """ivlm_sam_encode: [N,3,S,S] bf16 -> [N, (S/patch)^2, out_chans] bf16 in one call."""
+        _bf16(images)
+        assert images.is_contiguous()
+        N = images.shape[0]
+        d = self._dims
+        S = (d.sam_img // d.sam_patch) ** 2
+        emb = torch.empty((N, S, d.sam_out_chans), device=images.device, dtype=torch.bfloat16)
+        nbytes = int(self.lib.ivlm_sam_encode_arena_bytes(self.h, i32(N)))
+        arena = torch.empty(nbytes, device=images.device, dtype=torch.uint8)
+        a = L.SamEncodeArgs()
+        a.images, a.emb, a.N = images.data_ptr(), emb.data_ptr(), N
+        a.win_map, a.win_inv = win_map.data_ptr(), win_inv.data_ptr()
+        a.win_pads, a.n_pads = (win_pads.data_ptr() if win_pads.numel() else None), win_pads.numel()
+        a.arena, a.arena_bytes = arena.data_ptr(), nbytes
+        L.check(self.lib.ivlm_sam_encode(self.h, C.byref(a), self.stream), "sam_encode")
+        return emb
+
+    def llm_arena(self, tokens, device):
+        nbytes = int(self.lib.ivlm_llm_arena_bytes(self.h, i32(tokens)))
+        return torch.empty(nbytes, device=device, dtype=torch.uint8)
+
+    @staticmethod
+    def pointer_array(tensors):
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        return arr
+
+    def llm_prefill_stage(self, embeds2d, positions, slot_map, k_ptrs, v_ptrs, hidden, next_tok, last_rows, B, S, page_size):
+        _bf16(embeds2d)
+        assert embeds2d.is_contiguous() and hidden.is_contiguous()
+        arena = self.llm_arena(B * S, embeds2d.device)
+        a = L.LlmPrefillArgs()
+        a.embeds, a.positions, a.slot_map = embeds2d.data_ptr(), positions.data_ptr(), slot_map.data_ptr()
+        a.k_cache, a.v_cache = k_ptrs, v_ptrs
+        a.hidden, a.next_tok = hidden.data_ptr(), next_tok.data_ptr()
+        a.last_rows = last_rows.data_ptr() if last_rows is not None else None
+        a.B, a.S, a.max_len, a.page_size = B, S, hidden.shape[1], page_size
+        a.arena, a.arena_bytes = arena.data_ptr(), arena.numel()
+        L.check(self.lib.ivlm_llm_prefill(self.h, C.byref(a), self.stream), "llm_prefill")
+
+    def llm_decode_stage(self, st, S, G, eos, pad, page_size):
+        """ivlm_llm_decode_step over the decode-state dict of model.py (fixed buffers: CUDA-graph capturable)."""
+        a = L.LlmDecodeArgs()
+        a.state, a.S, a.G = st["state"].data_ptr(), S, G
+        a.S_rows = st["S_rows"].data_ptr() if st.get("S_rows") is not None else None
+        a.scripted = st["scripted"].data_ptr() if st.get("scripted") is not None else None
+        for k in ("next", "done", "out_tokens", "tok", "pos", "slot", "seq_lens", "slot_base"):
+            setattr(a, k, st[k].data_ptr())
+        a.eos, a.pad, a.B = eos, pad, st["tok"].numel()
+        a.k_cache, a.v_cache = st["k_ptrs"], st["v_ptrs"]
+        a.block_table, a.max_pages, a.page_size = st["block_table"].data_ptr(), st["block_table"].shape[1], page_size
+        a.hidden, a.max_len, a.hid_step = st["hidden"].data_ptr(), st["hidden"].shape[1], st["hid_step"].data_ptr()
+        a.arena, a.arena_bytes = st["decode_arena"].data_ptr(), st["decode_arena"].numel()
+        L.check(self.lib.ivlm_llm_decode_step(self.h, C.byref(a), self.stream), "llm_decode_step")
 
     # ------------------------------------------------------------------ dense
     def gemm(self, a, w, bias=None, act=ACT_NONE, residual=None, out=None, out_dtype=torch.bfloat16, row_map=None,
@@ -453,6 +537,16 @@ class Context:
         m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
         L.check(self.lib.ivlm_preprocess_u8_bf16(self.h, P(img_u8), P(out), i32(N), i32(H), i32(W), i32(size), f32c(pre), m3, s3,
                                                  self.stream), "preprocess_u8")
+        return out
+
+    def decode_jpeg(self, data: bytes):
+        """Compressed JPEG bytes -> uint8 [H,W,3] RGB CUDA tensor (nvJPEG)."""
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        H, W = i32(0), i32(0)
+        L.check(self.lib.ivlm_jpeg_info(self.h, buf, C.c_size_t(len(data)), C.byref(H), C.byref(W)), "jpeg_info")
+        out = torch.empty((H.value, W.value, 3), device=self.device, dtype=torch.uint8)
+        L.check(self.lib.ivlm_jpeg_decode_rgb(self.h, buf, C.c_size_t(len(data)), P(out), H, W, self.stream), "jpeg_decode")
+        torch.cuda.current_stream(self.device).synchronize()   # `buf` (host) must outlive the decode
         return out
 
     def resize_u8(self, img_u8, out_h, out_w, filt="bilinear"):

@@ -89,3 +89,30 @@ def test_prepare_inputs_from_raw_matches_reference_pipeline(model):
     cref = ((torch.from_numpy(c.copy()).permute(2, 0, 1).float() * (1 / 255.0) - torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(-1, 1, 1))
             / torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(-1, 1, 1)).bfloat16()
     assert (clip[0].float().cpu() - cref.float()).abs().max().item() <= 2 ** -6
+
+
+def test_jpeg_decode_on_the_gpu_matches_opencv_within_decoder_tolerance(ctx):
+    """ivlm_jpeg_decode_rgb (nvJPEG) against cv2.imdecode (libjpeg-turbo, what the reference's cv2.imread runs): same size,
+    pixels within a few grey levels (the two IDCT / chroma-upsampling implementations differ), 4:2:0 and 4:4:4, odd sizes."""
+    import cv2
+
+    g = np.random.default_rng(0)
+    for (H, W), quality, sub in (((357, 500), 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420), ((224, 224), 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444)):
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+        img = np.stack([127 + 100 * np.sin(xx / 37 + c) * np.cos(yy / 29 - c) for c in range(3)], -1)
+        img = np.clip(img + g.normal(0, 3, img.shape), 0, 255).astype(np.uint8)
+        ok, enc = cv2.imencode(".jpg", img[..., ::-1], [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sub])
+        assert ok
+        ref = cv2.cvtColor(cv2.imdecode(enc, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+        out = ctx.decode_jpeg(enc.tobytes()).cpu().numpy()
+        assert out.shape == ref.shape == (H, W, 3)
+        d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+        print(f"jpeg {H}x{W} q{quality}: max |diff| {d.max()}, mean {d.mean():.3f}")
+        # 4:4:4: only the IDCT / colour-conversion rounding differs; 4:2:0: libjpeg-turbo smooths the upsampled chroma
+        # ("fancy upsampling") and nvJPEG does not, which moves many pixels by one or two levels
+        if sub == cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444:
+            assert d.max() <= 4 and d.mean() < 0.8, (d.max(), d.mean())
+        else:
+            assert d.max() <= 24 and d.mean() < 2.0, (d.max(), d.mean())
+    with pytest.raises(RuntimeError):
+        ctx.decode_jpeg(b"not a jpeg at all")

@@ -388,3 +388,32 @@ def test_prompts_of_different_lengths_in_one_batch(tiny):
         one, _ = model.generate(clip[b:b + 1], prompts[b][None], max_new_tokens=3)
         n = one.shape[1]
         assert g_ids[b, :n].tolist() == one[0].tolist()
+
+
+def test_stage_level_abi_is_bit_identical_to_the_op_level_path(tiny):
+    """ivlm_sam_encode / ivlm_llm_prefill / ivlm_llm_decode_step (one C call per stage over a caller arena) against the op-by-op
+    loops of _Engine: the same kernels in the same order -> identical bits, fewer host calls."""
+    cfg, sd, model, _ = tiny
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
+    args = (clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2)
+    assert model.eng.stage_abi
+    outs = {}
+    for stage in (True, False):
+        model.eng.stage_abi = stage
+        model._graphs = {}
+        outs[stage] = (model.evaluate(*args, max_new_tokens=ans.shape[1], scripted=ans), model.evaluate(*args, max_new_tokens=5))
+    model.eng.stage_abi = True
+    model._graphs = {}
+    for k in (0, 1):
+        a, b = outs[True][k], outs[False][k]
+        assert torch.equal(a["output_ids"], b["output_ids"])
+        for x, y in zip(a["pred_masks"], b["pred_masks"]):
+            assert torch.equal(x, y)
+        assert (a["pred_contact_3d"] is None) == (b["pred_contact_3d"] is None)
+        if a["pred_contact_3d"] is not None:
+            assert torch.equal(a["pred_contact_3d"], b["pred_contact_3d"])
+    emb_s = model.eng.sam_encode(sam[0].cuda().bfloat16())
+    model.eng.stage_abi = False
+    emb_o = model.eng.sam_encode(sam[0].cuda().bfloat16())
+    model.eng.stage_abi = True
+    assert torch.equal(emb_s, emb_o)

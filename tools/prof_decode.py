@@ -117,6 +117,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "fused":
     for pdl in (0, 1):
         ctx.set_option("pdl", pdl)
         print(f"fused layer chain in a graph, pdl={pdl}: {graph_time(fused_chain):7.2f} us per layer;   9-launch chain: {graph_time(layer_chain):7.2f} us", flush=True)
+    ctx.set_option("pdl", 1)
+    for ns in (8, 6, 4, 3, 2):
+        ctx.set_option("ds_stages", ns)
+        row = "  ".join(f"{name.split('+')[0]} {graph_time(fn):6.2f}" for name, (fn, _) in list(fops.items())[:4])
+        print(f"ring depth {ns}: {row}  chain {graph_time(fused_chain):7.2f} us", flush=True)
+    ctx.set_option("ds_stages", 0)
     ctx.set_option("pdl", 0)
     sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "splits":
