@@ -67,6 +67,7 @@ extern "C" int ivlm_set_option(ivlm_handle h, const char* name, int32_t value) {
         h->global_attn_variant = value;
         return IVLM_OK;
     }
+    if (std::string(name) == "dec_warps") { h->dec_warps = value; return IVLM_OK; }
     if (std::string(name) == "ds_stages") { h->ds_stages = value; return IVLM_OK; }
     if (std::string(name) == "attn_prefetch_ahead") { h->attn_prefetch_ahead = value; return IVLM_OK; }
     if (std::string(name) == "window_attn_variant") {

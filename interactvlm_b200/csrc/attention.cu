@@ -260,8 +260,8 @@ __global__ void sam_relpos_kernel(const bf16* __restrict__ qkv, const bf16* __re
 // softmax in fp32 cast to bf16, bf16 P.V.  HBM-bound.  The cache is [pages, H, 16, HD]: one (page, head) is a contiguous
 // 16*HD*2-byte run, and one warp iteration consumes exactly one page with 16/RPI independent 16-byte loads per lane
 // (a single block-table lookup, no per-row index arithmetic).
-constexpr int DEC_WARPS = 8, DEC_PAGE = 16, DEC_MAX_PAGES = 256;
-template <int HD>
+constexpr int DEC_PAGE = 16, DEC_MAX_PAGES = 256;
+template <int HD, int DEC_WARPS>
 __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const bf16* __restrict__ q,
                                                                           const bf16* __restrict__ k_cache,
                                                                           const bf16* __restrict__ v_cache,
@@ -624,22 +624,27 @@ extern "C" int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, co
     IVLM_REQUIRE(page_size == DEC_PAGE, "decode_attention: page_size %d not instantiated (%d)", page_size, DEC_PAGE);
     const float inv_scale = 1.0f / scale;  // reference divides by sqrt(hd)
     dim3 grid(H, B);
+    // warps per CTA: every warp consumes whole pages.  8 is the default; 11 (two pages per warp at the bench's 22-page context
+    // instead of three for six of the eight warps) and 16 measured slower, 17.1 us against 16.0 us per layer inside the decode
+    // chain -- the extra warps lengthen the two block-wide reductions more than they shorten the page loops (option "dec_warps")
+    const int warps = h->dec_warps == 11 ? 11 : (h->dec_warps == 16 ? 16 : 8);
+#define IVLM_DEC(HD_, W_)                                                                                                        \
+    do {                                                                                                                         \
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_paged_kernel<HD_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                             (int)smem));                                                                        \
+        IVLM_CHECK_CUDA(launch_k(h, decode_attn_paged_kernel<HD_, W_>, grid, dim3(W_ * 32), smem, stream, (const bf16*)q,        \
+                                 (const bf16*)k_cache, (const bf16*)v_cache, (const int*)block_table, (const int*)seq_lens,      \
+                                 (bf16*)out, (int)H, (int)max_pages, inv_scale));                                                \
+    } while (0)
     if (hd == 128) {
-        IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_paged_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-        IVLM_CHECK_CUDA(launch_k(h, decode_attn_paged_kernel<128>, grid, dim3(DEC_WARPS * 32), smem, stream, (const bf16*)q,
-                                 (const bf16*)k_cache, (const bf16*)v_cache, (const int*)block_table, (const int*)seq_lens,
-                                 (bf16*)out, (int)H, (int)max_pages, inv_scale));
+        if (warps == 8) IVLM_DEC(128, 8); else if (warps == 16) IVLM_DEC(128, 16); else IVLM_DEC(128, 11);
     } else if (hd == 64) {
-        IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_paged_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-        IVLM_CHECK_CUDA(launch_k(h, decode_attn_paged_kernel<64>, grid, dim3(DEC_WARPS * 32), smem, stream, (const bf16*)q,
-                                 (const bf16*)k_cache, (const bf16*)v_cache, (const int*)block_table, (const int*)seq_lens,
-                                 (bf16*)out, (int)H, (int)max_pages, inv_scale));
+        if (warps == 8) IVLM_DEC(64, 8); else if (warps == 16) IVLM_DEC(64, 16); else IVLM_DEC(64, 11);
     } else {
         set_error("decode_attention: head_dim %d not instantiated (64, 128)", hd);
         return IVLM_ERR_ARG;
     }
+#undef IVLM_DEC
     h->launches++;
     IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;

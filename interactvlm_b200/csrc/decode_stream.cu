@@ -388,7 +388,7 @@ extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* 
     // shared memory: barriers + fold buffers, the resident activation (when it fits next to the ring), the 1024-byte aligned ring
     const size_t fixed = 128 + (DS_CONSUMERS + 1) * 128 * sizeof(float);
     const size_t act_bytes = (size_t)DS_MAX_M * (a->K + 8) * 2;
-    const int ns = (h->ds_stages >= 2 && h->ds_stages <= DS_STAGES) ? h->ds_stages : DS_STAGES;
+    const int ns = (h->ds_stages >= 2 && h->ds_stages <= DS_STAGES) ? h->ds_stages : 6;
     p.nstages = ns;
     const size_t ring_res = (size_t)ns * DS_W_BYTES, ring_str = (size_t)ns * (DS_W_BYTES + DS_A_BYTES);
     const size_t cap = 227 * 1024;

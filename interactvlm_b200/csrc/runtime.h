@@ -94,7 +94,8 @@ struct ivlm_ctx {
                                   // against 23 / 48 / 52, down_proj 40 / 57 / 62 against 56 / 136 / 130; tools/prof_decode.py variants)
     int small_m_variant = 0;      // 0: weight-streaming mma.sync kernel for token counts <= 64; 1: swapped-operand tcgen05 path
     int global_attn_variant = 0;  // 0: 64-key tiles, 2 CTAs/SM; 1: 128-key tiles, 1 CTA/SM (A/B switch)
-    int ds_stages = 0;            // decode_stream ring depth (0: 8 stages; A/B knob)
+    int ds_stages = 0;            // decode_stream ring depth (0: 6 stages -- 137 vs 139 us per layer with 8 in the same run; A/B knob)
+    int dec_warps = 0;            // paged decode attention: warps per CTA (0: 8; 11 or 16 for A/B)
     int attn_prefetch_ahead = 0;  // window attention: L2 prefetch of the successor CTA's tiles, distance in CTAs of the launch order
                                   // (0 = off, the default: measured neutral at 148 .. 1184 CTAs ahead, 0.366-0.379 ms per 16 views)
     int window_attn_variant = 0;  // 0: single-tile 2-CTA/SM window kernel, 1: the general tiled kernel (A/B switch)

@@ -123,6 +123,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "fused":
         row = "  ".join(f"{name.split('+')[0]} {graph_time(fn):6.2f}" for name, (fn, _) in list(fops.items())[:4])
         print(f"ring depth {ns}: {row}  chain {graph_time(fused_chain):7.2f} us", flush=True)
     ctx.set_option("ds_stages", 0)
+    for wv in (8, 11, 16):
+        ctx.set_option("dec_warps", wv)
+        print(f"decode attention with {wv} warps per CTA: {graph_time(fops['decode_attention'][0]):6.2f} us   chain {graph_time(fused_chain):7.2f} us", flush=True)
+    ctx.set_option("dec_warps", 0)
     ctx.set_option("pdl", 0)
     sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "splits":
