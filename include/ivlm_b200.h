@@ -287,7 +287,8 @@ IVLM_API int ivlm_decode_finish(ivlm_handle h, const int32_t* state, int32_t S, 
  *                     (rows h*hd+16b..+7 = features h*hd+8b..+7, rows +8..+15 = the same features + hd/2), v rows natural;
  *                     rotated q -> out [M, H*hd] (natural order), rotated k and v -> paged cache at slot_map[m]
  *                     (layout of ivlm_rope_kv_store_bf16).
- * Replaces, per decoder layer, the separate rmsnorm / rope_kv_store / silu_mul launches of the chain.  Needs a bound workspace;
+ * Replaces, per decoder layer, the separate rmsnorm / rope_kv_store / silu_mul launches of the chain (HF 4.31
+ * modeling_llama.py LlamaDecoderLayer.forward as driven by /root/reference model/llava/model/language_model/llava_llama.py:93-105).  Needs a bound workspace;
  * K must be a multiple of 64 and all operands 16-byte aligned (the weights arrive through a rank-3 TMA tensor map). */
 enum ivlm_decode_epilogue { IVLM_EPI_PLAIN = 0, IVLM_EPI_SWIGLU = 1, IVLM_EPI_ROPE_KV = 2 };
 typedef struct ivlm_decode_linear_args {
@@ -314,6 +315,15 @@ typedef struct ivlm_decode_linear_args {
     void* k_cache;            /* [pages, H, page_size, hd] bf16 */
     void* v_cache;
     int32_t H, hd, page_size;
+    /* optional: weights [prefetch_N, prefetch_K] of the NEXT ivlm_decode_linear launch on this stream.  Each CTA asks L2
+     * (cp.async.bulk.prefetch.L2) for the first prefetch_stages 16 KB stages its successor CTA will stream, once its own last
+     * stage is in flight -- the HBM pipe then stays busy across the launch boundary (and across the attention launch between
+     * qkv and o_proj).  0 stages = 256 KB per SM.  OFF unless option "ds_prefetch_kb" is set (-1: as asked, > 0: cap in KB):
+     * on the 13B chain it measured 1-10 % slower than no prefetch (the launches are bounded by their fixed costs, not by an
+     * idle HBM pipe), so it stays an A/B knob.  Results do not depend on it. */
+    const void* prefetch_w;
+    int64_t prefetch_ldw;
+    int32_t prefetch_N, prefetch_K, prefetch_stages;
 } ivlm_decode_linear_args;
 IVLM_API int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* args, void* stream);
 /* One-token attention over the paged KV cache: q [B,H*hd], block_table [B,max_pages], seq_lens [B]

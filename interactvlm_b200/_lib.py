@@ -59,6 +59,8 @@ class DecodeLinearArgs(C.Structure):
         ("positions", C.c_void_p), ("slot_map", C.c_void_p), ("cos_t", C.c_void_p), ("sin_t", C.c_void_p),
         ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
         ("H", C.c_int32), ("hd", C.c_int32), ("page_size", C.c_int32),
+        ("prefetch_w", C.c_void_p), ("prefetch_ldw", C.c_int64),
+        ("prefetch_N", C.c_int32), ("prefetch_K", C.c_int32), ("prefetch_stages", C.c_int32),
     ]
 
 

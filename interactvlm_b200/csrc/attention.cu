@@ -494,19 +494,161 @@ __global__ void __launch_bounds__(256) attn_few_queries_kernel(const bf16* __res
     }
 }
 
+// All NQ queries of a (sample, head) in one sweep: the K slice is read ONCE (scores of every query per key row, parked in shared
+// memory as the bf16 values the reference rounds them to), the softmax statistics come from shared memory, the V slice is read
+// ONCE with NQ x 16 accumulators per thread.  The per-query form above reads K three times and V once PER QUERY (27 + 9 sweeps
+// for the 9 decoder tokens: 0.33 ms per launch at 32 views); same rounding points, same per-thread key striding and reduction
+// order (so the outputs are bit-identical to it).
+template <int NQ>
+__global__ void __launch_bounds__(256, 1) attn_few_queries_all_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
+                                                                      const bf16* __restrict__ v, bf16* __restrict__ out,
+                                                                      int q_bcast, int Nq, int Nk, int heads) {
+    constexpr int HD = 16;
+    extern __shared__ __align__(16) uint8_t fq_smem[];
+    bf16* sc = reinterpret_cast<bf16*>(fq_smem);                        // [NQ][Nk] scores, then probabilities
+    float* red = reinterpret_cast<float*>(fq_smem + (size_t)NQ * Nk * 2);   // [8][NQ*HD]
+    float* stat = red + 8 * NQ * HD;                                     // [NQ] max, [NQ] 1/sum
+    const int hh = blockIdx.x, b = blockIdx.y;
+    const int C = heads * HD;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bf16* kb = k + (long long)b * Nk * C + hh * HD;
+    const bf16* vb = v + (long long)b * Nk * C + hh * HD;
+    const float inv_sqrt = sqrtf((float)HD);
+    // ---- pass A: scores of all queries, one read of K
+    {
+        float qr[NQ][HD];
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+            const uint4* qp = reinterpret_cast<const uint4*>(q + ((long long)(q_bcast ? 0 : b) * Nq + (qi < Nq ? qi : 0)) * C + hh * HD);
+#pragma unroll
+            for (int c8 = 0; c8 < HD / 8; ++c8) {
+                const uint4 u = __ldg(qp + c8);
+                const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+                qr[qi][c8 * 8 + 0] = a.x; qr[qi][c8 * 8 + 1] = a.y; qr[qi][c8 * 8 + 2] = bb.x; qr[qi][c8 * 8 + 3] = bb.y;
+                qr[qi][c8 * 8 + 4] = c.x; qr[qi][c8 * 8 + 5] = c.y; qr[qi][c8 * 8 + 6] = e.x; qr[qi][c8 * 8 + 7] = e.y;
+            }
+        }
+        float lmax[NQ];
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) lmax[qi] = -INFINITY;
+        for (int j = threadIdx.x; j < Nk; j += 256) {
+            const uint4* kp = reinterpret_cast<const uint4*>(kb + (long long)j * C);
+            float kr[HD];
+#pragma unroll
+            for (int c8 = 0; c8 < HD / 8; ++c8) {
+                const uint4 u = __ldg(kp + c8);
+                const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+                kr[c8 * 8 + 0] = a.x; kr[c8 * 8 + 1] = a.y; kr[c8 * 8 + 2] = bb.x; kr[c8 * 8 + 3] = bb.y;
+                kr[c8 * 8 + 4] = c.x; kr[c8 * 8 + 5] = c.y; kr[c8 * 8 + 6] = e.x; kr[c8 * 8 + 7] = e.y;
+            }
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+                float d = 0.f;
+#pragma unroll
+                for (int c8 = 0; c8 < HD / 8; ++c8) {
+                    const float* qq = qr[qi] + c8 * 8;
+                    const float* kk = kr + c8 * 8;
+                    d += qq[0] * kk[0] + qq[1] * kk[1] + qq[2] * kk[2] + qq[3] * kk[3] + qq[4] * kk[4] + qq[5] * kk[5] + qq[6] * kk[6] +
+                         qq[7] * kk[7];
+                }
+                d = bf16_round(bf16_round(d) / inv_sqrt);
+                sc[(size_t)qi * Nk + j] = __float2bfloat16_rn(d);
+                lmax[qi] = fmaxf(lmax[qi], d);
+            }
+        }
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+            const float m = warp_max(lmax[qi]);
+            if (lane == 0) red[warp * NQ + qi] = m;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        float m = red[threadIdx.x];
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w * NQ + threadIdx.x]);
+        stat[threadIdx.x] = m;
+    }
+    __syncthreads();
+    // ---- pass B: sum of exp per query (shared memory only), then probabilities in place
+    {
+        float lsum[NQ];
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) lsum[qi] = 0.f;
+        for (int j = threadIdx.x; j < Nk; j += 256) {
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) lsum[qi] += __expf(__bfloat162float(sc[(size_t)qi * Nk + j]) - stat[qi]);
+        }
+        __syncthreads();   // every thread has read the maxima' partials out of red
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+            const float t = warp_sum(lsum[qi]);
+            if (lane == 0) red[warp * NQ + qi] = t;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w * NQ + threadIdx.x];
+        stat[NQ + threadIdx.x] = 1.f / t;
+    }
+    __syncthreads();
+    // ---- pass C: probabilities (bf16, like the reference) times V, one read of V
+    float acc[NQ][HD];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+        for (int c = 0; c < HD; ++c) acc[qi][c] = 0.f;
+    for (int j = threadIdx.x; j < Nk; j += 256) {
+        const uint4* vp = reinterpret_cast<const uint4*>(vb + (long long)j * C);
+        float vr[HD];
+#pragma unroll
+        for (int c8 = 0; c8 < HD / 8; ++c8) {
+            const uint4 u = __ldg(vp + c8);
+            const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+            vr[c8 * 8 + 0] = a.x; vr[c8 * 8 + 1] = a.y; vr[c8 * 8 + 2] = bb.x; vr[c8 * 8 + 3] = bb.y;
+            vr[c8 * 8 + 4] = c.x; vr[c8 * 8 + 5] = c.y; vr[c8 * 8 + 6] = e.x; vr[c8 * 8 + 7] = e.y;
+        }
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+            const float pr = bf16_round(__expf(__bfloat162float(sc[(size_t)qi * Nk + j]) - stat[qi]) * stat[NQ + qi]);
+#pragma unroll
+            for (int c = 0; c < HD; ++c) acc[qi][c] += pr * vr[c];
+        }
+    }
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+        for (int c = 0; c < HD; ++c) {
+            const float t = warp_sum(acc[qi][c]);
+            if (lane == 0) red[warp * (NQ * HD) + qi * HD + c] = t;
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Nq * HD; i += 256) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w * (NQ * HD) + i];
+        const int qi = i / HD, c = i % HD;
+        out[((long long)b * Nq + qi) * C + hh * HD + c] = __float2bfloat16_rn(t);
+    }
+}
+
 // Many queries, few keys (<=16): thread per (query, head), head fastest so q/out accesses are contiguous.
+// Keys / values sit in shared memory as fp32 with one float of padding per head slice (8 heads at stride HD are 4 bank groups
+// otherwise); the score array is indexed by unrolled loops only, so it stays in registers (a run-time key count used to put it
+// in local memory: 0.15 ms per launch for 67 MB of traffic).
 template <int HD>
 __global__ void __launch_bounds__(256) attn_few_keys_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
                                                             const bf16* __restrict__ v, bf16* __restrict__ out, int Nq,
                                                             int Nk, int heads) {
     const int b = blockIdx.y;
     const int C = heads * HD;
-    extern __shared__ float kv_s[];  // k [Nk][C], v [Nk][C] as fp32
+    constexpr int HP = HD + 1;
+    extern __shared__ float kv_s[];  // k [Nk][heads][HD+1], v likewise, as fp32
     float* ks = kv_s;
-    float* vs = kv_s + Nk * C;
+    float* vs = kv_s + Nk * heads * HP;
     for (int i = threadIdx.x; i < Nk * C; i += blockDim.x) {
-        ks[i] = __bfloat162float(k[(long long)b * Nk * C + i]);
-        vs[i] = __bfloat162float(v[(long long)b * Nk * C + i]);
+        const int o = (i / HD) * HP + (i % HD);
+        ks[o] = __bfloat162float(k[(long long)b * Nk * C + i]);
+        vs[o] = __bfloat162float(v[(long long)b * Nk * C + i]);
     }
     __syncthreads();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -525,27 +667,39 @@ __global__ void __launch_bounds__(256) attn_few_keys_kernel(const bf16* __restri
     const float inv_sqrt = sqrtf((float)HD);
     float sc[16];
     float mx = -INFINITY;
-    for (int j = 0; j < Nk; ++j) {
-        float d = 0.f;
 #pragma unroll
-        for (int c = 0; c < HD; ++c) d += qr[c] * ks[j * C + hh * HD + c];
-        d = bf16_round(bf16_round(d) / inv_sqrt);
-        sc[j] = d;
-        mx = fmaxf(mx, d);
+    for (int j = 0; j < 16; ++j) {
+        sc[j] = -INFINITY;
+        if (j < Nk) {
+            const float* kj = ks + (j * heads + hh) * HP;
+            float d = 0.f;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) d += qr[c] * kj[c];
+            d = bf16_round(bf16_round(d) / inv_sqrt);
+            sc[j] = d;
+            mx = fmaxf(mx, d);
+        }
     }
     float sum = 0.f;
-    for (int j = 0; j < Nk; ++j) {
-        sc[j] = __expf(sc[j] - mx);
-        sum += sc[j];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (j < Nk) {
+            sc[j] = __expf(sc[j] - mx);
+            sum += sc[j];
+        }
     }
     const float inv = 1.f / sum;
     float acc[HD];
 #pragma unroll
     for (int c = 0; c < HD; ++c) acc[c] = 0.f;
-    for (int j = 0; j < Nk; ++j) {
-        const float pr = bf16_round(sc[j] * inv);
 #pragma unroll
-        for (int c = 0; c < HD; ++c) acc[c] += pr * vs[j * C + hh * HD + c];
+    for (int j = 0; j < 16; ++j) {
+        if (j < Nk) {
+            const float pr = bf16_round(sc[j] * inv);
+            const float* vj = vs + (j * heads + hh) * HP;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) acc[c] += pr * vj[c];
+        }
     }
     uint4* op = reinterpret_cast<uint4*>(out + ((long long)b * Nq + qi) * C + hh * HD);
 #pragma unroll
@@ -657,7 +811,7 @@ extern "C" int ivlm_attn_small_bf16(ivlm_handle h, const void* q, const void* k,
     IVLM_REQUIRE(hd == 16 || hd == 32, "attn_small: head_dim %d not instantiated (16, 32)", hd);
     if (Nk <= 16) {
         IVLM_REQUIRE(!q_bcast, "attn_small: broadcast q unsupported in the few-keys form");
-        const size_t smem = (size_t)2 * Nk * heads * hd * sizeof(float);
+        const size_t smem = (size_t)2 * Nk * heads * (hd + 1) * sizeof(float);
         dim3 grid((unsigned)(((long long)Nq * heads + 255) / 256), B);
         if (hd == 16)
             attn_few_keys_kernel<16><<<grid, 256, smem, stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v,
@@ -668,7 +822,22 @@ extern "C" int ivlm_attn_small_bf16(ivlm_handle h, const void* q, const void* k,
     } else {
         IVLM_REQUIRE(Nq <= 64, "attn_small: needs Nq <= 64 or Nk <= 16 (got Nq=%d Nk=%d)", Nq, Nk);
         dim3 grid(heads, B);
-        if (hd == 16)
+        // all queries in one sweep when the [NQ][Nk] bf16 score tile fits in shared memory (the SAM decoder: 9 tokens x 4096 keys)
+        const int nq_t = Nq <= 10 ? 10 : 16;
+        const size_t smem_all = (size_t)nq_t * Nk * 2 + (size_t)(8 * nq_t * 16 + 2 * nq_t) * sizeof(float);
+        if (hd == 16 && Nq <= 16 && smem_all <= 200 * 1024 && h->attn_small_variant == 0) {
+            if (!(h->attr_done & (1ull << 21))) {
+                IVLM_CHECK_CUDA(cudaFuncSetAttribute(attn_few_queries_all_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                IVLM_CHECK_CUDA(cudaFuncSetAttribute(attn_few_queries_all_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                h->attr_done |= 1ull << 21;
+            }
+            if (nq_t == 10)
+                attn_few_queries_all_kernel<10><<<grid, 256, smem_all, stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out,
+                                                                               q_bcast, Nq, Nk, heads);
+            else
+                attn_few_queries_all_kernel<16><<<grid, 256, smem_all, stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out,
+                                                                               q_bcast, Nq, Nk, heads);
+        } else if (hd == 16)
             attn_few_queries_kernel<16><<<grid, 256, 0, stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v,
                                                                   (bf16*)out, q_bcast, Nq, Nk, heads);
         else

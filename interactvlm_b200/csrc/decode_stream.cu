@@ -55,6 +55,9 @@ struct DecodeStreamParams {
     int resident;                    // 1: the whole activation sits in shared memory (required with gamma)
     int nstages;                     // ring depth in use (<= DS_STAGES; option "ds_stages")
     float* partial; int* flags;
+    // L2 prefetch of the SUCCESSOR's weights (the next launch of the decode chain): the first pf_n stages of the range its CTA
+    // with this index will stream, requested once this CTA's own last stage is on its way
+    const uint8_t* pf_w; long long pf_pitch; int pf_N, pf_rowbytes, pf_spt, pf_total, pf_grid, pf_n;
 };
 
 IVLM_DEVINL void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t policy) {
@@ -62,6 +65,9 @@ IVLM_DEVINL void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
         : "memory");
+}
+IVLM_DEVINL void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 IVLM_DEVINL void ldmatrix_x2(uint32_t& r0, uint32_t& r1, const void* smem_row) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(smem_row)));
@@ -134,6 +140,24 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             }
         } else {
             pdl_launch();
+        }
+        // The HBM pipe would idle from here to the successor's first loads (this CTA's tail, the launch hand-over, the successor's
+        // RMSNorm prologue): lanes 0-15 ask L2 for the rows of the stages the successor's CTA `cta` starts with.  Row segments of
+        // a tile are contiguous ((kb - ka) KB per row), so a stage range costs 16 requests per tile touched.
+        __syncwarp();
+        if (p.pf_w != nullptr && cta < p.pf_grid && lane < DS_ROWS) {
+            const int q0 = (int)((long long)p.pf_total * cta / p.pf_grid);
+            const int q1 = min(q0 + p.pf_n, (int)((long long)p.pf_total * (cta + 1) / p.pf_grid));
+            if (q1 > q0) {
+                const int t_first = q0 / p.pf_spt, t_last = (q1 - 1) / p.pf_spt;
+                for (int tl = t_first; tl <= t_last; ++tl) {
+                    const int ka = (tl == t_first) ? q0 - tl * p.pf_spt : 0;
+                    const int kb = (tl == t_last) ? q1 - tl * p.pf_spt : p.pf_spt;
+                    const int row = tl * DS_ROWS + lane;
+                    const int b0 = ka * (DS_KW * 2), b1 = min(kb * (DS_KW * 2), p.pf_rowbytes);
+                    if (row < p.pf_N && b1 > b0) l2_prefetch_bulk(p.pf_w + (long long)row * p.pf_pitch + b0, (uint32_t)(b1 - b0));
+                }
+            }
         }
         return;
     }
@@ -403,6 +427,21 @@ extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* 
     int grid = h->num_sms < p.tiles ? h->num_sms : p.tiles;
     p.partial = reinterpret_cast<float*>(h->ws + IVLM_WS_COUNTER_BYTES);
     p.flags = reinterpret_cast<int*>(h->ws + DS_FLAG_OFFSET_BYTES);
+    if (a->prefetch_w != nullptr && a->prefetch_N > 0 && a->prefetch_K > 0 && h->ds_prefetch_kb != 0) {
+        IVLM_REQUIRE((reinterpret_cast<uintptr_t>(a->prefetch_w) & 15) == 0 && (a->prefetch_ldw * 2) % 16 == 0 && a->prefetch_K % 8 == 0,
+                     "decode_linear: the prefetched matrix must be 16-byte aligned with 16-byte row pitches");
+        p.pf_w = reinterpret_cast<const uint8_t*>(a->prefetch_w); p.pf_pitch = a->prefetch_ldw * 2;
+        p.pf_N = a->prefetch_N; p.pf_rowbytes = a->prefetch_K * 2;
+        const int ptiles = (a->prefetch_N + DS_ROWS - 1) / DS_ROWS;
+        p.pf_spt = (a->prefetch_K + DS_KW - 1) / DS_KW;
+        p.pf_total = ptiles * p.pf_spt;
+        p.pf_grid = h->num_sms < ptiles ? h->num_sms : ptiles;       // the successor's grid (same rule as below)
+        // per-CTA budget in 16 KB stages: the caller's request, capped by the option (default 256 KB: 37 MB over 148 SMs)
+        const int cap_st = (h->ds_prefetch_kb > 0 ? h->ds_prefetch_kb : 256) / (DS_W_BYTES / 1024);
+        const int want = a->prefetch_stages > 0 ? a->prefetch_stages : cap_st;
+        p.pf_n = h->ds_prefetch_kb > 0 ? (want < cap_st ? want : cap_st) : want;
+        if (p.pf_n <= 0) p.pf_w = nullptr;
+    }
     if (!(h->attr_done & (1ull << 20))) {
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));

@@ -106,6 +106,92 @@ __global__ void __launch_bounds__(128) upscale_hyper_dot_kernel(const bf16* __re
     lowres[((long long)bv * LR + Y) * LR + X] = bf16_round(m);
 }
 
+// The same computation as a tensor-core GEMM [pixels, 64] x [64, 4*32] with the bias / GELU / hypernetwork dot as its epilogue
+// (mma.sync m16n8k16: K = 64 and 2 KB of operands per 16-pixel tile leave nothing for a TMA / tcgen05 pipeline to hide; the
+// launch reads up1 once -- 67 MB at 32 views -- and writes 8 MB).  The scalar kernel above spends 2048 shared-memory-fed FMAs per
+// pixel (0.42-0.54 ms per launch); it stays as the option-selected A/B form.  The k index is permuted consistently in both
+// operands (physical k = 16 t + 4 ks + e for fragment slot e of k-step ks) so that a thread's A fragments are the 32 contiguous
+// bytes it loads with two 16-byte requests and its B fragments one 16-byte shared-memory read per two k-steps.
+constexpr int UH_PITCH = 72;   // bf16 per weight row in shared memory: 36 words -> conflict-free 16-byte fragment reads
+__global__ void __launch_bounds__(128) upscale_hyper_dot_mma_kernel(const bf16* __restrict__ up1, const bf16* __restrict__ w2,
+                                                                    const bf16* __restrict__ b2, const bf16* __restrict__ hyper,
+                                                                    float* __restrict__ lowres, int G, int tiles_per_cta) {
+    __shared__ __align__(16) bf16 w_s[128 * UH_PITCH];
+    __shared__ float b_s[32], h_s[32];
+    const int bv = blockIdx.y;
+    for (int i = threadIdx.x; i < 128 * 8; i += blockDim.x) {   // 128 rows x 8 chunks of 16 bytes
+        const int n = i >> 3, c8 = i & 7;
+        *reinterpret_cast<uint4*>(w_s + n * UH_PITCH + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(w2) + i);
+    }
+    if (threadIdx.x < 32) {
+        b_s[threadIdx.x] = __bfloat162float(b2[threadIdx.x]);
+        h_s[threadIdx.x] = __bfloat162float(hyper[bv * 32 + threadIdx.x]);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const long long nvec = (long long)G * G * 4;
+    const int LR = G * 4;
+    const long long tile0 = (long long)blockIdx.x * tiles_per_cta;
+    for (int it = warp; it < tiles_per_cta; it += 4) {
+        const long long r0 = (tile0 + it) * 16 + g, r1 = r0 + 8;
+        if ((tile0 + it) * 16 >= nvec) break;
+        uint4 a0lo = make_uint4(0, 0, 0, 0), a0hi = a0lo, a1lo = a0lo, a1hi = a0lo;
+        if (r0 < nvec) {
+            const uint4* p0 = reinterpret_cast<const uint4*>(up1 + ((long long)bv * nvec + r0) * 64 + t * 16);
+            a0lo = __ldg(p0); a0hi = __ldg(p0 + 1);
+        }
+        if (r1 < nvec) {
+            const uint4* p1 = reinterpret_cast<const uint4*>(up1 + ((long long)bv * nvec + r1) * 64 + t * 16);
+            a1lo = __ldg(p1); a1hi = __ldg(p1 + 1);
+        }
+        // fragment registers of k-step ks: {row g: slots 0-1, row g+8: slots 0-1, row g: slots 2-3, row g+8: slots 2-3}
+        const uint32_t af[4][4] = {{a0lo.x, a1lo.x, a0lo.y, a1lo.y}, {a0lo.z, a1lo.z, a0lo.w, a1lo.w},
+                                   {a0hi.x, a1hi.x, a0hi.y, a1hi.y}, {a0hi.z, a1hi.z, a0hi.w, a1hi.w}};
+        float m0[4] = {0.f, 0.f, 0.f, 0.f}, m1[4] = {0.f, 0.f, 0.f, 0.f};   // per second-stage sub-pixel p2: rows g, g+8
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint4* bp = reinterpret_cast<const uint4*>(w_s + (j * 8 + g) * UH_PITCH + t * 16);
+            const uint4 blo = bp[0], bhi = bp[1];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_bf16_16816(acc, af[0], blo.x, blo.y);
+            mma_bf16_16816(acc, af[1], blo.z, blo.w);
+            mma_bf16_16816(acc, af[2], bhi.x, bhi.y);
+            mma_bf16_16816(acc, af[3], bhi.z, bhi.w);
+            const int c = (j & 3) * 8 + 2 * t;
+            const float bz0 = b_s[c], bz1 = b_s[c + 1], h0 = h_s[c], h1 = h_s[c + 1];
+            const float z00 = bf16_round(apply_act(bf16_round(acc[0] + bz0), ACT_GELU));
+            const float z01 = bf16_round(apply_act(bf16_round(acc[1] + bz1), ACT_GELU));
+            const float z10 = bf16_round(apply_act(bf16_round(acc[2] + bz0), ACT_GELU));
+            const float z11 = bf16_round(apply_act(bf16_round(acc[3] + bz1), ACT_GELU));
+            m0[j >> 2] += h0 * z00 + h1 * z01;
+            m1[j >> 2] += h0 * z10 + h1 * z11;
+        }
+#pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) {
+            m0[p2] += __shfl_xor_sync(0xffffffffu, m0[p2], 1);
+            m0[p2] += __shfl_xor_sync(0xffffffffu, m0[p2], 2);
+            m1[p2] += __shfl_xor_sync(0xffffffffu, m1[p2], 1);
+            m1[p2] += __shfl_xor_sync(0xffffffffu, m1[p2], 2);
+        }
+        // lane t stores sub-pixel p2 = t of both rows
+        const float v0 = t == 0 ? m0[0] : t == 1 ? m0[1] : t == 2 ? m0[2] : m0[3];
+        const float v1 = t == 0 ? m1[0] : t == 1 ? m1[1] : t == 2 ? m1[2] : m1[3];
+        const int p2 = t;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const long long vec = half ? r1 : r0;
+            if (vec >= nvec) continue;
+            const long long tok = vec >> 2;
+            const int p1 = (int)(vec & 3);
+            const int y = (int)(tok / G), x = (int)(tok % G);
+            const int Y = (y * 2 + (p1 >> 1)) * 2 + (p2 >> 1);
+            const int X = (x * 2 + (p1 & 1)) * 2 + (p2 & 1);
+            lowres[((long long)bv * LR + Y) * LR + X] = bf16_round(half ? v1 : v0);
+        }
+    }
+}
+
 // Device-side bookkeeping of the greedy / scripted decode loop, so that a decode step is a pure graph replay.
 // state[0] = number of tokens fed so far (advanced here), state[1] = the step the rest of this replay works on.
 __global__ void decode_prepare_kernel(int* __restrict__ state, int S, const int* __restrict__ S_rows, const int* __restrict__ scripted, int G,
@@ -194,9 +280,17 @@ extern "C" int ivlm_upscale_hyper_dot(ivlm_handle h, const void* up1, const void
                                       float* lowres, int32_t Bv, int32_t grid_, void* stream) {
     IVLM_REQUIRE(h && Bv > 0 && grid_ > 0, "upscale_hyper_dot: empty");
     const long long nvec = (long long)grid_ * grid_ * 4;
-    dim3 grid((unsigned)((nvec + 31) / 32), Bv);
-    upscale_hyper_dot_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        (const bf16*)up1, (const bf16*)w2, (const bf16*)b2, (const bf16*)hyper, lowres, grid_);
+    if (h->attn_small_variant == 0 && (reinterpret_cast<uintptr_t>(up1) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0) {
+        const long long tiles = (nvec + 15) / 16;
+        const int per_cta = tiles >= 64 ? 16 : 4;
+        dim3 grid((unsigned)((tiles + per_cta - 1) / per_cta), Bv);
+        upscale_hyper_dot_mma_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            (const bf16*)up1, (const bf16*)w2, (const bf16*)b2, (const bf16*)hyper, lowres, grid_, per_cta);
+    } else {
+        dim3 grid((unsigned)((nvec + 31) / 32), Bv);
+        upscale_hyper_dot_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            (const bf16*)up1, (const bf16*)w2, (const bf16*)b2, (const bf16*)hyper, lowres, grid_);
+    }
     h->launches++;
     IVLM_CHECK_CUDA(cudaGetLastError());
     return IVLM_OK;

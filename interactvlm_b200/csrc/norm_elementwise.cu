@@ -446,6 +446,27 @@ __global__ void bilinear_kernel(const float* __restrict__ src, float* __restrict
     }
 }
 
+// Row-blocked form for dw % 4 == 0 and 16-byte aligned planes: one thread per four consecutive outputs of one row -- no 64-bit
+// divisions (the generic kernel spends ~400 instructions per element on them: 0.56 TB/s), one 16-byte streaming store per thread,
+// the source rows (1/16 of the output at x4) stay in L1/L2.  Same tap arithmetic -> bit-identical to bilinear_kernel.
+__global__ void __launch_bounds__(256)
+bilinear_rows4_kernel(const float* __restrict__ src, float* __restrict__ dst, int sh, int sw, int ch, int cw, int dh, int dw) {
+    const float sy = (float)ch / (float)dh, sx = (float)cw / (float)dw;
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;     // group of four output columns
+    if (x4 * 4 >= dw) return;
+    const int y = blockIdx.y;
+    const long long n = blockIdx.z;
+    const float* plane = src + n * (long long)sh * sw;
+    float4 o;
+    float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const BilinearTap t = bilinear_tap(y, x4 * 4 + j, sy, sx, ch, cw, sw);
+        ov[j] = bilinear_eval(t, plane);
+    }
+    __stcs(reinterpret_cast<float4*>(dst + (n * dh + y) * (long long)dw) + x4, o);
+}
+
 // ------------------------------------------------------------------------------------------------ camera gate
 // One CTA of 256 threads per (sample, view). Every nn.Linear output is rounded to bf16 like the reference.
 __global__ void cam_gate_kernel(const bf16* __restrict__ cam, const bf16* __restrict__ emb, const bf16* __restrict__ w1,
@@ -682,8 +703,13 @@ extern "C" int ivlm_argmax_f32(ivlm_handle h, const float* logits, int32_t* out,
 extern "C" int ivlm_bilinear_f32(ivlm_handle h, const float* src, float* dst, int32_t N, int32_t sh, int32_t sw,
                                  int32_t crop_h, int32_t crop_w, int32_t dh, int32_t dw, void* stream) {
     IVLM_REQUIRE(h && crop_h <= sh && crop_w <= sw && crop_h > 0 && crop_w > 0 && N > 0, "bilinear: bad geometry");
-    bilinear_kernel<<<grid_for((long long)N * dh * dw, 256, h->num_sms), 256, 0, STREAM>>>(src, dst, N, sh, sw, crop_h,
-                                                                                         crop_w, dh, dw);
+    if (dw % 4 == 0 && dh <= 65535 && N <= 65535 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int tx = dw / 4 >= 256 ? 256 : ((dw / 4 + 31) / 32) * 32;
+        bilinear_rows4_kernel<<<dim3((dw / 4 + tx - 1) / tx, dh, N), tx, 0, STREAM>>>(src, dst, sh, sw, crop_h, crop_w, dh, dw);
+    } else {
+        bilinear_kernel<<<grid_for((long long)N * dh * dw, 256, h->num_sms), 256, 0, STREAM>>>(src, dst, N, sh, sw, crop_h,
+                                                                                             crop_w, dh, dw);
+    }
     DONE();
 }
 extern "C" int ivlm_cam_gate_bf16(ivlm_handle h, const void* cam, const void* emb, const void* w1, const void* b1,

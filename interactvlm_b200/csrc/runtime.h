@@ -94,6 +94,9 @@ struct ivlm_ctx {
                                   // against 23 / 48 / 52, down_proj 40 / 57 / 62 against 56 / 136 / 130; tools/prof_decode.py variants)
     int small_m_variant = 0;      // 0: weight-streaming mma.sync kernel for token counts <= 64; 1: swapped-operand tcgen05 path
     int global_attn_variant = 0;  // 0: 64-key tiles, 2 CTAs/SM; 1: 128-key tiles, 1 CTA/SM (A/B switch)
+    int attn_small_variant = 0;   // 1: per-query sweeps in the few-queries decoder attention (the round-1 kernel; A/B and bit-identity tests)
+    int ds_prefetch_kb = 0;       // decode_stream L2 prefetch of the successor's weights per CTA: 0 off (default: measured 1-10 % SLOWER on
+                                  // the 13B chain, profiles/r2_decode_layer_ops_in_graph.txt), -1 as the caller asks, > 0 cap in KB
     int ds_stages = 0;            // decode_stream ring depth (0: 6 stages -- 137 vs 139 us per layer with 8 in the same run; A/B knob)
     int dec_warps = 0;            // paged decode attention: warps per CTA (0: 8; 11 or 16 for A/B)
     int attn_prefetch_ahead = 0;  // window attention: L2 prefetch of the successor CTA's tiles, distance in CTAs of the launch order

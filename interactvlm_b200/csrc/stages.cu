@@ -266,20 +266,27 @@ extern "C" int ivlm_llm_decode_step(ivlm_handle h, const ivlm_llm_decode_args* a
         g.epilogue = IVLM_EPI_ROPE_KV; g.out = q; g.ldo = D; g.out_dtype = IVLM_BF16;
         g.positions = a->pos; g.slot_map = a->slot; g.cos_t = cos_t; g.sin_t = sin_t; g.k_cache = a->k_cache[i]; g.v_cache = a->v_cache[i];
         g.H = nh; g.hd = hd; g.page_size = a->page_size;
+        g.prefetch_w = wo; g.prefetch_ldw = D; g.prefetch_N = D; g.prefetch_K = D; g.prefetch_stages = 64;   // all of o_proj: it loads under the attention launch
         IVLM_TRY(ivlm_decode_linear(h, &g, stream));
         IVLM_TRY(ivlm_decode_attention_paged_bf16(h, q, a->k_cache[i], a->v_cache[i], a->block_table, a->seq_lens, o, B, nh, hd, a->page_size,
                                                   a->max_pages, 1.0f / sqrtf((float)hd), stream));
         memset(&g, 0, sizeof(g));
         g.a = o; g.lda = D; g.w = wo; g.ldw = D; g.M = B; g.N = D; g.K = D; g.epilogue = IVLM_EPI_PLAIN; g.residual = x; g.ldr = D;
         g.out = xn; g.ldo = D; g.out_dtype = IVLM_BF16;
+        g.prefetch_w = wgu; g.prefetch_ldw = D; g.prefetch_N = 2 * F; g.prefetch_K = D;
         IVLM_TRY(ivlm_decode_linear(h, &g, stream));
         memset(&g, 0, sizeof(g));
         g.a = xn; g.lda = D; g.w = wgu; g.ldw = D; g.M = B; g.N = 2 * F; g.K = D; g.norm_gamma = ln2; g.norm_eps = d.llm_rms_eps;
         g.epilogue = IVLM_EPI_SWIGLU; g.out = act; g.ldo = F; g.out_dtype = IVLM_BF16;
+        g.prefetch_w = wd; g.prefetch_ldw = F; g.prefetch_N = D; g.prefetch_K = F;
         IVLM_TRY(ivlm_decode_linear(h, &g, stream));
         memset(&g, 0, sizeof(g));
         g.a = act; g.lda = F; g.w = wd; g.ldw = F; g.M = B; g.N = D; g.K = F; g.epilogue = IVLM_EPI_PLAIN; g.residual = xn; g.ldr = D;
         g.out = x; g.ldo = D; g.out_dtype = IVLM_BF16;
+        if (i + 1 < d.llm_layers) {
+            IVLM_W(wqkv_next, "llm." + std::to_string(i + 1) + ".wqkv");
+            g.prefetch_w = wqkv_next; g.prefetch_ldw = D; g.prefetch_N = 3 * D; g.prefetch_K = D;
+        }
         IVLM_TRY(ivlm_decode_linear(h, &g, stream));
     }
     IVLM_W(norm, "llm.norm"); IVLM_W(lm_head, "llm.lm_head");

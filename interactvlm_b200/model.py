@@ -214,6 +214,7 @@ class _Engine:
         self.stage_abi = not getattr(ctx, "emulated", False)
         self._bind()
         self.skip_pad_rows = True  # SAM window blocks: GEMMs on the real tokens only (the padded rows' q/k/v are the bias)
+        self.decode_prefetch_wo = 64   # 16 KB stages of o_proj per SM requested into L2 by the qkv launch (1 MB: all of a 13B o_proj)
         self.fused_decode = True   # decode steps of <= 8 tokens through ivlm_decode_linear (5 launches per layer instead of 9)
         self.trace = None  # tests: dict of lists receiving the residual stream after every SAM block / LLaMA prefill layer
 
@@ -455,11 +456,14 @@ class _Engine:
             for i, lw in enumerate(W.llm):
                 rope = dict(positions=st["pos"], slot_map=st["slot"], cos=W.rope_cos, sin=W.rope_sin, k_cache=st["k"][i],
                             v_cache=st["v"][i], H=nh, hd=hd, page_size=PAGE)
-                q = ctx.decode_linear(x, lw["wqkv"], gamma=lw["ln1"], eps=cfg.rms_norm_eps, epilogue=EPI_ROPE_KV, rope=rope)
+                # every launch asks L2 for the head of its successor's weights (wo: all of it, it loads under the attention launch)
+                nxt = W.llm[i + 1]["wqkv"] if i + 1 < len(W.llm) else W.lm_head
+                q = ctx.decode_linear(x, lw["wqkv"], gamma=lw["ln1"], eps=cfg.rms_norm_eps, epilogue=EPI_ROPE_KV, rope=rope,
+                                      prefetch=lw["wo"], prefetch_stages=self.decode_prefetch_wo)
                 o = ctx.decode_attention(q, st["k"][i], st["v"][i], st["block_table"], st["seq_lens"], nh, hd, PAGE)
-                x = ctx.decode_linear(o, lw["wo"], residual=x)
-                y = ctx.decode_linear(x, lw["wgu"], gamma=lw["ln2"], eps=cfg.rms_norm_eps, epilogue=EPI_SWIGLU)
-                x = ctx.decode_linear(y, lw["wd"], residual=x)
+                x = ctx.decode_linear(o, lw["wo"], residual=x, prefetch=lw["wgu"])
+                y = ctx.decode_linear(x, lw["wgu"], gamma=lw["ln2"], eps=cfg.rms_norm_eps, epilogue=EPI_SWIGLU, prefetch=lw["wd"])
+                x = ctx.decode_linear(y, lw["wd"], residual=x, prefetch=nxt)
         else:
             for i, lw in enumerate(W.llm):
                 y = ctx.rmsnorm(x, lw["ln1"], cfg.rms_norm_eps)

@@ -279,10 +279,11 @@ class Context:
         return out
 
     def decode_linear(self, a, w, gamma=None, eps=0.0, epilogue=L.EPI_PLAIN, act=ACT_NONE, bias=None, residual=None, out=None,
-                      out_dtype=torch.bfloat16, rope=None):
+                      out_dtype=torch.bfloat16, rope=None, prefetch=None, prefetch_stages=0):
         """Weight-streaming linear layer of a decode step, M <= 8 tokens (ivlm_decode_linear): optional fused RMSNorm of `a`,
         epilogue PLAIN / SWIGLU (w rows interleaved) / ROPE_KV (w q,k rows paired; rope = dict(positions, slot_map, cos, sin,
-        k_cache, v_cache, H, hd, page_size))."""
+        k_cache, v_cache, H, hd, page_size)).  `prefetch` = the weight matrix of the next decode_linear launch (its first
+        stages are requested into L2 at the end of this one; prefetch_stages 16 KB stages per SM, 0 = library default)."""
         _bf16(a, "a"); _bf16(w, "w")
         M, K = a.shape
         N = w.shape[0]
@@ -308,6 +309,11 @@ class Context:
             g.cos_t, g.sin_t = rope["cos"].data_ptr(), rope["sin"].data_ptr()
             g.k_cache, g.v_cache = rope["k_cache"].data_ptr(), rope["v_cache"].data_ptr()
             g.H, g.hd, g.page_size = rope["H"], rope["hd"], rope["page_size"]
+        if prefetch is not None:
+            _bf16(prefetch, "prefetch")
+            assert prefetch.dim() == 2 and prefetch.stride(1) == 1
+            g.prefetch_w, g.prefetch_ldw = prefetch.data_ptr(), prefetch.stride(0)
+            g.prefetch_N, g.prefetch_K, g.prefetch_stages = prefetch.shape[0], prefetch.shape[1], int(prefetch_stages)
         L.check(self.lib.ivlm_decode_linear(self.h, C.byref(g), self.stream), "decode_linear")
         return out
 

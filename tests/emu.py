@@ -147,7 +147,7 @@ class EmuContext:
         return (_r(F.silu(gate.float())) * up.float()).to(BF)
 
     def decode_linear(self, a, w, gamma=None, eps=0.0, epilogue=0, act=ACT_NONE, bias=None, residual=None, out=None, out_dtype=BF,
-                      rope=None):
+                      rope=None, prefetch=None, prefetch_stages=0):
         """ivlm_decode_linear: rmsnorm? -> linear -> PLAIN / SWIGLU (interleaved rows) / ROPE_KV (paired q, k rows)."""
         assert a.shape[0] <= 8 and a.shape[1] % 16 == 0
         x = self.rmsnorm(a, gamma, eps) if gamma is not None else a

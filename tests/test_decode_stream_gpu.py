@@ -124,3 +124,17 @@ def test_fused_decode_step_equals_unfused_chain(ctx):
     n = outs[True][0].shape[1] - 1 + cfg.img_emb_len
     assert rel_err(outs[True][1][:, :n], outs[False][1][:, :n]) < 1e-2     # different GEMM kernels: bf16-level differences only
     assert outs[True][2] < outs[False][2]
+
+
+@pytest.mark.parametrize("nxt_shape,stages", [((5120, 5120), 64), ((27648, 5120), 0), ((5120, 13824), 0), ((40, 256), 3), ((2000, 1088), 1000)])
+def test_l2_prefetch_of_the_successor_does_not_change_results(ctx, nxt_shape, stages):
+    """prefetch_w only issues cp.async.bulk.prefetch.L2 requests: outputs are bit-identical with it, without it and with the
+    option that disables it, for successor shapes with ragged tiles / stages and fewer tiles than SMs."""
+    M, N, K = 8, 5120, 5120
+    a, w, res = rnd(M, K, seed=21), rnd(N, K, scale=K ** -0.5, seed=22), rnd(M, N, seed=23)
+    nxt = rnd(*nxt_shape, scale=0.02, seed=24)
+    base = ctx.decode_linear(a, w, residual=res)
+    for kb in (-1, 64, 0):                                   # as asked / capped / off (the default)
+        ctx.set_option("ds_prefetch_kb", kb)
+        assert torch.equal(ctx.decode_linear(a, w, residual=res, prefetch=nxt, prefetch_stages=stages), base)
+    torch.cuda.synchronize()

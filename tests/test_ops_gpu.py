@@ -256,6 +256,20 @@ def test_attn_small(ctx):
         vf = v.float().reshape(B, Nk, heads, hd).transpose(1, 2)
         ref = ((qf @ kf.transpose(-1, -2) / math.sqrt(hd)).softmax(-1) @ vf).transpose(1, 2).reshape(B, Nq, Cc)
         assert rel_err(out, ref) < 2e-2, (Bq, B, Nq, Nk, Cc)
+        if Nk > 16 and hd == 16:
+            # all-queries-in-one-sweep kernel against the per-query form it replaces: same rounding points and reduction order
+            ctx.set_option("attn_small_variant", 1)
+            old = ctx.attn_small(q, k, v, heads)
+            ctx.set_option("attn_small_variant", 0)
+            assert (out.float() - old.float()).abs().max().item() <= 2 ** -8 * old.float().abs().max().item()
+            assert rel_err(out, old) < 1e-3
+    # more than 10 queries (second instantiation), ragged key count
+    q, k, v = rnd(3, 13, 128, seed=58), rnd(3, 1000, 128, seed=59), rnd(3, 1000, 128, seed=60)
+    out = ctx.attn_small(q, k, v, heads)
+    ctx.set_option("attn_small_variant", 1)
+    old = ctx.attn_small(q, k, v, heads)
+    ctx.set_option("attn_small_variant", 0)
+    assert rel_err(out, old) < 1e-3
 
 
 def test_llm_glue(ctx):
@@ -323,6 +337,13 @@ def test_bilinear_matches_torch(ctx):
     out = ctx.bilinear(src, 300, 500, crop_h=200, crop_w=256)
     ref = torch.nn.functional.interpolate(src[None, :, :200, :256], (300, 500), mode="bilinear", align_corners=False)[0]
     assert (out - ref).abs().max().item() < 1e-5
+    # the row-blocked float4 kernel (aligned output, width % 4 == 0) and the generic one (here: a 4-byte-offset output) agree bit for bit
+    buf = torch.empty(3 * 300 * 500 + 1, device=DEV)
+    generic = ctx.bilinear(src, 300, 500, crop_h=200, crop_w=256, out=buf[1:].view(3, 300, 500))
+    assert torch.equal(generic, out)
+    out = ctx.bilinear(src, 77, 133)                                            # width % 4 != 0 -> generic kernel
+    ref = torch.nn.functional.interpolate(src[None], (77, 133), mode="bilinear", align_corners=False)[0]
+    assert (out - ref).abs().max().item() < 1e-5
 
 
 def test_cam_gate(ctx):
@@ -348,3 +369,16 @@ def test_upscale_hyper_dot(ctx):
     m = torch.einsum("btpqc,bc->btpq", z, hyper.float())  # [Bv, G*G, p1, p2]
     m = m.view(Bv, G, G, 2, 2, 2, 2).permute(0, 1, 3, 5, 2, 4, 6).reshape(Bv, G * 4, G * 4)
     assert rel_err(out, m) < 1e-2
+    ctx.set_option("attn_small_variant", 1)                 # the scalar form of the kernel (A/B option)
+    old = ctx.upscale_hyper_dot(up1, w2, b2, hyper, Bv, G)
+    ctx.set_option("attn_small_variant", 0)
+    assert rel_err(out, old) < 5e-3
+    for Bv, G in ((3, 64), (1, 3)):                         # full SAM grid; a grid whose pixel count is not a multiple of 16
+        up1 = rnd(Bv, G * G, 4, 64, seed=61)
+        hyper = rnd(Bv, 32, seed=62)
+        out = ctx.upscale_hyper_dot(up1, w2, b2, hyper, Bv, G)
+        z = torch.einsum("btpk,qck->btpqc", up1.float(), w2.float()) + b2.float()
+        z = torch.nn.functional.gelu(z.bfloat16().float()).bfloat16().float()
+        m = torch.einsum("btpqc,bc->btpq", z, hyper.float())
+        m = m.view(Bv, G, G, 2, 2, 2, 2).permute(0, 1, 3, 5, 2, 4, 6).reshape(Bv, G * 4, G * 4)
+        assert rel_err(out, m) < 1e-2, (Bv, G)

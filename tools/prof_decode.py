@@ -102,6 +102,29 @@ def fused_chain(i):
     return ctx.decode_linear(y, wd[i % NW], residual=x1)
 
 
+def fused_chain_pf(i, wo_stages=64, stages=0):
+    """fused_chain with every launch requesting the head of its successor's weights into L2 (as model.py drives it)"""
+    rope = dict(positions=pos, slot_map=slot, cos=cos_t, sin=sin_t, k_cache=kc[i % NW], v_cache=vc[i % NW], H=H, hd=hd, page_size=page)
+    q_ = ctx.decode_linear(x, wqkv[i % NW], gamma=gam, eps=1e-5, epilogue=2, rope=rope, prefetch=wo[i % NW], prefetch_stages=wo_stages)
+    o_ = ctx.decode_attention(q_, kc[i % NW], vc[i % NW], bt, sl, H, hd, page)
+    x1 = ctx.decode_linear(o_, wo[i % NW], residual=x, prefetch=wgu[i % NW], prefetch_stages=stages)
+    y = ctx.decode_linear(x1, wgu[i % NW], gamma=gam, eps=1e-5, epilogue=1, prefetch=wd[i % NW], prefetch_stages=stages)
+    return ctx.decode_linear(y, wd[i % NW], residual=x1, prefetch=wqkv[(i + 1) % NW], prefetch_stages=stages)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "prefetch":
+    ctx.set_option("pdl", 1)
+    ctx.set_option("ds_prefetch_kb", -1)   # the prefetch is off by default
+    ref = fused_chain(0).float()
+    print(f"fused chain, no prefetch: {graph_time(fused_chain):7.2f} us per layer", flush=True)
+    for wo_st, st in ((64, 0), (64, 8), (64, 32), (64, 64), (16, 16), (0, 16), (64, 4)):
+        us = graph_time(lambda i: fused_chain_pf(i, wo_st, st))
+        same = bool(torch.equal(fused_chain_pf(0, wo_st, st).float(), ref))
+        print(f"fused chain, L2 prefetch of the successor: wo {wo_st or 16} stages/SM, others {st or 16} stages/SM: {us:7.2f} us per layer; "
+              f"identical output: {same}", flush=True)
+    ctx.set_option("ds_prefetch_kb", 0)
+    ctx.set_option("pdl", 0)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "fused":
     fops = {
         "norm+qkv+rope+kv": (lambda i: ctx.decode_linear(x, wqkv[i % NW], gamma=gam, eps=1e-5, epilogue=2, rope=dict(

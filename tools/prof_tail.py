@@ -44,3 +44,16 @@ timed(lambda: ctx.bilinear(low.view(B * 4, 256, 256), 1024, 1024), "bilinear x4 
 timed(lambda: m(full, LIFT_HUMAN), "lift from 1024^2 logits (warp per vertex-view)", csr + out_b + B * 4 * 1048576 * 4 * 0.18)
 timed(lambda: m.lowres(low, LIFT_HUMAN), "lift from low-res logits (fused bilinear)", csr + out_b + B * 4 * 65536 * 4)
 print(f"nnz {m.nnz}, CSR {csr / 1e6:.1f} MB, batch {B}")
+
+# ---- SAM mask-decoder kernels at the bench shape (32 views): token->image attention (9 queries x 4096 keys, 8 heads of 16),
+# image->token attention (4096 queries x 9 keys), second transposed conv + hypernetwork dot.  Variant 1 = the round-1 kernels.
+nv, heads = B * 4, 8
+rb = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).bfloat16().cuda()
+qt, kt, vt = rb(nv, 9, 128), rb(nv, 4096, 128), rb(nv, 4096, 128)
+up1, w2, b2, hyp = rb(nv, 4096, 4, 64), rb(4, 32, 64, sc=0.2), rb(32), rb(nv, 32)
+for variant, label in ((0, "round 2"), (1, "round 1")):
+    ctx.set_option("attn_small_variant", variant)
+    timed(lambda: ctx.attn_small(qt, kt, vt, heads), f"attn 9 queries x 4096 keys ({label})", (2 * nv * 4096 * 128 + 2 * nv * 9 * 128) * 2)
+    timed(lambda: ctx.upscale_hyper_dot(up1, w2, b2, hyp, nv, 64), f"upscale + hyper dot ({label})", nv * 4096 * 4 * 64 * 2 + nv * 65536 * 4)
+ctx.set_option("attn_small_variant", 0)
+timed(lambda: ctx.attn_small(kt, qt, qt, heads), "attn 4096 queries x 9 keys", 2 * nv * 4096 * 128 * 2)
