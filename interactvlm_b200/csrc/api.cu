@@ -67,6 +67,8 @@ extern "C" int ivlm_set_option(ivlm_handle h, const char* name, int32_t value) {
         h->global_attn_variant = value;
         return IVLM_OK;
     }
+    if (std::string(name) == "dec_prefetch") { h->dec_prefetch = value; return IVLM_OK; }
+    if (std::string(name) == "ds_force_stream") { h->ds_force_stream = value; return IVLM_OK; }
     if (std::string(name) == "dec_warps") { h->dec_warps = value; return IVLM_OK; }
     if (std::string(name) == "ds_stages") { h->ds_stages = value; return IVLM_OK; }
     if (std::string(name) == "attn_small_variant") { h->attn_small_variant = value; return IVLM_OK; }

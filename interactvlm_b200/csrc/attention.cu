@@ -261,7 +261,7 @@ __global__ void sam_relpos_kernel(const bf16* __restrict__ qkv, const bf16* __re
 // 16*HD*2-byte run, and one warp iteration consumes exactly one page with 16/RPI independent 16-byte loads per lane
 // (a single block-table lookup, no per-row index arithmetic).
 constexpr int DEC_PAGE = 16, DEC_MAX_PAGES = 256;
-template <int HD, int DEC_WARPS>
+template <int HD, int DEC_WARPS, bool DEC_L2_PREFETCH>
 __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const bf16* __restrict__ q,
                                                                           const bf16* __restrict__ k_cache,
                                                                           const bf16* __restrict__ v_cache,
@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
     const int sub = lane / LPR, li = lane % LPR;
     const int len = seq_lens[b];
     const int n_pages = (len + DEC_PAGE - 1) / DEC_PAGE;
-    for (int i = threadIdx.x; i < n_pages; i += DEC_WARPS * 32) bt[i] = block_table[(long long)b * max_pages + i];
+    // the whole row of the block table (it exists up to max_pages): no dependency on the seq_lens load above
+    for (int i = threadIdx.x; i < max_pages; i += DEC_WARPS * 32) bt[i] = block_table[(long long)b * max_pages + i];
     float qr[8];
     {
         const uint4 u = *reinterpret_cast<const uint4*>(q + ((long long)b * H + h) * HD + li * 8);
@@ -291,28 +292,55 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
     }
     __syncthreads();
     const long long lane_off = (long long)sub * HD + li * 8;  // this lane's element offset inside a (page, head) run
-    // ---- phase 1: scores
+    // Experiment kept as an option (off): every K and V line this warp will touch is requested into L2 up front (one request per
+    // 128-byte line) so that the page loops below -- one page per iteration, few registers, three CTAs resident per SM -- would not
+    // pay an HBM round trip per iteration.  Measured 19.6 us against 16.0 us per layer: slower.
+    if (DEC_L2_PREFETCH && (li & 7) == 0) {
+        for (int pg = warp; pg < n_pages; pg += DEC_WARPS) {
+            const long long o = ((long long)bt[pg] * H + h) * (DEC_PAGE * HD) + lane_off;
+            const int k0 = pg * DEC_PAGE;
+#pragma unroll
+            for (int u = 0; u < NLD; ++u)
+                if (k0 + u * RPI + sub < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(k_cache + o + u * RPI * HD));
+#pragma unroll
+            for (int u = 0; u < NLD; ++u)
+                if (k0 + u * RPI + sub < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(v_cache + o + u * RPI * HD));
+        }
+    }
+    // ---- phase 1: scores.  The loops of both phases are software pipelined over HALF pages with two register buffers: the loads
+    // of unit i+1 are in flight while unit i is reduced, so a warp keeps requests outstanding all the time.  With one page per
+    // iteration all 320 CTAs issued a burst, waited out the HBM latency, computed, and issued the next burst (DRAM 40 % busy).
+    constexpr int UL = NLD / 2;                 // loads per unit (half a page)
+    const int my_pages = n_pages > warp ? (n_pages - warp + DEC_WARPS - 1) / DEC_WARPS : 0;
+    const int nU = 2 * my_pages;
+    uint4 bufA[UL], bufB[UL];
+    auto unit_k0 = [&](int ui) { return (warp + (ui >> 1) * DEC_WARPS) * DEC_PAGE + (ui & 1) * UL * RPI; };
+    auto unit_off = [&](int ui) {
+        return ((long long)bt[warp + (ui >> 1) * DEC_WARPS] * H + h) * (DEC_PAGE * HD) + lane_off + (long long)(ui & 1) * UL * RPI * HD;
+    };
+    auto load_unit = [&](uint4(&buf)[UL], const bf16* cache, int ui) {
+        const bf16* base = cache + unit_off(ui);
+        const int k0 = unit_k0(ui);
+#pragma unroll
+        for (int u = 0; u < UL; ++u)
+            buf[u] = (k0 + u * RPI + sub < len) ? *reinterpret_cast<const uint4*>(base + u * RPI * HD) : make_uint4(0, 0, 0, 0);
+    };
     float lmax = -INFINITY;
-    for (int pg = warp; pg < n_pages; pg += DEC_WARPS) {
-        const bf16* base = k_cache + ((long long)bt[pg] * H + h) * (DEC_PAGE * HD) + lane_off;
-        const int k0 = pg * DEC_PAGE;
-        uint4 kv[NLD];
+    auto score_unit = [&](const uint4(&buf)[UL], int ui) {
+        const int k0 = unit_k0(ui);
+        float d[UL];
 #pragma unroll
-        for (int u = 0; u < NLD; ++u)
-            kv[u] = (k0 + u * RPI + sub < len) ? *reinterpret_cast<const uint4*>(base + u * RPI * HD) : make_uint4(0, 0, 0, 0);
-        float d[NLD];
-#pragma unroll
-        for (int u = 0; u < NLD; ++u) {
-            const float2 a = unpack_bf16x2(kv[u].x), c = unpack_bf16x2(kv[u].y), e = unpack_bf16x2(kv[u].z), f = unpack_bf16x2(kv[u].w);
+        for (int u = 0; u < UL; ++u) {
+            const float2 a = unpack_bf16x2(buf[u].x), c = unpack_bf16x2(buf[u].y), e = unpack_bf16x2(buf[u].z), f = unpack_bf16x2(buf[u].w);
             d[u] = qr[0] * a.x + qr[1] * a.y + qr[2] * c.x + qr[3] * c.y + qr[4] * e.x + qr[5] * e.y + qr[6] * f.x + qr[7] * f.y;
         }
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) {
 #pragma unroll
-            for (int u = 0; u < NLD; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+            for (int u = 0; u < UL; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
         }
 #pragma unroll
-        for (int u = 0; u < NLD; ++u) {
+        for (int u = 0; u < UL; ++u) {
             const int kpos = k0 + u * RPI + sub;
             if (kpos < len) {
                 const float x = bf16_round(bf16_round(d[u]) / inv_scale);
@@ -320,6 +348,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
                 lmax = fmaxf(lmax, x);
             }
         }
+    };
+    if (nU > 0) load_unit(bufA, k_cache, 0);
+    for (int ui = 0; ui < nU; ui += 2) {     // nU is even
+        load_unit(bufB, k_cache, ui + 1);
+        score_unit(bufA, ui);
+        if (ui + 2 < nU) load_unit(bufA, k_cache, ui + 2);
+        score_unit(bufB, ui + 1);
     }
     lmax = warp_max(lmax);
     if (lane == 0) red[warp] = lmax;
@@ -346,24 +381,23 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int pg = warp; pg < n_pages; pg += DEC_WARPS) {
-        const bf16* base = v_cache + ((long long)bt[pg] * H + h) * (DEC_PAGE * HD) + lane_off;
-        const int k0 = pg * DEC_PAGE;
-        uint4 vv[NLD];
-        float pr[NLD];
+    auto pv_unit = [&](const uint4(&buf)[UL], int ui) {   // rows in cache order: the accumulation order of the unpipelined loop
+        const int k0 = unit_k0(ui);
 #pragma unroll
-        for (int u = 0; u < NLD; ++u) {
+        for (int u = 0; u < UL; ++u) {
             const int kpos = k0 + u * RPI + sub;
-            const bool ok = kpos < len;
-            vv[u] = ok ? *reinterpret_cast<const uint4*>(base + u * RPI * HD) : make_uint4(0, 0, 0, 0);
-            pr[u] = ok ? bf16_round(sc[kpos] * inv) : 0.f;
+            const float p_ = kpos < len ? bf16_round(sc[kpos] * inv) : 0.f;
+            const float2 a = unpack_bf16x2(buf[u].x), c = unpack_bf16x2(buf[u].y), e = unpack_bf16x2(buf[u].z), f = unpack_bf16x2(buf[u].w);
+            acc[0] += p_ * a.x; acc[1] += p_ * a.y; acc[2] += p_ * c.x; acc[3] += p_ * c.y;
+            acc[4] += p_ * e.x; acc[5] += p_ * e.y; acc[6] += p_ * f.x; acc[7] += p_ * f.y;
         }
-#pragma unroll
-        for (int u = 0; u < NLD; ++u) {
-            const float2 a = unpack_bf16x2(vv[u].x), c = unpack_bf16x2(vv[u].y), e = unpack_bf16x2(vv[u].z), f = unpack_bf16x2(vv[u].w);
-            acc[0] += pr[u] * a.x; acc[1] += pr[u] * a.y; acc[2] += pr[u] * c.x; acc[3] += pr[u] * c.y;
-            acc[4] += pr[u] * e.x; acc[5] += pr[u] * e.y; acc[6] += pr[u] * f.x; acc[7] += pr[u] * f.y;
-        }
+    };
+    if (nU > 0) load_unit(bufA, v_cache, 0);
+    for (int ui = 0; ui < nU; ui += 2) {
+        load_unit(bufB, v_cache, ui + 1);
+        pv_unit(bufA, ui);
+        if (ui + 2 < nU) load_unit(bufA, v_cache, ui + 2);
+        pv_unit(bufB, ui + 1);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) part[warp * RPI + sub][li * 8 + e] = acc[e];
@@ -782,18 +816,21 @@ extern "C" int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, co
     // instead of three for six of the eight warps) and 16 measured slower, 17.1 us against 16.0 us per layer inside the decode
     // chain -- the extra warps lengthen the two block-wide reductions more than they shorten the page loops (option "dec_warps")
     const int warps = h->dec_warps == 11 ? 11 : (h->dec_warps == 16 ? 16 : 8);
-#define IVLM_DEC(HD_, W_)                                                                                                        \
+#define IVLM_DEC(HD_, W_, PF_)                                                                                                   \
     do {                                                                                                                         \
-        IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_paged_kernel<HD_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_paged_kernel<HD_, W_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)smem));                                                                        \
-        IVLM_CHECK_CUDA(launch_k(h, decode_attn_paged_kernel<HD_, W_>, grid, dim3(W_ * 32), smem, stream, (const bf16*)q,        \
+        IVLM_CHECK_CUDA(launch_k(h, decode_attn_paged_kernel<HD_, W_, PF_>, grid, dim3(W_ * 32), smem, stream, (const bf16*)q,    \
                                  (const bf16*)k_cache, (const bf16*)v_cache, (const int*)block_table, (const int*)seq_lens,      \
                                  (bf16*)out, (int)H, (int)max_pages, inv_scale));                                                \
     } while (0)
+    const bool pf = h->dec_prefetch != 0;   // option "dec_prefetch" (default off, measured slower): L2 requests for the K / V working set up front
     if (hd == 128) {
-        if (warps == 8) IVLM_DEC(128, 8); else if (warps == 16) IVLM_DEC(128, 16); else IVLM_DEC(128, 11);
+        if (warps == 8) { if (pf) IVLM_DEC(128, 8, true); else IVLM_DEC(128, 8, false); }
+        else if (warps == 16) IVLM_DEC(128, 16, false);
+        else IVLM_DEC(128, 11, false);
     } else if (hd == 64) {
-        if (warps == 8) IVLM_DEC(64, 8); else if (warps == 16) IVLM_DEC(64, 16); else IVLM_DEC(64, 11);
+        if (pf) IVLM_DEC(64, 8, true); else IVLM_DEC(64, 8, false);
     } else {
         set_error("decode_attention: head_dim %d not instantiated (64, 128)", hd);
         return IVLM_ERR_ARG;

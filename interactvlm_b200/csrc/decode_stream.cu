@@ -35,6 +35,8 @@ namespace ivlm {
 constexpr int DS_ROWS = 16, DS_KW = 512, DS_STAGES = 8, DS_CONSUMERS = 8, DS_MAX_M = 8;
 constexpr int DS_W_BYTES = DS_ROWS * DS_KW * 2, DS_A_BYTES = DS_MAX_M * DS_KW * 2;  // per stage: weights 16 KB, streamed tokens 8 KB
 constexpr int DS_THREADS = (DS_CONSUMERS + 1) * 32;
+constexpr int DS_BAR_BYTES = 256, DS_ROPE_HALF = 64;   // rotary tables of the ROPE_KV epilogue: head_dim <= 128
+constexpr int DS_FIXED_BYTES = DS_BAR_BYTES + (DS_CONSUMERS + 1) * 128 * 4 + 2 * DS_MAX_M * DS_ROPE_HALF * 4 + 2 * DS_MAX_M * 4;
 constexpr int DS_FLAG_OFFSET_BYTES = (int)IVLM_WS_COUNTER_BYTES - 4096;  // last 1024 ints of the counter region
 
 enum { DS_EPI_PLAIN = 0, DS_EPI_SWIGLU = 1, DS_EPI_ROPE_KV = 2 };
@@ -83,16 +85,23 @@ template <bool RESIDENT>
 __global__ void __launch_bounds__(DS_THREADS, 1)
 decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const DecodeStreamParams p) {
     extern __shared__ __align__(128) uint8_t ds_smem[];
-    // [full bars | empty bars] [red: 8 warps x 16 x 8 fp32] [fin: 16 x 8 fp32] [resident activation] [ring, 1024-byte aligned]
+    // [full bars | empty bars | rope bar] [red: 8 warps x 16 x 8 fp32] [fin: 16 x 8 fp32] [rope: cos, sin [8][64] fp32, page / offset
+    // [8] int] [resident activation] [ring, 1024-byte aligned]
     uint64_t* full = reinterpret_cast<uint64_t*>(ds_smem);
     uint64_t* empty = full + DS_STAGES;
-    float* red = reinterpret_cast<float*>(ds_smem + 128);
+    uint64_t* rope_bar = empty + DS_STAGES;
+    float* red = reinterpret_cast<float*>(ds_smem + DS_BAR_BYTES);
     float* fin = red + DS_CONSUMERS * 128;
-    bf16* act = reinterpret_cast<bf16*>(fin + 128);
+    float* cos_s = fin + 128;
+    float* sin_s = cos_s + DS_MAX_M * DS_ROPE_HALF;
+    int* pg_s = reinterpret_cast<int*>(sin_s + DS_MAX_M * DS_ROPE_HALF);
+    int* off_s = pg_s + DS_MAX_M;
+    bf16* act = reinterpret_cast<bf16*>(off_s + DS_MAX_M);
     const int act_pitch = p.K + 8;
     constexpr uint32_t stage_bytes = DS_W_BYTES + (RESIDENT ? 0 : DS_A_BYTES);
     uint8_t* ring = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(act) + (RESIDENT ? (size_t)DS_MAX_M * act_pitch * 2 : 0) + 1023) & ~uintptr_t(1023));
+        (reinterpret_cast<uintptr_t>(act) + (RESIDENT ? (size_t)DS_MAX_M * act_pitch * 2 + (p.gamma != nullptr ? (size_t)p.K * 2 : 0) : 0) + 1023) &
+        ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -105,6 +114,7 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             mbar_init(full + i, 1);
             mbar_init(empty + i, DS_CONSUMERS);
         }
+        mbar_init(rope_bar, 31);
         fence_barrier_init();
     }
     __syncthreads();
@@ -140,6 +150,24 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             }
         } else {
             pdl_launch();
+            if (p.epi == DS_EPI_ROPE_KV) {
+                // lanes 1-31 (idle otherwise) stage what the epilogue needs per token -- cache page / offset and the cos / sin rows of
+                // its position -- so that a tile's epilogue reads shared memory instead of three dependent global loads per element
+                pdl_wait();
+                const int half = p.hd >> 1;
+                for (int i = lane - 1; i < p.M * half; i += 31) {
+                    const int tk = i / half, j = i - tk * half;
+                    const int pos = p.positions[tk];
+                    cos_s[tk * DS_ROPE_HALF + j] = __bfloat162float(p.cos_t[(long long)pos * p.hd + j]);
+                    sin_s[tk * DS_ROPE_HALF + j] = __bfloat162float(p.sin_t[(long long)pos * p.hd + j]);
+                }
+                for (int tk = lane - 1; tk < p.M; tk += 31) {
+                    const int slot_i = p.slot_map[tk];
+                    pg_s[tk] = slot_i / p.page;
+                    off_s[tk] = slot_i % p.page;
+                }
+                mbar_arrive(rope_bar);
+            }
         }
         // The HBM pipe would idle from here to the successor's first loads (this CTA's tail, the launch hand-over, the successor's
         // RMSNorm prologue): lanes 0-15 ask L2 for the rows of the stages the successor's CTA `cta` starts with.  Row segments of
@@ -164,9 +192,59 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
 
     // ---------------------------------------------------------------------- consumers (8 warps)
     pdl_launch();
+    bf16* gamma_s = act + (size_t)DS_MAX_M * act_pitch;   // RMSNorm weight, staged before the dependency wait (static operand)
+    if (RESIDENT && p.gamma != nullptr) {
+        const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma);
+        for (int i = threadIdx.x; i < (p.K >> 3); i += DS_CONSUMERS * 32) reinterpret_cast<uint4*>(gamma_s)[i] = __ldg(g4 + i);
+    }
     pdl_wait();
     const int g = lane >> 2, t = lane & 3;
-    if (RESIDENT) {
+    if (RESIDENT && p.gamma != nullptr) named_bar_sync(1, DS_CONSUMERS * 32);
+    if (RESIDENT && (p.K >> 3) <= 32 * 20) {
+        // one batch: the whole row of token m in this warp's registers (20 x 16 bytes per lane at K = 5120: a single L2 round trip),
+        // sum of squares in the association of rmsnorm_kernel (lane-strided, in order), normalised straight from the registers
+        const int nvec = p.K >> 3;
+        for (int m = warp; m < DS_MAX_M; m += DS_CONSUMERS) {
+            uint4* dst = reinterpret_cast<uint4*>(act + (size_t)m * act_pitch);
+            if (m >= p.M) {
+                for (int i = lane; i < nvec; i += 32) dst[i] = make_uint4(0, 0, 0, 0);
+                continue;
+            }
+            const uint4* xr = reinterpret_cast<const uint4*>(p.a + (long long)m * p.lda);
+            uint4 q[20];
+#pragma unroll
+            for (int u = 0; u < 20; ++u) q[u] = (lane + 32 * u < nvec) ? __ldcg(xr + lane + 32 * u) : make_uint4(0, 0, 0, 0);
+            if (p.gamma == nullptr) {
+#pragma unroll
+                for (int u = 0; u < 20; ++u)
+                    if (lane + 32 * u < nvec) dst[lane + 32 * u] = q[u];
+                continue;
+            }
+            float ss = 0.f;
+#pragma unroll
+            for (int u = 0; u < 20; ++u) {
+                const float2 a = unpack_bf16x2(q[u].x), b = unpack_bf16x2(q[u].y), c = unpack_bf16x2(q[u].z), d = unpack_bf16x2(q[u].w);
+                ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+            }
+            const float rstd = rsqrtf(warp_sum(ss) / (float)p.K + p.eps);
+#pragma unroll
+            for (int u = 0; u < 20; ++u) {
+                const int i = lane + 32 * u;
+                if (i < nvec) {
+                    const uint4 gm = reinterpret_cast<const uint4*>(gamma_s)[i];
+                    const uint32_t xi[4] = {q[u].x, q[u].y, q[u].z, q[u].w}, gi[4] = {gm.x, gm.y, gm.z, gm.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 xv = unpack_bf16x2(xi[j]), gv = unpack_bf16x2(gi[j]);
+                        o[j] = pack_bf16x2(gv.x * bf16_round(xv.x * rstd), gv.y * bf16_round(xv.y * rstd));
+                    }
+                    dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        named_bar_sync(1, DS_CONSUMERS * 32);
+    } else if (RESIDENT) {
         // warp m stages token m: raw copy + sum of squares (the association of rmsnorm_kernel: lane-strided, in order), then
         // normalise in place.  Loads go out in batches of 10 per lane so that a 5120-wide row costs two L2 round trips.
         const int nvec = p.K >> 3;
@@ -191,9 +269,9 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             }
             if (p.gamma != nullptr) {
                 const float rstd = rsqrtf(warp_sum(ss) / (float)p.K + p.eps);
-                const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma);
+                const uint4* g4 = reinterpret_cast<const uint4*>(gamma_s);
                 for (int i = lane; i < nvec; i += 32) {
-                    const uint4 q = dst[i], gm = __ldg(g4 + i);
+                    const uint4 q = dst[i], gm = g4[i];
                     const uint32_t xi[4] = {q.x, q.y, q.z, q.w}, gi[4] = {gm.x, gm.y, gm.z, gm.w};
                     uint32_t o[4];
 #pragma unroll
@@ -332,13 +410,12 @@ decode_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 } else {
                     const int D = p.H * p.hd, half = p.hd >> 1;
                     const int sec = row0 / D, r = row0 - sec * D;
-                    const long long slot_i = p.slot_map[tk];
-                    const long long pg = slot_i / p.page, off = slot_i % p.page;
+                    mbar_wait(rope_bar, 0);   // completes once per launch; later waits return at once
+                    const long long pg = pg_s[tk], off = off_s[tk];
                     if (sec < 2) {
                         const int hh = r / p.hd, j = ((r % p.hd) >> 4) * 8 + j8;   // rotary pair (j, j + half) of head hh
-                        const int pos = p.positions[tk];
-                        const float cs = __bfloat162float(p.cos_t[(long long)pos * p.hd + j]);
-                        const float sn = __bfloat162float(p.sin_t[(long long)pos * p.hd + j]);
+                        const float cs = cos_s[tk * DS_ROPE_HALF + j];
+                        const float sn = sin_s[tk * DS_ROPE_HALF + j];
                         const bf16 o1 = __float2bfloat16_rn(bf16_round(lo * cs) + bf16_round(-hi * sn));
                         const bf16 o2 = __float2bfloat16_rn(bf16_round(hi * cs) + bf16_round(lo * sn));
                         if (sec == 0) {
@@ -398,9 +475,9 @@ extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* 
     }
     if (a->epilogue == DS_EPI_ROPE_KV) {
         IVLM_REQUIRE(a->positions && a->slot_map && a->cos_t && a->sin_t && a->k_cache && a->v_cache && a->H > 0 && a->hd > 0 &&
-                         a->hd % 16 == 0 && a->N == 3 * a->H * a->hd && a->page_size > 0 && a->out_dtype == IVLM_BF16 && !a->bias &&
+                         a->hd % 16 == 0 && a->hd <= 2 * DS_ROPE_HALF && a->N == 3 * a->H * a->hd && a->page_size > 0 && a->out_dtype == IVLM_BF16 && !a->bias &&
                          !a->residual,
-                     "decode_linear: ROPE_KV needs N == 3*H*hd, hd %% 16 == 0, tables, cache and slot map, bf16 q output");
+                     "decode_linear: ROPE_KV needs N == 3*H*hd, hd %% 16 == 0, hd <= 128, tables, cache and slot map, bf16 q output");
         p.positions = a->positions; p.slot_map = a->slot_map;
         p.cos_t = reinterpret_cast<const bf16*>(a->cos_t); p.sin_t = reinterpret_cast<const bf16*>(a->sin_t);
         p.k_cache = reinterpret_cast<bf16*>(a->k_cache); p.v_cache = reinterpret_cast<bf16*>(a->v_cache);
@@ -410,15 +487,16 @@ extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* 
     p.spt = (a->K + DS_KW - 1) / DS_KW;
     p.total_stages = p.tiles * p.spt;
     // shared memory: barriers + fold buffers, the resident activation (when it fits next to the ring), the 1024-byte aligned ring
-    const size_t fixed = 128 + (DS_CONSUMERS + 1) * 128 * sizeof(float);
-    const size_t act_bytes = (size_t)DS_MAX_M * (a->K + 8) * 2;
+    const size_t fixed = DS_FIXED_BYTES;
+    const size_t act_bytes = (size_t)DS_MAX_M * (a->K + 8) * 2 + (a->norm_gamma != nullptr ? (size_t)a->K * 2 : 0);   // + staged RMSNorm weight
     const int ns = (h->ds_stages >= 2 && h->ds_stages <= DS_STAGES) ? h->ds_stages : 6;
     p.nstages = ns;
     const size_t ring_res = (size_t)ns * DS_W_BYTES, ring_str = (size_t)ns * (DS_W_BYTES + DS_A_BYTES);
     const size_t cap = 227 * 1024;
     p.resident = (fixed + act_bytes + 1024 + ring_res <= cap) ? 1 : 0;
+    if (h->ds_force_stream && a->norm_gamma == nullptr) p.resident = 0;
     IVLM_REQUIRE(p.resident || a->norm_gamma == nullptr, "decode_linear: fused RMSNorm needs K <= %d (activation resident in shared memory)",
-                 (int)((cap - fixed - 1024 - ring_res) / (2 * DS_MAX_M) - 8));
+                 (int)((cap - fixed - 1024 - ring_res) / (2 * (DS_MAX_M + 1)) - 8));
     const size_t smem = fixed + 1024 + (p.resident ? act_bytes + ring_res : ring_str);
     const CUtensorMap *tw, *ta;
     IVLM_TRY(get_tmap_bf16_kchunk3d(h, a->w, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, DS_ROWS, &tw));

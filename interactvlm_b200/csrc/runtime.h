@@ -98,6 +98,10 @@ struct ivlm_ctx {
     int ds_prefetch_kb = 0;       // decode_stream L2 prefetch of the successor's weights per CTA: 0 off (default: measured 1-10 % SLOWER on
                                   // the 13B chain, profiles/r2_decode_layer_ops_in_graph.txt), -1 as the caller asks, > 0 cap in KB
     int ds_stages = 0;            // decode_stream ring depth (0: 6 stages -- 137 vs 139 us per layer with 8 in the same run; A/B knob)
+    int ds_force_stream = 1;      // decode_stream: 1 streams the activation with the weights whenever no RMSNorm is fused (no prologue: o_proj
+                                  // 12.8 vs 13.7 us), 0 keeps it resident when it fits
+    int dec_prefetch = 0;         // paged decode attention: 1 requests the CTA's K / V lines into L2 before the page loops (A/B knob; measured
+                                  // SLOWER, 19.6 vs 16.0 us per layer: the requests queue in front of the demand loads they were meant to hide)
     int dec_warps = 0;            // paged decode attention: warps per CTA (0: 8; 11 or 16 for A/B)
     int attn_prefetch_ahead = 0;  // window attention: L2 prefetch of the successor CTA's tiles, distance in CTAs of the launch order
                                   // (0 = off, the default: measured neutral at 148 .. 1184 CTAs ahead, 0.366-0.379 ms per 16 views)

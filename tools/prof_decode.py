@@ -141,7 +141,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "fused":
         ctx.set_option("pdl", pdl)
         print(f"fused layer chain in a graph, pdl={pdl}: {graph_time(fused_chain):7.2f} us per layer;   9-launch chain: {graph_time(layer_chain):7.2f} us", flush=True)
     ctx.set_option("pdl", 1)
-    for ns in (8, 6, 4, 3, 2):
+    for ns in (7, 6, 5, 4, 3):   # 8 stages no longer fit next to the resident activation + staged RMSNorm weight
         ctx.set_option("ds_stages", ns)
         row = "  ".join(f"{name.split('+')[0]} {graph_time(fn):6.2f}" for name, (fn, _) in list(fops.items())[:4])
         print(f"ring depth {ns}: {row}  chain {graph_time(fused_chain):7.2f} us", flush=True)
@@ -150,6 +150,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "fused":
         ctx.set_option("dec_warps", wv)
         print(f"decode attention with {wv} warps per CTA: {graph_time(fops['decode_attention'][0]):6.2f} us   chain {graph_time(fused_chain):7.2f} us", flush=True)
     ctx.set_option("dec_warps", 0)
+    for pf in (0, 1):
+        ctx.set_option("dec_prefetch", pf)
+        print(f"decode attention, K / V lines requested into L2 up front = {pf}: {graph_time(fops['decode_attention'][0]):6.2f} us   "
+              f"chain {graph_time(fused_chain):7.2f} us", flush=True)
+    for fs in (1, 0):
+        ctx.set_option("ds_force_stream", fs)
+        print(f"o_proj with the activation {'streamed' if fs else 'resident'}: {graph_time(fops['o_proj+res'][0]):6.2f} us   "
+              f"chain {graph_time(fused_chain):7.2f} us", flush=True)
     ctx.set_option("pdl", 0)
     sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "splits":
