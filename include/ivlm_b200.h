@@ -326,6 +326,13 @@ typedef struct ivlm_decode_linear_args {
     int32_t prefetch_N, prefetch_K, prefetch_stages;
 } ivlm_decode_linear_args;
 IVLM_API int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* args, void* stream);
+/* n (1..4) ivlm_decode_linear launches that feed each other (phase i+1 reads what phase i wrote: o_proj -> gate/up ->
+ * down_proj -> the next layer's qkv) as ONE launch of a persistent kernel: the phases are separated by grid-wide barriers and the
+ * weight stream of phase i+1 is already in flight while phase i finishes, instead of paying a launch boundary per layer
+ * (HF LlamaDecoderLayer.forward, the part after the attention; /root/reference model/llava/model/language_model/llava_llama.py:93-105
+ * drives it).  Results are bit-identical to the separate launches.  Phases with norm_gamma keep their activation in shared
+ * memory, the others stream it; at most one ROPE_KV phase; prefetch_* fields are ignored. */
+IVLM_API int ivlm_decode_chain(ivlm_handle h, const ivlm_decode_linear_args* phases, int32_t n, void* stream);
 /* One-token attention over the paged KV cache: q [B,H*hd], block_table [B,max_pages], seq_lens [B]
  * (keys 0..seq_len-1, the current token already stored); caches laid out [pages, H, page_size, hd]. */
 IVLM_API int ivlm_decode_attention_paged_bf16(ivlm_handle h, const void* q, const void* k_cache, const void* v_cache,

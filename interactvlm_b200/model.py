@@ -214,7 +214,10 @@ class _Engine:
         self.stage_abi = not getattr(ctx, "emulated", False)
         self._bind()
         self.skip_pad_rows = True  # SAM window blocks: GEMMs on the real tokens only (the padded rows' q/k/v are the bias)
-        self.decode_prefetch_wo = 64   # 16 KB stages of o_proj per SM requested into L2 by the qkv launch (1 MB: all of a 13B o_proj)
+        # o_proj -> gate/up -> down_proj -> next qkv as ONE persistent launch per layer (ivlm_decode_chain, grid barriers between the
+        # phases).  Bit-identical, but measured SLOWER than the five PDL-chained launches (147 vs 135 us per 13B layer: a grid barrier
+        # plus the shallower 24 KB-stage ring cost more than a programmatic launch boundary), so it is off.
+        self.chained_decode = False
         self.fused_decode = True   # decode steps of <= 8 tokens through ivlm_decode_linear (5 launches per layer instead of 9)
         self.trace = None  # tests: dict of lists receiving the residual stream after every SAM block / LLaMA prefill layer
 
@@ -453,17 +456,39 @@ class _Engine:
             # 5 launches per layer (ivlm_decode_linear): [RMSNorm + qkv + RoPE + KV store] -> attention -> [o_proj + residual]
             # -> [RMSNorm + gate/up + SwiGLU] -> [down_proj + residual]
             EPI_SWIGLU, EPI_ROPE_KV = 1, 2
-            for i, lw in enumerate(W.llm):
-                rope = dict(positions=st["pos"], slot_map=st["slot"], cos=W.rope_cos, sin=W.rope_sin, k_cache=st["k"][i],
-                            v_cache=st["v"][i], H=nh, hd=hd, page_size=PAGE)
-                # every launch asks L2 for the head of its successor's weights (wo: all of it, it loads under the attention launch)
-                nxt = W.llm[i + 1]["wqkv"] if i + 1 < len(W.llm) else W.lm_head
-                q = ctx.decode_linear(x, lw["wqkv"], gamma=lw["ln1"], eps=cfg.rms_norm_eps, epilogue=EPI_ROPE_KV, rope=rope,
-                                      prefetch=lw["wo"], prefetch_stages=self.decode_prefetch_wo)
-                o = ctx.decode_attention(q, st["k"][i], st["v"][i], st["block_table"], st["seq_lens"], nh, hd, PAGE)
-                x = ctx.decode_linear(o, lw["wo"], residual=x, prefetch=lw["wgu"])
-                y = ctx.decode_linear(x, lw["wgu"], gamma=lw["ln2"], eps=cfg.rms_norm_eps, epilogue=EPI_SWIGLU, prefetch=lw["wd"])
-                x = ctx.decode_linear(y, lw["wd"], residual=x, prefetch=nxt)
+            rope_of = lambda i: dict(positions=st["pos"], slot_map=st["slot"], cos=W.rope_cos, sin=W.rope_sin, k_cache=st["k"][i],
+                                     v_cache=st["v"][i], H=nh, hd=hd, page_size=PAGE)
+            if self.chained_decode:
+                # 2 launches per layer: attention, then ONE persistent launch (ivlm_decode_chain) for o_proj -> gate/up -> down_proj
+                # -> the NEXT layer's qkv, its phases separated by grid barriers with the weight stream running through them
+                Bt, D, F = x.shape[0], cfg.hidden_size, cfg.intermediate_size
+                if "chain_bufs" not in st:
+                    mk = lambda w: torch.empty((Bt, w), device=x.device, dtype=torch.bfloat16)
+                    st["chain_bufs"] = dict(q=[mk(D), mk(D)], xn=mk(D), act=mk(F), x=mk(D))
+                bufs = st["chain_bufs"]
+                q = ctx.decode_linear(x, W.llm[0]["wqkv"], gamma=W.llm[0]["ln1"], eps=cfg.rms_norm_eps, epilogue=EPI_ROPE_KV, rope=rope_of(0),
+                                      out=bufs["q"][0])
+                xr = x                                   # residual stream entering the layer
+                for i, lw in enumerate(W.llm):
+                    o = ctx.decode_attention(q, st["k"][i], st["v"][i], st["block_table"], st["seq_lens"], nh, hd, PAGE)
+                    phases = [(o, lw["wo"], dict(residual=xr, out=bufs["xn"])),
+                              (bufs["xn"], lw["wgu"], dict(gamma=lw["ln2"], eps=cfg.rms_norm_eps, epilogue=EPI_SWIGLU, out=bufs["act"])),
+                              (bufs["act"], lw["wd"], dict(residual=bufs["xn"], out=bufs["x"]))]
+                    if i + 1 < len(W.llm):
+                        nw = W.llm[i + 1]
+                        phases.append((bufs["x"], nw["wqkv"], dict(gamma=nw["ln1"], eps=cfg.rms_norm_eps, epilogue=EPI_ROPE_KV,
+                                                                  rope=rope_of(i + 1), out=bufs["q"][(i + 1) & 1])))
+                    ctx.decode_chain(phases)
+                    xr = bufs["x"]
+                    q = bufs["q"][(i + 1) & 1]
+                x = bufs["x"]
+            else:
+                for i, lw in enumerate(W.llm):
+                    q = ctx.decode_linear(x, lw["wqkv"], gamma=lw["ln1"], eps=cfg.rms_norm_eps, epilogue=EPI_ROPE_KV, rope=rope_of(i))
+                    o = ctx.decode_attention(q, st["k"][i], st["v"][i], st["block_table"], st["seq_lens"], nh, hd, PAGE)
+                    x = ctx.decode_linear(o, lw["wo"], residual=x)
+                    y = ctx.decode_linear(x, lw["wgu"], gamma=lw["ln2"], eps=cfg.rms_norm_eps, epilogue=EPI_SWIGLU)
+                    x = ctx.decode_linear(y, lw["wd"], residual=x)
         else:
             for i, lw in enumerate(W.llm):
                 y = ctx.rmsnorm(x, lw["ln1"], cfg.rms_norm_eps)

@@ -67,7 +67,7 @@ class Context:
     # ------------------------------------------------------------------ per-kernel timing (bench.py roofline pass)
     _PROFILED = ("gemm", "attention", "layernorm", "rmsnorm", "add_bcast", "silu_mul", "im2col_patch", "im2col_3x3",
                  "sam_relpos", "sam_attention", "attn_small", "embed_splice", "embed_gather", "gather_rows", "rope_kv_store", "decode_linear",
-                 "decode_attention", "fill_rows", "decode_prepare", "decode_finish", "argmax", "cam_gate", "upscale_hyper_dot", "bilinear", "finalize")
+                 "decode_chain", "decode_attention", "fill_rows", "decode_prepare", "decode_finish", "argmax", "cam_gate", "upscale_hyper_dot", "bilinear", "finalize")
 
     def enable_profile(self):
         """Bracket every launch with CUDA events on the launching stream (no synchronisation until profile_report()).
@@ -90,6 +90,8 @@ class Context:
                         work = 2.0 * a[1].shape[0] * a[1].shape[1]  # bytes of weights read
                 elif _name == "decode_linear":
                     work = 2.0 * a[1].shape[0] * a[1].shape[1]  # bytes of weights streamed
+                elif _name == "decode_chain":
+                    work = sum(2.0 * ph[1].shape[0] * ph[1].shape[1] for ph in a[0])
                 elif _name == "sam_attention":
                     Bq, nh, S_, hd_ = a[3], a[4], a[5] * a[6], a[7]
                     work = 4.0 * Bq * nh * S_ * S_ * hd_
@@ -278,12 +280,8 @@ class Context:
                                             self.stream), "silu_mul")
         return out
 
-    def decode_linear(self, a, w, gamma=None, eps=0.0, epilogue=L.EPI_PLAIN, act=ACT_NONE, bias=None, residual=None, out=None,
-                      out_dtype=torch.bfloat16, rope=None, prefetch=None, prefetch_stages=0):
-        """Weight-streaming linear layer of a decode step, M <= 8 tokens (ivlm_decode_linear): optional fused RMSNorm of `a`,
-        epilogue PLAIN / SWIGLU (w rows interleaved) / ROPE_KV (w q,k rows paired; rope = dict(positions, slot_map, cos, sin,
-        k_cache, v_cache, H, hd, page_size)).  `prefetch` = the weight matrix of the next decode_linear launch (its first
-        stages are requested into L2 at the end of this one; prefetch_stages 16 KB stages per SM, 0 = library default)."""
+    def _decode_linear_args(self, a, w, gamma=None, eps=0.0, epilogue=L.EPI_PLAIN, act=ACT_NONE, bias=None, residual=None, out=None,
+                            out_dtype=torch.bfloat16, rope=None, prefetch=None, prefetch_stages=0):
         _bf16(a, "a"); _bf16(w, "w")
         M, K = a.shape
         N = w.shape[0]
@@ -314,8 +312,30 @@ class Context:
             assert prefetch.dim() == 2 and prefetch.stride(1) == 1
             g.prefetch_w, g.prefetch_ldw = prefetch.data_ptr(), prefetch.stride(0)
             g.prefetch_N, g.prefetch_K, g.prefetch_stages = prefetch.shape[0], prefetch.shape[1], int(prefetch_stages)
+        return g, out
+
+    def decode_linear(self, a, w, **kw):
+        """Weight-streaming linear layer of a decode step, M <= 8 tokens (ivlm_decode_linear): optional fused RMSNorm of `a`
+        (gamma, eps), epilogue PLAIN (act, bias, residual) / SWIGLU (w rows interleaved) / ROPE_KV (w q,k rows paired; rope =
+        dict(positions, slot_map, cos, sin, k_cache, v_cache, H, hd, page_size)); out / out_dtype.  `prefetch` = the weight matrix
+        of the next decode_linear launch (its first stages are requested into L2 at the end of this one when the option
+        ds_prefetch_kb enables it; prefetch_stages 16 KB stages per SM, 0 = library default)."""
+        g, out = self._decode_linear_args(a, w, **kw)
         L.check(self.lib.ivlm_decode_linear(self.h, C.byref(g), self.stream), "decode_linear")
         return out
+
+    def decode_chain(self, phases):
+        """Up to four dependent decode_linear launches as one persistent launch with grid-wide barriers between the phases
+        (ivlm_decode_chain).  phases: list of (a, w, kwargs) with decode_linear's keywords; a phase reads the `out` tensor of an
+        earlier one by passing it as `a` / `residual` (allocate the outputs first and pass them as out=).  Returns the outputs."""
+        arr = (L.DecodeLinearArgs * len(phases))()
+        outs = []
+        for i, (a, w, kw) in enumerate(phases):
+            g, out = self._decode_linear_args(a, w, **kw)
+            arr[i] = g
+            outs.append(out)
+        L.check(self.lib.ivlm_decode_chain(self.h, arr, i32(len(phases)), self.stream), "decode_chain")
+        return outs
 
     def finalize(self, acc, bias=None, residual=None, act=ACT_NONE, out=None):
         assert acc.dtype == torch.float32 and acc.is_contiguous()

@@ -146,6 +146,10 @@ class EmuContext:
             gate, up = gate_up[:, :Fh], gate_up[:, Fh:]
         return (_r(F.silu(gate.float())) * up.float()).to(BF)
 
+    def decode_chain(self, phases):
+        """ivlm_decode_chain: the phases one after the other; each writes its `out` tensor, which later phases read."""
+        return [self.decode_linear(a, w, **kw) for a, w, kw in phases]
+
     def decode_linear(self, a, w, gamma=None, eps=0.0, epilogue=0, act=ACT_NONE, bias=None, residual=None, out=None, out_dtype=BF,
                       rope=None, prefetch=None, prefetch_stages=0):
         """ivlm_decode_linear: rmsnorm? -> linear -> PLAIN / SWIGLU (interleaved rows) / ROPE_KV (paired q, k rows)."""

@@ -138,3 +138,88 @@ def test_l2_prefetch_of_the_successor_does_not_change_results(ctx, nxt_shape, st
         ctx.set_option("ds_prefetch_kb", kb)
         assert torch.equal(ctx.decode_linear(a, w, residual=res, prefetch=nxt, prefetch_stages=stages), base)
     torch.cuda.synchronize()
+
+
+def _chain_case(ctx, M, D, F, H, hd, seed):
+    """o_proj -> gate/up -> down_proj -> next qkv, once as four launches and once as one chained launch."""
+    page, pages_per = 16, 4
+    inv = 1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))
+    fr = torch.outer(torch.arange(64).float(), inv)
+    emb = torch.cat((fr, fr), -1)
+    cos_t, sin_t = emb.cos().bfloat16().to(DEV), emb.sin().bfloat16().to(DEV)
+    o, x = rnd(M, D, seed=seed), rnd(M, D, seed=seed + 1)
+    wo, wd = rnd(D, D, scale=D ** -0.5, seed=seed + 2), rnd(D, F, scale=F ** -0.5, seed=seed + 3)
+    wgu = interleave_gate_up(rnd(F, D, scale=D ** -0.5, seed=seed + 4), rnd(F, D, scale=D ** -0.5, seed=seed + 5))
+    wq, wk, wv = (rnd(D, D, scale=D ** -0.5, seed=seed + s) for s in (6, 7, 8))
+    wqkv = torch.cat([pair_rows(wq, H, hd), pair_rows(wk, H, hd), wv], 0)
+    g1 = (1 + 0.1 * torch.randn(D, generator=torch.Generator().manual_seed(seed + 9))).bfloat16().to(DEV)
+    g2 = (1 + 0.1 * torch.randn(D, generator=torch.Generator().manual_seed(seed + 10))).bfloat16().to(DEV)
+    positions = torch.arange(M, dtype=torch.int32, device=DEV) * 5 + 3
+    slot = (torch.arange(M, dtype=torch.int32, device=DEV) * pages_per * page + positions).contiguous()
+    res = {}
+    for chained in (False, True):
+        kc = torch.zeros(M * pages_per, H, page, hd, device=DEV, dtype=torch.bfloat16)
+        vc = torch.zeros_like(kc)
+        rope = dict(positions=positions, slot_map=slot, cos=cos_t, sin=sin_t, k_cache=kc, v_cache=vc, H=H, hd=hd, page_size=page)
+        mk = lambda w: torch.full((M, w), 7.0, device=DEV, dtype=torch.bfloat16)
+        xn, act, x2, q = mk(D), mk(F), mk(D), mk(D)
+        phases = [(o, wo, dict(residual=x, out=xn)),
+                  (xn, wgu, dict(gamma=g2, eps=1e-5, epilogue=1, out=act)),
+                  (act, wd, dict(residual=xn, out=x2)),
+                  (x2, wqkv, dict(gamma=g1, eps=1e-5, epilogue=2, rope=rope, out=q))]
+        if chained:
+            for _ in range(3):                       # barriers re-arm themselves between launches
+                ctx.decode_chain(phases)
+        else:
+            for a_, w_, kw in phases:
+                ctx.decode_linear(a_, w_, **kw)
+        torch.cuda.synchronize()
+        res[chained] = [t.clone() for t in (xn, act, x2, q, kc, vc)]
+    for name, a_, b_ in zip(("o_proj", "gate_up", "down", "q", "k_cache", "v_cache"), res[False], res[True]):
+        assert torch.equal(a_, b_), name
+    ref = (o.float() @ wo.float().t()).bfloat16().float() + x.float()
+    assert rel_err(res[True][0], ref) < 4e-3
+
+
+@pytest.mark.parametrize("M,D,F,H,hd", [(8, 5120, 13824, 40, 128), (3, 256, 704, 4, 64), (8, 512, 1408, 4, 128), (1, 128, 320, 2, 64)])
+def test_chained_launch_equals_separate_launches(ctx, M, D, F, H, hd):
+    """ivlm_decode_chain against four ivlm_decode_linear launches: bit-identical outputs (13B widths; tiny widths where phases have
+    fewer tiles than SMs, ragged K stages and M < 8), repeated launches (self-re-arming grid barriers)."""
+    _chain_case(ctx, M, D, F, H, hd, seed=100)
+
+
+def test_chained_launch_shorter_chains(ctx):
+    M, D, F = 4, 1024, 2816
+    o, x = rnd(M, D, seed=1), rnd(M, D, seed=2)
+    wo, wd = rnd(D, D, scale=D ** -0.5, seed=3), rnd(D, F, scale=F ** -0.5, seed=4)
+    y = rnd(M, F, seed=5)
+    a1 = ctx.decode_linear(o, wo, residual=x)
+    b1 = ctx.decode_linear(y, wd, residual=a1)
+    (a2,) = ctx.decode_chain([(o, wo, dict(residual=x))])
+    assert torch.equal(a1, a2)
+    a3 = torch.empty_like(a1)
+    outs = ctx.decode_chain([(o, wo, dict(residual=x, out=a3)), (y, wd, dict(residual=a3))])
+    assert torch.equal(outs[0], a1) and torch.equal(outs[1], b1)
+
+
+def test_chained_decode_step_is_bit_identical(ctx):
+    """The tiny model with model.eng.chained_decode (attention + one ivlm_decode_chain launch per layer) against the default
+    five launches per layer: same tokens, identical hidden states."""
+    from interactvlm_b200 import synthetic as S
+    from interactvlm_b200.config import IVLMConfig
+    from interactvlm_b200.model import InteractVLMForCausalLM
+    from oracle.make_goldens_model import TINY_SEED, tiny_inputs
+
+    cfg = IVLMConfig.tiny()
+    model = InteractVLMForCausalLM(cfg, S.make_state_dict(cfg, seed=TINY_SEED["weights"]), ctx=ctx)
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
+    outs = {}
+    for chained in (False, True):
+        model.eng.chained_decode = chained
+        model._graphs = {}
+        n0 = ctx.launch_count()
+        out_ids, hid = model.generate(clip, ids, max_new_tokens=ans.shape[1], scripted=ans)
+        outs[chained] = (out_ids.clone(), hid.clone(), ctx.launch_count() - n0)
+    model.eng.chained_decode = False
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    assert outs[True][2] < outs[False][2]

@@ -112,6 +112,31 @@ def fused_chain_pf(i, wo_stages=64, stages=0):
     return ctx.decode_linear(y, wd[i % NW], residual=x1, prefetch=wqkv[(i + 1) % NW], prefetch_stages=stages)
 
 
+xn_b, act_b, x_b, q_b = torch.empty_like(x), torch.empty_like(xf), torch.empty_like(x), torch.empty_like(x)
+
+
+def chained_chain(i):
+    """attention + ONE chained launch (o_proj -> gate/up -> down_proj -> next qkv), as model.py drives a layer"""
+    rope = dict(positions=pos, slot_map=slot, cos=cos_t, sin=sin_t, k_cache=kc[(i + 1) % NW], v_cache=vc[(i + 1) % NW], H=H, hd=hd, page_size=page)
+    o_ = ctx.decode_attention(q_b, kc[i % NW], vc[i % NW], bt, sl, H, hd, page)
+    ctx.decode_chain([(o_, wo[i % NW], dict(residual=x, out=xn_b)),
+                      (xn_b, wgu[i % NW], dict(gamma=gam, eps=1e-5, epilogue=1, out=act_b)),
+                      (act_b, wd[i % NW], dict(residual=xn_b, out=x_b)),
+                      (x_b, wqkv[(i + 1) % NW], dict(gamma=gam, eps=1e-5, epilogue=2, rope=rope, out=q_b))])
+    return q_b
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "chain2":
+    for pdl in (0, 1):
+        ctx.set_option("pdl", pdl)
+        print(f"pdl={pdl}: 5-launch layer {graph_time(fused_chain):7.2f} us;   attention + chained launch {graph_time(chained_chain):7.2f} us", flush=True)
+    ctx.set_option("pdl", 1)
+    for ns in (5, 4, 3):
+        ctx.set_option("ds_stages", ns)
+        print(f"chained launch, ring depth {ns}: {graph_time(chained_chain):7.2f} us per layer", flush=True)
+    ctx.set_option("ds_stages", 0)
+    ctx.set_option("pdl", 0)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "prefetch":
     ctx.set_option("pdl", 1)
     ctx.set_option("ds_prefetch_kb", -1)   # the prefetch is off by default
