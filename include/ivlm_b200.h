@@ -74,6 +74,10 @@ typedef struct ivlm_model_dims {
     int32_t llm_hidden, llm_intermediate, llm_layers, llm_heads, llm_head_dim, llm_vocab;
     float llm_rms_eps;
     int32_t llm_paired_layout;     /* 1: q/k rows paired and gate/up rows interleaved (interactvlm_b200/layout.py) */
+    /* CLIP tower (0 = not described: ivlm_clip_encode unavailable) */
+    int32_t clip_img, clip_patch, clip_hidden, clip_heads, clip_layers;
+    int32_t clip_ldk;              /* row pitch of the flattened patch-conv weight / im2col operand (3*patch^2 rounded up to 8) */
+    float clip_eps;
 } ivlm_model_dims;
 IVLM_API int ivlm_set_model_dims(ivlm_handle h, const ivlm_model_dims* dims);
 /* SAM ViT encoder on N views: images [N,3,S,S] bf16 -> emb [N, (S/patch)^2, out_chans] bf16 (token-major, the layout the mask
@@ -108,6 +112,41 @@ typedef struct ivlm_llm_prefill_args {
 } ivlm_llm_prefill_args;
 IVLM_API size_t ivlm_llm_arena_bytes(ivlm_handle h, int32_t tokens);
 IVLM_API int ivlm_llm_prefill(ivlm_handle h, const ivlm_llm_prefill_args* args, void* stream);
+/* CLIP ViT tower (all but the last layer) + patch-feature selection + mm_projector: what LlavaMetaForCausalLM.encode_images runs
+ * (clip_encoder.py:31-60, llava_arch.py:93-96).  images [B,3,S,S] bf16 -> feats [B, T-1, llm_hidden] bf16 (T = (S/patch)^2 + 1).
+ * patch_rows [B*(T-1)]: b*T + 1 + j; cls_rows [B]: b*T.  Weights "clip.*", "mm.w", "mm.b". */
+typedef struct ivlm_clip_encode_args {
+    const void* images;
+    void* feats;
+    int32_t B;
+    const int32_t* patch_rows;
+    const int32_t* cls_rows;
+    void* arena;
+    size_t arena_bytes;
+} ivlm_clip_encode_args;
+IVLM_API size_t ivlm_clip_encode_arena_bytes(ivlm_handle h, int32_t B);
+IVLM_API int ivlm_clip_encode(ivlm_handle h, const ivlm_clip_encode_args* args, void* stream);
+/* text_hidden_fcs[0] on the n hidden rows that predict [SEG] + the per-view camera gate (InteractVLM.py:100-112,268-294,551-556;
+ * components.py:541-572): hidden_rows [n, llm_hidden] bf16, cam [n,V,5] bf16 (NULL without camera conditioning) ->
+ * prompt [n,V,256] bf16 and emb [n,256] bf16 (the un-gated embedding).  Weights "seg.fc0_w" ... "seg.cam.*" (vi_v1 or none; the
+ * other encoder / token types stay on the op-level path).  arena >= n * 5120 * 2 bytes + 256. */
+IVLM_API int ivlm_seg_head(ivlm_handle h, const void* hidden_rows, const void* cam, void* prompt, void* emb, int32_t n, int32_t V,
+                           void* arena, size_t arena_bytes, void* stream);
+/* Prompt encoder + two-way mask decoder + output upscaling + hypernetwork dot for n samples of V views (InteractVLM.py:40-63,
+ * prompt_encoder.py:140-186, mask_decoder.py:116-164, transformer.py:62-242): emb [n*V, S, C] bf16 token-major (ivlm_sam_encode's
+ * output), prompt [n,V,C] bf16 -> low-res logits [n*V, 4g, 4g] fp32.  tok_idx [n*V*(5+V)]: for token row r of view (s,v), the row
+ * of the table [5 output tokens; n*V prompt rows] it is made of (t < 5: t, else 5 + s*V + (t-5)).  Weights "dec.*". */
+typedef struct ivlm_mask_decode_args {
+    const void* emb;
+    const void* prompt;
+    float* lowres;
+    int32_t n, V, heads;
+    const int32_t* tok_idx;
+    void* arena;
+    size_t arena_bytes;
+} ivlm_mask_decode_args;
+IVLM_API size_t ivlm_mask_decode_arena_bytes(ivlm_handle h, int32_t n, int32_t V);
+IVLM_API int ivlm_mask_decode(ivlm_handle h, const ivlm_mask_decode_args* args, void* stream);
 /* One decode step for B <= 8 sequences (the launch sequence a CUDA graph captures): bookkeeping buffers as ivlm_decode_prepare /
  * ivlm_decode_finish take them. */
 typedef struct ivlm_llm_decode_args {

@@ -77,7 +77,21 @@ class ModelDims(C.Structure):
     _fields_ = [("sam_img", C.c_int32), ("sam_patch", C.c_int32), ("sam_embed_dim", C.c_int32), ("sam_depth", C.c_int32),
                 ("sam_heads", C.c_int32), ("sam_window", C.c_int32), ("sam_out_chans", C.c_int32), ("sam_global_mask", C.c_uint32),
                 ("llm_hidden", C.c_int32), ("llm_intermediate", C.c_int32), ("llm_layers", C.c_int32), ("llm_heads", C.c_int32),
-                ("llm_head_dim", C.c_int32), ("llm_vocab", C.c_int32), ("llm_rms_eps", C.c_float), ("llm_paired_layout", C.c_int32)]
+                ("llm_head_dim", C.c_int32), ("llm_vocab", C.c_int32), ("llm_rms_eps", C.c_float), ("llm_paired_layout", C.c_int32),
+                ("clip_img", C.c_int32), ("clip_patch", C.c_int32), ("clip_hidden", C.c_int32), ("clip_heads", C.c_int32),
+                ("clip_layers", C.c_int32), ("clip_ldk", C.c_int32), ("clip_eps", C.c_float)]
+
+
+class ClipEncodeArgs(C.Structure):
+    """ivlm_clip_encode_args."""
+    _fields_ = [("images", C.c_void_p), ("feats", C.c_void_p), ("B", C.c_int32), ("patch_rows", C.c_void_p), ("cls_rows", C.c_void_p),
+                ("arena", C.c_void_p), ("arena_bytes", C.c_size_t)]
+
+
+class MaskDecodeArgs(C.Structure):
+    """ivlm_mask_decode_args."""
+    _fields_ = [("emb", C.c_void_p), ("prompt", C.c_void_p), ("lowres", C.c_void_p), ("n", C.c_int32), ("V", C.c_int32), ("heads", C.c_int32),
+                ("tok_idx", C.c_void_p), ("arena", C.c_void_p), ("arena_bytes", C.c_size_t)]
 
 
 class SamEncodeArgs(C.Structure):
@@ -135,6 +149,8 @@ def lib() -> C.CDLL:
         _lib.ivlm_lift_nnz.restype = C.c_int64
         _lib.ivlm_sam_encode_arena_bytes.restype = C.c_size_t
         _lib.ivlm_llm_arena_bytes.restype = C.c_size_t
+        _lib.ivlm_clip_encode_arena_bytes.restype = C.c_size_t
+        _lib.ivlm_mask_decode_arena_bytes.restype = C.c_size_t
         for name in declared_symbols():
             if not hasattr(_lib, name):
                 raise RuntimeError(f"libivlm_b200.so does not export {name}")

@@ -299,3 +299,237 @@ extern "C" int ivlm_llm_decode_step(ivlm_handle h, const ivlm_llm_decode_args* a
     IVLM_TRY(ivlm_argmax_f32(h, logits, a->next, B, d.llm_vocab, d.llm_vocab, stream));
     return IVLM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ CLIP tower + projector
+extern "C" size_t ivlm_clip_encode_arena_bytes(ivlm_handle h, int32_t B) {
+    if (!h || !h->dims_set || B <= 0 || h->dims.clip_hidden <= 0) return 0;
+    const ivlm_model_dims& d = h->dims;
+    const size_t g = d.clip_img / d.clip_patch, T = g * g + 1, C = d.clip_hidden, rows = (size_t)B * T;
+    // cols [B*(T-1), ldk]; h (two), y, o: rows x C; qkv: rows x 3C; mlp: rows x 4C; patches: B*(T-1) x C
+    return 2 * ((size_t)B * (T - 1) * d.clip_ldk + 4 * rows * C + 3 * rows * C + 4 * rows * C + (size_t)B * (T - 1) * C) + 16 * 256;
+}
+
+// CLIPVisionTower.forward + feature_select('patch', layer -2) + mm_projector (clip_encoder.py:31-60, llava_arch.py:93-96):
+// images [B,3,S,S] bf16 -> feats [B, T-1, llm_hidden] bf16.  The launch sequence of model.py's _Engine.clip_encode; weights
+// "clip.*" / "mm.*"; patch_rows [B*(T-1)] = b*T + 1 + j (destination row of every patch token), cls_rows [B] = b*T.
+extern "C" int ivlm_clip_encode(ivlm_handle h, const ivlm_clip_encode_args* a, void* stream) {
+    IVLM_REQUIRE(h && a && a->images && a->feats && a->patch_rows && a->cls_rows && a->arena && a->B > 0, "clip_encode: bad arguments");
+    IVLM_REQUIRE(h->dims_set && h->dims.clip_hidden > 0, "clip_encode: call ivlm_set_model_dims (with the clip_* fields) first");
+    const ivlm_model_dims& d = h->dims;
+    const int B = a->B, g = d.clip_img / d.clip_patch, T = g * g + 1, C = d.clip_hidden, nh = d.clip_heads, hd = C / nh, ldk = d.clip_ldk;
+    const int rows = B * T, prow = B * (T - 1);
+    Arena arena(a->arena, a->arena_bytes);
+    IVLM_TAKE(cols, uint16_t, (size_t)prow * ldk);
+    IVLM_TAKE(ha, uint16_t, (size_t)rows * C);
+    IVLM_TAKE(hb, uint16_t, (size_t)rows * C);
+    IVLM_TAKE(y, uint16_t, (size_t)rows * C);
+    IVLM_TAKE(o, uint16_t, (size_t)rows * C);
+    IVLM_TAKE(qkv, uint16_t, (size_t)rows * 3 * C);
+    IVLM_TAKE(mlp, uint16_t, (size_t)rows * 4 * C);
+    IVLM_TAKE(patches, uint16_t, (size_t)prow * C);
+    IVLM_W(w_patch, "clip.w_patch"); IVLM_W(pos, "clip.pos"); IVLM_W(cls_pos, "clip.cls_pos"); IVLM_W(pre_g, "clip.pre_g"); IVLM_W(pre_b, "clip.pre_b");
+    IVLM_TRY(ivlm_im2col_patch_bf16(h, a->images, cols, B, 3, d.clip_img, d.clip_img, d.clip_patch, ldk, stream));
+    IVLM_TRY(ivlm_fill_rows_bf16(h, ha, C, a->cls_rows, B, cls_pos, C, stream));
+    IVLM_TRY(gemm(h, cols, ldk, w_patch, ldk, ha, C, prow, C, ldk, nullptr, 0, pos, C, a->patch_rows, T, -1, IVLM_BF16, stream));
+    IVLM_TRY(ivlm_layernorm_bf16(h, ha, hb, pre_g, pre_b, rows, C, d.clip_eps, nullptr, 0, stream));
+    uint16_t *x = hb, *xn = ha;
+    for (int i = 0; i < d.clip_layers; ++i) {
+        const std::string p = "clip." + std::to_string(i) + ".";
+        IVLM_W(ln1g, p + "ln1g"); IVLM_W(ln1b, p + "ln1b"); IVLM_W(wqkv, p + "wqkv"); IVLM_W(bqkv, p + "bqkv"); IVLM_W(wo, p + "wo");
+        IVLM_W(bo, p + "bo"); IVLM_W(ln2g, p + "ln2g"); IVLM_W(ln2b, p + "ln2b"); IVLM_W(w1, p + "w1"); IVLM_W(b1, p + "b1");
+        IVLM_W(w2, p + "w2"); IVLM_W(b2, p + "b2");
+        IVLM_TRY(ivlm_layernorm_bf16(h, x, y, ln1g, ln1b, rows, C, d.clip_eps, nullptr, 0, stream));
+        IVLM_TRY(gemm(h, y, C, wqkv, C, qkv, 3 * C, rows, 3 * C, C, bqkv, 0, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+        ivlm_attn_args at;
+        memset(&at, 0, sizeof(at));
+        at.q = qkv; at.k = qkv + C; at.v = qkv + 2 * C; at.out = o;
+        at.q_bs = at.k_bs = at.v_bs = (int64_t)T * 3 * C; at.q_ts = at.k_ts = at.v_ts = 3 * C; at.q_hs = at.k_hs = at.v_hs = hd;
+        at.o_bs = (int64_t)T * C; at.o_ts = C; at.o_hs = hd;
+        at.B = B; at.H = nh; at.Sq = T; at.Sk = T; at.D = hd;
+        at.scale = 1.0f / sqrtf((float)hd);
+        IVLM_TRY(ivlm_attention_bf16(h, &at, stream));
+        IVLM_TRY(gemm(h, o, C, wo, C, xn, C, rows, C, C, bo, 0, x, C, nullptr, 0, 0, IVLM_BF16, stream));
+        IVLM_TRY(ivlm_layernorm_bf16(h, xn, y, ln2g, ln2b, rows, C, d.clip_eps, nullptr, 0, stream));
+        IVLM_TRY(gemm(h, y, C, w1, C, mlp, 4 * C, rows, 4 * C, C, b1, IVLM_ACT_QUICK_GELU, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+        IVLM_TRY(gemm(h, mlp, 4 * C, w2, 4 * C, x, C, rows, C, 4 * C, b2, 0, xn, C, nullptr, 0, 0, IVLM_BF16, stream));
+    }
+    IVLM_W(mm_w, "mm.w"); IVLM_W(mm_b, "mm.b");
+    IVLM_TRY(ivlm_gather_rows_bf16(h, x, a->patch_rows, patches, prow, C, stream));
+    IVLM_TRY(gemm(h, patches, C, mm_w, C, a->feats, d.llm_hidden, prow, d.llm_hidden, C, mm_b, 0, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+    return IVLM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ [SEG] head
+// text_hidden_fcs[0] on the rows that predict [SEG] (InteractVLM.py:100-112,551-556) and the camera conditioning of
+// process_embeddings (InteractVLM.py:268-294) for the released configurations: VIv1CamPoseEncoder (components.py:541-572) or no
+// conditioning.  hidden_rows [n, llm_hidden], cam [n,V,5] -> prompt [n,V,out] (+ emb [n,out], the un-gated embedding).
+extern "C" int ivlm_seg_head(ivlm_handle h, const void* hidden_rows, const void* cam, void* prompt, void* emb, int32_t n, int32_t V,
+                             void* arena_, size_t arena_bytes, void* stream) {
+    IVLM_REQUIRE(h && hidden_rows && prompt && emb && arena_ && n > 0 && V > 0, "seg_head: bad arguments");
+    IVLM_REQUIRE(h->dims_set, "seg_head: call ivlm_set_model_dims first");
+    const int D = h->dims.llm_hidden;
+    IVLM_W(fc0_w, "seg.fc0_w"); IVLM_W(fc0_b, "seg.fc0_b"); IVLM_W(fc2_w, "seg.fc2_w"); IVLM_W(fc2_b, "seg.fc2_b");
+    const int Hm = (int)fc0_w_w->shape[0], O = (int)fc2_w_w->shape[0];
+    Arena arena(arena_, arena_bytes);
+    IVLM_TAKE(y, uint16_t, (size_t)n * Hm);
+    IVLM_TRY(gemm(h, hidden_rows, D, fc0_w, D, y, Hm, n, Hm, D, fc0_b, IVLM_ACT_RELU, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+    IVLM_TRY(gemm(h, y, Hm, fc2_w, Hm, emb, O, n, O, Hm, fc2_b, 0, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+    if (find_weight(h, "seg.cam.w1") != nullptr) {
+        IVLM_REQUIRE(cam != nullptr, "seg_head: camera parameters missing");
+        IVLM_W(w1, "seg.cam.w1"); IVLM_W(b1, "seg.cam.b1"); IVLM_W(w2, "seg.cam.w2"); IVLM_W(b2, "seg.cam.b2"); IVLM_W(wv, "seg.cam.wv");
+        IVLM_W(bv, "seg.cam.bv");
+        IVLM_REQUIRE(wv_w->shape[0] == V && O == 256, "seg_head: the camera gate covers %d views of 256 channels", (int)wv_w->shape[0]);
+        IVLM_TRY(ivlm_cam_gate_bf16(h, cam, emb, w1, b1, w2, b2, wv, bv, prompt, n, V, stream));
+    } else {
+        // no conditioning: every view gets the embedding
+        IVLM_CHECK_CUDA(cudaMemcpy2DAsync(prompt, sizeof(uint16_t) * (size_t)V * O, emb, sizeof(uint16_t) * (size_t)O, sizeof(uint16_t) * (size_t)O,
+                                          (size_t)n, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+        for (int v = 1; v < V; ++v)
+            IVLM_CHECK_CUDA(cudaMemcpy2DAsync(reinterpret_cast<uint16_t*>(prompt) + (size_t)v * O, sizeof(uint16_t) * (size_t)V * O, emb,
+                                              sizeof(uint16_t) * (size_t)O, sizeof(uint16_t) * (size_t)O, (size_t)n, cudaMemcpyDeviceToDevice,
+                                              reinterpret_cast<cudaStream_t>(stream)));
+    }
+    return IVLM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ prompt encoder + mask decoder
+namespace ivlm {
+struct DecAttnW { const Weight *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo; };
+static bool dec_attn_weights(ivlm_ctx* h, const std::string& p, DecAttnW& w) {
+    w.wq = find_weight(h, p + "wq"); w.bq = find_weight(h, p + "bq"); w.wk = find_weight(h, p + "wk"); w.bk = find_weight(h, p + "bk");
+    w.wv = find_weight(h, p + "wv"); w.bv = find_weight(h, p + "bv"); w.wo = find_weight(h, p + "wo"); w.bo = find_weight(h, p + "bo");
+    return w.wq && w.bq && w.wk && w.bk && w.wv && w.bv && w.wo && w.bo;
+}
+// transformer.py:185-242 Attention: q [B,Nq,C], k / v [B,Nk,C] -> out [B,Nq,C] (+ residual); qp / kp / vp / ao: scratch
+static int dec_attn(ivlm_ctx* h, const DecAttnW& w, const void* q, const void* k, const void* v, const void* residual, void* out, int B, int Nq,
+                    int Nk, int C, int heads, uint16_t* qp, uint16_t* kp, uint16_t* vp, uint16_t* ao, void* stream) {
+    const int I = (int)w.wq->shape[0];   // internal width (C, or C / downsample_rate for the cross attentions)
+    IVLM_TRY(gemm(h, q, C, w.wq->ptr, C, qp, I, B * Nq, I, C, w.bq->ptr, 0, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+    IVLM_TRY(gemm(h, k, C, w.wk->ptr, C, kp, I, B * Nk, I, C, w.bk->ptr, 0, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+    IVLM_TRY(gemm(h, v, C, w.wv->ptr, C, vp, I, B * Nk, I, C, w.bv->ptr, 0, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+    IVLM_TRY(ivlm_attn_small_bf16(h, qp, kp, vp, ao, B, 0, Nq, Nk, heads, I / heads, stream));
+    return gemm(h, ao, I, w.wo->ptr, I, out, C, B * Nq, C, I, w.bo->ptr, 0, residual, C, nullptr, 0, 0, IVLM_BF16, stream);
+}
+}  // namespace ivlm
+
+extern "C" size_t ivlm_mask_decode_arena_bytes(ivlm_handle h, int32_t n, int32_t V) {
+    if (!h || !h->dims_set || n <= 0 || V <= 0) return 0;
+    const ivlm_model_dims& d = h->dims;
+    const size_t g = d.sam_img / d.sam_patch, S = g * g, C = d.sam_out_chans, nv = (size_t)n * V, ntok = 5 + (size_t)V;
+    // image side: keys (two), k, kp, vp, ao(image->token out), up1 (two): 8 buffers of nv*S*C; token side: a handful of nv*ntok*2048
+    return 2 * (8 * nv * S * C + 12 * nv * ntok * 2048) + (size_t)(5 + nv) * C * 2 + 64 * 256;
+}
+
+// ModifiedSAM.forward -> PromptEncoder (text tokens as sparse prompts, no_mask dense embedding, dense PE) -> MaskDecoder.predict_masks
+// (InteractVLM.py:40-63, prompt_encoder.py:140-186, mask_decoder.py:116-164, transformer.py:62-182): emb [n*V, S, C] token-major,
+// prompt [n, V, C] -> low-res logits [n*V, 4g, 4g] fp32.  Every view of a sample sees the 5 output tokens + the sample's V prompt
+// tokens.  The launch sequence of model.py's _Engine.mask_decode; weights "dec.*"; tok_idx [n*V*(5+V)]: row of the token table
+// [out_tokens (5 rows); prompt (n*V rows)] that makes up token row r.
+extern "C" int ivlm_mask_decode(ivlm_handle h, const ivlm_mask_decode_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    IVLM_REQUIRE(h && a && a->emb && a->prompt && a->lowres && a->tok_idx && a->arena && a->n > 0 && a->V > 0 && a->heads > 0,
+                 "mask_decode: bad arguments");
+    IVLM_REQUIRE(h->dims_set, "mask_decode: call ivlm_set_model_dims first");
+    const ivlm_model_dims& d = h->dims;
+    const int g = d.sam_img / d.sam_patch, S = g * g, C = d.sam_out_chans, n = a->n, V = a->V, nv = n * V, heads = a->heads;
+    IVLM_W(out_tokens, "dec.out_tokens"); IVLM_W(no_mask, "dec.no_mask"); IVLM_W(dense_pe, "dec.dense_pe");
+    const int n_out = (int)out_tokens_w->shape[0], ntok = n_out + V, QT = nv * ntok;
+    IVLM_REQUIRE(n_out == 5 || n_out >= 1, "mask_decode: malformed output tokens");
+    Arena arena(a->arena, a->arena_bytes);
+    const size_t img = (size_t)nv * S * C, tk = (size_t)QT * 2048;
+    IVLM_TAKE(table, uint16_t, (size_t)(n_out + nv) * C);
+    IVLM_TAKE(tokens, uint16_t, (size_t)QT * C);
+    IVLM_TAKE(qa, uint16_t, (size_t)QT * C);
+    IVLM_TAKE(qb, uint16_t, (size_t)QT * C);
+    IVLM_TAKE(qc, uint16_t, (size_t)QT * C);
+    IVLM_TAKE(qpe, uint16_t, (size_t)QT * C);
+    IVLM_TAKE(tq, uint16_t, tk);      // token-side projections / mlp hidden
+    IVLM_TAKE(tk_, uint16_t, tk);
+    IVLM_TAKE(tv, uint16_t, tk);
+    IVLM_TAKE(ta, uint16_t, tk);
+    IVLM_TAKE(keys_a, uint16_t, img);
+    IVLM_TAKE(keys_b, uint16_t, img);
+    IVLM_TAKE(kpe, uint16_t, img);
+    IVLM_TAKE(ip, uint16_t, img);     // image-side projections (internal width <= C)
+    IVLM_TAKE(iv, uint16_t, img);
+    IVLM_TAKE(ia, uint16_t, img);
+    IVLM_TAKE(up_a, uint16_t, img);
+    IVLM_TAKE(up_b, uint16_t, img);
+    // token table -> tokens [nv, ntok, C] (the query positional encoding of the decoder)
+    IVLM_CHECK_CUDA(cudaMemcpyAsync(table, out_tokens, sizeof(uint16_t) * (size_t)n_out * C, cudaMemcpyDeviceToDevice, stream));
+    IVLM_CHECK_CUDA(cudaMemcpyAsync(table + (size_t)n_out * C, a->prompt, sizeof(uint16_t) * (size_t)nv * C, cudaMemcpyDeviceToDevice, stream));
+    IVLM_TRY(ivlm_gather_rows_bf16(h, table, a->tok_idx, tokens, QT, C, stream_));
+    IVLM_TRY(ivlm_add_bcast_bf16(h, a->emb, no_mask, keys_a, (int64_t)img, C, stream_));
+    uint16_t *keys = keys_a, *keys_n = keys_b;
+    const uint16_t* queries = tokens;
+    uint16_t* qbuf[3] = {qa, qb, qc};
+    int qi = 0;
+    auto next_q = [&]() { uint16_t* r = qbuf[qi]; qi = (qi + 1) % 3; return r; };
+    int depth = 0;
+    while (find_weight(h, "dec." + std::to_string(depth) + ".w1") != nullptr) ++depth;
+    IVLM_REQUIRE(depth > 0, "mask_decode: no decoder layers bound (dec.0.*)");
+    for (int i = 0; i < depth; ++i) {
+        const std::string p = "dec." + std::to_string(i) + ".";
+        DecAttnW sa, t2i, i2t;
+        IVLM_REQUIRE(dec_attn_weights(h, p + "self.", sa) && dec_attn_weights(h, p + "t2i.", t2i) && dec_attn_weights(h, p + "i2t.", i2t),
+                     "mask_decode: attention weights of layer %d are not bound", i);
+        IVLM_W(n0g, p + "n0g"); IVLM_W(n0b, p + "n0b"); IVLM_W(n1g, p + "n1g"); IVLM_W(n1b, p + "n1b"); IVLM_W(n2g, p + "n2g");
+        IVLM_W(n2b, p + "n2b"); IVLM_W(n3g, p + "n3g"); IVLM_W(n3b, p + "n3b"); IVLM_W(w1, p + "w1"); IVLM_W(b1, p + "b1");
+        IVLM_W(w2, p + "w2"); IVLM_W(b2, p + "b2");
+        const int Fm = (int)w1_w->shape[0];
+        IVLM_REQUIRE(Fm <= 2048, "mask_decode: mlp width %d exceeds the scratch rows (2048)", Fm);
+        uint16_t* t0 = next_q();
+        if (i == 0) {
+            IVLM_TRY(dec_attn(h, sa, queries, queries, queries, nullptr, t0, nv, ntok, ntok, C, heads, tq, tk_, tv, ta, stream_));
+        } else {
+            IVLM_TRY(ivlm_add_bcast_bf16(h, queries, tokens, qpe, (int64_t)QT * C, 0, stream_));
+            IVLM_TRY(dec_attn(h, sa, qpe, qpe, queries, queries, t0, nv, ntok, ntok, C, heads, tq, tk_, tv, ta, stream_));
+        }
+        uint16_t* t1 = next_q();
+        IVLM_TRY(ivlm_layernorm_bf16(h, t0, t1, n0g, n0b, QT, C, 1e-5f, nullptr, 0, stream_));
+        IVLM_TRY(ivlm_add_bcast_bf16(h, t1, tokens, qpe, (int64_t)QT * C, 0, stream_));
+        IVLM_TRY(ivlm_add_bcast_bf16(h, keys, dense_pe, kpe, (int64_t)img, (int64_t)S * C, stream_));
+        uint16_t* t2 = next_q();   // == t0's buffer two steps later: t0 is dead
+        IVLM_TRY(dec_attn(h, t2i, qpe, kpe, keys, t1, t2, nv, ntok, S, C, heads, tq, ip, iv, ta, stream_));
+        uint16_t* t3 = next_q();
+        IVLM_TRY(ivlm_layernorm_bf16(h, t2, t3, n1g, n1b, QT, C, 1e-5f, nullptr, 0, stream_));
+        IVLM_TRY(gemm(h, t3, C, w1, C, tq, Fm, QT, Fm, C, b1, IVLM_ACT_RELU, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream_));
+        uint16_t* t4 = next_q();
+        IVLM_TRY(gemm(h, tq, Fm, w2, Fm, t4, C, QT, C, Fm, b2, 0, t3, C, nullptr, 0, 0, IVLM_BF16, stream_));
+        uint16_t* t5 = next_q();
+        IVLM_TRY(ivlm_layernorm_bf16(h, t4, t5, n2g, n2b, QT, C, 1e-5f, nullptr, 0, stream_));
+        IVLM_TRY(ivlm_add_bcast_bf16(h, t5, tokens, qpe, (int64_t)QT * C, 0, stream_));
+        // image -> token: queries are the image tokens (+ pe), keys the decoder tokens (+ pe), values the decoder tokens
+        IVLM_TRY(dec_attn(h, i2t, kpe, qpe, t5, keys, keys_n, nv, S, ntok, C, heads, ip, tk_, tv, ia, stream_));
+        IVLM_TRY(ivlm_layernorm_bf16(h, keys_n, keys, n3g, n3b, (int64_t)nv * S, C, 1e-5f, nullptr, 0, stream_));
+        queries = t5;
+    }
+    DecAttnW fin;
+    IVLM_REQUIRE(dec_attn_weights(h, "dec.final.", fin), "mask_decode: final attention weights are not bound");
+    IVLM_W(nfg, "dec.nfg"); IVLM_W(nfb, "dec.nfb");
+    IVLM_TRY(ivlm_add_bcast_bf16(h, queries, tokens, qpe, (int64_t)QT * C, 0, stream_));
+    IVLM_TRY(ivlm_add_bcast_bf16(h, keys, dense_pe, kpe, (int64_t)img, (int64_t)S * C, stream_));
+    uint16_t* f0 = next_q();
+    if (f0 == queries) f0 = next_q();
+    IVLM_TRY(dec_attn(h, fin, qpe, kpe, keys, queries, f0, nv, ntok, S, C, heads, tq, ip, iv, ta, stream_));
+    uint16_t* hs = next_q();
+    if (hs == queries) hs = next_q();
+    IVLM_TRY(ivlm_layernorm_bf16(h, f0, hs, nfg, nfb, QT, C, 1e-5f, nullptr, 0, stream_));
+    // mask token 0 (row 1 of every view: row 0 is the IoU token) -> hypernetwork MLP
+    uint16_t* mt = tq;
+    IVLM_CHECK_CUDA(cudaMemcpy2DAsync(mt, sizeof(uint16_t) * (size_t)C, hs + C, sizeof(uint16_t) * (size_t)ntok * C, sizeof(uint16_t) * (size_t)C,
+                                      (size_t)nv, cudaMemcpyDeviceToDevice, stream));
+    IVLM_W(hw0, "dec.hyper0_w"); IVLM_W(hb0, "dec.hyper0_b"); IVLM_W(hw1, "dec.hyper1_w"); IVLM_W(hb1, "dec.hyper1_b");
+    IVLM_W(hw2, "dec.hyper2_w"); IVLM_W(hb2, "dec.hyper2_b");
+    const int Hh = (int)hw0_w->shape[0], Ho = (int)hw2_w->shape[0];
+    IVLM_TRY(gemm(h, mt, C, hw0, C, tk_, Hh, nv, Hh, C, hb0, IVLM_ACT_RELU, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream_));
+    IVLM_TRY(gemm(h, tk_, Hh, hw1, Hh, tv, Hh, nv, Hh, Hh, hb1, IVLM_ACT_RELU, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream_));
+    IVLM_TRY(gemm(h, tv, Hh, hw2, Hh, ta, Ho, nv, Ho, Hh, hb2, 0, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream_));
+    IVLM_W(up0_w, "dec.up0_w"); IVLM_W(up0_b, "dec.up0_b"); IVLM_W(up_lng, "dec.up_lng"); IVLM_W(up_lnb, "dec.up_lnb");
+    IVLM_W(up3_w, "dec.up3_w"); IVLM_W(up3_b, "dec.up3_b");
+    const int U = (int)up0_w_w->shape[0];   // 4 * co
+    IVLM_REQUIRE(U == C && Ho == 32 && U / 4 == 64, "mask_decode: the fused upscaling covers SAM's 256 -> 64 -> 32 channels");
+    IVLM_TRY(gemm(h, keys, C, up0_w, C, up_a, U, nv * S, U, C, up0_b, 0, nullptr, 0, nullptr, 0, -1, IVLM_BF16, stream_));
+    IVLM_TRY(ivlm_layernorm_bf16(h, up_a, up_b, up_lng, up_lnb, (int64_t)nv * S * 4, U / 4, 1e-6f, nullptr, IVLM_ACT_GELU, stream_));
+    return ivlm_upscale_hyper_dot(h, up_b, up3_w, up3_b, ta, a->lowres, nv, g, stream_);
+}

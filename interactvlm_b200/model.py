@@ -185,6 +185,36 @@ class _Weights:
         for i, bw in enumerate(self.sam["blocks"]):
             for k, t in bw.items():
                 nm[f"sam.blocks.{i}.{k}"] = t
+        # CLIP tower + projector (ivlm_clip_encode)
+        for k in ("w_patch", "pos", "cls_pos", "pre_g", "pre_b"):
+            nm["clip." + k] = self.clip[k]
+        for i, lw in enumerate(self.clip["layers"]):
+            for k, t in lw.items():
+                nm[f"clip.{i}.{k}"] = t
+        nm["mm.w"], nm["mm.b"] = self.mm_w, self.mm_b
+        # [SEG] head (ivlm_seg_head): text_hidden_fcs + the vi_v1 camera gate
+        nm["seg.fc0_w"], nm["seg.fc0_b"], nm["seg.fc2_w"], nm["seg.fc2_b"] = self.fc
+        if self.cam is not None and self.cam_type == "vi_v1":
+            for k, t in zip(("w1", "b1", "w2", "b2", "wv", "bv"), self.cam):
+                nm["seg.cam." + k] = t
+        # prompt-encoder constants + mask decoder (ivlm_mask_decode)
+        dd = self.dec
+        nm["dec.out_tokens"], nm["dec.no_mask"], nm["dec.dense_pe"] = dd["out_tokens"], self.no_mask, self.dense_pe
+        for i, lw in enumerate(dd["layers"]):
+            for an, key in (("self", "self_attn"), ("t2i", "t2i"), ("i2t", "i2t")):
+                for k, t in lw[key].items():
+                    nm[f"dec.{i}.{an}.{k}"] = t
+            for j, (gm, bt) in enumerate(lw["n"]):
+                nm[f"dec.{i}.n{j}g"], nm[f"dec.{i}.n{j}b"] = gm, bt
+            for k in ("w1", "b1", "w2", "b2"):
+                nm[f"dec.{i}.{k}"] = lw[k]
+        for k, t in dd["final"].items():
+            nm["dec.final." + k] = t
+        nm["dec.nfg"], nm["dec.nfb"] = dd["nfg"], dd["nfb"]
+        for j, (wt, bs) in enumerate(dd["hyper"]):
+            nm[f"dec.hyper{j}_w"], nm[f"dec.hyper{j}_b"] = wt, bs
+        nm["dec.up0_w"], nm["dec.up0_b"], nm["dec.up_lng"], nm["dec.up_lnb"] = dd["up0_w"], dd["up0_b"], dd["up_ln"][0], dd["up_ln"][1]
+        nm["dec.up3_w"], nm["dec.up3_b"] = dd["up3_w"], dd["up3_b"]
 
     @staticmethod
     def _dense_pe(G, cfg):
@@ -237,6 +267,14 @@ class _Engine:
         C, nh = cfg.clip_hidden_size, cfg.clip_num_attention_heads
         hd = C // nh
         T = cfg.clip_tokens
+        if self.stage_abi and self.trace is None and not ctx.profiling:
+            # one C call (ivlm_clip_encode): the launch sequence below, driven from the library
+            key = ("clip_rows", B)
+            if key not in self._win_maps:
+                rm_ = (torch.arange(B, dtype=torch.int32)[:, None] * T + 1 + torch.arange(T - 1, dtype=torch.int32)[None]).reshape(-1)
+                self._win_maps[key] = (rm_.to(self.device), (torch.arange(B, dtype=torch.int32) * T).to(self.device))
+            self._bind()
+            return ctx.clip_encode_stage(images_clip.contiguous(), *self._win_maps[key])
         cols = ctx.im2col_patch(images_clip.contiguous(), cfg.clip_patch_size, ldk=self.w.clip_ldk)
         rm = (torch.arange(B, dtype=torch.int32)[:, None] * T + 1 + torch.arange(T - 1, dtype=torch.int32)[None]).reshape(-1)
         h = torch.empty((B * T, C), device=self.device, dtype=torch.bfloat16)
@@ -511,6 +549,10 @@ class _Engine:
         (InteractVLM.py:268-294,551-556)."""
         ctx, w, cfg = self.ctx, self.w, self.cfg
         V = cfg.multiview_channels
+        if (self.stage_abi and self.trace is None and not ctx.profiling and w.splitter is None and (w.cam is None or w.cam_type == "vi_v1")
+                and w.fc[2].shape[0] == 256):
+            self._bind()   # one C call (ivlm_seg_head) for the released configurations
+            return ctx.seg_head_stage(hidden_rows.contiguous(), cam_params.contiguous() if w.cam is not None else None, V)
         y = ctx.gemm(hidden_rows, w.fc[0], bias=w.fc[1], act=ACT_RELU)
         emb = ctx.gemm(y, w.fc[2], bias=w.fc[3])
         n = emb.shape[0]
@@ -567,6 +609,18 @@ class _Engine:
         nv, S = emb.shape[0], emb.shape[1]
         heads = cfg.sam_dec_heads
         ntok = w["out_tokens"].shape[0] + V
+        if (self.stage_abi and self.trace is None and not ctx.profiling and w["up0_w"].shape[0] == C and w["hyper"][2][0].shape[0] == 32
+                and w["layers"][0]["w1"].shape[0] <= 2048 and S == cfg.sam_grid ** 2 and C == cfg.sam_out_chans):
+            # one C call (ivlm_mask_decode): the launch sequence below, driven from the library
+            key = ("tok_idx", n, V)
+            if key not in self._win_maps:
+                n_out = ntok - V
+                t = np.arange(ntok)[None, None, :]
+                smp = np.arange(n)[:, None, None]
+                idx = np.where(t < n_out, t, n_out + smp * V + (t - n_out)) + np.zeros((n, V, 1), np.int64)
+                self._win_maps[key] = _i32(idx.reshape(-1), self.device)
+            self._bind()
+            return ctx.mask_decode_stage(emb.contiguous(), prompt.contiguous(), self._win_maps[key], heads, cfg.sam_grid)
         tokens = torch.empty((n, V, ntok, C), device=self.device, dtype=torch.bfloat16)
         tokens[:, :, : ntok - V] = w["out_tokens"]
         tokens[:, :, ntok - V:] = prompt[:, None]

@@ -144,6 +144,9 @@ class Context:
         d.llm_hidden, d.llm_intermediate, d.llm_layers = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
         d.llm_heads, d.llm_head_dim, d.llm_vocab = cfg.num_attention_heads, cfg.head_dim, cfg.vocab_size
         d.llm_rms_eps, d.llm_paired_layout = cfg.rms_norm_eps, 1 if paired_layout else 0
+        d.clip_img, d.clip_patch, d.clip_hidden = cfg.clip_image_size, cfg.clip_patch_size, cfg.clip_hidden_size
+        d.clip_heads, d.clip_layers = cfg.clip_num_attention_heads, cfg.clip_layers_used
+        d.clip_ldk, d.clip_eps = (3 * cfg.clip_patch_size ** 2 + 7) // 8 * 8, cfg.clip_layer_norm_eps
         L.check(self.lib.ivlm_set_model_dims(self.h, C.byref(d)), "set_model_dims")
         self._dims = d
 
@@ -164,6 +167,49 @@ class Context:
         a.arena, a.arena_bytes = arena.data_ptr(), nbytes
         L.check(self.lib.ivlm_sam_encode(self.h, C.byref(a), self.stream), "sam_encode")
         return emb
+
+    def clip_encode_stage(self, images, patch_rows, cls_rows):
+        """ivlm_clip_encode: [B,3,S,S] bf16 -> projected patch features [B, T-1, llm_hidden] bf16 in one call."""
+        _bf16(images)
+        assert images.is_contiguous() and patch_rows.dtype == torch.int32 and cls_rows.dtype == torch.int32
+        B, d = images.shape[0], self._dims
+        T1 = (d.clip_img // d.clip_patch) ** 2
+        feats = torch.empty((B, T1, d.llm_hidden), device=images.device, dtype=torch.bfloat16)
+        nbytes = int(self.lib.ivlm_clip_encode_arena_bytes(self.h, i32(B)))
+        arena = torch.empty(nbytes, device=images.device, dtype=torch.uint8)
+        a = L.ClipEncodeArgs()
+        a.images, a.feats, a.B = images.data_ptr(), feats.data_ptr(), B
+        a.patch_rows, a.cls_rows = patch_rows.data_ptr(), cls_rows.data_ptr()
+        a.arena, a.arena_bytes = arena.data_ptr(), nbytes
+        L.check(self.lib.ivlm_clip_encode(self.h, C.byref(a), self.stream), "clip_encode")
+        return feats
+
+    def seg_head_stage(self, hidden_rows, cam_params, V, out_dim=256):
+        """ivlm_seg_head: [n, D] hidden rows (+ [n,V,5] camera parameters) -> prompt [n,V,out_dim], emb [n,out_dim]."""
+        _bf16(hidden_rows)
+        assert hidden_rows.is_contiguous() and (cam_params is None or cam_params.is_contiguous())
+        n = hidden_rows.shape[0]
+        prompt = torch.empty((n, V, out_dim), device=hidden_rows.device, dtype=torch.bfloat16)
+        emb = torch.empty((n, out_dim), device=hidden_rows.device, dtype=torch.bfloat16)
+        arena = torch.empty(n * hidden_rows.shape[1] * 2 + 4096, device=hidden_rows.device, dtype=torch.uint8)
+        L.check(self.lib.ivlm_seg_head(self.h, P(hidden_rows), P(cam_params) if cam_params is not None else None, P(prompt), P(emb), i32(n), i32(V),
+                                       P(arena), C.c_size_t(arena.numel()), self.stream), "seg_head")
+        return prompt, emb
+
+    def mask_decode_stage(self, emb, prompt, tok_idx, heads, grid):
+        """ivlm_mask_decode: emb [n*V, S, C], prompt [n, V, C] -> low-res logits [n*V, 4*grid, 4*grid] fp32 in one call."""
+        _bf16(emb); _bf16(prompt)
+        assert emb.is_contiguous() and prompt.is_contiguous() and tok_idx.dtype == torch.int32
+        n, V = prompt.shape[0], prompt.shape[1]
+        low = torch.empty((n * V, 4 * grid, 4 * grid), device=emb.device, dtype=torch.float32)
+        nbytes = int(self.lib.ivlm_mask_decode_arena_bytes(self.h, i32(n), i32(V)))
+        arena = torch.empty(nbytes, device=emb.device, dtype=torch.uint8)
+        a = L.MaskDecodeArgs()
+        a.emb, a.prompt, a.lowres = emb.data_ptr(), prompt.data_ptr(), low.data_ptr()
+        a.n, a.V, a.heads, a.tok_idx = n, V, heads, tok_idx.data_ptr()
+        a.arena, a.arena_bytes = arena.data_ptr(), nbytes
+        L.check(self.lib.ivlm_mask_decode(self.h, C.byref(a), self.stream), "mask_decode")
+        return low
 
     def llm_arena(self, tokens, device):
         nbytes = int(self.lib.ivlm_llm_arena_bytes(self.h, i32(tokens)))

@@ -214,6 +214,7 @@ def test_chained_decode_step_is_bit_identical(ctx):
     model = InteractVLMForCausalLM(cfg, S.make_state_dict(cfg, seed=TINY_SEED["weights"]), ctx=ctx)
     ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
     outs = {}
+    model.eng.stage_abi = False          # the op-level decode step (the C stage driver always issues the five launches)
     for chained in (False, True):
         model.eng.chained_decode = chained
         model._graphs = {}
@@ -221,5 +222,6 @@ def test_chained_decode_step_is_bit_identical(ctx):
         out_ids, hid = model.generate(clip, ids, max_new_tokens=ans.shape[1], scripted=ans)
         outs[chained] = (out_ids.clone(), hid.clone(), ctx.launch_count() - n0)
     model.eng.chained_decode = False
+    model.eng.stage_abi = True
     assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
     assert outs[True][2] < outs[False][2]

@@ -391,7 +391,8 @@ def test_prompts_of_different_lengths_in_one_batch(tiny):
 
 
 def test_stage_level_abi_is_bit_identical_to_the_op_level_path(tiny):
-    """ivlm_sam_encode / ivlm_llm_prefill / ivlm_llm_decode_step (one C call per stage over a caller arena) against the op-by-op
+    """ivlm_clip_encode / ivlm_sam_encode / ivlm_llm_prefill / ivlm_llm_decode_step / ivlm_seg_head / ivlm_mask_decode (one C call
+    per stage over a caller arena) against the op-by-op
     loops of _Engine: the same kernels in the same order -> identical bits, fewer host calls."""
     cfg, sd, model, _ = tiny
     ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
@@ -417,3 +418,16 @@ def test_stage_level_abi_is_bit_identical_to_the_op_level_path(tiny):
     emb_o = model.eng.sam_encode(sam[0].cuda().bfloat16())
     model.eng.stage_abi = True
     assert torch.equal(emb_s, emb_o)
+    # ivlm_clip_encode / ivlm_seg_head / ivlm_mask_decode, stage by stage
+    g = torch.Generator().manual_seed(5)
+    hid = (torch.randn(2, cfg.hidden_size, generator=g)).bfloat16().cuda()
+    res = {}
+    for stage in (True, False):
+        model.eng.stage_abi = stage
+        feats = model.eng.clip_encode(clip.cuda().bfloat16())
+        prompt, emb = model.eng.seg_prompt(hid, cam.cuda().bfloat16())
+        low = model.eng.mask_decode(emb_s.repeat(2, 1, 1)[: 2 * cfg.multiview_channels].contiguous(), prompt)
+        res[stage] = (feats, prompt, emb, low)
+    model.eng.stage_abi = True
+    for name, x, y in zip(("clip", "prompt", "emb", "lowres"), res[True], res[False]):
+        assert torch.equal(x, y), name
