@@ -305,8 +305,10 @@ extern "C" size_t ivlm_clip_encode_arena_bytes(ivlm_handle h, int32_t B) {
     if (!h || !h->dims_set || B <= 0 || h->dims.clip_hidden <= 0) return 0;
     const ivlm_model_dims& d = h->dims;
     const size_t g = d.clip_img / d.clip_patch, T = g * g + 1, C = d.clip_hidden, rows = (size_t)B * T;
-    // cols [B*(T-1), ldk]; h (two), y, o: rows x C; qkv: rows x 3C; mlp: rows x 4C; patches: B*(T-1) x C
-    return 2 * ((size_t)B * (T - 1) * d.clip_ldk + 4 * rows * C + 3 * rows * C + 4 * rows * C + (size_t)B * (T - 1) * C) + 16 * 256;
+    const Weight* w1 = find_weight(h, "clip.0.w1");
+    const size_t F = w1 ? (size_t)w1->shape[0] : 4 * C;   // mlp width
+    // cols [B*(T-1), ldk]; h (two), y, o: rows x C; qkv: rows x 3C; mlp: rows x F; patches: B*(T-1) x C
+    return 2 * ((size_t)B * (T - 1) * d.clip_ldk + 4 * rows * C + 3 * rows * C + F * rows + (size_t)B * (T - 1) * C) + 16 * 256;
 }
 
 // CLIPVisionTower.forward + feature_select('patch', layer -2) + mm_projector (clip_encoder.py:31-60, llava_arch.py:93-96):
@@ -325,7 +327,10 @@ extern "C" int ivlm_clip_encode(ivlm_handle h, const ivlm_clip_encode_args* a, v
     IVLM_TAKE(y, uint16_t, (size_t)rows * C);
     IVLM_TAKE(o, uint16_t, (size_t)rows * C);
     IVLM_TAKE(qkv, uint16_t, (size_t)rows * 3 * C);
-    IVLM_TAKE(mlp, uint16_t, (size_t)rows * 4 * C);
+    const Weight* w1_first = find_weight(h, "clip.0.w1");
+    IVLM_REQUIRE(w1_first != nullptr, "clip_encode: weights 'clip.*' are not bound (ivlm_bind_weights)");
+    const int F = (int)w1_first->shape[0];   // mlp width (4 C for the OpenAI towers)
+    IVLM_TAKE(mlp, uint16_t, (size_t)rows * F);
     IVLM_TAKE(patches, uint16_t, (size_t)prow * C);
     IVLM_W(w_patch, "clip.w_patch"); IVLM_W(pos, "clip.pos"); IVLM_W(cls_pos, "clip.cls_pos"); IVLM_W(pre_g, "clip.pre_g"); IVLM_W(pre_b, "clip.pre_b");
     IVLM_TRY(ivlm_im2col_patch_bf16(h, a->images, cols, B, 3, d.clip_img, d.clip_img, d.clip_patch, ldk, stream));
@@ -350,8 +355,8 @@ extern "C" int ivlm_clip_encode(ivlm_handle h, const ivlm_clip_encode_args* a, v
         IVLM_TRY(ivlm_attention_bf16(h, &at, stream));
         IVLM_TRY(gemm(h, o, C, wo, C, xn, C, rows, C, C, bo, 0, x, C, nullptr, 0, 0, IVLM_BF16, stream));
         IVLM_TRY(ivlm_layernorm_bf16(h, xn, y, ln2g, ln2b, rows, C, d.clip_eps, nullptr, 0, stream));
-        IVLM_TRY(gemm(h, y, C, w1, C, mlp, 4 * C, rows, 4 * C, C, b1, IVLM_ACT_QUICK_GELU, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
-        IVLM_TRY(gemm(h, mlp, 4 * C, w2, 4 * C, x, C, rows, C, 4 * C, b2, 0, xn, C, nullptr, 0, 0, IVLM_BF16, stream));
+        IVLM_TRY(gemm(h, y, C, w1, C, mlp, F, rows, F, C, b1, IVLM_ACT_QUICK_GELU, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+        IVLM_TRY(gemm(h, mlp, F, w2, F, x, C, rows, C, F, b2, 0, xn, C, nullptr, 0, 0, IVLM_BF16, stream));
     }
     IVLM_W(mm_w, "mm.w"); IVLM_W(mm_b, "mm.b");
     IVLM_TRY(ivlm_gather_rows_bf16(h, x, a->patch_rows, patches, prow, C, stream));
