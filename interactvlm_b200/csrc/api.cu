@@ -71,6 +71,7 @@ extern "C" int ivlm_set_option(ivlm_handle h, const char* name, int32_t value) {
     if (std::string(name) == "ds_force_stream") { h->ds_force_stream = value; return IVLM_OK; }
     if (std::string(name) == "dec_warps") { h->dec_warps = value; return IVLM_OK; }
     if (std::string(name) == "ds_stages") { h->ds_stages = value; return IVLM_OK; }
+    if (std::string(name) == "attn_variant") { h->attn_variant = value; return IVLM_OK; }
     if (std::string(name) == "attn_small_variant") { h->attn_small_variant = value; return IVLM_OK; }
     if (std::string(name) == "ds_prefetch_kb") { h->ds_prefetch_kb = value; return IVLM_OK; }
     if (std::string(name) == "attn_prefetch_ahead") { h->attn_prefetch_ahead = value; return IVLM_OK; }

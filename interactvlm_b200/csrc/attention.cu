@@ -771,6 +771,14 @@ extern "C" int ivlm_attention_bf16(ivlm_handle h, const ivlm_attn_args* a, void*
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk;
     p.scale = a->scale;
     p.rel_h = a->rel_h; p.rel_w = a->rel_w; p.kh = a->kh; p.kw = a->kw;
+    {   // CLIP (head_dim 64) and LLaMA prefill (128, causal) run on the tcgen05 kernel when the layout allows
+        const int took = attention_tcgen05_try(h, a, stream);
+        if (took < 0) return IVLM_ERR_CUDA;
+        if (took == 1) {
+            h->launches++;
+            return IVLM_OK;
+        }
+    }
     if (a->D == 80) {
         return rel ? launch_fa<80, false, true>(h, p, stream) : launch_fa<80, false, false>(h, p, stream);
     } else if (a->D == 64) {

@@ -1451,6 +1451,286 @@ sam_attn_window_h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ plain / causal attention
+// softmax(q k^T * scale [+ causal mask]) v for head_dim 64 (CLIP ViT-L, 257 tokens) and 128 (LLaMA prefill, causal): the
+// structure of sam_attn_tcgen05_kernel without the rel-pos prologue.  One CTA per (128-query tile, head, sequence); warp 0 = TMA
+// producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = softmax (one query row per thread) / correction / epilogue.
+//   smem  Q [HD/64 tiles of 128 x 64, 128B-swizzled] | 2 stages x (K, V: HD/64 tiles each) | P [2 tiles of 128 x 64 keys]
+//   TMEM  S double buffer [0,128) [128,256), O [256, 256 + HD)
+// q / k / v are row-major [tokens, heads*HD] matrices (any pitch) whose sequences follow each other, described by three 2-D tensor
+// maps; rows of the next sequence (or past the end: zero-filled) that land in a tile are masked by key index / never stored.
+// Replaces the mma.sync flash_attn_kernel on this path (70-95 TFLOP/s).
+constexpr int FT_BQ = 128, FT_BK = 128, FT_NS = 2, FT_THREADS = 256, FT_O_COL = 256;
+template <int HD> struct FtCfg {
+    static constexpr int NC = HD / 64;                       // 64-column chunks of the head dimension
+    static constexpr int Q_BYTES = NC * FT_BQ * 128;
+    static constexpr int KV_BYTES = NC * FT_BK * 128;        // K or V of one stage
+    static constexpr int STAGE = 2 * KV_BYTES;
+    static constexpr int P_BYTES = FT_BQ * FT_BK * 2;
+    static constexpr int SMEM = Q_BYTES + FT_NS * STAGE + P_BYTES + 1024 + 256;
+};
+struct FtParams {
+    bf16* out;
+    long long o_bs, o_ts, o_hs;
+    int Sq, Sk;
+    float scale_log2;
+};
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(FT_THREADS, 1)
+flash_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const FtParams p) {
+    using Cfg = FtCfg<HD>;
+    constexpr int NC = Cfg::NC;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_s = smem;
+    uint8_t* stage0 = q_s + Cfg::Q_BYTES;
+    auto k_s = [&](int s) { return stage0 + s * Cfg::STAGE; };
+    auto v_s = [&](int s) { return stage0 + s * Cfg::STAGE + Cfg::KV_BYTES; };
+    uint8_t* p_s = stage0 + FT_NS * Cfg::STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + Cfg::P_BYTES);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* kv_full = bars + 1;       // FT_NS
+    uint64_t* kv_empty = bars + 3;      // FT_NS
+    uint64_t* s_full = bars + 5;        // 2
+    uint64_t* s_empty = bars + 7;       // 2
+    uint64_t* p_full = bars + 9;        // 1
+    uint64_t* pv_done = bars + 10;      // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * FT_BQ, h = blockIdx.y, b = blockIdx.z;
+    const int off = p.Sk - p.Sq;                     // causal offset: query i sees keys <= i + off
+    int kv_end = p.Sk;
+    if (CAUSAL) kv_end = min(p.Sk, q0 + FT_BQ + off);
+    const int n_tiles = (kv_end + FT_BK - 1) / FT_BK;
+    const int q_row = b * p.Sq + q0, k_row = b * p.Sk;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < FT_NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
+        mbar_init(p_full, 4);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) tma_load_2d(q_s + c * (FT_BQ * 128), &tmQ, q_full, h * HD + c * 64, q_row);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % FT_NS;
+                if (j >= FT_NS) mbar_wait(&kv_empty[s], ((j / FT_NS) - 1) & 1);
+                mbar_arrive_expect_tx(&kv_full[s], Cfg::STAGE);
+                const int r = k_row + j * FT_BK;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    tma_load_2d(k_s(s) + c * (FT_BK * 128), &tmK, &kv_full[s], h * HD + c * 64, r);
+                    tma_load_2d(v_s(s) + c * (FT_BK * 128), &tmV, &kv_full[s], h * HD + c * 64, r);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            mbar_wait(q_full, 0);
+            auto issue_s = [&](int j) {
+                const int s = j % FT_NS, sb = j & 1;
+                mbar_wait(&kv_full[s], (j / FT_NS) & 1);
+                if (j >= 2) mbar_wait(&s_empty[sb], ((j >> 1) - 1) & 1);
+                tc_fence_after();
+                constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const uint64_t da = umma_desc_sw128_kmajor(smem_u32(q_s + c * (FT_BQ * 128)));
+                    const uint64_t db = umma_desc_sw128_kmajor(smem_u32(k_s(s) + c * (FT_BK * 128)));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + sb * FT_BK, da + 2 * k, db + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&s_full[sb]);
+            };
+            issue_s(0);
+            constexpr uint32_t idesc64 = umma_idesc_bf16_bmn(128, 64);
+            for (int j = 0; j < n_tiles; ++j) {
+                if (j + 1 < n_tiles) issue_s(j + 1);
+                const int s = j % FT_NS;
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < FT_BK / 16; ++ks) {
+                    const uint64_t dp = umma_desc_sw128_kmajor(smem_u32(p_s + (ks >> 2) * (FT_BQ * 128))) + 2 * (ks & 3);
+                    const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+                        umma_bf16(tmem_base + FT_O_COL + c * 64, dp, umma_desc_sw128_mnmajor(smem_u32(v_s(s) + c * (FT_BK * 128) + ks * 2048)),
+                                  idesc64, acc);
+                }
+                umma_commit(&kv_empty[s]);
+                umma_commit(pv_done);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ softmax / correction / epilogue
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;  // query row inside the tile == TMEM lane
+        const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16);
+        const int qtok = q0 + r;
+        const int k_last = CAUSAL ? min(qtok + off, p.Sk - 1) : p.Sk - 1;   // last key this row attends to
+        float m_ref = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int sb = j & 1;
+            mbar_wait(&s_full[sb], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t xr[FT_BK];
+#pragma unroll
+            for (int c0 = 0; c0 < FT_BK; c0 += 32)
+                tmem_ld_32x32(lane_addr + sb * FT_BK + c0, reinterpret_cast<uint32_t(&)[32]>(xr[c0]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[sb]);
+            float x[FT_BK];
+            float mx = -INFINITY;
+            const int kbase = j * FT_BK;
+#pragma unroll
+            for (int c = 0; c < FT_BK; ++c) {
+                x[c] = (kbase + c <= k_last) ? __uint_as_float(xr[c]) * p.scale_log2 : -INFINITY;
+                mx = fmaxf(mx, x[c]);
+            }
+            // online softmax with lazy rescaling (see sam_attn_tcgen05_kernel); a row whose keys are all masked keeps m_ref
+            float corr = 1.f;
+            bool moved = false;
+            if (m_ref == -INFINITY) {
+                m_ref = mx;          // first tile with a live key (tile 0 always has one for rows < Sq)
+            } else if (mx > m_ref + 8.f) {
+                corr = ex2_approx(m_ref - mx);
+                m_ref = mx;
+                moved = true;
+            }
+            const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
+            float sum = 0.f;
+            uint32_t pk[FT_BK / 2];
+#pragma unroll
+            for (int c = 0; c < FT_BK; c += 2) {
+                const float p0 = ex2_approx(x[c] - mr), p1 = ex2_approx(x[c + 1] - mr);
+                sum += p0 + p1;
+                pk[c >> 1] = pack_bf16x2(p0, p1);
+            }
+            l_run = l_run * corr + sum;
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, moved)) {
+#pragma unroll
+                    for (int c0 = 0; c0 < HD; c0 += 16) {
+                        uint32_t o[16];
+                        tmem_ld_32x16(lane_addr + FT_O_COL + c0, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                        tmem_st_32x16(lane_addr + FT_O_COL + c0, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint8_t* row = p_s + ch * (FT_BQ * 128) + r * 128;
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {
+                    const int i = ch * 32 + c16 * 4;
+                    *reinterpret_cast<uint4*>(row + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(pv_done, (n_tiles - 1) & 1);
+        tc_fence_after();
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        bf16* orow = p.out + (long long)b * p.o_bs + (long long)qtok * p.o_ts + (long long)h * p.o_hs;
+#pragma unroll
+        for (int c0 = 0; c0 < HD; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld_32x16(lane_addr + FT_O_COL + c0, o);
+            tmem_ld_wait();
+            if (qtok < p.Sq) {
+                uint4 u0, u1;
+                u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+                u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+                u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+                u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+                u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+                reinterpret_cast<uint4*>(orow + c0)[0] = u0;
+                reinterpret_cast<uint4*>(orow + c0)[1] = u1;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int HD, bool CAUSAL>
+static int launch_ft(ivlm_ctx* h, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv, const FtParams& p, dim3 grid,
+                     cudaStream_t stream) {
+    using Cfg = FtCfg<HD>;
+    const uint64_t bit = 1ull << (24 + (HD == 128 ? 0 : 2) + (CAUSAL ? 1 : 0));
+    if (!(h->attr_done & bit)) {
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_tcgen05_kernel<HD, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        h->attr_done |= bit;
+    }
+    flash_attn_tcgen05_kernel<HD, CAUSAL><<<grid, FT_THREADS, Cfg::SMEM, stream>>>(*tq, *tk, *tv, p);
+    IVLM_CHECK_CUDA(cudaGetLastError());
+    return IVLM_OK;
+}
+
+// Returns 1 when the launch was taken by the tcgen05 kernel, 0 when the layout does not fit it (the caller falls back to
+// flash_attn_kernel), < 0 on error.
+int attention_tcgen05_try(ivlm_ctx* h, const ivlm_attn_args* a, cudaStream_t stream) {
+    if (h->attn_variant == 1 || a->rel_h != nullptr || (a->D != 64 && a->D != 128)) return 0;
+    // sequences follow each other with one row pitch, heads are HD apart, 16-byte aligned bases / pitches / outputs
+    if (a->q_hs != a->D || a->k_hs != a->D || a->v_hs != a->D) return 0;
+    if (a->q_bs != (int64_t)a->Sq * a->q_ts || a->k_bs != (int64_t)a->Sk * a->k_ts || a->v_bs != (int64_t)a->Sk * a->v_ts) return 0;
+    if (a->q_ts % 8 || a->k_ts % 8 || a->v_ts % 8 || a->o_ts % 8 || a->o_hs % 8 || a->o_bs % 8) return 0;
+    if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
+         reinterpret_cast<uintptr_t>(a->out)) & 15) return 0;
+    const uint64_t cols = (uint64_t)a->H * a->D;
+    const CUtensorMap *tq, *tk, *tv;
+    if (get_tmap_bf16_ex(h, a->q, (uint64_t)a->B * a->Sq, cols, (uint64_t)a->q_ts, FT_BQ, 64, 128, &tq) != IVLM_OK) return -1;
+    if (get_tmap_bf16_ex(h, a->k, (uint64_t)a->B * a->Sk, cols, (uint64_t)a->k_ts, FT_BK, 64, 128, &tk) != IVLM_OK) return -1;
+    if (get_tmap_bf16_ex(h, a->v, (uint64_t)a->B * a->Sk, cols, (uint64_t)a->v_ts, FT_BK, 64, 128, &tv) != IVLM_OK) return -1;
+    FtParams p;
+    p.out = reinterpret_cast<bf16*>(a->out);
+    p.o_bs = a->o_bs; p.o_ts = a->o_ts; p.o_hs = a->o_hs;
+    p.Sq = a->Sq; p.Sk = a->Sk;
+    p.scale_log2 = a->scale * AT_LOG2E;
+    dim3 grid((a->Sq + FT_BQ - 1) / FT_BQ, a->H, a->B);
+    int rc;
+    if (a->D == 128) rc = a->causal ? launch_ft<128, true>(h, tq, tk, tv, p, grid, stream) : launch_ft<128, false>(h, tq, tk, tv, p, grid, stream);
+    else rc = a->causal ? launch_ft<64, true>(h, tq, tk, tv, p, grid, stream) : launch_ft<64, false>(h, tq, tk, tv, p, grid, stream);
+    return rc == IVLM_OK ? 1 : -1;
+}
+
 }  // namespace ivlm
 
 using namespace ivlm;

@@ -94,6 +94,7 @@ struct ivlm_ctx {
                                   // against 23 / 48 / 52, down_proj 40 / 57 / 62 against 56 / 136 / 130; tools/prof_decode.py variants)
     int small_m_variant = 0;      // 0: weight-streaming mma.sync kernel for token counts <= 64; 1: swapped-operand tcgen05 path
     int global_attn_variant = 0;  // 0: 64-key tiles, 2 CTAs/SM; 1: 128-key tiles, 1 CTA/SM (A/B switch)
+    int attn_variant = 0;         // 1: plain / causal attention on the mma.sync flash kernel instead of the tcgen05 one (A/B, fallback)
     int attn_small_variant = 0;   // 1: per-query sweeps in the few-queries decoder attention (the round-1 kernel; A/B and bit-identity tests)
     int ds_prefetch_kb = 0;       // decode_stream L2 prefetch of the successor's weights per CTA: 0 off (default: measured 1-10 % SLOWER on
                                   // the 13B chain, profiles/r2_decode_layer_ops_in_graph.txt), -1 as the caller asks, > 0 cap in KB
@@ -158,6 +159,8 @@ int get_tmap_bf16_kchunk3d(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t
 // Weight-streaming small-token GEMM (gemv_small_m.cu); arguments as ivlm_gemm_bf16.
 int launch_gemv_small_m(ivlm_ctx* h, const ivlm_gemm_args* a, cudaStream_t stream);
 // General form: box = box_rows x box_cols elements, swizzle_bytes in {128, 64, 32} (box_cols * 2 must not exceed it).
+// plain / causal attention on tcgen05 (attention_tcgen05.cu): 1 = launched, 0 = layout not covered (use flash_attn_kernel), < 0 error
+int attention_tcgen05_try(ivlm_ctx* h, const ivlm_attn_args* a, cudaStream_t stream);
 int get_tmap_bf16_ex(ivlm_ctx* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols, uint32_t swizzle_bytes, const CUtensorMap** out);
 }  // namespace ivlm

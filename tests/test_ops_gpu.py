@@ -165,6 +165,41 @@ def test_flash_attention(ctx, B, H, Sq, Sk, D, causal):
     ref = (s.softmax(-1) @ vf).permute(0, 2, 1, 3)
     assert rel_err(out, ref) < 8e-3
     assert (out.float() - ref).abs().max().item() < 3e-2
+    if D in (64, 128) and Sq == Sk:
+        # this layout runs on flash_attn_tcgen05_kernel; option attn_variant = 1 selects the mma.sync kernel it replaces
+        ctx.set_option("attn_variant", 1)
+        old = ctx.attention(q, k, v, scale, causal=causal)
+        ctx.set_option("attn_variant", 0)
+        assert rel_err(old, ref) < 8e-3 and rel_err(out, old) < 8e-3
+
+
+@pytest.mark.parametrize("B,H,S,D,causal", [(8, 40, 329, 128, True), (8, 16, 257, 64, False), (1, 2, 128, 128, True), (3, 2, 129, 64, True),
+                                            (2, 3, 700, 128, True), (2, 2, 640, 64, False), (5, 1, 1, 128, True)])
+def test_flash_attention_tcgen05(ctx, B, H, S, D, causal):
+    """flash_attn_tcgen05_kernel at the path's shapes (LLaMA prefill: 8 x 40 heads x 329 rows, causal; CLIP: 257 tokens) and at
+    tile edges (S = 128, 129, several key tiles, one token), separate q / k / v matrices with their own pitches (the prefill
+    layout) and a packed qkv matrix (the CLIP layout), against fp32 torch."""
+    C = H * D
+    for packed in (False, True):
+        if packed:
+            qkv = rnd(B, S, 3, H, D, seed=70)
+            q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        else:
+            q, k, v = (rnd(B, S, H, D, seed=71 + i) for i in range(3))
+        out = ctx.attention(q, k, v, D ** -0.5, causal=causal)
+        qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+        sc = qf @ kf.transpose(-1, -2) * D ** -0.5
+        if causal:
+            sc = sc.masked_fill(~torch.ones(S, S, device=DEV).tril().bool(), float("-inf"))
+        ref = (sc.softmax(-1) @ vf).permute(0, 2, 1, 3)
+        assert torch.isfinite(out.float()).all()
+        assert rel_err(out, ref) < 8e-3, (packed, rel_err(out, ref))
+        assert (out.float() - ref).abs().max().item() < 3e-2
+        n0 = ctx.launch_count()
+        ctx.set_option("attn_variant", 1)
+        old = ctx.attention(q, k, v, D ** -0.5, causal=causal)
+        ctx.set_option("attn_variant", 0)
+        assert rel_err(out, old) < 8e-3
 
 
 @pytest.mark.parametrize("Hq,Wq,B", [(14, 14, 5), (64, 64, 1)])

@@ -60,3 +60,14 @@ for name, B, side in (("global_16views", 16, 64), ("window_16views", 400, 14)):
 
         ms = timeit(old)
         print(f"{name} relpos + mma.sync flash: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+# ---- plain / causal attention of the path: LLaMA prefill (8 x 40 heads x 329 rows x 128, causal) and CLIP (8 x 16 x 257 x 64)
+for name, B, H, S_, D, causal in (("llama_prefill_8x329", 8, 40, 329, 128, True), ("clip_8x257", 8, 16, 257, 64, False),
+                                  ("llama_prefill_8x1024", 8, 40, 1024, 128, True)):
+    q, k, v = (rnd(B, S_, H, D, sc=0.5) for _ in range(3))
+    fl = 4.0 * B * H * S_ * S_ * D * (0.5 if causal else 1.0)
+    for variant, label in ((0, "tcgen05"), (1, "mma.sync flash (round 1)")):
+        ctx.set_option("attn_variant", variant)
+        ms = timeit(lambda: ctx.attention(q, k, v, D ** -0.5, causal=causal))
+        print(f"{name} {label}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    ctx.set_option("attn_variant", 0)
