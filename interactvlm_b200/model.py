@@ -1267,7 +1267,10 @@ class InteractVLMForCausalLM:
         return output_ids, hidden, box["emb"]
 
     def _masks_from_hidden(self, hidden, output_ids, images, cam_params, resize_list, original_size_list,
-                           image_embeddings=None):
+                           image_embeddings=None, offset=None):
+        """`offset` [n_images + 1] (collate_fn, datasets/dataset.py:159-178): conversation rows offset[i]..offset[i+1]-1 belong to
+        image i -- the reference's validation layout of one image with several conversations (InteractVLM.py:346,578-600 decodes
+        every [SEG] of those rows against image i's embeddings).  Without it, row b uses image b."""
         cfg, eng = self.config, self.eng
         B = output_ids.shape[0]
         V = cfg.multiview_channels
@@ -1290,12 +1293,23 @@ class InteractVLMForCausalLM:
             image_embeddings = self.get_visual_embs(images)  # computed for every sample, like the reference (:578)
         self._mark("sam_encoder")
         S, C = image_embeddings.shape[1], image_embeddings.shape[2]
+        n_img = image_embeddings.shape[0] // V
+        img_of = list(range(B))
+        if n_img != B:   # fewer images than conversation rows: rows -> image through `offset` (one image: every row uses it)
+            off = [int(x) for x in (offset.tolist() if hasattr(offset, "tolist") else offset)] if offset is not None else [0, B]
+            if len(off) != n_img + 1 or off[0] != 0 or off[-1] != B:
+                raise ValueError(f"{n_img} image(s) for {B} conversation rows need offset [n_images + 1] ending in {B}, got {off}")
+            img_of = [i for i in range(n_img) for _ in range(off[i + 1] - off[i])]
+        per_row = lambda lst: (lambda b: lst[b] if len(lst) == B else lst[img_of[b]])   # per-row or per-image lists
+        resize_of, orig_of = per_row(resize_list), per_row(original_size_list)
+        resize_list, original_size_list = [resize_of(b) for b in range(B)], [orig_of(b) for b in range(B)]
         pred_masks = [None] * B
         if owners:
             hrows = self.ctx.gather_rows(hidden.view(-1, hidden.shape[-1]), _i32(rows, self.device))
-            cam = self._bf16(torch.as_tensor(cam_params))[owners].contiguous()
+            cam_all = self._bf16(torch.as_tensor(cam_params))
+            cam = cam_all[owners if cam_all.shape[0] == B else [img_of[b] for b in owners]].contiguous()
             prompt, _ = eng.seg_prompt(hrows, cam, tokens)
-            emb = image_embeddings.view(B, V, S, C)[owners].reshape(len(owners) * V, S, C)
+            emb = image_embeddings.view(n_img, V, S, C)[[img_of[b] for b in owners]].reshape(len(owners) * V, S, C)
             low = eng.mask_decode(emb, prompt).view(len(owners), V, 4 * cfg.sam_grid, 4 * cfg.sam_grid)
             S_img = cfg.sam_img_size
             same = all(tuple(int(x) for x in resize_list[b]) == (S_img, S_img) and
@@ -1339,8 +1353,10 @@ class InteractVLMForCausalLM:
         st = eng.llm_alloc(B, embeds.shape[1])
         eng.llm_prefill(st, embeds)
         sizes = [tuple(l.shape[-2:]) for l in label_list] if label_list is not None else list(resize_list)
-        pred_masks = self._masks_from_hidden(st["hidden"], ids, images, cam_params, resize_list, sizes)
+        pred_masks = self._masks_from_hidden(st["hidden"], ids, images, cam_params, resize_list, sizes, offset=offset)
         ds = ds_name_list or ["hcontact"] * B
+        if len(ds) != B:   # per-image names in the one-image / several-conversations layout
+            ds = [ds[0]] * B if len(ds) == 1 else list(ds)
         for i, name in enumerate(ds):  # HM view types feed sigmoid-ed maps to the affordance lift (:452-456)
             if "oafford" in name and cfg.oC_sam_view_type and "HM" in cfg.oC_sam_view_type:
                 gt = None

@@ -122,6 +122,26 @@ def test_model_forward_teacher_forced(setup):
     assert out["pred_human_3d_contact"].shape == (1, S.N_SMPL)
 
 
+def test_model_forward_one_image_several_conversations(setup):
+    """The reference's validation layout (InteractVLM.py:346: images_clip batch 1, offset = [0, n]): n conversation rows share one
+    image -- its CLIP features, SAM embeddings, camera parameters and sizes -- and every row's [SEG] is decoded against them."""
+    cfg, sd, model, _ = setup
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 1)
+    full = torch.cat([ids, ans], 1)
+    two = torch.cat([full, full], 0)
+    kw = dict(labels=two, attention_masks=torch.ones_like(two), masks_list=[torch.zeros(4, 1, *SIZE)], label_list=[torch.zeros(SIZE)],
+              gt_contact_3d_list=[None], cam_params=cam, resize_list=[SIZE], ds_name_list=["damon_hcontact"], mask_paths_list=[None],
+              inference=True)
+    out = model(images=sam, images_clip=clip, input_ids=two, offset=torch.tensor([0, 2]), **kw)
+    one = model(images=sam, images_clip=clip, input_ids=full, offset=torch.tensor([0, 1]), **{**kw, "labels": full,
+                                                                                         "attention_masks": torch.ones_like(full)})
+    assert len(out["pred_masks"]) == 2 and out["pred_human_3d_contact"].shape == (2, S.N_SMPL)
+    for b in range(2):   # both conversations are the same prompt: same masks as the single-conversation call
+        assert torch.allclose(out["pred_masks"][b], one["pred_masks"][0], atol=1e-5)
+    with pytest.raises(ValueError):
+        model(images=sam, images_clip=clip, input_ids=two, offset=torch.tensor([0, 1]), **kw)
+
+
 def test_checkpoint_roundtrip_and_api_surface(tmp_path, setup):
     cfg, sd, model, _ = setup
     save_pretrained(tmp_path / "ckpt", cfg, sd)
