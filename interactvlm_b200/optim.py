@@ -306,7 +306,7 @@ def calculate_centroid(mask):
     cols = torch.arange(W, device=mask.device, dtype=mask.dtype)
     tot = mask.sum()
     c = torch.stack([(mask.sum(1) * rows).sum(), (mask.sum(0) * cols).sum()]) / torch.where(tot != 0, tot, torch.ones_like(tot))
-    centre = torch.tensor([H / 2, W / 2], device=mask.device, dtype=mask.dtype)
+    centre = torch.stack([tot.new_full((), H / 2), tot.new_full((), W / 2)])   # fill kernels: no host -> device copy (graph capture)
     return torch.where(tot != 0, c, centre)
 
 
@@ -381,16 +381,65 @@ class ObjPose_Opt(torch.nn.Module):
         return total, output
 
 
+def _fit_graphed(model, loss_weights, max_iter, optimizer):
+    """The loop of fit() with each iteration (forward, backward, Adam step: ~150 small launches that the host issues in ~4 ms)
+    captured ONCE per schedule segment into a CUDA graph and replayed.  The set of active loss terms only changes at the kick-in
+    steps, so the iterations between two kick-ins are the same launch sequence; the first iterations of every segment run eagerly
+    (they are real iterations and warm the allocator / autograd up), one is captured, the rest are replays."""
+    start = model.step
+    kicks = {int(w["kick_in"]) - start for w in loss_weights.values() if 0 < int(w.get("kick_in", -1)) - start < max_iter}
+    bounds = sorted({0, max_iter} | kicks)
+    # eager iterations and the capture share one side stream (torch's whole-network capture recipe: the autograd thread's cuBLAS
+    # workspaces etc. must exist on the capture stream, or their creation lands on the legacy stream and invalidates the capture)
+    cur = torch.cuda.current_stream(model.rotation.device)
+    side = torch.cuda.Stream(device=model.rotation.device)
+
+    def eager(k):
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(k):
+                optimizer.zero_grad(set_to_none=True)
+                loss, _ = model(loss_weights, log=False)
+                loss.backward()
+                optimizer.step()
+        cur.wait_stream(side)
+
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        n, warm = b - a, min(3, b - a)
+        eager(warm)
+        if n - warm < 2:
+            eager(n - warm)
+            continue
+        step_py = model.step
+        g = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(g, stream=side):
+            loss, _ = model(loss_weights, log=False)
+            loss.backward()
+            optimizer.step()
+        model.step = step_py                 # the capture pass recorded an iteration, it did not run one
+        for _ in range(n - warm):
+            g.replay()
+        model.step = step_py + (n - warm)
+        del g
+    assert model.step == start + max_iter
+
+
 def fit(model: ObjPose_Opt, loss_weights: dict, max_iter: int = 250, lr_rotation: float = 5.0e-2, lr_translation: float = 1.0e-2,
-        lr_scale: float = 1.0e-2, early_stop: bool = False, record: bool = True):
+        lr_scale: float = 1.0e-2, early_stop: bool = False, record: bool = True, graph: bool | None = None):
     """The Adam loop of optim/fit.py:216-290 (per-parameter learning rates of :218-224, optional early stop of :279-283).
     -> list of per-iteration dicts (loss, weighted terms, centroid distance); record=False (no early stop) runs the loop
-    without reading anything back and returns an empty list."""
+    without reading anything back and returns an empty list -- by default (graph=None -> True on CUDA) as CUDA-graph replays of
+    one captured iteration per schedule segment (_fit_graphed); graph=False issues every iteration from the host."""
     groups = [{"params": [model.rotation], "lr": lr_rotation}, {"params": [model.translation], "lr": lr_translation}]
     if isinstance(model.scale, torch.nn.Parameter):
         groups.append({"params": [model.scale], "lr": lr_scale})
-    optimizer = torch.optim.Adam(groups)
+    use_graph = (graph if graph is not None else True) and not record and not early_stop and model.rotation.is_cuda
+    optimizer = torch.optim.Adam(groups, capturable=True) if use_graph else torch.optim.Adam(groups)
     history, prev = [], 1e10
+    if use_graph:
+        _fit_graphed(model, loss_weights, max_iter, optimizer)
+        return history
     if not record and not early_stop:
         for _ in range(max_iter):
             optimizer.zero_grad()

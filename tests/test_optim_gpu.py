@@ -212,7 +212,14 @@ def test_fit_driver_on_a_synthetic_scene(ctx):
     assert len(res.history) == 80 and res.history[-1]["loss"] < res.history[0]["loss"]
     err_end = float((res.translation - gt_t).norm())
     assert err_end < 0.25, err_end
+    # record=False replays ONE captured iteration as a CUDA graph (optim._fit_graphed).  The soft-silhouette backward accumulates
+    # per-vertex gradients with float atomics and the loop amplifies the differences (two EAGER runs differ by ~7e-4 after 80
+    # steps, 1e-5 after 40): the loops are compared after 30 steps, the converged poses loosely
     res2 = FIT.run_fit(human, obj, cam, (128, 128), opt, record=False)
-    # the soft-silhouette backward accumulates per-vertex gradients with float atomics: two runs agree to ~1e-4 after 80 steps
-    assert res2.history == [] and torch.allclose(res2.translation, res.translation, atol=2e-3)
-    assert torch.allclose(res2.rotation6d, res.rotation6d, atol=2e-3)
+    assert res2.history == [] and torch.allclose(res2.translation, res.translation, atol=8e-3)
+    assert torch.allclose(res2.rotation6d, res.rotation6d, atol=8e-3)
+    assert float((res2.translation - gt_t).norm()) < 0.25
+    opt["max_iter"] = 30
+    a = FIT.run_fit(human, obj, cam, (128, 128), opt, record=True)
+    b = FIT.run_fit(human, obj, cam, (128, 128), opt, record=False)
+    assert torch.allclose(a.translation, b.translation, atol=3e-4) and torch.allclose(a.rotation6d, b.rotation6d, atol=3e-4)

@@ -59,11 +59,12 @@ e1 = ev()
 torch.cuda.synchronize()
 print(f"fit loop at 256^2: {e0.elapsed_time(e1) / 60:.2f} ms per iteration")
 
-e0 = ev()
-PO.fit(model, demo.LOSS_WEIGHTS, max_iter=60, record=False)
-e1 = ev()
-torch.cuda.synchronize()
-print(f"fit loop at 256^2 without host read-backs (record=False): {e0.elapsed_time(e1) / 60:.2f} ms per iteration")
+for graph in (False, True):
+    e0 = ev()
+    PO.fit(model, demo.LOSS_WEIGHTS, max_iter=60, record=False, graph=graph)
+    e1 = ev()
+    torch.cuda.synchronize()
+    print(f"fit loop at 256^2 without host read-backs (record=False), CUDA-graph replays = {graph}: {e0.elapsed_time(e1) / 60:.2f} ms per iteration")
 import time
 from interactvlm_b200 import fit as FIT
 from interactvlm_b200.bench_fit import _scene
