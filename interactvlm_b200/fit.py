@@ -194,11 +194,8 @@ class FitResult:
     icp_rmse: float | None = None
 
 
-def run_fit(human: HumanParams, obj: ObjectParams, cam: CameraParams, img_shape, opt: dict | None = None, record=False,
-            ctx=None) -> FitResult:
-    """fit.py:86-290 without the logging side: initial pose -> ObjPose_Opt -> Adam loop.  `record` keeps the per-iteration
-    loss values (one host synchronisation per iteration, like the reference's progress bar); off for throughput runs."""
-    opt = opt or default_options()
+def _setup_fit(human: HumanParams, obj: ObjectParams, cam: CameraParams, img_shape, opt: dict, ctx=None):
+    """fit.py:86-215: initial pose (mask-centroid translation, normal-filtered contact ICP) -> (ObjPose_Opt, icp rmse)."""
     dev = human.vertices.device
     rot = PO.matrix_to_rot6d(torch.eye(3, device=dev)[None])[0]
     trans = torch.zeros(3, device=dev)
@@ -225,10 +222,44 @@ def run_fit(human: HumanParams, obj: ObjectParams, cam: CameraParams, img_shape,
     model = PO.ObjPose_Opt(rot, trans, scale, {"vertices": human.vertices, "contact_verts": human.contact_verts,
                                                "centroid_offset": human.centroid_offset},
                            {"vertices": obj.vertices, "contact_verts": o_probs, "mask": obj.mask}, ren, vars=tuple(opt["vars"]), ctx=ctx).to(dev)
-    hist = PO.fit(model, opt["loss_weights"], max_iter=opt["max_iter"], early_stop=opt["early_stop"], record=record)
+    return model, rmse
+
+
+def _result(model, hist, rmse) -> FitResult:
     with torch.no_grad():
         verts = PO.apply_transformation(model.obj_vertices, model.rotation, model.translation, model.scale)
     return FitResult(model.rotation.detach(), model.translation.detach(), torch.as_tensor(model.scale).detach(), verts, hist, rmse)
+
+
+def run_fit(human: HumanParams, obj: ObjectParams, cam: CameraParams, img_shape, opt: dict | None = None, record=False,
+            ctx=None) -> FitResult:
+    """fit.py:86-290 without the logging side: initial pose -> ObjPose_Opt -> Adam loop.  `record` keeps the per-iteration
+    loss values (one host synchronisation per iteration, like the reference's progress bar); off for throughput runs."""
+    opt = opt or default_options()
+    model, rmse = _setup_fit(human, obj, cam, img_shape, opt, ctx)
+    hist = PO.fit(model, opt["loss_weights"], max_iter=opt["max_iter"], early_stop=opt["early_stop"], record=record)
+    return _result(model, hist, rmse)
+
+
+_CTX_POOL: dict = {}
+
+
+def run_fit_many(scenes, img_shape, opt: dict | None = None) -> list:
+    """run_fit(record=False) for several (human, object, camera) scenes on one GPU, advanced together: every fit gets its own
+    ivlm handle (scratch workspace) and stream, one iteration of each is captured as a CUDA graph and the replays are interleaved
+    (optim.fit_many).  The reference runs one `python -m optim.fit` process per sample."""
+    opt = opt or default_options()
+    if opt["early_stop"]:
+        return [run_fit(h, o, c, img_shape, opt) for h, o, c in scenes]
+    from .ops import Context
+
+    dev = scenes[0][0].vertices.device
+    pool = _CTX_POOL.setdefault(dev.index or 0, [])
+    while len(pool) < len(scenes):
+        pool.append(Context(dev.index or 0))
+    built = [_setup_fit(h, o, c, img_shape, opt, ctx=pool[i]) for i, (h, o, c) in enumerate(scenes)]
+    PO.fit_many([m for m, _ in built], opt["loss_weights"], max_iter=opt["max_iter"])
+    return [_result(m, [], rmse) for m, rmse in built]
 
 
 def save_obj(path, verts, faces):

@@ -381,48 +381,89 @@ class ObjPose_Opt(torch.nn.Module):
         return total, output
 
 
-def _fit_graphed(model, loss_weights, max_iter, optimizer):
-    """The loop of fit() with each iteration (forward, backward, Adam step: ~150 small launches that the host issues in ~4 ms)
-    captured ONCE per schedule segment into a CUDA graph and replayed.  The set of active loss terms only changes at the kick-in
-    steps, so the iterations between two kick-ins are the same launch sequence; the first iterations of every segment run eagerly
-    (they are real iterations and warm the allocator / autograd up), one is captured, the rest are replays."""
-    start = model.step
+REPLAYED_LAUNCHES = [0]   # kernels of this library launched through CUDA-graph replays (the handles' own counters miss them)
+
+
+def _adam_groups(model, lr_rotation, lr_translation, lr_scale):
+    groups = [{"params": [model.rotation], "lr": lr_rotation}, {"params": [model.translation], "lr": lr_translation}]
+    if isinstance(model.scale, torch.nn.Parameter):
+        groups.append({"params": [model.scale], "lr": lr_scale})
+    return groups
+
+
+def _fit_graphed(models, loss_weights, max_iter, optimizers):
+    """The loop of fit() for one or SEVERAL independent models with each iteration (forward, backward, Adam step: ~150 small
+    launches that the host issues in 2-4 ms) captured ONCE per schedule segment into a CUDA graph and replayed.  The set of
+    active loss terms only changes at the kick-in steps, so the iterations between two kick-ins are the same launch sequence; the
+    first iterations of every segment run eagerly (they are real iterations and warm the allocator / autograd up), one is
+    captured, the rest are replays.  Every model has its own side stream; the replays of different models are issued round-robin
+    so that their small kernels overlap on the GPU (a 250-iteration fit is a 0.2 s chain of 2-5 us kernels on its own).
+    Models advanced together must not share scratch: give each its own ops.Context (the contact term uses the handle's
+    workspace)."""
+    dev = models[0].rotation.device
+    start = models[0].step
+    assert all(m.step == start for m in models)
     kicks = {int(w["kick_in"]) - start for w in loss_weights.values() if 0 < int(w.get("kick_in", -1)) - start < max_iter}
     bounds = sorted({0, max_iter} | kicks)
-    # eager iterations and the capture share one side stream (torch's whole-network capture recipe: the autograd thread's cuBLAS
-    # workspaces etc. must exist on the capture stream, or their creation lands on the legacy stream and invalidates the capture)
-    cur = torch.cuda.current_stream(model.rotation.device)
-    side = torch.cuda.Stream(device=model.rotation.device)
+    # eager iterations and the capture share one side stream per model (torch's whole-network capture recipe: the autograd
+    # thread's cuBLAS workspaces etc. must exist on the capture stream, or their creation lands on the legacy stream and
+    # invalidates the capture)
+    cur = torch.cuda.current_stream(dev)
+    sides = [torch.cuda.Stream(device=dev) for _ in models]
 
-    def eager(k):
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
+    def eager(i, k):
+        sides[i].wait_stream(cur)
+        with torch.cuda.stream(sides[i]):
             for _ in range(k):
-                optimizer.zero_grad(set_to_none=True)
-                loss, _ = model(loss_weights, log=False)
+                optimizers[i].zero_grad(set_to_none=True)
+                loss, _ = models[i](loss_weights, log=False)
                 loss.backward()
-                optimizer.step()
-        cur.wait_stream(side)
+                optimizers[i].step()
 
     for a, b in zip(bounds[:-1], bounds[1:]):
         n, warm = b - a, min(3, b - a)
-        eager(warm)
-        if n - warm < 2:
-            eager(n - warm)
-            continue
-        step_py = model.step
-        g = torch.cuda.CUDAGraph()
-        optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(g, stream=side):
-            loss, _ = model(loss_weights, log=False)
-            loss.backward()
-            optimizer.step()
-        model.step = step_py                 # the capture pass recorded an iteration, it did not run one
-        for _ in range(n - warm):
-            g.replay()
-        model.step = step_py + (n - warm)
-        del g
-    assert model.step == start + max_iter
+        graphs = []
+        for i, model in enumerate(models):
+            eager(i, warm)
+            if n - warm < 2:
+                eager(i, n - warm)
+                continue
+            step_py = model.step
+            g = torch.cuda.CUDAGraph()
+            mctx = model.ctx or _ctx(dev)
+            l0 = mctx.launch_count()
+            optimizers[i].zero_grad(set_to_none=True)
+            # capture_begin / capture_end directly: the torch.cuda.graph context manager also runs gc.collect() and
+            # torch.cuda.empty_cache(), which hands the model's multi-GB activation arenas back to the driver before every fit
+            with torch.cuda.stream(sides[i]):
+                g.capture_begin()
+                try:
+                    loss, _ = model(loss_weights, log=False)
+                    loss.backward()
+                    optimizers[i].step()
+                finally:
+                    g.capture_end()
+            model.step = step_py             # the capture pass recorded an iteration, it did not run one
+            REPLAYED_LAUNCHES[0] += (mctx.launch_count() - l0) * (n - warm - 1)   # launches of this library a replay stands for
+            graphs.append((i, g))
+        for _ in range(n - warm if graphs else 0):
+            for i, g in graphs:
+                with torch.cuda.stream(sides[i]):
+                    g.replay()
+        for i, g in graphs:
+            models[i].step += n - warm
+        for sd in sides:
+            cur.wait_stream(sd)
+        del graphs
+    assert all(m.step == start + max_iter for m in models)
+
+
+def fit_many(models, loss_weights: dict, max_iter: int = 250, lr_rotation: float = 5.0e-2, lr_translation: float = 1.0e-2,
+             lr_scale: float = 1.0e-2):
+    """fit(record=False) for several independent ObjPose_Opt models advanced together (see _fit_graphed): the batch of BASELINE
+    configs[3] on one GPU.  Each model needs its own ops.Context."""
+    opts = [torch.optim.Adam(_adam_groups(m, lr_rotation, lr_translation, lr_scale), capturable=True) for m in models]
+    _fit_graphed(list(models), loss_weights, max_iter, opts)
 
 
 def fit(model: ObjPose_Opt, loss_weights: dict, max_iter: int = 250, lr_rotation: float = 5.0e-2, lr_translation: float = 1.0e-2,
@@ -431,14 +472,12 @@ def fit(model: ObjPose_Opt, loss_weights: dict, max_iter: int = 250, lr_rotation
     -> list of per-iteration dicts (loss, weighted terms, centroid distance); record=False (no early stop) runs the loop
     without reading anything back and returns an empty list -- by default (graph=None -> True on CUDA) as CUDA-graph replays of
     one captured iteration per schedule segment (_fit_graphed); graph=False issues every iteration from the host."""
-    groups = [{"params": [model.rotation], "lr": lr_rotation}, {"params": [model.translation], "lr": lr_translation}]
-    if isinstance(model.scale, torch.nn.Parameter):
-        groups.append({"params": [model.scale], "lr": lr_scale})
+    groups = _adam_groups(model, lr_rotation, lr_translation, lr_scale)
     use_graph = (graph if graph is not None else True) and not record and not early_stop and model.rotation.is_cuda
     optimizer = torch.optim.Adam(groups, capturable=True) if use_graph else torch.optim.Adam(groups)
     history, prev = [], 1e10
     if use_graph:
-        _fit_graphed(model, loss_weights, max_iter, optimizer)
+        _fit_graphed([model], loss_weights, max_iter, [optimizer])
         return history
     if not record and not early_stop:
         for _ in range(max_iter):

@@ -223,3 +223,20 @@ def test_fit_driver_on_a_synthetic_scene(ctx):
     a = FIT.run_fit(human, obj, cam, (128, 128), opt, record=True)
     b = FIT.run_fit(human, obj, cam, (128, 128), opt, record=False)
     assert torch.allclose(a.translation, b.translation, atol=3e-4) and torch.allclose(a.rotation6d, b.rotation6d, atol=3e-4)
+
+
+def test_fits_advanced_together_equal_separate_fits(ctx):
+    """fit.run_fit_many (one handle + stream + captured iteration per scene, interleaved graph replays) against run_fit per scene."""
+    from interactvlm_b200 import fit as FIT
+    from interactvlm_b200.bench_fit import _scene
+
+    dev = torch.device("cuda")
+    scenes = [_scene(128, 3 + i, dev) for i in range(3)]
+    opt = FIT.default_options()
+    opt["max_iter"] = 30
+    opt["init"]["translation_hum_centroid"] = False
+    many = FIT.run_fit_many(scenes, (128, 128), opt)
+    for (h, o, c), r in zip(scenes, many):
+        one = FIT.run_fit(h, o, c, (128, 128), opt, record=False)
+        assert torch.allclose(one.translation, r.translation, atol=3e-4) and torch.allclose(one.rotation6d, r.rotation6d, atol=3e-4)
+    assert len({tuple(round(float(x), 3) for x in r.translation) for r in many}) == 3      # three different scenes, three poses
