@@ -141,6 +141,15 @@ def test_im2col(ctx):
     cols = ctx.im2col_patch(img, 14, ldk=592)
     ref = torch.nn.functional.unfold(img.float(), 14, stride=14).transpose(1, 2).reshape(-1, 588)
     assert torch.equal(cols[:, :588].float(), ref) and cols[:, 588:].abs().max().item() == 0
+    # patch sizes that are multiples of 8 take the 16-byte-per-thread kernel (SAM: 16 x 16 patches), with and without a padded pitch
+    img = rnd(3, 3, 64, 96, seed=63)
+    ref = torch.nn.functional.unfold(img.float(), 16, stride=16).transpose(1, 2).reshape(-1, 768)
+    assert torch.equal(ctx.im2col_patch(img, 16).float(), ref)
+    cols = ctx.im2col_patch(img, 16, ldk=776)
+    assert torch.equal(cols[:, :768].float(), ref) and cols[:, 768:].abs().max().item() == 0
+    img = rnd(2, 3, 48, 24, seed=64)
+    ref = torch.nn.functional.unfold(img.float(), 8, stride=8).transpose(1, 2).reshape(-1, 192)
+    assert torch.equal(ctx.im2col_patch(img, 8).float(), ref)
     x = rnd(2, 6, 5, 16, seed=34)  # [N,H,W,C]
     cols = ctx.im2col_3x3(x.contiguous(), 2, 6, 5)
     ref = torch.nn.functional.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1)  # [N, C*9, HW] with k = c*9 + tap
