@@ -26,7 +26,11 @@ typedef struct ivlm_ctx* ivlm_handle;
 
 enum ivlm_status { IVLM_OK = 0, IVLM_ERR_ARG = -1, IVLM_ERR_CUDA = -2, IVLM_ERR_NOMEM = -3 };
 enum ivlm_dtype { IVLM_BF16 = 0, IVLM_F32 = 1, IVLM_I32 = 2, IVLM_I64 = 3 };
-enum ivlm_act { IVLM_ACT_NONE = 0, IVLM_ACT_GELU = 1, IVLM_ACT_QUICK_GELU = 2, IVLM_ACT_RELU = 3, IVLM_ACT_SILU = 4 };
+enum ivlm_act { IVLM_ACT_NONE = 0, IVLM_ACT_GELU = 1, IVLM_ACT_QUICK_GELU = 2, IVLM_ACT_RELU = 3, IVLM_ACT_SILU = 4,
+                /* ivlm_gemm_bf16 only (token count > 64, bf16 output, no bias / residual): `w` holds gate / up rows interleaved in
+                 * blocks of 8 (IVLM_EPI_SWIGLU's order) and the epilogue writes out[m, f] = bf16(bf16(silu(gate)) * up), N / 2
+                 * columns -- HF LlamaMLP's gate without the [M, 2F] round trip through HBM */
+                IVLM_ACT_SWIGLU = 5 };
 enum ivlm_lift_mode {
     IVLM_LIFT_HUMAN = 0,       /* HumanContact3DPredictor: clamp +-20, sigmoid, final clamp [0,1] */
     IVLM_LIFT_OBJECT_MESH = 1, /* ObjectMeshContact3DPredictor: sigmoid, only pixels with p > thr vote */

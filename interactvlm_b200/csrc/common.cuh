@@ -44,7 +44,8 @@ IVLM_DEVINL float warp_max(float v) {
 
 // Activations. GELU is the exact erf form (torch.nn.GELU default); quick_gelu is
 // x*sigmoid(1.702x) (HF CLIP "quick_gelu").
-enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_QUICK_GELU = 2, ACT_RELU = 3, ACT_SILU = 4 };
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_QUICK_GELU = 2, ACT_RELU = 3, ACT_SILU = 4,
+                 ACT_SWIGLU = 5 /* gemm_tcgen05 staged epilogue only: interleaved gate / up columns -> silu(gate) * up, N / 2 outputs */ };
 
 IVLM_DEVINL float apply_act(float x, int act) {
     switch (act) {

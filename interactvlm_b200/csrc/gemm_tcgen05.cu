@@ -101,6 +101,23 @@ IVLM_DEVINL void epi_stage_chunk(const uint32_t (&raw)[32], const float* __restr
     }
 }
 
+// Phase 1 for ACT_SWIGLU: the warp's 32 accumulator columns are [gate 0-7 | up 0-7 | gate 8-15 | up 8-15] of 16 features ->
+// 16 outputs bf16(bf16(silu(bf16(gate))) * bf16(up)) (the rounding points of silu_mul_kernel) -> two 16-byte segments.
+IVLM_DEVINL void epi_stage_swiglu(const uint32_t (&raw)[32], uint8_t* buf, int rloc, int seg0) {
+#pragma unroll
+    for (int h8 = 0; h8 < 2; ++h8) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float g = bf16_round(__uint_as_float(raw[h8 * 16 + j])), u = bf16_round(__uint_as_float(raw[h8 * 16 + 8 + j]));
+            o[j] = bf16_round(apply_act_fast(g, ACT_SILU)) * u;
+        }
+        uint4 q;
+        q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]); q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(buf + rloc * 128 + (((seg0 + h8) ^ (rloc & 7)) << 4)) = q;
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -266,6 +283,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             case ACT_QUICK_GELU: epi_stage_chunk<ACT_QUICK_GELU>(raw, bs, has_bias, buf, rloc, chalf * 4); break;
                             case ACT_RELU: epi_stage_chunk<ACT_RELU>(raw, bs, has_bias, buf, rloc, chalf * 4); break;
                             case ACT_SILU: epi_stage_chunk<ACT_SILU>(raw, bs, has_bias, buf, rloc, chalf * 4); break;
+                            case ACT_SWIGLU: epi_stage_swiglu(raw, buf, rloc, chalf * 2); break;
                             default: epi_stage_chunk<ACT_NONE>(raw, bs, has_bias, buf, rloc, chalf * 4); break;
                         }
                         if (slab + 1 < NSLAB) {
@@ -277,7 +295,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         }
                         named_bar_sync(1, EPI_THREADS);
                         const int seg = et & 7;
-                        const int col = n0 + slab * 64 + seg * 8;
+                        // SWIGLU: a 64-column slab of accumulators is 32 output columns (segments 0-3 of the staging rows)
+                        const bool sw = p.act == ACT_SWIGLU;
+                        const int col = sw ? (n0 >> 1) + slab * 32 + seg * 8 : n0 + slab * 64 + seg * 8;
+                        const int ncol = (sw && seg >= 4) ? 0 : (sw ? (p.N >> 1) : p.N);
                         // all row-map lookups first, then all residual loads, then add + store: the loads of the four rows a
                         // thread moves are in flight together instead of one dependent chain per row
                         constexpr int NIT = BM * 8 / EPI_THREADS;
@@ -286,7 +307,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                         for (int i = 0; i < NIT; ++i) {
                             const int grow = m0 + i * (EPI_THREADS / 8) + (et >> 3);
-                            int orow = (grow < p.M && col < p.N) ? grow : -1;
+                            int orow = (grow < p.M && col < ncol) ? grow : -1;
                             if (orow >= 0 && p.row_map != nullptr) orow = p.row_map[grow];
                             orow_[i] = orow;
                         }
@@ -644,6 +665,8 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
     IVLM_REQUIRE(!split || (a->out_dtype == IVLM_F32 && !a->bias && !a->residual && a->act == 0),
                  "gemm: split-K accumulates raw fp32 (no bias/act/residual)");
 
+    IVLM_REQUIRE(a->act != ACT_SWIGLU || (a->M > 64 && a->force_swap <= 0 && !split),
+                 "gemm: SWIGLU needs more than 64 tokens (the decode path fuses it in ivlm_decode_linear)");
     // Small token counts are weight streaming (HBM-bound): dedicated kernel built around the weight stream.
     if (h->small_m_variant == 0 && a->M <= h->gv_max_m && a->N <= h->gv_max_n && a->force_swap >= 0 && a->row_map == nullptr && a->k_splits <= 1 &&
         a->K % 32 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0 && a->res_row_mod == 0 &&
@@ -717,6 +740,10 @@ extern "C" int ivlm_gemm_bf16(ivlm_handle h, const ivlm_gemm_args* a, void* stre
     p.atomic = split ? 1 : 0;
     p.round_steps = (a->out_dtype == IVLM_BF16 && !a->no_round) ? 1 : 0;
     p.staged = (!swap && !split && a->out_dtype == IVLM_BF16 && !a->no_round && bn >= 64) ? 1 : 0;
+    if (a->act == ACT_SWIGLU)
+        IVLM_REQUIRE(p.staged && a->N % 16 == 0 && !a->bias && !a->residual && a->row_map == nullptr,
+                     "gemm: SWIGLU runs in the staged epilogue only (token count > 64, N >= 64 and a multiple of 16, bf16 output, no bias / "
+                     "residual / row_map); got M=%d N=%d", a->M, a->N);
     // keep the smaller operand L2-resident across the sweep of the other dimension
     p.n_fastest = ((long long)p.N * p.K < (long long)p.M * p.K) ? 1 : 0;
     p.a_static = swap ? 1 : 0;

@@ -202,8 +202,13 @@ extern "C" int ivlm_llm_prefill(ivlm_handle h, const ivlm_llm_prefill_args* a, v
         IVLM_TRY(ivlm_attention_bf16(h, &at, stream));
         IVLM_TRY(gemm(h, o, D, wo, D, xa, D, T, D, D, nullptr, 0, x, D, nullptr, 0, 0, IVLM_BF16, stream));
         IVLM_TRY(ivlm_rmsnorm_bf16(h, xa, y, ln2, T, D, d.llm_rms_eps, stream));
-        IVLM_TRY(gemm(h, y, D, wgu, D, gu, 2 * F, T, 2 * F, D, nullptr, 0, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
-        IVLM_TRY(ivlm_silu_mul_bf16(h, gu, act, T, F, d.llm_paired_layout, stream));
+        if (d.llm_paired_layout && T > 64 && 2 * F > 32 && F % 8 == 0) {
+            // gate / up rows are interleaved: the GEMM epilogue applies the SwiGLU gate and writes [T, F] directly
+            IVLM_TRY(gemm(h, y, D, wgu, D, act, F, T, 2 * F, D, nullptr, IVLM_ACT_SWIGLU, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+        } else {
+            IVLM_TRY(gemm(h, y, D, wgu, D, gu, 2 * F, T, 2 * F, D, nullptr, 0, nullptr, 0, nullptr, 0, 0, IVLM_BF16, stream));
+            IVLM_TRY(ivlm_silu_mul_bf16(h, gu, act, T, F, d.llm_paired_layout, stream));
+        }
         IVLM_TRY(gemm(h, act, F, wd, F, xb, D, T, D, F, nullptr, 0, xa, D, nullptr, 0, 0, IVLM_BF16, stream));
         x = xb;
     }

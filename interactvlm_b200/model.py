@@ -24,7 +24,7 @@ from .layout import interleave_gate_up, pair_rows
 from .synthetic import CLIP_PREFIX, SAM_PREFIX
 
 IMAGE_TOKEN_INDEX = -200
-ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_RELU, ACT_SILU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_RELU, ACT_SILU, ACT_SWIGLU = 0, 1, 2, 3, 4, 5
 LIFT_HUMAN, LIFT_OBJECT_MESH, LIFT_POINTS = 0, 1, 2
 PAGE = 16  # KV-cache page size (tokens)
 
@@ -428,7 +428,11 @@ class _Engine:
             o = ctx.attention(q.view(B, S, nh, hd), k.view(B, S, nh, hd), v.view(B, S, nh, hd), 1.0 / math.sqrt(hd), causal=True)
             x = ctx.gemm(o.view(B * S, D), lw["wo"], residual=x)
             y = ctx.rmsnorm(x, lw["ln2"], cfg.rms_norm_eps)
-            y = ctx.silu_mul(ctx.gemm(y, lw["wgu"]), interleaved=W.paired_qk)
+            F = cfg.intermediate_size
+            if W.paired_qk and y.shape[0] > 64 and 2 * F > 32 and F % 8 == 0:   # SwiGLU gate in the GEMM epilogue (interleaved rows)
+                y = ctx.gemm(y, lw["wgu"], act=ACT_SWIGLU, out=torch.empty((y.shape[0], F), device=y.device, dtype=torch.bfloat16))
+            else:
+                y = ctx.silu_mul(ctx.gemm(y, lw["wgu"]), interleaved=W.paired_qk)
             x = ctx.gemm(y, lw["wd"], residual=x)
             if self.trace is not None:
                 self.trace.setdefault("llm", []).append(x)

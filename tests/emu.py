@@ -14,7 +14,7 @@ import torch
 import torch.nn.functional as F
 
 BF = torch.bfloat16
-ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_RELU, ACT_SILU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_RELU, ACT_SILU, ACT_SWIGLU = 0, 1, 2, 3, 4, 5
 
 
 def _act(x, act):
@@ -75,6 +75,14 @@ class EmuContext:
              k_splits=1, force_swap=0, no_round=False, res_row_mod=0):
         self.launches += 1
         assert a.dtype == BF and w.dtype == BF and a.shape[1] == w.shape[1] and a.shape[1] % 8 == 0
+        if act == ACT_SWIGLU:   # interleaved gate / up rows -> bf16(bf16(silu(gate)) * up), N / 2 columns (the staged GEMM epilogue)
+            assert a.shape[0] > 64 and bias is None and residual is None and row_map is None
+            y = self.silu_mul(_r(a.float() @ w.float().t()).to(BF), interleaved=True)
+            self.launches -= 1
+            if out is not None:
+                out.copy_(y)
+                return out
+            return y
         M, N = a.shape[0], w.shape[0]
         swap = force_swap == 1 or (force_swap == 0 and M <= 64 and row_map is None)
         if not swap:

@@ -426,3 +426,21 @@ def test_upscale_hyper_dot(ctx):
         m = torch.einsum("btpqc,bc->btpq", z, hyper.float())
         m = m.view(Bv, G, G, 2, 2, 2, 2).permute(0, 1, 3, 5, 2, 4, 6).reshape(Bv, G * 4, G * 4)
         assert rel_err(out, m) < 1e-2, (Bv, G)
+
+
+@pytest.mark.parametrize("M,F,K", [(2632, 13824, 5120), (130, 704, 256), (300, 40, 512), (65, 1416, 64)])
+def test_gemm_swiglu_epilogue(ctx, M, F, K):
+    """ivlm_gemm_bf16 with IVLM_ACT_SWIGLU (interleaved gate / up rows, the SwiGLU gate applied in the staged epilogue: [M, F]
+    written instead of [M, 2F]) against the two launches it replaces and against fp32 torch."""
+    from interactvlm_b200.layout import interleave_gate_up
+    x = rnd(M, K, seed=80)
+    gate, up = rnd(F, K, scale=K ** -0.5, seed=81), rnd(F, K, scale=K ** -0.5, seed=82)
+    wil = interleave_gate_up(gate, up)
+    out = ctx.gemm(x, wil, act=5, out=torch.empty((M, F), device=DEV, dtype=torch.bfloat16))
+    two = ctx.silu_mul(ctx.gemm(x, wil), interleaved=True)
+    g, u = (x.float() @ gate.float().t()).bfloat16().float(), (x.float() @ up.float().t()).bfloat16().float()
+    ref = torch.nn.functional.silu(g).bfloat16().float() * u
+    assert out.shape == (M, F) and torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 4e-3 and rel_err(out, two) < 2e-3
+    # the SFU silu of the epilogue against the expf silu of silu_mul_kernel: at most one bf16 ulp of the product apart
+    assert ((out.float() - two.float()).abs() <= 2 ** -7 * two.float().abs() + 1e-6).all()

@@ -42,3 +42,30 @@ for name, fn in cases.items():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     print(f"{name}: {ms:.4f} ms  {flops[name] / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+# ---- LLaMA prefill gate / up projection (8 x 329 rows): SwiGLU gate in the GEMM epilogue against GEMM + silu_mul
+if len(sys.argv) > 2 and sys.argv[2] == "swiglu":
+    from interactvlm_b200.layout import interleave_gate_up
+    T, D, F = 2632, 5120, 13824
+    xp = rnd(T, D)
+    wil = interleave_gate_up(rnd(F, D, sc=D ** -0.5), rnd(F, D, sc=D ** -0.5))
+    outp = torch.empty((T, F), device="cuda", dtype=torch.bfloat16)
+
+    def t(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 20
+
+    a = t(lambda: ctx.gemm(xp, wil, act=5, out=outp))
+    b = t(lambda: ctx.silu_mul(ctx.gemm(xp, wil), interleaved=True))
+    c = t(lambda: ctx.gemm(xp, wil))
+    fl = 2.0 * T * 2 * F * D
+    print(f"prefill gate/up {T} x {2 * F} x {D}: fused SwiGLU epilogue {a * 1e3:.1f} us ({fl / a / 1e9:.0f} TFLOP/s); GEMM alone {c * 1e3:.1f} us "
+          f"({fl / c / 1e9:.0f}); GEMM + silu_mul {b * 1e3:.1f} us", flush=True)
