@@ -113,31 +113,38 @@ class _Weights:
         # prompt encoder constants + mask decoder
         self.no_mask = g(SAM_PREFIX + "prompt_encoder.no_mask_embed.weight").reshape(-1).contiguous()
         self.dense_pe = self._dense_pe(g(SAM_PREFIX + "prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"), cfg)
-        d = SAM_PREFIX + "mask_decoder."
-
         def attn(p):
             return dict(wq=g(p + "q_proj.weight"), bq=g(p + "q_proj.bias"), wk=g(p + "k_proj.weight"), bk=g(p + "k_proj.bias"),
                         wv=g(p + "v_proj.weight"), bv=g(p + "v_proj.bias"), wo=g(p + "out_proj.weight"), bo=g(p + "out_proj.bias"))
 
-        self.dec = dict(layers=[], final=attn(d + "transformer.final_attn_token_to_image."),
-                        nfg=g(d + "transformer.norm_final_attn.weight"), nfb=g(d + "transformer.norm_final_attn.bias"),
-                        out_tokens=torch.cat([g(d + "iou_token.weight"), g(d + "mask_tokens.weight")], 0).contiguous())
-        for i in range(cfg.sam_dec_depth):
-            p = d + f"transformer.layers.{i}."
-            self.dec["layers"].append(dict(
-                self_attn=attn(p + "self_attn."), t2i=attn(p + "cross_attn_token_to_image."), i2t=attn(p + "cross_attn_image_to_token."),
-                n=[(g(p + f"norm{k}.weight"), g(p + f"norm{k}.bias")) for k in (1, 2, 3, 4)],
-                w1=g(p + "mlp.lin1.weight"), b1=g(p + "mlp.lin1.bias"), w2=g(p + "mlp.lin2.weight"), b2=g(p + "mlp.lin2.bias")))
-        up0 = g(d + "output_upscaling.0.weight")  # [ci, co, dy, dx]
-        co = up0.shape[1]
-        self.dec["up0_w"] = up0.permute(2, 3, 1, 0).reshape(4 * co, up0.shape[0]).contiguous()  # row (dy*2+dx)*co + c
-        self.dec["up0_b"] = g(d + "output_upscaling.0.bias").repeat(4).contiguous()
-        self.dec["up_ln"] = (g(d + "output_upscaling.1.weight"), g(d + "output_upscaling.1.bias"))
-        up3 = g(d + "output_upscaling.3.weight")
-        self.dec["up3_w"] = up3.permute(2, 3, 1, 0).reshape(4, up3.shape[1], up3.shape[0]).contiguous()  # [sub-pixel, co, ci]
-        self.dec["up3_b"] = g(d + "output_upscaling.3.bias")
-        hp = d + "output_hypernetworks_mlps.0.layers."  # multimask_output=False keeps mask token 0 only
-        self.dec["hyper"] = [(g(hp + f"{k}.weight"), g(hp + f"{k}.bias")) for k in range(3)]
+        def decoder(d):
+            dec = dict(layers=[], final=attn(d + "transformer.final_attn_token_to_image."),
+                       nfg=g(d + "transformer.norm_final_attn.weight"), nfb=g(d + "transformer.norm_final_attn.bias"),
+                       out_tokens=torch.cat([g(d + "iou_token.weight"), g(d + "mask_tokens.weight")], 0).contiguous())
+            for i in range(cfg.sam_dec_depth):
+                p = d + f"transformer.layers.{i}."
+                dec["layers"].append(dict(
+                    self_attn=attn(p + "self_attn."), t2i=attn(p + "cross_attn_token_to_image."), i2t=attn(p + "cross_attn_image_to_token."),
+                    n=[(g(p + f"norm{k}.weight"), g(p + f"norm{k}.bias")) for k in (1, 2, 3, 4)],
+                    w1=g(p + "mlp.lin1.weight"), b1=g(p + "mlp.lin1.bias"), w2=g(p + "mlp.lin2.weight"), b2=g(p + "mlp.lin2.bias")))
+            up0 = g(d + "output_upscaling.0.weight")  # [ci, co, dy, dx]
+            co = up0.shape[1]
+            dec["up0_w"] = up0.permute(2, 3, 1, 0).reshape(4 * co, up0.shape[0]).contiguous()  # row (dy*2+dx)*co + c
+            dec["up0_b"] = g(d + "output_upscaling.0.bias").repeat(4).contiguous()
+            dec["up_ln"] = (g(d + "output_upscaling.1.weight"), g(d + "output_upscaling.1.bias"))
+            up3 = g(d + "output_upscaling.3.weight")
+            dec["up3_w"] = up3.permute(2, 3, 1, 0).reshape(4, up3.shape[1], up3.shape[0]).contiguous()  # [sub-pixel, co, ci]
+            dec["up3_b"] = g(d + "output_upscaling.3.bias")
+            hp = d + "output_hypernetworks_mlps.0.layers."  # multimask_output=False keeps mask token 0 only
+            dec["hyper"] = [(g(hp + f"{k}.weight"), g(hp + f"{k}.bias")) for k in range(3)]
+            return dec
+
+        self.dec = decoder(SAM_PREFIX + "mask_decoder.")
+        # token types '*-DifDe': separate copies for human contact and for object contact / affordance (InteractVLM.py:44-53,114-122)
+        self.dec_human = self.dec_object = None
+        if "DifDe" in cfg.token_type:
+            self.dec_human = decoder(SAM_PREFIX + "human_mask_decoder.")
+            self.dec_object = decoder(SAM_PREFIX + "object_mask_decoder.")
         # [SEG] projection, camera gate
         self.fc = (g("model.text_hidden_fcs.0.0.weight"), g("model.text_hidden_fcs.0.0.bias"),
                    g("model.text_hidden_fcs.0.2.weight"), g("model.text_hidden_fcs.0.2.bias"))
@@ -605,15 +612,25 @@ class _Engine:
         res = residual.reshape(-1, C) if residual is not None else None
         return ctx.gemm(o.reshape(-1, o.shape[-1]), aw["wo"], bias=aw["bo"], residual=res).view(o.shape[0], o.shape[1], C)
 
-    def mask_decode(self, emb, prompt):
+    def decoder_for(self, ds_name):
+        """ModifiedSAM.forward (InteractVLM.py:44-53): which mask decoder serves a dataset / contact-type name."""
+        if self.w.dec_human is not None and ds_name is not None:
+            if "hcontact" in ds_name:
+                return self.w.dec_human
+            if "oafford" in ds_name or "ocontact" in ds_name:
+                return self.w.dec_object
+        return self.w.dec
+
+    def mask_decode(self, emb, prompt, dec=None):
         """emb [n*V,4096,256] token-major SAM embeddings, prompt [n,V,256] -> low-res logits [n*V,256,256] fp32.
-        Every view of a sample sees the sample's 5 output tokens + all V gated prompt tokens."""
-        ctx, cfg, w = self.ctx, self.cfg, self.w.dec
+        Every view of a sample sees the sample's 5 output tokens + all V gated prompt tokens.  dec: one of the
+        decoder weight sets (default: the shared one; the stage-level C call covers that one)."""
+        ctx, cfg, w = self.ctx, self.cfg, (dec if dec is not None else self.w.dec)
         n, V, C = prompt.shape
         nv, S = emb.shape[0], emb.shape[1]
         heads = cfg.sam_dec_heads
         ntok = w["out_tokens"].shape[0] + V
-        if (self.stage_abi and self.trace is None and not ctx.profiling and w["up0_w"].shape[0] == C and w["hyper"][2][0].shape[0] == 32
+        if (self.stage_abi and self.trace is None and not ctx.profiling and w is self.w.dec and w["up0_w"].shape[0] == C and w["hyper"][2][0].shape[0] == 32
                 and w["layers"][0]["w1"].shape[0] <= 2048 and S == cfg.sam_grid ** 2 and C == cfg.sam_out_chans):
             # one C call (ivlm_mask_decode): the launch sequence below, driven from the library
             key = ("tok_idx", n, V)
@@ -834,6 +851,9 @@ class InteractVLMForCausalLM:
             # static, so the next GEMM's first pipeline stages stream while the previous kernel runs (include/ivlm_b200.h,
             # option "pdl").  Bit-identical; 159 -> 153 us per 13B decode layer inside the captured graph.
             ctx.set_option("pdl", 1)
+        if getattr(config, "use_fusion", False) or getattr(config, "use_uncertainty", False):
+            # LLaVASAMFusion / UncertaintyModule (components.py:40-153): off in every released configuration, not on the hot path
+            raise NotImplementedError("use_fusion / use_uncertainty are outside the hot path (flags off in every released checkpoint)")
         self.w = _Weights(state_dict, config, self.device)
         self.eng = _Engine(ctx, config, self.w)
         self.use_cuda_graph = use_cuda_graph and self.device.type == "cuda"
@@ -1152,8 +1172,6 @@ class InteractVLMForCausalLM:
         """model/InteractVLM.py:510-638.  Returns {"output_ids", "pred_masks" (list of [V,H,W] fp32 logits),
         "pred_contact_3d" ([B,6890] / [1,Nv] fp32 or None)}."""
         cfg = self.config
-        if "DifDe" in cfg.token_type:
-            raise NotImplementedError("token_type '*-DifDe' (separate human / object mask decoders) is outside the hot path")
         emb = None
         if self.overlap is not None and self._view_cache is None and not self.record_stages and self.stage_delay is None:
             output_ids, hidden, emb = self._generate_and_encode(images_clip, images, input_ids, max_new_tokens, scripted,
@@ -1161,7 +1179,7 @@ class InteractVLMForCausalLM:
         else:
             output_ids, hidden = self.generate(images_clip, input_ids, max_new_tokens, scripted, prompt_lens=prompt_lens)
         pred_masks = self._masks_from_hidden(hidden, output_ids, images, cam_params, resize_list, original_size_list,
-                                             image_embeddings=emb)
+                                             image_embeddings=emb, ds_names=[contact_type] * output_ids.shape[0])
         pred_contact_3d = None
         # the reference (batch 1) lifts when its sample produced a mask (:618); batched: when any sample did -- the others
         # get a zero row (and a [0,H,W] entry in pred_masks, as the reference files them)
@@ -1271,7 +1289,7 @@ class InteractVLMForCausalLM:
         return output_ids, hidden, box["emb"]
 
     def _masks_from_hidden(self, hidden, output_ids, images, cam_params, resize_list, original_size_list,
-                           image_embeddings=None, offset=None):
+                           image_embeddings=None, offset=None, ds_names=None):
         """`offset` [n_images + 1] (collate_fn, datasets/dataset.py:159-178): conversation rows offset[i]..offset[i+1]-1 belong to
         image i -- the reference's validation layout of one image with several conversations (InteractVLM.py:346,578-600 decodes
         every [SEG] of those rows against image i's embeddings).  Without it, row b uses image b."""
@@ -1314,7 +1332,17 @@ class InteractVLMForCausalLM:
             cam = cam_all[owners if cam_all.shape[0] == B else [img_of[b] for b in owners]].contiguous()
             prompt, _ = eng.seg_prompt(hrows, cam, tokens)
             emb = image_embeddings.view(n_img, V, S, C)[[img_of[b] for b in owners]].reshape(len(owners) * V, S, C)
-            low = eng.mask_decode(emb, prompt).view(len(owners), V, 4 * cfg.sam_grid, 4 * cfg.sam_grid)
+            decs = [eng.decoder_for(ds_names[b] if ds_names is not None else None) for b in owners]
+            if all(d_ is decs[0] for d_ in decs):
+                low = eng.mask_decode(emb, prompt, decs[0])
+            else:   # '*-DifDe' with human and object samples in one batch: one decode per decoder copy
+                low = torch.empty((len(owners) * V, 4 * cfg.sam_grid, 4 * cfg.sam_grid), device=self.device, dtype=torch.float32)
+                emb4, low4 = emb.view(len(owners), V, S, C), low.view(len(owners), V, 4 * cfg.sam_grid, 4 * cfg.sam_grid)
+                for d_ in {id(x): x for x in decs}.values():
+                    sel = [k for k, x in enumerate(decs) if x is d_]
+                    low4[sel] = eng.mask_decode(emb4[sel].reshape(len(sel) * V, S, C).contiguous(), prompt[sel].contiguous(), d_).view(
+                        len(sel), V, 4 * cfg.sam_grid, 4 * cfg.sam_grid)
+            low = low.view(len(owners), V, 4 * cfg.sam_grid, 4 * cfg.sam_grid)
             S_img = cfg.sam_img_size
             same = all(tuple(int(x) for x in resize_list[b]) == (S_img, S_img) and
                        tuple(int(x) for x in original_size_list[b]) == (S_img, S_img) for b in owners)
@@ -1357,10 +1385,10 @@ class InteractVLMForCausalLM:
         st = eng.llm_alloc(B, embeds.shape[1])
         eng.llm_prefill(st, embeds)
         sizes = [tuple(l.shape[-2:]) for l in label_list] if label_list is not None else list(resize_list)
-        pred_masks = self._masks_from_hidden(st["hidden"], ids, images, cam_params, resize_list, sizes, offset=offset)
         ds = ds_name_list or ["hcontact"] * B
         if len(ds) != B:   # per-image names in the one-image / several-conversations layout
             ds = [ds[0]] * B if len(ds) == 1 else list(ds)
+        pred_masks = self._masks_from_hidden(st["hidden"], ids, images, cam_params, resize_list, sizes, offset=offset, ds_names=ds)
         for i, name in enumerate(ds):  # HM view types feed sigmoid-ed maps to the affordance lift (:452-456)
             if "oafford" in name and cfg.oC_sam_view_type and "HM" in cfg.oC_sam_view_type:
                 gt = None

@@ -226,36 +226,38 @@ def state_dict_spec(cfg) -> dict:
     pe = SAM_PREFIX + "prompt_encoder."
     s[pe + "pe_layer.positional_encoding_gaussian_matrix"] = ((2, O // 2), "pe")
     s[pe + "no_mask_embed.weight"] = ((1, O), "e")
-    # mask decoder
-    d = SAM_PREFIX + "mask_decoder."
+    # mask decoder(s): the '*-DifDe' token types carry a human and an object copy next to the shared one (InteractVLM.py:114-122)
     nm = cfg.sam_num_multimask_outputs + 1
+    decoders = ["mask_decoder"] + (["human_mask_decoder", "object_mask_decoder"] if "DifDe" in cfg.token_type else [])
+    for _dec in decoders:
+        d = SAM_PREFIX + _dec + "."
 
-    def attn(p, internal):
-        for n in ("q_proj", "k_proj", "v_proj"):
-            s[p + n + ".weight"] = ((internal, O), "w"); s[p + n + ".bias"] = ((internal,), "b")
-        s[p + "out_proj.weight"] = ((O, internal), "w"); s[p + "out_proj.bias"] = ((O,), "b")
+        def attn(p, internal):
+            for n in ("q_proj", "k_proj", "v_proj"):
+                s[p + n + ".weight"] = ((internal, O), "w"); s[p + n + ".bias"] = ((internal,), "b")
+            s[p + "out_proj.weight"] = ((O, internal), "w"); s[p + "out_proj.bias"] = ((O,), "b")
 
-    for i in range(cfg.sam_dec_depth):
-        p = d + f"transformer.layers.{i}."
-        attn(p + "self_attn.", O)
-        attn(p + "cross_attn_token_to_image.", O // 2)
-        attn(p + "cross_attn_image_to_token.", O // 2)
-        for n in ("norm1", "norm2", "norm3", "norm4"):
-            s[p + n + ".weight"] = ((O,), "g"); s[p + n + ".bias"] = ((O,), "b")
-        s[p + "mlp.lin1.weight"] = ((cfg.sam_dec_mlp_dim, O), "w"); s[p + "mlp.lin1.bias"] = ((cfg.sam_dec_mlp_dim,), "b")
-        s[p + "mlp.lin2.weight"] = ((O, cfg.sam_dec_mlp_dim), "w"); s[p + "mlp.lin2.bias"] = ((O,), "b")
-    attn(d + "transformer.final_attn_token_to_image.", O // 2)
-    s[d + "transformer.norm_final_attn.weight"] = ((O,), "g"); s[d + "transformer.norm_final_attn.bias"] = ((O,), "b")
-    s[d + "iou_token.weight"] = ((1, O), "e")
-    s[d + "mask_tokens.weight"] = ((nm, O), "e")
-    s[d + "output_upscaling.0.weight"] = ((O, O // 4, 2, 2), "w"); s[d + "output_upscaling.0.bias"] = ((O // 4,), "b")
-    s[d + "output_upscaling.1.weight"] = ((O // 4,), "g"); s[d + "output_upscaling.1.bias"] = ((O // 4,), "b")
-    s[d + "output_upscaling.3.weight"] = ((O // 4, O // 8, 2, 2), "w"); s[d + "output_upscaling.3.bias"] = ((O // 8,), "b")
-    for i in range(nm):
-        p = d + f"output_hypernetworks_mlps.{i}.layers."
-        s[p + "0.weight"] = ((O, O), "w"); s[p + "0.bias"] = ((O,), "b")
-        s[p + "1.weight"] = ((O, O), "w"); s[p + "1.bias"] = ((O,), "b")
-        s[p + "2.weight"] = ((O // 8, O), "w"); s[p + "2.bias"] = ((O // 8,), "b")
+        for i in range(cfg.sam_dec_depth):
+            p = d + f"transformer.layers.{i}."
+            attn(p + "self_attn.", O)
+            attn(p + "cross_attn_token_to_image.", O // 2)
+            attn(p + "cross_attn_image_to_token.", O // 2)
+            for n in ("norm1", "norm2", "norm3", "norm4"):
+                s[p + n + ".weight"] = ((O,), "g"); s[p + n + ".bias"] = ((O,), "b")
+            s[p + "mlp.lin1.weight"] = ((cfg.sam_dec_mlp_dim, O), "w"); s[p + "mlp.lin1.bias"] = ((cfg.sam_dec_mlp_dim,), "b")
+            s[p + "mlp.lin2.weight"] = ((O, cfg.sam_dec_mlp_dim), "w"); s[p + "mlp.lin2.bias"] = ((O,), "b")
+        attn(d + "transformer.final_attn_token_to_image.", O // 2)
+        s[d + "transformer.norm_final_attn.weight"] = ((O,), "g"); s[d + "transformer.norm_final_attn.bias"] = ((O,), "b")
+        s[d + "iou_token.weight"] = ((1, O), "e")
+        s[d + "mask_tokens.weight"] = ((nm, O), "e")
+        s[d + "output_upscaling.0.weight"] = ((O, O // 4, 2, 2), "w"); s[d + "output_upscaling.0.bias"] = ((O // 4,), "b")
+        s[d + "output_upscaling.1.weight"] = ((O // 4,), "g"); s[d + "output_upscaling.1.bias"] = ((O // 4,), "b")
+        s[d + "output_upscaling.3.weight"] = ((O // 4, O // 8, 2, 2), "w"); s[d + "output_upscaling.3.bias"] = ((O // 8,), "b")
+        for i in range(nm):
+            p = d + f"output_hypernetworks_mlps.{i}.layers."
+            s[p + "0.weight"] = ((O, O), "w"); s[p + "0.bias"] = ((O,), "b")
+            s[p + "1.weight"] = ((O, O), "w"); s[p + "1.bias"] = ((O,), "b")
+            s[p + "2.weight"] = ((O // 8, O), "w"); s[p + "2.bias"] = ((O // 8,), "b")
     # [SEG] projection and camera gate
     s["model.text_hidden_fcs.0.0.weight"] = ((D, D), "w"); s["model.text_hidden_fcs.0.0.bias"] = ((D,), "b")
     s["model.text_hidden_fcs.0.2.weight"] = ((cfg.out_dim, D), "w"); s["model.text_hidden_fcs.0.2.bias"] = ((cfg.out_dim,), "b")

@@ -332,9 +332,20 @@ def _dec_attn(w: W, p, q, k, v, nh):
     return F.linear(o, w("out_proj.weight", p), w("out_proj.bias", p))
 
 
-def mask_decoder(w: W, cfg, image_embeddings, sparse):
+def decoder_name(cfg, ds_name):
+    """ModifiedSAM.forward (InteractVLM.py:44-53): with token_type '*-DifDe' the human / object copies of the mask decoder
+    (initialize_separate_decoders, :114-122) serve 'hcontact' / 'oafford' + 'ocontact'; everything else the shared one."""
+    if "DifDe" in cfg.token_type and ds_name is not None:
+        if "hcontact" in ds_name:
+            return "human_mask_decoder"
+        if "oafford" in ds_name or "ocontact" in ds_name:
+            return "object_mask_decoder"
+    return "mask_decoder"
+
+
+def mask_decoder(w: W, cfg, image_embeddings, sparse, which="mask_decoder"):
     """image_embeddings [V,256,64,64], sparse [1,V,256] -> low-res logits [V,1,256,256] (multimask_output=False)."""
-    d = SAM_PREFIX + "mask_decoder."
+    d = SAM_PREFIX + which + "."
     nh = cfg.sam_dec_heads
     nm = cfg.sam_num_multimask_outputs + 1
     out_tok = torch.cat([w("iou_token.weight", d), w("mask_tokens.weight", d)], 0)[None].expand(sparse.shape[0], -1, -1)
@@ -420,8 +431,11 @@ def greedy_generate(w: W, cfg, images_clip, input_ids, max_new_tokens, scripted=
     return ids, hidden, torch.stack(greedy, 1)
 
 
-def masks_from_hidden(w: W, cfg, hidden, output_ids, images, cam_params, resize_list, original_size_list, stages=None):
-    """Everything downstream of the language model (InteractVLM.py:535-612): per sample a [V,H,W] fp32 logit map."""
+def masks_from_hidden(w: W, cfg, hidden, output_ids, images, cam_params, resize_list, original_size_list, stages=None,
+                      ds_names=None):
+    """Everything downstream of the language model (InteractVLM.py:535-612): per sample a [V,H,W] fp32 logit map.
+    ds_names: per-sample dataset / contact-type names (ds_name_list[i] at :435, contact_type at :604) -- they select the
+    decoder copy of the '*-DifDe' token types."""
     rows, tokens = seg_rows(cfg, output_ids, with_tokens=True)
     pred_masks = []
     for b in range(hidden.shape[0]):
@@ -435,7 +449,7 @@ def masks_from_hidden(w: W, cfg, hidden, output_ids, images, cam_params, resize_
             continue
         assert pe.shape[0] == 1, "multi-view decoding broadcasts only for one [SEG] per sample (SURVEY.md 0.5)"
         prompt = process_embeddings(w, cfg, pe, cam_params[b], tokens[b])
-        low = mask_decoder(w, cfg, emb_img, prompt)
+        low = mask_decoder(w, cfg, emb_img, prompt, decoder_name(cfg, ds_names[b] if ds_names is not None else None))
         pm = postprocess_masks(cfg, low, resize_list[b], original_size_list[b])
         if stages is not None:
             stages.setdefault("prompt", []).append(prompt)
@@ -454,7 +468,7 @@ def evaluate(sd, cfg, images_clip, images, input_ids, cam_params, resize_list, o
             stages["hidden"] = hidden
             stages["greedy"] = greedy
         pred_masks = masks_from_hidden(w, cfg, hidden, output_ids, images.to(dtype), cam_params.to(dtype), resize_list,
-                                       original_size_list, stages)
+                                       original_size_list, stages, ds_names=[contact_type] * output_ids.shape[0])
     contact = None
     if pred_masks[0].shape[0] > 0 and lift_maps is not None:
         p2v, bary, n = lift_maps
@@ -467,7 +481,7 @@ def evaluate(sd, cfg, images_clip, images, input_ids, cam_params, resize_list, o
 
 
 def model_forward(sd, cfg, images, images_clip, input_ids, cam_params, resize_list, label_shapes, lift_maps=None,
-                  dtype=torch.float32, stages=None):
+                  dtype=torch.float32, stages=None, ds_name_list=None):
     """model_forward(inference=True) (InteractVLM.py:296-474): one teacher-forced pass over prompt+answer."""
     w = W(sd, dtype)
     with torch.no_grad():
@@ -475,7 +489,7 @@ def model_forward(sd, cfg, images, images_clip, input_ids, cam_params, resize_li
         if stages is not None:
             stages["hidden"] = hidden
         pred_masks = masks_from_hidden(w, cfg, hidden, input_ids, images.to(dtype), cam_params.to(dtype), resize_list,
-                                       label_shapes, stages)
+                                       label_shapes, stages, ds_names=ds_name_list)
     out = {"pred_masks": pred_masks}
     if lift_maps is not None and cfg.hC_loss_weight > 0:
         p2v, bary, n = lift_maps

@@ -431,3 +431,34 @@ def test_stage_level_abi_is_bit_identical_to_the_op_level_path(tiny):
     model.eng.stage_abi = True
     for name, x, y in zip(("clip", "prompt", "emb", "lowres"), res[True], res[False]):
         assert torch.equal(x, y), name
+
+
+def test_separate_human_and_object_mask_decoders_vs_oracle(ctx):
+    """token_type 'Gen-DifDe' (InteractVLM.py:44-53,114-122) on the GPU: contact_type picks the human / object copy of the mask
+    decoder; each against the oracle (fp32), and a batch that mixes both dataset names through model_forward."""
+    from interactvlm_b200.model import InteractVLMForCausalLM
+    from oracle import model as OM
+
+    cfg = IVLMConfig.tiny()
+    cfg.token_type = "Gen-DifDe"
+    sd = S.make_state_dict(cfg, seed=TINY_SEED["weights"])
+    model = InteractVLMForCausalLM(cfg, sd, ctx=ctx)
+    p2v, bary = S.make_mesh_lift_maps(seed=TINY_SEED["maps"])
+    model.set_human_lift_maps(p2v, bary)
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 2)
+    got = {}
+    for ct in ("hcontact", "ocontact"):
+        ev = model.evaluate(clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, contact_type=ct, max_new_tokens=ans.shape[1], scripted=ans)
+        ref = OM.evaluate(sd, cfg, clip, sam, ids, cam, [SIZE] * 2, [SIZE] * 2, contact_type=ct, max_new_tokens=ans.shape[1], scripted=ans)
+        for b in range(2):
+            a, r = ev["pred_masks"][b].float().cpu(), ref["pred_masks"][b].float()
+            assert (a - r).abs().max().item() < 0.05 * r.abs().max().item(), (ct, b)
+        got[ct] = [m.float().cpu() for m in ev["pred_masks"]]
+    assert (got["hcontact"][0] - got["ocontact"][0]).abs().max().item() > 0.1 * got["hcontact"][0].abs().max().item()
+    full = torch.cat([ids, ans], 1)
+    fw = model(images=sam, images_clip=clip, input_ids=full, labels=full, attention_masks=torch.ones_like(full), offset=torch.tensor([0, 1, 2]),
+               masks_list=[torch.zeros(4, 1, *SIZE)] * 2, label_list=[torch.zeros(SIZE)] * 2, gt_contact_3d_list=[None] * 2, cam_params=cam,
+               resize_list=[SIZE] * 2, ds_name_list=["damon_hcontact", "pico_ocontact"], mask_paths_list=[None] * 2, inference=True)
+    for b, ct in enumerate(("hcontact", "ocontact")):   # the mixed batch runs one decode per decoder copy
+        a, r = fw["pred_masks"][b].float().cpu(), got[ct][b]
+        assert (a - r).abs().max().item() < 0.05 * r.abs().max().item(), ct

@@ -282,3 +282,29 @@ def test_prompts_of_different_lengths_in_one_batch(setup):
             seq, _, _ = OM.greedy_generate(w, cfg, clip[b:b + 1], prompts[b][None], 3)
         n = seq.shape[1]
         assert g_ids[b, :n].tolist() == seq[0].tolist()
+
+
+def test_separate_human_and_object_mask_decoders():
+    """token_type '*-DifDe' (InteractVLM.py:44-53,114-122): 'hcontact' decodes with human_mask_decoder, 'ocontact' / 'oafford'
+    with object_mask_decoder, anything else with the shared copy -- against the oracle, and the three decoders must differ."""
+    cfg = IVLMConfig.tiny()
+    cfg.token_type = "Gen-DifDe"
+    sd = S.make_state_dict(cfg, seed=TINY_SEED["weights"])
+    model = InteractVLMForCausalLM(cfg, sd, ctx=EmuContext())
+    p2v, bary = S.make_mesh_lift_maps(seed=TINY_SEED["maps"])
+    model.set_human_lift_maps(p2v, bary)
+    ids, ans, clip, sam, cam = tiny_inputs(cfg, 1)
+    outs = {}
+    for ct in ("hcontact", "ocontact"):
+        ev = model.evaluate(clip, sam, ids, cam, [SIZE], [SIZE], contact_type=ct, max_new_tokens=ans.shape[1], scripted=ans)
+        ref = OM.evaluate(sd, cfg, clip, sam, ids, cam, [SIZE], [SIZE], contact_type=ct, max_new_tokens=ans.shape[1], scripted=ans,
+                          dtype=torch.bfloat16)
+        a, b = ev["pred_masks"][0].float(), ref["pred_masks"][0].float()
+        assert (a - b).abs().max().item() < 0.06 * b.abs().max().item(), ct
+        outs[ct] = a
+    assert (outs["hcontact"] - outs["ocontact"]).abs().max().item() > 0.1 * outs["hcontact"].abs().max().item()
+    full = torch.cat([ids, ans], 1)
+    fw = model(images=sam, images_clip=clip, input_ids=full, labels=full, attention_masks=torch.ones_like(full), offset=torch.tensor([0, 1]),
+               masks_list=[torch.zeros(4, 1, *SIZE)], label_list=[torch.zeros(SIZE)], gt_contact_3d_list=[None], cam_params=cam,
+               resize_list=[SIZE], ds_name_list=["pico_ocontact"], mask_paths_list=[None], inference=True)
+    assert (fw["pred_masks"][0].float() - outs["ocontact"]).abs().max().item() < 0.05 * outs["ocontact"].abs().max().item()
