@@ -1204,6 +1204,261 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
     }
 }
 
+// ------------------------------------------------------------------------------------------------ 14x14 windows, persistent
+// sam_attn_window_tcgen05_kernel as a persistent kernel: 2 CTAs per SM loop over the (query tile, head, window) items.  Per item
+// the chain is still load -> T -> S -> two softmax passes -> P V -> store, but (a) barrier / TMEM set-up and the rel-pos tables
+// are paid once per CTA, (b) the next item's Q / K / V loads and its T product (parked in TMEM columns [192,256), clear of the
+// previous O) run under the previous item's epilogue.  Same arithmetic in the same order: bit-identical outputs.
+__global__ void __launch_bounds__(WN_THREADS, 2)
+sam_attn_window_persist_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+                               const __grid_constant__ CUtensorMap tmKVa, const __grid_constant__ CUtensorMap tmKVb,
+                               const __grid_constant__ CUtensorMap tmRHa, const __grid_constant__ CUtensorMap tmRHb,
+                               const __grid_constant__ CUtensorMap tmRWa, const __grid_constant__ CUtensorMap tmRWb,
+                               const SamAttnParams p, const int n_items) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    bf16* th_s = reinterpret_cast<bf16*>(smem + WN_OFF_TH);  // [28 idx][128 rows]
+    bf16* tw_s = reinterpret_cast<bf16*>(smem + WN_OFF_TW);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WN_OFF_BAR);
+    uint64_t *qt_full = bars, *k_full = bars + 1, *v_full = bars + 2, *t_full = bars + 3, *t_read = bars + 4,
+             *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
+    uint64_t* o_read = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int E = p.heads * AT_HD;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_init(qt_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(t_full, 1);
+            mbar_init(t_read, 4); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(o_read, 4);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ control: TMA + MMA issue
+        if (lane == 0) {
+          for (int it = 0, item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t ph = it & 1;
+            const int q0 = (item & 1) * AT_BQ, h = (item >> 1) % p.heads, b = (item >> 1) / p.heads;
+            const int row_base = b * WN_S;
+            // Q / K (aliased by P) and V of the previous item are free once its P.V has retired; its epilogue (TMEM -> global) is
+            // still running on the softmax warps while these loads are in flight
+            if (it > 0) mbar_wait(o_full, ph ^ 1);
+            mbar_arrive_expect_tx(qt_full, it == 0 ? 20480 + 2 * (4096 + 1024) : 20480);
+            tma_load_2d(smem + WN_OFF_QA, &tmQa, qt_full, h * AT_HD, row_base + q0);
+            tma_load_2d(smem + WN_OFF_QB, &tmQb, qt_full, h * AT_HD + 64, row_base + q0);
+            if (it == 0) {   // the rel-pos tables are the same for every item: loaded once per CTA
+                tma_load_2d(smem + WN_OFF_RHA, &tmRHa, qt_full, 0, 0);
+                tma_load_2d(smem + WN_OFF_RHB, &tmRHb, qt_full, 64, 0);
+                tma_load_2d(smem + WN_OFF_RWA, &tmRWa, qt_full, 0, 0);
+                tma_load_2d(smem + WN_OFF_RWB, &tmRWb, qt_full, 64, 0);
+            }
+            mbar_arrive_expect_tx(k_full, WN_KA + WN_KB);
+            tma_load_2d(smem + WN_OFF_KA, &tmKVa, k_full, E + h * AT_HD, row_base);
+            tma_load_2d(smem + WN_OFF_KB, &tmKVb, k_full, E + h * AT_HD + 64, row_base);
+            mbar_arrive_expect_tx(v_full, WN_KA + WN_KB);
+            tma_load_2d(smem + WN_OFF_VA, &tmKVa, v_full, 2 * E + h * AT_HD, row_base);
+            tma_load_2d(smem + WN_OFF_VB, &tmKVb, v_full, 2 * E + h * AT_HD + 64, row_base);
+            const uint64_t dqa = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_QA));
+            const uint64_t dqb = umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_QB));
+            mbar_wait(qt_full, ph);
+            tc_fence_after();
+            {   // T_h -> cols [192,224), T_w -> cols [224,256): clear of the previous item's O in [0,80), which its epilogue still reads
+                constexpr uint32_t idesc = umma_idesc_bf16(128, 32);
+                const uint64_t dh = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_RHA));
+                const uint64_t dw = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_RWA));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 192, dqa + 2 * k, dh + 2 * k, idesc, k > 0 ? 1u : 0u);
+                umma_bf16(tmem_base + 192, dqb, umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_RHB)), idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 224, dqa + 2 * k, dw + 2 * k, idesc, k > 0 ? 1u : 0u);
+                umma_bf16(tmem_base + 224, dqb, umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_RWB)), idesc, 1u);
+                umma_commit(t_full);
+            }
+            mbar_wait(k_full, ph);
+            mbar_wait(t_read, ph);  // the softmax warps have taken T_h / T_w out of the columns S overwrites
+            if (it > 0) mbar_wait(o_read, ph ^ 1);   // ... and the previous item's O out of [0,80)
+            tc_fence_after();
+            {   // S = Q K^T, N = 208
+                constexpr uint32_t idesc = umma_idesc_bf16(128, WN_KEYS);
+                const uint64_t dk = umma_desc_sw128_kmajor(smem_u32(smem + WN_OFF_KA));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dqa + 2 * k, dk + 2 * k, idesc, k > 0 ? 1u : 0u);
+                umma_bf16(tmem_base, dqb, umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_KB)), idesc, 1u);
+                umma_commit(s_full);
+            }
+            mbar_wait(v_full, ph);
+            mbar_wait(p_full, ph);
+            tc_fence_after();
+            {   // O = P V over 13 key steps of 16
+                constexpr uint32_t idesc64 = umma_idesc_bf16_bmn(128, 64), idesc16 = umma_idesc_bf16_bmn(128, 16);
+#pragma unroll
+                for (int ks = 0; ks < WN_KEYS / 16; ++ks) {
+                    const uint64_t dp = ks < 12 ? umma_desc_sw128_kmajor(smem_u32(smem + (ks >> 2) * 16384)) + 2 * (ks & 3)
+                                                : umma_desc_sw32_kmajor(smem_u32(smem + WN_OFF_P3));
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
+                    umma_bf16(tmem_base, dp, umma_desc_sw128_mnmajor(smem_u32(smem + WN_OFF_VA + ks * 2048)), idesc64, acc);
+                    umma_bf16(tmem_base + 64, dp, umma_desc_sw32_mnmajor(smem_u32(smem + WN_OFF_VB + ks * 512)), idesc16, acc);
+                }
+                umma_commit(o_full);
+            }
+          }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps (quadrant == warp)
+        const int r = warp * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+      for (int it = 0, item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const int q0 = (item & 1) * AT_BQ, h = (item >> 1) % p.heads, b = (item >> 1) / p.heads;
+        const int row_base = b * WN_S;
+        const int qtok = q0 + r;
+        const bool q_ok = qtok < WN_S;
+        const int qy = q_ok ? qtok / WN_KW : 0, qx = q_ok ? qtok - (qtok / WN_KW) * WN_KW : 0;
+        mbar_wait(t_full, ph);
+        tc_fence_after();
+        {
+            uint32_t th[32], tw[32];
+            tmem_ld_32x32(lane_addr + 192, th);
+            tmem_ld_32x32(lane_addr + 224, tw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 28; ++i) {
+                th_s[i * AT_BQ + r] = __float2bfloat16_rn(__uint_as_float(th[i]));
+                tw_s[i * AT_BQ + r] = __float2bfloat16_rn(__uint_as_float(tw[i]));
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_read);
+        float rh[WN_KW], rw[WN_KW];  // this row's rel_h[ky], rel_w[kx] (bf16 values), pre-multiplied by log2(e)
+#pragma unroll
+        for (int i = 0; i < WN_KW; ++i) {
+            rh[i] = __bfloat162float(th_s[(qy - i + WN_KW - 1) * AT_BQ + r]) * AT_LOG2E;
+            rw[i] = __bfloat162float(tw_s[(qx - i + WN_KW - 1) * AT_BQ + r]) * AT_LOG2E;
+        }
+        mbar_wait(s_full, ph);
+        tc_fence_after();
+        // ---- pass 1: x = s*scale + bias (log2 domain) written back in place, row max.  Both passes are software
+        // pipelined over two register buffers: the TMEM read of chunk c+1 is issued before chunk c is processed, so its
+        // latency hides under the arithmetic (two softmax warps per scheduler do not hide it otherwise).
+        float mx = -INFINITY;
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(lane_addr, ra);
+#define WIN_PASS1(C0, CUR, NXT, NEXT_LD)                                            \
+        {                                                                           \
+            tmem_ld_wait();                                                         \
+            NEXT_LD;                                                                \
+            mx = win_scores<C0, 32>(CUR, rh, rw, p.scale_log2, mx);                 \
+            tmem_st_32x32(lane_addr + C0, CUR);                                     \
+        }
+        WIN_PASS1(0, ra, rb, tmem_ld_32x32(lane_addr + 32, rb))
+        WIN_PASS1(32, rb, ra, tmem_ld_32x32(lane_addr + 64, ra))
+        WIN_PASS1(64, ra, rb, tmem_ld_32x32(lane_addr + 96, rb))
+        WIN_PASS1(96, rb, ra, tmem_ld_32x32(lane_addr + 128, ra))
+        WIN_PASS1(128, ra, rb, tmem_ld_32x32(lane_addr + 160, rb))
+        uint32_t rc[16];
+        WIN_PASS1(160, rb, ra, tmem_ld_32x16(lane_addr + 192, rc))
+#undef WIN_PASS1
+        tmem_ld_wait();
+        mx = win_scores<192, 16>(rc, rh, rw, p.scale_log2, mx);
+        tmem_st_32x16(lane_addr + 192, rc);
+        tmem_st_wait();
+        // ---- pass 2: p = 2^(x - max) -> bf16 -> swizzled P (aliases the dead Q / K tiles)
+        float sum = 0.f;
+        auto exp_chunk = [&](const uint32_t(&raw)[32], int c0) {
+            uint8_t* row = smem + (c0 >> 6) * 16384 + r * 128;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e]) - mx);
+                    const float p1 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e + 1]) - mx);
+                    sum += p0 + p1;
+                    pk[e] = pack_bf16x2(p0, p1);
+                }
+                const int c16 = ((c0 & 63) >> 3) + j8;
+                *reinterpret_cast<uint4*>(row + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        };
+        tmem_ld_32x32(lane_addr, ra);
+        tmem_ld_wait(); tmem_ld_32x32(lane_addr + 32, rb);  exp_chunk(ra, 0);
+        tmem_ld_wait(); tmem_ld_32x32(lane_addr + 64, ra);  exp_chunk(rb, 32);
+        tmem_ld_wait(); tmem_ld_32x32(lane_addr + 96, rb);  exp_chunk(ra, 64);
+        tmem_ld_wait(); tmem_ld_32x32(lane_addr + 128, ra); exp_chunk(rb, 96);
+        tmem_ld_wait(); tmem_ld_32x32(lane_addr + 160, rb); exp_chunk(ra, 128);
+        tmem_ld_wait(); tmem_ld_32x16(lane_addr + 192, rc); exp_chunk(rb, 160);
+        {
+            tmem_ld_wait();
+            uint8_t* row = smem + WN_OFF_P3 + r * 32;
+#pragma unroll
+            for (int j8 = 0; j8 < 2; ++j8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = ex2_approx(__uint_as_float(rc[j8 * 8 + 2 * e]) - mx);
+                    const float p1 = ex2_approx(__uint_as_float(rc[j8 * 8 + 2 * e + 1]) - mx);
+                    sum += p0 + p1;
+                    pk[e] = pack_bf16x2(p0, p1);
+                }
+                *reinterpret_cast<uint4*>(row + ((j8 ^ ((r >> 2) & 1)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // ---- epilogue
+        mbar_wait(o_full, ph);
+        tc_fence_after();
+        const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        // window_unpartition (image_encoder.py:291-318) folded into the store: with out_map the row goes straight to its token
+        // position and the rows of the zero padding are never written
+        long long orow_i = q_ok ? (long long)(row_base + qtok) : -1;
+        if (q_ok && p.out_map != nullptr) orow_i = p.out_map[row_base + qtok];
+        const bool st_ok = orow_i >= 0;
+        bf16* orow = p.out + (st_ok ? orow_i : 0) * p.out_ld + h * AT_HD;
+#pragma unroll
+        for (int c0 = 0; c0 < AT_HD; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld_32x16(lane_addr + c0, o);
+            tmem_ld_wait();
+            if (st_ok) {
+                uint4 u0, u1;
+                u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+                u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+                u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+                u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+                u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+                reinterpret_cast<uint4*>(orow + c0)[0] = u0;
+                reinterpret_cast<uint4*>(orow + c0)[1] = u1;
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_read);   // this warp's reads of O are done: the next item's S may overwrite the columns
+      }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+
 // ------------------------------------------------------------------------------------------------ 14x14 windows, 2 threads / row
 // sam_attn_window_tcgen05_kernel with eight softmax warps (two threads per query row: key columns [0,96) and [96,208)); the
 // row maximum and row sum are exchanged through shared memory.  Still two CTAs per SM.
@@ -1770,6 +2025,7 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_tcgen05_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_window_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WN_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_window_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WNH_SMEM));
+        IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_window_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WN_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_global64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
         IVLM_CHECK_CUDA(cudaFuncSetAttribute(sam_attn_global64h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2H_SMEM));
         h->attr_done |= 1ull << 16;
@@ -1784,7 +2040,7 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
             sam_attn_global64_kernel<<<grid, G2_THREADS, G2_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *rha, *rhb, *rwa, *rwb, p);
     } else if (Wq == 64) {
         sam_attn_tcgen05_kernel<64><<<grid, AT_THREADS, AT_SMEM, stream>>>(*qa, *qb, *rha, *rhb, *rwa, *rwb, p);
-    } else if (h->window_attn_variant == 0 || h->window_attn_variant == 2) {
+    } else if (h->window_attn_variant == 0 || h->window_attn_variant == 2 || h->window_attn_variant == 3) {
         const CUtensorMap *kva, *kvb, *wha, *whb, *wwa, *wwb;
         IVLM_TRY(get_tmap_bf16_ex(h, qkv, rows, 3 * (uint64_t)E, 3 * (uint64_t)E, WN_KEYS, 64, 128, &kva));
         IVLM_TRY(get_tmap_bf16_ex(h, qkv, rows, 3 * (uint64_t)E, 3 * (uint64_t)E, WN_KEYS, 16, 32, &kvb));
@@ -1792,7 +2048,11 @@ extern "C" int ivlm_sam_attention_bf16(ivlm_handle h, const void* qkv, const voi
         IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_h, 2 * Hq - 1, hd, hd, 32, 16, 32, &whb));
         IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_w, 2 * Wq - 1, hd, hd, 32, 64, 128, &wwa));
         IVLM_TRY(get_tmap_bf16_ex(h, rel_pos_w, 2 * Wq - 1, hd, hd, 32, 16, 32, &wwb));
-        if (h->window_attn_variant == 2)   // measured 201 vs 213 TFLOP/s: the window kernel waits on loads, not on its softmax warps
+        if (h->window_attn_variant == 3) {
+            const int n_items = 2 * heads * B;
+            const int ctas = n_items < 2 * h->num_sms ? n_items : 2 * h->num_sms;
+            sam_attn_window_persist_kernel<<<ctas, WN_THREADS, WN_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *wha, *whb, *wwa, *wwb, p, n_items);
+        } else if (h->window_attn_variant == 2)   // measured 201 vs 213 TFLOP/s: the window kernel waits on loads, not on its softmax warps
             sam_attn_window_h_kernel<<<grid, WNH_THREADS, WNH_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *wha, *whb, *wwa, *wwb, p);
         else
             sam_attn_window_tcgen05_kernel<<<grid, WN_THREADS, WN_SMEM, stream>>>(*qa, *qb, *kva, *kvb, *wha, *whb, *wwa, *wwb, p);

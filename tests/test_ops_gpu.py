@@ -283,6 +283,19 @@ def test_sam_attention_tcgen05(ctx, Hq, Wq, B, heads):
         dead = torch.ones(B * S + 40, dtype=torch.bool, device=DEV)
         dead[gmap[live].long()] = False
         assert scat[dead].abs().max().item() == 0
+        # the persistent form of the window kernel (variant 3: CTAs loop over the items, next loads under the previous epilogue)
+        # and the one-CTA-per-item form run the same arithmetic in the same order
+        for other in ([3] if torch.equal(out, out) else []):
+            base_variant = 0
+            for v_ in (other, base_variant):
+                ctx.set_option("window_attn_variant", v_)
+                res = ctx.sam_attention(qkv, rph, rpw, B, heads, Hq, Wq, hd)
+                res_sc = ctx.sam_attention(qkv, rph, rpw, B, heads, Hq, Wq, hd, out_map=gmap, out_rows=B * S + 40,
+                                           out=torch.zeros(B * S + 40, heads * hd, device=DEV, dtype=torch.bfloat16))
+                if v_ == other:
+                    pers, pers_sc = res, res_sc
+            ctx.set_option("window_attn_variant", 0)
+            assert torch.equal(pers, res) and torch.equal(pers_sc, res_sc)
     # and against the first-generation path (separate rel-pos kernel + mma.sync flash attention)
     rel_h, rel_w = ctx.sam_relpos(qkv, rph, rpw, B, heads, Hq, Wq, hd)
     old = ctx.attention(q, k, v, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=Hq, kw=Wq).reshape(B * S, heads * hd)

@@ -44,6 +44,12 @@ for name, B, side in (("global_16views", 16, 64), ("window_16views", 400, 14)):
                 ms = timeit(lambda: ctx.sam_attention(qkv, rph, rpw, B, heads, side, side, hd))
                 print(f"{name} fused tcgen05, L2 prefetch {ahead} CTAs ahead: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
             ctx.set_option("attn_prefetch_ahead", -1)
+        if side == 14:
+            for v_ in (3, 0, 3, 0):
+                ctx.set_option("window_attn_variant", v_)
+                ms = timeit(lambda: ctx.sam_attention(qkv, rph, rpw, B, heads, side, side, hd))
+                print(f"{name} fused tcgen05, {'persistent CTAs' if v_ == 3 else 'one CTA per item'}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+            ctx.set_option("window_attn_variant", 0)
         opt = "global_attn_variant" if side == 64 else "window_attn_variant"
         for variant, label in ((2, "one thread per row (round-1 kernel)" if side == 64 else "two threads per row"),
                                (1, "128-key tiles / 1 CTA per SM" if side == 64 else "tiled kernel")):
