@@ -78,7 +78,16 @@ IVLM_DEVINL float gelu_fast(float x) {
     poly = fmaf(t, poly, 0.5f * -0.284496736f);
     poly = fmaf(t, poly, 0.5f * 0.254829592f);
     const float half_pe = poly * t * ex2_approx_ftz((x * x) * (-0.5f * 1.4426950408889634f));
-    return x * (x < 0.f ? half_pe : 1.0f - half_pe);
+    // x >= 0: x (1 - h) = x - |x| h;  x < 0: x h = -|x| h  ->  relu(x) - |x| h: one max and one fma instead of compare / select / mul
+    return fmaf(-fabsf(x), half_pe, fmaxf(x, 0.f));
+}
+// two fp32 values rounded to bf16 (round-to-nearest-even) and widened again: ONE conversion instruction for the pair
+// (cvt.rn.bf16x2.f32) plus two integer ops, instead of two conversions + two shifts -- the conversion unit is quarter-rate and
+// shared with MUFU, which the activation epilogues of the GEMM already load
+IVLM_DEVINL void bf16_round_pair(float& a, float& b) {
+    const uint32_t p = pack_bf16x2(a, b);
+    a = __uint_as_float(p << 16);
+    b = __uint_as_float(p & 0xffff0000u);
 }
 // act followed by the bf16 rounding the eager reference applies to the activation output
 IVLM_DEVINL float apply_act_fast(float x, int act) {

@@ -86,11 +86,16 @@ IVLM_DEVINL void epi_stage_chunk(const uint32_t (&raw)[32], const float* __restr
                                  int seg0) {
     float x[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        float y = __uint_as_float(raw[j]);
-        if (has_bias) y += bs[j];
-        if (ACT != ACT_NONE) y = apply_act_fast(bf16_round(y), ACT);
-        x[j] = y;
+    for (int j = 0; j < 32; j += 2) {
+        float y0 = __uint_as_float(raw[j]), y1 = __uint_as_float(raw[j + 1]);
+        if (has_bias) { y0 += bs[j]; y1 += bs[j + 1]; }
+        if (ACT != ACT_NONE) {
+            bf16_round_pair(y0, y1);   // the Linear output as the reference holds it (bf16) before the activation
+            y0 = apply_act_fast(y0, ACT);
+            y1 = apply_act_fast(y1, ACT);
+        }
+        x[j] = y0;
+        x[j + 1] = y1;
     }
 #pragma unroll
     for (int j8 = 0; j8 < 4; ++j8) {

@@ -69,3 +69,19 @@ if len(sys.argv) > 2 and sys.argv[2] == "swiglu":
     fl = 2.0 * T * 2 * F * D
     print(f"prefill gate/up {T} x {2 * F} x {D}: fused SwiGLU epilogue {a * 1e3:.1f} us ({fl / a / 1e9:.0f} TFLOP/s); GEMM alone {c * 1e3:.1f} us "
           f"({fl / c / 1e9:.0f}); GEMM + silu_mul {b * 1e3:.1f} us", flush=True)
+
+# ---- is the GELU epilogue what separates MLP-1 from the other shapes?  Same launch with each activation.
+if len(sys.argv) > 2 and sys.argv[2] == "acts":
+    for act, label in ((0, "none"), (3, "relu"), (2, "quick_gelu (1 MUFU pair)"), (1, "gelu (erf form)")):
+        fn = lambda: ctx.gemm(x, w1, bias=b1, act=act, force_swap=-1)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print(f"mlp1 M={M} N={4 * E} K={E} act={label}: {ms * 1e3:.1f} us  {flops['mlp1_gelu'] / ms / 1e9:.0f} TFLOP/s", flush=True)
