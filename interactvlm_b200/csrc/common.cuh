@@ -89,6 +89,49 @@ IVLM_DEVINL void bf16_round_pair(float& a, float& b) {
     a = __uint_as_float(p << 16);
     b = __uint_as_float(p & 0xffff0000u);
 }
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 operations per issued instruction).  The activation epilogues
+// and the softmax loops are instruction-issue-bound, not FMA-pipe-bound, so halving the instruction count of their fma chains
+// is what speeds them up.  Same IEEE operations per element as the scalar forms (fma.rn / mul.rn / add.rn): identical results.
+IVLM_DEVINL uint64_t f32x2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+IVLM_DEVINL void f32x2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+IVLM_DEVINL uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+IVLM_DEVINL uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+IVLM_DEVINL uint64_t f32x2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// gelu_fast on two values: the same operations in the same order per element (the polynomial carries the minus sign of
+// relu(x) - |x| h in its constants), 9 issued instructions per element instead of 13
+IVLM_DEVINL void gelu_fast_pair(float& x0, float& x1) {
+    const uint64_t X = f32x2_pack(x0, x1);
+    const uint64_t A = f32x2_pack(fabsf(x0), fabsf(x1));
+    const float k = 0.3275911f * 0.70710678118654752440f;
+    float a0, a1;
+    f32x2_unpack(f32x2_fma(A, f32x2_pack(k, k), f32x2_pack(1.0f, 1.0f)), a0, a1);
+    const uint64_t T = f32x2_pack(rcp_approx(a0), rcp_approx(a1));
+    auto c2 = [](float c) { return f32x2_pack(c, c); };
+    uint64_t P = f32x2_fma(T, c2(-0.5f * 1.061405429f), c2(-0.5f * -1.453152027f));
+    P = f32x2_fma(T, P, c2(-0.5f * 1.421413741f));
+    P = f32x2_fma(T, P, c2(-0.5f * -0.284496736f));
+    P = f32x2_fma(T, P, c2(-0.5f * 0.254829592f));
+    float e0, e1;
+    f32x2_unpack(f32x2_mul(f32x2_mul(X, X), c2(-0.5f * 1.4426950408889634f)), e0, e1);
+    const uint64_t NH = f32x2_mul(f32x2_mul(P, T), f32x2_pack(ex2_approx_ftz(e0), ex2_approx_ftz(e1)));   // -h
+    f32x2_unpack(f32x2_fma(A, NH, f32x2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
+}
 // act followed by the bf16 rounding the eager reference applies to the activation output
 IVLM_DEVINL float apply_act_fast(float x, int act) {
     switch (act) {

@@ -91,8 +91,12 @@ IVLM_DEVINL void epi_stage_chunk(const uint32_t (&raw)[32], const float* __restr
         if (has_bias) { y0 += bs[j]; y1 += bs[j + 1]; }
         if (ACT != ACT_NONE) {
             bf16_round_pair(y0, y1);   // the Linear output as the reference holds it (bf16) before the activation
-            y0 = apply_act_fast(y0, ACT);
-            y1 = apply_act_fast(y1, ACT);
+            if (ACT == ACT_GELU) {
+                gelu_fast_pair(y0, y1);
+            } else {
+                y0 = apply_act_fast(y0, ACT);
+                y1 = apply_act_fast(y1, ACT);
+            }
         }
         x[j] = y0;
         x[j + 1] = y1;
@@ -113,9 +117,15 @@ IVLM_DEVINL void epi_stage_swiglu(const uint32_t (&raw)[32], uint8_t* buf, int r
     for (int h8 = 0; h8 < 2; ++h8) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float g = bf16_round(__uint_as_float(raw[h8 * 16 + j])), u = bf16_round(__uint_as_float(raw[h8 * 16 + 8 + j]));
-            o[j] = bf16_round(apply_act_fast(g, ACT_SILU)) * u;
+        for (int j = 0; j < 8; j += 2) {
+            float g0 = __uint_as_float(raw[h8 * 16 + j]), u0 = __uint_as_float(raw[h8 * 16 + 8 + j]);
+            float g1 = __uint_as_float(raw[h8 * 16 + j + 1]), u1 = __uint_as_float(raw[h8 * 16 + 8 + j + 1]);
+            bf16_round_pair(g0, u0);
+            bf16_round_pair(g1, u1);
+            float s0 = apply_act_fast(g0, ACT_SILU), s1 = apply_act_fast(g1, ACT_SILU);
+            bf16_round_pair(s0, s1);
+            o[j] = s0 * u0;
+            o[j + 1] = s1 * u1;
         }
         uint4 q;
         q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]); q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
