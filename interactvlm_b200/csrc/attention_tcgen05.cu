@@ -824,12 +824,17 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
             const float rh = __bfloat162float(th_r[j * AT_BQ]);   // key row ky == j
             const float cbase = fmaf(rh, AT_LOG2E, -m_ref);
             float mx = -INFINITY;
+            // two score elements per issued instruction (FFMA2): the loop is issue-bound, the arithmetic per element is unchanged
+            const uint64_t cbase2 = f32x2_pack(cbase, cbase), l2e2 = f32x2_pack(AT_LOG2E, AT_LOG2E), sc2 = f32x2_pack(p.scale_log2, p.scale_log2);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float tw = __uint_as_float((i & 1) ? (twp[i >> 1] & 0xffff0000u) : (twp[i >> 1] << 16));
-                const float x = fmaf(__uint_as_float(xr[i]), p.scale_log2, fmaf(tw, AT_LOG2E, cbase));
-                mx = fmaxf(mx, x);
-                xr[i] = __float_as_uint(ex2_approx(x));
+            for (int i = 0; i < 32; i += 2) {
+                const uint64_t tw2 = f32x2_pack(__uint_as_float(twp[i >> 1] << 16), __uint_as_float(twp[i >> 1] & 0xffff0000u));
+                const uint64_t s2 = f32x2_pack(__uint_as_float(xr[i]), __uint_as_float(xr[i + 1]));
+                float x0, x1;
+                f32x2_unpack(f32x2_fma(s2, sc2, f32x2_fma(tw2, l2e2, cbase2)), x0, x1);
+                mx = fmaxf(mx, fmaxf(x0, x1));
+                xr[i] = __float_as_uint(ex2_approx(x0));
+                xr[i + 1] = __float_as_uint(ex2_approx(x1));
             }
             // row maximum over both halves (relative to m_ref)
             float* mb = mxbuf + (j & 1) * 2 * AT_BQ;
@@ -841,17 +846,26 @@ sam_attn_global64h_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid
             if (moved) {
                 corr = ex2_approx(-mx);
                 m_ref += mx;
+                const uint64_t corr2 = f32x2_pack(corr, corr);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) xr[i] = __float_as_uint(__uint_as_float(xr[i]) * corr);
+                for (int i = 0; i < 32; i += 2) {
+                    float a0, a1;
+                    f32x2_unpack(f32x2_mul(f32x2_pack(__uint_as_float(xr[i]), __uint_as_float(xr[i + 1])), corr2), a0, a1);
+                    xr[i] = __float_as_uint(a0);
+                    xr[i + 1] = __float_as_uint(a1);
+                }
             }
-            float sum = 0.f;
+            uint64_t sum2 = f32x2_pack(0.f, 0.f);
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
                 const float p0 = __uint_as_float(xr[c]), p1 = __uint_as_float(xr[c + 1]);
-                sum += p0 + p1;
+                sum2 = f32x2_add(sum2, f32x2_pack(p0, p1));
                 pk[c >> 1] = pack_bf16x2(p0, p1);
             }
+            float sum_lo, sum_hi;
+            f32x2_unpack(sum2, sum_lo, sum_hi);
+            const float sum = sum_lo + sum_hi;
             l_run = l_run * corr + sum;
             if (j > 0) {
                 mbar_wait(pv_done, (j - 1) & 1);
@@ -936,19 +950,21 @@ static_assert(WN_OFF_KB + WN_KB <= WN_OFF_VA && WN_OFF_VB + WN_KB <= WN_OFF_RHA 
 
 template <int C0, int N>
 IVLM_DEVINL float win_scores(uint32_t (&raw)[N], const float (&rh)[WN_KW], const float (&rw)[WN_KW], float scale_log2, float mx) {
+    // two keys per FFMA2 (N and the 196-key limit are even: a pair is valid or masked as a whole)
+    const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        constexpr int dummy = 0;
-        (void)dummy;
+    for (int i = 0; i < N; i += 2) {
         const int k = C0 + i;  // compile-time after unrolling
-        float x;
+        float x0, x1;
         if (k < WN_S) {
-            x = fmaf(__uint_as_float(raw[i]), scale_log2, rh[k / WN_KW] + rw[k % WN_KW]);
-            mx = fmaxf(mx, x);
+            const uint64_t bias2 = f32x2_pack(rh[k / WN_KW] + rw[k % WN_KW], rh[(k + 1) / WN_KW] + rw[(k + 1) % WN_KW]);
+            f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])), sc2, bias2), x0, x1);
+            mx = fmaxf(mx, fmaxf(x0, x1));
         } else {
-            x = -INFINITY;
+            x0 = x1 = -INFINITY;
         }
-        raw[i] = __float_as_uint(x);
+        raw[i] = __float_as_uint(x0);
+        raw[i + 1] = __float_as_uint(x1);
     }
     return mx;
 }
@@ -1122,7 +1138,8 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
         tmem_st_32x16(lane_addr + 192, rc);
         tmem_st_wait();
         // ---- pass 2: p = 2^(x - max) -> bf16 -> swizzled P (aliases the dead Q / K tiles)
-        float sum = 0.f;
+        uint64_t sum2 = f32x2_pack(0.f, 0.f);            // two partial row sums (FADD2), combined after the pass
+        const uint64_t nmx2 = f32x2_pack(-mx, -mx);
         auto exp_chunk = [&](const uint32_t(&raw)[32], int c0) {
             uint8_t* row = smem + (c0 >> 6) * 16384 + r * 128;
 #pragma unroll
@@ -1130,9 +1147,10 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
                 uint32_t pk[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float p0 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e]) - mx);
-                    const float p1 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e + 1]) - mx);
-                    sum += p0 + p1;
+                    float d0, d1;
+                    f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(raw[j8 * 8 + 2 * e]), __uint_as_float(raw[j8 * 8 + 2 * e + 1])), nmx2), d0, d1);
+                    const float p0 = ex2_approx(d0), p1 = ex2_approx(d1);
+                    sum2 = f32x2_add(sum2, f32x2_pack(p0, p1));
                     pk[e] = pack_bf16x2(p0, p1);
                 }
                 const int c16 = ((c0 & 63) >> 3) + j8;
@@ -1154,9 +1172,10 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
                 uint32_t pk[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float p0 = ex2_approx(__uint_as_float(rc[j8 * 8 + 2 * e]) - mx);
-                    const float p1 = ex2_approx(__uint_as_float(rc[j8 * 8 + 2 * e + 1]) - mx);
-                    sum += p0 + p1;
+                    float d0, d1;
+                    f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(rc[j8 * 8 + 2 * e]), __uint_as_float(rc[j8 * 8 + 2 * e + 1])), nmx2), d0, d1);
+                    const float p0 = ex2_approx(d0), p1 = ex2_approx(d1);
+                    sum2 = f32x2_add(sum2, f32x2_pack(p0, p1));
                     pk[e] = pack_bf16x2(p0, p1);
                 }
                 *reinterpret_cast<uint4*>(row + ((j8 ^ ((r >> 2) & 1)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -1169,6 +1188,9 @@ sam_attn_window_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQa, const _
         // ---- epilogue
         mbar_wait(o_full, 0);
         tc_fence_after();
+        float sum_lo, sum_hi;
+        f32x2_unpack(sum2, sum_lo, sum_hi);
+        const float sum = sum_lo + sum_hi;
         const float inv = sum > 0.f ? 1.f / sum : 0.f;
         // window_unpartition (image_encoder.py:291-318) folded into the store: with out_map the row goes straight to its token
         // position and the rows of the zero padding are never written
@@ -1373,7 +1395,8 @@ sam_attn_window_persist_kernel(const __grid_constant__ CUtensorMap tmQa, const _
         tmem_st_32x16(lane_addr + 192, rc);
         tmem_st_wait();
         // ---- pass 2: p = 2^(x - max) -> bf16 -> swizzled P (aliases the dead Q / K tiles)
-        float sum = 0.f;
+        uint64_t sum2 = f32x2_pack(0.f, 0.f);            // two partial row sums (FADD2), combined after the pass
+        const uint64_t nmx2 = f32x2_pack(-mx, -mx);
         auto exp_chunk = [&](const uint32_t(&raw)[32], int c0) {
             uint8_t* row = smem + (c0 >> 6) * 16384 + r * 128;
 #pragma unroll
@@ -1381,9 +1404,10 @@ sam_attn_window_persist_kernel(const __grid_constant__ CUtensorMap tmQa, const _
                 uint32_t pk[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float p0 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e]) - mx);
-                    const float p1 = ex2_approx(__uint_as_float(raw[j8 * 8 + 2 * e + 1]) - mx);
-                    sum += p0 + p1;
+                    float d0, d1;
+                    f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(raw[j8 * 8 + 2 * e]), __uint_as_float(raw[j8 * 8 + 2 * e + 1])), nmx2), d0, d1);
+                    const float p0 = ex2_approx(d0), p1 = ex2_approx(d1);
+                    sum2 = f32x2_add(sum2, f32x2_pack(p0, p1));
                     pk[e] = pack_bf16x2(p0, p1);
                 }
                 const int c16 = ((c0 & 63) >> 3) + j8;
@@ -1405,9 +1429,10 @@ sam_attn_window_persist_kernel(const __grid_constant__ CUtensorMap tmQa, const _
                 uint32_t pk[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float p0 = ex2_approx(__uint_as_float(rc[j8 * 8 + 2 * e]) - mx);
-                    const float p1 = ex2_approx(__uint_as_float(rc[j8 * 8 + 2 * e + 1]) - mx);
-                    sum += p0 + p1;
+                    float d0, d1;
+                    f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(rc[j8 * 8 + 2 * e]), __uint_as_float(rc[j8 * 8 + 2 * e + 1])), nmx2), d0, d1);
+                    const float p0 = ex2_approx(d0), p1 = ex2_approx(d1);
+                    sum2 = f32x2_add(sum2, f32x2_pack(p0, p1));
                     pk[e] = pack_bf16x2(p0, p1);
                 }
                 *reinterpret_cast<uint4*>(row + ((j8 ^ ((r >> 2) & 1)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -1420,6 +1445,9 @@ sam_attn_window_persist_kernel(const __grid_constant__ CUtensorMap tmQa, const _
         // ---- epilogue
         mbar_wait(o_full, ph);
         tc_fence_after();
+        float sum_lo, sum_hi;
+        f32x2_unpack(sum2, sum_lo, sum_hi);
+        const float sum = sum_lo + sum_hi;
         const float inv = sum > 0.f ? 1.f / sum : 0.f;
         // window_unpartition (image_encoder.py:291-318) folded into the store: with out_map the row goes straight to its token
         // position and the rows of the zero padding are never written

@@ -88,7 +88,10 @@ IVLM_DEVINL void epi_stage_chunk(const uint32_t (&raw)[32], const float* __restr
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
         float y0 = __uint_as_float(raw[j]), y1 = __uint_as_float(raw[j + 1]);
-        if (has_bias) { y0 += bs[j]; y1 += bs[j + 1]; }
+        if (has_bias) {   // one FADD2 for the pair (bias_s is 8-byte aligned, j is even)
+            const float2 b2 = *reinterpret_cast<const float2*>(bs + j);
+            f32x2_unpack(f32x2_add(f32x2_pack(y0, y1), f32x2_pack(b2.x, b2.y)), y0, y1);
+        }
         if (ACT != ACT_NONE) {
             bf16_round_pair(y0, y1);   // the Linear output as the reference holds it (bf16) before the activation
             if (ACT == ACT_GELU) {
