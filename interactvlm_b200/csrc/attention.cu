@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    uint64_t acc2[4] = {f32x2_pack(0.f, 0.f), f32x2_pack(0.f, 0.f), f32x2_pack(0.f, 0.f), f32x2_pack(0.f, 0.f)};
     auto pv_unit = [&](const uint4(&buf)[UL], int ui) {   // rows in cache order: the accumulation order of the unpipelined loop
         const int k0 = unit_k0(ui);
 #pragma unroll
@@ -388,8 +389,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
             const int kpos = k0 + u * RPI + sub;
             const float p_ = kpos < len ? bf16_round(sc[kpos] * inv) : 0.f;
             const float2 a = unpack_bf16x2(buf[u].x), c = unpack_bf16x2(buf[u].y), e = unpack_bf16x2(buf[u].z), f = unpack_bf16x2(buf[u].w);
-            acc[0] += p_ * a.x; acc[1] += p_ * a.y; acc[2] += p_ * c.x; acc[3] += p_ * c.y;
-            acc[4] += p_ * e.x; acc[5] += p_ * e.y; acc[6] += p_ * f.x; acc[7] += p_ * f.y;
+            const uint64_t p2 = f32x2_pack(p_, p_);   // FFMA2: two of the eight independent accumulators per instruction, same fma per element
+            acc2[0] = f32x2_fma(p2, f32x2_pack(a.x, a.y), acc2[0]);
+            acc2[1] = f32x2_fma(p2, f32x2_pack(c.x, c.y), acc2[1]);
+            acc2[2] = f32x2_fma(p2, f32x2_pack(e.x, e.y), acc2[2]);
+            acc2[3] = f32x2_fma(p2, f32x2_pack(f.x, f.y), acc2[3]);
         }
     };
     if (nU > 0) load_unit(bufA, v_cache, 0);
@@ -399,6 +403,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_paged_kernel(const
         if (ui + 2 < nU) load_unit(bufA, v_cache, ui + 2);
         pv_unit(bufB, ui + 1);
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) f32x2_unpack(acc2[e], acc[2 * e], acc[2 * e + 1]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) part[warp * RPI + sub][li * 8 + e] = acc[e];
     __syncthreads();

@@ -1886,10 +1886,14 @@ flash_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
             float x[FT_BK];
             float mx = -INFINITY;
             const int kbase = j * FT_BK;
+            const uint64_t sc2 = f32x2_pack(p.scale_log2, p.scale_log2);   // two scores per FMUL2 / FADD2 (issue-bound loop)
 #pragma unroll
-            for (int c = 0; c < FT_BK; ++c) {
-                x[c] = (kbase + c <= k_last) ? __uint_as_float(xr[c]) * p.scale_log2 : -INFINITY;
-                mx = fmaxf(mx, x[c]);
+            for (int c = 0; c < FT_BK; c += 2) {
+                float x0, x1;
+                f32x2_unpack(f32x2_mul(f32x2_pack(__uint_as_float(xr[c]), __uint_as_float(xr[c + 1])), sc2), x0, x1);
+                x[c] = (kbase + c <= k_last) ? x0 : -INFINITY;
+                x[c + 1] = (kbase + c + 1 <= k_last) ? x1 : -INFINITY;
+                mx = fmaxf(mx, fmaxf(x[c], x[c + 1]));
             }
             // online softmax with lazy rescaling (see sam_attn_tcgen05_kernel); a row whose keys are all masked keeps m_ref
             float corr = 1.f;
@@ -1902,15 +1906,20 @@ flash_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 moved = true;
             }
             const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
-            float sum = 0.f;
+            const uint64_t nmr2 = f32x2_pack(-mr, -mr);
+            uint64_t sum2 = f32x2_pack(0.f, 0.f);
             uint32_t pk[FT_BK / 2];
 #pragma unroll
             for (int c = 0; c < FT_BK; c += 2) {
-                const float p0 = ex2_approx(x[c] - mr), p1 = ex2_approx(x[c + 1] - mr);
-                sum += p0 + p1;
+                float d0, d1;
+                f32x2_unpack(f32x2_add(f32x2_pack(x[c], x[c + 1]), nmr2), d0, d1);
+                const float p0 = ex2_approx(d0), p1 = ex2_approx(d1);
+                sum2 = f32x2_add(sum2, f32x2_pack(p0, p1));
                 pk[c >> 1] = pack_bf16x2(p0, p1);
             }
-            l_run = l_run * corr + sum;
+            float sum_lo, sum_hi;
+            f32x2_unpack(sum2, sum_lo, sum_hi);
+            l_run = l_run * corr + (sum_lo + sum_hi);
             if (j > 0) {
                 mbar_wait(pv_done, (j - 1) & 1);
                 tc_fence_after();
