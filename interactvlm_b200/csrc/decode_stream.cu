@@ -856,7 +856,18 @@ extern "C" int ivlm_decode_linear(ivlm_handle h, const ivlm_decode_linear_args* 
     // shared memory: barriers + fold buffers, the resident activation (when it fits next to the ring), the 1024-byte aligned ring
     const size_t fixed = DS_FIXED_BYTES;
     const size_t act_bytes = (size_t)DS_MAX_M * (a->K + 8) * 2 + (a->norm_gamma != nullptr ? (size_t)a->K * 2 : 0);   // + staged RMSNorm weight
-    const int ns = (h->ds_stages >= 2 && h->ds_stages <= DS_STAGES) ? h->ds_stages : 6;
+    // ring depth: 7 stages when they fit next to the resident activation (133.1-133.4 us per 13B layer against 134.4-134.9 with 6 in
+    // three runs of tools/prof_decode.py; 8 no longer fits with the staged RMSNorm weight), option "ds_stages" overrides
+    int ns = (h->ds_stages >= 2 && h->ds_stages <= DS_STAGES) ? h->ds_stages : 7;
+    {
+        const size_t cap_ = 227 * 1024;
+        const size_t act_ = (size_t)DS_MAX_M * (a->K + 8) * 2 + (a->norm_gamma != nullptr ? (size_t)a->K * 2 : 0);
+        const bool res_ = !(h->ds_force_stream && a->norm_gamma == nullptr) && DS_FIXED_BYTES + act_ + 1024 + (size_t)6 * DS_W_BYTES <= cap_;
+        if (h->ds_stages == 0) {
+            const size_t need7 = DS_FIXED_BYTES + 1024 + (res_ ? act_ + (size_t)7 * DS_W_BYTES : (size_t)7 * (DS_W_BYTES + DS_A_BYTES));
+            if (need7 > cap_) ns = 6;
+        }
+    }
     p.nstages = ns;
     const size_t ring_res = (size_t)ns * DS_W_BYTES, ring_str = (size_t)ns * (DS_W_BYTES + DS_A_BYTES);
     const size_t cap = 227 * 1024;
